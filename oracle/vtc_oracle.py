@@ -1,0 +1,462 @@
+"""CPU ORACLE for the VTC contrastive-retrieval hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  Nothing under ``vtc_b200/``
+imports it; the product path fails loudly when its CUDA library is missing.
+
+What is restated here (citations are ``path:line`` in /root/reference):
+
+* ``normalize``                      model/model.py:26-27   (no eps; zero row -> NaN)
+* ``sim_matrix``                     model/model.py:369,478,504,621  ((s*A) @ B.T)
+* ``clip_loss``                      model/loss.py:18-22
+* ``FlatL2Index`` / ``recall_at_k``  model/metric.py:137-161 with a CPU stand-in for
+                                     ``faiss.GpuIndexFlatL2`` (exact fp32 L2, ascending,
+                                     ties by index, -1 fill)
+* ``compute_recall``                 evaluation/retrieval_evaluation.py:23-47
+* ``eval_tail``                      evaluation/retrieval_evaluation.py:238-260
+* ``transformer`` / ``adapt_feature``  model/model.py:141-205 over a functional
+                                     ``clip.model.Transformer`` whose block structure
+                                     follows the in-repo mirror
+                                     model/timesformer_clip_alt.py:22-33,43-67,112-124
+* ``averaging_fusion``               model/model.py:356-362
+* rank0 / MedR / exact top-k         NOT in the reference; defined in SURVEY.md §8a R3 and
+                                     implemented in fp64-sequential arithmetic by
+                                     ``oracle/vtc_oracle.c``.
+
+PARITY STATUS: **parity unpinned** at the ``faiss`` and ``clip.model.Transformer``
+boundaries (both are un-vendored, un-pinned third-party packages absent from this image and
+from /root/reference; the reference's own tests hold no golden vector for this path --
+SURVEY.md §4, §8c).  What *is* pinned: ``tests/golden/generate_golden.py`` executes the
+reference's own function bodies (``clip_loss``, ``RecallAtK.compute``, ``compute_recall``,
+``_adapt_feature``, ``_encode_with_comments``) in this container through the shims in
+``oracle/reference_shims.py`` and commits their outputs; ``tests/test_oracle_golden.py``
+checks this restatement against those fixtures.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libvtc_oracle.so")
+
+METRIC_DOT = 0
+METRIC_L2 = 1
+
+
+# --------------------------------------------------------------------------------------
+# C library (fp64-sequential exact arithmetic)
+# --------------------------------------------------------------------------------------
+def build_c_oracle(force: bool = False) -> str:
+    """Compile oracle/vtc_oracle.c into oracle/_ref/ (building the checker is not using it)."""
+    src = os.path.join(_HERE, "vtc_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "CC=gcc"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def _clib():
+    global _lib
+    if _lib is None:
+        build_c_oracle()
+        lib = ctypes.CDLL(_LIB_PATH)
+        c_f = ctypes.POINTER(ctypes.c_float)
+        c_d = ctypes.POINTER(ctypes.c_double)
+        c_i64 = ctypes.POINTER(ctypes.c_int64)
+        c_i32 = ctypes.POINTER(ctypes.c_int32)
+        lib.vtc_oracle_sqnorm64.argtypes = [c_f, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_d]
+        lib.vtc_oracle_sqnorm64.restype = None
+        lib.vtc_oracle_scores64.argtypes = [c_f, c_f, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                            ctypes.c_int, c_d]
+        lib.vtc_oracle_scores64.restype = None
+        lib.vtc_oracle_rank_range.argtypes = [c_f, c_f, c_d, ctypes.c_int64, ctypes.c_int64,
+                                              ctypes.c_int64, ctypes.c_int, c_i64, ctypes.c_int64,
+                                              ctypes.c_int, c_i32]
+        lib.vtc_oracle_rank_range.restype = None
+        lib.vtc_oracle_topk_range.argtypes = [c_f, c_f, c_d, ctypes.c_int64, ctypes.c_int64,
+                                              ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int64, c_d, c_i64]
+        lib.vtc_oracle_topk_range.restype = None
+        _lib = lib
+    return _lib
+
+
+def _f32c(x) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().float().numpy()
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def _ptr(a: np.ndarray, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+def _ranges(n: int, threads: int) -> List[Tuple[int, int]]:
+    threads = max(1, min(threads, n))
+    step = -(-n // threads)
+    return [(s, min(n, s + step)) for s in range(0, n, step)]
+
+
+def host_threads() -> int:
+    return os.cpu_count() or 1
+
+
+def sqnorm64(X) -> np.ndarray:
+    X = _f32c(X)
+    out = np.empty(X.shape[0], dtype=np.float64)
+    _clib().vtc_oracle_sqnorm64(_ptr(X, ctypes.c_float), X.shape[0], X.shape[1], X.shape[1],
+                                _ptr(out, ctypes.c_double))
+    return out
+
+
+def scores64(Q, G, metric: int = METRIC_L2) -> np.ndarray:
+    """Full fp64-sequential score matrix d(t,j) (small cases only)."""
+    Q, G = _f32c(Q), _f32c(G)
+    out = np.empty((Q.shape[0], G.shape[0]), dtype=np.float64)
+    _clib().vtc_oracle_scores64(_ptr(Q, ctypes.c_float), _ptr(G, ctypes.c_float), Q.shape[0],
+                                G.shape[0], Q.shape[1], metric, _ptr(out, ctypes.c_double))
+    return out
+
+
+def rank0_exact(Q, G, gt: Optional[Sequence[int]] = None, row_offset: int = 0,
+                metric: int = METRIC_L2, threads: Optional[int] = None) -> np.ndarray:
+    """rank0[t] in fp64-sequential arithmetic; int32 [N]."""
+    Q, G = _f32c(Q), _f32c(G)
+    N, D = Q.shape
+    M = G.shape[0]
+    assert G.shape[1] == D
+    sq = sqnorm64(G)
+    out = np.zeros(N, dtype=np.int32)
+    gt_arr = None if gt is None else np.ascontiguousarray(np.asarray(gt), dtype=np.int64)
+    gt_p = None if gt_arr is None else _ptr(gt_arr, ctypes.c_int64)
+    lib = _clib()
+
+    def work(r):
+        lib.vtc_oracle_rank_range(_ptr(Q, ctypes.c_float), _ptr(G, ctypes.c_float),
+                                  _ptr(sq, ctypes.c_double), r[0], r[1], M, D, gt_p, row_offset,
+                                  metric, _ptr(out, ctypes.c_int32))
+
+    rs = _ranges(N, threads or host_threads())
+    with ThreadPoolExecutor(len(rs)) as ex:
+        list(ex.map(work, rs))
+    return out
+
+
+def topk_exact(Q, G, k: int, metric: int = METRIC_L2, col_offset: int = 0,
+               threads: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """Exact k smallest scores per query: (vals fp64 [N,k], idx int64 [N,k]); -1/+inf fill."""
+    Q, G = _f32c(Q), _f32c(G)
+    N, D = Q.shape
+    M = G.shape[0]
+    sq = sqnorm64(G)
+    vals = np.empty((N, k), dtype=np.float64)
+    idx = np.empty((N, k), dtype=np.int64)
+    lib = _clib()
+
+    def work(r):
+        lib.vtc_oracle_topk_range(_ptr(Q, ctypes.c_float), _ptr(G, ctypes.c_float),
+                                  _ptr(sq, ctypes.c_double), r[0], r[1], M, D, metric, k, col_offset,
+                                  _ptr(vals, ctypes.c_double), _ptr(idx, ctypes.c_int64))
+
+    rs = _ranges(N, threads or host_threads())
+    with ThreadPoolExecutor(len(rs)) as ex:
+        list(ex.map(work, rs))
+    return vals, idx
+
+
+def recall_from_ranks(rank0: np.ndarray, k_vals: Iterable[int], denom: Optional[int] = None
+                      ) -> List[Tuple[int, float]]:
+    """R@k = #(rank0 < k) / denom; denom defaults to len(rank0) (model/metric.py:138,158)."""
+    rank0 = np.asarray(rank0)
+    denom = len(rank0) if denom is None else denom
+    return [(int(k), float(np.sum(rank0 < k)) / denom) for k in k_vals]
+
+
+def medr(rank0: np.ndarray) -> float:
+    """Median rank, 1-based, numpy median semantics."""
+    return float(np.median(np.asarray(rank0))) + 1.0
+
+
+def bf16_round(x) -> np.ndarray:
+    """Round-to-nearest-even to bf16 and back to fp32 (what the bf16 product path ranks)."""
+    t = torch.as_tensor(_f32c(x))
+    return t.to(torch.bfloat16).to(torch.float32).numpy()
+
+
+# --------------------------------------------------------------------------------------
+# H1 / H2 / H3: normalise, similarity, symmetric InfoNCE
+# --------------------------------------------------------------------------------------
+def normalize(x: torch.Tensor) -> torch.Tensor:
+    """model/model.py:26-27 -- x / ||x||_2 over the last dim, no eps."""
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+def sim_matrix(feats_a: torch.Tensor, feats_b: torch.Tensor, logit_scale_exp) -> torch.Tensor:
+    """model/model.py:369 -- `s * A @ B.t()` parses as (s*A) @ B.t()."""
+    return logit_scale_exp * feats_a @ feats_b.t()
+
+
+def clip_loss(sim: torch.Tensor) -> torch.Tensor:
+    """model/loss.py:18-22 on a materialised similarity matrix."""
+    labels = torch.arange(sim.shape[0], device=sim.device)
+    return 0.5 * (F.cross_entropy(sim, labels) + F.cross_entropy(sim.t(), labels))
+
+
+def clip_loss_parts64(feats_a, feats_b, logit_scale_exp: float) -> Dict[str, np.ndarray]:
+    """fp64 reference for the fused kernel's outputs: loss, row/col LSE and diagonal."""
+    a = torch.as_tensor(_f32c(feats_a)).double()
+    b = torch.as_tensor(_f32c(feats_b)).double()
+    sim = float(logit_scale_exp) * a @ b.t()
+    row = torch.logsumexp(sim, dim=1)
+    col = torch.logsumexp(sim, dim=0)
+    diag = sim.diagonal()
+    loss = 0.5 * ((row - diag).mean() + (col - diag).mean())
+    return {"loss": np.float64(loss.item()), "row_lse": row.numpy(), "col_lse": col.numpy(),
+            "diag": diag.numpy(), "sim": sim.numpy()}
+
+
+# --------------------------------------------------------------------------------------
+# R1 / R4 / R5: RecallAtK.compute, compute_recall, eval tail
+# --------------------------------------------------------------------------------------
+class FlatL2Index:
+    """CPU stand-in for faiss.GpuIndexFlatL2(res, d, cfg) as used at model/metric.py:140-146.
+
+    Exact fp32 squared-L2 (||q||^2 + ||x||^2 - 2 q.x, the decomposition faiss' flat index
+    uses), ascending, ties broken by lower index (stable), -1 / +inf fill when k > ntotal.
+    Query-tiled so no N x M block above ~1 GB is formed.
+    """
+
+    def __init__(self, d: int, tile_rows: int = 4096):
+        self.d = d
+        self.tile_rows = tile_rows
+        self.x = None
+
+    def add(self, x: np.ndarray) -> None:
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        assert x.ndim == 2 and x.shape[1] == self.d
+        self.x = x if self.x is None else torch.cat([self.x, x])
+
+    def search(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+        assert q.ndim == 2 and q.shape[1] == self.d
+        x = self.x
+        m = x.shape[0]
+        kk = min(k, m)
+        xsq = (x * x).sum(1)
+        D = np.full((q.shape[0], k), np.inf, dtype=np.float32)
+        I = np.full((q.shape[0], k), -1, dtype=np.int64)
+        for s in range(0, q.shape[0], self.tile_rows):
+            qt = q[s:s + self.tile_rows]
+            dist = (qt * qt).sum(1, keepdim=True) + xsq[None, :] - 2.0 * (qt @ x.t())
+            dist = torch.nan_to_num(dist, nan=float("inf"))
+            # stable ascending selection: sort by (dist, index)
+            vals, idx = torch.sort(dist, dim=1, stable=True)
+            D[s:s + qt.shape[0], :kk] = vals[:, :kk].numpy()
+            I[s:s + qt.shape[0], :kk] = idx[:, :kk].numpy()
+        return D, I
+
+    def search_fast(self, q: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Same contract via torch.topk (not index-stable on exact ties); the CPU-baseline leg
+        times this one because a full sort is not what faiss does."""
+        q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+        x = self.x
+        kk = min(k, x.shape[0])
+        xsq = (x * x).sum(1)
+        D = np.full((q.shape[0], k), np.inf, dtype=np.float32)
+        I = np.full((q.shape[0], k), -1, dtype=np.int64)
+        for s in range(0, q.shape[0], self.tile_rows):
+            qt = q[s:s + self.tile_rows]
+            dist = (qt * qt).sum(1, keepdim=True) + xsq[None, :] - 2.0 * (qt @ x.t())
+            vals, idx = torch.topk(dist, kk, dim=1, largest=False, sorted=True)
+            D[s:s + qt.shape[0], :kk] = vals.numpy()
+            I[s:s + qt.shape[0], :kk] = idx.numpy()
+        return D, I
+
+
+def recall_at_k(features_a: np.ndarray, features_b: np.ndarray, k_vals: Sequence[int],
+                fast: bool = False) -> List[Tuple[int, float]]:
+    """model/metric.py:137-161 -- gallery = a, queries = b, gt(t) = t, depth max(k)+1."""
+    num_samples = features_a.shape[0]
+    num_dims = features_a.shape[1]
+    index = FlatL2Index(num_dims)
+    index.add(features_a)
+    search = index.search_fast if fast else index.search
+    _, k_closest_points = search(features_b, int(np.max(k_vals) + 1))
+    recall_all_k = []
+    for k in k_vals:
+        hits = 0
+        for target, rp in enumerate(k_closest_points):  # the reference's host loop, :149-160
+            if target in rp[:k]:
+                hits += 1
+        recall_all_k.append((k, hits / num_samples))
+    return recall_all_k
+
+
+def compute_recall(tensor_v: torch.Tensor, tensor_t: torch.Tensor, split: str = "full-test",
+                   dataset_name: str = "MSRVTT", fast: bool = False):
+    """evaluation/retrieval_evaluation.py:23-47 (labels, not variable names, are authoritative)."""
+    import pandas as pd
+
+    recall_range = [1, 5, 10]
+    t2 = tensor_t.numpy().squeeze()
+    # gallery = videos, queries = texts  -> "Text to Video"
+    vtr = np.array(recall_at_k(tensor_v.numpy(), t2, recall_range, fast))[:, 1] * 100.0
+    # gallery = texts, queries = videos  -> "Video to Text"
+    tvr = np.array(recall_at_k(t2, tensor_v.numpy(), recall_range, fast))[:, 1] * 100.0
+    return pd.DataFrame(
+        {f"{dataset_name} {split} split Video to Text": tvr,
+         f"{dataset_name} {split} split Text to Video": vtr},
+        index=[f"R@{i}" for i in recall_range])
+
+
+def eval_tail(video_feats: List[torch.Tensor], caption_feats: List[torch.Tensor]
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """evaluation/retrieval_evaluation.py:238-260 -- -inf caption padding, per-video mean of
+    frame/chunk features (NOT renormalised), stack."""
+    max_length = max(s.shape[0] for s in caption_feats)
+    padded = [torch.cat([k, torch.full((max_length - k.shape[0], k.shape[1]), float("-inf"))])
+              for k in caption_feats]
+    video_joint = torch.cat([torch.mean(k, dim=0, keepdim=True) for k in video_feats])
+    caption_joint = torch.stack(padded)
+    return video_joint, caption_joint
+
+
+# --------------------------------------------------------------------------------------
+# H4 / H4' / H5 / H6: Context Adapter Module
+# --------------------------------------------------------------------------------------
+def cam_param_names(layers: int) -> List[str]:
+    names = []
+    for i in range(layers):
+        p = f"resblocks.{i}."
+        names += [p + "attn.in_proj_weight", p + "attn.in_proj_bias", p + "attn.out_proj.weight",
+                  p + "attn.out_proj.bias", p + "ln_1.weight", p + "ln_1.bias",
+                  p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", p + "mlp.c_proj.weight",
+                  p + "mlp.c_proj.bias", p + "ln_2.weight", p + "ln_2.bias"]
+    return names
+
+
+def make_cam_params(width: int, layers: int, heads: int, seed: int = 1023, zero_init: bool = True,
+                    rerandomise: bool = False) -> Dict[str, torch.Tensor]:
+    """Deterministic CAM weights: torch default init of nn.MultiheadAttention / Linear /
+    LayerNorm under manual_seed(seed), then the reference's zero-inits
+    (model/model.py:440-450) when ``zero_init``; ``rerandomise`` re-draws the zeroed tensors
+    (otherwise the transformer is an identity on the residual stream)."""
+    g = torch.Generator().manual_seed(seed)
+    p: Dict[str, torch.Tensor] = {}
+    for i in range(layers):
+        pre = f"resblocks.{i}."
+        bound = math.sqrt(6.0 / (width + 3 * width))  # xavier_uniform on [3D, D]
+        p[pre + "attn.in_proj_weight"] = (torch.rand(3 * width, width, generator=g) * 2 - 1) * bound
+        p[pre + "attn.in_proj_bias"] = torch.zeros(3 * width)
+        kb = 1.0 / math.sqrt(width)
+        p[pre + "attn.out_proj.weight"] = (torch.rand(width, width, generator=g) * 2 - 1) * kb
+        p[pre + "attn.out_proj.bias"] = torch.zeros(width)
+        p[pre + "ln_1.weight"] = torch.ones(width)
+        p[pre + "ln_1.bias"] = torch.zeros(width)
+        p[pre + "mlp.c_fc.weight"] = (torch.rand(4 * width, width, generator=g) * 2 - 1) * kb
+        p[pre + "mlp.c_fc.bias"] = (torch.rand(4 * width, generator=g) * 2 - 1) * kb
+        kb2 = 1.0 / math.sqrt(4 * width)
+        p[pre + "mlp.c_proj.weight"] = (torch.rand(width, 4 * width, generator=g) * 2 - 1) * kb2
+        p[pre + "mlp.c_proj.bias"] = (torch.rand(width, generator=g) * 2 - 1) * kb2
+        p[pre + "ln_2.weight"] = torch.ones(width)
+        p[pre + "ln_2.bias"] = torch.zeros(width)
+        if zero_init and not rerandomise:
+            p[pre + "mlp.c_proj.weight"].zero_()
+            p[pre + "mlp.c_proj.bias"].zero_()
+            p[pre + "attn.out_proj.weight"].zero_()
+        if rerandomise:
+            p[pre + "ln_1.weight"] = 1.0 + 0.1 * torch.randn(width, generator=g)
+            p[pre + "ln_1.bias"] = 0.1 * torch.randn(width, generator=g)
+            p[pre + "ln_2.weight"] = 1.0 + 0.1 * torch.randn(width, generator=g)
+            p[pre + "ln_2.bias"] = 0.1 * torch.randn(width, generator=g)
+            p[pre + "attn.in_proj_bias"] = 0.02 * torch.randn(3 * width, generator=g)
+            p[pre + "attn.out_proj.bias"] = 0.02 * torch.randn(width, generator=g)
+    return p
+
+
+def quick_gelu(x: torch.Tensor) -> torch.Tensor:
+    """model/timesformer_clip_alt.py:31-33."""
+    return x * torch.sigmoid(1.702 * x)
+
+
+def _layer_norm(x, w, b):
+    """model/timesformer_clip_alt.py:22-28 (fp32 LayerNorm, eps 1e-5)."""
+    return F.layer_norm(x.float(), (x.shape[-1],), w, b, 1e-5).to(x.dtype)
+
+
+def mha_self(x: torch.Tensor, in_w, in_b, out_w, out_b, heads: int) -> torch.Tensor:
+    """nn.MultiheadAttention(d, h) self-attention, sequence-first [L, b, D], no mask
+    (structure: model/timesformer_clip_alt.py:43-67)."""
+    L, b, D = x.shape
+    hd = D // heads
+    qkv = x @ in_w.t() + in_b
+    q, k, v = qkv.chunk(3, dim=-1)
+    q = q * (float(hd) ** -0.5)
+    # [L, b, h, hd] -> [b*h, L, hd]
+    def split(t):
+        return t.reshape(L, b * heads, hd).transpose(0, 1)
+    qh, kh, vh = split(q), split(k), split(v)
+    att = torch.softmax(qh @ kh.transpose(1, 2), dim=-1)
+    o = (att @ vh).transpose(0, 1).reshape(L, b, D)
+    return o @ out_w.t() + out_b
+
+
+def transformer(x: torch.Tensor, p: Dict[str, torch.Tensor], layers: int, heads: int) -> torch.Tensor:
+    """clip.model.Transformer(width, layers, heads) forward on [L, b, D]
+    (block layout: model/timesformer_clip_alt.py:112-124)."""
+    for i in range(layers):
+        pre = f"resblocks.{i}."
+        h = _layer_norm(x, p[pre + "ln_1.weight"], p[pre + "ln_1.bias"])
+        x = x + mha_self(h, p[pre + "attn.in_proj_weight"], p[pre + "attn.in_proj_bias"],
+                         p[pre + "attn.out_proj.weight"], p[pre + "attn.out_proj.bias"], heads)
+        h = _layer_norm(x, p[pre + "ln_2.weight"], p[pre + "ln_2.bias"])
+        h = quick_gelu(h @ p[pre + "mlp.c_fc.weight"].t() + p[pre + "mlp.c_fc.bias"])
+        x = x + (h @ p[pre + "mlp.c_proj.weight"].t() + p[pre + "mlp.c_proj.bias"])
+    return x
+
+
+def adapt_feature(feature_main: torch.Tensor, features_aux, params: Dict[str, torch.Tensor],
+                  layers: int, heads: int, init_from_avg: bool = True,
+                  final_linear_weight: Optional[torch.Tensor] = None,
+                  skip_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """model/model.py:141-205 with residual_activation None/'none' (identity, :65-77).
+
+    ``skip_mask`` [b] bool reproduces the train-time random adapter skip (:199-201) with the
+    mask supplied by the caller (the reference draws it from the global CPU RNG)."""
+    assert feature_main.dim() == 2
+    concat = torch.stack([feature_main, *features_aux], dim=0)          # :150
+    concat = normalize(concat)                                           # :151
+    tfm = transformer(concat, params, layers, heads)                     # :155
+    if init_from_avg:
+        res = normalize(torch.mean(torch.stack([normalize(s) for s in tfm], 0), dim=0))  # :156-159
+    else:
+        res = tfm[0] @ final_linear_weight.t()                           # :161
+    if skip_mask is not None:
+        res = res.clone()
+        res[skip_mask] = 0.0                                             # :199-201
+    return normalize(normalize(feature_main) + res)                      # :203
+
+
+def averaging_fusion(feats_title: torch.Tensor, feats_comm: torch.Tensor) -> torch.Tensor:
+    """model/model.py:356-362 + :366 -- mean over [title, *comments] then normalise."""
+    x = torch.cat([feats_title.unsqueeze(0), feats_comm.permute(1, 0, 2)], 0)
+    return normalize(torch.mean(x, dim=0))
+
+
+def cam_closed_form_at_init(feature_main: torch.Tensor, features_aux) -> torch.Tensor:
+    """with init_from_avg and the reference's zero-inits the transformer is
+    the identity on the residual stream, so CAM has this closed form."""
+    x = normalize(torch.stack([feature_main, *features_aux], 0))
+    res = normalize(torch.mean(normalize(x), dim=0))
+    return normalize(normalize(feature_main) + res)
