@@ -1,0 +1,201 @@
+/*
+ * vtc_b200.h -- C ABI of the B200-native contrastive-retrieval hot path of unitaryai/VTC.
+ *
+ * The reference has no FFI/plugin registry: its extension mechanism is name lookup on Python
+ * modules (train.py:85-89, utils/parse_config.py:97-112).  The Python shims in
+ * vtc_b200/{model,evaluation}/ keep those symbols and call the entry points below through
+ * ctypes with `tensor.data_ptr()` and `torch.cuda.current_stream().cuda_stream`.
+ * Each entry point names the reference call site it replaces (path:line in unitaryai/VTC).
+ *
+ * Conventions (all entry points):
+ *   - extern "C", return int: 0 = VTC_OK, < 0 = error (see vtc_strerror); never throw.
+ *   - never allocate device memory, never synchronise: all work is enqueued on `stream`;
+ *     the caller owns every buffer including the workspace (size from vtc_workspace_bytes);
+ *   - all pointers are DEVICE pointers unless said otherwise; matrices are row-major with an
+ *     explicit leading dimension in ELEMENTS;
+ *   - re-entrant: no mutable global state besides read-only lazily-resolved driver entry points.
+ */
+#ifndef VTC_B200_H_
+#define VTC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define VTC_ABI_VERSION 1
+
+typedef void* vtc_stream_t; /* a cudaStream_t */
+
+/* storage type of an embedding matrix handed to the library */
+enum { VTC_F32 = 0, VTC_BF16 = 1 };
+
+/* retrieval score: DOT ranks by -q.x, L2 by ||x||^2 - 2 q.x (what faiss' IndexFlatL2 orders by;
+ * the gallery is NOT assumed unit-norm, evaluation/retrieval_evaluation.py:254-259) */
+enum { VTC_METRIC_DOT = 0, VTC_METRIC_L2 = 1 };
+
+/*
+ * arithmetic of the similarity pass.
+ *   VTC_PREC_EXACT : the values ranked are the caller's fp32 inputs.  Tensor-core pass on a
+ *                    3-term bf16 split (hi*hi + hi*lo + lo*hi), guard band, fp64 re-check of the
+ *                    ambiguous pairs => ranks / top-k indices identical to fp64-sequential
+ *                    arithmetic (oracle/vtc_oracle.c).  Loss/similarity within 1e-4 rel.
+ *   VTC_PREC_BF16  : inputs are first rounded to bf16 (RN-even); one tensor-core pass; the same
+ *                    guard band + fp64 re-check => ranks identical to fp64-sequential arithmetic
+ *                    ON THE ROUNDED inputs.  Loss/similarity within 2e-2 rel of fp32.
+ *   VTC_PREC_BRUTE : fp64 SIMT brute force over the fp32 inputs (no tensor cores); the anchor the
+ *                    other two are tested against and their overflow fallback.
+ */
+enum { VTC_PREC_EXACT = 0, VTC_PREC_BF16 = 1, VTC_PREC_BRUTE = 2 };
+
+/* ops for vtc_workspace_bytes */
+enum {
+  VTC_OP_SIM_RANK = 0,
+  VTC_OP_SIM_TOPK = 1,
+  VTC_OP_INFONCE_FWD = 2,
+  VTC_OP_SIM_MATRIX = 3,
+  VTC_OP_INFONCE_BWD = 4,
+  VTC_OP_GT_SCORES = 5,
+  VTC_OP_LINEAR = 6 /* N = rows, M = out_features, D = in_features */
+};
+
+/* CAM read-out modes (model/model.py:156-161, :356-362) */
+enum { VTC_CAM_READOUT_AVG = 0, VTC_CAM_READOUT_RESIDUAL_ONLY = 1, VTC_CAM_READOUT_UNIFORM = 2 };
+
+enum {
+  VTC_OK = 0,
+  VTC_ERR_INVALID_ARG = -1,
+  VTC_ERR_UNSUPPORTED_SHAPE = -2,
+  VTC_ERR_WORKSPACE = -3,
+  VTC_ERR_NO_DEVICE = -4,
+  VTC_ERR_DRIVER = -5,
+  VTC_ERR_CUDA_BASE = -1000 /* -1000 - cudaError_t */
+};
+
+int vtc_abi_version(void);
+const char* vtc_strerror(int code);
+
+/* bytes of caller-owned workspace an op needs; 0 on invalid arguments. */
+size_t vtc_workspace_bytes(int op, int64_t N, int64_t M, int D, int precision);
+
+/* ---- H1: normalize(x) = x / ||x||_2, no eps (model/model.py:26-27) ---------------------------
+ * vtc_row_norms writes inv_norm[r] = 1/||x_r|| and sq_norm[r] = ||x_r||^2 (either may be NULL);
+ * vtc_normalize writes Y = X / ||X|| (Y may alias X).  A zero row yields NaN like the reference. */
+int vtc_row_norms(const void* X, int64_t rows, int D, int64_t ldx, int dtype, float* inv_norm,
+                  float* sq_norm, vtc_stream_t stream);
+int vtc_normalize(const void* X, int64_t rows, int D, int64_t ldx, int dtype, void* Y, int64_t ldy,
+                  vtc_stream_t stream);
+
+/* ---- H2: sim = (scale * A) @ B^T materialised (model/model.py:369,478,504,621) ---------------
+ * Only for callers that really need the tensor; the fused ops below never form it.
+ * A [N,D], B [M,D]; out fp32 [N,M] with leading dimension ldo; *scale is a device scalar. */
+int vtc_sim_matrix(const void* A, const void* B, int64_t N, int64_t M, int D, int dtype,
+                   int precision, const float* scale, float* out, int64_t ldo, void* ws,
+                   size_t ws_bytes, vtc_stream_t stream);
+
+/* ---- R1/R3: fused similarity + rank of ground truth ------------------------------------------
+ * Replaces faiss.GpuIndexFlatL2.add/search + the host loop of RecallAtK.compute
+ * (model/metric.py:137-161).  Q [N,D] queries, G [M,D] gallery (a chunk of the gallery when
+ * col_offset/gt_score are used).  Ground truth of query t is gallery row gt[t] (global index) or
+ * t + row_offset when gt == NULL.  rank0[t] (int32) receives, or with accumulate != 0 is
+ * incremented by,
+ *     #{ j in this G : j_glob != gt, d(t,j) < d(t,gt) } + #{ j_glob < gt : d(t,j) == d(t,gt) }
+ * with j_glob = j + col_offset.  gt_score [N] (fp64, device) is d(t,gt); when NULL it is computed
+ * from this G (gt must then lie inside it) and, if gt_score_out != NULL, stored there.
+ * Finish with vtc_rank_finalize once all gallery chunks are accumulated. */
+int vtc_sim_rank(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                 const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
+                 int precision, const double* gt_score, double* gt_score_out, int accumulate,
+                 int32_t* rank0, void* ws, size_t ws_bytes, vtc_stream_t stream);
+
+/* fp64-sequential d(t,gt) for each query (also the pre-pass of vtc_sim_rank). */
+int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                  const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
+                  int precision, double* gt_score, void* ws, size_t ws_bytes,
+                  vtc_stream_t stream);
+
+/* rank0[t] = M_total where gt_score[t] is NaN ("never retrieved"); hits[i] = #{t: rank0[t] <
+ * k_vals[i]} (int64, device; replaces model/metric.py:149-160); k_vals is a HOST array, nk <= 8.
+ * medr (device double, may be NULL) = median(rank0) + 1 with numpy semantics.
+ * hist_ws: >= 2*65536*4 bytes of workspace when medr != NULL. */
+int vtc_rank_finalize(int32_t* rank0, const double* gt_score, int64_t N, int64_t M_total,
+                      const int* k_vals, int nk, int64_t* hits, double* medr, void* hist_ws,
+                      size_t hist_ws_bytes, vtc_stream_t stream);
+
+/* ---- K7: fused similarity + streaming top-k ----------------------------------------------------
+ * The `search(b, max(k)+1)` of model/metric.py:144-146 without the N x M matrix.  k <= 16.
+ * out_val fp32 [N,k] ascending score d (L2: ||x||^2 - 2q.x + ||q||^2 like faiss; DOT: -q.x),
+ * out_idx int64 [N,k] = j + col_offset, ties by lower index, -1/+inf fill when M < k. */
+int vtc_sim_topk(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype, int metric,
+                 int precision, int k, int64_t col_offset, float* out_val, int64_t* out_idx,
+                 void* ws, size_t ws_bytes, vtc_stream_t stream);
+
+/* merge `parts` sorted candidate lists vals/idx [parts,N,k] into the k best per row. */
+int vtc_topk_merge(const float* vals, const int64_t* idx, int parts, int64_t N, int k,
+                   float* out_val, int64_t* out_idx, vtc_stream_t stream);
+
+/* ---- H2+H3: fused similarity + symmetric InfoNCE (model/loss.py:18-22) -------------------------
+ * A [n,D], B [n,D] (already normalised); logits = (*scale) * A B^T never reach HBM.
+ * loss (device float) = 0.5 * (mean_i[row_lse_i - diag_i] + mean_j[col_lse_j - diag_j]);
+ * row_lse/col_lse/diag [n] fp32 are saved for the backward. */
+int vtc_infonce_fwd(const void* A, const void* B, int64_t n, int D, int dtype, int precision,
+                    const float* scale, float* loss, float* row_lse, float* col_lse, float* diag,
+                    void* ws, size_t ws_bytes, vtc_stream_t stream);
+
+/* backward of vtc_infonce_fwd: dA, dB fp32 [n,D], dscale (device float); grad_loss device float. */
+int vtc_infonce_bwd(const void* A, const void* B, int64_t n, int D, int dtype, const float* scale,
+                    const float* row_lse, const float* col_lse, const float* grad_loss, float* dA,
+                    float* dB, float* dscale, void* ws, size_t ws_bytes, vtc_stream_t stream);
+
+/* ---- H4: Context Adapter Module pieces (model/model.py:141-205) --------------------------------
+ * vtc_cam_stack_normalize: X[l] = normalize(l == 0 ? main : aux[l-1]) -> X [L,b,D]   (:150-151)
+ * vtc_layernorm          : fp32 LayerNorm over the last dim, eps 1e-5 (clip.model.LayerNorm)
+ * vtc_cam_attn_core      : per (token batch, head) softmax(q k^T / sqrt(hd)) v over L <= 16
+ *                          tokens; QKV [L,b,3D] (in_proj output), out [L,b,D]       (:155, MHA)
+ * vtc_bias_act           : Y = act(X + bias) (+ residual); act 0 = none, 1 = QuickGELU
+ * vtc_cam_readout        : AVG:  res = normalize(mean_l normalize(T_l))            (:156-159)
+ *                          RESIDUAL_ONLY: res = `res_in` [b,D] (final_linear done by caller, :161)
+ *                          UNIFORM: out = normalize(mean_l T_l)  (averaging fusion, :356-366)
+ *                          then (AVG / RESIDUAL_ONLY) zero rows where skip_mask != 0 (:199-201)
+ *                          and out = normalize(normalize(main) + res)               (:203) */
+int vtc_cam_stack_normalize(const float* main, const float* aux, int L, int64_t b, int D,
+                            float* X, vtc_stream_t stream);
+int vtc_layernorm(const float* X, const float* gamma, const float* beta, int64_t rows, int D,
+                  float eps, float* Y, vtc_stream_t stream);
+int vtc_cam_attn_core(const float* QKV, int L, int64_t b, int D, int heads, float* out,
+                      vtc_stream_t stream);
+int vtc_bias_act(const float* X, const float* bias, const float* residual, int64_t rows, int D,
+                 int act, float* Y, vtc_stream_t stream);
+int vtc_cam_readout(const float* T, const float* main, const float* res_in,
+                    const uint8_t* skip_mask, int L, int64_t b, int D, int mode, float* out,
+                    vtc_stream_t stream);
+
+/* ---- dense linear on the tensor cores (CAM projections / MLP) ----------------------------------
+ * Y[rows,out_f] = act(X[rows,in_f] @ W[out_f,in_f]^T + bias) + residual, fused in the GEMM
+ * epilogue (fp32 in/out; bias [out_f] and residual [rows,out_f] nullable; act 0 none / 1
+ * QuickGELU; precision EXACT or BF16). */
+int vtc_linear(const float* X, const float* W, const float* bias, const float* residual,
+               int64_t rows, int in_f, int out_f, int act, int precision, float* Y, void* ws,
+               size_t ws_bytes, vtc_stream_t stream);
+
+/* number of kernels this library has launched since load (for bench.py's gpu_launches). */
+uint64_t vtc_launch_count(void);
+
+/* Opt-in profiling aid: while enabled, every tensor-core similarity launch is bracketed by CUDA
+ * events on its own stream.  vtc_kernel_timer_read synchronises those events, returns their summed
+ * duration (HOST pointers: total_ms, count) and clears the list.  Off by default. */
+int vtc_kernel_timer_enable(int on);
+int vtc_kernel_timer_read(double* total_ms, int* count);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTC_B200_H_ */

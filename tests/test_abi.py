@@ -1,0 +1,100 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol
+include/vtc_b200.h declares, and rejects bad arguments without touching a GPU."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "vtc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vtc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_what_the_binding_binds():
+    from vtc_b200 import _ffi
+
+    declared = _declared_symbols()
+    assert declared, "no declarations parsed"
+    assert sorted(_ffi.SIGNATURES) == declared
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in _declared_symbols():
+        assert hasattr(lib, name), f"{name} not exported by libvtc_b200.so"
+    assert lib.vtc_abi_version() == 1
+    assert lib.vtc_strerror(0) == b"ok"
+    assert b"workspace" in lib.vtc_strerror(-3)
+
+
+def test_argument_counts_match_header(lib):
+    from vtc_b200 import _ffi
+
+    text = open(os.path.join(ROOT, "include", "vtc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, (_, argtypes) in _ffi.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, text, flags=re.S)
+        assert m, name
+        args = m.group(1).strip()
+        n = 0 if args in ("void", "") else args.count(",") + 1
+        assert n == len(argtypes), f"{name}: header has {n} parameters, binding {len(argtypes)}"
+
+
+def test_workspace_sizes_are_sane(lib):
+    from vtc_b200 import _ffi
+
+    small = lib.vtc_workspace_bytes(_ffi.OP_SIM_RANK, 1000, 1000, 512, _ffi.PREC_BF16)
+    big = lib.vtc_workspace_bytes(_ffi.OP_SIM_RANK, 100000, 100000, 512, _ffi.PREC_BF16)
+    exact = lib.vtc_workspace_bytes(_ffi.OP_SIM_RANK, 100000, 100000, 512, _ffi.PREC_EXACT)
+    assert 0 < small < big < exact < 2 * 1024 ** 3
+    # operands dominate: 2 * 100k * 512 * 2 B (bf16) and 3x that for the split
+    assert big > 2 * 100000 * 512 * 2
+    assert exact > 2 * 100000 * 1536 * 2
+    assert lib.vtc_workspace_bytes(99, 1, 1, 1, 0) == 0
+    assert lib.vtc_workspace_bytes(_ffi.OP_SIM_RANK, -1, 1, 1, 0) == 0
+
+
+def test_invalid_arguments_are_rejected_before_any_launch(lib):
+    from vtc_b200 import _ffi
+
+    before = lib.vtc_launch_count()
+    assert lib.vtc_row_norms(None, 4, 8, 8, _ffi.F32, None, None, None) == -1
+    assert lib.vtc_sim_rank(None, None, 4, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
+                            _ffi.PREC_EXACT, None, None, 0, None, None, 0, None) == -1
+    assert lib.vtc_topk_merge(None, None, 2, 4, 3, None, None, None) == -1
+    assert lib.vtc_cam_attn_core(None, 6, 4, 512, 8, None, None) == -1
+    assert lib.vtc_launch_count() == before
+
+
+def test_product_path_fails_loudly_without_cuda():
+    """No CPU fallback: CPU tensors are refused."""
+    import numpy as np
+    import torch
+
+    from vtc_b200 import VtcError, ops
+    from vtc_b200.model import RecallAtK, clip_loss
+
+    x = torch.randn(4, 8)
+    with pytest.raises(VtcError):
+        ops.normalize(x)
+    with pytest.raises(VtcError):
+        ops.sim_rank(x, x)
+    with pytest.raises(VtcError):
+        clip_loss((x, x, x @ x.t()), {})
+    if not torch.cuda.is_available():
+        with pytest.raises(VtcError):
+            RecallAtK("a", "b", [1]).compute(np.zeros((4, 8), np.float32), np.zeros((4, 8), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under vtc_b200/ may import or call it."""
+    pkg = os.path.join(ROOT, "vtc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "vtc_oracle" not in src.replace("oracle/vtc_oracle", ""), f

@@ -1,0 +1,84 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU work)."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_reference_symbols_and_signatures_exist():
+    import inspect
+
+    from vtc_b200.evaluation.retrieval_evaluation import compute_recall
+    from vtc_b200.model.loss import clip_loss
+    from vtc_b200.model.metric import RecallAtK
+
+    sig = inspect.signature(compute_recall)
+    assert list(sig.parameters)[:4] == ["tensor_v", "tensor_t", "split", "dataset_name"]
+    assert sig.parameters["split"].default == "full-test"
+    assert sig.parameters["dataset_name"].default == "MSRVTT"
+    assert list(inspect.signature(clip_loss).parameters)[:2] == ["input", "meta"]
+    m = RecallAtK("visual", "titles", k_vals=5)  # scalar k like the reference default
+    assert m.k_vals == [5] and m.name == "recall@k" and m.is_train is False and m.is_val is True
+    for meth in ("set_writer", "reset", "update", "avg", "result", "compute"):
+        assert callable(getattr(m, meth))
+    assert m.avg() is None
+
+
+def test_checkpoint_parameter_names_match_the_reference():
+    """final_transformer.resblocks.{i}.* / final_linear.weight / mask_embedding must survive
+    (trainer/base_trainer.py:175-176, train.py:105)."""
+    from oracle.vtc_oracle import cam_param_names
+    from vtc_b200.model import PretrainedCLIP_finaltf
+
+    m = PretrainedCLIP_finaltf(64, n_layers=2, n_heads=2)
+    names = {n for n, _ in m.named_parameters()}
+    for n in cam_param_names(2):
+        assert "final_transformer." + n in names, n
+    assert "final_linear.weight" in names and "mask_embedding" in names
+    # the reference's zero-inits (model/model.py:440-452)
+    for blk in m.final_transformer.resblocks:
+        assert blk.mlp.c_proj.weight.abs().sum() == 0 and blk.mlp.c_proj.bias.abs().sum() == 0
+        assert blk.attn.out_proj.weight.abs().sum() == 0
+    assert m.final_linear.weight.abs().sum() == 0
+    # shapes follow nn.MultiheadAttention / clip.model.Transformer
+    sd = m.state_dict()
+    assert sd["final_transformer.resblocks.0.attn.in_proj_weight"].shape == (192, 64)
+    assert sd["final_transformer.resblocks.1.mlp.c_fc.weight"].shape == (256, 64)
+
+
+def test_lazy_sim_metadata_needs_no_gpu():
+    from vtc_b200.model import LazySim
+
+    a, b = torch.randn(5, 8), torch.randn(7, 8)
+    s = LazySim(a, b, 100.0)
+    assert tuple(s.shape) == (5, 7) and s.size(0) == 5 and s.dim() == 2 and len(s) == 5
+    assert s.dtype == torch.float32 and s.device == a.device
+
+
+def test_multi_caption_input_is_rejected_clearly():
+    from vtc_b200.evaluation.retrieval_evaluation import _squeeze_text
+
+    with pytest.raises(ValueError, match="one text per video"):
+        _squeeze_text(torch.zeros(10, 20, 8))
+    assert _squeeze_text(torch.zeros(10, 1, 8)).shape == (10, 8)
+    assert _squeeze_text(torch.zeros(1, 1, 8)).shape == (1, 8)
+
+
+def test_shard_bounds_partition():
+    from vtc_b200.parallel import shard_bounds
+
+    for n in (0, 1, 7, 100, 100003):
+        for w in (1, 2, 3, 8):
+            cuts = [shard_bounds(n, w, r) for r in range(w)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_recipe_is_calibrated():
+    from vtc_b200.synthetic import make_retrieval_pair
+
+    T, V = make_retrieval_pair(1000, 1000, 512)
+    np.testing.assert_allclose(T.norm(dim=-1).numpy(), 1.0, rtol=1e-5)
+    cos = (T * V).sum(1)
+    assert abs(cos.mean().item() - 1 / np.sqrt(1 + 36)) < 0.01

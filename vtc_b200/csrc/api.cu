@@ -1,0 +1,571 @@
+// api.cu -- the extern "C" entry points declared in include/vtc_b200.h.
+//
+// Each entry point validates its arguments, carves the caller's workspace, and enqueues kernels on
+// the caller's stream.  Nothing here allocates device memory or synchronises.
+#include <cstdlib>
+#include <cstring>
+
+#include "cam.cuh"
+#include "exact.cuh"
+#include "prep.cuh"
+#include "reduce.cuh"
+#include "sim_tc.cuh"
+
+namespace vtc {
+std::atomic<uint64_t> g_launch_count{0};
+
+namespace {
+
+float guard_rel_for(int precision) {
+  // Bounds on |tensor-core dot - exact dot| / (|q| |x|); see DESIGN.md "guard band".
+  //   BF16 : products of bf16 are exact in fp32, only the fp32 accumulation of K/16 MMAs errs.
+  //   EXACT: 3-term bf16 split drops <= 3 * 2^-18 of each product, plus 3x the accumulation.
+  const char* e = getenv(precision == VTC_PREC_BF16 ? "VTC_GUARD_REL_BF16" : "VTC_GUARD_REL_EXACT");
+  if (e && *e) {
+    const float v = (float)atof(e);
+    if (v > 0.f) return v;
+  }
+  return precision == VTC_PREC_BF16 ? 6.103515625e-05f /* 2^-14 */ : 1.220703125e-04f /* 2^-13 */;
+}
+
+bool valid_dtype(int d) { return d == VTC_F32 || d == VTC_BF16; }
+bool valid_metric(int m) { return m == VTC_METRIC_DOT || m == VTC_METRIC_L2; }
+bool valid_prec(int p) { return p == VTC_PREC_EXACT || p == VTC_PREC_BF16 || p == VTC_PREC_BRUTE; }
+
+// Operand plan of a tensor-core pass: which layout the bf16 operands take and which arrays hold
+// the canonical values the exact kernels read.
+struct OperandPlan {
+  bool split;  // 3-term bf16 split (fp32 inputs ranked exactly)
+  int Kp;      // padded K' of the bf16 operands
+};
+OperandPlan plan_operands(int D, int dtype, int precision) {
+  OperandPlan o;
+  o.split = (precision == VTC_PREC_EXACT && dtype == VTC_F32);
+  o.Kp = round_up(o.split ? 3 * D : D, tc::BK);
+  return o;
+}
+
+constexpr int64_t kMaxRows = (int64_t)1 << 30;
+
+// ------------------------------------------------------------------------------------ sim_rank
+struct RankWs {
+  __nv_bfloat16 *opQ, *opG;
+  double *sq64, *dgt;
+  float* sq32;
+  unsigned int* scalars;  // [0] max_sq_bits, [1] amb_count, [2] overflow
+  float2* thr;
+  int* rank_tmp;
+  int2* amb;
+  size_t amb_cap;
+};
+
+size_t amb_entries_wanted(int64_t N) {
+  const int64_t want = 64 * N;
+  return (size_t)(want < (1 << 20) ? (1 << 20) : want);
+}
+
+RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int precision,
+                  bool sizing) {
+  RankWs r;
+  memset(&r, 0, sizeof(r));
+  r.sq64 = ws.take<double>(M);
+  r.dgt = ws.take<double>(N);
+  r.scalars = ws.take<unsigned int>(64);
+  if (precision != VTC_PREC_BRUTE) {
+    const OperandPlan o = plan_operands(D, dtype, precision);
+    r.opQ = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
+    r.opG = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
+    r.sq32 = ws.take<float>(M);
+    r.thr = ws.take<float2>(N);
+    r.rank_tmp = ws.take<int>(N);
+    if (sizing) {
+      r.amb_cap = amb_entries_wanted(N);
+      ws.take<int2>(r.amb_cap);
+    } else {
+      const size_t left = ws.size > ws.used ? ws.size - ws.used : 0;
+      size_t cap = left / sizeof(int2);
+      if (cap > 0x7fffffffu) cap = 0x7fffffffu;
+      r.amb_cap = cap;
+      r.amb = cap ? ws.take<int2>(cap) : nullptr;
+    }
+  }
+  return r;
+}
+
+int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                  const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
+                  int precision, const double* gt_score, double* gt_score_out, int accumulate,
+                  int32_t* rank0, void* wsp, size_t ws_bytes, cudaStream_t s) {
+  if (!Q || !G || !rank0 || N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) ||
+      !valid_metric(metric) || !valid_prec(precision))
+    return VTC_ERR_INVALID_ARG;
+  if (N > kMaxRows || M > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
+  if (N == 0) return VTC_OK;
+  Workspace ws(wsp, ws_bytes);
+  RankWs w = carve_rank(ws, N, M, D, dtype, precision, false);
+  if (!ws.ok() || !w.sq64 || !w.dgt || !w.scalars) return VTC_ERR_WORKSPACE;
+  const bool in_bf16 = dtype == VTC_BF16;
+  cudaError_t e = cudaMemsetAsync(w.scalars, 0, 64 * sizeof(unsigned int), s);
+  if (e != cudaSuccess) return cuda_err(e);
+
+  if (precision == VTC_PREC_BRUTE || M == 0) {
+    ExactArgs ex{Q, G, D, D, in_bf16, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
+    if (M > 0 && metric == VTC_METRIC_L2)
+      VTC_RETURN_IF_ERROR(launch_sqnorm64(G, in_bf16, M, D, D, w.sq64, nullptr, nullptr, s));
+    VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, nullptr, nullptr, 0.f, s));
+    if (gt_score_out) {
+      e = cudaMemcpyAsync(gt_score_out, w.dgt, sizeof(double) * N, cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return cuda_err(e);
+    }
+    if (!accumulate) {
+      e = cudaMemsetAsync(rank0, 0, sizeof(int32_t) * N, s);
+      if (e != cudaSuccess) return cuda_err(e);
+    }
+    return launch_rank_brute(ex, w.dgt, rank0, nullptr, s);
+  }
+
+  if (!w.opQ || !w.opG || !w.thr || !w.rank_tmp || !w.amb || w.amb_cap < 1024)
+    return VTC_ERR_WORKSPACE;
+  const OperandPlan o = plan_operands(D, dtype, precision);
+  // 1. bf16 operands
+  VTC_RETURN_IF_ERROR(launch_prep_operand(Q, in_bf16, N, D, D, o.split ? PREP_SPLIT_A : PREP_PLAIN,
+                                          w.opQ, o.Kp, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D, o.split ? PREP_SPLIT_B : PREP_PLAIN,
+                                          w.opG, o.Kp, s));
+  // canonical values: fp32 inputs (split) or the bf16 roundings just written
+  ExactArgs ex;
+  if (o.split)
+    ex = ExactArgs{Q, G, D, D, false, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
+  else
+    ex = ExactArgs{w.opQ, w.opG, o.Kp, o.Kp, true, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
+  // 2. canonical norms, ground-truth scores, guard band
+  VTC_RETURN_IF_ERROR(launch_sqnorm64(ex.G, ex.bf16, M, D, ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
+  VTC_RETURN_IF_ERROR(
+      launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0], guard_rel_for(precision), s));
+  if (gt_score_out) {
+    e = cudaMemcpyAsync(gt_score_out, w.dgt, sizeof(double) * N, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return cuda_err(e);
+  }
+  e = cudaMemsetAsync(w.rank_tmp, 0, sizeof(int) * N, s);
+  if (e != cudaSuccess) return cuda_err(e);
+  // 3. tensor-core pass
+  tc::Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
+  p.col_bias = metric == VTC_METRIC_L2 ? w.sq32 : nullptr;
+  p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
+  p.oob_bias = INFINITY;
+  p.thr = w.thr, p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_count = &w.scalars[1];
+  p.amb_cap = (unsigned int)w.amb_cap;
+  const int grid = tc::plan_tiles(p, 64);
+  CUtensorMap tmA, tmB;
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN, &tmB));
+  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, tmA, tmB, p, grid, s));
+  // 4. exact re-check of the guard-band pairs; brute force if the list overflowed
+  VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[1], (unsigned int)w.amb_cap, w.dgt,
+                                     w.rank_tmp, &w.scalars[2], s));
+  VTC_RETURN_IF_ERROR(launch_zero_if_flag(w.rank_tmp, N, &w.scalars[2], s));
+  VTC_RETURN_IF_ERROR(launch_rank_brute(ex, w.dgt, w.rank_tmp, &w.scalars[2], s));
+  return launch_rank_commit(w.rank_tmp, rank0, N, accumulate, s);
+}
+
+// ------------------------------------------------------------------------------------ sim_topk
+struct TopkWs {
+  __nv_bfloat16 *opQ, *opG;
+  double* sq64;
+  float* sq32;
+  unsigned int* scalars;
+  float* pool_val;
+  int* pool_idx;
+  float2* pool_meta;
+  unsigned int* row_flag;
+};
+constexpr int kTopkMaxSplits = 8;
+
+TopkWs carve_topk(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int precision) {
+  TopkWs t;
+  memset(&t, 0, sizeof(t));
+  const int prec = precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision;
+  const OperandPlan o = plan_operands(D, dtype, prec);
+  t.sq64 = ws.take<double>(M);
+  t.sq32 = ws.take<float>(M);
+  t.scalars = ws.take<unsigned int>(64);
+  t.row_flag = ws.take<unsigned int>(N);
+  t.opQ = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
+  t.opG = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
+  t.pool_val = ws.take<float>((size_t)kTopkMaxSplits * N * tc::TOPK_POOL);
+  t.pool_idx = ws.take<int>((size_t)kTopkMaxSplits * N * tc::TOPK_POOL);
+  t.pool_meta = ws.take<float2>((size_t)kTopkMaxSplits * N);
+  return t;
+}
+
+int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype, int metric,
+                  int precision, int k, int64_t col_offset, float* out_val, int64_t* out_idx,
+                  void* wsp, size_t ws_bytes, cudaStream_t s) {
+  if (!Q || !G || !out_val || !out_idx || N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) ||
+      !valid_metric(metric) || !valid_prec(precision) || k < 1)
+    return VTC_ERR_INVALID_ARG;
+  if (k > 16 || N > kMaxRows || M > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
+  if (N == 0) return VTC_OK;
+  Workspace ws(wsp, ws_bytes);
+  TopkWs w = carve_topk(ws, N, M, D, dtype, precision);
+  if (!ws.ok()) return VTC_ERR_WORKSPACE;
+  const bool in_bf16 = dtype == VTC_BF16;
+  cudaError_t e = cudaMemsetAsync(w.scalars, 0, 64 * sizeof(unsigned int), s);
+  if (e != cudaSuccess) return cuda_err(e);
+  const bool brute = precision == VTC_PREC_BRUTE || M == 0;
+  const OperandPlan o = plan_operands(D, dtype, brute ? VTC_PREC_EXACT : precision);
+  const bool canon_inputs = brute || o.split;
+
+  TopkSelectArgs a;
+  memset(&a, 0, sizeof(a));
+  if (canon_inputs)
+    a.ex = ExactArgs{Q, G, D, D, in_bf16, N, M, D, w.sq64, nullptr, 0, col_offset, metric};
+  else
+    a.ex = ExactArgs{w.opQ, w.opG, o.Kp, o.Kp, true, N, M, D, w.sq64, nullptr, 0, col_offset, metric};
+  a.pool_val = w.pool_val, a.pool_idx = w.pool_idx, a.pool_meta = w.pool_meta;
+  a.pool = tc::TOPK_POOL, a.k = k;
+  a.guard_rel = guard_rel_for(precision);
+  a.max_sq_bits = &w.scalars[0];
+  a.out_val = out_val, a.out_idx = out_idx, a.row_flag = w.row_flag;
+
+  if (brute) {
+    if (M > 0)
+      VTC_RETURN_IF_ERROR(launch_sqnorm64(G, in_bf16, M, D, D, w.sq64, nullptr, nullptr, s));
+    e = cudaMemsetAsync(w.row_flag, 0xff, sizeof(unsigned int) * N, s);  // every row brute-forced
+    if (e != cudaSuccess) return cuda_err(e);
+    return launch_topk_brute_rows(a, s);
+  }
+
+  VTC_RETURN_IF_ERROR(launch_prep_operand(Q, in_bf16, N, D, D, o.split ? PREP_SPLIT_A : PREP_PLAIN,
+                                          w.opQ, o.Kp, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D, o.split ? PREP_SPLIT_B : PREP_PLAIN,
+                                          w.opG, o.Kp, s));
+  VTC_RETURN_IF_ERROR(
+      launch_sqnorm64(a.ex.G, a.ex.bf16, M, D, a.ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
+  tc::Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
+  p.col_bias = metric == VTC_METRIC_L2 ? w.sq32 : nullptr;
+  p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
+  p.oob_bias = INFINITY;
+  p.pool_val = w.pool_val, p.pool_idx = w.pool_idx, p.pool_meta = w.pool_meta;
+  const int grid = tc::plan_tiles(p, kTopkMaxSplits);
+  a.splits = p.g_splits;
+  CUtensorMap tmA, tmB;
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN, &tmB));
+  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_TOPK, p.num_kb <= 8, tmA, tmB, p, grid, s));
+  VTC_RETURN_IF_ERROR(launch_topk_select(a, s));
+  return launch_topk_brute_rows(a, s);
+}
+
+// --------------------------------------------------------------------------- dense TC products
+// out[N,M] = act(scale * A B^T + bias) + residual, fp32 in/out.
+struct GemmWs {
+  __nv_bfloat16 *opA, *opB;
+};
+GemmWs carve_gemm(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int precision) {
+  const OperandPlan o = plan_operands(D, dtype, precision);
+  GemmWs g;
+  g.opA = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
+  g.opB = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
+  return g;
+}
+
+int gemm_store_impl(const void* A, const void* B, int64_t N, int64_t M, int D, int dtype,
+                    int precision, const float* scale_ptr, const float* bias,
+                    const float* residual, int act, float* out, int64_t ldo, void* wsp,
+                    size_t ws_bytes, cudaStream_t s) {
+  if (!A || !B || !out || N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) || ldo < M ||
+      (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16))
+    return VTC_ERR_INVALID_ARG;
+  if (N > kMaxRows || M > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
+  if (N == 0 || M == 0) return VTC_OK;
+  Workspace ws(wsp, ws_bytes);
+  GemmWs g = carve_gemm(ws, N, M, D, dtype, precision);
+  if (!ws.ok()) return VTC_ERR_WORKSPACE;
+  const OperandPlan o = plan_operands(D, dtype, precision);
+  const bool in_bf16 = dtype == VTC_BF16;
+  VTC_RETURN_IF_ERROR(launch_prep_operand(A, in_bf16, N, D, D, o.split ? PREP_SPLIT_A : PREP_PLAIN,
+                                          g.opA, o.Kp, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(B, in_bf16, M, D, D, o.split ? PREP_SPLIT_B : PREP_PLAIN,
+                                          g.opB, o.Kp, s));
+  tc::Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
+  p.col_bias = bias, p.scale_ptr = scale_ptr, p.scale = 1.f, p.oob_bias = 0.f;
+  p.out = out, p.ldo = ldo, p.residual = residual, p.act = act;
+  const int grid = tc::plan_tiles(p, 1);
+  CUtensorMap tmA, tmB;
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opA, N, o.Kp, o.Kp, tc::BM, &tmA));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opB, M, o.Kp, o.Kp, tc::BN, &tmB));
+  return tc::launch_sim_tc(tc::EPI_STORE, p.num_kb <= 8, tmA, tmB, p, grid, s);
+}
+
+// ------------------------------------------------------------------------------------- InfoNCE
+struct NceWs {
+  __nv_bfloat16 *a_as_a, *b_as_b, *b_as_a, *a_as_b;
+  float2 *part_row, *part_col;
+  float* diag_raw;
+};
+constexpr int kNceMaxSplits = 8;
+NceWs carve_nce(Workspace& ws, int64_t n, int D, int dtype, int precision) {
+  const OperandPlan o = plan_operands(D, dtype, precision);
+  NceWs w;
+  memset(&w, 0, sizeof(w));
+  w.a_as_a = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
+  w.b_as_b = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
+  if (o.split) {
+    w.b_as_a = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
+    w.a_as_b = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
+  } else {
+    w.b_as_a = w.b_as_b;
+    w.a_as_b = w.a_as_a;
+  }
+  w.part_row = ws.take<float2>((size_t)kNceMaxSplits * n);
+  w.part_col = ws.take<float2>((size_t)kNceMaxSplits * n);
+  w.diag_raw = ws.take<float>(n);
+  return w;
+}
+
+int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, int precision,
+                     const float* scale, float* loss, float* row_lse, float* col_lse, float* diag,
+                     void* wsp, size_t ws_bytes, cudaStream_t s) {
+  if (!A || !B || !scale || !loss || !row_lse || !col_lse || !diag || n <= 0 || D <= 0 ||
+      !valid_dtype(dtype) || (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16))
+    return VTC_ERR_INVALID_ARG;
+  if (n > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
+  Workspace ws(wsp, ws_bytes);
+  NceWs w = carve_nce(ws, n, D, dtype, precision);
+  if (!ws.ok()) return VTC_ERR_WORKSPACE;
+  const OperandPlan o = plan_operands(D, dtype, precision);
+  const bool in_bf16 = dtype == VTC_BF16;
+  const int ma = o.split ? PREP_SPLIT_A : PREP_PLAIN, mb = o.split ? PREP_SPLIT_B : PREP_PLAIN;
+  VTC_RETURN_IF_ERROR(launch_prep_operand(A, in_bf16, n, D, D, ma, w.a_as_a, o.Kp, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(B, in_bf16, n, D, D, mb, w.b_as_b, o.Kp, s));
+  if (o.split) {
+    VTC_RETURN_IF_ERROR(launch_prep_operand(B, in_bf16, n, D, D, ma, w.b_as_a, o.Kp, s));
+    VTC_RETURN_IF_ERROR(launch_prep_operand(A, in_bf16, n, D, D, mb, w.a_as_b, o.Kp, s));
+  }
+  for (int dir = 0; dir < 2; ++dir) {
+    tc::Params p;
+    memset(&p, 0, sizeof(p));
+    p.N = n, p.M = n, p.num_kb = o.Kp / tc::BK;
+    p.scale_ptr = scale, p.scale = 1.4426950408889634f;  // logits in log2 units
+    p.oob_bias = -INFINITY;
+    p.lse_part = dir == 0 ? w.part_row : w.part_col;
+    p.diag = dir == 0 ? w.diag_raw : nullptr;
+    p.diag_offset = 0;
+    const int grid = tc::plan_tiles(p, kNceMaxSplits);
+    CUtensorMap tmA, tmB;
+    VTC_RETURN_IF_ERROR(
+        tc::make_operand_tmap(dir == 0 ? w.a_as_a : w.b_as_a, n, o.Kp, o.Kp, tc::BM, &tmA));
+    VTC_RETURN_IF_ERROR(
+        tc::make_operand_tmap(dir == 0 ? w.b_as_b : w.a_as_b, n, o.Kp, o.Kp, tc::BN, &tmB));
+    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_LSE, p.num_kb <= 8, tmA, tmB, p, grid, s));
+    VTC_RETURN_IF_ERROR(launch_lse_merge(p.lse_part, p.g_splits, n, dir == 0 ? row_lse : col_lse, s));
+  }
+  return launch_infonce_loss(row_lse, col_lse, w.diag_raw, scale, n, diag, loss, s);
+}
+
+}  // namespace
+}  // namespace vtc
+
+using namespace vtc;
+
+extern "C" {
+
+int vtc_abi_version(void) { return VTC_ABI_VERSION; }
+
+const char* vtc_strerror(int code) {
+  switch (code) {
+    case VTC_OK: return "ok";
+    case VTC_ERR_INVALID_ARG: return "invalid argument";
+    case VTC_ERR_UNSUPPORTED_SHAPE: return "unsupported shape";
+    case VTC_ERR_WORKSPACE: return "workspace missing or too small (see vtc_workspace_bytes)";
+    case VTC_ERR_NO_DEVICE: return "no CUDA device";
+    case VTC_ERR_DRIVER: return "CUDA driver entry point unavailable or tensor-map encode failed";
+    default: break;
+  }
+  if (code <= VTC_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(VTC_ERR_CUDA_BASE - code));
+  return "unknown error";
+}
+
+uint64_t vtc_launch_count(void) { return g_launch_count.load(); }
+
+int vtc_kernel_timer_enable(int on) {
+  tc::kernel_timer_enable(on != 0);
+  return VTC_OK;
+}
+
+int vtc_kernel_timer_read(double* total_ms, int* count) {
+  return tc::kernel_timer_read(total_ms, count);
+}
+
+size_t vtc_workspace_bytes(int op, int64_t N, int64_t M, int D, int precision) {
+  if (N < 0 || M < 0 || D <= 0 || !valid_prec(precision)) return 0;
+  Workspace ws(nullptr, 0);
+  // sizes do not depend on the storage dtype except through the split; assume fp32 inputs (worst)
+  switch (op) {
+    case VTC_OP_SIM_RANK: carve_rank(ws, N, M, D, VTC_F32, precision, true); break;
+    case VTC_OP_SIM_TOPK: carve_topk(ws, N, M, D, VTC_F32, precision); break;
+    case VTC_OP_INFONCE_FWD:
+      carve_nce(ws, N, D, VTC_F32, precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision);
+      break;
+    case VTC_OP_SIM_MATRIX:
+      carve_gemm(ws, N, M, D, VTC_F32, precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision);
+      break;
+    case VTC_OP_LINEAR:
+      carve_gemm(ws, N, M, D, VTC_F32, precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision);
+      break;
+    case VTC_OP_INFONCE_BWD: ws.take<float>((size_t)N * N); break;
+    case VTC_OP_GT_SCORES:
+      ws.take<double>(M);
+      ws.take<__nv_bfloat16>((size_t)N * round_up(D, tc::BK));
+      ws.take<__nv_bfloat16>((size_t)M * round_up(D, tc::BK));
+      break;
+    default: return 0;
+  }
+  return ws.used + 512;
+}
+
+int vtc_row_norms(const void* X, int64_t rows, int D, int64_t ldx, int dtype, float* inv_norm,
+                  float* sq_norm, vtc_stream_t stream) {
+  if (!X || rows < 0 || D <= 0 || ldx < D || !valid_dtype(dtype)) return VTC_ERR_INVALID_ARG;
+  return launch_row_norms(X, dtype == VTC_BF16, rows, D, ldx, inv_norm, sq_norm,
+                          (cudaStream_t)stream);
+}
+
+int vtc_normalize(const void* X, int64_t rows, int D, int64_t ldx, int dtype, void* Y, int64_t ldy,
+                  vtc_stream_t stream) {
+  if (!X || !Y || rows < 0 || D <= 0 || ldx < D || ldy < D || !valid_dtype(dtype))
+    return VTC_ERR_INVALID_ARG;
+  return launch_normalize(X, dtype == VTC_BF16, rows, D, ldx, Y, ldy, (cudaStream_t)stream);
+}
+
+int vtc_sim_matrix(const void* A, const void* B, int64_t N, int64_t M, int D, int dtype,
+                   int precision, const float* scale, float* out, int64_t ldo, void* ws,
+                   size_t ws_bytes, vtc_stream_t stream) {
+  return gemm_store_impl(A, B, N, M, D, dtype, precision, scale, nullptr, nullptr, 0, out, ldo, ws,
+                         ws_bytes, (cudaStream_t)stream);
+}
+
+int vtc_linear(const float* X, const float* W, const float* bias, const float* residual,
+               int64_t rows, int in_f, int out_f, int act, int precision, float* Y, void* ws,
+               size_t ws_bytes, vtc_stream_t stream) {
+  if (act != 0 && act != 1) return VTC_ERR_INVALID_ARG;
+  return gemm_store_impl(X, W, rows, out_f, in_f, VTC_F32, precision, nullptr, bias, residual, act,
+                         Y, out_f, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int vtc_sim_rank(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                 const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
+                 int precision, const double* gt_score, double* gt_score_out, int accumulate,
+                 int32_t* rank0, void* ws, size_t ws_bytes, vtc_stream_t stream) {
+  return sim_rank_impl(Q, G, N, M, D, dtype, gt, row_offset, col_offset, metric, precision,
+                       gt_score, gt_score_out, accumulate, rank0, ws, ws_bytes,
+                       (cudaStream_t)stream);
+}
+
+int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                  const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
+                  int precision, double* gt_score, void* wsp, size_t ws_bytes,
+                  vtc_stream_t stream) {
+  if (!Q || !G || !gt_score || N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) ||
+      !valid_metric(metric) || !valid_prec(precision))
+    return VTC_ERR_INVALID_ARG;
+  if (N == 0) return VTC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace ws(wsp, ws_bytes);
+  double* sq64 = ws.take<double>(M);
+  const bool in_bf16 = dtype == VTC_BF16;
+  // VTC_PREC_BF16 ranks the bf16 roundings of fp32 inputs: round them first
+  __nv_bfloat16 *opQ = nullptr, *opG = nullptr;
+  const bool round_first = precision == VTC_PREC_BF16 && !in_bf16;
+  const int Kp = round_up(D, tc::BK);
+  if (round_first) {
+    opQ = ws.take<__nv_bfloat16>((size_t)N * Kp);
+    opG = ws.take<__nv_bfloat16>((size_t)M * Kp);
+  }
+  if (!ws.ok()) return VTC_ERR_WORKSPACE;
+  ExactArgs ex;
+  if (round_first) {
+    VTC_RETURN_IF_ERROR(launch_prep_operand(Q, false, N, D, D, PREP_PLAIN, opQ, Kp, s));
+    VTC_RETURN_IF_ERROR(launch_prep_operand(G, false, M, D, D, PREP_PLAIN, opG, Kp, s));
+    ex = ExactArgs{opQ, opG, Kp, Kp, true, N, M, D, sq64, gt, row_offset, col_offset, metric};
+  } else {
+    ex = ExactArgs{Q, G, D, D, in_bf16, N, M, D, sq64, gt, row_offset, col_offset, metric};
+  }
+  if (metric == VTC_METRIC_L2 && M > 0)
+    VTC_RETURN_IF_ERROR(launch_sqnorm64(ex.G, ex.bf16, M, D, ex.ldg, sq64, nullptr, nullptr, s));
+  return launch_gt_score(ex, nullptr, gt_score, nullptr, nullptr, 0.f, s);
+}
+
+int vtc_rank_finalize(int32_t* rank0, const double* gt_score, int64_t N, int64_t M_total,
+                      const int* k_vals, int nk, int64_t* hits, double* medr, void* hist_ws,
+                      size_t hist_ws_bytes, vtc_stream_t stream) {
+  if (!rank0 || N < 0 || nk < 0 || nk > 8 || (nk > 0 && (!k_vals || !hits)))
+    return VTC_ERR_INVALID_ARG;
+  if (medr && (!hist_ws || hist_ws_bytes < 65536 * sizeof(unsigned int))) return VTC_ERR_WORKSPACE;
+  return launch_rank_finalize(rank0, gt_score, N, M_total, k_vals, nk, hits, medr, hist_ws,
+                              (cudaStream_t)stream);
+}
+
+int vtc_sim_topk(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype, int metric,
+                 int precision, int k, int64_t col_offset, float* out_val, int64_t* out_idx,
+                 void* ws, size_t ws_bytes, vtc_stream_t stream) {
+  return sim_topk_impl(Q, G, N, M, D, dtype, metric, precision, k, col_offset, out_val, out_idx, ws,
+                       ws_bytes, (cudaStream_t)stream);
+}
+
+int vtc_topk_merge(const float* vals, const int64_t* idx, int parts, int64_t N, int k,
+                   float* out_val, int64_t* out_idx, vtc_stream_t stream) {
+  if (!vals || !idx || !out_val || !out_idx || N < 0) return VTC_ERR_INVALID_ARG;
+  return launch_topk_merge(vals, idx, parts, N, k, out_val, out_idx, (cudaStream_t)stream);
+}
+
+int vtc_infonce_fwd(const void* A, const void* B, int64_t n, int D, int dtype, int precision,
+                    const float* scale, float* loss, float* row_lse, float* col_lse, float* diag,
+                    void* ws, size_t ws_bytes, vtc_stream_t stream) {
+  return infonce_fwd_impl(A, B, n, D, dtype, precision, scale, loss, row_lse, col_lse, diag, ws,
+                          ws_bytes, (cudaStream_t)stream);
+}
+
+int vtc_cam_stack_normalize(const float* main, const float* aux, int L, int64_t b, int D, float* X,
+                            vtc_stream_t stream) {
+  if (!main || !X || L < 1 || (L > 1 && !aux) || b < 0 || D <= 0) return VTC_ERR_INVALID_ARG;
+  return launch_cam_stack_normalize(main, aux, L, b, D, X, (cudaStream_t)stream);
+}
+
+int vtc_layernorm(const float* X, const float* gamma, const float* beta, int64_t rows, int D,
+                  float eps, float* Y, vtc_stream_t stream) {
+  if (!X || !gamma || !beta || !Y || rows < 0 || D <= 0) return VTC_ERR_INVALID_ARG;
+  return launch_layernorm(X, gamma, beta, rows, D, eps, Y, (cudaStream_t)stream);
+}
+
+int vtc_cam_attn_core(const float* QKV, int L, int64_t b, int D, int heads, float* out,
+                      vtc_stream_t stream) {
+  if (!QKV || !out || b < 0 || D <= 0) return VTC_ERR_INVALID_ARG;
+  return launch_cam_attn_core(QKV, L, b, D, heads, out, (cudaStream_t)stream);
+}
+
+int vtc_bias_act(const float* X, const float* bias, const float* residual, int64_t rows, int D,
+                 int act, float* Y, vtc_stream_t stream) {
+  if (!X || !Y || rows < 0 || D <= 0 || (act != 0 && act != 1)) return VTC_ERR_INVALID_ARG;
+  return launch_bias_act(X, bias, residual, rows, D, act, Y, (cudaStream_t)stream);
+}
+
+int vtc_cam_readout(const float* T, const float* main, const float* res_in,
+                    const uint8_t* skip_mask, int L, int64_t b, int D, int mode, float* out,
+                    vtc_stream_t stream) {
+  if (!out || b < 0 || D <= 0 || L < 1) return VTC_ERR_INVALID_ARG;
+  if (mode == VTC_CAM_READOUT_RESIDUAL_ONLY ? (!res_in || !main)
+                                            : (!T || (mode == VTC_CAM_READOUT_AVG && !main)))
+    return VTC_ERR_INVALID_ARG;
+  if (mode < 0 || mode > 2) return VTC_ERR_INVALID_ARG;
+  return launch_cam_readout(T, main, res_in, skip_mask, L, b, D, mode, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

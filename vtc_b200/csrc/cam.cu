@@ -1,0 +1,271 @@
+// cam.cu -- Context Adapter Module kernels (model/model.py:141-205; clip.model.Transformer block
+// structure per model/timesformer_clip_alt.py:22-33,43-67,112-124).  All fp32, HBM/latency-bound:
+// vectorised, coalesced row kernels (one warp per row) and a one-warp-per-(sample, head) attention
+// core for the short token axis (L = 1 + #comments <= 16).  The dense projections run on the
+// tensor cores through vtc_linear (sim_tc.cu, EPI_STORE).
+#include "cam.cuh"
+
+namespace vtc {
+
+constexpr int WARPS = 8;
+constexpr int MAX_VEC = 8;  // float4 per lane: rows up to D = 1024
+
+// row r of the stacked input: l == 0 -> main[b], else aux[l-1][b]
+__global__ void __launch_bounds__(256)
+cam_stack_normalize_kernel(const float* __restrict__ main, const float* __restrict__ aux, int L,
+                           int64_t b, int D, float* __restrict__ X) {
+  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= (int64_t)L * b) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t l = r / b, bi = r % b;
+  const float* src = l == 0 ? main + bi * D : aux + ((l - 1) * b + bi) * D;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) s = fmaf(src[k], src[k], s);
+  const float nrm = sqrtf(warp_sum(s));
+  float* dst = X + r * D;
+  for (int k = lane; k < D; k += 32) dst[k] = src[k] / nrm;
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int64_t rows, int D, float eps,
+                 float* __restrict__ Y) {
+  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* x = X + r * D;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) s += x[k];
+  const float mean = warp_sum(s) / (float)D;
+  float v = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float d = x[k] - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)D + eps);
+  float* y = Y + r * D;
+  for (int k = lane; k < D; k += 32) y[k] = (x[k] - mean) * rstd * gamma[k] + beta[k];
+}
+
+// One warp per (sample, head).  QKV is the in_proj output [L, b, 3D] (q | k | v along the last
+// dim, heads contiguous inside each), out is [L, b, D].  head_dim <= 128 (4 floats per lane).
+template <int MAXL>
+__global__ void __launch_bounds__(256)
+cam_attn_core_kernel(const float* __restrict__ QKV, int L, int64_t b, int D, int heads,
+                     float* __restrict__ out) {
+  const int64_t w = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (w >= b * heads) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t bi = w / heads;
+  const int h = (int)(w % heads);
+  const int hd = D / heads;
+  const int per = (hd + 31) / 32;  // dims per lane (<= 4)
+  const float scaling = rsqrtf((float)hd);
+  float q[MAXL][4], k[MAXL][4], v[MAXL][4];
+#pragma unroll
+  for (int l = 0; l < MAXL; ++l) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      q[l][e] = k[l][e] = v[l][e] = 0.f;
+      const int d = lane + 32 * e;
+      if (l < L && e < per && d < hd) {
+        const float* base = QKV + ((int64_t)l * b + bi) * 3 * D + h * hd + d;
+        q[l][e] = base[0] * scaling;  // q = q * head_dim^-0.5 (timesformer_clip_alt.py:43)
+        k[l][e] = base[D];
+        v[l][e] = base[2 * D];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXL; ++i) {
+    if (i >= L) break;
+    float s[MAXL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j) {
+      float part = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) part = fmaf(q[i][e], k[j][e], part);
+      s[j] = j < L ? warp_sum(part) : -INFINITY;
+      mx = fmaxf(mx, s[j]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXL; ++j) {
+      s[j] = j < L ? __expf(s[j] - mx) : 0.f;
+      den += s[j];
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = lane + 32 * e;
+      if (e < per && d < hd) {
+        float o = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXL; ++j) o = fmaf(s[j] * inv, v[j][e], o);
+        out[((int64_t)i * b + bi) * D + h * hd + d] = o;
+      }
+    }
+  }
+}
+
+__global__ void bias_act_kernel(const float* __restrict__ X, const float* __restrict__ bias,
+                                const float* __restrict__ residual, int64_t total, int D, int act,
+                                float* __restrict__ Y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float z = X[i] + (bias ? bias[i % D] : 0.f);
+    if (act == 1) z = z / (1.f + __expf(-1.702f * z));
+    Y[i] = z + (residual ? residual[i] : 0.f);
+  }
+}
+
+// One warp per sample.  T is [L, b, D].
+__global__ void __launch_bounds__(256)
+cam_readout_kernel(const float* __restrict__ T, const float* __restrict__ main,
+                   const float* __restrict__ res_in, const uint8_t* __restrict__ skip_mask, int L,
+                   int64_t b, int D, int mode, float* __restrict__ out) {
+  const int64_t bi = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (bi >= b) return;
+  const int lane = threadIdx.x & 31;
+  float4 acc[MAX_VEC];
+  const int nvec = D / 4;  // D % 4 == 0 checked by the launcher
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mode == VTC_CAM_READOUT_AVG || mode == VTC_CAM_READOUT_UNIFORM) {
+    for (int l = 0; l < L; ++l) {
+      const float4* x = reinterpret_cast<const float4*>(T + ((int64_t)l * b + bi) * D);
+      float4 xv[MAX_VEC];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAX_VEC; ++i) {
+        const int c = lane + 32 * i;
+        xv[i] = c < nvec ? x[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+      }
+      // AVG: mean of normalised tokens (model.py:156-159); UNIFORM: plain mean (:356-362)
+      const float w = mode == VTC_CAM_READOUT_AVG ? 1.f / sqrtf(warp_sum(s)) : 1.f;
+#pragma unroll
+      for (int i = 0; i < MAX_VEC; ++i) {
+        acc[i].x = fmaf(xv[i].x, w, acc[i].x);
+        acc[i].y = fmaf(xv[i].y, w, acc[i].y);
+        acc[i].z = fmaf(xv[i].z, w, acc[i].z);
+        acc[i].w = fmaf(xv[i].w, w, acc[i].w);
+      }
+    }
+    const float invL = 1.f / (float)L;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+      acc[i].x *= invL, acc[i].y *= invL, acc[i].z *= invL, acc[i].w *= invL;
+      s += acc[i].x * acc[i].x + acc[i].y * acc[i].y + acc[i].z * acc[i].z + acc[i].w * acc[i].w;
+    }
+    const float nrm = sqrtf(warp_sum(s));
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i)
+      acc[i].x /= nrm, acc[i].y /= nrm, acc[i].z /= nrm, acc[i].w /= nrm;
+    if (mode == VTC_CAM_READOUT_UNIFORM) {
+      float4* o = reinterpret_cast<float4*>(out + bi * D);
+#pragma unroll
+      for (int i = 0; i < MAX_VEC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec) o[c] = acc[i];
+      }
+      return;
+    }
+  } else {
+    const float4* x = reinterpret_cast<const float4*>(res_in + bi * D);
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) acc[i] = x[c];
+    }
+  }
+  if (skip_mask && skip_mask[bi]) {  // random adapter skip (model.py:199-201)
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // adapted = normalize(normalize(main) + res)   (model.py:203)
+  const float4* m = reinterpret_cast<const float4*>(main + bi * D);
+  float4 mv[MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int c = lane + 32 * i;
+    mv[i] = c < nvec ? m[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += mv[i].x * mv[i].x + mv[i].y * mv[i].y + mv[i].z * mv[i].z + mv[i].w * mv[i].w;
+  }
+  const float mn = sqrtf(warp_sum(s));
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    acc[i].x += mv[i].x / mn, acc[i].y += mv[i].y / mn;
+    acc[i].z += mv[i].z / mn, acc[i].w += mv[i].w / mn;
+    s2 += acc[i].x * acc[i].x + acc[i].y * acc[i].y + acc[i].z * acc[i].z + acc[i].w * acc[i].w;
+  }
+  const float n2 = sqrtf(warp_sum(s2));
+  float4* o = reinterpret_cast<float4*>(out + bi * D);
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) o[c] = make_float4(acc[i].x / n2, acc[i].y / n2, acc[i].z / n2, acc[i].w / n2);
+  }
+}
+
+// --------------------------------------------------------------------------------- launchers
+int launch_cam_stack_normalize(const float* main, const float* aux, int L, int64_t b, int D,
+                               float* X, cudaStream_t s) {
+  const int64_t rows = (int64_t)L * b;
+  if (rows == 0) return VTC_OK;
+  cam_stack_normalize_kernel<<<(unsigned)ceil_div<int64_t>(rows, WARPS), 256, 0, s>>>(main, aux, L,
+                                                                                      b, D, X);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_layernorm(const float* X, const float* gamma, const float* beta, int64_t rows, int D,
+                     float eps, float* Y, cudaStream_t s) {
+  if (rows == 0) return VTC_OK;
+  layernorm_kernel<<<(unsigned)ceil_div<int64_t>(rows, WARPS), 256, 0, s>>>(X, gamma, beta, rows, D,
+                                                                           eps, Y);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_cam_attn_core(const float* QKV, int L, int64_t b, int D, int heads, float* out,
+                         cudaStream_t s) {
+  if (b == 0) return VTC_OK;
+  if (L < 1 || L > 16 || heads < 1 || D % heads || D / heads > 128) return VTC_ERR_UNSUPPORTED_SHAPE;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(b * heads, WARPS);
+  if (L <= 8)
+    cam_attn_core_kernel<8><<<grid, 256, 0, s>>>(QKV, L, b, D, heads, out);
+  else
+    cam_attn_core_kernel<16><<<grid, 256, 0, s>>>(QKV, L, b, D, heads, out);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_bias_act(const float* X, const float* bias, const float* residual, int64_t rows, int D,
+                    int act, float* Y, cudaStream_t s) {
+  const int64_t total = rows * D;
+  if (total == 0) return VTC_OK;
+  const int64_t blocks = ceil_div<int64_t>(total, 256);
+  bias_act_kernel<<<(unsigned)(blocks < kNumSMs * 16 ? blocks : kNumSMs * 16), 256, 0, s>>>(
+      X, bias, residual, total, D, act, Y);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_cam_readout(const float* T, const float* main, const float* res_in,
+                       const uint8_t* skip_mask, int L, int64_t b, int D, int mode, float* out,
+                       cudaStream_t s) {
+  if (b == 0) return VTC_OK;
+  if (D % 4 || D > 128 * MAX_VEC) return VTC_ERR_UNSUPPORTED_SHAPE;
+  cam_readout_kernel<<<(unsigned)ceil_div<int64_t>(b, WARPS), 256, 0, s>>>(T, main, res_in,
+                                                                         skip_mask, L, b, D, mode,
+                                                                         out);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+}  // namespace vtc

@@ -1,0 +1,301 @@
+// reduce.cu -- reductions that follow the fused similarity GEMM.
+//   * InfoNCE (model/loss.py:18-22): merge the per-split online log-sum-exp partials and form
+//     0.5 * (CE(sim, arange) + CE(sim.t(), arange)) without ever seeing `sim`;
+//   * exact top-k (model/metric.py:144-146 `search(b, k)`): re-score the streamed candidate pools
+//     in fp64-sequential arithmetic, select the k best by (score, index), prove completeness
+//     against the guard band or flag the row for the brute-force kernel;
+//   * k-way merge of per-shard top-k lists (gallery-sharded multi-GPU search).
+#include "reduce.cuh"
+
+namespace vtc {
+
+// ------------------------------------------------------------------------------------- InfoNCE
+__global__ void lse_merge_kernel(const float2* __restrict__ part, int splits, int64_t n,
+                                 float* __restrict__ lse) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  float m = -INFINITY;
+  for (int s = 0; s < splits; ++s) m = fmaxf(m, part[(int64_t)s * n + t].x);
+  float l = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float2 p = part[(int64_t)s * n + t];
+    if (p.x > -INFINITY) l += p.y * exp2f(p.x - m);
+  }
+  lse[t] = 0.6931471805599453f * (m + log2f(l));
+}
+
+__global__ void __launch_bounds__(1024)
+infonce_loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse,
+                    const float* __restrict__ diag_raw, const float* __restrict__ scale_ptr,
+                    int64_t n, float* __restrict__ diag_out, float* __restrict__ loss) {
+  __shared__ double sh[32];
+  const float scale = scale_ptr ? *scale_ptr : 1.f;
+  double acc = 0.0;
+  for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+    const float d = scale * diag_raw[t];
+    if (diag_out) diag_out[t] = d;
+    acc += ((double)row_lse[t] - (double)d) + ((double)col_lse[t] - (double)d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += sh[i];
+    *loss = (float)(0.5 * tot / (double)n);
+  }
+}
+
+int launch_lse_merge(const float2* part, int splits, int64_t n, float* lse, cudaStream_t s) {
+  if (n == 0) return VTC_OK;
+  lse_merge_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, s>>>(part, splits, n, lse);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_infonce_loss(const float* row_lse, const float* col_lse, const float* diag_raw,
+                        const float* scale_ptr, int64_t n, float* diag_out, float* loss,
+                        cudaStream_t s) {
+  infonce_loss_kernel<<<1, 1024, 0, s>>>(row_lse, col_lse, diag_raw, scale_ptr, n, diag_out, loss);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+// --------------------------------------------------------------------------------------- top-k
+constexpr int SEL_WARPS = 4;
+constexpr int SEL_MAX_CAND = 8 * 32;  // splits <= 8, pool = 32
+
+template <typename T>
+__device__ __forceinline__ double exact_score(const T* __restrict__ q, const T* __restrict__ x, int D,
+                                              int metric, double sq) {
+  double acc = 0.0;
+  for (int k = 0; k < D; ++k) acc = fma(to_f64(q[k]), to_f64(x[k]), acc);
+  return metric == VTC_METRIC_L2 ? sq - 2.0 * acc : -acc;
+}
+
+// lexicographic (d, j) less-than; j < 0 marks "no candidate"
+__device__ __forceinline__ bool cand_less(double d1, int j1, double d2, int j2) {
+  if (j1 < 0) return false;
+  if (j2 < 0) return true;
+  return d1 < d2 || (d1 == d2 && j1 < j2);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+topk_select_kernel(TopkSelectArgs a) {
+  __shared__ double cd[SEL_WARPS][SEL_MAX_CAND];
+  __shared__ int cj[SEL_WARPS][SEL_MAX_CAND];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * SEL_WARPS + w;
+  if (t >= a.ex.N) return;
+  const T* Q = (const T*)a.ex.Q;
+  const T* G = (const T*)a.ex.G;
+  const T* q = Q + t * a.ex.ldq;
+  const int ncand = a.splits * a.pool;
+  // exact re-scoring of every pooled candidate
+  for (int c = lane; c < ncand; c += 32) {
+    const int s = c / a.pool, i = c % a.pool;
+    const int64_t slot = (int64_t)s * a.ex.N + t;
+    const int fill = (int)a.pool_meta[slot].x;
+    int j = -1;
+    double d = 0.0;
+    if (i < fill) {
+      j = a.pool_idx[slot * a.pool + i];
+      if (j >= 0 && j < a.ex.M) {
+        d = exact_score(q, G + (int64_t)j * a.ex.ldg, a.ex.D, a.ex.metric,
+                        a.ex.metric == VTC_METRIC_L2 ? a.ex.sq64[j] : 0.0);
+        if (d != d) j = -1;  // NaN scores are never selected
+      } else {
+        j = -1;
+      }
+    }
+    cd[w][c] = d;
+    cj[w][c] = j;
+  }
+  __syncwarp();
+  double qq = 0.0;  // every lane computes it (cheap, keeps the warp convergent)
+  for (int k = 0; k < a.ex.D; ++k) {
+    const double v = to_f64(q[k]);
+    qq = fma(v, v, qq);
+  }
+  double dk = -INFINITY;  // exact score of the last selected candidate
+  int found = 0;
+  for (int r = 0; r < a.k; ++r) {
+    double bd = 0.0;
+    int bj = -1, bc = -1;
+    for (int c = lane; c < ncand; c += 32) {
+      if (cand_less(cd[w][c], cj[w][c], bd, bj)) bd = cd[w][c], bj = cj[w][c], bc = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (cand_less(od, oj, bd, bj)) bd = od, bj = oj, bc = oc;
+    }
+    if (bj >= 0) {
+      if (lane == 0) {
+        a.out_val[t * a.k + r] =
+            (float)(a.ex.metric == VTC_METRIC_L2 ? bd + qq : bd);
+        a.out_idx[t * a.k + r] = (int64_t)bj + a.ex.col_offset;
+      }
+      if ((bc & 31) == lane) cj[w][bc] = -1;  // owner retires it
+      dk = bd;
+      ++found;
+    } else if (lane == 0) {
+      a.out_val[t * a.k + r] = INFINITY;
+      a.out_idx[t * a.k + r] = -1;
+    }
+    __syncwarp();
+  }
+  // completeness: every column outside a FULL pool has approx score >= tau, hence exact score
+  // >= tau - delta; the selection is provably right when the k-th exact score is below that.
+  if (lane == 0) {
+    const double qn = sqrt(qq);
+    const double gmax_sq = (double)__uint_as_float(*a.max_sq_bits);
+    const double gn = sqrt(gmax_sq);
+    const double delta = a.ex.metric == VTC_METRIC_L2
+                             ? 2.0 * a.guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn)
+                             : (double)a.guard_rel * qn * gn + 1.2e-7 * qn * gn;
+    bool ok = qq == qq;
+    for (int s = 0; s < a.splits; ++s) {
+      const float2 meta = a.pool_meta[(int64_t)s * a.ex.N + t];
+      if ((int)meta.x >= a.pool) {
+        if (found < a.k || !(dk < (double)meta.y - delta)) ok = false;
+      }
+    }
+    a.row_flag[t] = ok ? 0u : 1u;
+  }
+}
+
+constexpr int BRUTE_THREADS = 128;
+constexpr int BRUTE_KMAX = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(BRUTE_THREADS)
+topk_brute_rows_kernel(TopkSelectArgs a) {
+  const int64_t t = blockIdx.x;
+  if (a.row_flag[t] == 0) return;
+  __shared__ double ld[BRUTE_THREADS][BRUTE_KMAX];
+  __shared__ int lj[BRUTE_THREADS][BRUTE_KMAX];
+  __shared__ double rd[BRUTE_THREADS / 32];
+  __shared__ int rj[BRUTE_THREADS / 32], rt[BRUTE_THREADS / 32];
+  __shared__ int winner;
+  const int tid = threadIdx.x;
+  const T* q = (const T*)a.ex.Q + t * a.ex.ldq;
+  const T* G = (const T*)a.ex.G;
+  const int k = a.k;
+  int fill = 0;
+  for (int64_t j = tid; j < a.ex.M; j += BRUTE_THREADS) {
+    const double d = exact_score(q, G + j * a.ex.ldg, a.ex.D, a.ex.metric,
+                                 a.ex.metric == VTC_METRIC_L2 ? a.ex.sq64[j] : 0.0);
+    if (d != d) continue;
+    if (fill == k && !(d < ld[tid][k - 1])) continue;  // j grows: ties keep the earlier index
+    int pos = fill < k ? fill : k - 1;
+    while (pos > 0 && d < ld[tid][pos - 1]) {
+      ld[tid][pos] = ld[tid][pos - 1];
+      lj[tid][pos] = lj[tid][pos - 1];
+      --pos;
+    }
+    ld[tid][pos] = d;
+    lj[tid][pos] = (int)j;
+    if (fill < k) ++fill;
+  }
+  double qq = 0.0;
+  for (int kk = 0; kk < a.ex.D; ++kk) {
+    const double v = to_f64(q[kk]);
+    qq = fma(v, v, qq);
+  }
+  int head = 0;
+  for (int r = 0; r < k; ++r) {
+    double bd = head < fill ? ld[tid][head] : 0.0;
+    int bj = head < fill ? lj[tid][head] : -1;
+    int bt = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+      if (cand_less(od, oj, bd, bj)) bd = od, bj = oj, bt = ot;
+    }
+    if ((tid & 31) == 0) rd[tid >> 5] = bd, rj[tid >> 5] = bj, rt[tid >> 5] = bt;
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < BRUTE_THREADS / 32; ++i)
+        if (cand_less(rd[i], rj[i], rd[0], rj[0])) rd[0] = rd[i], rj[0] = rj[i], rt[0] = rt[i];
+      winner = rj[0] >= 0 ? rt[0] : -1;
+      a.out_val[t * k + r] =
+          rj[0] >= 0 ? (float)(a.ex.metric == VTC_METRIC_L2 ? rd[0] + qq : rd[0]) : INFINITY;
+      a.out_idx[t * k + r] = rj[0] >= 0 ? (int64_t)rj[0] + a.ex.col_offset : -1;
+    }
+    __syncthreads();
+    if (winner == tid) ++head;
+    __syncthreads();
+  }
+}
+
+__global__ void topk_merge_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx,
+                                  int parts, int64_t N, int k, float* __restrict__ out_val,
+                                  int64_t* __restrict__ out_idx) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  unsigned char head[64];
+  for (int p = 0; p < parts; ++p) head[p] = 0;
+  for (int r = 0; r < k; ++r) {
+    int best = -1;
+    float bv = 0.f;
+    int64_t bi = -1;
+    for (int p = 0; p < parts; ++p) {
+      if (head[p] >= k) continue;
+      const int64_t off = ((int64_t)p * N + t) * k + head[p];
+      const int64_t ci = idx[off];
+      if (ci < 0) continue;
+      const float cv = vals[off];
+      if (best < 0 || cv < bv || (cv == bv && ci < bi)) best = p, bv = cv, bi = ci;
+    }
+    if (best >= 0) {
+      out_val[t * k + r] = bv;
+      out_idx[t * k + r] = bi;
+      ++head[best];
+    } else {
+      out_val[t * k + r] = INFINITY;
+      out_idx[t * k + r] = -1;
+    }
+  }
+}
+
+int launch_topk_select(const TopkSelectArgs& a, cudaStream_t s) {
+  if (a.ex.N == 0) return VTC_OK;
+  if (a.splits * a.pool > SEL_MAX_CAND || a.k > BRUTE_KMAX) return VTC_ERR_UNSUPPORTED_SHAPE;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(a.ex.N, SEL_WARPS);
+  if (a.ex.bf16)
+    topk_select_kernel<__nv_bfloat16><<<grid, SEL_WARPS * 32, 0, s>>>(a);
+  else
+    topk_select_kernel<float><<<grid, SEL_WARPS * 32, 0, s>>>(a);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_topk_brute_rows(const TopkSelectArgs& a, cudaStream_t s) {
+  if (a.ex.N == 0) return VTC_OK;
+  if (a.k > BRUTE_KMAX) return VTC_ERR_UNSUPPORTED_SHAPE;
+  if (a.ex.bf16)
+    topk_brute_rows_kernel<__nv_bfloat16><<<(unsigned)a.ex.N, BRUTE_THREADS, 0, s>>>(a);
+  else
+    topk_brute_rows_kernel<float><<<(unsigned)a.ex.N, BRUTE_THREADS, 0, s>>>(a);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_topk_merge(const float* vals, const int64_t* idx, int parts, int64_t N, int k,
+                      float* out_val, int64_t* out_idx, cudaStream_t s) {
+  if (N == 0) return VTC_OK;
+  if (parts < 1 || parts > 64 || k < 1 || k > 255) return VTC_ERR_INVALID_ARG;
+  topk_merge_kernel<<<(unsigned)ceil_div<int64_t>(N, 128), 128, 0, s>>>(vals, idx, parts, N, k,
+                                                                        out_val, out_idx);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+}  // namespace vtc

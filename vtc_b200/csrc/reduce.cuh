@@ -1,0 +1,33 @@
+// reduce.cuh -- launchers of the post-GEMM reductions (reduce.cu): InfoNCE loss from the fused
+// log-sum-exp partials, exact top-k selection from the streamed candidate pools, top-k merge.
+#pragma once
+#include "common.cuh"
+#include "exact.cuh"
+
+namespace vtc {
+
+// row_lse[t] = ln2 * (max + log2(sum)) merged over `splits` partials [splits, n]
+int launch_lse_merge(const float2* part, int splits, int64_t n, float* lse, cudaStream_t s);
+// loss = 0.5 * (mean(row_lse - diag) + mean(col_lse - diag)); diag = scale * diag_raw (written back)
+int launch_infonce_loss(const float* row_lse, const float* col_lse, const float* diag_raw,
+                        const float* scale_ptr, int64_t n, float* diag_out, float* loss,
+                        cudaStream_t s);
+
+struct TopkSelectArgs {
+  ExactArgs ex;              // canonical operands (Q, G, sq64, metric, col_offset ...)
+  const float* pool_val;     // [splits, N, pool]
+  const int* pool_idx;       // [splits, N, pool]
+  const float2* pool_meta;   // [splits, N] (fill, tau)
+  int splits, pool, k;
+  float guard_rel;
+  const unsigned int* max_sq_bits;
+  float* out_val;            // [N, k]
+  int64_t* out_idx;          // [N, k]
+  unsigned int* row_flag;    // [N] 1 = pool could not prove completeness -> brute-force row
+};
+int launch_topk_select(const TopkSelectArgs& a, cudaStream_t s);
+int launch_topk_brute_rows(const TopkSelectArgs& a, cudaStream_t s);
+int launch_topk_merge(const float* vals, const int64_t* idx, int parts, int64_t N, int k,
+                      float* out_val, int64_t* out_idx, cudaStream_t s);
+
+}  // namespace vtc

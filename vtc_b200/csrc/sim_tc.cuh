@@ -1,0 +1,67 @@
+// sim_tc.cuh -- interface of the tcgen05 similarity GEMM with fused epilogues (sim_tc.cu).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vtc {
+namespace tc {
+
+constexpr int BM = 128;  // query rows per CTA tile  (UMMA M, TMEM lanes)
+constexpr int BN = 256;  // gallery rows per tile    (UMMA N, TMEM columns per accumulator stage)
+constexpr int BK = 64;   // bf16 per k-block = one 128-byte swizzle atom
+
+enum Epilogue { EPI_RANK = 0, EPI_LSE = 1, EPI_STORE = 2, EPI_TOPK = 3 };
+
+constexpr int TOPK_POOL = 32;  // candidates kept per (row, gallery split)
+
+struct Params {
+  int64_t N, M;          // valid rows of A (queries) and B (gallery)
+  int num_kb;            // K' / 64
+  int q_tiles, g_tiles;  // ceil(N/128), ceil(M/256)
+  int g_splits;          // gallery is cut into g_splits contiguous tile ranges
+  int tiles_per_split;
+  // score = scale * acc + col_bias[j]   (col_bias NULL = 0; out-of-range columns use oob_bias)
+  const float* col_bias;
+  const float* scale_ptr;  // optional device scalar multiplied into `scale`
+  float scale;
+  float oob_bias;
+  // EPI_RANK
+  const float2* thr;  // [N] (lo, hi) guard band around d(t, gt)
+  int* rank;          // [N] += #{j : score < lo}
+  int2* amb_list;     // (t, j) pairs with lo <= score <= hi
+  unsigned int* amb_count;
+  unsigned int amb_cap;
+  // EPI_LSE  (score is the logit in log2 units: scale already includes log2(e))
+  float2* lse_part;     // [g_splits, N] running (max, sum) in log2 domain
+  float* diag;          // [N] raw accumulator of column t + diag_offset (nullable)
+  int64_t diag_offset;
+  // EPI_STORE
+  float* out;  // [N, ldo]
+  int64_t ldo;
+  const float* residual;  // optional [N, ldo]
+  int act;                // 0 none, 1 QuickGELU (applied after bias, before residual)
+  // EPI_TOPK
+  float* pool_val;   // [g_splits, N, TOPK_POOL]
+  int* pool_idx;     // [g_splits, N, TOPK_POOL]
+  float2* pool_meta; // [g_splits, N] (fill, tau)
+};
+
+// Row-major bf16 [rows, cols] with leading dimension ld (elements) -> 2-D TMA descriptor with a
+// {64, box_rows} box and 128-byte swizzle.
+int make_operand_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                      CUtensorMap* out);
+
+// a_resident: keep the whole 128 x K' query tile in shared memory (needs num_kb <= 8).
+int launch_sim_tc(int epilogue, bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                  const Params& p, int grid, cudaStream_t s);
+
+// opt-in CUDA-event timing of the tensor-core launches (bench.py roofline)
+void kernel_timer_enable(bool on);
+int kernel_timer_read(double* total_ms, int* count);
+
+// fills q_tiles / g_tiles / g_splits / tiles_per_split and returns the grid size
+int plan_tiles(Params& p, int max_splits);
+
+}  // namespace tc
+}  // namespace vtc

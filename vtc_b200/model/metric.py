@@ -1,0 +1,201 @@
+"""Drop-in for the reference's model/metric.py::RecallAtK (model/metric.py:103-187).
+
+Same constructor, attributes and methods (`set_writer`, `reset`, `update`, `avg`, `result`,
+`compute`), same result keys.  What changes underneath:
+
+* `compute(features_a, features_b)` no longer builds a faiss index and a Python loop
+  (model/metric.py:140-160); it calls the fused similarity + rank-of-ground-truth kernel
+  (vtc_sim_rank) and counts `rank0 < k` on the device (vtc_rank_finalize).  R@k is identical to
+  "gt index is inside the top-k list" because rank0 is the position of the ground truth in a
+  stable ascending sort of the same exact-L2 scores.
+* `update` keeps the per-batch features on the GPU instead of `.cpu()` per batch (:129-130).
+* `compute_full` additionally returns per-query ranks and the median rank (MedR), which the
+  reference does not define.
+
+Inputs may be numpy arrays / CPU tensors (as the reference passes them): they are staged through
+pinned host memory to the current CUDA device.  There is no CPU compute path.
+"""
+from __future__ import annotations
+
+import collections.abc
+import time
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import ops
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+__all__ = ["BaseMetric", "RecallAtK", "MetricTracker"]
+
+
+class BaseMetric:
+    """model/metric.py:45-65."""
+
+    def __init__(self, name, is_train=True, is_val=True):
+        self.name = name
+        self.writer = None
+        self.is_train = is_train
+        self.is_val = is_val
+
+    def set_writer(self, writer):
+        self.writer = writer
+
+    def reset(self):
+        raise NotImplementedError
+
+    def update(self, loss, output, meta):
+        raise NotImplementedError
+
+    def avg(self):
+        raise NotImplementedError
+
+    def result(self):
+        raise NotImplementedError
+
+
+class MetricTracker:
+    """model/metric.py:10-42 (thin host glue, kept as is)."""
+
+    def __init__(self, *metrics, writer=None):
+        self.writer = writer
+        self.metrics = metrics
+        for met in self.metrics:
+            met.set_writer(writer)
+        self.reset()
+
+    def reset(self):
+        for met in self.metrics:
+            met.reset()
+
+    def update(self, loss, output, meta):
+        for met in self.metrics:
+            met.update(loss, output, meta)
+
+    def avg(self):
+        return {met.name: met.avg() for met in self.metrics if met.avg() is not None}
+
+    def result(self):
+        res = {}
+        for met in self.metrics:
+            r = met.result()
+            if isinstance(r, dict):
+                res.update(r)
+            else:
+                res[met.name] = r
+        return res
+
+
+def _to_device(x: ArrayLike, device: torch.device) -> torch.Tensor:
+    """numpy / CPU tensor -> CUDA fp32 (or bf16) tensor via pinned staging; CUDA tensors pass."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"expected numpy array or tensor, got {type(x)}")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if x.is_cuda:
+        return x
+    if not x.is_pinned():
+        x = x.contiguous().pin_memory()
+    return x.to(device, non_blocking=True)
+
+
+def _default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise ops.VtcError("RecallAtK needs a CUDA device: vtc_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class RecallAtK(BaseMetric):
+    def __init__(self, name_a, name_b, k_vals=5, precision: str = "exact", metric: str = "l2"):
+        super().__init__("recall@k")
+        if not isinstance(k_vals, collections.abc.Iterable):
+            k_vals = [k_vals]
+        self.k_vals = list(k_vals)
+        self.name_a = name_a
+        self.name_b = name_b
+        self.is_train = False
+        self.precision = precision  # "exact" (fp32 inputs ranked exactly) | "bf16" | "brute"
+        self.metric = metric        # "l2" = what faiss.GpuIndexFlatL2 ranks by
+        self.insert_index = 0
+        self.features_a_list: List[torch.Tensor] = []
+        self.features_b_list: List[torch.Tensor] = []
+
+    def reset(self):
+        self.insert_index = 0
+        self.features_a_list = []
+        self.features_b_list = []
+
+    def update(self, loss, output, meta):
+        fa = output[0]
+        fb = output[1]
+        batch_size = fa.shape[0]
+        end = self.insert_index + batch_size
+        # the reference moves every batch to the CPU here (model/metric.py:129-130); the features
+        # stay on the device and are consumed there by result()
+        self.features_a_list.append(fa.detach())
+        self.features_b_list.append(fb.detach())
+        self.insert_index = end
+
+    # ------------------------------------------------------------------ the hot path
+    def compute_full(self, features_a: ArrayLike, features_b: ArrayLike,
+                     device: Optional[torch.device] = None) -> Dict[str, object]:
+        """gallery = features_a, queries = features_b, gt(t) = t (model/metric.py:137-161).
+
+        Returns device tensors: rank0 int32 [N], hits int64 [nk], medr fp64 [1], plus sizes."""
+        if getattr(features_b, "ndim", 2) != 2 or getattr(features_a, "ndim", 2) != 2:
+            raise ValueError(
+                "RecallAtK.compute needs 2-D [N, D] features: one text per video "
+                "(multi-caption 3-D inputs are not supported, SURVEY.md App. B #8)")
+        if device is None:
+            for x in (features_a, features_b):
+                if isinstance(x, torch.Tensor) and x.is_cuda:
+                    device = x.device
+            device = device or _default_device()
+        a = _to_device(features_a, device)
+        b = _to_device(features_b, device)
+        if a.dtype != b.dtype:
+            a, b = a.float(), b.float()
+        num_samples = a.shape[0]
+        if b.shape[0] != num_samples:
+            # gt(t) = t and the denominator is the gallery size (model/metric.py:138,154-158)
+            raise AssertionError(
+                f"RecallAtK assumes len(a) == len(b) (got {num_samples} vs {b.shape[0]})")
+        rank0, gt_score = ops.sim_rank(b, a, metric=self.metric, precision=self.precision)
+        hits, medr = ops.rank_finalize(rank0, gt_score, num_samples, self.k_vals)
+        return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": num_samples}
+
+    def compute(self, features_a: ArrayLike, features_b: ArrayLike) -> List[Tuple[int, float]]:
+        full = self.compute_full(features_a, features_b)
+        hits = full["hits"].cpu().numpy()  # the one device->host read of the result
+        num_samples = full["num_samples"]
+        return [(k, float(h) / num_samples) for k, h in zip(self.k_vals, hits)]
+
+    def avg(self):
+        return None
+
+    def result(self):
+        tic = time.time()
+        print("RecallAtK: result()...", end=" ", flush=True)
+
+        features_a = torch.cat(self.features_a_list)
+        features_b = torch.cat(self.features_b_list)
+
+        assert self.insert_index == len(features_a)
+
+        res = {}
+        for k, recall in self.compute(features_a, features_b):
+            res[f"{self.name_b}_from_{self.name_a}-recall_at_{k}"] = recall
+        for k, recall in self.compute(features_b, features_a):
+            res[f"{self.name_a}_from_{self.name_b}-recall_at_{k}"] = recall
+
+        if self.writer:
+            for name, recall in res.items():
+                self.writer.add_scalar(name, recall)
+
+        print("RecallAtK: result() took %.3fs" % (time.time() - tic))
+
+        return res

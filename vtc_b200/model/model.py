@@ -1,0 +1,299 @@
+"""Drop-in for the hot-path part of the reference's model/model.py: `normalize` (:26-27), the
+Context Adapter Module `PretrainedCLIPBase._adapt_feature` (:141-205) with its transformer
+(`clip.model.Transformer`, constructed at :396-398), `_encode_with_comments` (:216-266), the
+averaging fusion (:356-362) and the `(feats_vis, feats_text, sim)` forward contract (:326-371,
+:458-480).
+
+The CLIP / TimeSformer backbones are out of scope: the model classes here
+take precomputed features (`len(shape) == 2` branch of the reference forward, :328-330,:460-462)
+or any `backbone` object exposing `encode_image` / `encode_text`.  Parameter names match the
+reference (`final_transformer.resblocks.{i}.attn.in_proj_weight`, ..., `final_linear.weight`,
+`mask_embedding`) so its checkpoints load and `train.py:105`'s substring grouping keeps working.
+
+The CAM forward runs on the CUDA kernels of csrc/cam.cu + csrc/sim_tc.cu (dense projections on
+the tensor cores).  It is inference-only in this round: calling it with autograd enabled on
+parameters that require grad raises (the CAM backward is listed as "next" in DESIGN.md).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import List, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+from .. import _ffi, ops
+from .lazy import LazySim
+
+__all__ = [
+    "normalize",
+    "CAMTransformer",
+    "PretrainedCLIPBase",
+    "PretrainedCLIP",
+    "PretrainedCLIP_finaltf",
+    "RESIDUAL_ACTIVATIONS",
+]
+
+
+def normalize(x: torch.Tensor) -> torch.Tensor:
+    """x / x.norm(dim=-1, keepdim=True) -- model/model.py:26-27 (no eps; zero row -> NaN)."""
+    return ops.normalize(x)
+
+
+# residual activations (model/model.py:65-77).  Every shipped config uses None / "none"; the
+# others are listed as a "next" row and rejected loudly.
+RESIDUAL_ACTIVATIONS = {None: "identity", "none": "identity"}
+
+
+class _Attn(nn.Module):
+    """Parameter container with nn.MultiheadAttention's names (in_proj_weight, in_proj_bias,
+    out_proj.weight, out_proj.bias) and default initialisation."""
+
+    def __init__(self, width: int, heads: int):
+        super().__init__()
+        self.embed_dim = width
+        self.num_heads = heads
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * width, width))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * width))
+        self.out_proj = nn.Linear(width, width)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.out_proj.bias, 0.0)
+
+
+class _ResBlock(nn.Module):
+    def __init__(self, width: int, heads: int):
+        super().__init__()
+        self.attn = _Attn(width, heads)
+        self.ln_1 = nn.LayerNorm(width)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(width, width * 4)),
+            ("gelu", nn.Identity()),  # QuickGELU is fused into the c_fc GEMM epilogue
+            ("c_proj", nn.Linear(width * 4, width)),
+        ]))
+        self.ln_2 = nn.LayerNorm(width)
+
+
+class CAMTransformer(nn.Module):
+    """clip.model.Transformer(width, layers, heads) for the CAM (model/model.py:396-398): per block
+    x += MHA(LN1(x)); x += c_proj(QuickGELU(c_fc(LN2(x)))) on sequence-first [L, b, D], no mask
+    (block layout: model/timesformer_clip_alt.py:112-124)."""
+
+    def __init__(self, width: int, layers: int, heads: int, precision: str = "exact"):
+        super().__init__()
+        self.width = width
+        self.layers = layers
+        self.heads = heads
+        self.precision = precision
+        self.resblocks = nn.Sequential(*[_ResBlock(width, heads) for _ in range(layers)])
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "CAMTransformer is forward-only in this round (wrap the call in torch.no_grad(); "
+                "the CAM backward kernels are listed as next in DESIGN.md)")
+        L, b, D = x.shape
+        prec = self.precision
+        x2 = x.float().contiguous().reshape(L * b, D)
+        for blk in self.resblocks:
+            h = ops.layernorm(x2, blk.ln_1.weight, blk.ln_1.bias, blk.ln_1.eps)
+            qkv = ops.linear(h, blk.attn.in_proj_weight, blk.attn.in_proj_bias, precision=prec)
+            a = ops.cam_attn_core(qkv.reshape(L, b, 3 * D), self.heads).reshape(L * b, D)
+            x2 = ops.linear(a, blk.attn.out_proj.weight, blk.attn.out_proj.bias, residual=x2,
+                            precision=prec)
+            h = ops.layernorm(x2, blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
+            f = ops.linear(h, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, act=1, precision=prec)
+            x2 = ops.linear(f, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, residual=x2,
+                            precision=prec)
+        return x2.reshape(L, b, D)
+
+
+class PretrainedCLIPBase(nn.Module):
+    """model/model.py:132-305 (hot-path methods only)."""
+
+    # attributes the methods read; subclasses set them in __init__
+    feature_dim: int
+    residual_activation = None
+    init_from_avg = True
+    random_skip_adapter = True
+    random_comment_masking = False
+    branch_to_adapt = "text"
+    branch_to_adapt_val = "text"
+    precision = "exact"
+
+    def _adapt_feature(self, feature_main: torch.Tensor, features_aux) -> torch.Tensor:
+        """CAM: model/model.py:141-205.  feature_main [b, D]; features_aux [nc, b, D] tensor or a
+        list of nc [b, D] tensors.  Returns the adapted, unit-norm feature [b, D]."""
+        if self.residual_activation not in RESIDUAL_ACTIVATIONS:
+            raise NotImplementedError(
+                f"residual_activation={self.residual_activation!r}: only None/'none' is built "
+                "(every shipped config uses it; the others are a 'next' row in DESIGN.md)")
+        assert len(feature_main.shape) == 2
+        b = feature_main.shape[0]
+        if not isinstance(features_aux, torch.Tensor):
+            features_aux = torch.stack(list(features_aux), dim=0)
+        assert features_aux.shape[1] == b
+        concat_feats = ops.cam_stack_normalize(feature_main, features_aux)       # :150-151
+        comm_tfm = self.final_transformer(concat_feats)                          # :155
+
+        # the reference draws one number from the global CPU RNG here for a 5 % debug print
+        # (:163); keep the draw so RNG streams stay aligned with it, drop the print.
+        torch.rand([])
+
+        skip_mask = None
+        if self.training and self.random_skip_adapter:
+            skip_mask = torch.rand(b) > 0.5                                      # :199-201
+        if self.init_from_avg:
+            return ops.cam_readout(comm_tfm, feature_main, _ffi.CAM_READOUT_AVG,
+                                   skip_mask=skip_mask)                          # :156-159,:203
+        comm_res = ops.linear(comm_tfm[0], self.final_linear.weight,
+                              precision=self.precision)                          # :161
+        return ops.cam_readout(None, feature_main, _ffi.CAM_READOUT_RESIDUAL_ONLY,
+                               res_in=comm_res, skip_mask=skip_mask)             # :203
+
+    def _load_comment_features(self, comments) -> torch.Tensor:
+        """model/model.py:207-214.  `comments` is either precomputed comment embeddings
+        [b, nc, D] (optionally a tuple (embeddings, empty_mask [b, nc])) or token ids
+        [b, nc, ntoks] when a backbone with `encode_text` is attached."""
+        empty_mask = None
+        if isinstance(comments, (tuple, list)):
+            comments, empty_mask = comments
+        if comments.dtype in (torch.int32, torch.int64):
+            if getattr(self, "model", None) is None:
+                raise ops.VtcError("token-id comments need a backbone with encode_text")
+            empty_mask = comments[..., 1] == 49407                               # :208
+            b, ncomms, ntoks = comments.shape
+            feats_comm = self.model.encode_text(comments.reshape(b * ncomms, ntoks))
+            feats_comm = feats_comm.reshape(b, ncomms, self.feature_dim).float()
+        else:
+            feats_comm = comments.float().clone()
+        if empty_mask is not None:
+            feats_comm[empty_mask] = self.mask_embedding.detach().to(feats_comm.dtype)  # :212
+        return feats_comm.permute(1, 0, 2)                                       # :213
+
+    def _encode_with_comments(self, feats_vis, feats_title, comments):
+        """model/model.py:216-266 (audio branch out of scope)."""
+        feats_comm = self._load_comment_features(comments)
+        bs = feats_title.shape[0]
+        if self.training:
+            if self.random_comment_masking:
+                comm_masks = [torch.randint(low=0, high=2, size=(bs, 1), device=comm.device)
+                              for comm in feats_comm]                             # :237-240
+            else:
+                comm_masks = torch.ones(len(feats_comm)).to(feats_comm.device)
+            feats_comm = [comm * mask + self.mask_embedding.detach() * (1 - mask)
+                          for comm, mask in zip(feats_comm, comm_masks)]          # :243-246
+            branch_to_adapt = self.branch_to_adapt
+        else:
+            branch_to_adapt = self.branch_to_adapt_val
+
+        if branch_to_adapt == "text":
+            feats_vis_out = feats_vis
+            feats_text_out = self._adapt_feature(feats_title, feats_comm)
+        elif branch_to_adapt == "image":
+            feats_vis_out = self._adapt_feature(feats_vis, feats_comm)
+            feats_text_out = feats_title
+        elif branch_to_adapt == "skip":
+            feats_vis_out = feats_vis
+            feats_text_out = feats_title
+        else:
+            raise Exception("Unknown branch_to_adapt")
+
+        return normalize(feats_vis_out.float()), normalize(feats_text_out.float())  # :263-264
+
+    # ---- shared forward helpers -------------------------------------------------------------
+    def _features(self, vis, title):
+        shp = vis.shape
+        if len(shp) == 2 and shp[1] == self.feature_dim:
+            feats_vis = vis                                                      # precomputed, :328-330
+        else:
+            if getattr(self, "model", None) is None:
+                raise ops.VtcError("raw frames need a backbone with encode_image")
+            if len(shp) == 4:
+                feats_vis = self.model.encode_image(vis).float()
+            else:                                                                # :335-340
+                feats_vis = self.model.encode_image(
+                    vis.reshape(shp[0] * shp[1], shp[2], shp[3], shp[4])).float()
+                feats_vis = feats_vis.reshape(shp[0], shp[1], -1).mean(1)
+        if title.dim() == 2 and title.dtype.is_floating_point and title.shape[1] == self.feature_dim:
+            feats_title = title
+        else:
+            if getattr(self, "model", None) is None:
+                raise ops.VtcError("token-id titles need a backbone with encode_text")
+            feats_title = self.model.encode_text(title)
+        return feats_vis, feats_title
+
+    def _logit_scale_exp(self, device):
+        if getattr(self, "model", None) is not None and hasattr(self.model, "logit_scale"):
+            return self.model.logit_scale.exp().to(device)
+        return self.logit_scale.exp().to(device)
+
+
+class PretrainedCLIP(PretrainedCLIPBase):
+    """model/model.py:308-371 with the backbone made pluggable."""
+
+    def __init__(self, feature_dim: int = 512, backbone=None, residual_activation=None,
+                 comment_fusion=None, logit_scale_init: float = math.log(1 / 0.07),
+                 precision: str = "exact", lazy_sim: bool = True):
+        super().__init__()
+        self.model = backbone
+        self.feature_dim = feature_dim
+        self.residual_activation = residual_activation
+        self.comment_fusion = comment_fusion
+        self.precision = precision
+        self.lazy_sim = lazy_sim
+        if backbone is None or not hasattr(backbone, "logit_scale"):
+            self.logit_scale = nn.Parameter(torch.ones([]) * logit_scale_init)
+
+    def forward(self, vis, title, comments=None):
+        feats_vis, feats_title = self._features(vis, title)
+        if comments is None or self.comment_fusion is None or self.comment_fusion == "None":
+            feats_text = normalize(feats_title.float())
+        elif self.comment_fusion == "averaging":
+            feats_comm = self._load_comment_features(comments)                   # [nc, b, D]
+            stacked = torch.cat([feats_title.float().unsqueeze(0), feats_comm], 0)
+            feats_text = ops.cam_readout(stacked, None, _ffi.CAM_READOUT_UNIFORM)  # :356-362,:366
+        else:
+            raise ValueError("Comment fusion method not specified.")
+        feats_vis = normalize(feats_vis.float())                                 # :367
+        sim = LazySim(feats_vis, feats_text, self._logit_scale_exp(feats_vis.device), self.precision)
+        return feats_vis, feats_text, (sim if self.lazy_sim else sim.materialize())
+
+
+class PretrainedCLIP_finaltf(PretrainedCLIPBase):
+    """model/model.py:374-480 with the backbone made pluggable (audio branch out of scope)."""
+
+    def __init__(self, feature_dim: int = 512, backbone=None, branch_to_adapt="text",
+                 branch_to_adapt_val="text", residual_activation=None, n_layers=2, n_heads=8,
+                 init_from_avg=True, random_comment_masking=False, random_skip_adapter=True,
+                 logit_scale_init: float = math.log(1 / 0.07), precision: str = "exact",
+                 lazy_sim: bool = True):
+        super().__init__()
+        self.model = backbone
+        self.feature_dim = feature_dim
+        self.final_transformer = CAMTransformer(feature_dim, int(n_layers), int(n_heads), precision)
+        self.final_linear = nn.Linear(feature_dim, feature_dim, bias=False)
+        self.mask_embedding = nn.Parameter(torch.randn(1, feature_dim))
+        self.branch_to_adapt = branch_to_adapt
+        self.branch_to_adapt_val = branch_to_adapt_val
+        self.residual_activation = residual_activation
+        self.init_from_avg = init_from_avg
+        self.random_comment_masking = random_comment_masking
+        self.random_skip_adapter = random_skip_adapter
+        self.precision = precision
+        self.lazy_sim = lazy_sim
+        if backbone is None or not hasattr(backbone, "logit_scale"):
+            self.logit_scale = nn.Parameter(torch.ones([]) * logit_scale_init)
+        if self.init_from_avg:                                                   # :440-450
+            for blk in self.final_transformer.resblocks:
+                blk.mlp.c_proj.weight.data.zero_()
+                blk.mlp.c_proj.bias.data.zero_()
+                blk.attn.out_proj.weight.data.zero_()
+        nn.init.constant_(self.final_linear.weight, 0.0)                         # :452
+
+    def forward(self, vis, title, comments):
+        feats_vis, feats_title = self._features(vis, title)
+        feats_vis, feats_text = self._encode_with_comments(feats_vis.float(), feats_title.float(),
+                                                           comments)
+        sim = LazySim(feats_vis, feats_text, self._logit_scale_exp(feats_vis.device), self.precision)
+        return feats_vis, feats_text, (sim if self.lazy_sim else sim.materialize())

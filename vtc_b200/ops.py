@@ -1,0 +1,402 @@
+"""Tensor-level wrappers over the C ABI (include/vtc_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream.  Every function takes CUDA
+tensors, hands raw pointers + the current stream to libvtc_b200.so and returns CUDA tensors;
+nothing synchronises.  There is no CPU path: a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import torch
+
+from . import _ffi
+from ._ffi import VtcError
+
+_PREC = {"exact": _ffi.PREC_EXACT, "fp32": _ffi.PREC_EXACT, "bf16": _ffi.PREC_BF16,
+         "brute": _ffi.PREC_BRUTE}
+_METRIC = {"dot": _ffi.METRIC_DOT, "l2": _ffi.METRIC_L2}
+
+
+def _prec(p) -> int:
+    if isinstance(p, int):
+        return p
+    try:
+        return _PREC[p]
+    except KeyError:
+        raise ValueError(f"precision must be one of {sorted(_PREC)}, got {p!r}")
+
+
+def _metric(m) -> int:
+    if isinstance(m, int):
+        return m
+    try:
+        return _METRIC[m]
+    except KeyError:
+        raise ValueError(f"metric must be 'l2' or 'dot', got {m!r}")
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _ffi.F32
+    if t.dtype == torch.bfloat16:
+        return _ffi.BF16
+    raise TypeError(f"embeddings must be float32 or bfloat16, got {t.dtype}")
+
+
+def _req_cuda(*ts: torch.Tensor) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise VtcError("vtc_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise VtcError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _mat(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D [rows, D], got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+# workspace cache: one growing byte buffer per (device, stream); use is stream-ordered
+_ws: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=dev)
+        _ws[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    _ws.clear()
+
+
+def _ws_bytes(op: int, N: int, M: int, D: int, prec: int) -> int:
+    n = _ffi.load().vtc_workspace_bytes(op, N, M, D, prec)
+    if n == 0:
+        raise VtcError("vtc_workspace_bytes rejected the arguments")
+    return int(n)
+
+
+# ------------------------------------------------------------------------------------------ H1
+def normalize(x: torch.Tensor) -> torch.Tensor:
+    """x / x.norm(dim=-1, keepdim=True) (model/model.py:26-27), any leading shape."""
+    dev = _req_cuda(x)
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1]).contiguous()
+    y = torch.empty_like(x2)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_normalize(_ptr(x2), x2.shape[0], x2.shape[1], x2.shape[1],
+                                             _dtype_code(x2), _ptr(y), x2.shape[1], _stream(dev)),
+                   "vtc_normalize")
+    return y.reshape(shp)
+
+
+def row_norms(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(1/||x_r||, ||x_r||^2) per row, fp32."""
+    dev = _req_cuda(x)
+    x = _mat(x, "x")
+    inv = torch.empty(x.shape[0], dtype=torch.float32, device=dev)
+    sq = torch.empty_like(inv)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_row_norms(_ptr(x), x.shape[0], x.shape[1], x.shape[1],
+                                             _dtype_code(x), _ptr(inv), _ptr(sq), _stream(dev)),
+                   "vtc_row_norms")
+    return inv, sq
+
+
+# ------------------------------------------------------------------------------------------ H2
+def _scale_tensor(scale, dev) -> torch.Tensor:
+    if isinstance(scale, torch.Tensor):
+        return scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    return torch.full((1,), float(scale), dtype=torch.float32, device=dev)
+
+
+def sim_matrix(a: torch.Tensor, b: torch.Tensor, scale=1.0, precision="exact") -> torch.Tensor:
+    """(scale * a) @ b.t() materialised as fp32 [N, M] (model/model.py:369)."""
+    dev = _req_cuda(a, b)
+    a, b = _mat(a, "a"), _mat(b, "b")
+    if a.shape[1] != b.shape[1] or a.dtype != b.dtype:
+        raise ValueError("a and b must share D and dtype")
+    N, D = a.shape
+    M = b.shape[0]
+    prec = _prec(precision)
+    sc = _scale_tensor(scale, dev)
+    out = torch.empty(N, M, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_SIM_MATRIX, N, M, D, prec))
+        _ffi.check(_ffi.load().vtc_sim_matrix(_ptr(a), _ptr(b), N, M, D, _dtype_code(a), prec,
+                                              _ptr(sc), _ptr(out), M, _ptr(ws), ws.numel(),
+                                              _stream(dev)), "vtc_sim_matrix")
+    return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, act: int = 0, precision="exact") -> torch.Tensor:
+    """act(x @ w.t() + bias) + residual on the tensor cores; x [rows, in], w [out, in], fp32."""
+    dev = _req_cuda(x, w, bias, residual)
+    x, w = _mat(x.float(), "x"), _mat(w.float(), "w")
+    rows, in_f = x.shape
+    out_f = w.shape[0]
+    if w.shape[1] != in_f:
+        raise ValueError("x and w disagree on in_features")
+    if bias is not None:
+        bias = bias.float().contiguous()
+    if residual is not None:
+        residual = residual.float().contiguous()
+        if residual.shape != (rows, out_f):
+            raise ValueError("residual must be [rows, out_features]")
+    prec = _prec(precision)
+    y = torch.empty(rows, out_f, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_LINEAR, rows, out_f, in_f, prec))
+        _ffi.check(_ffi.load().vtc_linear(_ptr(x), _ptr(w), _ptr(bias), _ptr(residual), rows, in_f,
+                                          out_f, act, prec, _ptr(y), _ptr(ws), ws.numel(),
+                                          _stream(dev)), "vtc_linear")
+    return y
+
+
+# ------------------------------------------------------------------------------------ R1 / R3
+def sim_rank(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None,
+             row_offset: int = 0, col_offset: int = 0, metric="l2", precision="exact",
+             gt_score: Optional[torch.Tensor] = None, rank0: Optional[torch.Tensor] = None,
+             accumulate: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused similarity + rank of ground truth.  Returns (rank0 int32 [N], gt_score fp64 [N]).
+
+    rank0 is NOT finalised (NaN ground truths still hold their partial count): call
+    :func:`rank_finalize` once every gallery chunk has been accumulated."""
+    dev = _req_cuda(q, g, gt, gt_score, rank0)
+    q, g = _mat(q, "q"), _mat(g, "g")
+    if q.shape[1] != g.shape[1] or q.dtype != g.dtype:
+        raise ValueError("queries and gallery must share D and dtype")
+    N, D = q.shape
+    M = g.shape[0]
+    prec, met = _prec(precision), _metric(metric)
+    if gt is not None:
+        gt = gt.to(torch.int64).contiguous()
+        if gt.shape != (N,):
+            raise ValueError("gt must be [N]")
+    if rank0 is None:
+        rank0 = torch.zeros(N, dtype=torch.int32, device=dev)
+        accumulate = False
+    elif rank0.dtype != torch.int32 or rank0.shape != (N,) or not rank0.is_contiguous():
+        raise ValueError("rank0 must be a contiguous int32 [N] tensor")
+    gs_out = None
+    if gt_score is None:
+        gs_out = torch.empty(N, dtype=torch.float64, device=dev)
+    elif gt_score.dtype != torch.float64 or gt_score.shape != (N,):
+        raise ValueError("gt_score must be float64 [N]")
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_SIM_RANK, N, M, D, prec))
+        _ffi.check(_ffi.load().vtc_sim_rank(
+            _ptr(q), _ptr(g), N, M, D, _dtype_code(q), _ptr(gt), row_offset, col_offset, met, prec,
+            _ptr(gt_score), _ptr(gs_out), 1 if accumulate else 0, _ptr(rank0), _ptr(ws), ws.numel(),
+            _stream(dev)), "vtc_sim_rank")
+    return rank0, (gt_score if gt_score is not None else gs_out)
+
+
+def gt_scores(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None,
+              row_offset: int = 0, col_offset: int = 0, metric="l2", precision="exact"
+              ) -> torch.Tensor:
+    """fp64-sequential d(t, gt(t)); NaN where gt lies outside this gallery chunk."""
+    dev = _req_cuda(q, g, gt)
+    q, g = _mat(q, "q"), _mat(g, "g")
+    N, D = q.shape
+    M = g.shape[0]
+    prec, met = _prec(precision), _metric(metric)
+    if gt is not None:
+        gt = gt.to(torch.int64).contiguous()
+    out = torch.empty(N, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_GT_SCORES, N, M, D, prec))
+        _ffi.check(_ffi.load().vtc_gt_scores(_ptr(q), _ptr(g), N, M, D, _dtype_code(q), _ptr(gt),
+                                             row_offset, col_offset, met, prec, _ptr(out), _ptr(ws),
+                                             ws.numel(), _stream(dev)), "vtc_gt_scores")
+    return out
+
+
+def rank_finalize(rank0: torch.Tensor, gt_score: Optional[torch.Tensor], M_total: int,
+                  k_vals: Sequence[int], want_medr: bool = True
+                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """In place: rank0 = M_total where gt_score is NaN.  Returns (hits int64 [nk], medr fp64 [1])."""
+    dev = _req_cuda(rank0, gt_score)
+    k_vals = [int(k) for k in k_vals]
+    if len(k_vals) > 8:
+        raise ValueError("at most 8 k values")
+    hits = torch.zeros(max(1, len(k_vals)), dtype=torch.int64, device=dev)
+    medr = torch.empty(1, dtype=torch.float64, device=dev) if want_medr else None
+    karr = (ctypes.c_int * max(1, len(k_vals)))(*k_vals)
+    with torch.cuda.device(dev):
+        hist = _workspace(dev, 2 * 65536 * 4)
+        _ffi.check(_ffi.load().vtc_rank_finalize(_ptr(rank0), _ptr(gt_score), rank0.shape[0],
+                                                 int(M_total), karr, len(k_vals), _ptr(hits),
+                                                 _ptr(medr), _ptr(hist), hist.numel(),
+                                                 _stream(dev)), "vtc_rank_finalize")
+    return hits[:len(k_vals)], medr
+
+
+# ------------------------------------------------------------------------------------------ K7
+def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int, metric="l2", precision="exact",
+             col_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused similarity + streaming top-k: (vals fp32 [N,k] ascending, idx int64 [N,k])."""
+    dev = _req_cuda(q, g)
+    q, g = _mat(q, "q"), _mat(g, "g")
+    if q.shape[1] != g.shape[1] or q.dtype != g.dtype:
+        raise ValueError("queries and gallery must share D and dtype")
+    N, D = q.shape
+    M = g.shape[0]
+    prec, met = _prec(precision), _metric(metric)
+    vals = torch.empty(N, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(N, k, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_SIM_TOPK, N, M, D, prec))
+        _ffi.check(_ffi.load().vtc_sim_topk(_ptr(q), _ptr(g), N, M, D, _dtype_code(q), met, prec, k,
+                                            col_offset, _ptr(vals), _ptr(idx), _ptr(ws), ws.numel(),
+                                            _stream(dev)), "vtc_sim_topk")
+    return vals, idx
+
+
+def topk_merge(vals: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge [parts, N, k] sorted candidate lists into the k best per row."""
+    dev = _req_cuda(vals, idx)
+    vals = vals.float().contiguous()
+    idx = idx.to(torch.int64).contiguous()
+    parts, N, k = vals.shape
+    ov = torch.empty(N, k, dtype=torch.float32, device=dev)
+    oi = torch.empty(N, k, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_topk_merge(_ptr(vals), _ptr(idx), parts, N, k, _ptr(ov), _ptr(oi),
+                                              _stream(dev)), "vtc_topk_merge")
+    return ov, oi
+
+
+# ------------------------------------------------------------------------------------- H2 + H3
+def infonce_fwd(a: torch.Tensor, b: torch.Tensor, scale, precision="exact"
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fused symmetric InfoNCE forward: (loss [1], row_lse [n], col_lse [n], diag [n])."""
+    dev = _req_cuda(a, b)
+    a, b = _mat(a, "a"), _mat(b, "b")
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("clip_loss needs a square similarity: a and b must have the same shape")
+    n, D = a.shape
+    prec = _prec(precision)
+    sc = _scale_tensor(scale, dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    row = torch.empty(n, dtype=torch.float32, device=dev)
+    col = torch.empty_like(row)
+    diag = torch.empty_like(row)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_INFONCE_FWD, n, n, D, prec))
+        _ffi.check(_ffi.load().vtc_infonce_fwd(_ptr(a), _ptr(b), n, D, _dtype_code(a), prec,
+                                               _ptr(sc), _ptr(loss), _ptr(row), _ptr(col),
+                                               _ptr(diag), _ptr(ws), ws.numel(), _stream(dev)),
+                   "vtc_infonce_fwd")
+    return loss, row, col, diag
+
+
+def infonce_bwd(a: torch.Tensor, b: torch.Tensor, scale, row_lse: torch.Tensor,
+                col_lse: torch.Tensor, grad_loss: torch.Tensor
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(dA [n,D], dB [n,D], dscale [1]) fp32."""
+    dev = _req_cuda(a, b, row_lse, col_lse, grad_loss)
+    a, b = _mat(a, "a"), _mat(b, "b")
+    n, D = a.shape
+    sc = _scale_tensor(scale, dev)
+    g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+    dA = torch.empty(n, D, dtype=torch.float32, device=dev)
+    dB = torch.empty_like(dA)
+    ds = torch.empty(1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_INFONCE_BWD, n, n, D, _ffi.PREC_EXACT))
+        _ffi.check(_ffi.load().vtc_infonce_bwd(_ptr(a), _ptr(b), n, D, _dtype_code(a), _ptr(sc),
+                                               _ptr(row_lse), _ptr(col_lse), _ptr(g), _ptr(dA),
+                                               _ptr(dB), _ptr(ds), _ptr(ws), ws.numel(),
+                                               _stream(dev)), "vtc_infonce_bwd")
+    return dA, dB, ds
+
+
+# ------------------------------------------------------------------------------------------ H4
+def cam_stack_normalize(main: torch.Tensor, aux: torch.Tensor) -> torch.Tensor:
+    """normalize(stack([main, *aux])) -> [1+nc, b, D] (model/model.py:150-151)."""
+    dev = _req_cuda(main, aux)
+    main = main.float().contiguous()
+    aux = aux.float().contiguous()
+    b, D = main.shape
+    nc = aux.shape[0]
+    if aux.shape[1:] != (b, D):
+        raise ValueError("aux must be [nc, b, D]")
+    X = torch.empty(nc + 1, b, D, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_cam_stack_normalize(_ptr(main), _ptr(aux), nc + 1, b, D, _ptr(X),
+                                                       _stream(dev)), "vtc_cam_stack_normalize")
+    return X
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5
+              ) -> torch.Tensor:
+    dev = _req_cuda(x, gamma, beta)
+    shp = x.shape
+    x2 = x.float().reshape(-1, shp[-1]).contiguous()
+    y = torch.empty_like(x2)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_layernorm(_ptr(x2), _ptr(gamma.float().contiguous()),
+                                             _ptr(beta.float().contiguous()), x2.shape[0],
+                                             x2.shape[1], eps, _ptr(y), _stream(dev)),
+                   "vtc_layernorm")
+    return y.reshape(shp)
+
+
+def cam_attn_core(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    """softmax(q k^T / sqrt(hd)) v per (sample, head); qkv [L, b, 3D] -> [L, b, D]."""
+    dev = _req_cuda(qkv)
+    qkv = qkv.float().contiguous()
+    L, b, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty(L, b, D, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_cam_attn_core(_ptr(qkv), L, b, D, heads, _ptr(out),
+                                                 _stream(dev)), "vtc_cam_attn_core")
+    return out
+
+
+def cam_readout(T: Optional[torch.Tensor], main: Optional[torch.Tensor], mode: int,
+                res_in: Optional[torch.Tensor] = None, skip_mask: Optional[torch.Tensor] = None
+                ) -> torch.Tensor:
+    dev = _req_cuda(T, main, res_in, skip_mask)
+    if T is not None:
+        T = T.float().contiguous()
+        L, b, D = T.shape
+    else:
+        L = 1
+        b, D = res_in.shape
+        res_in = res_in.float().contiguous()
+    if main is not None:
+        main = main.float().contiguous()
+    if skip_mask is not None:
+        skip_mask = skip_mask.to(device=dev, dtype=torch.uint8).contiguous()
+    out = torch.empty(b, D, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_cam_readout(_ptr(T), _ptr(main), _ptr(res_in), _ptr(skip_mask),
+                                               L, b, D, mode, _ptr(out), _stream(dev)),
+                   "vtc_cam_readout")
+    return out

@@ -1,0 +1,166 @@
+"""Multi-GPU retrieval evaluation: one process per GPU, torch.distributed (NCCL over NVLink 5 /
+NVSwitch on the box, gloo in the CPU tests) for the plumbing.  SURVEY.md §8e.
+
+The reference has no multi-GPU evaluation (its only parallelism is a nominal, shape-inconsistent
+DataParallel, train.py:76-82); this is the explicit design that replaces it:
+
+* row-sharded rank eval (BASELINE config 4, N ~ M): rank r owns query rows and gallery rows
+  [r*n/g, (r+1)*n/g).  The gallery shards are all-gathered; every rank ranks ITS queries against
+  each gallery chunk with `vtc_sim_rank(accumulate=1, col_offset=chunk start)` -- rank counts are
+  additive over gallery chunks -- starting with its own chunk while the gather is in flight.
+  The only other exchange is the reduction of the R@K hit counts and a gather of the int32 ranks
+  for the median.
+* gallery-sharded top-k (config 5, M >> N): queries are replicated, each rank scans its gallery
+  shard with `vtc_sim_topk(col_offset=shard start)`, the [N, k] candidates are all-gathered and
+  merged with `vtc_topk_merge`.  The gallery never moves.
+
+The compute backend is injectable so that the host logic is testable on CPU with gloo
+(tests/test_dist_gloo.py plugs the oracle in); the default backend is the CUDA library.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous balanced split of range(n): the first n % world shards get one extra row."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class CudaBackend:
+    """The product backend: libvtc_b200.so through vtc_b200.ops."""
+
+    def __init__(self):
+        from . import ops
+
+        self.ops = ops
+
+    def gt_scores(self, q, g, row_offset, col_offset, metric, precision):
+        return self.ops.gt_scores(q, g, None, row_offset, col_offset, metric, precision)
+
+    def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0):
+        self.ops.sim_rank(q, g, None, row_offset, col_offset, metric, precision, gt_score, rank0,
+                          accumulate=True)
+
+    def rank_finalize(self, rank0, gt_score, M_total, k_vals, want_medr):
+        return self.ops.rank_finalize(rank0, gt_score, M_total, k_vals, want_medr)
+
+    def sim_topk(self, q, g, k, metric, precision, col_offset):
+        return self.ops.sim_topk(q, g, k, metric, precision, col_offset)
+
+    def topk_merge(self, vals, idx):
+        return self.ops.topk_merge(vals, idx)
+
+
+def _world(group) -> Tuple[int, int]:
+    if not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _all_gather_padded(x: torch.Tensor, sizes: Sequence[int], group, async_op: bool = False):
+    """all_gather of row-shards with unequal row counts (pads to the largest shard)."""
+    world = len(sizes)
+    mx = max(sizes)
+    if x.shape[0] < mx:
+        pad = torch.zeros((mx - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        x = torch.cat([x, pad])
+    out = [torch.empty_like(x) for _ in range(world)]
+    work = dist.all_gather(out, x.contiguous(), group=group, async_op=async_op)
+    return out, work
+
+
+def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int, M_total: int,
+                      k_vals: Sequence[int] = (1, 5, 10), metric: str = "l2",
+                      precision: str = "exact", group=None, backend=None,
+                      want_medr: bool = True) -> Dict[str, object]:
+    """Row-sharded similarity + rank + R@K (+MedR).  q_local / g_local are this rank's
+    shard_bounds() rows of the global query / gallery matrices; gt(t) = t (global row index).
+
+    Returns {"hits": int64 [nk] (global), "medr": float or None, "rank0_local": int32 [n_r],
+             "num_queries": N_total}.  hits / medr are identical on every rank."""
+    backend = backend or CudaBackend()
+    world, rank = _world(group)
+    qs, qe = shard_bounds(N_total, world, rank)
+    assert q_local.shape[0] == qe - qs, "q_local does not match shard_bounds(N_total)"
+    g_sizes = [shard_bounds(M_total, world, r)[1] - shard_bounds(M_total, world, r)[0]
+               for r in range(world)]
+    g_starts = [shard_bounds(M_total, world, r)[0] for r in range(world)]
+    assert g_local.shape[0] == g_sizes[rank], "g_local does not match shard_bounds(M_total)"
+    dev = q_local.device
+
+    work = None
+    chunks: List[Optional[torch.Tensor]] = [None] * world
+    chunks[rank] = g_local
+    gathered = None
+    if world > 1:
+        gathered, work = _all_gather_padded(g_local, g_sizes, group, async_op=True)
+
+    # ground-truth scores: d(t, gt) lives in the chunk that owns gallery row t; start with ours
+    n_local = qe - qs
+    gt_score = backend.gt_scores(q_local, g_local, qs, g_starts[rank], metric, precision)
+    rank0 = torch.zeros(n_local, dtype=torch.int32, device=dev)
+    gt_local = world == 1 or _gt_all_local(qs, qe, g_starts[rank], g_sizes[rank])
+    todo = list(range(world))
+    if gt_local and g_sizes[rank] > 0:
+        # every ground truth is in our own chunk: rank against it while the gather is in flight
+        backend.sim_rank(q_local, g_local, qs, g_starts[rank], metric, precision, gt_score, rank0)
+        todo.remove(rank)
+    if work is not None:
+        work.wait()
+        for r in range(world):
+            if r != rank:
+                chunks[r] = gathered[r][:g_sizes[r]]
+        if not gt_local:
+            for r in range(world):
+                if r != rank and g_sizes[r] > 0:
+                    other = backend.gt_scores(q_local, chunks[r], qs, g_starts[r], metric, precision)
+                    gt_score = torch.where(torch.isnan(gt_score), other, gt_score)
+    for r in todo:
+        if g_sizes[r] > 0 and chunks[r] is not None:
+            backend.sim_rank(q_local, chunks[r], qs, g_starts[r], metric, precision, gt_score, rank0)
+
+    hits, _ = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), False)
+    hits = hits.clone()
+    medr = None
+    if world > 1:
+        dist.all_reduce(hits, op=dist.ReduceOp.SUM, group=group)
+    if want_medr:
+        if world > 1:
+            q_sizes = [shard_bounds(N_total, world, r)[1] - shard_bounds(N_total, world, r)[0]
+                       for r in range(world)]
+            allr, _ = _all_gather_padded(rank0, q_sizes, group)
+            full = torch.cat([allr[r][:q_sizes[r]] for r in range(world)])
+        else:
+            full = rank0
+        _, m = backend.rank_finalize(full.clone(), None, M_total, [], True)
+        medr = m
+    return {"hits": hits, "medr": medr, "rank0_local": rank0, "num_queries": N_total}
+
+
+def _gt_all_local(qs: int, qe: int, g_start: int, g_size: int) -> bool:
+    return qs >= g_start and qe <= g_start + g_size
+
+
+def sharded_topk(q: torch.Tensor, g_local: torch.Tensor, M_total: int, k: int, metric: str = "l2",
+                 precision: str = "bf16", group=None, backend=None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gallery-sharded streaming top-k: every rank holds all queries `q` and its shard_bounds()
+    rows of the gallery.  Returns the merged (vals [N,k], idx int64 [N,k]) on every rank."""
+    backend = backend or CudaBackend()
+    world, rank = _world(group)
+    gs, ge = shard_bounds(M_total, world, rank)
+    assert g_local.shape[0] == ge - gs, "g_local does not match shard_bounds(M_total)"
+    vals, idx = backend.sim_topk(q, g_local, k, metric, precision, gs)
+    if world == 1:
+        return vals, idx
+    av = [torch.empty_like(vals) for _ in range(world)]
+    ai = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(av, vals.contiguous(), group=group)
+    dist.all_gather(ai, idx.contiguous(), group=group)
+    return backend.topk_merge(torch.stack(av), torch.stack(ai))
