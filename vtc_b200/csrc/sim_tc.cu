@@ -463,15 +463,23 @@ int make_operand_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
 int plan_tiles(Params& p, int max_splits) {
   p.q_tiles = (int)ceil_div<int64_t>(p.N, BM);
   p.g_tiles = (int)ceil_div<int64_t>(p.M, BN);
-  // enough items to fill the machine a few times over, but keep >= 8 gallery tiles per item so
-  // the (re)load of the resident query tile stays amortised
-  int splits = 1;
-  while (splits < max_splits && (int64_t)p.q_tiles * splits < 4 * kNumSMs &&
-         p.g_tiles / (splits * 2) >= 8)
-    splits *= 2;
-  if (splits > p.g_tiles) splits = p.g_tiles > 0 ? p.g_tiles : 1;
-  p.tiles_per_split = ceil_div(p.g_tiles, splits);
-  p.g_splits = ceil_div(p.g_tiles, p.tiles_per_split);
+  // Items are dealt round-robin to one CTA per SM, so the cost is ceil(items / SMs) rounds.
+  // Cut the gallery into the number of splits that wastes the fewest CTA-rounds, keeping >= 8
+  // gallery tiles per item so the (re)load of the resident query tile stays amortised.
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_splits && s <= (p.g_tiles > 0 ? p.g_tiles : 1); ++s) {
+    const int tps = ceil_div(p.g_tiles, s);
+    if (s > 1 && tps < 8) break;
+    const int64_t items = (int64_t)p.q_tiles * ceil_div(p.g_tiles, tps);
+    const int64_t rounds = ceil_div<int64_t>(items, kNumSMs);
+    // rounds are tps tiles long (+ ~1 tile-time to swap the resident query tile);
+    // efficiency = useful tile-slots / occupied tile-slots
+    const double eff = (double)p.q_tiles * p.g_tiles / ((double)rounds * kNumSMs * (tps + 1));
+    if (eff > best_eff + 1e-9) best_eff = eff, best = s;
+  }
+  p.tiles_per_split = ceil_div(p.g_tiles > 0 ? p.g_tiles : 1, best);
+  p.g_splits = ceil_div(p.g_tiles > 0 ? p.g_tiles : 1, p.tiles_per_split);
   const int64_t items = (int64_t)p.q_tiles * p.g_splits;
   return (int)(items < kNumSMs ? items : kNumSMs);
 }
