@@ -82,7 +82,8 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
       r.amb_cap = amb_entries_wanted(N);
       ws.take<int2>(r.amb_cap);
     } else {
-      const size_t left = ws.size > ws.used ? ws.size - ws.used : 0;
+      size_t left = ws.size > ws.used ? ws.size - ws.used : 0;
+      left -= left % 256;  // take() hands out 256-byte granules
       size_t cap = left / sizeof(int2);
       if (cap > 0x7fffffffu) cap = 0x7fffffffu;
       r.amb_cap = cap;
