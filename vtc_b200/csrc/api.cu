@@ -158,11 +158,11 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.oob_bias = INFINITY;
   p.thr = w.thr, p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_count = &w.scalars[1];
   p.amb_cap = (unsigned int)w.amb_cap;
-  const int grid = tc::plan_tiles(p, 64);
+  const tc::Plan pl = tc::plan_tiles(p, 64, tc::choose_cluster(N, M));
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN, &tmB));
-  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, tmA, tmB, p, grid, s));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
+  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
   // 4. exact re-check of the guard-band pairs; brute force if the list overflowed
   VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[1], (unsigned int)w.amb_cap, w.dgt,
                                      w.rank_tmp, &w.scalars[2], s));
@@ -252,12 +252,12 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
   p.oob_bias = INFINITY;
   p.pool_val = w.pool_val, p.pool_idx = w.pool_idx, p.pool_meta = w.pool_meta;
-  const int grid = tc::plan_tiles(p, kTopkMaxSplits);
+  const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, tc::choose_cluster(N, M));
   a.splits = p.g_splits;
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN, &tmB));
-  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_TOPK, p.num_kb <= 8, tmA, tmB, p, grid, s));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
+  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_TOPK, p.num_kb <= 8, pl, tmA, tmB, p, s));
   VTC_RETURN_IF_ERROR(launch_topk_select(a, s));
   return launch_topk_brute_rows(a, s);
 }
@@ -298,11 +298,11 @@ int gemm_store_impl(const void* A, const void* B, int64_t N, int64_t M, int D, i
   p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
   p.col_bias = bias, p.scale_ptr = scale_ptr, p.scale = 1.f, p.oob_bias = 0.f;
   p.out = out, p.ldo = ldo, p.residual = residual, p.act = act;
-  const int grid = tc::plan_tiles(p, 1);
+  const tc::Plan pl = tc::plan_tiles(p, 1, 1);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opA, N, o.Kp, o.Kp, tc::BM, &tmA));
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opB, M, o.Kp, o.Kp, tc::BN, &tmB));
-  return tc::launch_sim_tc(tc::EPI_STORE, p.num_kb <= 8, tmA, tmB, p, grid, s);
+  return tc::launch_sim_tc(tc::EPI_STORE, p.num_kb <= 8, pl, tmA, tmB, p, s);
 }
 
 // ------------------------------------------------------------------------------------- InfoNCE
@@ -359,13 +359,13 @@ int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, 
     p.lse_part = dir == 0 ? w.part_row : w.part_col;
     p.diag = dir == 0 ? w.diag_raw : nullptr;
     p.diag_offset = 0;
-    const int grid = tc::plan_tiles(p, kNceMaxSplits);
+    const tc::Plan pl = tc::plan_tiles(p, kNceMaxSplits, 1);
     CUtensorMap tmA, tmB;
     VTC_RETURN_IF_ERROR(
         tc::make_operand_tmap(dir == 0 ? w.a_as_a : w.b_as_a, n, o.Kp, o.Kp, tc::BM, &tmA));
     VTC_RETURN_IF_ERROR(
         tc::make_operand_tmap(dir == 0 ? w.b_as_b : w.a_as_b, n, o.Kp, o.Kp, tc::BN, &tmB));
-    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_LSE, p.num_kb <= 8, tmA, tmB, p, grid, s));
+    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_LSE, p.num_kb <= 8, pl, tmA, tmB, p, s));
     VTC_RETURN_IF_ERROR(launch_lse_merge(p.lse_part, p.g_splits, n, dir == 0 ? row_lse : col_lse, s));
   }
   return launch_infonce_loss(row_lse, col_lse, w.diag_raw, scale, n, diag, loss, s);

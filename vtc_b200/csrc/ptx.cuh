@@ -88,6 +88,30 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* tm,
+                                                      uint64_t* bar, int32_t c0, int32_t c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------- clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // -------------------------------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -127,6 +151,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+// same, arriving on the mbarrier at this CTA-relative offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
 }
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {

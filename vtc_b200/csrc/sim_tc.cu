@@ -1,431 +1,26 @@
-// sim_tc.cu -- the similarity GEMM of the retrieval hot path on the 5th-gen tensor cores.
-//
-//   S[t, j] = scale * <A_t, B_j> + bias_j        A: queries [N, K'] bf16, B: gallery [M, K'] bf16
-//
-// replaces `feats_a @ feats_b.t()` (model/model.py:369,478,504,621) and the SGEMM inside
-// faiss.GpuIndexFlatL2.search (model/metric.py:144-146).  S is never written to HBM: each
-// 128 x 256 fp32 tile lives in TMEM and is consumed by a fused epilogue:
-//   EPI_RANK   count columns whose score beats the ground-truth score (guard-banded; ambiguous
-//              pairs go to a list that exact.cu re-checks in fp64)        -> rank / R@K / MedR
-//   EPI_LSE    online row log-sum-exp + diagonal                           -> symmetric InfoNCE
-//   EPI_TOPK   streaming top-k candidate pool per row                      -> faiss-style search
-//   EPI_STORE  materialise (bias / QuickGELU / residual)                   -> sim tensor, linears
-//
-// Structure (one CTA per SM, persistent over work items, 256 threads):
-//   warp 0   TMA producer  : cp.async.bulk.tensor 2-D loads, 128B-swizzled K-major tiles
-//   warp 1   MMA issuer    : one thread issues tcgen05.mma (M128 x N256 x K16, bf16 -> fp32 TMEM)
-//   warp 2   TMEM allocator: 512 columns = 2 accumulator stages of 256
-//   warp 4-7 epilogue      : tcgen05.ld 32x32b (thread = tile row), fused reduction
-// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
-// With `kRes` the 128 x K' query tile stays resident in shared memory for a whole work item
-// (K' <= 512), so only gallery tiles stream from L2: 64 B/clk/SM instead of 96.
-//
-// Work item = (query tile, gallery split); items are ordered so that CTAs running concurrently
-// sweep the same gallery range (B tiles are shared through the 126 MB L2).
+// sim_tc.cu -- host side of the tcgen05 similarity GEMM: TMA descriptors, work planning, cluster
+// choice, dispatch to the per-epilogue instantiations (sim_tc_{rank,topk,lse,store}.cu) and the
+// opt-in CUDA-event timer bench.py uses for the roofline.
+#include <cstdlib>
 #include <mutex>
 #include <utility>
 #include <vector>
 
-#include "ptx.cuh"
 #include "sim_tc.cuh"
 
 namespace vtc {
 namespace tc {
 
-using namespace ptx;
+int launch_rank(bool a_resident, int cluster, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                const Params& p, int grid, cudaStream_t s);
+int launch_topk(bool a_resident, int cluster, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                const Params& p, int grid, cudaStream_t s);
+int launch_lse(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
+               int grid, cudaStream_t s);
+int launch_store(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
+                 int grid, cudaStream_t s);
+int max_active_clusters_rank(int cluster);
 
-constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int MAX_RES_KB = 8;              // resident A: up to K' = 512
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_WARP0 = 4;
-constexpr int TMEM_COLS = 512;
-
-template <bool kRes>
-struct SmemLayout {
-  static constexpr int kStages = kRes ? 3 : 4;
-  static constexpr int kStageBytes = kRes ? B_TILE_BYTES : (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int kResBytes = kRes ? MAX_RES_KB * A_TILE_BYTES : 0;
-  static constexpr int kStagesOff = kResBytes;
-  static constexpr int kBiasOff = kStagesOff + kStages * kStageBytes;  // 2 x 256 floats
-  static constexpr int kBarOff = kBiasOff + 2 * BN * 4;
-  static constexpr int kNumBars = 2 * kStages + MAX_RES_KB + 1 + 2 + 2;
-  static constexpr int kTotal = kBarOff + 256;
-  static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
-  static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
-};
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// ------------------------------------------------------------------------------------ epilogues
-// Each epilogue thread owns one tile row (= TMEM lane).  `begin_item` / `chunk` / `end_item`.
-
-struct RankEpi {
-  float lo, hi;
-  int cnt;
-  int64_t t;
-  __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int) {
-    t = t_;
-    cnt = 0;
-    lo = hi = nanf("");
-    if (t < p.N) {
-      const float2 th = p.thr[t];
-      lo = th.x;
-      hi = th.y;
-    }
-  }
-  __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
-                                        const float* __restrict__ cb, float scale, int64_t jbase) {
-    int lt = 0, le = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = reinterpret_cast<const float4*>(cb)[i];
-      const float d0 = fmaf(scale, __uint_as_float(v[4 * i + 0]), b.x);
-      const float d1 = fmaf(scale, __uint_as_float(v[4 * i + 1]), b.y);
-      const float d2 = fmaf(scale, __uint_as_float(v[4 * i + 2]), b.z);
-      const float d3 = fmaf(scale, __uint_as_float(v[4 * i + 3]), b.w);
-      lt += (d0 < lo) + (d1 < lo) + (d2 < lo) + (d3 < lo);
-      le += (d0 <= hi) + (d1 <= hi) + (d2 <= hi) + (d3 <= hi);
-    }
-    cnt += lt;
-    if (le != lt) {  // rare: some score falls inside the guard band
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float d = fmaf(scale, __uint_as_float(v[i]), cb[i]);
-        if (d <= hi && !(d < lo)) {
-          const unsigned int pos = atomicAdd(p.amb_count, 1u);
-          if (pos < p.amb_cap) p.amb_list[pos] = make_int2((int)t, (int)(jbase + i));
-        }
-      }
-    }
-  }
-  __device__ __forceinline__ void end_item(const Params& p, int) {
-    if (t < p.N && cnt) atomicAdd(&p.rank[t], cnt);
-  }
-};
-
-struct LseEpi {
-  float m, l, dv;
-  int64_t t, jd;
-  __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int) {
-    t = t_;
-    m = -INFINITY;
-    l = 0.f;
-    dv = nanf("");
-    jd = p.diag ? t + p.diag_offset : -1;
-  }
-  __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
-                                        const float* __restrict__ cb, float scale, int64_t jbase) {
-    float x[32];
-    float cmax = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = reinterpret_cast<const float4*>(cb)[i];
-      x[4 * i + 0] = fmaf(scale, __uint_as_float(v[4 * i + 0]), b.x);
-      x[4 * i + 1] = fmaf(scale, __uint_as_float(v[4 * i + 1]), b.y);
-      x[4 * i + 2] = fmaf(scale, __uint_as_float(v[4 * i + 2]), b.z);
-      x[4 * i + 3] = fmaf(scale, __uint_as_float(v[4 * i + 3]), b.w);
-      cmax = fmaxf(cmax, fmaxf(fmaxf(x[4 * i], x[4 * i + 1]), fmaxf(x[4 * i + 2], x[4 * i + 3])));
-    }
-    if (cmax > -INFINITY) {
-      const float mn = fmaxf(m, cmax);
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) s += ex2_approx(x[i] - mn);
-      l = l * ex2_approx(m - mn) + s;
-      m = mn;
-    }
-    if (jd >= jbase && jd < jbase + 32) {
-      const int sel = (int)(jd - jbase);
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i == sel) dv = __uint_as_float(v[i]);
-    }
-  }
-  __device__ __forceinline__ void end_item(const Params& p, int split) {
-    if (t < p.N) {
-      p.lse_part[(int64_t)split * p.N + t] = make_float2(m, l);
-      if (p.diag && dv == dv) p.diag[t] = dv;
-    }
-  }
-};
-
-struct StoreEpi {
-  int64_t t;
-  __device__ __forceinline__ void begin_item(const Params&, int64_t t_, int) { t = t_; }
-  __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
-                                        const float* __restrict__ cb, float scale, int64_t jbase) {
-    if (t >= p.N) return;
-    float* o = p.out + t * p.ldo + jbase;
-    const float* r = p.residual ? p.residual + t * p.ldo + jbase : nullptr;
-    const bool vec = (jbase + 32 <= p.M) && ((p.ldo & 3) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
-                     (!r || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-    float y[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float z = fmaf(scale, __uint_as_float(v[i]), cb[i]);
-      if (p.act == 1) z = z / (1.f + __expf(-1.702f * z));  // QuickGELU: z * sigmoid(1.702 z)
-      y[i] = z;
-    }
-    if (vec) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 w = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-        if (r) {
-          const float4 q = reinterpret_cast<const float4*>(r)[i];
-          w.x += q.x, w.y += q.y, w.z += q.z, w.w += q.w;
-        }
-        reinterpret_cast<float4*>(o)[i] = w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (jbase + i < p.M) o[i] = y[i] + (r ? r[i] : 0.f);
-    }
-  }
-  __device__ __forceinline__ void end_item(const Params&, int) {}
-};
-
-struct TopkEpi {
-  float tau;
-  int fill;
-  int64_t t;
-  float* pv;
-  int* pi;
-  __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int split) {
-    t = t_;
-    tau = INFINITY;
-    fill = 0;
-    const int64_t slot = ((int64_t)split * p.N + (t < p.N ? t : 0)) * TOPK_POOL;
-    pv = p.pool_val + slot;
-    pi = p.pool_idx + slot;
-    if (t >= p.N) tau = -INFINITY;  // padded rows never insert
-  }
-  __device__ __forceinline__ void insert(float d, int j) {
-    if (fill < TOPK_POOL) {
-      pv[fill] = d;
-      pi[fill] = j;
-      ++fill;
-      if (fill < TOPK_POOL) return;
-    } else {
-      int worst = 0;
-      float wv = pv[0];
-      for (int i = 1; i < TOPK_POOL; ++i) {
-        const float x = pv[i];
-        if (x > wv) wv = x, worst = i;
-      }
-      pv[worst] = d;
-      pi[worst] = j;
-    }
-    float mx = pv[0];
-    for (int i = 1; i < TOPK_POOL; ++i) mx = fmaxf(mx, pv[i]);
-    tau = mx;
-  }
-  __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
-                                        const float* __restrict__ cb, float scale, int64_t jbase) {
-    int any = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = reinterpret_cast<const float4*>(cb)[i];
-      any += (fmaf(scale, __uint_as_float(v[4 * i + 0]), b.x) < tau) +
-             (fmaf(scale, __uint_as_float(v[4 * i + 1]), b.y) < tau) +
-             (fmaf(scale, __uint_as_float(v[4 * i + 2]), b.z) < tau) +
-             (fmaf(scale, __uint_as_float(v[4 * i + 3]), b.w) < tau);
-    }
-    if (any) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float d = fmaf(scale, __uint_as_float(v[i]), cb[i]);
-        if (d < tau) insert(d, (int)(jbase + i));
-      }
-    }
-  }
-  __device__ __forceinline__ void end_item(const Params& p, int split) {
-    if (t < p.N) p.pool_meta[(int64_t)split * p.N + t] = make_float2((float)fill, tau);
-  }
-};
-
-// ------------------------------------------------------------------------------------- kernel
-template <typename Epi, bool kRes>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const Params p) {
-  using L = SmemLayout<kRes>;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* res_a = smem;
-  uint8_t* stages = smem + L::kStagesOff;
-  float* colbias = reinterpret_cast<float*>(smem + L::kBiasOff);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* full = bars;
-  uint64_t* empty = full + L::kStages;
-  uint64_t* a_full = empty + L::kStages;
-  uint64_t* a_empty = a_full + MAX_RES_KB;
-  uint64_t* tmem_full = a_empty + 1;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
-    prefetch_tensormap(&tmA);
-    prefetch_tensormap(&tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < L::kStages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    for (int i = 0; i < MAX_RES_KB; ++i) mbar_init(&a_full[i], 1);
-    mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int num_items = p.q_tiles * p.g_splits;
-  const int num_kb = p.num_kb;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int qt = item % p.q_tiles, split = item / p.q_tiles;
-        const int t0 = split * p.tiles_per_split;
-        const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
-        if (kRes) mbar_wait(a_empty, (it & 1) ^ 1);  // previous item's MMAs have drained
-        for (int tile = t0; tile < t1; ++tile) {
-          for (int kb = 0; kb < num_kb; ++kb) {
-            if (kRes && tile == t0) {
-              mbar_arrive_expect_tx(&a_full[kb], A_TILE_BYTES);
-              tma_load_2d(res_a + kb * A_TILE_BYTES, &tmA, &a_full[kb], kb * BK, qt * BM);
-            }
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], L::kStageBytes);
-            uint8_t* st = stages + stage * L::kStageBytes;
-            if (!kRes) tma_load_2d(st, &tmA, &full[stage], kb * BK, qt * BM);
-            tma_load_2d(st + (kRes ? 0 : A_TILE_BYTES), &tmB, &full[stage], kb * BK, tile * BN);
-            if (++stage == L::kStages) stage = 0, phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
-      uint32_t stage = 0, phase = 0, as = 0, aphase = 0, it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int split = item / p.q_tiles;
-        const int t0 = split * p.tiles_per_split;
-        const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
-        for (int tile = t0; tile < t1; ++tile) {
-          mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * BN;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            if (kRes && tile == t0) mbar_wait(&a_full[kb], it & 1);
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            uint8_t* st = stages + stage * L::kStageBytes;
-            const uint64_t adesc =
-                make_smem_desc_sw128(smem_u32(kRes ? res_a + kb * A_TILE_BYTES : st));
-            const uint64_t bdesc = make_smem_desc_sw128(smem_u32(st + (kRes ? 0 : A_TILE_BYTES)));
-#pragma unroll
-            for (int k4 = 0; k4 < BK / 16; ++k4)
-              umma_bf16(d_tmem, desc_advance(adesc, k4 * 32), desc_advance(bdesc, k4 * 32), idesc,
-                        (uint32_t)((kb | k4) != 0));
-            umma_commit(&empty[stage]);  // smem slot free once these MMAs retire
-            if (++stage == L::kStages) stage = 0, phase ^= 1;
-          }
-          umma_commit(&tmem_full[as]);  // accumulator complete
-          as ^= 1;
-          if (as == 0) aphase ^= 1;
-        }
-        if (kRes) umma_commit(a_empty);
-      }
-    }
-  } else if (warp >= EPI_WARP0) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quarter this warp may read
-    const int row = ew * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
-    const int etid = threadIdx.x - EPI_WARP0 * 32;
-    const float scale = p.scale * (p.scale_ptr ? *p.scale_ptr : 1.0f);
-    uint32_t as = 0, aphase = 0;
-    Epi epi;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int qt = item % p.q_tiles, split = item / p.q_tiles;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
-      epi.begin_item(p, (int64_t)qt * BM + row, split);
-      for (int tile = t0; tile < t1; ++tile) {
-        const int64_t j0 = (int64_t)tile * BN;
-        float* cb = colbias + as * BN;
-        for (int i = etid; i < BN; i += 128) {
-          const int64_t j = j0 + i;
-          cb[i] = j < p.M ? (p.col_bias ? p.col_bias[j] : 0.f) : p.oob_bias;
-        }
-        named_bar_sync(1, 128);
-        mbar_wait(&tmem_full[as], aphase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_off + as * BN;
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(taddr, va);
-        tmem_ld_wait(va);
-#pragma unroll
-        for (int c = 0; c < BN / 32; c += 2) {
-          tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-          epi.chunk(p, va, cb + c * 32, scale, j0 + c * 32);
-          tmem_ld_wait(vb);
-          if (c + 2 < BN / 32) {
-            tmem_ld_32x32(taddr + (c + 2) * 32, va);
-          } else {
-            // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
-          }
-          epi.chunk(p, vb, cb + (c + 1) * 32, scale, j0 + (c + 1) * 32);
-          if (c + 2 < BN / 32) tmem_ld_wait(va);
-        }
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
-      }
-      epi.end_item(p, split);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
-// ------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -460,28 +55,59 @@ int make_operand_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
   return r == CUDA_SUCCESS ? VTC_OK : VTC_ERR_DRIVER;
 }
 
-int plan_tiles(Params& p, int max_splits) {
+// Cluster size for the gallery multicast.  Clusters must be co-resident (persistent kernel), and a
+// GPC only hosts whole clusters, so the usable SM count can shrink with the cluster size; the
+// planner works with the real number from cudaOccupancyMaxActiveClusters.
+static int active_clusters(int cluster) {
+  static int cache[5] = {0, 0, 0, 0, 0};
+  static std::mutex mu;
+  if (cluster <= 1) return kNumSMs;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache[cluster] == 0) {
+    int n = max_active_clusters_rank(cluster);
+    cache[cluster] = n > 0 ? n : -1;
+  }
+  return cache[cluster] > 0 ? cache[cluster] : 0;
+}
+
+int choose_cluster(int64_t N, int64_t M) {
+  int want = 2;  // default: pairs lose no SMs (148 = 2 x 74) and halve the L2 -> SM gallery traffic
+  const char* e = getenv("VTC_CLUSTER");
+  if (e && *e) want = atoi(e);
+  if (want != 1 && want != 2 && want != 4) want = 1;
+  const int64_t q_tiles = ceil_div<int64_t>(N, BM);
+  while (want > 1 && (q_tiles < want || active_clusters(want) <= 0)) want /= 2;
+  (void)M;
+  return want;
+}
+
+Plan plan_tiles(Params& p, int max_splits, int cluster) {
+  Plan pl;
+  pl.cluster = cluster < 1 ? 1 : cluster;
   p.q_tiles = (int)ceil_div<int64_t>(p.N, BM);
   p.g_tiles = (int)ceil_div<int64_t>(p.M, BN);
-  // Items are dealt round-robin to one CTA per SM, so the cost is ceil(items / SMs) rounds.
-  // Cut the gallery into the number of splits that wastes the fewest CTA-rounds, keeping >= 8
-  // gallery tiles per item so the (re)load of the resident query tile stays amortised.
+  const int units = pl.cluster > 1 ? active_clusters(pl.cluster) : kNumSMs;  // co-resident clusters
+  const int q_groups = ceil_div(p.q_tiles, pl.cluster);
+  // Items are dealt round-robin to the co-resident clusters, so the cost is ceil(items / units)
+  // rounds of tiles_per_split tiles (+ ~1 tile-time to swap the resident query tile).  Pick the
+  // split count with the best useful / occupied tile-slot ratio, keeping >= 8 tiles per item.
+  const int g_tiles = p.g_tiles > 0 ? p.g_tiles : 1;
   int best = 1;
   double best_eff = 0.0;
-  for (int s = 1; s <= max_splits && s <= (p.g_tiles > 0 ? p.g_tiles : 1); ++s) {
-    const int tps = ceil_div(p.g_tiles, s);
+  for (int s = 1; s <= max_splits && s <= g_tiles; ++s) {
+    const int tps = ceil_div(g_tiles, s);
     if (s > 1 && tps < 8) break;
-    const int64_t items = (int64_t)p.q_tiles * ceil_div(p.g_tiles, tps);
-    const int64_t rounds = ceil_div<int64_t>(items, kNumSMs);
-    // rounds are tps tiles long (+ ~1 tile-time to swap the resident query tile);
-    // efficiency = useful tile-slots / occupied tile-slots
-    const double eff = (double)p.q_tiles * p.g_tiles / ((double)rounds * kNumSMs * (tps + 1));
+    const int64_t items = (int64_t)q_groups * ceil_div(g_tiles, tps);
+    const int64_t rounds = ceil_div<int64_t>(items, units);
+    const double eff =
+        (double)p.q_tiles * g_tiles / ((double)rounds * units * pl.cluster * (tps + 1));
     if (eff > best_eff + 1e-9) best_eff = eff, best = s;
   }
-  p.tiles_per_split = ceil_div(p.g_tiles > 0 ? p.g_tiles : 1, best);
-  p.g_splits = ceil_div(p.g_tiles > 0 ? p.g_tiles : 1, p.tiles_per_split);
-  const int64_t items = (int64_t)p.q_tiles * p.g_splits;
-  return (int)(items < kNumSMs ? items : kNumSMs);
+  p.tiles_per_split = ceil_div(g_tiles, best);
+  p.g_splits = ceil_div(g_tiles, p.tiles_per_split);
+  const int64_t items = (int64_t)q_groups * p.g_splits;
+  pl.grid = (int)(items < units ? items : units) * pl.cluster;
+  return pl;
 }
 
 // Opt-in profiling aid (bench.py): CUDA events around every tensor-core launch on its own stream.
@@ -520,14 +146,10 @@ int kernel_timer_read(double* total_ms, int* count) {
   return VTC_OK;
 }
 
-template <typename Epi, bool kRes>
-static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid,
-                    cudaStream_t s) {
-  using L = SmemLayout<kRes>;
-  auto* kern = &sim_tc_kernel<Epi, kRes>;
-  // the attribute is per function and per device: cheap, so set it on every launch
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-  if (e != cudaSuccess) return cuda_err(e);
+int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorMap& tmA,
+                  const CUtensorMap& tmB, const Params& p, cudaStream_t s) {
+  if (pl.grid <= 0) return VTC_OK;
+  if (a_resident && p.num_kb > 8) return VTC_ERR_UNSUPPORTED_SHAPE;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool timed;
   {
@@ -539,35 +161,26 @@ static int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params
     cudaEventCreate(&e1);
     cudaEventRecord(e0, s);
   }
-  kern<<<grid, NUM_THREADS, L::kTotal, s>>>(tmA, tmB, p);
+  int rc;
+  switch (epilogue) {
+    case EPI_RANK: rc = launch_rank(a_resident, pl.cluster, tmA, tmB, p, pl.grid, s); break;
+    case EPI_TOPK: rc = launch_topk(a_resident, pl.cluster, tmA, tmB, p, pl.grid, s); break;
+    case EPI_LSE:
+      rc = pl.cluster == 1 ? launch_lse(a_resident, tmA, tmB, p, pl.grid, s) : VTC_ERR_INVALID_ARG;
+      break;
+    case EPI_STORE:
+      rc = pl.cluster == 1 ? launch_store(a_resident, tmA, tmB, p, pl.grid, s) : VTC_ERR_INVALID_ARG;
+      break;
+    default: rc = VTC_ERR_INVALID_ARG;
+  }
   if (timed) {
     cudaEventRecord(e1, s);
     std::lock_guard<std::mutex> lk(g_timer.mu);
     g_timer.events.emplace_back(e0, e1);
   }
+  if (rc != VTC_OK) return rc;
   VTC_LAUNCH_CHECK();
   return VTC_OK;
-}
-
-int launch_sim_tc(int epilogue, bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                  const Params& p, int grid, cudaStream_t s) {
-  if (grid <= 0) return VTC_OK;
-  if (a_resident && p.num_kb > MAX_RES_KB) return VTC_ERR_UNSUPPORTED_SHAPE;
-  switch (epilogue) {
-    case EPI_RANK:
-      return a_resident ? launch_t<RankEpi, true>(tmA, tmB, p, grid, s)
-                        : launch_t<RankEpi, false>(tmA, tmB, p, grid, s);
-    case EPI_LSE:
-      return a_resident ? launch_t<LseEpi, true>(tmA, tmB, p, grid, s)
-                        : launch_t<LseEpi, false>(tmA, tmB, p, grid, s);
-    case EPI_STORE:
-      return a_resident ? launch_t<StoreEpi, true>(tmA, tmB, p, grid, s)
-                        : launch_t<StoreEpi, false>(tmA, tmB, p, grid, s);
-    case EPI_TOPK:
-      return a_resident ? launch_t<TopkEpi, true>(tmA, tmB, p, grid, s)
-                        : launch_t<TopkEpi, false>(tmA, tmB, p, grid, s);
-  }
-  return VTC_ERR_INVALID_ARG;
 }
 
 }  // namespace tc

@@ -52,16 +52,24 @@ struct Params {
 int make_operand_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                       CUtensorMap* out);
 
+// cluster size (1, 2 or 4) used to multicast the gallery stream; honours VTC_CLUSTER
+int choose_cluster(int64_t N, int64_t M);
+
+struct Plan {
+  int cluster;  // CTAs per cluster sharing each gallery tile
+  int grid;     // CTAs to launch (multiple of cluster)
+};
+// fills q_tiles / g_tiles / g_splits / tiles_per_split for the given cluster size
+Plan plan_tiles(Params& p, int max_splits, int cluster);
+
 // a_resident: keep the whole 128 x K' query tile in shared memory (needs num_kb <= 8).
-int launch_sim_tc(int epilogue, bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                  const Params& p, int grid, cudaStream_t s);
+// tmB must have been built with box_rows = BN / pl.cluster.
+int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorMap& tmA,
+                  const CUtensorMap& tmB, const Params& p, cudaStream_t s);
 
 // opt-in CUDA-event timing of the tensor-core launches (bench.py roofline)
 void kernel_timer_enable(bool on);
 int kernel_timer_read(double* total_ms, int* count);
-
-// fills q_tiles / g_tiles / g_splits / tiles_per_split and returns the grid size
-int plan_tiles(Params& p, int max_splits);
 
 }  // namespace tc
 }  // namespace vtc
