@@ -122,7 +122,7 @@ int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int
 /* rank0[t] = M_total where gt_score[t] is NaN ("never retrieved"); hits[i] = #{t: rank0[t] <
  * k_vals[i]} (int64, device; replaces model/metric.py:149-160); k_vals is a HOST array, nk <= 8.
  * medr (device double, may be NULL) = median(rank0) + 1 with numpy semantics.
- * hist_ws: >= 2*65536*4 bytes of workspace when medr != NULL. */
+ * hist_ws: >= (3*65536+8)*4 bytes of workspace when medr != NULL. */
 int vtc_rank_finalize(int32_t* rank0, const double* gt_score, int64_t N, int64_t M_total,
                       const int* k_vals, int nk, int64_t* hits, double* medr, void* hist_ws,
                       size_t hist_ws_bytes, vtc_stream_t stream);

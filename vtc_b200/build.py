@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import hashlib
 import os
+import re
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -24,45 +25,58 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
-def _tree_hash() -> str:
+def _includes(path: str, seen=None):
+    """Transitive closure of the quoted #include's of a source file (paths resolved like nvcc)."""
+    seen = seen if seen is not None else set()
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for m in re.finditer(r'^\s*#include\s+"([^"]+)"', open(path).read(), flags=re.M):
+        _includes(os.path.normpath(os.path.join(os.path.dirname(path), m.group(1))), seen)
+    return seen
+
+
+def _unit_hash(src: str) -> str:
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
-        for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h")):
-                with open(os.path.join(root, name), "rb") as f:
-                    h.update(name.encode())
-                    h.update(f.read())
+    for f in sorted(_includes(os.path.join(CSRC, src))):
+        h.update(f.encode())
+        h.update(open(f, "rb").read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Incremental: a translation unit is recompiled only when it or a header it includes changed."""
     os.makedirs(OBJDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, "build.sha256")
-    want = _tree_hash()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == want:
-        return LIB
     if not os.path.exists(NVCC):
+        if os.path.exists(LIB):
+            return LIB  # e.g. a box without the toolkit: use the library that travelled with the repo
         raise RuntimeError(f"nvcc not found at {NVCC}; cannot build {LIB}")
 
-    def compile_one(src: str) -> str:
+    def compile_one(src: str):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        stamp = obj + ".sha256"
+        want = _unit_hash(src)
+        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
+            return obj, False
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         if verbose and r.stderr:
             print(r.stderr, file=sys.stderr)
-        return obj
+        with open(stamp, "w") as f:
+            f.write(want)
+        return obj, True
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
-        f.write(want)
+        results = list(ex.map(compile_one, SOURCES))
+    objs = [o for o, _ in results]
+    if not os.path.exists(LIB) or any(changed for _, changed in results):
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

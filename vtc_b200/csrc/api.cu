@@ -16,16 +16,19 @@ std::atomic<uint64_t> g_launch_count{0};
 
 namespace {
 
-float guard_rel_for(int precision) {
-  // Bounds on |tensor-core dot - exact dot| / (|q| |x|); see DESIGN.md "guard band".
-  //   BF16 : products of bf16 are exact in fp32, only the fp32 accumulation of K/16 MMAs errs.
-  //   EXACT: 3-term bf16 split drops <= 3 * 2^-18 of each product, plus 3x the accumulation.
+// Bound on |tensor-core dot - exact dot| / (|q| |x|) for operands of padded depth Kp; see
+// DESIGN.md "guard band".  Each of the Kp/16 accumulation steps of the fp32 accumulator may lose
+// up to 2 ulp (2^-23) of |q||x| (measured total on B200: <= 1.8e-7 at K = 768).
+//   BF16 : products of bf16 are exact in fp32, so that is the whole error;
+//   EXACT: the 3-term bf16 split additionally drops <= 3 * 2^-18 (1.15e-5) of each product.
+float guard_rel_for(int precision, int Kp) {
   const char* e = getenv(precision == VTC_PREC_BF16 ? "VTC_GUARD_REL_BF16" : "VTC_GUARD_REL_EXACT");
   if (e && *e) {
     const float v = (float)atof(e);
     if (v > 0.f) return v;
   }
-  return precision == VTC_PREC_BF16 ? 6.103515625e-05f /* 2^-14 */ : 1.220703125e-04f /* 2^-13 */;
+  const float accum = (float)(Kp / 16 + 8) * 1.1920929e-07f;
+  return precision == VTC_PREC_BF16 ? accum : 1.2e-05f + accum;
 }
 
 bool valid_dtype(int d) { return d == VTC_F32 || d == VTC_BF16; }
@@ -52,7 +55,7 @@ struct RankWs {
   __nv_bfloat16 *opQ, *opG;
   double *sq64, *dgt;
   float* sq32;
-  unsigned int* scalars;  // [0] max_sq_bits, [1] amb_count, [2] overflow
+  unsigned int* scalars;  // [0] max_sq_bits, [2] overflow, [64..] per-CTA list segment counts
   float2* thr;
   int* rank_tmp;
   int2* amb;
@@ -70,12 +73,12 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   memset(&r, 0, sizeof(r));
   r.sq64 = ws.take<double>(M);
   r.dgt = ws.take<double>(N);
-  r.scalars = ws.take<unsigned int>(64);
+  r.scalars = ws.take<unsigned int>(64 + 256);
   if (precision != VTC_PREC_BRUTE) {
     const OperandPlan o = plan_operands(D, dtype, precision);
     r.opQ = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
     r.opG = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
-    r.sq32 = ws.take<float>(M);
+    r.sq32 = ws.take<float>(round_up<int64_t>(M, tc::BN));
     r.thr = ws.take<float2>(N);
     r.rank_tmp = ws.take<int>(N);
     if (sizing) {
@@ -106,7 +109,7 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   RankWs w = carve_rank(ws, N, M, D, dtype, precision, false);
   if (!ws.ok() || !w.sq64 || !w.dgt || !w.scalars) return VTC_ERR_WORKSPACE;
   const bool in_bf16 = dtype == VTC_BF16;
-  cudaError_t e = cudaMemsetAsync(w.scalars, 0, 64 * sizeof(unsigned int), s);
+  cudaError_t e = cudaMemsetAsync(w.scalars, 0, (64 + 256) * sizeof(unsigned int), s);
   if (e != cudaSuccess) return cuda_err(e);
 
   if (precision == VTC_PREC_BRUTE || M == 0) {
@@ -141,8 +144,11 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     ex = ExactArgs{w.opQ, w.opG, o.Kp, o.Kp, true, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
   // 2. canonical norms, ground-truth scores, guard band
   VTC_RETURN_IF_ERROR(launch_sqnorm64(ex.G, ex.bf16, M, D, ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
-  VTC_RETURN_IF_ERROR(
-      launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0], guard_rel_for(precision), s));
+  VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0],
+                                      guard_rel_for(precision, o.Kp), s));
+  // per-column epilogue bias: ||x_j||^2 (L2) or 0 (DOT); padding columns are +inf (never counted)
+  VTC_RETURN_IF_ERROR(launch_fill_bias(w.sq32, metric == VTC_METRIC_L2 ? w.sq32 : nullptr, M,
+                                       round_up<int64_t>(M, tc::BN), INFINITY, s));
   if (gt_score_out) {
     e = cudaMemcpyAsync(gt_score_out, w.dgt, sizeof(double) * N, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return cuda_err(e);
@@ -153,18 +159,18 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   tc::Params p;
   memset(&p, 0, sizeof(p));
   p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
-  p.col_bias = metric == VTC_METRIC_L2 ? w.sq32 : nullptr;
+  p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
-  p.oob_bias = INFINITY;
-  p.thr = w.thr, p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_count = &w.scalars[1];
-  p.amb_cap = (unsigned int)w.amb_cap;
+  p.thr = w.thr, p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_seg_count = &w.scalars[64];
   const tc::Plan pl = tc::plan_tiles(p, 64, tc::choose_cluster(N, M));
+  if (pl.grid > 256) return VTC_ERR_UNSUPPORTED_SHAPE;
+  p.amb_seg_cap = (unsigned int)(w.amb_cap / (size_t)pl.grid);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
   VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
   // 4. exact re-check of the guard-band pairs; brute force if the list overflowed
-  VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[1], (unsigned int)w.amb_cap, w.dgt,
+  VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[64], pl.grid, p.amb_seg_cap, w.dgt,
                                      w.rank_tmp, &w.scalars[2], s));
   VTC_RETURN_IF_ERROR(launch_zero_if_flag(w.rank_tmp, N, &w.scalars[2], s));
   VTC_RETURN_IF_ERROR(launch_rank_brute(ex, w.dgt, w.rank_tmp, &w.scalars[2], s));
@@ -190,7 +196,7 @@ TopkWs carve_topk(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   const int prec = precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision;
   const OperandPlan o = plan_operands(D, dtype, prec);
   t.sq64 = ws.take<double>(M);
-  t.sq32 = ws.take<float>(M);
+  t.sq32 = ws.take<float>(round_up<int64_t>(M, tc::BN));
   t.scalars = ws.take<unsigned int>(64);
   t.row_flag = ws.take<unsigned int>(N);
   t.opQ = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
@@ -227,7 +233,7 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     a.ex = ExactArgs{w.opQ, w.opG, o.Kp, o.Kp, true, N, M, D, w.sq64, nullptr, 0, col_offset, metric};
   a.pool_val = w.pool_val, a.pool_idx = w.pool_idx, a.pool_meta = w.pool_meta;
   a.pool = tc::TOPK_POOL, a.k = k;
-  a.guard_rel = guard_rel_for(precision);
+  a.guard_rel = guard_rel_for(precision, o.Kp);
   a.max_sq_bits = &w.scalars[0];
   a.out_val = out_val, a.out_idx = out_idx, a.row_flag = w.row_flag;
 
@@ -248,9 +254,10 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   tc::Params p;
   memset(&p, 0, sizeof(p));
   p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
-  p.col_bias = metric == VTC_METRIC_L2 ? w.sq32 : nullptr;
+  VTC_RETURN_IF_ERROR(launch_fill_bias(w.sq32, metric == VTC_METRIC_L2 ? w.sq32 : nullptr, M,
+                                       round_up<int64_t>(M, tc::BN), INFINITY, s));
+  p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
-  p.oob_bias = INFINITY;
   p.pool_val = w.pool_val, p.pool_idx = w.pool_idx, p.pool_meta = w.pool_meta;
   const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, tc::choose_cluster(N, M));
   a.splits = p.g_splits;
@@ -266,12 +273,14 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
 // out[N,M] = act(scale * A B^T + bias) + residual, fp32 in/out.
 struct GemmWs {
   __nv_bfloat16 *opA, *opB;
+  float* bias;  // padded per-column bias
 };
 GemmWs carve_gemm(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int precision) {
   const OperandPlan o = plan_operands(D, dtype, precision);
   GemmWs g;
   g.opA = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
   g.opB = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
+  g.bias = ws.take<float>(round_up<int64_t>(M, tc::BN));
   return g;
 }
 
@@ -296,7 +305,8 @@ int gemm_store_impl(const void* A, const void* B, int64_t N, int64_t M, int D, i
   tc::Params p;
   memset(&p, 0, sizeof(p));
   p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
-  p.col_bias = bias, p.scale_ptr = scale_ptr, p.scale = 1.f, p.oob_bias = 0.f;
+  VTC_RETURN_IF_ERROR(launch_fill_bias(g.bias, bias, M, round_up<int64_t>(M, tc::BN), 0.f, s));
+  p.col_bias = g.bias, p.scale_ptr = scale_ptr, p.scale = 1.f;
   p.out = out, p.ldo = ldo, p.residual = residual, p.act = act;
   const tc::Plan pl = tc::plan_tiles(p, 1, 1);
   CUtensorMap tmA, tmB;
@@ -310,6 +320,7 @@ struct NceWs {
   __nv_bfloat16 *a_as_a, *b_as_b, *b_as_a, *a_as_b;
   float2 *part_row, *part_col;
   float* diag_raw;
+  float* bias;  // zeros, -inf padding
 };
 constexpr int kNceMaxSplits = 8;
 NceWs carve_nce(Workspace& ws, int64_t n, int D, int dtype, int precision) {
@@ -328,6 +339,7 @@ NceWs carve_nce(Workspace& ws, int64_t n, int D, int dtype, int precision) {
   w.part_row = ws.take<float2>((size_t)kNceMaxSplits * n);
   w.part_col = ws.take<float2>((size_t)kNceMaxSplits * n);
   w.diag_raw = ws.take<float>(n);
+  w.bias = ws.take<float>(round_up<int64_t>(n, tc::BN));
   return w;
 }
 
@@ -350,12 +362,13 @@ int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, 
     VTC_RETURN_IF_ERROR(launch_prep_operand(B, in_bf16, n, D, D, ma, w.b_as_a, o.Kp, s));
     VTC_RETURN_IF_ERROR(launch_prep_operand(A, in_bf16, n, D, D, mb, w.a_as_b, o.Kp, s));
   }
+  VTC_RETURN_IF_ERROR(launch_fill_bias(w.bias, nullptr, n, round_up<int64_t>(n, tc::BN), -INFINITY, s));
   for (int dir = 0; dir < 2; ++dir) {
     tc::Params p;
     memset(&p, 0, sizeof(p));
     p.N = n, p.M = n, p.num_kb = o.Kp / tc::BK;
     p.scale_ptr = scale, p.scale = 1.4426950408889634f;  // logits in log2 units
-    p.oob_bias = -INFINITY;
+    p.col_bias = w.bias;
     p.lse_part = dir == 0 ? w.part_row : w.part_col;
     p.diag = dir == 0 ? w.diag_raw : nullptr;
     p.diag_offset = 0;
@@ -509,7 +522,8 @@ int vtc_rank_finalize(int32_t* rank0, const double* gt_score, int64_t N, int64_t
                       size_t hist_ws_bytes, vtc_stream_t stream) {
   if (!rank0 || N < 0 || nk < 0 || nk > 8 || (nk > 0 && (!k_vals || !hits)))
     return VTC_ERR_INVALID_ARG;
-  if (medr && (!hist_ws || hist_ws_bytes < 65536 * sizeof(unsigned int))) return VTC_ERR_WORKSPACE;
+  if (medr && (!hist_ws || hist_ws_bytes < (3 * 65536 + 8) * sizeof(unsigned int)))
+    return VTC_ERR_WORKSPACE;
   return launch_rank_finalize(rank0, gt_score, N, M_total, k_vals, nk, hits, medr, hist_ws,
                               (cudaStream_t)stream);
 }

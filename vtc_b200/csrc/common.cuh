@@ -70,6 +70,61 @@ __device__ __forceinline__ double to_f64(__nv_bfloat16 v) { return (double)__bfl
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// 8 consecutive elements widened to double with 128-bit loads (p must be 16-byte aligned).
+__device__ __forceinline__ void load8_f64(const float* p, double (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void load8_f64(const __nv_bfloat16* p, double (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = (double)__uint_as_float(w[i] << 16);
+    v[2 * i + 1] = (double)__uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <typename T>
+__device__ __forceinline__ bool aligned16(const T* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+// fp64-sequential dot product: acc = fma(q[k], x[k], acc) for k = 0..D-1, in that order.
+template <typename T>
+__device__ __forceinline__ double dot_seq64(const T* __restrict__ q, const T* __restrict__ x, int D) {
+  double acc = 0.0;
+  int k = 0;
+  if (aligned16(q) && aligned16(x)) {
+    for (; k + 8 <= D; k += 8) {
+      double a[8], b[8];
+      load8_f64(q + k, a);
+      load8_f64(x + k, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fma(a[i], b[i], acc);
+    }
+  }
+  for (; k < D; ++k) acc = fma(to_f64(q[k]), to_f64(x[k]), acc);
+  return acc;
+}
+template <typename T>
+__device__ __forceinline__ double sq_seq64(const T* __restrict__ x, int D) {
+  double acc = 0.0;
+  int k = 0;
+  if (aligned16(x)) {
+    for (; k + 8 <= D; k += 8) {
+      double a[8];
+      load8_f64(x + k, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fma(a[i], a[i], acc);
+    }
+  }
+  for (; k < D; ++k) {
+    const double v = to_f64(x[k]);
+    acc = fma(v, v, acc);
+  }
+  return acc;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -23,12 +23,7 @@ __global__ void sqnorm64_kernel(const T* __restrict__ X, int64_t rows, int D, in
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float mine = 0.f;
   if (r < rows) {
-    const T* x = X + r * ld;
-    double acc = 0.0;
-    for (int k = 0; k < D; ++k) {
-      const double v = to_f64(x[k]);
-      acc = fma(v, v, acc);
-    }
+    const double acc = sq_seq64(X + r * ld, D);
     if (sq64) sq64[r] = acc;
     const float f = (float)acc;
     if (sq32) sq32[r] = f;
@@ -60,9 +55,7 @@ __global__ void gt_score_kernel(const T* __restrict__ Q, int64_t ldq, const T* _
   } else {
     const int64_t g = (gt ? gt[t] : t + row_offset) - col_offset;
     if (g >= 0 && g < M) {
-      const T* x = G + g * ldg;
-      double acc = 0.0;
-      for (int k = 0; k < D; ++k) acc = fma(to_f64(q[k]), to_f64(x[k]), acc);
+      const double acc = dot_seq64(q, G + g * ldg, D);
       d0 = metric == VTC_METRIC_L2 ? sq64[g] - 2.0 * acc : -acc;
     } else {
       d0 = nan("");
@@ -70,11 +63,7 @@ __global__ void gt_score_kernel(const T* __restrict__ Q, int64_t ldq, const T* _
   }
   if (gt_out) gt_out[t] = d0;
   if (thr) {
-    double qq = 0.0;
-    for (int k = 0; k < D; ++k) {
-      const double v = to_f64(q[k]);
-      qq = fma(v, v, qq);
-    }
+    const double qq = sq_seq64(q, D);
     const double qn = sqrt(qq);
     const double gmax_sq = (double)__uint_as_float(*max_sq_bits);
     const double gn = sqrt(gmax_sq);
@@ -172,36 +161,49 @@ rank_brute_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ G,
 }
 
 // ------------------------------------------------------------------------------------------------
-// re-check of the ambiguous (query, gallery) pairs emitted by the tensor-core pass
+// re-check of the ambiguous column groups emitted by the tensor-core pass
 // ------------------------------------------------------------------------------------------------
+// The list has one segment per CTA of the tensor-core launch; entry (t, j0) means "row t has a
+// score inside the guard band among gallery columns [j0, j0 + 8)": the tensor-core pass added
+// nothing for that group, so all 8 columns are decided here in canonical arithmetic.
+constexpr int RECHECK_GROUP = 8;
+constexpr int RECHECK_PARTS = 4;  // blocks per segment
+
 template <typename T>
-__global__ void recheck_kernel(const int2* __restrict__ list, const unsigned int* __restrict__ count,
-                               unsigned int cap, const T* __restrict__ Q, int64_t ldq,
-                               const T* __restrict__ G, int64_t ldg,
-                               const double* __restrict__ sq64, const double* __restrict__ dgt,
-                               int64_t N, int64_t M, int D, const int64_t* __restrict__ gt,
-                               int64_t row_offset, int64_t col_offset, int metric,
-                               int* __restrict__ rank, unsigned int* __restrict__ overflow) {
-  const unsigned int n = *count;
-  if (n > cap) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1u;
+__global__ void __launch_bounds__(256)
+recheck_kernel(const int2* __restrict__ list, const unsigned int* __restrict__ seg_count,
+               unsigned int seg_cap, const T* __restrict__ Q, int64_t ldq,
+               const T* __restrict__ G, int64_t ldg, const double* __restrict__ sq64,
+               const double* __restrict__ dgt, int64_t N, int64_t M, int D,
+               const int64_t* __restrict__ gt, int64_t row_offset, int64_t col_offset, int metric,
+               int* __restrict__ rank, unsigned int* __restrict__ overflow) {
+  const int seg = blockIdx.x / RECHECK_PARTS, part = blockIdx.x % RECHECK_PARTS;
+  const unsigned int n = seg_count[seg];
+  if (n > seg_cap) {
+    if (part == 0 && threadIdx.x == 0) *overflow = 1u;
     return;  // the brute-force fallback recomputes everything
   }
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int2 e = list[i];
-    const int64_t t = e.x, jl = e.y;
+  const int2* seg_list = list + (size_t)seg * seg_cap;
+  for (unsigned int u = part * blockDim.x + threadIdx.x; u < n * RECHECK_GROUP;
+       u += RECHECK_PARTS * blockDim.x) {
+    const int2 e = seg_list[u / RECHECK_GROUP];
+    const int64_t t = e.x, jl = (int64_t)e.y + (u % RECHECK_GROUP);
     if (t >= N || jl >= M) continue;  // zero-padded tile rows / columns
     const int64_t g = gt ? gt[t] : t + row_offset;
     const int64_t jg = jl + col_offset;
     if (jg == g) continue;
-    const T* q = Q + t * ldq;
-    const T* x = G + jl * ldg;
-    double acc = 0.0;
-    for (int k = 0; k < D; ++k) acc = fma(to_f64(q[k]), to_f64(x[k]), acc);
+    const double acc = dot_seq64(Q + t * ldq, G + jl * ldg, D);
     const double d = metric == VTC_METRIC_L2 ? sq64[jl] - 2.0 * acc : -acc;
     const double d0 = dgt[t];
     if ((d < d0) || (d == d0 && jg < g)) atomicAdd(&rank[t], 1);
   }
+}
+
+// dst[j] = j < M ? (src ? src[j] : 0) : pad   for j in [0, Mpad)   (in place allowed)
+__global__ void fill_bias_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t M,
+                                 int64_t Mpad, float pad) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < Mpad) dst[j] = j < M ? (src ? src[j] : 0.f) : pad;
 }
 
 __global__ void zero_if_flag_kernel(int* __restrict__ buf, int64_t n,
@@ -261,72 +263,82 @@ __global__ void rank_finalize_kernel(int* __restrict__ rank, const double* __res
     atomicAdd(&hits[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
-// median(rank)+1 with numpy semantics by a two-level 16-bit radix select; one block.
-// hist: 65536 uint32 bins of workspace.
-__device__ __forceinline__ void radix_find(const unsigned int* hist, const unsigned int* part,
-                                           unsigned int target, unsigned int* bin_out,
-                                           unsigned int* rem_out) {
-  unsigned int run = 0;
-  int b = 0;
-  while (b < 1023 && run + part[b] <= target) run += part[b++];
-  int bin = b * 64;
-  while (bin < b * 64 + 63 && run + hist[bin] <= target) run += hist[bin++];
-  *bin_out = (unsigned int)bin;
-  *rem_out = target - run;
+// median(rank)+1 with numpy semantics by a two-level radix select over multi-block histograms.
+// ws layout (uint32): hist0[65536] | hist1a[65536] | hist1b[65536] | sel[8]
+//   level 0 bins by rank >> shift (shift chosen so that bins cover [0, M_total]), level 1 by the
+//   low `shift` bits of the ranks inside the selected bucket(s).
+constexpr int MED_BINS = 65536;
+
+__global__ void med_hist0_kernel(const int* __restrict__ rank, int64_t N, int shift,
+                                 unsigned int* __restrict__ hist0) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned int b = ((unsigned int)rank[i]) >> shift;
+    if (b >= MED_BINS) b = MED_BINS - 1;
+    atomicAdd(&hist0[b], 1u);
+  }
+}
+
+// one block: locate the bin holding order statistic `target` (exclusive prefix <= target)
+__device__ void med_find(const unsigned int* __restrict__ hist, unsigned int target,
+                         unsigned int* part /*[1024] smem*/, unsigned int* bin_out,
+                         unsigned int* rem_out) {
+  const int tid = threadIdx.x;
+  unsigned int s = 0;
+  for (int i = 0; i < MED_BINS / 1024; ++i) s += hist[tid * (MED_BINS / 1024) + i];
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int run = 0;
+    int b = 0;
+    while (b < 1023 && run + part[b] <= target) run += part[b++];
+    int bin = b * (MED_BINS / 1024);
+    const int last = bin + MED_BINS / 1024 - 1;
+    while (bin < last && run + hist[bin] <= target) run += hist[bin++];
+    *bin_out = (unsigned int)bin;
+    *rem_out = target - run;
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024)
-rank_median_kernel(const int* __restrict__ rank, int64_t N, unsigned int* __restrict__ hist,
-                   double* __restrict__ medr) {
+med_select0_kernel(const unsigned int* __restrict__ hist0, int64_t N, unsigned int* __restrict__ sel) {
   __shared__ unsigned int part[1024];
-  __shared__ unsigned int sel[2], rem[2], res[2];
-  const int tid = threadIdx.x;
-  if (N <= 0) {
-    if (tid == 0) *medr = nan("");
-    return;
-  }
-  // level 0: bits [16,32) of every rank
-  for (int i = tid; i < 65536; i += 1024) hist[i] = 0;
-  __syncthreads();
-  for (int64_t i = tid; i < N; i += 1024) atomicAdd(&hist[((unsigned int)rank[i]) >> 16], 1u);
-  __syncthreads();
-  {
-    unsigned int s = 0;
-    for (int i = 0; i < 64; ++i) s += hist[tid * 64 + i];
-    part[tid] = s;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    radix_find(hist, part, (unsigned int)((N - 1) / 2), &sel[0], &rem[0]);
-    radix_find(hist, part, (unsigned int)(N / 2), &sel[1], &rem[1]);
-  }
-  __syncthreads();
-  // level 1: bits [0,16) of the ranks inside the selected bucket(s)
-  for (int w = 0; w < 2; ++w) {
-    if (w == 0 || sel[1] != sel[0]) {
-      const unsigned int want = sel[w];
-      __syncthreads();
-      for (int i = tid; i < 65536; i += 1024) hist[i] = 0;
-      __syncthreads();
-      for (int64_t i = tid; i < N; i += 1024) {
-        const unsigned int r = (unsigned int)rank[i];
-        if ((r >> 16) == want) atomicAdd(&hist[r & 0xffffu], 1u);
-      }
-      __syncthreads();
-      unsigned int s = 0;
-      for (int i = 0; i < 64; ++i) s += hist[tid * 64 + i];
-      part[tid] = s;
-      __syncthreads();
-    }
-    if (tid == 0) {
-      unsigned int bin, r2;
-      radix_find(hist, part, rem[w], &bin, &r2);
-      res[w] = (sel[w] << 16) | bin;
-    }
-    __syncthreads();
-  }
-  if (tid == 0) *medr = 0.5 * ((double)res[0] + (double)res[1]) + 1.0;
+  med_find(hist0, (unsigned int)((N - 1) / 2), part, &sel[0], &sel[1]);
+  med_find(hist0, (unsigned int)(N / 2), part, &sel[2], &sel[3]);
 }
+
+__global__ void med_hist1_kernel(const int* __restrict__ rank, int64_t N, int shift,
+                                 const unsigned int* __restrict__ sel,
+                                 unsigned int* __restrict__ hist1a,
+                                 unsigned int* __restrict__ hist1b) {
+  const unsigned int ba = sel[0], bb = sel[2];
+  const unsigned int mask = (1u << shift) - 1u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned int r = (unsigned int)rank[i];
+    unsigned int b = r >> shift;
+    if (b >= MED_BINS) b = MED_BINS - 1;
+    if (b == ba) atomicAdd(&hist1a[r & mask], 1u);
+    if (b == bb && bb != ba) atomicAdd(&hist1b[r & mask], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+med_select1_kernel(const unsigned int* __restrict__ hist1a, const unsigned int* __restrict__ hist1b,
+                   int shift, const unsigned int* __restrict__ sel, double* __restrict__ medr) {
+  __shared__ unsigned int part[1024];
+  __shared__ unsigned int lo[2], rem[2];
+  med_find(hist1a, sel[1], part, &lo[0], &rem[0]);
+  med_find(sel[2] != sel[0] ? hist1b : hist1a, sel[3], part, &lo[1], &rem[1]);
+  if (threadIdx.x == 0) {
+    const double v0 = (double)((sel[0] << shift) | lo[0]);
+    const double v1 = (double)((sel[2] << shift) | lo[1]);
+    *medr = 0.5 * (v0 + v1) + 1.0;
+  }
+}
+
+__global__ void med_nan_kernel(double* medr) { *medr = nan(""); }
 
 // ------------------------------------------------------------------------------------------------
 // host launchers
@@ -381,21 +393,31 @@ int launch_rank_brute(const ExactArgs& a, const double* dgt, int* rank,
 }
 
 template <typename T>
-static int launch_recheck_t(const ExactArgs& a, const int2* list, const unsigned int* count,
-                            unsigned int cap, const double* dgt, int* rank, unsigned int* overflow,
-                            cudaStream_t s) {
-  recheck_kernel<T><<<kNumSMs * 8, 128, 0, s>>>(list, count, cap, (const T*)a.Q, a.ldq,
-                                                (const T*)a.G, a.ldg, a.sq64, dgt, a.N, a.M, a.D,
-                                                a.gt, a.row_offset, a.col_offset, a.metric, rank,
-                                                overflow);
+static int launch_recheck_t(const ExactArgs& a, const int2* list, const unsigned int* seg_count,
+                            int nseg, unsigned int seg_cap, const double* dgt, int* rank,
+                            unsigned int* overflow, cudaStream_t s) {
+  if (nseg <= 0) return VTC_OK;
+  recheck_kernel<T><<<nseg * RECHECK_PARTS, 256, 0, s>>>(list, seg_count, seg_cap, (const T*)a.Q,
+                                                        a.ldq, (const T*)a.G, a.ldg, a.sq64, dgt,
+                                                        a.N, a.M, a.D, a.gt, a.row_offset,
+                                                        a.col_offset, a.metric, rank, overflow);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }
-int launch_recheck(const ExactArgs& a, const int2* list, const unsigned int* count,
-                   unsigned int cap, const double* dgt, int* rank, unsigned int* overflow,
+int launch_recheck(const ExactArgs& a, const int2* list, const unsigned int* seg_count, int nseg,
+                   unsigned int seg_cap, const double* dgt, int* rank, unsigned int* overflow,
                    cudaStream_t s) {
-  return a.bf16 ? launch_recheck_t<__nv_bfloat16>(a, list, count, cap, dgt, rank, overflow, s)
-                : launch_recheck_t<float>(a, list, count, cap, dgt, rank, overflow, s);
+  return a.bf16 ? launch_recheck_t<__nv_bfloat16>(a, list, seg_count, nseg, seg_cap, dgt, rank,
+                                                  overflow, s)
+                : launch_recheck_t<float>(a, list, seg_count, nseg, seg_cap, dgt, rank, overflow, s);
+}
+
+int launch_fill_bias(float* dst, const float* src, int64_t M, int64_t Mpad, float pad,
+                     cudaStream_t s) {
+  if (Mpad <= 0) return VTC_OK;
+  fill_bias_kernel<<<(unsigned)ceil_div<int64_t>(Mpad, 256), 256, 0, s>>>(dst, src, M, Mpad, pad);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
 }
 
 int launch_zero_if_flag(int* buf, int64_t n, const unsigned int* flag, cudaStream_t s) {
@@ -431,7 +453,29 @@ int launch_rank_finalize(int* rank, const double* dgt, int64_t N, int64_t M_tota
     VTC_LAUNCH_CHECK();
   }
   if (medr) {
-    rank_median_kernel<<<1, 1024, 0, s>>>(rank, N, (unsigned int*)hist_ws, medr);
+    if (N <= 0) {
+      med_nan_kernel<<<1, 1, 0, s>>>(medr);
+      VTC_LAUNCH_CHECK();
+      return VTC_OK;
+    }
+    unsigned int* h0 = (unsigned int*)hist_ws;
+    unsigned int* h1a = h0 + MED_BINS;
+    unsigned int* h1b = h1a + MED_BINS;
+    unsigned int* sel = h1b + MED_BINS;
+    cudaError_t e = cudaMemsetAsync(h0, 0, (3 * MED_BINS + 8) * sizeof(unsigned int), s);
+    if (e != cudaSuccess) return cuda_err(e);
+    int shift = 0;  // level-0 bins must cover ranks up to M_total (and any int32 beyond, clamped)
+    while (shift < 16 && (M_total >> shift) >= MED_BINS) ++shift;
+    const unsigned blocks = (unsigned)(ceil_div<int64_t>(N, 256) < kNumSMs * 4
+                                           ? ceil_div<int64_t>(N, 256)
+                                           : kNumSMs * 4);
+    med_hist0_kernel<<<blocks, 256, 0, s>>>(rank, N, shift, h0);
+    VTC_LAUNCH_CHECK();
+    med_select0_kernel<<<1, 1024, 0, s>>>(h0, N, sel);
+    VTC_LAUNCH_CHECK();
+    med_hist1_kernel<<<blocks, 256, 0, s>>>(rank, N, shift, sel, h1a, h1b);
+    VTC_LAUNCH_CHECK();
+    med_select1_kernel<<<1, 1024, 0, s>>>(h1a, h1b, shift, sel, medr);
     VTC_LAUNCH_CHECK();
   }
   return VTC_OK;

@@ -69,8 +69,7 @@ constexpr int SEL_MAX_CAND = 8 * 32;  // splits <= 8, pool = 32
 template <typename T>
 __device__ __forceinline__ double exact_score(const T* __restrict__ q, const T* __restrict__ x, int D,
                                               int metric, double sq) {
-  double acc = 0.0;
-  for (int k = 0; k < D; ++k) acc = fma(to_f64(q[k]), to_f64(x[k]), acc);
+  const double acc = dot_seq64(q, x, D);
   return metric == VTC_METRIC_L2 ? sq - 2.0 * acc : -acc;
 }
 
@@ -114,11 +113,7 @@ topk_select_kernel(TopkSelectArgs a) {
     cj[w][c] = j;
   }
   __syncwarp();
-  double qq = 0.0;  // every lane computes it (cheap, keeps the warp convergent)
-  for (int k = 0; k < a.ex.D; ++k) {
-    const double v = to_f64(q[k]);
-    qq = fma(v, v, qq);
-  }
+  const double qq = sq_seq64(q, a.ex.D);  // every lane computes it (keeps the warp convergent)
   double dk = -INFINITY;  // exact score of the last selected candidate
   int found = 0;
   for (int r = 0; r < a.k; ++r) {
@@ -202,11 +197,7 @@ topk_brute_rows_kernel(TopkSelectArgs a) {
     lj[tid][pos] = (int)j;
     if (fill < k) ++fill;
   }
-  double qq = 0.0;
-  for (int kk = 0; kk < a.ex.D; ++kk) {
-    const double v = to_f64(q[kk]);
-    qq = fma(v, v, qq);
-  }
+  const double qq = sq_seq64(q, a.ex.D);
   int head = 0;
   for (int r = 0; r < k; ++r) {
     double bd = head < fill ? ld[tid][head] : 0.0;

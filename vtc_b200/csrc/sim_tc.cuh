@@ -21,17 +21,18 @@ struct Params {
   int q_tiles, g_tiles;  // ceil(N/128), ceil(M/256)
   int g_splits;          // gallery is cut into g_splits contiguous tile ranges
   int tiles_per_split;
-  // score = scale * acc + col_bias[j]   (col_bias NULL = 0; out-of-range columns use oob_bias)
+  // score = scale * acc + col_bias[j].  col_bias is REQUIRED and padded to a multiple of BN
+  // entries; the padding holds the epilogue's neutral value (+inf rank/top-k, -inf LSE, 0 store).
   const float* col_bias;
   const float* scale_ptr;  // optional device scalar multiplied into `scale`
   float scale;
-  float oob_bias;
   // EPI_RANK
   const float2* thr;  // [N] (lo, hi) guard band around d(t, gt)
   int* rank;          // [N] += #{j : score < lo}
-  int2* amb_list;     // (t, j) pairs with lo <= score <= hi
-  unsigned int* amb_count;
-  unsigned int amb_cap;
+  int2* amb_list;     // (t, j0): row t has a score in [lo, hi] among columns [j0, j0 + 8);
+                      // one segment of amb_seg_cap entries per CTA
+  unsigned int* amb_seg_count;  // [grid] entries each CTA wanted to push (may exceed the capacity)
+  unsigned int amb_seg_cap;
   // EPI_LSE  (score is the logit in log2 units: scale already includes log2(e))
   float2* lse_part;     // [g_splits, N] running (max, sum) in log2 domain
   float* diag;          // [N] raw accumulator of column t + diag_offset (nullable)

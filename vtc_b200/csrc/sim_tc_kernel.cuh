@@ -46,8 +46,7 @@ struct SmemLayout {
   static constexpr int kStageBytes = kRes ? B_TILE_BYTES : (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int kResBytes = kRes ? MAX_RES_KB * A_TILE_BYTES : 0;
   static constexpr int kStagesOff = kResBytes;
-  static constexpr int kBiasOff = kStagesOff + kStages * kStageBytes;  // 2 x 256 floats
-  static constexpr int kBarOff = kBiasOff + 2 * BN * 4;
+  static constexpr int kBarOff = kStagesOff + kStages * kStageBytes;
   static constexpr int kNumBars = 2 * kStages + MAX_RES_KB + 1 + 2 + 2;
   static constexpr int kTotal = kBarOff + 256;
   static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
@@ -66,6 +65,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // ------------------------------------------------------------------------------------ epilogues
 // Each epilogue thread owns one tile row (= TMEM lane).  `begin_item` / `chunk` / `end_item`.
+// `bias` points at 32 consecutive entries of the per-column bias in GLOBAL memory (padded to a
+// multiple of 256 columns by the host, out-of-range columns hold the epilogue's neutral value), so
+// the loads are warp-uniform 128-bit L1 hits and the epilogue warps never synchronise with each
+// other.  Code size matters here (one warp per scheduler, 32 KB of L1.5 I-cache): rare paths are
+// kept tiny and out of line.
+
+constexpr int RANK_GROUP = 8;  // columns re-checked together when any of them is in the guard band
 
 struct RankEpi {
   float lo, hi;
@@ -81,33 +87,45 @@ struct RankEpi {
       hi = th.y;
     }
   }
+  // rare: this row has a score inside the guard band among columns [j, j+8): hand the whole group
+  // to the fp64 re-check (its definite count is NOT added here).  List segments are per CTA, slots
+  // come from a shared-memory counter, so there is no global atomic hot spot.
+  __device__ __noinline__ void push_group(const Params& p, unsigned int* seg_count, int64_t j) {
+    const unsigned int slot = atomicAdd(seg_count, 1u);
+    if (slot < p.amb_seg_cap)
+      p.amb_list[(size_t)blockIdx.x * p.amb_seg_cap + slot] = make_int2((int)t, (int)j);
+  }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
-                                        const float* __restrict__ cb, float scale, int64_t jbase) {
-    // counts kept as floats: (d < lo) ? 1.f : 0.f is one FSET, the add one FADD (exact, <= 32)
-    float lt = 0.f, le = 0.f;
+                                        const float* __restrict__ bias, float scale, int64_t jbase,
+                                        unsigned int* seg_count) {
+    // counts kept as floats: (d < lo) ? 1.f : 0.f is one FSET, the add one FADD (exact, <= 8)
+    float csum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = reinterpret_cast<const float4*>(cb)[i];
-      const float d0 = fmaf(scale, __uint_as_float(v[4 * i + 0]), b.x);
-      const float d1 = fmaf(scale, __uint_as_float(v[4 * i + 1]), b.y);
-      const float d2 = fmaf(scale, __uint_as_float(v[4 * i + 2]), b.z);
-      const float d3 = fmaf(scale, __uint_as_float(v[4 * i + 3]), b.w);
-      lt += (d0 < lo ? 1.f : 0.f) + (d1 < lo ? 1.f : 0.f) + (d2 < lo ? 1.f : 0.f) +
-            (d3 < lo ? 1.f : 0.f);
-      le += (d0 <= hi ? 1.f : 0.f) + (d1 <= hi ? 1.f : 0.f) + (d2 <= hi ? 1.f : 0.f) +
-            (d3 <= hi ? 1.f : 0.f);
+    for (int g = 0; g < 32 / RANK_GROUP; ++g) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g + 1);
+      const float d0 = fmaf(scale, __uint_as_float(v[8 * g + 0]), b0.x);
+      const float d1 = fmaf(scale, __uint_as_float(v[8 * g + 1]), b0.y);
+      const float d2 = fmaf(scale, __uint_as_float(v[8 * g + 2]), b0.z);
+      const float d3 = fmaf(scale, __uint_as_float(v[8 * g + 3]), b0.w);
+      const float d4 = fmaf(scale, __uint_as_float(v[8 * g + 4]), b1.x);
+      const float d5 = fmaf(scale, __uint_as_float(v[8 * g + 5]), b1.y);
+      const float d6 = fmaf(scale, __uint_as_float(v[8 * g + 6]), b1.z);
+      const float d7 = fmaf(scale, __uint_as_float(v[8 * g + 7]), b1.w);
+      const float lt = ((d0 < lo ? 1.f : 0.f) + (d1 < lo ? 1.f : 0.f)) +
+                       ((d2 < lo ? 1.f : 0.f) + (d3 < lo ? 1.f : 0.f)) +
+                       ((d4 < lo ? 1.f : 0.f) + (d5 < lo ? 1.f : 0.f)) +
+                       ((d6 < lo ? 1.f : 0.f) + (d7 < lo ? 1.f : 0.f));
+      const float le = ((d0 <= hi ? 1.f : 0.f) + (d1 <= hi ? 1.f : 0.f)) +
+                       ((d2 <= hi ? 1.f : 0.f) + (d3 <= hi ? 1.f : 0.f)) +
+                       ((d4 <= hi ? 1.f : 0.f) + (d5 <= hi ? 1.f : 0.f)) +
+                       ((d6 <= hi ? 1.f : 0.f) + (d7 <= hi ? 1.f : 0.f));
+      if (le != lt)
+        push_group(p, seg_count, jbase + RANK_GROUP * g);
+      else
+        csum += lt;
     }
-    cnt += (int)lt;
-    if (le != lt) {  // rare: some score falls inside the guard band
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float d = fmaf(scale, __uint_as_float(v[i]), cb[i]);
-        if (d <= hi && !(d < lo)) {
-          const unsigned int pos = atomicAdd(p.amb_count, 1u);
-          if (pos < p.amb_cap) p.amb_list[pos] = make_int2((int)t, (int)(jbase + i));
-        }
-      }
-    }
+    cnt += (int)csum;
   }
   __device__ __forceinline__ void end_item(const Params& p, int) {
     if (t < p.N && cnt) atomicAdd(&p.rank[t], cnt);
@@ -125,12 +143,13 @@ struct LseEpi {
     jd = p.diag ? t + p.diag_offset : -1;
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
-                                        const float* __restrict__ cb, float scale, int64_t jbase) {
+                                        const float* __restrict__ bias, float scale, int64_t jbase,
+                                        unsigned int*) {
     float x[32];
     float cmax = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 b = reinterpret_cast<const float4*>(cb)[i];
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i);
       x[4 * i + 0] = fmaf(scale, __uint_as_float(v[4 * i + 0]), b.x);
       x[4 * i + 1] = fmaf(scale, __uint_as_float(v[4 * i + 1]), b.y);
       x[4 * i + 2] = fmaf(scale, __uint_as_float(v[4 * i + 2]), b.z);
@@ -164,7 +183,8 @@ struct StoreEpi {
   int64_t t;
   __device__ __forceinline__ void begin_item(const Params&, int64_t t_, int) { t = t_; }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
-                                        const float* __restrict__ cb, float scale, int64_t jbase) {
+                                        const float* __restrict__ bias, float scale, int64_t jbase,
+                                        unsigned int*) {
     if (t >= p.N) return;
     float* o = p.out + t * p.ldo + jbase;
     const float* r = p.residual ? p.residual + t * p.ldo + jbase : nullptr;
@@ -173,10 +193,15 @@ struct StoreEpi {
                      (!r || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     float y[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float z = fmaf(scale, __uint_as_float(v[i]), cb[i]);
-      if (p.act == 1) z = z / (1.f + __expf(-1.702f * z));  // QuickGELU: z * sigmoid(1.702 z)
-      y[i] = z;
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i);
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float z = fmaf(scale, __uint_as_float(v[4 * i + e]), bb[e]);
+        if (p.act == 1) z = z / (1.f + __expf(-1.702f * z));  // QuickGELU: z * sigmoid(1.702 z)
+        y[4 * i + e] = z;
+      }
     }
     if (vec) {
 #pragma unroll
@@ -212,7 +237,9 @@ struct TopkEpi {
     pi = p.pool_idx + slot;
     if (t >= p.N) tau = -INFINITY;  // padded rows never insert
   }
-  __device__ __forceinline__ void insert(float d, int j) {
+  // rare (~pool * ln(M / pool) times per row): keep the TOPK_POOL smallest scores seen so far
+  __device__ __noinline__ void insert(float d, int j) {
+    if (!(d < tau)) return;
     if (fill < TOPK_POOL) {
       pv[fill] = d;
       pi[fill] = j;
@@ -233,21 +260,26 @@ struct TopkEpi {
     tau = mx;
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
-                                        const float* __restrict__ cb, float scale, int64_t jbase) {
-    int any = 0;
+                                        const float* __restrict__ bias, float scale, int64_t jbase,
+                                        unsigned int*) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = reinterpret_cast<const float4*>(cb)[i];
-      any += (fmaf(scale, __uint_as_float(v[4 * i + 0]), b.x) < tau) +
-             (fmaf(scale, __uint_as_float(v[4 * i + 1]), b.y) < tau) +
-             (fmaf(scale, __uint_as_float(v[4 * i + 2]), b.z) < tau) +
-             (fmaf(scale, __uint_as_float(v[4 * i + 3]), b.w) < tau);
-    }
-    if (any) {
+    for (int g = 0; g < 4; ++g) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g + 1);
+      float d[8];
+      d[0] = fmaf(scale, __uint_as_float(v[8 * g + 0]), b0.x);
+      d[1] = fmaf(scale, __uint_as_float(v[8 * g + 1]), b0.y);
+      d[2] = fmaf(scale, __uint_as_float(v[8 * g + 2]), b0.z);
+      d[3] = fmaf(scale, __uint_as_float(v[8 * g + 3]), b0.w);
+      d[4] = fmaf(scale, __uint_as_float(v[8 * g + 4]), b1.x);
+      d[5] = fmaf(scale, __uint_as_float(v[8 * g + 5]), b1.y);
+      d[6] = fmaf(scale, __uint_as_float(v[8 * g + 6]), b1.z);
+      d[7] = fmaf(scale, __uint_as_float(v[8 * g + 7]), b1.w);
+      const float mn = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])),
+                             fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
+      if (mn < tau) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float d = fmaf(scale, __uint_as_float(v[i]), cb[i]);
-        if (d < tau) insert(d, (int)(jbase + i));
+        for (int i = 0; i < 8; ++i) insert(d[i], (int)(jbase + 8 * g + i));
       }
     }
   }
@@ -265,7 +297,6 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* res_a = smem;
   uint8_t* stages = smem + L::kStagesOff;
-  float* colbias = reinterpret_cast<float*>(smem + L::kBiasOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* full = bars;
   uint64_t* empty = full + L::kStages;
@@ -274,11 +305,13 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* tmem_full = a_empty + 1;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  unsigned int* seg_count = tmem_slot + 1;  // EPI_RANK: entries this CTA pushed to its list segment
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    *seg_count = 0;
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
@@ -393,7 +426,6 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int ew = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quarter this warp may read
     const int row = ew * 32 + lane;
     const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
-    const int etid = threadIdx.x - EPI_WARP0 * 32;
     const float scale = p.scale * (p.scale_ptr ? *p.scale_ptr : 1.0f);
     uint32_t as = 0, aphase = 0;
     Epi epi;
@@ -404,22 +436,17 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       epi.begin_item(p, (int64_t)qt * BM + row, split);
       for (int tile = t0; tile < t1; ++tile) {
         const int64_t j0 = (int64_t)tile * BN;
-        float* cb = colbias + as * BN;
-        for (int i = etid; i < BN; i += 128) {
-          const int64_t j = j0 + i;
-          cb[i] = j < p.M ? (p.col_bias ? p.col_bias[j] : 0.f) : p.oob_bias;
-        }
-        named_bar_sync(1, 128);
+        const float* bias = p.col_bias + j0;  // padded to a multiple of BN by the host
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_off + as * BN;
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
         tmem_ld_wait(va);
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < BN / 32; c += 2) {
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-          epi.chunk(p, va, cb + c * 32, scale, j0 + c * 32);
+          epi.chunk(p, va, bias + c * 32, scale, j0 + c * 32, seg_count);
           tmem_ld_wait(vb);
           if (c + 2 < BN / 32) {
             tmem_ld_32x32(taddr + (c + 2) * 32, va);
@@ -429,7 +456,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
-          epi.chunk(p, vb, cb + (c + 1) * 32, scale, j0 + (c + 1) * 32);
+          epi.chunk(p, vb, bias + (c + 1) * 32, scale, j0 + (c + 1) * 32, seg_count);
           if (c + 2 < BN / 32) tmem_ld_wait(va);
         }
         as ^= 1;
@@ -441,6 +468,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0 && p.amb_seg_count) p.amb_seg_count[blockIdx.x] = *seg_count;
   if (kC > 1) cluster_sync_all();  // no CTA leaves while peers may still signal its barriers
   if (warp == 2) {
     tc_fence_after();

@@ -247,7 +247,7 @@ def rank_finalize(rank0: torch.Tensor, gt_score: Optional[torch.Tensor], M_total
     medr = torch.empty(1, dtype=torch.float64, device=dev) if want_medr else None
     karr = (ctypes.c_int * max(1, len(k_vals)))(*k_vals)
     with torch.cuda.device(dev):
-        hist = _workspace(dev, 2 * 65536 * 4)
+        hist = _workspace(dev, (3 * 65536 + 8) * 4)
         _ffi.check(_ffi.load().vtc_rank_finalize(_ptr(rank0), _ptr(gt_score), rank0.shape[0],
                                                  int(M_total), karr, len(k_vals), _ptr(hits),
                                                  _ptr(medr), _ptr(hist), hist.numel(),
