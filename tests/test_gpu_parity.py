@@ -45,7 +45,8 @@ def test_normalize_matches_reference_semantics(cuda_dev):
 @pytest.mark.parametrize("precision", ["bf16", "exact"])
 def test_sim_matrix_tensor_core_gemm(cuda_dev, N, M, D, precision):
     """The tcgen05 GEMM core (EPI_STORE) against fp64; also the evidence for the guard band:
-    |tc - exact| / (|a||b|) must stay well inside guard_rel (2^-14 bf16, 2^-13 exact)."""
+    |tc - exact| / (|a||b|) must stay well inside the library's guard_rel (csrc/api.cu
+    guard_rel_for: (K'/16 + 8) * 2^-23, plus 1.2e-5 for the bf16x3 split)."""
     from vtc_b200 import ops
 
     g = torch.Generator().manual_seed(N * 7 + M)
@@ -61,10 +62,11 @@ def test_sim_matrix_tensor_core_gemm(cuda_dev, N, M, D, precision):
     want = scale * (a_ref.double() @ b_ref.double().t()).numpy()
     norms = (a_ref.norm(dim=-1, keepdim=True) * b_ref.norm(dim=-1, keepdim=True).t()).double().numpy()
     rel = np.abs(out - want) / (scale * norms)
-    guard = 2.0 ** -14 if precision == "bf16" else 2.0 ** -13
+    kp = -(-(D if precision == "bf16" else 3 * D) // 64) * 64
+    guard = (kp // 16 + 8) * 2.0 ** -23 + (0.0 if precision == "bf16" else 1.2e-5)
     print(f"\n[guard-band evidence] {precision} N={N} M={M} D={D}: max rel err {rel.max():.3e} "
           f"(guard {guard:.3e}, margin x{guard / max(rel.max(), 1e-30):.1f})")
-    assert rel.max() < guard / 4
+    assert rel.max() < guard / 3
     # against fp32 inputs the north_star tolerances hold
     full = scale * (a.double() @ b.double().t()).numpy()
     tol = 2e-2 if precision == "bf16" else 1e-4
@@ -247,6 +249,22 @@ def test_recall_at_k_and_compute_recall_golden(cuda_dev, golden):
         got = m.compute(V.numpy(), T.numpy())
         assert [k for k, _ in got] == [1, 5, 10]
         np.testing.assert_array_equal(np.array([r for _, r in got]) * 100.0, g[key][:, 1])
+
+
+def test_recall_pipelined_host_staging(cuda_dev):
+    """Large host inputs are staged chunk by chunk on a copy stream (H2D overlaps ranking); the
+    result must not depend on the chunking."""
+    from vtc_b200.model.metric import RecallAtK
+
+    T, V = make_retrieval_pair(1003, 1003, 256, sigma=4.0, seed=17)
+    want = O.rank0_exact(T, V)
+    m = RecallAtK("videos", "titles", [1, 5, 10])
+    m.PIPELINE_MIN_BYTES = 0
+    for qa, ga in ((T, V), (T.numpy(), V.numpy()), (T.pin_memory(), V.to(cuda_dev))):
+        full = m.compute_full(ga, qa)
+        np.testing.assert_array_equal(_np(full["rank0"]), want)
+        np.testing.assert_array_equal(_np(full["hits"]), [np.sum(want < k) for k in (1, 5, 10)])
+        assert _np(full["medr"])[0] == O.medr(want)
 
 
 def test_recall_at_k_update_result_protocol(cuda_dev):

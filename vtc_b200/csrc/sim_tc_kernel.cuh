@@ -47,8 +47,9 @@ struct SmemLayout {
   static constexpr int kResBytes = kRes ? MAX_RES_KB * A_TILE_BYTES : 0;
   static constexpr int kStagesOff = kResBytes;
   static constexpr int kBarOff = kStagesOff + kStages * kStageBytes;
+  static constexpr int kBiasOff = kBarOff + 256;  // 4 epilogue warps x 128 floats
   static constexpr int kNumBars = 2 * kStages + MAX_RES_KB + 1 + 2 + 2;
-  static constexpr int kTotal = kBarOff + 256;
+  static constexpr int kTotal = kBiasOff + 4 * 128 * 4;
   static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
@@ -65,11 +66,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // ------------------------------------------------------------------------------------ epilogues
 // Each epilogue thread owns one tile row (= TMEM lane).  `begin_item` / `chunk` / `end_item`.
-// `bias` points at 32 consecutive entries of the per-column bias in GLOBAL memory (padded to a
-// multiple of 256 columns by the host, out-of-range columns hold the epilogue's neutral value), so
-// the loads are warp-uniform 128-bit L1 hits and the epilogue warps never synchronise with each
-// other.  Code size matters here (one warp per scheduler, 32 KB of L1.5 I-cache): rare paths are
-// kept tiny and out of line.
+// `bias` points at 32 consecutive entries of the per-column bias staged in this WARP'S PRIVATE
+// shared-memory buffer (128 columns at a time; the global array is padded to a multiple of 256
+// columns by the host, out-of-range columns hold the epilogue's neutral value): reads are
+// warp-uniform 128-bit LDS broadcasts and the epilogue warps never synchronise with each other.
+// Code size matters here (one warp per scheduler, 32 KB of L1.5 I-cache): rare paths are kept tiny
+// and out of line.
 
 constexpr int RANK_GROUP = 8;  // columns re-checked together when any of them is in the guard band
 
@@ -102,8 +104,8 @@ struct RankEpi {
     float csum = 0.f;
 #pragma unroll
     for (int g = 0; g < 32 / RANK_GROUP; ++g) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g);
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g + 1);
+      const float4 b0 = reinterpret_cast<const float4*>(bias)[2 * g];
+      const float4 b1 = reinterpret_cast<const float4*>(bias)[2 * g + 1];
       const float d0 = fmaf(scale, __uint_as_float(v[8 * g + 0]), b0.x);
       const float d1 = fmaf(scale, __uint_as_float(v[8 * g + 1]), b0.y);
       const float d2 = fmaf(scale, __uint_as_float(v[8 * g + 2]), b0.z);
@@ -149,7 +151,7 @@ struct LseEpi {
     float cmax = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i);
+      const float4 b = reinterpret_cast<const float4*>(bias)[i];
       x[4 * i + 0] = fmaf(scale, __uint_as_float(v[4 * i + 0]), b.x);
       x[4 * i + 1] = fmaf(scale, __uint_as_float(v[4 * i + 1]), b.y);
       x[4 * i + 2] = fmaf(scale, __uint_as_float(v[4 * i + 2]), b.z);
@@ -194,7 +196,7 @@ struct StoreEpi {
     float y[32];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i);
+      const float4 b = reinterpret_cast<const float4*>(bias)[i];
       const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -264,8 +266,8 @@ struct TopkEpi {
                                         unsigned int*) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g);
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * g + 1);
+      const float4 b0 = reinterpret_cast<const float4*>(bias)[2 * g];
+      const float4 b1 = reinterpret_cast<const float4*>(bias)[2 * g + 1];
       float d[8];
       d[0] = fmaf(scale, __uint_as_float(v[8 * g + 0]), b0.x);
       d[1] = fmaf(scale, __uint_as_float(v[8 * g + 1]), b0.y);
@@ -429,6 +431,12 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const float scale = p.scale * (p.scale_ptr ? *p.scale_ptr : 1.0f);
     uint32_t as = 0, aphase = 0;
     Epi epi;
+    float* wbias = reinterpret_cast<float*>(smem + L::kBiasOff) + ew * 128;
+    float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cluster_id < num_items)  // bias of the first 128 columns of this CTA's first tile
+      bias_pre = __ldg(reinterpret_cast<const float4*>(
+                           p.col_bias + (int64_t)(cluster_id / q_groups) * p.tiles_per_split * BN) +
+                       lane);
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int qt = (item % q_groups) * kC + cta_rank, split = item / q_groups;
       const int t0 = split * p.tiles_per_split;
@@ -436,7 +444,12 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       epi.begin_item(p, (int64_t)qt * BM + row, split);
       for (int tile = t0; tile < t1; ++tile) {
         const int64_t j0 = (int64_t)tile * BN;
-        const float* bias = p.col_bias + j0;  // padded to a multiple of BN by the host
+        // first column of the tile this warp will process next (for the bias prefetch)
+        int64_t next_j0 = j0 + BN;
+        if (tile + 1 >= t1) {
+          const int nitem = item + num_clusters;
+          next_j0 = nitem < num_items ? (int64_t)(nitem / q_groups) * p.tiles_per_split * BN : 0;
+        }
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_off + as * BN;
@@ -445,8 +458,18 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tmem_ld_wait(va);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; c += 2) {
+          if ((c & 3) == 0) {
+            // stage the bias of columns [32c, 32c + 128) in this warp's private buffer and start
+            // fetching the following 128 (second half of this tile, or the next tile's first half)
+            __syncwarp();
+            reinterpret_cast<float4*>(wbias)[lane] = bias_pre;
+            __syncwarp();
+            const int64_t nj = c == 0 ? j0 + 128 : next_j0;
+            bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + nj) + lane);
+          }
+          const float* bias = wbias + (c & 3) * 32;
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-          epi.chunk(p, va, bias + c * 32, scale, j0 + c * 32, seg_count);
+          epi.chunk(p, va, bias, scale, j0 + c * 32, seg_count);
           tmem_ld_wait(vb);
           if (c + 2 < BN / 32) {
             tmem_ld_32x32(taddr + (c + 2) * 32, va);
@@ -456,7 +479,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
-          epi.chunk(p, vb, bias + (c + 1) * 32, scale, j0 + (c + 1) * 32, seg_count);
+          epi.chunk(p, vb, bias + 32, scale, j0 + (c + 1) * 32, seg_count);
           if (c + 2 < BN / 32) tmem_ld_wait(va);
         }
         as ^= 1;

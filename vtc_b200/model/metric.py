@@ -155,18 +155,70 @@ class RecallAtK(BaseMetric):
                 if isinstance(x, torch.Tensor) and x.is_cuda:
                     device = x.device
             device = device or _default_device()
+        num_samples = features_a.shape[0]
+        if features_b.shape[0] != num_samples:
+            # gt(t) = t and the denominator is the gallery size (model/metric.py:138,154-158)
+            raise AssertionError(
+                f"RecallAtK assumes len(a) == len(b) (got {num_samples} vs {features_b.shape[0]})")
+        host_b = not (isinstance(features_b, torch.Tensor) and features_b.is_cuda)
+        if host_b and num_samples * features_b.shape[1] * 4 >= self.PIPELINE_MIN_BYTES:
+            return self._compute_full_pipelined(features_a, features_b, device)
         a = _to_device(features_a, device)
         b = _to_device(features_b, device)
         if a.dtype != b.dtype:
             a, b = a.float(), b.float()
-        num_samples = a.shape[0]
-        if b.shape[0] != num_samples:
-            # gt(t) = t and the denominator is the gallery size (model/metric.py:138,154-158)
-            raise AssertionError(
-                f"RecallAtK assumes len(a) == len(b) (got {num_samples} vs {b.shape[0]})")
         rank0, gt_score = ops.sim_rank(b, a, metric=self.metric, precision=self.precision)
         hits, medr = ops.rank_finalize(rank0, gt_score, num_samples, self.k_vals)
         return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": num_samples}
+
+    # host inputs of at least this many bytes are staged in chunks on a copy stream so that the
+    # host->device transfer of query chunk i+1 overlaps the ranking of chunk i
+    PIPELINE_MIN_BYTES = 32 << 20
+    PIPELINE_CHUNKS = 4
+
+    def _compute_full_pipelined(self, features_a: ArrayLike, features_b: ArrayLike,
+                                device: torch.device) -> Dict[str, object]:
+        def host(x):
+            if isinstance(x, np.ndarray):
+                x = torch.from_numpy(np.ascontiguousarray(x))
+            if x.dtype not in (torch.float32, torch.bfloat16):
+                x = x.float()
+            x = x.contiguous()
+            return x if x.is_pinned() else x.pin_memory()
+
+        a = _to_device(features_a, device) if (isinstance(features_a, torch.Tensor)
+                                              and features_a.is_cuda) else None
+        ha = None if a is not None else host(features_a)
+        hb = host(features_b)
+        n = hb.shape[0]
+        dtype = hb.dtype if (ha is None or ha.dtype == hb.dtype) else torch.float32
+        main = torch.cuda.current_stream(device)
+        copy = torch.cuda.Stream(device)
+        bounds = [n * i // self.PIPELINE_CHUNKS for i in range(self.PIPELINE_CHUNKS + 1)]
+        rank0 = torch.empty(n, dtype=torch.int32, device=device)
+        gt_score = torch.empty(n, dtype=torch.float64, device=device)
+        chunks, events = [], []
+        with torch.cuda.stream(copy):
+            copy.wait_stream(main)
+            if a is None:
+                a = ha.to(device, non_blocking=True).to(dtype)
+            for s, e in zip(bounds[:-1], bounds[1:]):
+                chunks.append(hb[s:e].to(device, non_blocking=True).to(dtype))
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                events.append(ev)
+        a = a.to(dtype)
+        for (s, e), qc, ev in zip(zip(bounds[:-1], bounds[1:]), chunks, events):
+            if e == s:
+                continue
+            main.wait_event(ev)
+            qc.record_stream(main)
+            r, g = ops.sim_rank(qc, a, row_offset=s, metric=self.metric, precision=self.precision)
+            rank0[s:e] = r
+            gt_score[s:e] = g
+        a.record_stream(main)
+        hits, medr = ops.rank_finalize(rank0, gt_score, a.shape[0], self.k_vals)
+        return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": a.shape[0]}
 
     def compute(self, features_a: ArrayLike, features_b: ArrayLike) -> List[Tuple[int, float]]:
         full = self.compute_full(features_a, features_b)
