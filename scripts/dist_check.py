@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, launched under torchrun (one rank per GPU, NCCL):
+row-sharded rank eval and gallery-sharded top-k against the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import vtc_oracle as O  # noqa: E402
+from vtc_b200.parallel import shard_bounds, sharded_rank_eval, sharded_topk  # noqa: E402
+from vtc_b200.synthetic import make_retrieval_pair  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for (N, M, D, prec) in ((3001, 3001, 512, "exact"), (2000, 5003, 256, "bf16"), (4096, 4096, 768, "bf16")):
+        T, V = make_retrieval_pair(N, M, D, sigma=4.0, seed=N)
+        qs, qe = shard_bounds(N, world, rank)
+        gs, ge = shard_bounds(M, world, rank)
+        res = sharded_rank_eval(T[qs:qe].contiguous().to(dev), V[gs:ge].contiguous().to(dev), N, M,
+                                precision=prec)
+        Tq, Vq = (O.bf16_round(T), O.bf16_round(V)) if prec == "bf16" else (T, V)
+        want = O.rank0_exact(Tq, Vq)
+        got = res["rank0_local"].cpu().numpy()
+        hits = res["hits"].cpu().numpy()
+        medr = float(res["medr"].cpu()[0])
+        good = (np.array_equal(got, want[qs:qe]) and
+                list(hits) == [int((want < k).sum()) for k in (1, 5, 10)] and medr == O.medr(want))
+        tv, ti = sharded_topk(T[:64].contiguous().to(dev), V[gs:ge].contiguous().to(dev), M, 11,
+                              precision=prec)
+        wi = O.topk_exact(Tq[:64], Vq, 11)[1]
+        good = good and np.array_equal(ti.cpu().numpy(), wi)
+        print(f"[rank {rank}/{world}] N={N} M={M} D={D} {prec}: {'OK' if good else 'MISMATCH'}", flush=True)
+        ok = ok and good
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()
