@@ -130,3 +130,8 @@ def test_row_sharded_eval_square_world2():
 def test_row_sharded_eval_rectangular_world2():
     """N != M: some ground truths live in the other rank's gallery shard."""
     _run(90, 151)
+
+
+def test_row_sharded_eval_equal_shards_world2():
+    """Equal shards: the gathered gallery is used as two contiguous remote ranges."""
+    _run(100, 100)

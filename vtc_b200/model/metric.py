@@ -103,6 +103,20 @@ def _to_device(x: ArrayLike, device: torch.device) -> torch.Tensor:
     return x.to(device, non_blocking=True)
 
 
+_copy_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _copy_stream(device: torch.device) -> "torch.cuda.Stream":
+    """One persistent H2D staging stream per device (the caching allocator pools blocks per
+    stream, so a fresh stream per call would cudaMalloc every time)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _copy_streams.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device)
+        _copy_streams[idx] = st
+    return st
+
+
 def _default_device() -> torch.device:
     if not torch.cuda.is_available():
         raise ops.VtcError("RecallAtK needs a CUDA device: vtc_b200 has no CPU fallback")
@@ -193,7 +207,7 @@ class RecallAtK(BaseMetric):
         n = hb.shape[0]
         dtype = hb.dtype if (ha is None or ha.dtype == hb.dtype) else torch.float32
         main = torch.cuda.current_stream(device)
-        copy = torch.cuda.Stream(device)
+        copy = _copy_stream(device)
         bounds = [n * i // self.PIPELINE_CHUNKS for i in range(self.PIPELINE_CHUNKS + 1)]
         rank0 = torch.empty(n, dtype=torch.int32, device=device)
         gt_score = torch.empty(n, dtype=torch.float64, device=device)

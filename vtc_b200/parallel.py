@@ -94,36 +94,50 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     assert g_local.shape[0] == g_sizes[rank], "g_local does not match shard_bounds(M_total)"
     dev = q_local.device
 
+    # gallery exchange: one all_gather into a single [world * max_shard, D] buffer, so that with
+    # equal shards the remote rows form (at most) two contiguous ranges [0, gs) and [ge, M)
     work = None
-    chunks: List[Optional[torch.Tensor]] = [None] * world
-    chunks[rank] = g_local
     gathered = None
+    mx = max(g_sizes)
+    equal = all(sz == mx for sz in g_sizes)
     if world > 1:
-        gathered, work = _all_gather_padded(g_local, g_sizes, group, async_op=True)
+        send = g_local
+        if send.shape[0] < mx:
+            pad = torch.zeros((mx - send.shape[0], send.shape[1]), dtype=send.dtype, device=dev)
+            send = torch.cat([send, pad])
+        gathered = torch.empty((world * mx, send.shape[1]), dtype=send.dtype, device=dev)
+        work = dist.all_gather_into_tensor(gathered, send.contiguous(), group=group, async_op=True)
 
     # ground-truth scores: d(t, gt) lives in the chunk that owns gallery row t; start with ours
     n_local = qe - qs
-    gt_score = backend.gt_scores(q_local, g_local, qs, g_starts[rank], metric, precision)
+    gs0, ge0 = g_starts[rank], g_starts[rank] + g_sizes[rank]
+    gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
     rank0 = torch.zeros(n_local, dtype=torch.int32, device=dev)
-    gt_local = world == 1 or _gt_all_local(qs, qe, g_starts[rank], g_sizes[rank])
-    todo = list(range(world))
+    gt_local = world == 1 or _gt_all_local(qs, qe, gs0, g_sizes[rank])
+    local_done = False
     if gt_local and g_sizes[rank] > 0:
         # every ground truth is in our own chunk: rank against it while the gather is in flight
-        backend.sim_rank(q_local, g_local, qs, g_starts[rank], metric, precision, gt_score, rank0)
-        todo.remove(rank)
+        backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
+        local_done = True
     if work is not None:
         work.wait()
-        for r in range(world):
-            if r != rank:
-                chunks[r] = gathered[r][:g_sizes[r]]
+        # remote row ranges as (start row in the global gallery, tensor)
+        if equal:
+            remote = [(0, gathered[:gs0]), (ge0, gathered[ge0:M_total])]
+        else:
+            remote = [(g_starts[r], gathered[r * mx:r * mx + g_sizes[r]])
+                      for r in range(world) if r != rank]
+        remote = [(st, t) for st, t in remote if t.shape[0] > 0]
         if not gt_local:
-            for r in range(world):
-                if r != rank and g_sizes[r] > 0:
-                    other = backend.gt_scores(q_local, chunks[r], qs, g_starts[r], metric, precision)
-                    gt_score = torch.where(torch.isnan(gt_score), other, gt_score)
-    for r in todo:
-        if g_sizes[r] > 0 and chunks[r] is not None:
-            backend.sim_rank(q_local, chunks[r], qs, g_starts[r], metric, precision, gt_score, rank0)
+            for st, t in remote:
+                other = backend.gt_scores(q_local, t, qs, st, metric, precision)
+                gt_score = torch.where(torch.isnan(gt_score), other, gt_score)
+        if not local_done and g_sizes[rank] > 0:
+            backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
+        for st, t in remote:
+            backend.sim_rank(q_local, t, qs, st, metric, precision, gt_score, rank0)
+    elif not local_done and g_sizes[rank] > 0:
+        backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
 
     hits, _ = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), False)
     hits = hits.clone()
