@@ -183,6 +183,27 @@ int vtc_linear(const float* X, const float* W, const float* bias, const float* r
                int64_t rows, int in_f, int out_f, int act, int precision, float* Y, void* ws,
                size_t ws_bytes, vtc_stream_t stream);
 
+/* ---- H4 in one call: prepared linears + the whole CAM forward -----------------------------------
+ * vtc_linear_prepare writes a weight once as the gallery-side bf16 operand (+ padded bias) into a
+ * caller-owned buffer of vtc_linear_prepared_bytes(); vtc_cam_forward then runs
+ *   stack+normalize -> layers x [LN1+prep, QKV GEMM, attention core, out_proj GEMM(+residual),
+ *                                LN2+prep, c_fc GEMM(+QuickGELU, bf16 operand out), c_proj GEMM(+res)]
+ *   -> read-out (AVG, or final_linear(token 0) for RESIDUAL_ONLY) -> normalize(normalize(main)+res)
+ * i.e. PretrainedCLIPBase._adapt_feature (model/model.py:141-205) in 2 + 7*layers launches.
+ * `layers_params` is a HOST array of `layers` structs holding DEVICE pointers. */
+typedef struct {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;  /* LayerNorm weight / bias [D] */
+  const void *qkv, *out, *fc, *proj;           /* prepared linears: D->3D, D->D, D->4D, 4D->D */
+} vtc_cam_layer;
+size_t vtc_linear_prepared_bytes(int in_f, int out_f, int precision);
+int vtc_linear_prepare(const float* W, const float* bias, int in_f, int out_f, int precision,
+                       void* prepared, vtc_stream_t stream);
+size_t vtc_cam_workspace_bytes(int L, int64_t b, int D, int precision);
+int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D, int heads,
+                    int layers, const vtc_cam_layer* layers_params, int readout_mode,
+                    const void* final_linear_prepared, const uint8_t* skip_mask, int precision,
+                    float* out, void* ws, size_t ws_bytes, vtc_stream_t stream);
+
 /* number of kernels this library has launched since load (for bench.py's gpu_launches). */
 uint64_t vtc_launch_count(void);
 

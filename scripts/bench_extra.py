@@ -100,7 +100,12 @@ def config2():
             torch.nn.init.normal_(blk.attn.out_proj.weight, std=0.02)
         with torch.no_grad():
             us, nl = timeit(lambda: cam._adapt_feature(m, x), iters=30)
-        emit(bench="c2_cam_adapt_feature", precision=prec, us=us, launches=nl)
+            emit(bench="c2_cam_adapt_feature", precision=prec, us=us, launches=nl)
+            try:
+                us_g, _ = timeit(graphed(lambda: cam._adapt_feature(m, x)), iters=30)
+                emit(bench="c2_cam_adapt_feature_cudagraph", precision=prec, us=us_g)
+            except Exception as e:  # noqa: BLE001
+                emit(bench="c2_cam_adapt_feature_cudagraph", precision=prec, error=str(e)[:200])
 
     # stock torch CAM (nn.MultiheadAttention blocks), eager fp32 and bf16 autocast
     class Block(torch.nn.Module):

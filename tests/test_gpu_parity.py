@@ -328,11 +328,16 @@ def test_topk_small_gallery_and_merge(cuda_dev):
 # ------------------------------------------------------------------------------------- H2 + H3
 @pytest.mark.parametrize("name", ["c2_s100", "c2_s14", "small", "ragged"])
 @pytest.mark.parametrize("precision", ["exact", "bf16"])
-def test_clip_loss_fused_matches_reference_golden(cuda_dev, golden, name, precision):
+@pytest.mark.parametrize("path", ["fused_small", "tcgen05"])
+def test_clip_loss_fused_matches_reference_golden(cuda_dev, golden, monkeypatch, name, precision, path):
     """model/loss.py::clip_loss through the LazySim route against the value the reference's own
-    clip_loss produced (fixtures), and the saved LSEs against fp64."""
+    clip_loss produced (fixtures), and the saved LSEs against fp64.  Both kernels are covered: the
+    single-launch fused kernel used for n <= 2048 and the tcgen05 online-LSE kernel."""
     from vtc_b200 import ops
     from vtc_b200.model import LazySim, clip_loss
+
+    if path == "tcgen05":
+        monkeypatch.setenv("VTC_INFONCE_FORCE_TC", "1")
 
     g = golden("clip_loss.npz")
     b, D, s = g[name + "_cfg"]
@@ -349,6 +354,19 @@ def test_clip_loss_fused_matches_reference_golden(cuda_dev, golden, name, precis
     np.testing.assert_allclose(_np(row), p64["row_lse"], atol=atol, rtol=0)
     np.testing.assert_allclose(_np(col), p64["col_lse"], atol=atol, rtol=0)
     np.testing.assert_allclose(_np(diag), p64["diag"], atol=atol, rtol=0)
+
+
+def test_clip_loss_large_batch_tcgen05(cuda_dev):
+    """n = 3000 > 2048 takes the tcgen05 online-LSE path by itself (several gallery tiles)."""
+    from vtc_b200 import ops
+
+    vis, txt = make_batch_pair(3000, 256, seed=5)
+    for precision, tol in (("exact", 1e-4), ("bf16", 2e-2)):
+        loss, row, col, diag = ops.infonce_fwd(vis.to(cuda_dev), txt.to(cuda_dev), 50.0, precision)
+        p64 = O.clip_loss_parts64(vis, txt, 50.0)
+        np.testing.assert_allclose(loss.item(), p64["loss"], rtol=tol)
+        np.testing.assert_allclose(_np(row), p64["row_lse"], atol=tol * 50, rtol=0)
+        np.testing.assert_allclose(_np(col), p64["col_lse"], atol=tol * 50, rtol=0)
 
 
 def test_clip_loss_backward_and_dense_sim(cuda_dev, golden):
@@ -412,6 +430,25 @@ def test_cam_adapt_feature_golden(cuda_dev, golden, name, precision):
     tol = dict(rtol=1e-4, atol=1e-5) if precision == "exact" else dict(rtol=2e-2, atol=2e-3)
     np.testing.assert_allclose(_np(out)[:want.shape[0]], want, **tol)
     np.testing.assert_allclose(_np(out.norm(dim=-1)), 1.0, rtol=1e-5)
+
+
+def test_cam_transformer_module_forward(cuda_dev):
+    """The op-by-op CAMTransformer.forward (LayerNorm / tcgen05 linears / attention core as separate
+    C-ABI calls) against the oracle's clip.model.Transformer restatement."""
+    from vtc_b200.model import CAMTransformer
+
+    L, b, D, layers, heads = 6, 40, 256, 2, 4
+    params = O.make_cam_params(D, layers, heads, seed=5, rerandomise=True)
+    tfm = CAMTransformer(D, layers, heads, "exact")
+    tfm.load_state_dict(params, strict=True)
+    tfm = tfm.to(cuda_dev).eval()
+    x = torch.randn(L, b, D, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        got = tfm(x.to(cuda_dev))
+    want = O.transformer(x, params, layers, heads)
+    np.testing.assert_allclose(_np(got), want.numpy(), rtol=2e-4, atol=2e-5)
+    with pytest.raises(NotImplementedError):
+        tfm(x.to(cuda_dev))  # autograd on: forward-only this round
 
 
 def test_cam_properties(cuda_dev):

@@ -56,6 +56,20 @@ SIGNATURES = {
 }
 
 
+class CamLayer(ctypes.Structure):
+    """vtc_cam_layer of include/vtc_b200.h (device pointers)."""
+    _fields_ = [(n, c_void_p) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "qkv", "out", "fc", "proj")]
+
+
+SIGNATURES.update({
+    "vtc_linear_prepared_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "vtc_linear_prepare": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
+    "vtc_cam_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
+    "vtc_cam_forward": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, c_int, POINTER(CamLayer), c_int,
+                                _P, _P, c_int, _P, _P, c_size_t, _P]),
+})
+
+
 class VtcError(RuntimeError):
     pass
 

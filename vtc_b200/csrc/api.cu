@@ -14,6 +14,12 @@
 namespace vtc {
 std::atomic<uint64_t> g_launch_count{0};
 
+// infonce_small.cu
+size_t infonce_small_ws_bytes(int64_t n);
+int launch_infonce_small(const void* A, const void* B, int64_t n, int D, bool in_bf16,
+                         bool round_bf16, const float* scale, float* loss, float* row_lse,
+                         float* col_lse, float* diag, void* wsp, size_t ws_bytes, cudaStream_t s);
+
 namespace {
 
 // Bound on |tensor-core dot - exact dot| / (|q| |x|) for operands of padded depth Kp; see
@@ -183,8 +189,7 @@ struct TopkWs {
   double* sq64;
   float* sq32;
   unsigned int* scalars;
-  float* pool_val;
-  int* pool_idx;
+  float2* pool;
   float2* pool_meta;
   unsigned int* row_flag;
 };
@@ -201,8 +206,7 @@ TopkWs carve_topk(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   t.row_flag = ws.take<unsigned int>(N);
   t.opQ = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
   t.opG = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
-  t.pool_val = ws.take<float>((size_t)kTopkMaxSplits * N * tc::TOPK_POOL);
-  t.pool_idx = ws.take<int>((size_t)kTopkMaxSplits * N * tc::TOPK_POOL);
+  t.pool = ws.take<float2>((size_t)kTopkMaxSplits * N * tc::TOPK_POOL);
   t.pool_meta = ws.take<float2>((size_t)kTopkMaxSplits * N);
   return t;
 }
@@ -231,7 +235,7 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     a.ex = ExactArgs{Q, G, D, D, in_bf16, N, M, D, w.sq64, nullptr, 0, col_offset, metric};
   else
     a.ex = ExactArgs{w.opQ, w.opG, o.Kp, o.Kp, true, N, M, D, w.sq64, nullptr, 0, col_offset, metric};
-  a.pool_val = w.pool_val, a.pool_idx = w.pool_idx, a.pool_meta = w.pool_meta;
+  a.pool_buf = w.pool, a.pool_meta = w.pool_meta;
   a.pool = tc::TOPK_POOL, a.k = k;
   a.guard_rel = guard_rel_for(precision, o.Kp);
   a.max_sq_bits = &w.scalars[0];
@@ -258,7 +262,7 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
                                        round_up<int64_t>(M, tc::BN), INFINITY, s));
   p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
-  p.pool_val = w.pool_val, p.pool_idx = w.pool_idx, p.pool_meta = w.pool_meta;
+  p.pool = w.pool, p.pool_meta = w.pool_meta;
   const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, tc::choose_cluster(N, M));
   a.splits = p.g_splits;
   CUtensorMap tmA, tmB;
@@ -308,7 +312,7 @@ int gemm_store_impl(const void* A, const void* B, int64_t N, int64_t M, int D, i
   VTC_RETURN_IF_ERROR(launch_fill_bias(g.bias, bias, M, round_up<int64_t>(M, tc::BN), 0.f, s));
   p.col_bias = g.bias, p.scale_ptr = scale_ptr, p.scale = 1.f;
   p.out = out, p.ldo = ldo, p.residual = residual, p.act = act;
-  const tc::Plan pl = tc::plan_tiles(p, 1, 1);
+  const tc::Plan pl = tc::plan_tiles(p, 64, 1, 1);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opA, N, o.Kp, o.Kp, tc::BM, &tmA));
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opB, M, o.Kp, o.Kp, tc::BN, &tmB));
@@ -323,6 +327,7 @@ struct NceWs {
   float* bias;  // zeros, -inf padding
 };
 constexpr int kNceMaxSplits = 8;
+constexpr int64_t kNceSmallMax = 2048;
 NceWs carve_nce(Workspace& ws, int64_t n, int D, int dtype, int precision) {
   const OperandPlan o = plan_operands(D, dtype, precision);
   NceWs w;
@@ -350,6 +355,11 @@ int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, 
       !valid_dtype(dtype) || (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16))
     return VTC_ERR_INVALID_ARG;
   if (n > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
+  // training-sized batches are launch-latency bound: one fused SIMT launch (infonce_small.cu);
+  // larger ones stream through the tcgen05 kernel with the online-LSE epilogue
+  if (n <= kNceSmallMax && !getenv("VTC_INFONCE_FORCE_TC"))
+    return launch_infonce_small(A, B, n, D, dtype == VTC_BF16, precision == VTC_PREC_BF16, scale,
+                                loss, row_lse, col_lse, diag, wsp, ws_bytes, s);
   Workspace ws(wsp, ws_bytes);
   NceWs w = carve_nce(ws, n, D, dtype, precision);
   if (!ws.ok()) return VTC_ERR_WORKSPACE;
@@ -382,6 +392,59 @@ int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, 
     VTC_RETURN_IF_ERROR(launch_lse_merge(p.lse_part, p.g_splits, n, dir == 0 ? row_lse : col_lse, s));
   }
   return launch_infonce_loss(row_lse, col_lse, w.diag_raw, scale, n, diag, loss, s);
+}
+
+
+// ----------------------------------------------------------------------- prepared linears / CAM
+// A "prepared" linear holds its weight as the gallery-side bf16 operand [out_f, Kp] followed by the
+// bias padded to a multiple of 256 floats; both are written once (vtc_linear_prepare) and reused
+// by every forward, so a linear is ONE launch: TMA-fed tcgen05 GEMM with bias / QuickGELU /
+// residual in the epilogue, output as fp32 and/or as the next GEMM's bf16 operand.
+size_t prepared_linear_bytes(int in_f, int out_f, int precision) {
+  const OperandPlan o = plan_operands(in_f, VTC_F32, precision);
+  return round_up<size_t>((size_t)out_f * o.Kp * sizeof(__nv_bfloat16), 256) +
+         round_up<size_t>(round_up<int64_t>(out_f, tc::BN) * sizeof(float), 256);
+}
+const float* prepared_bias(const void* prepared, int in_f, int out_f, int precision) {
+  const OperandPlan o = plan_operands(in_f, VTC_F32, precision);
+  return (const float*)((const char*)prepared +
+                        round_up<size_t>((size_t)out_f * o.Kp * sizeof(__nv_bfloat16), 256));
+}
+
+int linear_prepared(const __nv_bfloat16* Xop, const void* prepared, const float* residual,
+                    int64_t rows, int in_f, int out_f, int act, int precision, float* Y,
+                    __nv_bfloat16* Yop, int Yop_kp, cudaStream_t s) {
+  const OperandPlan o = plan_operands(in_f, VTC_F32, precision);
+  tc::Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = rows, p.M = out_f, p.num_kb = o.Kp / tc::BK;
+  p.col_bias = prepared_bias(prepared, in_f, out_f, precision);
+  p.scale = 1.f;
+  p.out = Y, p.ldo = out_f, p.residual = residual, p.act = act;
+  p.out_op = Yop, p.out_op_kp = Yop_kp, p.out_op_split = o.split ? 1 : 0;
+  const tc::Plan pl = tc::plan_tiles(p, 64, 1, 1);
+  CUtensorMap tmA, tmB;
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(Xop, rows, o.Kp, o.Kp, tc::BM, &tmA));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(prepared, out_f, o.Kp, o.Kp, tc::BN, &tmB));
+  return tc::launch_sim_tc(tc::EPI_STORE, p.num_kb <= 8, pl, tmA, tmB, p, s);
+}
+
+struct CamWs {
+  float *X0, *X1, *QKV, *res;
+  __nv_bfloat16 *Hop, *Fop;
+};
+CamWs carve_cam(Workspace& ws, int L, int64_t b, int D, int precision) {
+  const int64_t rows = (int64_t)L * b;
+  const OperandPlan od = plan_operands(D, VTC_F32, precision);
+  const OperandPlan of = plan_operands(4 * D, VTC_F32, precision);
+  CamWs w;
+  w.X0 = ws.take<float>((size_t)rows * D);
+  w.X1 = ws.take<float>((size_t)rows * D);
+  w.QKV = ws.take<float>((size_t)rows * 3 * D);
+  w.res = ws.take<float>((size_t)b * D);
+  w.Hop = ws.take<__nv_bfloat16>((size_t)rows * od.Kp);
+  w.Fop = ws.take<__nv_bfloat16>((size_t)rows * of.Kp);
+  return w;
 }
 
 }  // namespace
@@ -425,9 +488,12 @@ size_t vtc_workspace_bytes(int op, int64_t N, int64_t M, int D, int precision) {
   switch (op) {
     case VTC_OP_SIM_RANK: carve_rank(ws, N, M, D, VTC_F32, precision, true); break;
     case VTC_OP_SIM_TOPK: carve_topk(ws, N, M, D, VTC_F32, precision); break;
-    case VTC_OP_INFONCE_FWD:
+    case VTC_OP_INFONCE_FWD: {
       carve_nce(ws, N, D, VTC_F32, precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision);
+      const size_t small = N <= kNceSmallMax ? infonce_small_ws_bytes(N) : 0;
+      if (small > ws.used) ws.used = small;
       break;
+    }
     case VTC_OP_SIM_MATRIX:
       carve_gemm(ws, N, M, D, VTC_F32, precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision);
       break;
@@ -563,7 +629,7 @@ int vtc_layernorm(const float* X, const float* gamma, const float* beta, int64_t
 int vtc_cam_attn_core(const float* QKV, int L, int64_t b, int D, int heads, float* out,
                       vtc_stream_t stream) {
   if (!QKV || !out || b < 0 || D <= 0) return VTC_ERR_INVALID_ARG;
-  return launch_cam_attn_core(QKV, L, b, D, heads, out, (cudaStream_t)stream);
+  return launch_cam_attn_core(QKV, L, b, D, heads, out, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
 int vtc_bias_act(const float* X, const float* bias, const float* residual, int64_t rows, int D,
@@ -581,6 +647,79 @@ int vtc_cam_readout(const float* T, const float* main, const float* res_in,
     return VTC_ERR_INVALID_ARG;
   if (mode < 0 || mode > 2) return VTC_ERR_INVALID_ARG;
   return launch_cam_readout(T, main, res_in, skip_mask, L, b, D, mode, out, (cudaStream_t)stream);
+}
+
+size_t vtc_linear_prepared_bytes(int in_f, int out_f, int precision) {
+  if (in_f <= 0 || out_f <= 0 || (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16)) return 0;
+  return prepared_linear_bytes(in_f, out_f, precision);
+}
+
+int vtc_linear_prepare(const float* W, const float* bias, int in_f, int out_f, int precision,
+                       void* prepared, vtc_stream_t stream) {
+  if (!W || !prepared || in_f <= 0 || out_f <= 0 ||
+      (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16))
+    return VTC_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const OperandPlan o = plan_operands(in_f, VTC_F32, precision);
+  VTC_RETURN_IF_ERROR(launch_prep_operand(W, false, out_f, in_f, in_f,
+                                          o.split ? PREP_SPLIT_B : PREP_PLAIN,
+                                          (__nv_bfloat16*)prepared, o.Kp, s));
+  return launch_fill_bias((float*)prepared_bias(prepared, in_f, out_f, precision), bias, out_f,
+                          round_up<int64_t>(out_f, tc::BN), 0.f, s);
+}
+
+size_t vtc_cam_workspace_bytes(int L, int64_t b, int D, int precision) {
+  if (L < 1 || b < 0 || D <= 0 || (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16)) return 0;
+  Workspace ws(nullptr, 0);
+  carve_cam(ws, L, b, D, precision);
+  return ws.used + 512;
+}
+
+int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D, int heads,
+                    int layers, const vtc_cam_layer* lp, int readout_mode, const void* final_linear,
+                    const uint8_t* skip_mask, int precision, float* out, void* wsp, size_t ws_bytes,
+                    vtc_stream_t stream) {
+  if (!main || !out || L < 1 || (L > 1 && !aux) || b < 0 || D <= 0 || heads < 1 || layers < 0 ||
+      (layers > 0 && !lp) || (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16) ||
+      (readout_mode != VTC_CAM_READOUT_AVG && readout_mode != VTC_CAM_READOUT_RESIDUAL_ONLY) ||
+      (readout_mode == VTC_CAM_READOUT_RESIDUAL_ONLY && !final_linear))
+    return VTC_ERR_INVALID_ARG;
+  if (b == 0) return VTC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace ws(wsp, ws_bytes);
+  CamWs w = carve_cam(ws, L, b, D, precision);
+  if (!ws.ok()) return VTC_ERR_WORKSPACE;
+  const int64_t rows = (int64_t)L * b;
+  const OperandPlan od = plan_operands(D, VTC_F32, precision);
+  const OperandPlan of = plan_operands(4 * D, VTC_F32, precision);
+  const int split = od.split ? 1 : 0;
+  if (of.Kp != (split ? 3 : 1) * 4 * D) {  // padding columns of the MLP operand must be zero
+    cudaError_t e = cudaMemsetAsync(w.Fop, 0, (size_t)rows * of.Kp * sizeof(__nv_bfloat16), s);
+    if (e != cudaSuccess) return cuda_err(e);
+  }
+  VTC_RETURN_IF_ERROR(launch_cam_stack_normalize(main, aux, L, b, D, w.X0, s));  // model.py:150-151
+  float *X = w.X0, *X2 = w.X1;
+  for (int i = 0; i < layers; ++i) {  // clip.model.Transformer block (timesformer_clip_alt.py:112-124)
+    const vtc_cam_layer& l = lp[i];
+    VTC_RETURN_IF_ERROR(launch_layernorm_prep(X, l.ln1_g, l.ln1_b, rows, D, 1e-5f, split, w.Hop, od.Kp, s));
+    VTC_RETURN_IF_ERROR(linear_prepared(w.Hop, l.qkv, nullptr, rows, D, 3 * D, 0, precision, w.QKV,
+                                        nullptr, 0, s));
+    VTC_RETURN_IF_ERROR(launch_cam_attn_core(w.QKV, L, b, D, heads, nullptr, w.Hop, od.Kp, split, s));
+    VTC_RETURN_IF_ERROR(linear_prepared(w.Hop, l.out, X, rows, D, D, 0, precision, X2, nullptr, 0, s));
+    VTC_RETURN_IF_ERROR(launch_layernorm_prep(X2, l.ln2_g, l.ln2_b, rows, D, 1e-5f, split, w.Hop, od.Kp, s));
+    VTC_RETURN_IF_ERROR(linear_prepared(w.Hop, l.fc, nullptr, rows, D, 4 * D, 1, precision, nullptr,
+                                        w.Fop, of.Kp, s));
+    VTC_RETURN_IF_ERROR(linear_prepared(w.Fop, l.proj, X2, rows, 4 * D, D, 0, precision, X, nullptr, 0, s));
+  }
+  if (readout_mode == VTC_CAM_READOUT_AVG)
+    return launch_cam_readout(X, main, nullptr, skip_mask, L, b, D, VTC_CAM_READOUT_AVG, out, s);
+  // final_linear(token 0)  (model/model.py:161): token 0 = the first b rows of X
+  VTC_RETURN_IF_ERROR(launch_prep_operand(X, false, b, D, D, split ? PREP_SPLIT_A : PREP_PLAIN, w.Hop,
+                                          od.Kp, s));
+  VTC_RETURN_IF_ERROR(linear_prepared(w.Hop, final_linear, nullptr, b, D, D, 0, precision, w.res,
+                                      nullptr, 0, s));
+  return launch_cam_readout(nullptr, main, w.res, skip_mask, L, b, D, VTC_CAM_READOUT_RESIDUAL_ONLY,
+                            out, s);
 }
 
 }  // extern "C"

@@ -47,12 +47,47 @@ layernorm_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
   for (int k = lane; k < D; k += 32) y[k] = (x[k] - mean) * rstd * gamma[k] + beta[k];
 }
 
+// bf16 operand element(s) of value v at column k of a row laid out as [x] or [hi | hi | lo]
+__device__ __forceinline__ void put_operand(__nv_bfloat16* row, int k, int D, int split, float v) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  row[k] = hi;
+  if (split) {
+    row[D + k] = hi;
+    row[2 * D + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+// LayerNorm fused with operand preparation: the normalised row goes straight out as the
+// query-side bf16 operand of the following linear (no fp32 round trip, one launch less).
+__global__ void __launch_bounds__(256)
+layernorm_prep_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int64_t rows, int D, float eps, int split,
+                      __nv_bfloat16* __restrict__ out, int Kp) {
+  const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* x = X + r * D;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) s += x[k];
+  const float mean = warp_sum(s) / (float)D;
+  float v = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float d = x[k] - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)D + eps);
+  __nv_bfloat16* o = out + r * (int64_t)Kp;
+  for (int k = lane; k < D; k += 32)
+    put_operand(o, k, D, split, (x[k] - mean) * rstd * gamma[k] + beta[k]);
+  for (int k = (split ? 3 : 1) * D + lane; k < Kp; k += 32) o[k] = __float2bfloat16_rn(0.f);
+}
+
 // One warp per (sample, head).  QKV is the in_proj output [L, b, 3D] (q | k | v along the last
 // dim, heads contiguous inside each), out is [L, b, D].  head_dim <= 128 (4 floats per lane).
 template <int MAXL>
 __global__ void __launch_bounds__(256)
 cam_attn_core_kernel(const float* __restrict__ QKV, int L, int64_t b, int D, int heads,
-                     float* __restrict__ out) {
+                     float* __restrict__ out, __nv_bfloat16* __restrict__ out_op, int Kp, int split) {
   const int64_t w = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (w >= b * heads) return;
   const int lane = threadIdx.x & 31;
@@ -103,7 +138,8 @@ cam_attn_core_kernel(const float* __restrict__ QKV, int L, int64_t b, int D, int
         float o = 0.f;
 #pragma unroll
         for (int j = 0; j < MAXL; ++j) o = fmaf(s[j] * inv, v[j][e], o);
-        out[((int64_t)i * b + bi) * D + h * hd + d] = o;
+        if (out) out[((int64_t)i * b + bi) * D + h * hd + d] = o;
+        if (out_op) put_operand(out_op + ((int64_t)i * b + bi) * Kp, h * hd + d, D, split, o);
       }
     }
   }
@@ -233,14 +269,23 @@ int launch_layernorm(const float* X, const float* gamma, const float* beta, int6
 }
 
 int launch_cam_attn_core(const float* QKV, int L, int64_t b, int D, int heads, float* out,
-                         cudaStream_t s) {
+                         __nv_bfloat16* out_op, int Kp, int split, cudaStream_t s) {
   if (b == 0) return VTC_OK;
   if (L < 1 || L > 16 || heads < 1 || D % heads || D / heads > 128) return VTC_ERR_UNSUPPORTED_SHAPE;
   const unsigned grid = (unsigned)ceil_div<int64_t>(b * heads, WARPS);
   if (L <= 8)
-    cam_attn_core_kernel<8><<<grid, 256, 0, s>>>(QKV, L, b, D, heads, out);
+    cam_attn_core_kernel<8><<<grid, 256, 0, s>>>(QKV, L, b, D, heads, out, out_op, Kp, split);
   else
-    cam_attn_core_kernel<16><<<grid, 256, 0, s>>>(QKV, L, b, D, heads, out);
+    cam_attn_core_kernel<16><<<grid, 256, 0, s>>>(QKV, L, b, D, heads, out, out_op, Kp, split);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_layernorm_prep(const float* X, const float* gamma, const float* beta, int64_t rows, int D,
+                          float eps, int split, __nv_bfloat16* out, int Kp, cudaStream_t s) {
+  if (rows == 0) return VTC_OK;
+  layernorm_prep_kernel<<<(unsigned)ceil_div<int64_t>(rows, WARPS), 256, 0, s>>>(X, gamma, beta, rows,
+                                                                                D, eps, split, out, Kp);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }

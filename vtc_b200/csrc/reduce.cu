@@ -64,7 +64,7 @@ int launch_infonce_loss(const float* row_lse, const float* col_lse, const float*
 
 // --------------------------------------------------------------------------------------- top-k
 constexpr int SEL_WARPS = 4;
-constexpr int SEL_MAX_CAND = 8 * 32;  // splits <= 8, pool = 32
+constexpr int SEL_MAX_CAND = 8 * 64;  // splits <= 8, pool = 64
 
 template <typename T>
 __device__ __forceinline__ double exact_score(const T* __restrict__ q, const T* __restrict__ x, int D,
@@ -100,7 +100,7 @@ topk_select_kernel(TopkSelectArgs a) {
     int j = -1;
     double d = 0.0;
     if (i < fill) {
-      j = a.pool_idx[slot * a.pool + i];
+      j = __float_as_int(a.pool_buf[slot * a.pool + i].y);
       if (j >= 0 && j < a.ex.M) {
         d = exact_score(q, G + (int64_t)j * a.ex.ldg, a.ex.D, a.ex.metric,
                         a.ex.metric == VTC_METRIC_L2 ? a.ex.sq64[j] : 0.0);
@@ -144,8 +144,9 @@ topk_select_kernel(TopkSelectArgs a) {
     }
     __syncwarp();
   }
-  // completeness: every column outside a FULL pool has approx score >= tau, hence exact score
-  // >= tau - delta; the selection is provably right when the k-th exact score is below that.
+  // completeness: every column outside a pool has approx score >= its tau (+inf while the pool
+  // still holds every column seen), hence exact score >= tau - delta; the selection is provably
+  // right when the k-th exact score is below that.
   if (lane == 0) {
     const double qn = sqrt(qq);
     const double gmax_sq = (double)__uint_as_float(*a.max_sq_bits);
@@ -156,7 +157,7 @@ topk_select_kernel(TopkSelectArgs a) {
     bool ok = qq == qq;
     for (int s = 0; s < a.splits; ++s) {
       const float2 meta = a.pool_meta[(int64_t)s * a.ex.N + t];
-      if ((int)meta.x >= a.pool) {
+      if (meta.y < INFINITY) {
         if (found < a.k || !(dk < (double)meta.y - delta)) ok = false;
       }
     }

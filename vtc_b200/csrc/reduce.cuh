@@ -15,9 +15,8 @@ int launch_infonce_loss(const float* row_lse, const float* col_lse, const float*
 
 struct TopkSelectArgs {
   ExactArgs ex;              // canonical operands (Q, G, sq64, metric, col_offset ...)
-  const float* pool_val;     // [splits, N, pool]
-  const int* pool_idx;       // [splits, N, pool]
-  const float2* pool_meta;   // [splits, N] (fill, tau)
+  const float2* pool_buf;    // [splits, N, pool] (approx score, column index as int bits)
+  const float2* pool_meta;   // [splits, N] (entries, tau)
   int splits, pool, k;
   float guard_rel;
   const unsigned int* max_sq_bits;

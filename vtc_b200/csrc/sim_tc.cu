@@ -81,7 +81,7 @@ int choose_cluster(int64_t N, int64_t M) {
   return want;
 }
 
-Plan plan_tiles(Params& p, int max_splits, int cluster) {
+Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split) {
   Plan pl;
   pl.cluster = cluster < 1 ? 1 : cluster;
   p.q_tiles = (int)ceil_div<int64_t>(p.N, BM);
@@ -90,13 +90,14 @@ Plan plan_tiles(Params& p, int max_splits, int cluster) {
   const int q_groups = ceil_div(p.q_tiles, pl.cluster);
   // Items are dealt round-robin to the co-resident clusters, so the cost is ceil(items / units)
   // rounds of tiles_per_split tiles (+ ~1 tile-time to swap the resident query tile).  Pick the
-  // split count with the best useful / occupied tile-slot ratio, keeping >= 8 tiles per item.
+  // split count with the best useful / occupied tile-slot ratio, keeping >= min_tiles_per_split
+  // tiles per item (8 for the streaming epilogues, 1 for small dense products).
   const int g_tiles = p.g_tiles > 0 ? p.g_tiles : 1;
   int best = 1;
   double best_eff = 0.0;
   for (int s = 1; s <= max_splits && s <= g_tiles; ++s) {
     const int tps = ceil_div(g_tiles, s);
-    if (s > 1 && tps < 8) break;
+    if (s > 1 && tps < min_tiles_per_split) break;
     const int64_t items = (int64_t)q_groups * ceil_div(g_tiles, tps);
     const int64_t rounds = ceil_div<int64_t>(items, units);
     const double eff =

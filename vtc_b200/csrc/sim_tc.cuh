@@ -13,7 +13,8 @@ constexpr int BK = 64;   // bf16 per k-block = one 128-byte swizzle atom
 
 enum Epilogue { EPI_RANK = 0, EPI_LSE = 1, EPI_STORE = 2, EPI_TOPK = 3 };
 
-constexpr int TOPK_POOL = 32;  // candidates kept per (row, gallery split)
+constexpr int TOPK_POOL = 64;  // buffer entries per (row, gallery split)
+constexpr int TOPK_KEEP = 32;  // entries kept when a buffer is compacted
 
 struct Params {
   int64_t N, M;          // valid rows of A (queries) and B (gallery)
@@ -38,14 +39,16 @@ struct Params {
   float* diag;          // [N] raw accumulator of column t + diag_offset (nullable)
   int64_t diag_offset;
   // EPI_STORE
-  float* out;  // [N, ldo]
+  float* out;  // [N, ldo] (nullable when only out_op is wanted)
   int64_t ldo;
+  __nv_bfloat16* out_op;  // optional: the result as query-side bf16 operand [N, out_op_kp]
+  int out_op_kp;
+  int out_op_split;       // 0: [x], 1: [hi | hi | lo] (VTC_PREC_EXACT)
   const float* residual;  // optional [N, ldo]
   int act;                // 0 none, 1 QuickGELU (applied after bias, before residual)
   // EPI_TOPK
-  float* pool_val;   // [g_splits, N, TOPK_POOL]
-  int* pool_idx;     // [g_splits, N, TOPK_POOL]
-  float2* pool_meta; // [g_splits, N] (fill, tau)
+  float2* pool;       // [g_splits, N, TOPK_POOL] (score, column index as int bits)
+  float2* pool_meta;  // [g_splits, N] (entries, tau): every column outside the pool scores >= tau
 };
 
 // Row-major bf16 [rows, cols] with leading dimension ld (elements) -> 2-D TMA descriptor with a
@@ -61,7 +64,7 @@ struct Plan {
   int grid;     // CTAs to launch (multiple of cluster)
 };
 // fills q_tiles / g_tiles / g_splits / tiles_per_split for the given cluster size
-Plan plan_tiles(Params& p, int max_splits, int cluster);
+Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split = 8);
 
 // a_resident: keep the whole 128 x K' query tile in shared memory (needs num_kb <= 8).
 // tmB must have been built with box_rows = BN / pl.cluster.

@@ -23,6 +23,8 @@
 // Work item = (query tile, gallery split); items are ordered so that CTAs running concurrently
 // sweep the same gallery range (B tiles are shared through the 126 MB L2).
 #pragma once
+#include <cuda_bf16.h>
+
 #include <cstring>
 
 #include "ptx.cuh"
@@ -184,13 +186,27 @@ struct LseEpi {
 struct StoreEpi {
   int64_t t;
   __device__ __forceinline__ void begin_item(const Params&, int64_t t_, int) { t = t_; }
+  // 8 floats -> 8 bf16 (RN) packed in a uint4; with `lo` the residuals x - bf16(x) instead
+  static __device__ __forceinline__ uint4 pack8(const float* y, bool lo) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat16 a = __float2bfloat16_rn(y[2 * i]), b = __float2bfloat16_rn(y[2 * i + 1]);
+      if (lo) {
+        a = __float2bfloat16_rn(y[2 * i] - __bfloat162float(a));
+        b = __float2bfloat16_rn(y[2 * i + 1] - __bfloat162float(b));
+      }
+      w[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
                                         unsigned int*) {
     if (t >= p.N) return;
-    float* o = p.out + t * p.ldo + jbase;
     const float* r = p.residual ? p.residual + t * p.ldo + jbase : nullptr;
-    const bool vec = (jbase + 32 <= p.M) && ((p.ldo & 3) == 0) &&
+    const bool full = jbase + 32 <= p.M;
+    const bool vec = full && ((p.ldo & 3) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                      (!r || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     float y[32];
@@ -205,61 +221,132 @@ struct StoreEpi {
         y[4 * i + e] = z;
       }
     }
-    if (vec) {
+    if (r) {
+      if (vec) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 w = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-        if (r) {
+        for (int i = 0; i < 8; ++i) {
           const float4 q = reinterpret_cast<const float4*>(r)[i];
-          w.x += q.x, w.y += q.y, w.z += q.z, w.w += q.w;
+          y[4 * i] += q.x, y[4 * i + 1] += q.y, y[4 * i + 2] += q.z, y[4 * i + 3] += q.w;
         }
-        reinterpret_cast<float4*>(o)[i] = w;
-      }
-    } else {
+      } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (jbase + i < p.M) o[i] = y[i] + (r ? r[i] : 0.f);
+        for (int i = 0; i < 32; ++i)
+          if (jbase + i < p.M) y[i] += r[i];
+      }
+    }
+    if (p.out) {
+      float* o = p.out + t * p.ldo + jbase;
+      if (vec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(o)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (jbase + i < p.M) o[i] = y[i];
+      }
+    }
+    if (p.out_op) {
+      // the result as the query-side bf16 operand of the NEXT GEMM: [x] or the split [hi|hi|lo]
+      __nv_bfloat16* oo = p.out_op + t * (int64_t)p.out_op_kp + jbase;
+      const bool ovec = full && ((p.M & 7) == 0) && ((p.out_op_kp & 7) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out_op) & 15) == 0);
+      if (ovec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 hi = pack8(y + 8 * i, false);
+          reinterpret_cast<uint4*>(oo)[i] = hi;
+          if (p.out_op_split) {
+            reinterpret_cast<uint4*>(oo + p.M)[i] = hi;
+            reinterpret_cast<uint4*>(oo + 2 * p.M)[i] = pack8(y + 8 * i, true);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (jbase + i < p.M) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(y[i]);
+            oo[i] = hi;
+            if (p.out_op_split) {
+              oo[p.M + i] = hi;
+              oo[2 * p.M + i] = __float2bfloat16_rn(y[i] - __bfloat162float(hi));
+            }
+          }
+        }
+      }
     }
   }
   __device__ __forceinline__ void end_item(const Params&, int) {}
 };
 
+// Streaming top-k: every row appends the scores that beat its threshold `tau` to a 64-entry
+// buffer in global memory (fire-and-forget stores); when a buffer is nearly full the WARP sorts
+// it cooperatively (bitonic network over 64 entries, two per lane), keeps the TOPK_KEEP smallest
+// and lowers tau to the largest kept score.  Invariant: every column that is not in the buffer has
+// score >= tau, which is what topk_select_kernel's completeness proof needs.  A row compacts only
+// O(log(M / 64)) times, so the per-column cost stays at one FFMA + one compare.
 struct TopkEpi {
   float tau;
-  int fill;
+  int cnt;
   int64_t t;
-  float* pv;
-  int* pi;
+  float2* buf;  // (score, column as int bits), TOPK_POOL entries
+
+  __device__ __forceinline__ float2* buf_of(const Params& p, int64_t row, int split) const {
+    return p.pool + ((int64_t)split * p.N + row) * TOPK_POOL;
+  }
   __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int split) {
     t = t_;
     tau = INFINITY;
-    fill = 0;
-    const int64_t slot = ((int64_t)split * p.N + (t < p.N ? t : 0)) * TOPK_POOL;
-    pv = p.pool_val + slot;
-    pi = p.pool_idx + slot;
-    if (t >= p.N) tau = -INFINITY;  // padded rows never insert
+    cnt = 0;
+    buf = buf_of(p, t < p.N ? t : 0, split);
+    if (t >= p.N) tau = -INFINITY;  // padded rows never append
   }
-  // rare (~pool * ln(M / pool) times per row): keep the TOPK_POOL smallest scores seen so far
-  __device__ __noinline__ void insert(float d, int j) {
-    if (!(d < tau)) return;
-    if (fill < TOPK_POOL) {
-      pv[fill] = d;
-      pi[fill] = j;
-      ++fill;
-      if (fill < TOPK_POOL) return;
-    } else {
-      int worst = 0;
-      float wv = pv[0];
-      for (int i = 1; i < TOPK_POOL; ++i) {
-        const float x = pv[i];
-        if (x > wv) wv = x, worst = i;
+  // warp-cooperative: sort lane `r`'s buffer, keep the TOPK_KEEP smallest, update its tau / cnt
+  __device__ __noinline__ void compact(int r) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)buf, r);
+    float2* rb = reinterpret_cast<float2*>(bp);
+    const int n = __shfl_sync(0xffffffffu, cnt, r);
+    __syncwarp();  // lane r's appends are visible to the whole warp
+    float2 e0 = lane < n ? rb[lane] : make_float2(INFINITY, 0.f);
+    float2 e1 = lane + 32 < n ? rb[lane + 32] : make_float2(INFINITY, 0.f);
+    // bitonic sort, ascending, of the 64 entries at positions p = lane (e0) and lane + 32 (e1)
+#pragma unroll
+    for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j >= 1; j >>= 1) {
+        if (j == 32) {  // partner is this lane's other slot; k == 64: ascending everywhere
+          if (e1.x < e0.x) {
+            const float2 tmp = e0;
+            e0 = e1;
+            e1 = tmp;
+          }
+        } else {
+          const bool lower = (lane & j) == 0;
+          {
+            const float ox = __shfl_xor_sync(0xffffffffu, e0.x, j);
+            const float oy = __shfl_xor_sync(0xffffffffu, e0.y, j);
+            const bool asc = (lane & k) == 0;  // position p = lane
+            const bool take = (lower == asc) ? (ox < e0.x) : (e0.x < ox);
+            if (take) e0 = make_float2(ox, oy);
+          }
+          {
+            const float ox = __shfl_xor_sync(0xffffffffu, e1.x, j);
+            const float oy = __shfl_xor_sync(0xffffffffu, e1.y, j);
+            const bool asc = ((lane + 32) & k) == 0;  // position p = lane + 32
+            const bool take = (lower == asc) ? (ox < e1.x) : (e1.x < ox);
+            if (take) e1 = make_float2(ox, oy);
+          }
+        }
       }
-      pv[worst] = d;
-      pi[worst] = j;
     }
-    float mx = pv[0];
-    for (int i = 1; i < TOPK_POOL; ++i) mx = fmaxf(mx, pv[i]);
-    tau = mx;
+    rb[lane] = e0;  // positions 0..31 = the TOPK_KEEP smallest
+    const float new_tau = __shfl_sync(0xffffffffu, e0.x, TOPK_KEEP - 1);
+    if (lane == r) {
+      cnt = TOPK_KEEP;
+      tau = new_tau;
+    }
+    __syncwarp();
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
@@ -279,14 +366,26 @@ struct TopkEpi {
       d[7] = fmaf(scale, __uint_as_float(v[8 * g + 7]), b1.w);
       const float mn = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])),
                              fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
-      if (mn < tau) {
+      if (mn < tau) {  // rare after the first few hundred columns
 #pragma unroll
-        for (int i = 0; i < 8; ++i) insert(d[i], (int)(jbase + 8 * g + i));
+        for (int i = 0; i < 8; ++i) {
+          if (d[i] < tau) {
+            buf[cnt] = make_float2(d[i], __int_as_float((int)(jbase + 8 * g + i)));
+            ++cnt;
+          }
+        }
+      }
+      // cnt <= TOPK_POOL - 8 before a group, so a group can never overflow the buffer
+      unsigned int full = __ballot_sync(0xffffffffu, cnt > TOPK_POOL - 8);
+      while (full) {
+        const int r = __ffs(full) - 1;
+        full &= full - 1;
+        compact(r);
       }
     }
   }
   __device__ __forceinline__ void end_item(const Params& p, int split) {
-    if (t < p.N) p.pool_meta[(int64_t)split * p.N + t] = make_float2((float)fill, tau);
+    if (t < p.N) p.pool_meta[(int64_t)split * p.N + t] = make_float2((float)cnt, tau);
   }
 };
 

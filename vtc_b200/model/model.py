@@ -87,6 +87,39 @@ class CAMTransformer(nn.Module):
         self.precision = precision
         self.resblocks = nn.Sequential(*[_ResBlock(width, heads) for _ in range(layers)])
 
+    # ---- prepared weights: bf16 tensor-core operands + padded biases, rebuilt only when a
+    # parameter changes (torch bumps `_version` on every in-place update / optimizer step)
+    def _param_key(self, extra=()):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple(extra)
+
+    def prepared(self):
+        """(ctypes array of vtc_cam_layer, keep-alive list) for vtc_cam_forward."""
+        key = self._param_key((self.precision,))
+        cache = getattr(self, "_prepared_cache", None)
+        if cache is not None and cache[0] == key:
+            return cache[1], cache[2]
+        keep = []
+        arr = (_ffi.CamLayer * len(self.resblocks))()
+        for i, blk in enumerate(self.resblocks):
+            def prep(w, b):
+                buf = ops.linear_prepare(w, b, self.precision)
+                keep.append(buf)
+                return buf.data_ptr()
+
+            def f32(t):
+                t = t.detach().float().contiguous()
+                keep.append(t)
+                return t.data_ptr()
+
+            arr[i].ln1_g, arr[i].ln1_b = f32(blk.ln_1.weight), f32(blk.ln_1.bias)
+            arr[i].ln2_g, arr[i].ln2_b = f32(blk.ln_2.weight), f32(blk.ln_2.bias)
+            arr[i].qkv = prep(blk.attn.in_proj_weight, blk.attn.in_proj_bias)
+            arr[i].out = prep(blk.attn.out_proj.weight, blk.attn.out_proj.bias)
+            arr[i].fc = prep(blk.mlp.c_fc.weight, blk.mlp.c_fc.bias)
+            arr[i].proj = prep(blk.mlp.c_proj.weight, blk.mlp.c_proj.bias)
+        self._prepared_cache = (key, arr, keep)
+        return arr, keep
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
@@ -133,23 +166,33 @@ class PretrainedCLIPBase(nn.Module):
         if not isinstance(features_aux, torch.Tensor):
             features_aux = torch.stack(list(features_aux), dim=0)
         assert features_aux.shape[1] == b
-        concat_feats = ops.cam_stack_normalize(feature_main, features_aux)       # :150-151
-        comm_tfm = self.final_transformer(concat_feats)                          # :155
-
+        tfm = self.final_transformer
+        if torch.is_grad_enabled() and any(p.requires_grad for p in tfm.parameters()):
+            raise NotImplementedError(
+                "the CAM is forward-only in this round (wrap the call in torch.no_grad(); the CAM "
+                "backward kernels are listed as next in DESIGN.md)")
         # the reference draws one number from the global CPU RNG here for a 5 % debug print
         # (:163); keep the draw so RNG streams stay aligned with it, drop the print.
         torch.rand([])
-
         skip_mask = None
         if self.training and self.random_skip_adapter:
             skip_mask = torch.rand(b) > 0.5                                      # :199-201
-        if self.init_from_avg:
-            return ops.cam_readout(comm_tfm, feature_main, _ffi.CAM_READOUT_AVG,
-                                   skip_mask=skip_mask)                          # :156-159,:203
-        comm_res = ops.linear(comm_tfm[0], self.final_linear.weight,
-                              precision=self.precision)                          # :161
-        return ops.cam_readout(None, feature_main, _ffi.CAM_READOUT_RESIDUAL_ONLY,
-                               res_in=comm_res, skip_mask=skip_mask)             # :203
+        layers, _keep = tfm.prepared()
+        final = None
+        if not self.init_from_avg:                                               # :161
+            w = self.final_linear.weight
+            key = (w.data_ptr(), w._version, self.precision)
+            cache = getattr(self, "_final_prepared", None)
+            if cache is None or cache[0] != key:
+                cache = (key, ops.linear_prepare(w, None, self.precision))
+                self._final_prepared = cache
+            final = cache[1]
+        # stack + normalize (:150-151) -> transformer (:155) -> read-out (:156-161) -> skip
+        # (:199-201) -> normalize(normalize(main) + res) (:203): 2 + 7 * layers launches
+        return ops.cam_forward(feature_main, features_aux, layers, tfm.heads,
+                               _ffi.CAM_READOUT_AVG if self.init_from_avg
+                               else _ffi.CAM_READOUT_RESIDUAL_ONLY,
+                               final_linear=final, skip_mask=skip_mask, precision=self.precision)
 
     def _load_comment_features(self, comments) -> torch.Tensor:
         """model/model.py:207-214.  `comments` is either precomputed comment embeddings

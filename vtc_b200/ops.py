@@ -400,3 +400,50 @@ def cam_readout(T: Optional[torch.Tensor], main: Optional[torch.Tensor], mode: i
                                                L, b, D, mode, _ptr(out), _stream(dev)),
                    "vtc_cam_readout")
     return out
+
+
+# --------------------------------------------------------------------- H4 in one call (prepared)
+def linear_prepare(w: torch.Tensor, bias: Optional[torch.Tensor], precision="exact") -> torch.Tensor:
+    """Weight [out, in] (+bias) -> opaque prepared buffer (bf16 gallery-side operand + padded bias)."""
+    dev = _req_cuda(w, bias)
+    w = w.detach().float().contiguous()
+    out_f, in_f = w.shape
+    prec = _prec(precision)
+    lib = _ffi.load()
+    nbytes = lib.vtc_linear_prepared_bytes(in_f, out_f, prec)
+    if nbytes == 0:
+        raise VtcError("vtc_linear_prepared_bytes rejected the arguments")
+    buf = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    b = None if bias is None else bias.detach().float().contiguous()
+    with torch.cuda.device(dev):
+        _ffi.check(lib.vtc_linear_prepare(_ptr(w), _ptr(b), in_f, out_f, prec, _ptr(buf), _stream(dev)),
+                   "vtc_linear_prepare")
+    return buf
+
+
+def cam_forward(main: torch.Tensor, aux: torch.Tensor, layers, heads: int, readout_mode: int,
+                final_linear: Optional[torch.Tensor] = None, skip_mask: Optional[torch.Tensor] = None,
+                precision="exact") -> torch.Tensor:
+    """PretrainedCLIPBase._adapt_feature (model/model.py:141-205) in one C call.
+
+    `layers` is a ctypes array of _ffi.CamLayer built from prepared linears (see
+    vtc_b200.model.model.CAMTransformer.prepared)."""
+    dev = _req_cuda(main, aux, final_linear, skip_mask)
+    main = main.float().contiguous()
+    aux = aux.float().contiguous()
+    b, D = main.shape
+    nc = aux.shape[0]
+    if aux.shape[1:] != (b, D):
+        raise ValueError("aux must be [nc, b, D]")
+    prec = _prec(precision)
+    if skip_mask is not None:
+        skip_mask = skip_mask.to(device=dev, dtype=torch.uint8).contiguous()
+    out = torch.empty(b, D, dtype=torch.float32, device=dev)
+    lib = _ffi.load()
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, int(lib.vtc_cam_workspace_bytes(nc + 1, b, D, prec)))
+        _ffi.check(lib.vtc_cam_forward(_ptr(main), _ptr(aux), nc + 1, b, D, heads, len(layers), layers,
+                                       readout_mode, _ptr(final_linear), _ptr(skip_mask), prec,
+                                       _ptr(out), _ptr(ws), ws.numel(), _stream(dev)),
+                   "vtc_cam_forward")
+    return out
