@@ -94,10 +94,12 @@ struct RankEpi {
   // rare: this row has a score inside the guard band among columns [j, j+8): hand the whole group
   // to the fp64 re-check (its definite count is NOT added here).  List segments are per CTA, slots
   // come from a shared-memory counter, so there is no global atomic hot spot.
-  __device__ __noinline__ void push_group(const Params& p, unsigned int* seg_count, int64_t j) {
+  // (static + by-value arguments: a member function would force the epilogue state through
+  // `this`, i.e. into local memory, on the hot path)
+  static __device__ __noinline__ void push_group(int2* __restrict__ seg_list, unsigned int seg_cap,
+                                                 unsigned int* seg_count, int t, int j) {
     const unsigned int slot = atomicAdd(seg_count, 1u);
-    if (slot < p.amb_seg_cap)
-      p.amb_list[(size_t)blockIdx.x * p.amb_seg_cap + slot] = make_int2((int)t, (int)j);
+    if (slot < seg_cap) seg_list[slot] = make_int2(t, j);
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
@@ -125,7 +127,8 @@ struct RankEpi {
                        ((d4 <= hi ? 1.f : 0.f) + (d5 <= hi ? 1.f : 0.f)) +
                        ((d6 <= hi ? 1.f : 0.f) + (d7 <= hi ? 1.f : 0.f));
       if (le != lt)
-        push_group(p, seg_count, jbase + RANK_GROUP * g);
+        push_group(p.amb_list + (size_t)blockIdx.x * p.amb_seg_cap, p.amb_seg_cap, seg_count,
+                   (int)t, (int)(jbase + RANK_GROUP * g));
       else
         csum += lt;
     }
@@ -301,12 +304,14 @@ struct TopkEpi {
     buf = buf_of(p, t < p.N ? t : 0, split);
     if (t >= p.N) tau = -INFINITY;  // padded rows never append
   }
-  // warp-cooperative: sort lane `r`'s buffer, keep the TOPK_KEEP smallest, update its tau / cnt
-  __device__ __noinline__ void compact(int r) {
+  // warp-cooperative: sort lane `r`'s buffer (`my_buf` / `my_cnt` are each lane's own), keep the
+  // TOPK_KEEP smallest in place and return the new threshold to every lane.  Static with by-value
+  // arguments so that the epilogue state stays in registers (no `this` escaping to local memory).
+  static __device__ __noinline__ float compact(float2* my_buf, int my_cnt, int r) {
     const int lane = threadIdx.x & 31;
-    const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)buf, r);
+    const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
     float2* rb = reinterpret_cast<float2*>(bp);
-    const int n = __shfl_sync(0xffffffffu, cnt, r);
+    const int n = __shfl_sync(0xffffffffu, my_cnt, r);
     __syncwarp();  // lane r's appends are visible to the whole warp
     float2 e0 = lane < n ? rb[lane] : make_float2(INFINITY, 0.f);
     float2 e1 = lane + 32 < n ? rb[lane + 32] : make_float2(INFINITY, 0.f);
@@ -342,11 +347,8 @@ struct TopkEpi {
     }
     rb[lane] = e0;  // positions 0..31 = the TOPK_KEEP smallest
     const float new_tau = __shfl_sync(0xffffffffu, e0.x, TOPK_KEEP - 1);
-    if (lane == r) {
-      cnt = TOPK_KEEP;
-      tau = new_tau;
-    }
     __syncwarp();
+    return new_tau;
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
@@ -380,7 +382,11 @@ struct TopkEpi {
       while (full) {
         const int r = __ffs(full) - 1;
         full &= full - 1;
-        compact(r);
+        const float nt = compact(buf, cnt, r);
+        if ((int)(threadIdx.x & 31) == r) {
+          cnt = TOPK_KEEP;
+          tau = nt;
+        }
       }
     }
   }
