@@ -287,7 +287,8 @@ def test_recall_at_k_update_result_protocol(cuda_dev):
 # ------------------------------------------------------------------------------------------ K7
 @pytest.mark.parametrize("precision", ["brute", "exact", "bf16"])
 @pytest.mark.parametrize("metric", ["l2", "dot"])
-def test_topk_matches_oracle(cuda_dev, precision, metric):
+@pytest.mark.parametrize("k", [11, 16])
+def test_topk_matches_oracle(cuda_dev, precision, metric, k):
     from vtc_b200 import ops
 
     T, V = make_retrieval_pair(300, 5000, 256, sigma=3.0, seed=31)
@@ -295,7 +296,6 @@ def test_topk_matches_oracle(cuda_dev, precision, metric):
     V[100] = V[7]
     V[4000] = V[7]  # exact ties across tiles
     V[50] *= 0.5    # non-unit row
-    k = 11
     vals, idx = ops.sim_topk(T.to(cuda_dev), V.to(cuda_dev), k, metric=metric, precision=precision,
                              col_offset=1000)
     Tq, Vq = (O.bf16_round(T), O.bf16_round(V)) if precision == "bf16" else (T.numpy(), V.numpy())

@@ -263,6 +263,7 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
   p.pool = w.pool, p.pool_meta = w.pool_meta;
+  p.topk_keep = k <= 12 ? 16 : tc::TOPK_KEEP_MAX;
   const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, tc::choose_cluster(N, M));
   a.splits = p.g_splits;
   CUtensorMap tmA, tmB;

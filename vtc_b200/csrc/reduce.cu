@@ -84,6 +84,7 @@ template <typename T>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 topk_select_kernel(TopkSelectArgs a) {
   __shared__ double cd[SEL_WARPS][SEL_MAX_CAND];
+  __shared__ float ca[SEL_WARPS][SEL_MAX_CAND];
   __shared__ int cj[SEL_WARPS][SEL_MAX_CAND];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * SEL_WARPS + w;
@@ -92,28 +93,71 @@ topk_select_kernel(TopkSelectArgs a) {
   const T* G = (const T*)a.ex.G;
   const T* q = Q + t * a.ex.ldq;
   const int ncand = a.splits * a.pool;
-  // exact re-scoring of every pooled candidate
+  // 1. gather the pooled candidates (approximate score, column)
   for (int c = lane; c < ncand; c += 32) {
     const int s = c / a.pool, i = c % a.pool;
     const int64_t slot = (int64_t)s * a.ex.N + t;
     const int fill = (int)a.pool_meta[slot].x;
     int j = -1;
-    double d = 0.0;
+    float ap = INFINITY;
     if (i < fill) {
-      j = __float_as_int(a.pool_buf[slot * a.pool + i].y);
-      if (j >= 0 && j < a.ex.M) {
-        d = exact_score(q, G + (int64_t)j * a.ex.ldg, a.ex.D, a.ex.metric,
-                        a.ex.metric == VTC_METRIC_L2 ? a.ex.sq64[j] : 0.0);
-        if (d != d) j = -1;  // NaN scores are never selected
-      } else {
-        j = -1;
-      }
+      const float2 e = a.pool_buf[slot * a.pool + i];
+      j = __float_as_int(e.y);
+      ap = e.x;
+      if (j < 0 || j >= a.ex.M || ap != ap) j = -1;
+    }
+    ca[w][c] = ap;
+    cj[w][c] = j;
+  }
+  __syncwarp();
+  const double qq = sq_seq64(q, a.ex.D);  // every lane computes it (keeps the warp convergent)
+  const double qn = sqrt(qq);
+  const double gmax_sq = (double)__uint_as_float(*a.max_sq_bits);
+  const double gn = sqrt(gmax_sq);
+  const double delta = a.ex.metric == VTC_METRIC_L2
+                           ? 2.0 * a.guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn)
+                           : (double)a.guard_rel * qn * gn + 1.2e-7 * qn * gn;
+  // 2. k-th smallest APPROXIMATE score a_k (k rounds of "smallest (value, slot) above the last")
+  float last_v = -INFINITY;
+  int last_c = -1;
+  int have = 0;
+  for (int r = 0; r < a.k; ++r) {
+    float bv = INFINITY;
+    int bc = 0x7fffffff;
+    for (int c = lane; c < ncand; c += 32) {
+      if (cj[w][c] < 0) continue;
+      const float x = ca[w][c];
+      const bool above = x > last_v || (x == last_v && c > last_c);
+      if (above && (x < bv || (x == bv && c < bc))) bv = x, bc = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (ov < bv || (ov == bv && oc < bc)) bv = ov, bc = oc;
+    }
+    if (bc == 0x7fffffff) break;
+    last_v = bv, last_c = bc;
+    ++have;
+  }
+  // every member of the exact top-k has approximate score <= a_k + 2 delta
+  const double thr = have == a.k ? (double)last_v + 2.0 * delta : INFINITY;
+  // 3. exact re-scoring of the candidates that can still be in the top-k
+  for (int c = lane; c < ncand; c += 32) {
+    int j = cj[w][c];
+    double d = 0.0;
+    if (j >= 0 && (double)ca[w][c] <= thr) {
+      d = exact_score(q, G + (int64_t)j * a.ex.ldg, a.ex.D, a.ex.metric,
+                      a.ex.metric == VTC_METRIC_L2 ? a.ex.sq64[j] : 0.0);
+      if (d != d) j = -1;  // NaN scores are never selected
+    } else {
+      j = -1;
     }
     cd[w][c] = d;
     cj[w][c] = j;
   }
   __syncwarp();
-  const double qq = sq_seq64(q, a.ex.D);  // every lane computes it (keeps the warp convergent)
+  // 4. exact selection by (score, column)
   double dk = -INFINITY;  // exact score of the last selected candidate
   int found = 0;
   for (int r = 0; r < a.k; ++r) {
@@ -144,16 +188,10 @@ topk_select_kernel(TopkSelectArgs a) {
     }
     __syncwarp();
   }
-  // completeness: every column outside a pool has approx score >= its tau (+inf while the pool
+  // 5. completeness: every column outside a pool has approx score >= its tau (+inf while the pool
   // still holds every column seen), hence exact score >= tau - delta; the selection is provably
   // right when the k-th exact score is below that.
   if (lane == 0) {
-    const double qn = sqrt(qq);
-    const double gmax_sq = (double)__uint_as_float(*a.max_sq_bits);
-    const double gn = sqrt(gmax_sq);
-    const double delta = a.ex.metric == VTC_METRIC_L2
-                             ? 2.0 * a.guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn)
-                             : (double)a.guard_rel * qn * gn + 1.2e-7 * qn * gn;
     bool ok = qq == qq;
     for (int s = 0; s < a.splits; ++s) {
       const float2 meta = a.pool_meta[(int64_t)s * a.ex.N + t];

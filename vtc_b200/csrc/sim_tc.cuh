@@ -14,7 +14,7 @@ constexpr int BK = 64;   // bf16 per k-block = one 128-byte swizzle atom
 enum Epilogue { EPI_RANK = 0, EPI_LSE = 1, EPI_STORE = 2, EPI_TOPK = 3 };
 
 constexpr int TOPK_POOL = 64;  // buffer entries per (row, gallery split)
-constexpr int TOPK_KEEP = 32;  // entries kept when a buffer is compacted
+constexpr int TOPK_KEEP_MAX = 32;  // entries kept when a buffer is compacted: 16 for k <= 12, else 32
 
 struct Params {
   int64_t N, M;          // valid rows of A (queries) and B (gallery)
@@ -49,6 +49,7 @@ struct Params {
   // EPI_TOPK
   float2* pool;       // [g_splits, N, TOPK_POOL] (score, column index as int bits)
   float2* pool_meta;  // [g_splits, N] (entries, tau): every column outside the pool scores >= tau
+  int topk_keep;      // entries kept by a compaction (>= k, <= TOPK_KEEP_MAX)
 };
 
 // Row-major bf16 [rows, cols] with leading dimension ld (elements) -> 2-D TMA descriptor with a

@@ -307,7 +307,7 @@ struct TopkEpi {
   // warp-cooperative: sort lane `r`'s buffer (`my_buf` / `my_cnt` are each lane's own), keep the
   // TOPK_KEEP smallest in place and return the new threshold to every lane.  Static with by-value
   // arguments so that the epilogue state stays in registers (no `this` escaping to local memory).
-  static __device__ __noinline__ float compact(float2* my_buf, int my_cnt, int r) {
+  static __device__ __noinline__ float compact(float2* my_buf, int my_cnt, int r, int keep) {
     const int lane = threadIdx.x & 31;
     const unsigned long long bp = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
     float2* rb = reinterpret_cast<float2*>(bp);
@@ -345,36 +345,29 @@ struct TopkEpi {
         }
       }
     }
-    rb[lane] = e0;  // positions 0..31 = the TOPK_KEEP smallest
-    const float new_tau = __shfl_sync(0xffffffffu, e0.x, TOPK_KEEP - 1);
+    if (lane < keep) rb[lane] = e0;  // positions 0..keep-1 = the `keep` smallest
+    const float new_tau = __shfl_sync(0xffffffffu, e0.x, keep - 1);
     __syncwarp();
     return new_tau;
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
                                         unsigned int*) {
+    const int keep = p.topk_keep;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float4 b0 = reinterpret_cast<const float4*>(bias)[2 * g];
       const float4 b1 = reinterpret_cast<const float4*>(bias)[2 * g + 1];
-      float d[8];
-      d[0] = fmaf(scale, __uint_as_float(v[8 * g + 0]), b0.x);
-      d[1] = fmaf(scale, __uint_as_float(v[8 * g + 1]), b0.y);
-      d[2] = fmaf(scale, __uint_as_float(v[8 * g + 2]), b0.z);
-      d[3] = fmaf(scale, __uint_as_float(v[8 * g + 3]), b0.w);
-      d[4] = fmaf(scale, __uint_as_float(v[8 * g + 4]), b1.x);
-      d[5] = fmaf(scale, __uint_as_float(v[8 * g + 5]), b1.y);
-      d[6] = fmaf(scale, __uint_as_float(v[8 * g + 6]), b1.z);
-      d[7] = fmaf(scale, __uint_as_float(v[8 * g + 7]), b1.w);
-      const float mn = fminf(fminf(fminf(d[0], d[1]), fminf(d[2], d[3])),
-                             fminf(fminf(d[4], d[5]), fminf(d[6], d[7])));
-      if (mn < tau) {  // rare after the first few hundred columns
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      // branch-free appends: with 32 independent rows per warp SOME lane beats its threshold in
+      // almost every group, so a "rare path" branch would be taken all the time; predicated stores
+      // cost three issue slots per column and no divergence
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (d[i] < tau) {
-            buf[cnt] = make_float2(d[i], __int_as_float((int)(jbase + 8 * g + i)));
-            ++cnt;
-          }
+      for (int i = 0; i < 8; ++i) {
+        const float d = fmaf(scale, __uint_as_float(v[8 * g + i]), bb[i]);
+        if (d < tau) {
+          buf[cnt] = make_float2(d, __int_as_float((int)(jbase + 8 * g + i)));
+          ++cnt;
         }
       }
       // cnt <= TOPK_POOL - 8 before a group, so a group can never overflow the buffer
@@ -382,9 +375,9 @@ struct TopkEpi {
       while (full) {
         const int r = __ffs(full) - 1;
         full &= full - 1;
-        const float nt = compact(buf, cnt, r);
+        const float nt = compact(buf, cnt, r, keep);
         if ((int)(threadIdx.x & 31) == r) {
-          cnt = TOPK_KEEP;
+          cnt = keep;
           tau = nt;
         }
       }
