@@ -67,6 +67,17 @@ enum {
 /* CAM read-out modes (model/model.py:156-161, :356-362) */
 enum { VTC_CAM_READOUT_AVG = 0, VTC_CAM_READOUT_RESIDUAL_ONLY = 1, VTC_CAM_READOUT_UNIFORM = 2 };
 
+/* residual activations applied to the CAM residual (model/model.py:30-77, :168-171):
+ * NORMALIZE_EPS = "normalize", SQUASH = "squash*" (res_scale = 1, 10, 1.2, 1.5, 1.8), TANH,
+ * AFFINE = eval-mode "sub_mean" / "bn": (x - res_shift) * res_mul with the BatchNorm running stats */
+enum {
+  VTC_RESACT_NONE = 0,
+  VTC_RESACT_NORMALIZE_EPS = 1,
+  VTC_RESACT_SQUASH = 2,
+  VTC_RESACT_TANH = 3,
+  VTC_RESACT_AFFINE = 4
+};
+
 enum {
   VTC_OK = 0,
   VTC_ERR_INVALID_ARG = -1,
@@ -122,7 +133,7 @@ int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int
 /* rank0[t] = M_total where gt_score[t] is NaN ("never retrieved"); hits[i] = #{t: rank0[t] <
  * k_vals[i]} (int64, device; replaces model/metric.py:149-160); k_vals is a HOST array, nk <= 8.
  * medr (device double, may be NULL) = median(rank0) + 1 with numpy semantics.
- * hist_ws: >= (3*65536+8)*4 bytes of workspace when medr != NULL. */
+ * hist_ws: >= (3*65536+8)*4 bytes of workspace when medr != NULL (three-level radix select). */
 int vtc_rank_finalize(int32_t* rank0, const double* gt_score, int64_t N, int64_t M_total,
                       const int* k_vals, int nk, int64_t* hits, double* medr, void* hist_ws,
                       size_t hist_ws_bytes, vtc_stream_t stream);
@@ -172,7 +183,8 @@ int vtc_cam_attn_core(const float* QKV, int L, int64_t b, int D, int heads, floa
 int vtc_bias_act(const float* X, const float* bias, const float* residual, int64_t rows, int D,
                  int act, float* Y, vtc_stream_t stream);
 int vtc_cam_readout(const float* T, const float* main, const float* res_in,
-                    const uint8_t* skip_mask, int L, int64_t b, int D, int mode, float* out,
+                    const uint8_t* skip_mask, int L, int64_t b, int D, int mode, int res_act,
+                    float res_scale, const float* res_shift, const float* res_mul, float* out,
                     vtc_stream_t stream);
 
 /* ---- dense linear on the tensor cores (CAM projections / MLP) ----------------------------------
@@ -201,7 +213,8 @@ int vtc_linear_prepare(const float* W, const float* bias, int in_f, int out_f, i
 size_t vtc_cam_workspace_bytes(int L, int64_t b, int D, int precision);
 int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D, int heads,
                     int layers, const vtc_cam_layer* layers_params, int readout_mode,
-                    const void* final_linear_prepared, const uint8_t* skip_mask, int precision,
+                    const void* final_linear_prepared, const uint8_t* skip_mask, int res_act,
+                    float res_scale, const float* res_shift, const float* res_mul, int precision,
                     float* out, void* ws, size_t ws_bytes, vtc_stream_t stream);
 
 /* number of kernels this library has launched since load (for bench.py's gpu_launches). */

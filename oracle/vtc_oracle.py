@@ -426,11 +426,36 @@ def transformer(x: torch.Tensor, p: Dict[str, torch.Tensor], layers: int, heads:
     return x
 
 
+def residual_activation_fn(name, bn_state=None):
+    """model/model.py:30-77 (eval-mode forms of the stateful `sub_mean` / `bn`);
+    bn_state = (running_mean, running_var, eps) of the BatchNorm1d(affine=False) at :133-139."""
+    def squash(s):                                                       # :34-39
+        s = s + 1e-9
+        mag_sq = torch.sum(s ** 2, dim=-1, keepdim=True)
+        mag = torch.sqrt(mag_sq)
+        return (mag_sq / (1.0 + mag_sq)) * (s / mag)
+
+    table = {
+        None: lambda x: x, "none": lambda x: x,
+        "normalize": lambda x: normalize(x + 1e-9),                      # :30-31
+        "squash": squash, "squash10": lambda x: 10 * squash(x),
+        "squash1p2": lambda x: 1.2 * squash(x), "squash1p5": lambda x: 1.5 * squash(x),
+        "squash1p8": lambda x: 1.8 * squash(x),
+        "tanh": torch.tanh,
+    }
+    if name == "sub_mean":                                               # :42-51 (eval branch)
+        return lambda x: x - bn_state[0]
+    if name == "bn":                                                     # :54-61 (eval)
+        return lambda x: (x - bn_state[0]) / torch.sqrt(bn_state[1] + bn_state[2])
+    return table[name]
+
+
 def adapt_feature(feature_main: torch.Tensor, features_aux, params: Dict[str, torch.Tensor],
                   layers: int, heads: int, init_from_avg: bool = True,
                   final_linear_weight: Optional[torch.Tensor] = None,
-                  skip_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """model/model.py:141-205 with residual_activation None/'none' (identity, :65-77).
+                  skip_mask: Optional[torch.Tensor] = None, residual_activation=None,
+                  bn_state=None) -> torch.Tensor:
+    """model/model.py:141-205; residual activations per :65-77 (default None = identity).
 
     ``skip_mask`` [b] bool reproduces the train-time random adapter skip (:199-201) with the
     mask supplied by the caller (the reference draws it from the global CPU RNG)."""
@@ -442,6 +467,7 @@ def adapt_feature(feature_main: torch.Tensor, features_aux, params: Dict[str, to
         res = normalize(torch.mean(torch.stack([normalize(s) for s in tfm], 0), dim=0))  # :156-159
     else:
         res = tfm[0] @ final_linear_weight.t()                           # :161
+    res = residual_activation_fn(residual_activation, bn_state)(res)     # :168-171
     if skip_mask is not None:
         res = res.clone()
         res[skip_mask] = 0.0                                             # :199-201

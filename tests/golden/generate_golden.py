@@ -145,6 +145,25 @@ def gen_cam(model_mod):
             for k, v in params.items():
                 out["small_param/" + k] = v.numpy()
         print("cam", name, adapted.shape, float(adapted.norm(dim=-1).mean()))
+    # residual-activation variants (model/model.py:30-77) on the stored small case
+    b, nc, D, layers, heads = 8, 3, 64, 2, 2
+    params = O.make_cam_params(D, layers, heads, seed=1023, rerandomise=True)
+    main, aux = make_cam_inputs(b, nc, D, seed=1023)
+    g = torch.Generator().manual_seed(7)
+    run_mean = 0.05 * torch.randn(D, generator=g)
+    run_var = 0.5 + torch.rand(D, generator=g)
+    out["act_running_mean"] = run_mean.numpy()
+    out["act_running_var"] = run_var.numpy()
+    for act in ("normalize", "squash", "squash10", "squash1p5", "tanh", "sub_mean", "bn"):
+        cam = RS.make_ref_cam(D, layers, heads, params=params, residual_activation=act)
+        cam._common_init()                                  # creates mean_center_bn when needed
+        if act in ("sub_mean", "bn"):
+            cam.mean_center_bn.running_mean.copy_(run_mean)
+            cam.mean_center_bn.running_var.copy_(run_var)
+        cam.eval()
+        with torch.no_grad():
+            out["act_" + act] = cam._adapt_feature(main, aux).numpy()
+        print("cam act", act, float(np.abs(out["act_" + act]).max()))
     np.savez_compressed(os.path.join(OUT, "cam.npz"), **out)
 
 

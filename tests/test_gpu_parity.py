@@ -267,6 +267,22 @@ def test_recall_pipelined_host_staging(cuda_dev):
         assert _np(full["medr"])[0] == O.medr(want)
 
 
+def test_recall_from_cached_embedding_files(cuda_dev, tmp_path):
+    """the reference's cached-feature .pth files feed the eval kernels."""
+    from vtc_b200.data import recall_from_cached
+
+    T, V = make_retrieval_pair(500, 500, 128, sigma=3.0, seed=8)
+    ids = torch.arange(1000, 1500, dtype=torch.int64)
+    perm = torch.randperm(500, generator=torch.Generator().manual_seed(1))
+    torch.save({"reddit_ids": ids, "embeddings": V * 3.0}, tmp_path / "v.pth")          # un-normalised
+    torch.save({"reddit_ids": ids[perm], "embeddings": (T * 0.5)[perm]}, tmp_path / "t.pth")  # shuffled
+    df = recall_from_cached(str(tmp_path / "v.pth"), str(tmp_path / "t.pth"), split="s", dataset_name="d")
+    want = O.compute_recall(O.normalize(V * 3.0), O.normalize(T * 0.5).unsqueeze(1), split="s",
+                            dataset_name="d")
+    assert list(df.columns) == list(want.columns)
+    np.testing.assert_array_equal(df.values, want.values)
+
+
 def test_recall_at_k_update_result_protocol(cuda_dev):
     from vtc_b200.model.metric import MetricTracker, RecallAtK
 
@@ -430,6 +446,27 @@ def test_cam_adapt_feature_golden(cuda_dev, golden, name, precision):
     tol = dict(rtol=1e-4, atol=1e-5) if precision == "exact" else dict(rtol=2e-2, atol=2e-3)
     np.testing.assert_allclose(_np(out)[:want.shape[0]], want, **tol)
     np.testing.assert_allclose(_np(out.norm(dim=-1)), 1.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("act", ["normalize", "squash", "squash10", "squash1p5", "tanh", "sub_mean", "bn"])
+def test_cam_residual_activations_golden(cuda_dev, golden, act):
+    """the residual-activation table of model/model.py:30-77 inside the fused
+    read-out kernel, against the reference's own outputs."""
+    from vtc_b200.model import PretrainedCLIP_finaltf
+
+    g = golden("cam.npz")
+    b, nc, D, layers, heads = 8, 3, 64, 2, 2
+    params = O.make_cam_params(D, layers, heads, seed=1023, rerandomise=True)
+    m = PretrainedCLIP_finaltf(D, n_layers=layers, n_heads=heads, residual_activation=act)
+    m.final_transformer.load_state_dict(params, strict=True)
+    if act in ("sub_mean", "bn"):
+        m.mean_center_bn.running_mean.copy_(torch.from_numpy(g["act_running_mean"]))
+        m.mean_center_bn.running_var.copy_(torch.from_numpy(g["act_running_var"]))
+    m = m.to(cuda_dev).eval()
+    main, aux = make_cam_inputs(b, nc, D, seed=1023)
+    with torch.no_grad():
+        out = m._adapt_feature(main.to(cuda_dev), aux.to(cuda_dev))
+    np.testing.assert_allclose(_np(out), g["act_" + act], rtol=2e-4, atol=1e-5)
 
 
 def test_cam_transformer_module_forward(cuda_dev):

@@ -82,3 +82,30 @@ def test_synthetic_recipe_is_calibrated():
     np.testing.assert_allclose(T.norm(dim=-1).numpy(), 1.0, rtol=1e-5)
     cos = (T * V).sum(1)
     assert abs(cos.mean().item() - 1 / np.sqrt(1 + 36)) < 0.01
+
+
+def test_cached_embedding_reader_and_alignment(tmp_path):
+    """The reference's cached-feature format (scripts/get_clip_vit_embeddings.py:72-78)."""
+    from vtc_b200.data import align_by_id, load_cached_embeddings
+
+    g = torch.Generator().manual_seed(0)
+    ids_a = torch.tensor([7, 3, 11, 5, 2], dtype=torch.int64)
+    ids_b = torch.tensor([5, 7, 2, 99, 3], dtype=torch.int64)
+    ea, eb = torch.randn(5, 8, generator=g), torch.randn(5, 8, generator=g)
+    pa, pb = tmp_path / "a.pth", tmp_path / "b.pth"
+    torch.save({"reddit_ids": ids_a, "embeddings": ea}, pa)
+    torch.save({"reddit_ids": ids_b, "embeddings": eb}, pb)
+    ia, xa = load_cached_embeddings(str(pa), pin=False)
+    ib, xb = load_cached_embeddings(str(pb), pin=False)
+    assert torch.equal(ia, ids_a) and torch.equal(xa, ea)
+    ids, va, vb = align_by_id(ia, xa, ib, xb)
+    assert ids.tolist() == [7, 3, 5, 2]  # file-a order, shared ids only
+    assert torch.equal(va[0], ea[0]) and torch.equal(vb[0], eb[1])
+    assert torch.equal(va[3], ea[4]) and torch.equal(vb[3], eb[2])
+    ids2, _, _ = align_by_id(ia, xa, ib, xb, order=[2, 7])
+    assert ids2.tolist() == [2, 7]
+    with pytest.raises(KeyError):
+        align_by_id(ia, xa, ib, xb, order=[11])
+    torch.save({"reddit_ids": ids_a.int(), "embeddings": ea}, pa)
+    with pytest.raises(AssertionError):
+        load_cached_embeddings(str(pa), pin=False)

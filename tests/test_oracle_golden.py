@@ -111,6 +111,18 @@ def test_cam_golden(golden):
         np.testing.assert_allclose(tfm[0, :8].numpy(), g[name + "_tfm_tok0"], rtol=1e-4, atol=2e-6)
 
 
+def test_cam_residual_activations_golden(golden):
+    """model/model.py:30-77 variants against what the reference's own table produced."""
+    g = golden("cam.npz")
+    b, nc, D, layers, heads = 8, 3, 64, 2, 2
+    params = O.make_cam_params(D, layers, heads, seed=1023, rerandomise=True)
+    main, aux = make_cam_inputs(b, nc, D, seed=1023)
+    bn = (torch.from_numpy(g["act_running_mean"]), torch.from_numpy(g["act_running_var"]), 1e-5)
+    for act in ("normalize", "squash", "squash10", "squash1p5", "tanh", "sub_mean", "bn"):
+        out = O.adapt_feature(main, aux, params, layers, heads, residual_activation=act, bn_state=bn)
+        np.testing.assert_allclose(out.numpy(), g["act_" + act], rtol=1e-4, atol=2e-6)
+
+
 def test_cam_closed_form_at_init():
     """SURVEY.md App. B #10: reference zero-inits make the transformer an identity."""
     params = O.make_cam_params(512, 2, 8, seed=1023)

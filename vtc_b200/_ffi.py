@@ -17,6 +17,7 @@ METRIC_DOT, METRIC_L2 = 0, 1
 PREC_EXACT, PREC_BF16, PREC_BRUTE = 0, 1, 2
 OP_SIM_RANK, OP_SIM_TOPK, OP_INFONCE_FWD, OP_SIM_MATRIX, OP_INFONCE_BWD, OP_GT_SCORES, OP_LINEAR = range(7)
 CAM_READOUT_AVG, CAM_READOUT_RESIDUAL_ONLY, CAM_READOUT_UNIFORM = 0, 1, 2
+RESACT_NONE, RESACT_NORMALIZE_EPS, RESACT_SQUASH, RESACT_TANH, RESACT_AFFINE = range(5)
 ABI_VERSION = 1
 
 _P = c_void_p
@@ -47,7 +48,8 @@ SIGNATURES = {
     "vtc_layernorm": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P]),
     "vtc_cam_attn_core": (c_int, [_P, c_int, c_int64, c_int, c_int, _P, _P]),
     "vtc_bias_act": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P]),
-    "vtc_cam_readout": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
+    "vtc_cam_readout": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, c_float, _P, _P, _P,
+                                _P]),
     "vtc_linear": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_size_t,
                            _P]),
     "vtc_launch_count": (c_uint64, []),
@@ -66,7 +68,7 @@ SIGNATURES.update({
     "vtc_linear_prepare": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "vtc_cam_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
     "vtc_cam_forward": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, c_int, POINTER(CamLayer), c_int,
-                                _P, _P, c_int, _P, _P, c_size_t, _P]),
+                                _P, _P, c_int, c_float, _P, _P, c_int, _P, _P, c_size_t, _P]),
 })
 
 

@@ -640,14 +640,16 @@ int vtc_bias_act(const float* X, const float* bias, const float* residual, int64
 }
 
 int vtc_cam_readout(const float* T, const float* main, const float* res_in,
-                    const uint8_t* skip_mask, int L, int64_t b, int D, int mode, float* out,
+                    const uint8_t* skip_mask, int L, int64_t b, int D, int mode, int res_act,
+                    float res_scale, const float* res_shift, const float* res_mul, float* out,
                     vtc_stream_t stream) {
   if (!out || b < 0 || D <= 0 || L < 1) return VTC_ERR_INVALID_ARG;
   if (mode == VTC_CAM_READOUT_RESIDUAL_ONLY ? (!res_in || !main)
                                             : (!T || (mode == VTC_CAM_READOUT_AVG && !main)))
     return VTC_ERR_INVALID_ARG;
   if (mode < 0 || mode > 2) return VTC_ERR_INVALID_ARG;
-  return launch_cam_readout(T, main, res_in, skip_mask, L, b, D, mode, out, (cudaStream_t)stream);
+  return launch_cam_readout(T, main, res_in, skip_mask, L, b, D, mode, res_act, res_scale, res_shift,
+                            res_mul, out, (cudaStream_t)stream);
 }
 
 size_t vtc_linear_prepared_bytes(int in_f, int out_f, int precision) {
@@ -678,7 +680,8 @@ size_t vtc_cam_workspace_bytes(int L, int64_t b, int D, int precision) {
 
 int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D, int heads,
                     int layers, const vtc_cam_layer* lp, int readout_mode, const void* final_linear,
-                    const uint8_t* skip_mask, int precision, float* out, void* wsp, size_t ws_bytes,
+                    const uint8_t* skip_mask, int res_act, float res_scale, const float* res_shift,
+                    const float* res_mul, int precision, float* out, void* wsp, size_t ws_bytes,
                     vtc_stream_t stream) {
   if (!main || !out || L < 1 || (L > 1 && !aux) || b < 0 || D <= 0 || heads < 1 || layers < 0 ||
       (layers > 0 && !lp) || (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16) ||
@@ -713,14 +716,15 @@ int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D
     VTC_RETURN_IF_ERROR(linear_prepared(w.Fop, l.proj, X2, rows, 4 * D, D, 0, precision, X, nullptr, 0, s));
   }
   if (readout_mode == VTC_CAM_READOUT_AVG)
-    return launch_cam_readout(X, main, nullptr, skip_mask, L, b, D, VTC_CAM_READOUT_AVG, out, s);
+    return launch_cam_readout(X, main, nullptr, skip_mask, L, b, D, VTC_CAM_READOUT_AVG, res_act,
+                              res_scale, res_shift, res_mul, out, s);
   // final_linear(token 0)  (model/model.py:161): token 0 = the first b rows of X
   VTC_RETURN_IF_ERROR(launch_prep_operand(X, false, b, D, D, split ? PREP_SPLIT_A : PREP_PLAIN, w.Hop,
                                           od.Kp, s));
   VTC_RETURN_IF_ERROR(linear_prepared(w.Hop, final_linear, nullptr, b, D, D, 0, precision, w.res,
                                       nullptr, 0, s));
   return launch_cam_readout(nullptr, main, w.res, skip_mask, L, b, D, VTC_CAM_READOUT_RESIDUAL_ONLY,
-                            out, s);
+                            res_act, res_scale, res_shift, res_mul, out, s);
 }
 
 }  // extern "C"

@@ -160,7 +160,9 @@ __global__ void bias_act_kernel(const float* __restrict__ X, const float* __rest
 __global__ void __launch_bounds__(256)
 cam_readout_kernel(const float* __restrict__ T, const float* __restrict__ main,
                    const float* __restrict__ res_in, const uint8_t* __restrict__ skip_mask, int L,
-                   int64_t b, int D, int mode, float* __restrict__ out) {
+                   int64_t b, int D, int mode, int res_act, float res_scale,
+                   const float* __restrict__ res_shift, const float* __restrict__ res_mul,
+                   float* __restrict__ out) {
   const int64_t bi = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (bi >= b) return;
   const int lane = threadIdx.x & 31;
@@ -215,6 +217,43 @@ cam_readout_kernel(const float* __restrict__ T, const float* __restrict__ main,
     for (int i = 0; i < MAX_VEC; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) acc[i] = x[c];
+    }
+  }
+  // residual activation (model/model.py:30-77, applied at :168-171)
+  if (res_act != VTC_RESACT_NONE) {
+    if (res_act == VTC_RESACT_NORMALIZE_EPS || res_act == VTC_RESACT_SQUASH) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAX_VEC; ++i) {
+        if (lane + 32 * i < nvec) {
+          acc[i].x += 1e-9f, acc[i].y += 1e-9f, acc[i].z += 1e-9f, acc[i].w += 1e-9f;
+          s += acc[i].x * acc[i].x + acc[i].y * acc[i].y + acc[i].z * acc[i].z + acc[i].w * acc[i].w;
+        }
+      }
+      const float mag_sq = warp_sum(s);
+      const float mag = sqrtf(mag_sq);
+      // normalize_eps: (x + eps) / |x + eps|;  squash: c * mag^2 / (1 + mag^2) * (x + eps) / mag
+      const float f = res_act == VTC_RESACT_NORMALIZE_EPS
+                          ? 1.f / mag
+                          : res_scale * (mag_sq / (1.f + mag_sq)) / mag;
+#pragma unroll
+      for (int i = 0; i < MAX_VEC; ++i) acc[i].x *= f, acc[i].y *= f, acc[i].z *= f, acc[i].w *= f;
+    } else if (res_act == VTC_RESACT_TANH) {
+#pragma unroll
+      for (int i = 0; i < MAX_VEC; ++i)
+        acc[i] = make_float4(tanhf(acc[i].x), tanhf(acc[i].y), tanhf(acc[i].z), tanhf(acc[i].w));
+    } else if (res_act == VTC_RESACT_AFFINE) {  // eval-mode sub_mean / bn: (x - shift) * mul
+#pragma unroll
+      for (int i = 0; i < MAX_VEC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec) {
+          const float4 sh = reinterpret_cast<const float4*>(res_shift)[c];
+          const float4 mu = res_mul ? reinterpret_cast<const float4*>(res_mul)[c]
+                                    : make_float4(1.f, 1.f, 1.f, 1.f);
+          acc[i] = make_float4((acc[i].x - sh.x) * mu.x, (acc[i].y - sh.y) * mu.y,
+                               (acc[i].z - sh.z) * mu.z, (acc[i].w - sh.w) * mu.w);
+        }
+      }
     }
   }
   if (skip_mask && skip_mask[bi]) {  // random adapter skip (model.py:199-201)
@@ -302,13 +341,16 @@ int launch_bias_act(const float* X, const float* bias, const float* residual, in
 }
 
 int launch_cam_readout(const float* T, const float* main, const float* res_in,
-                       const uint8_t* skip_mask, int L, int64_t b, int D, int mode, float* out,
+                       const uint8_t* skip_mask, int L, int64_t b, int D, int mode, int res_act,
+                       float res_scale, const float* res_shift, const float* res_mul, float* out,
                        cudaStream_t s) {
   if (b == 0) return VTC_OK;
   if (D % 4 || D > 128 * MAX_VEC) return VTC_ERR_UNSUPPORTED_SHAPE;
-  cam_readout_kernel<<<(unsigned)ceil_div<int64_t>(b, WARPS), 256, 0, s>>>(T, main, res_in,
-                                                                         skip_mask, L, b, D, mode,
-                                                                         out);
+  if (res_act < VTC_RESACT_NONE || res_act > VTC_RESACT_AFFINE ||
+      (res_act == VTC_RESACT_AFFINE && !res_shift))
+    return VTC_ERR_INVALID_ARG;
+  cam_readout_kernel<<<(unsigned)ceil_div<int64_t>(b, WARPS), 256, 0, s>>>(
+      T, main, res_in, skip_mask, L, b, D, mode, res_act, res_scale, res_shift, res_mul, out);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }

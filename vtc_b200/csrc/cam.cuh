@@ -16,7 +16,8 @@ int launch_layernorm_prep(const float* X, const float* gamma, const float* beta,
 int launch_bias_act(const float* X, const float* bias, const float* residual, int64_t rows, int D,
                     int act, float* Y, cudaStream_t s);
 int launch_cam_readout(const float* T, const float* main, const float* res_in,
-                       const uint8_t* skip_mask, int L, int64_t b, int D, int mode, float* out,
+                       const uint8_t* skip_mask, int L, int64_t b, int D, int mode, int res_act,
+                       float res_scale, const float* res_shift, const float* res_mul, float* out,
                        cudaStream_t s);
 
 }  // namespace vtc

@@ -263,78 +263,95 @@ __global__ void rank_finalize_kernel(int* __restrict__ rank, const double* __res
     atomicAdd(&hits[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
-// median(rank)+1 with numpy semantics by a two-level radix select over multi-block histograms.
-// ws layout (uint32): hist0[65536] | hist1a[65536] | hist1b[65536] | sel[8]
-//   level 0 bins by rank >> shift (shift chosen so that bins cover [0, M_total]), level 1 by the
-//   low `shift` bits of the ranks inside the selected bucket(s).
-constexpr int MED_BINS = 65536;
+// median(rank)+1 with numpy semantics: three-level radix select (bits [21,32), [10,21), [0,10))
+// over block-privatised shared-memory histograms.  Two order statistics are tracked at once
+// (k_lo = (N-1)/2 and k_hi = N/2; their mean is the median), they may part ways at any level.
+// ws layout (uint32): hist[3 levels][2 stats][2048] | state[8] = {prefix_lo, rem_lo, prefix_hi, rem_hi}
+constexpr int MED_BINS = 2048;
+__device__ __forceinline__ int med_shift(int level) { return level == 0 ? 21 : (level == 1 ? 10 : 0); }
+__device__ __forceinline__ unsigned int med_mask(int level) { return level == 2 ? 1023u : 2047u; }
 
-__global__ void med_hist0_kernel(const int* __restrict__ rank, int64_t N, int shift,
-                                 unsigned int* __restrict__ hist0) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    unsigned int b = ((unsigned int)rank[i]) >> shift;
-    if (b >= MED_BINS) b = MED_BINS - 1;
-    atomicAdd(&hist0[b], 1u);
-  }
-}
-
-// one block: locate the bin holding order statistic `target` (exclusive prefix <= target)
-__device__ void med_find(const unsigned int* __restrict__ hist, unsigned int target,
-                         unsigned int* part /*[1024] smem*/, unsigned int* bin_out,
-                         unsigned int* rem_out) {
-  const int tid = threadIdx.x;
-  unsigned int s = 0;
-  for (int i = 0; i < MED_BINS / 1024; ++i) s += hist[tid * (MED_BINS / 1024) + i];
-  part[tid] = s;
+__global__ void __launch_bounds__(256)
+med_hist_kernel(const int* __restrict__ rank, int64_t N, int level,
+                const unsigned int* __restrict__ state, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[2][MED_BINS];
+  for (int i = threadIdx.x; i < 2 * MED_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
   __syncthreads();
-  if (tid == 0) {
-    unsigned int run = 0;
-    int b = 0;
-    while (b < 1023 && run + part[b] <= target) run += part[b++];
-    int bin = b * (MED_BINS / 1024);
-    const int last = bin + MED_BINS / 1024 - 1;
-    while (bin < last && run + hist[bin] <= target) run += hist[bin++];
-    *bin_out = (unsigned int)bin;
-    *rem_out = target - run;
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(1024)
-med_select0_kernel(const unsigned int* __restrict__ hist0, int64_t N, unsigned int* __restrict__ sel) {
-  __shared__ unsigned int part[1024];
-  med_find(hist0, (unsigned int)((N - 1) / 2), part, &sel[0], &sel[1]);
-  med_find(hist0, (unsigned int)(N / 2), part, &sel[2], &sel[3]);
-}
-
-__global__ void med_hist1_kernel(const int* __restrict__ rank, int64_t N, int shift,
-                                 const unsigned int* __restrict__ sel,
-                                 unsigned int* __restrict__ hist1a,
-                                 unsigned int* __restrict__ hist1b) {
-  const unsigned int ba = sel[0], bb = sel[2];
-  const unsigned int mask = (1u << shift) - 1u;
+  const int shift = med_shift(level);
+  const unsigned int mask = med_mask(level);
+  // ranks must match the prefix selected so far (bits above this level's field)
+  const int up = level == 0 ? 32 : med_shift(level - 1);
+  const unsigned int pa = level == 0 ? 0u : state[0], pb = level == 0 ? 0u : state[2];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
        i += (int64_t)gridDim.x * blockDim.x) {
     const unsigned int r = (unsigned int)rank[i];
-    unsigned int b = r >> shift;
-    if (b >= MED_BINS) b = MED_BINS - 1;
-    if (b == ba) atomicAdd(&hist1a[r & mask], 1u);
-    if (b == bb && bb != ba) atomicAdd(&hist1b[r & mask], 1u);
+    const unsigned int hi = up >= 32 ? 0u : (r >> up);
+    const unsigned int bin = (r >> shift) & mask;
+    if (hi == pa) atomicAdd(&sh[0][bin], 1u);
+    if (hi == pb && pb != pa) atomicAdd(&sh[1][bin], 1u);
+  }
+  __syncthreads();
+  unsigned int* h = hist + (size_t)level * 2 * MED_BINS;
+  for (int i = threadIdx.x; i < 2 * MED_BINS; i += blockDim.x) {
+    const unsigned int v = (&sh[0][0])[i];
+    if (v) atomicAdd(&h[i], v);
   }
 }
 
+// one block of 1024 threads, 2 bins each: exclusive scan, then the thread whose bin straddles the
+// target records (bin, remainder)
+__device__ void med_pick(const unsigned int* __restrict__ h, unsigned int target,
+                         unsigned int* sh_warp /*[32]*/, unsigned int* out_bin, unsigned int* out_rem) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned int c0 = h[2 * tid], c1 = h[2 * tid + 1];
+  unsigned int incl = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) sh_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    unsigned int x = sh_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += v;
+    }
+    sh_warp[lane] = x;  // inclusive over warps
+  }
+  __syncthreads();
+  const unsigned int base = (w ? sh_warp[w - 1] : 0u) + incl - (c0 + c1);  // exclusive prefix
+  if (target >= base && target < base + c0) {
+    *out_bin = 2 * tid;
+    *out_rem = target - base;
+  } else if (target >= base + c0 && target < base + c0 + c1) {
+    *out_bin = 2 * tid + 1;
+    *out_rem = target - base - c0;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024)
-med_select1_kernel(const unsigned int* __restrict__ hist1a, const unsigned int* __restrict__ hist1b,
-                   int shift, const unsigned int* __restrict__ sel, double* __restrict__ medr) {
-  __shared__ unsigned int part[1024];
-  __shared__ unsigned int lo[2], rem[2];
-  med_find(hist1a, sel[1], part, &lo[0], &rem[0]);
-  med_find(sel[2] != sel[0] ? hist1b : hist1a, sel[3], part, &lo[1], &rem[1]);
+med_select_kernel(const unsigned int* __restrict__ hist, int64_t N, int level,
+                  unsigned int* __restrict__ state, double* __restrict__ medr) {
+  __shared__ unsigned int sh_warp[32];
+  __shared__ unsigned int bin[2], rem[2];
+  const unsigned int* h = hist + (size_t)level * 2 * MED_BINS;
+  const bool same = level == 0 || state[0] == state[2];
+  const unsigned int ta = level == 0 ? (unsigned int)((N - 1) / 2) : state[1];
+  const unsigned int tb = level == 0 ? (unsigned int)(N / 2) : state[3];
+  if (threadIdx.x == 0) bin[0] = bin[1] = rem[0] = rem[1] = 0;
+  __syncthreads();
+  med_pick(h, ta, sh_warp, &bin[0], &rem[0]);
+  med_pick(same ? h : h + MED_BINS, tb, sh_warp, &bin[1], &rem[1]);
   if (threadIdx.x == 0) {
-    const double v0 = (double)((sel[0] << shift) | lo[0]);
-    const double v1 = (double)((sel[2] << shift) | lo[1]);
-    *medr = 0.5 * (v0 + v1) + 1.0;
+    const int bits = level == 2 ? 10 : 11;
+    const unsigned int pa = ((level == 0 ? 0u : state[0]) << bits) | bin[0];
+    const unsigned int pb = ((level == 0 ? 0u : state[2]) << bits) | bin[1];
+    state[0] = pa, state[1] = rem[0], state[2] = pb, state[3] = rem[1];
+    if (level == 2) *medr = 0.5 * ((double)pa + (double)pb) + 1.0;
   }
 }
 
@@ -458,25 +475,19 @@ int launch_rank_finalize(int* rank, const double* dgt, int64_t N, int64_t M_tota
       VTC_LAUNCH_CHECK();
       return VTC_OK;
     }
-    unsigned int* h0 = (unsigned int*)hist_ws;
-    unsigned int* h1a = h0 + MED_BINS;
-    unsigned int* h1b = h1a + MED_BINS;
-    unsigned int* sel = h1b + MED_BINS;
-    cudaError_t e = cudaMemsetAsync(h0, 0, (3 * MED_BINS + 8) * sizeof(unsigned int), s);
+    unsigned int* hist = (unsigned int*)hist_ws;
+    unsigned int* state = hist + 3 * 2 * MED_BINS;
+    cudaError_t e = cudaMemsetAsync(hist, 0, (3 * 2 * MED_BINS + 8) * sizeof(unsigned int), s);
     if (e != cudaSuccess) return cuda_err(e);
-    int shift = 0;  // level-0 bins must cover ranks up to M_total (and any int32 beyond, clamped)
-    while (shift < 16 && (M_total >> shift) >= MED_BINS) ++shift;
-    const unsigned blocks = (unsigned)(ceil_div<int64_t>(N, 256) < kNumSMs * 4
-                                           ? ceil_div<int64_t>(N, 256)
-                                           : kNumSMs * 4);
-    med_hist0_kernel<<<blocks, 256, 0, s>>>(rank, N, shift, h0);
-    VTC_LAUNCH_CHECK();
-    med_select0_kernel<<<1, 1024, 0, s>>>(h0, N, sel);
-    VTC_LAUNCH_CHECK();
-    med_hist1_kernel<<<blocks, 256, 0, s>>>(rank, N, shift, sel, h1a, h1b);
-    VTC_LAUNCH_CHECK();
-    med_select1_kernel<<<1, 1024, 0, s>>>(h1a, h1b, shift, sel, medr);
-    VTC_LAUNCH_CHECK();
+    const unsigned blocks = (unsigned)(ceil_div<int64_t>(N, 1024) < kNumSMs
+                                           ? ceil_div<int64_t>(N, 1024)
+                                           : kNumSMs);
+    for (int level = 0; level < 3; ++level) {
+      med_hist_kernel<<<blocks, 256, 0, s>>>(rank, N, level, state, hist);
+      VTC_LAUNCH_CHECK();
+      med_select_kernel<<<1, 1024, 0, s>>>(hist, N, level, state, medr);
+      VTC_LAUNCH_CHECK();
+    }
   }
   return VTC_OK;
 }

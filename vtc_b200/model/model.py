@@ -41,9 +41,18 @@ def normalize(x: torch.Tensor) -> torch.Tensor:
     return ops.normalize(x)
 
 
-# residual activations (model/model.py:65-77).  Every shipped config uses None / "none"; the
-# others are listed as a "next" row and rejected loudly.
-RESIDUAL_ACTIVATIONS = {None: "identity", "none": "identity"}
+# residual activations (model/model.py:30-77) -> (VTC_RESACT_*, scale); "sub_mean" / "bn" use the
+# BatchNorm1d running statistics (eval mode only: the CAM is forward-only this round)
+RESIDUAL_ACTIVATIONS = {
+    None: (_ffi.RESACT_NONE, 1.0), "none": (_ffi.RESACT_NONE, 1.0),
+    "normalize": (_ffi.RESACT_NORMALIZE_EPS, 1.0),
+    "squash": (_ffi.RESACT_SQUASH, 1.0), "squash10": (_ffi.RESACT_SQUASH, 10.0),
+    "squash1p2": (_ffi.RESACT_SQUASH, 1.2), "squash1p5": (_ffi.RESACT_SQUASH, 1.5),
+    "squash1p8": (_ffi.RESACT_SQUASH, 1.8),
+    "tanh": (_ffi.RESACT_TANH, 1.0),
+    "sub_mean": (_ffi.RESACT_AFFINE, 1.0), "bn": (_ffi.RESACT_AFFINE, 1.0),
+}
+NEEDS_STATE = ["sub_mean", "bn"]
 
 
 class _Attn(nn.Module):
@@ -154,13 +163,30 @@ class PretrainedCLIPBase(nn.Module):
     branch_to_adapt_val = "text"
     precision = "exact"
 
+    def _common_init(self):
+        """model/model.py:133-139: a BatchNorm1d holds the running stats of sub_mean / bn."""
+        if getattr(self, "residual_activation", None) in NEEDS_STATE:
+            self.mean_center_bn = nn.BatchNorm1d(self.feature_dim, affine=False, momentum=0.2)
+
+    def _res_act(self):
+        name = self.residual_activation
+        if name not in RESIDUAL_ACTIVATIONS:
+            raise KeyError(f"unknown residual_activation {name!r}")
+        act, scale = RESIDUAL_ACTIVATIONS[name]
+        if name in NEEDS_STATE:
+            if self.training and "finaltf" not in getattr(self, "branch_to_freeze", ""):
+                raise NotImplementedError(
+                    f"residual_activation={name!r} in training mode updates batch statistics "
+                    "(model/model.py:41-60); only the eval-mode form is built")
+            bn = self.mean_center_bn
+            mul = None if name == "sub_mean" else torch.rsqrt(bn.running_var + bn.eps)
+            return act, scale, bn.running_mean, mul
+        return act, scale, None, None
+
     def _adapt_feature(self, feature_main: torch.Tensor, features_aux) -> torch.Tensor:
         """CAM: model/model.py:141-205.  feature_main [b, D]; features_aux [nc, b, D] tensor or a
         list of nc [b, D] tensors.  Returns the adapted, unit-norm feature [b, D]."""
-        if self.residual_activation not in RESIDUAL_ACTIVATIONS:
-            raise NotImplementedError(
-                f"residual_activation={self.residual_activation!r}: only None/'none' is built "
-                "(every shipped config uses it; the others are a 'next' row in DESIGN.md)")
+        res_act = self._res_act()
         assert len(feature_main.shape) == 2
         b = feature_main.shape[0]
         if not isinstance(features_aux, torch.Tensor):
@@ -192,7 +218,8 @@ class PretrainedCLIPBase(nn.Module):
         return ops.cam_forward(feature_main, features_aux, layers, tfm.heads,
                                _ffi.CAM_READOUT_AVG if self.init_from_avg
                                else _ffi.CAM_READOUT_RESIDUAL_ONLY,
-                               final_linear=final, skip_mask=skip_mask, precision=self.precision)
+                               final_linear=final, skip_mask=skip_mask, precision=self.precision,
+                               res_act=res_act)
 
     def _load_comment_features(self, comments) -> torch.Tensor:
         """model/model.py:207-214.  `comments` is either precomputed comment embeddings
@@ -325,6 +352,8 @@ class PretrainedCLIP_finaltf(PretrainedCLIPBase):
         self.random_skip_adapter = random_skip_adapter
         self.precision = precision
         self.lazy_sim = lazy_sim
+        self.branch_to_freeze = ""
+        self._common_init()
         if backbone is None or not hasattr(backbone, "logit_scale"):
             self.logit_scale = nn.Parameter(torch.ones([]) * logit_scale_init)
         if self.init_from_avg:                                                   # :440-450

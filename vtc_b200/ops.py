@@ -379,9 +379,18 @@ def cam_attn_core(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     return out
 
 
+def _res_act_args(res_act, dev):
+    """(act, scale, shift, mul) -> ctypes-ready (int, float, tensor|None, tensor|None)."""
+    if res_act is None:
+        return _ffi.RESACT_NONE, 1.0, None, None
+    act, scale, shift, mul = res_act
+    f = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+    return int(act), float(scale), f(shift), f(mul)
+
+
 def cam_readout(T: Optional[torch.Tensor], main: Optional[torch.Tensor], mode: int,
-                res_in: Optional[torch.Tensor] = None, skip_mask: Optional[torch.Tensor] = None
-                ) -> torch.Tensor:
+                res_in: Optional[torch.Tensor] = None, skip_mask: Optional[torch.Tensor] = None,
+                res_act=None) -> torch.Tensor:
     dev = _req_cuda(T, main, res_in, skip_mask)
     if T is not None:
         T = T.float().contiguous()
@@ -396,8 +405,10 @@ def cam_readout(T: Optional[torch.Tensor], main: Optional[torch.Tensor], mode: i
         skip_mask = skip_mask.to(device=dev, dtype=torch.uint8).contiguous()
     out = torch.empty(b, D, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
+        act, scale, shift, mul = _res_act_args(res_act, dev)
         _ffi.check(_ffi.load().vtc_cam_readout(_ptr(T), _ptr(main), _ptr(res_in), _ptr(skip_mask),
-                                               L, b, D, mode, _ptr(out), _stream(dev)),
+                                               L, b, D, mode, act, scale, _ptr(shift), _ptr(mul),
+                                               _ptr(out), _stream(dev)),
                    "vtc_cam_readout")
     return out
 
@@ -423,7 +434,7 @@ def linear_prepare(w: torch.Tensor, bias: Optional[torch.Tensor], precision="exa
 
 def cam_forward(main: torch.Tensor, aux: torch.Tensor, layers, heads: int, readout_mode: int,
                 final_linear: Optional[torch.Tensor] = None, skip_mask: Optional[torch.Tensor] = None,
-                precision="exact") -> torch.Tensor:
+                precision="exact", res_act=None) -> torch.Tensor:
     """PretrainedCLIPBase._adapt_feature (model/model.py:141-205) in one C call.
 
     `layers` is a ctypes array of _ffi.CamLayer built from prepared linears (see
@@ -442,8 +453,10 @@ def cam_forward(main: torch.Tensor, aux: torch.Tensor, layers, heads: int, reado
     lib = _ffi.load()
     with torch.cuda.device(dev):
         ws = _workspace(dev, int(lib.vtc_cam_workspace_bytes(nc + 1, b, D, prec)))
+        act, scale, shift, mul = _res_act_args(res_act, dev)
         _ffi.check(lib.vtc_cam_forward(_ptr(main), _ptr(aux), nc + 1, b, D, heads, len(layers), layers,
-                                       readout_mode, _ptr(final_linear), _ptr(skip_mask), prec,
-                                       _ptr(out), _ptr(ws), ws.numel(), _stream(dev)),
+                                       readout_mode, _ptr(final_linear), _ptr(skip_mask), act, scale,
+                                       _ptr(shift), _ptr(mul), prec, _ptr(out), _ptr(ws), ws.numel(),
+                                       _stream(dev)),
                    "vtc_cam_forward")
     return out
