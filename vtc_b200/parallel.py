@@ -93,6 +93,11 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     g_starts = [shard_bounds(M_total, world, r)[0] for r in range(world)]
     assert g_local.shape[0] == g_sizes[rank], "g_local does not match shard_bounds(M_total)"
     dev = q_local.device
+    if precision == "bf16" and q_local.dtype == torch.float32 and g_local.dtype == torch.float32:
+        # the bf16 mode ranks the RN-even bf16 roundings of the inputs: round BEFORE the exchange
+        # (identical results, half the NVLink bytes and half the operand-prep reads)
+        q_local = q_local.to(torch.bfloat16)
+        g_local = g_local.to(torch.bfloat16)
 
     # gallery exchange: one all_gather into a single [world * max_shard, D] buffer, so that with
     # equal shards the remote rows form (at most) two contiguous ranges [0, gs) and [ge, M)
