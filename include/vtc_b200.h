@@ -217,6 +217,27 @@ int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D
                     float res_scale, const float* res_shift, const float* res_mul, int precision,
                     float* out, void* ws, size_t ws_bytes, vtc_stream_t stream);
 
+/* ---- backward of the CAM (training: trainer/trainer.py:79 back-propagates through
+ * _adapt_feature).  Dense products of the backward are vtc_linear on transposed copies
+ * (dX = dY W = linear(dY, W^T), dW = dY^T X = linear(dY^T, X^T)); the rest is here.
+ * vtc_layernorm_bwd: dX = LN'(dY) + dres (dres nullable), dgamma / dbeta [D] overwritten.
+ * vtc_cam_readout_bwd: residual activation NONE only; AVG writes dT [L,b,D], RESIDUAL_ONLY writes
+ * dres [b,D]; dmain [b,D] is the part through normalize(main) at model.py:203.
+ * vtc_cam_stack_normalize_bwd: dX [L,b,D] -> dmain [b,D] (token 0), daux [L-1,b,D]. */
+int vtc_transpose(const float* in, int64_t rows, int64_t cols, float* out, vtc_stream_t stream);
+int vtc_gelu_bwd(const float* dF, const float* U, int64_t n, float* dU, vtc_stream_t stream);
+int vtc_colsum(const float* X, int64_t rows, int64_t cols, float* out, vtc_stream_t stream);
+int vtc_layernorm_bwd(const float* dY, const float* X, const float* gamma, int64_t rows, int D,
+                      float eps, const float* dres, float* dX, float* dgamma, float* dbeta,
+                      vtc_stream_t stream);
+int vtc_cam_attn_core_bwd(const float* QKV, const float* dO, int L, int64_t b, int D, int heads,
+                          float* dQKV, vtc_stream_t stream);
+int vtc_cam_stack_normalize_bwd(const float* main, const float* aux, const float* dX, int L,
+                                int64_t b, int D, float* dmain, float* daux, vtc_stream_t stream);
+int vtc_cam_readout_bwd(const float* T, const float* main, const float* res_in,
+                        const uint8_t* skip_mask, const float* dout, int L, int64_t b, int D,
+                        int mode, float* dT, float* dres, float* dmain, vtc_stream_t stream);
+
 /* number of kernels this library has launched since load (for bench.py's gpu_launches). */
 uint64_t vtc_launch_count(void);
 

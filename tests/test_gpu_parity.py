@@ -469,6 +469,60 @@ def test_cam_residual_activations_golden(cuda_dev, golden, act):
     np.testing.assert_allclose(_np(out), g["act_" + act], rtol=2e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("avg", [True, False])
+def test_cam_backward_matches_autograd_oracle(cuda_dev, avg):
+    """Training path: gradients of `_adapt_feature` w.r.t. inputs and every CAM parameter against
+    torch autograd through the oracle restatement (CPU)."""
+    from vtc_b200.model import PretrainedCLIP_finaltf
+
+    b, nc, D, layers, heads = 24, 5, 128, 2, 4
+    params = O.make_cam_params(D, layers, heads, seed=11, rerandomise=True)
+    flw = torch.randn(D, D, generator=torch.Generator().manual_seed(3)) / D ** 0.5
+    main, aux = make_cam_inputs(b, nc, D, seed=6)
+    w = torch.randn(b, D, generator=torch.Generator().manual_seed(9))  # loss = sum(out * w)
+    skip = torch.zeros(b, dtype=torch.bool)
+    skip[::5] = True
+    # oracle gradients
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    mo, ao, fo = main.clone().requires_grad_(True), aux.clone().requires_grad_(True), flw.clone().requires_grad_(True)
+    out_o = O.adapt_feature(mo, ao, po, layers, heads, init_from_avg=avg, final_linear_weight=fo,
+                            skip_mask=skip)
+    (out_o * w).sum().backward()
+    # CUDA path
+    m = PretrainedCLIP_finaltf(D, n_layers=layers, n_heads=heads, init_from_avg=avg).to(cuda_dev)
+    m.final_transformer.load_state_dict(params, strict=True)
+    with torch.no_grad():
+        m.final_linear.weight.copy_(flw)
+    m.train()
+    m.random_skip_adapter = False  # the mask is injected below instead of drawn
+    mg, ag = main.to(cuda_dev).requires_grad_(True), aux.to(cuda_dev).requires_grad_(True)
+    from vtc_b200.model.model import _CamAdaptFunction, _layer_params
+
+    plist = [p for blk in m.final_transformer.resblocks for p in _layer_params(blk)]
+    cfg = (layers, heads, avg, "exact")
+    out = _CamAdaptFunction.apply(mg, ag, skip.to(cuda_dev), cfg, None if avg else m.final_linear.weight,
+                                  *plist)
+    np.testing.assert_allclose(_np(out), out_o.detach().numpy(), rtol=2e-4, atol=2e-5)
+    (out * w.to(cuda_dev)).sum().backward()
+
+    def close(got, want, name):
+        want = want.numpy()
+        scale = np.abs(want).max() + 1e-12
+        err = np.abs(_np(got) - want).max() / scale
+        assert err < 3e-3, f"{name}: max err / max |grad| = {err:.3e}"
+
+    close(mg.grad, mo.grad, "dmain")
+    close(ag.grad, ao.grad, "daux")
+    for n_, p in m.final_transformer.named_parameters():
+        close(p.grad, po[n_].grad, n_)
+    if not avg:
+        close(m.final_linear.weight.grad, fo.grad, "final_linear.weight")
+    # and through the module call site (train mode, autograd on) the same function is used
+    m.zero_grad()
+    out2 = m._adapt_feature(mg, ag)
+    assert out2.requires_grad
+
+
 def test_cam_transformer_module_forward(cuda_dev):
     """The op-by-op CAMTransformer.forward (LayerNorm / tcgen05 linears / attention core as separate
     C-ABI calls) against the oracle's clip.model.Transformer restatement."""

@@ -72,6 +72,17 @@ SIGNATURES.update({
 })
 
 
+SIGNATURES.update({
+    "vtc_transpose": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "vtc_gelu_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
+    "vtc_colsum": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "vtc_layernorm_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P, _P, _P, _P]),
+    "vtc_cam_attn_core_bwd": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
+    "vtc_cam_stack_normalize_bwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P, _P]),
+    "vtc_cam_readout_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P]),
+})
+
+
 class VtcError(RuntimeError):
     pass
 

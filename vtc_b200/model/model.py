@@ -150,6 +150,108 @@ class CAMTransformer(nn.Module):
         return x2.reshape(L, b, D)
 
 
+_PARAMS_PER_LAYER = 12
+
+
+def _layer_params(blk) -> list:
+    return [blk.attn.in_proj_weight, blk.attn.in_proj_bias, blk.attn.out_proj.weight,
+            blk.attn.out_proj.bias, blk.ln_1.weight, blk.ln_1.bias, blk.mlp.c_fc.weight,
+            blk.mlp.c_fc.bias, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias, blk.ln_2.weight,
+            blk.ln_2.bias]
+
+
+class _CamAdaptFunction(torch.autograd.Function):
+    """Differentiable `_adapt_feature` (model/model.py:141-205) for training: the forward runs the
+    CUDA ops one by one and keeps the activations, the backward is built from the kernels of
+    csrc/cam_bwd.cu plus tensor-core GEMMs on transposed copies (dX = dY W, dW = dY^T X)."""
+
+    @staticmethod
+    def forward(ctx, main, aux, skip_mask, cfg, flw, *params):
+        layers, heads, avg, prec = cfg
+        main, aux = main.detach().float().contiguous(), aux.detach().float().contiguous()
+        L, (b, D) = aux.shape[0] + 1, main.shape
+        X = ops.cam_stack_normalize(main, aux).reshape(L * b, D)
+        saved = []
+        for i in range(layers):
+            wqkv, bqkv, wo, bo, g1, b1, wfc, bfc, wpr, bpr, g2, b2 = (
+                t.detach() for t in params[_PARAMS_PER_LAYER * i:_PARAMS_PER_LAYER * (i + 1)])
+            H1 = ops.layernorm(X, g1, b1)
+            QKV = ops.linear(H1, wqkv, bqkv, precision=prec)
+            A = ops.cam_attn_core(QKV.reshape(L, b, 3 * D), heads).reshape(L * b, D)
+            X2 = ops.linear(A, wo, bo, residual=X, precision=prec)
+            H2 = ops.layernorm(X2, g2, b2)
+            U = ops.linear(H2, wfc, bfc, precision=prec)
+            Fa = ops.bias_act(U, act=1)
+            Xn = ops.linear(Fa, wpr, bpr, residual=X2, precision=prec)
+            saved += [X, H1, QKV, A, X2, H2, U, Fa]
+            X = Xn
+        T = X.reshape(L, b, D)
+        res = None
+        if avg:
+            out = ops.cam_readout(T, main, _ffi.CAM_READOUT_AVG, skip_mask=skip_mask)
+        else:
+            res = ops.linear(T[0], flw.detach(), precision=prec)
+            out = ops.cam_readout(None, main, _ffi.CAM_READOUT_RESIDUAL_ONLY, res_in=res,
+                                  skip_mask=skip_mask)
+        ctx.cfg = cfg
+        ctx.skip_mask = skip_mask
+        ctx.dims = (L, b, D)
+        ctx.has_flw = flw is not None
+        ctx.save_for_backward(main, aux, T, res if res is not None else main,
+                              flw.detach() if flw is not None else main,
+                              *[p.detach() for p in params], *saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        layers, heads, avg, prec = ctx.cfg
+        L, b, D = ctx.dims
+        sv = ctx.saved_tensors
+        main, aux, T, res, flw = sv[:5]
+        params = sv[5:5 + _PARAMS_PER_LAYER * layers]
+        acts = sv[5 + _PARAMS_PER_LAYER * layers:]
+        lin = lambda x, w: ops.linear(x, w, precision=prec)  # noqa: E731  x @ w.t()
+        tr = ops.transpose
+        dflw = None
+        if avg:
+            dT, _, dmain = ops.cam_readout_bwd(T, main, dout, _ffi.CAM_READOUT_AVG,
+                                               skip_mask=ctx.skip_mask)
+        else:
+            _, dres, dmain = ops.cam_readout_bwd(None, main, dout, _ffi.CAM_READOUT_RESIDUAL_ONLY,
+                                                 res_in=res, skip_mask=ctx.skip_mask, L=L)
+            dT = torch.zeros_like(T)
+            dT[0] = lin(dres, tr(flw))                       # d token0 = dres @ W
+            dflw = lin(tr(dres), tr(T[0].contiguous()))      # dW = dres^T @ token0
+        dX = dT.reshape(L * b, D)
+        grads = [None] * len(params)
+        for i in reversed(range(layers)):
+            wqkv, bqkv, wo, bo, g1, b1, wfc, bfc, wpr, bpr, g2, b2 = params[
+                _PARAMS_PER_LAYER * i:_PARAMS_PER_LAYER * (i + 1)]
+            X, H1, QKV, A, X2, H2, U, Fa = acts[8 * i:8 * (i + 1)]
+            o = _PARAMS_PER_LAYER * i
+            dXt = tr(dX)
+            dF = lin(dX, tr(wpr))                            # [rows, 4D]
+            grads[o + 8] = lin(dXt, tr(Fa))                  # dW_proj [D, 4D]
+            grads[o + 9] = ops.colsum(dX)
+            dU = ops.gelu_bwd(dF, U)
+            dH2 = lin(dU, tr(wfc))                           # [rows, D]
+            grads[o + 6] = lin(tr(dU), tr(H2))               # dW_fc [4D, D]
+            grads[o + 7] = ops.colsum(dU)
+            dX2, grads[o + 10], grads[o + 11] = ops.layernorm_bwd(dH2, X2, g2, dres=dX)
+            dA = lin(dX2, tr(wo))
+            grads[o + 2] = lin(tr(dX2), tr(A))
+            grads[o + 3] = ops.colsum(dX2)
+            dQKV = ops.cam_attn_core_bwd(QKV.reshape(L, b, 3 * D), dA.reshape(L, b, D),
+                                         heads).reshape(L * b, 3 * D)
+            dH1 = lin(dQKV, tr(wqkv))
+            grads[o + 0] = lin(tr(dQKV), tr(H1))
+            grads[o + 1] = ops.colsum(dQKV)
+            dX, grads[o + 4], grads[o + 5] = ops.layernorm_bwd(dH1, X, g1, dres=dX2)
+        dmain2, daux = ops.cam_stack_normalize_bwd(main, aux, dX.reshape(L, b, D))
+        dmain = ops.bias_act(dmain, residual=dmain2)
+        return (dmain, daux, None, None, dflw if ctx.has_flw else None, *grads)
+
+
 class PretrainedCLIPBase(nn.Module):
     """model/model.py:132-305 (hot-path methods only)."""
 
@@ -193,16 +295,26 @@ class PretrainedCLIPBase(nn.Module):
             features_aux = torch.stack(list(features_aux), dim=0)
         assert features_aux.shape[1] == b
         tfm = self.final_transformer
-        if torch.is_grad_enabled() and any(p.requires_grad for p in tfm.parameters()):
-            raise NotImplementedError(
-                "the CAM is forward-only in this round (wrap the call in torch.no_grad(); the CAM "
-                "backward kernels are listed as next in DESIGN.md)")
         # the reference draws one number from the global CPU RNG here for a 5 % debug print
         # (:163); keep the draw so RNG streams stay aligned with it, drop the print.
         torch.rand([])
         skip_mask = None
         if self.training and self.random_skip_adapter:
             skip_mask = torch.rand(b) > 0.5                                      # :199-201
+        needs_grad = torch.is_grad_enabled() and (
+            feature_main.requires_grad or features_aux.requires_grad
+            or any(p.requires_grad for p in tfm.parameters())
+            or (not self.init_from_avg and self.final_linear.weight.requires_grad))
+        if needs_grad:
+            if res_act[0] != _ffi.RESACT_NONE:
+                raise NotImplementedError(
+                    f"residual_activation={self.residual_activation!r} has no backward yet; only "
+                    "None/'none' (what every shipped config uses) is differentiable")
+            params = [p for blk in tfm.resblocks for p in _layer_params(blk)]
+            cfg = (len(tfm.resblocks), tfm.heads, bool(self.init_from_avg), self.precision)
+            sm = None if skip_mask is None else skip_mask.to(feature_main.device)
+            flw = None if self.init_from_avg else self.final_linear.weight
+            return _CamAdaptFunction.apply(feature_main, features_aux, sm, cfg, flw, *params)
         layers, _keep = tfm.prepared()
         final = None
         if not self.init_from_avg:                                               # :161

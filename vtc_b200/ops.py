@@ -460,3 +460,114 @@ def cam_forward(main: torch.Tensor, aux: torch.Tensor, layers, heads: int, reado
                                        _stream(dev)),
                    "vtc_cam_forward")
     return out
+
+
+# ------------------------------------------------------------------------------ CAM backward ops
+def _call(name, *args):
+    _ffi.check(getattr(_ffi.load(), name)(*args), name)
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """[R, C] fp32 -> [C, R] (materialised; operands of the backward GEMMs)."""
+    dev = _req_cuda(x)
+    x = _mat(x.float(), "x")
+    R, C = x.shape
+    out = torch.empty(C, R, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("vtc_transpose", _ptr(x), R, C, _ptr(out), _stream(dev))
+    return out
+
+
+def gelu_bwd(dF: torch.Tensor, U: torch.Tensor) -> torch.Tensor:
+    dev = _req_cuda(dF, U)
+    dF, U = dF.float().contiguous(), U.float().contiguous()
+    out = torch.empty_like(dF)
+    with torch.cuda.device(dev):
+        _call("vtc_gelu_bwd", _ptr(dF), _ptr(U), dF.numel(), _ptr(out), _stream(dev))
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    dev = _req_cuda(x)
+    x = _mat(x.float(), "x")
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call("vtc_colsum", _ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream(dev))
+    return out
+
+
+def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor] = None,
+             residual: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
+    dev = _req_cuda(x, bias, residual)
+    x = _mat(x.float(), "x")
+    out = torch.empty_like(x)
+    b = None if bias is None else bias.float().contiguous()
+    r = None if residual is None else residual.float().contiguous()
+    with torch.cuda.device(dev):
+        _call("vtc_bias_act", _ptr(x), _ptr(b), _ptr(r), x.shape[0], x.shape[1], act, _ptr(out),
+              _stream(dev))
+    return out
+
+
+def layernorm_bwd(dY: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5,
+                  dres: Optional[torch.Tensor] = None):
+    """-> (dX [rows, D] (+ dres), dgamma [D], dbeta [D])."""
+    dev = _req_cuda(dY, x, gamma, dres)
+    dY, x = _mat(dY.float(), "dY"), _mat(x.float(), "x")
+    rows, D = x.shape
+    g = gamma.detach().float().contiguous()
+    dres = None if dres is None else dres.float().contiguous()
+    dX = torch.empty_like(x)
+    dg = torch.empty(D, dtype=torch.float32, device=dev)
+    db = torch.empty_like(dg)
+    with torch.cuda.device(dev):
+        _call("vtc_layernorm_bwd", _ptr(dY), _ptr(x), _ptr(g), rows, D, eps, _ptr(dres), _ptr(dX),
+              _ptr(dg), _ptr(db), _stream(dev))
+    return dX, dg, db
+
+
+def cam_attn_core_bwd(qkv: torch.Tensor, dO: torch.Tensor, heads: int) -> torch.Tensor:
+    dev = _req_cuda(qkv, dO)
+    qkv, dO = qkv.float().contiguous(), dO.float().contiguous()
+    L, b, D3 = qkv.shape
+    out = torch.empty_like(qkv)
+    with torch.cuda.device(dev):
+        _call("vtc_cam_attn_core_bwd", _ptr(qkv), _ptr(dO), L, b, D3 // 3, heads, _ptr(out), _stream(dev))
+    return out
+
+
+def cam_stack_normalize_bwd(main: torch.Tensor, aux: torch.Tensor, dX: torch.Tensor):
+    dev = _req_cuda(main, aux, dX)
+    main, aux, dX = main.float().contiguous(), aux.float().contiguous(), dX.float().contiguous()
+    b, D = main.shape
+    L = aux.shape[0] + 1
+    dmain = torch.empty_like(main)
+    daux = torch.empty_like(aux)
+    with torch.cuda.device(dev):
+        _call("vtc_cam_stack_normalize_bwd", _ptr(main), _ptr(aux), _ptr(dX), L, b, D, _ptr(dmain),
+              _ptr(daux), _stream(dev))
+    return dmain, daux
+
+
+def cam_readout_bwd(T: Optional[torch.Tensor], main: torch.Tensor, dout: torch.Tensor, mode: int,
+                    res_in: Optional[torch.Tensor] = None, skip_mask: Optional[torch.Tensor] = None,
+                    L: int = 1):
+    """-> (dT [L,b,D] or None, dres [b,D] or None, dmain [b,D])."""
+    dev = _req_cuda(T, main, dout, res_in, skip_mask)
+    main, dout = main.float().contiguous(), dout.float().contiguous()
+    b, D = main.shape
+    dT = dres = None
+    if mode == _ffi.CAM_READOUT_AVG:
+        T = T.float().contiguous()
+        L = T.shape[0]
+        dT = torch.empty_like(T)
+    else:
+        res_in = res_in.float().contiguous()
+        dres = torch.empty_like(res_in)
+    if skip_mask is not None:
+        skip_mask = skip_mask.to(device=dev, dtype=torch.uint8).contiguous()
+    dmain = torch.empty_like(main)
+    with torch.cuda.device(dev):
+        _call("vtc_cam_readout_bwd", _ptr(T), _ptr(main), _ptr(res_in), _ptr(skip_mask), _ptr(dout), L, b,
+              D, mode, _ptr(dT), _ptr(dres), _ptr(dmain), _stream(dev))
+    return dT, dres, dmain
