@@ -206,8 +206,8 @@ TopkWs carve_topk(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   t.row_flag = ws.take<unsigned int>(N);
   t.opQ = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
   t.opG = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
-  t.pool = ws.take<float2>((size_t)kTopkMaxSplits * N * tc::TOPK_POOL);
-  t.pool_meta = ws.take<float2>((size_t)kTopkMaxSplits * N);
+  t.pool = ws.take<float2>((size_t)2 * kTopkMaxSplits * N * tc::TOPK_POOL);
+  t.pool_meta = ws.take<float2>((size_t)2 * kTopkMaxSplits * N);
   return t;
 }
 
@@ -265,7 +265,7 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.pool = w.pool, p.pool_meta = w.pool_meta;
   p.topk_keep = k <= 12 ? 16 : tc::TOPK_KEEP_MAX;
   const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, tc::choose_cluster(N, M));
-  a.splits = p.g_splits;
+  a.splits = 2 * p.g_splits;  // two column halves per gallery split
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
@@ -342,8 +342,8 @@ NceWs carve_nce(Workspace& ws, int64_t n, int D, int dtype, int precision) {
     w.b_as_a = w.b_as_b;
     w.a_as_b = w.a_as_a;
   }
-  w.part_row = ws.take<float2>((size_t)kNceMaxSplits * n);
-  w.part_col = ws.take<float2>((size_t)kNceMaxSplits * n);
+  w.part_row = ws.take<float2>((size_t)2 * kNceMaxSplits * n);
+  w.part_col = ws.take<float2>((size_t)2 * kNceMaxSplits * n);
   w.diag_raw = ws.take<float>(n);
   w.bias = ws.take<float>(round_up<int64_t>(n, tc::BN));
   return w;
@@ -390,7 +390,8 @@ int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, 
     VTC_RETURN_IF_ERROR(
         tc::make_operand_tmap(dir == 0 ? w.b_as_b : w.a_as_b, n, o.Kp, o.Kp, tc::BN, &tmB));
     VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_LSE, p.num_kb <= 8, pl, tmA, tmB, p, s));
-    VTC_RETURN_IF_ERROR(launch_lse_merge(p.lse_part, p.g_splits, n, dir == 0 ? row_lse : col_lse, s));
+    VTC_RETURN_IF_ERROR(
+        launch_lse_merge(p.lse_part, 2 * p.g_splits, n, dir == 0 ? row_lse : col_lse, s));
   }
   return launch_infonce_loss(row_lse, col_lse, w.diag_raw, scale, n, diag, loss, s);
 }

@@ -63,8 +63,8 @@ int launch_infonce_loss(const float* row_lse, const float* col_lse, const float*
 }
 
 // --------------------------------------------------------------------------------------- top-k
-constexpr int SEL_WARPS = 4;
-constexpr int SEL_MAX_CAND = 8 * 64;  // splits <= 8, pool = 64
+constexpr int SEL_WARPS = 2;
+constexpr int SEL_MAX_CAND = 16 * 64;  // 2 column halves x 8 splits, pool = 64
 
 template <typename T>
 __device__ __forceinline__ double exact_score(const T* __restrict__ q, const T* __restrict__ x, int D,

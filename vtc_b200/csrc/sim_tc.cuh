@@ -35,7 +35,7 @@ struct Params {
   unsigned int* amb_seg_count;  // [grid] entries each CTA wanted to push (may exceed the capacity)
   unsigned int amb_seg_cap;
   // EPI_LSE  (score is the logit in log2 units: scale already includes log2(e))
-  float2* lse_part;     // [g_splits, N] running (max, sum) in log2 domain
+  float2* lse_part;     // [2 * g_splits, N] running (max, sum) in log2 domain (part = 2*split + half)
   float* diag;          // [N] raw accumulator of column t + diag_offset (nullable)
   int64_t diag_offset;
   // EPI_STORE
@@ -47,8 +47,8 @@ struct Params {
   const float* residual;  // optional [N, ldo]
   int act;                // 0 none, 1 QuickGELU (applied after bias, before residual)
   // EPI_TOPK
-  float2* pool;       // [g_splits, N, TOPK_POOL] (score, column index as int bits)
-  float2* pool_meta;  // [g_splits, N] (entries, tau): every column outside the pool scores >= tau
+  float2* pool;       // [2 * g_splits, N, TOPK_POOL] (score, column index as int bits)
+  float2* pool_meta;  // [2 * g_splits, N] (entries, tau): every column outside the pool scores >= tau
   int topk_keep;      // entries kept by a compaction (>= k, <= TOPK_KEEP_MAX)
 };
 

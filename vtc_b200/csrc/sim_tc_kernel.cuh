@@ -38,8 +38,9 @@ using namespace ptx;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int MAX_RES_KB = 8;              // resident A: up to K' = 512
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;      // two per scheduler: each TMEM lane quarter is split in two column halves
 constexpr int TMEM_COLS = 512;
 
 template <bool kRes>
@@ -49,9 +50,9 @@ struct SmemLayout {
   static constexpr int kResBytes = kRes ? MAX_RES_KB * A_TILE_BYTES : 0;
   static constexpr int kStagesOff = kResBytes;
   static constexpr int kBarOff = kStagesOff + kStages * kStageBytes;
-  static constexpr int kBiasOff = kBarOff + 256;  // 4 epilogue warps x 128 floats
+  static constexpr int kBiasOff = kBarOff + 256;  // 8 epilogue warps x 64 floats
   static constexpr int kNumBars = 2 * kStages + MAX_RES_KB + 1 + 2 + 2;
-  static constexpr int kTotal = kBiasOff + 4 * 128 * 4;
+  static constexpr int kTotal = kBiasOff + EPI_WARPS * 64 * 4;
   static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
   static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
@@ -67,7 +68,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ------------------------------------------------------------------------------------ epilogues
-// Each epilogue thread owns one tile row (= TMEM lane).  `begin_item` / `chunk` / `end_item`.
+// Each epilogue thread owns one tile row (= TMEM lane) and one column half of every tile.
+// `begin_item(p, row, part)` / `chunk` / `end_item(p, part)` with part = 2 * split + half.
 // `bias` points at 32 consecutive entries of the per-column bias staged in this WARP'S PRIVATE
 // shared-memory buffer (128 columns at a time; the global array is padded to a multiple of 256
 // columns by the host, out-of-range columns hold the epilogue's neutral value): reads are
@@ -425,7 +427,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -523,67 +525,77 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quarter this warp may read
-    const int row = ew * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+    // Warp w reads TMEM lane quarter w % 4 (a hardware rule) and column half (w - 4) / 4 of every
+    // accumulator: 8 epilogue warps = two per scheduler, so one warp's TMEM / shared-memory
+    // latencies hide behind the other's arithmetic.  Each (row, half) keeps its own epilogue state;
+    // partial results are indexed by part = 2 * split + half.
+    const int q4 = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float scale = p.scale * (p.scale_ptr ? *p.scale_ptr : 1.0f);
+    constexpr int kHalfCols = BN / 2;  // 128 columns = 4 chunks of 32
     uint32_t as = 0, aphase = 0;
     Epi epi;
-    float* wbias = reinterpret_cast<float*>(smem + L::kBiasOff) + ew * 128;
+    float* wbias = reinterpret_cast<float*>(smem + L::kBiasOff) + (warp - EPI_WARP0) * 64;
+    // column bias, staged 64 columns at a time in this warp's private buffer; lanes 0..15 carry the
+    // next 64 values in registers (prefetched one step ahead so the L2 latency is never exposed)
     float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cluster_id < num_items)  // bias of the first 128 columns of this CTA's first tile
+    if (cluster_id < num_items && lane < 16)
       bias_pre = __ldg(reinterpret_cast<const float4*>(
-                           p.col_bias + (int64_t)(cluster_id / q_groups) * p.tiles_per_split * BN) +
+                           p.col_bias + (int64_t)(cluster_id / q_groups) * p.tiles_per_split * BN +
+                           half * kHalfCols) +
                        lane);
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int qt = (item % q_groups) * kC + cta_rank, split = item / q_groups;
       const int t0 = split * p.tiles_per_split;
       const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
-      epi.begin_item(p, (int64_t)qt * BM + row, split);
+      epi.begin_item(p, (int64_t)qt * BM + row, 2 * split + half);
       for (int tile = t0; tile < t1; ++tile) {
-        const int64_t j0 = (int64_t)tile * BN;
-        // first column of the tile this warp will process next (for the bias prefetch)
+        const int64_t j0 = (int64_t)tile * BN + half * kHalfCols;
+        // first column this warp will process in its next tile (for the bias prefetch)
         int64_t next_j0 = j0 + BN;
         if (tile + 1 >= t1) {
           const int nitem = item + num_clusters;
-          next_j0 = nitem < num_items ? (int64_t)(nitem / q_groups) * p.tiles_per_split * BN : 0;
+          next_j0 = nitem < num_items
+                        ? (int64_t)(nitem / q_groups) * p.tiles_per_split * BN + half * kHalfCols
+                        : 0;
         }
         mbar_wait(&tmem_full[as], aphase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_off + as * BN;
+        const uint32_t taddr = tmem_base + lane_off + as * BN + half * kHalfCols;
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
         tmem_ld_wait(va);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c += 2) {
-          if ((c & 3) == 0) {
-            // stage the bias of columns [32c, 32c + 128) in this warp's private buffer and start
-            // fetching the following 128 (second half of this tile, or the next tile's first half)
-            __syncwarp();
-            reinterpret_cast<float4*>(wbias)[lane] = bias_pre;
-            __syncwarp();
-            const int64_t nj = c == 0 ? j0 + 128 : next_j0;
+        for (int c = 0; c < kHalfCols / 32; c += 2) {
+          // stage the bias of columns [32c, 32c + 64) and start fetching the following 64
+          __syncwarp();
+          if (lane < 16) reinterpret_cast<float4*>(wbias)[lane] = bias_pre;
+          __syncwarp();
+          if (lane < 16) {
+            const int64_t nj = c == 0 ? j0 + 64 : next_j0;
             bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + nj) + lane);
           }
-          const float* bias = wbias + (c & 3) * 32;
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-          epi.chunk(p, va, bias, scale, j0 + c * 32, seg_count);
+          epi.chunk(p, va, wbias, scale, j0 + c * 32, seg_count);
           tmem_ld_wait(vb);
-          if (c + 2 < BN / 32) {
+          if (c + 2 < kHalfCols / 32) {
             tmem_ld_32x32(taddr + (c + 2) * 32, va);
           } else {
-            // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+            // this warp's TMEM reads of the accumulator are complete: one of the 8 arrivals that
+            // hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
-          epi.chunk(p, vb, bias + 32, scale, j0 + (c + 1) * 32, seg_count);
-          if (c + 2 < BN / 32) tmem_ld_wait(va);
+          epi.chunk(p, vb, wbias + 32, scale, j0 + (c + 1) * 32, seg_count);
+          if (c + 2 < kHalfCols / 32) tmem_ld_wait(va);
         }
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
-      epi.end_item(p, split);
+      epi.end_item(p, 2 * split + half);
     }
   }
 
