@@ -322,6 +322,28 @@ def test_topk_matches_oracle(cuda_dev, precision, metric, k):
     np.testing.assert_allclose(_np(vals), wv, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+@pytest.mark.parametrize("k", [11, 16])
+def test_topk_sample_pass_large_gallery(cuda_dev, monkeypatch, precision, k):
+    """Galleries of >= 128 tiles take a sample pass first (per-row threshold from the first 1/16 of
+    the gallery); results must equal the oracle and the single-pass path."""
+    from vtc_b200 import ops
+
+    T, V = make_retrieval_pair(257, 40_000, 64, sigma=2.0, seed=77)
+    V = V.clone()
+    V[39_000] = V[5]      # exact tie between a sample column and a late column
+    V[100] = V[20_000]    # and the other way round
+    q, g = T.to(cuda_dev), V.to(cuda_dev)
+    vals, idx = ops.sim_topk(q, g, k, precision=precision)
+    Tq, Vq = (O.bf16_round(T), O.bf16_round(V)) if precision == "bf16" else (T.numpy(), V.numpy())
+    wv, wi = O.topk_exact(Tq, Vq, k)
+    np.testing.assert_array_equal(_np(idx), wi)
+    monkeypatch.setenv("VTC_TOPK_NO_SAMPLE", "1")
+    vals2, idx2 = ops.sim_topk(q, g, k, precision=precision)
+    np.testing.assert_array_equal(_np(idx2), wi)
+    np.testing.assert_allclose(_np(vals2), _np(vals), rtol=0, atol=0)
+
+
 def test_topk_small_gallery_and_merge(cuda_dev):
     from vtc_b200 import ops
 

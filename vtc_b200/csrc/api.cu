@@ -192,6 +192,7 @@ struct TopkWs {
   float2* pool;
   float2* pool_meta;
   unsigned int* row_flag;
+  float* tau0;
 };
 constexpr int kTopkMaxSplits = 8;
 
@@ -208,6 +209,7 @@ TopkWs carve_topk(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   t.opG = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
   t.pool = ws.take<float2>((size_t)2 * kTopkMaxSplits * N * tc::TOPK_POOL);
   t.pool_meta = ws.take<float2>((size_t)2 * kTopkMaxSplits * N);
+  t.tau0 = ws.take<float>(N);
   return t;
 }
 
@@ -264,10 +266,28 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
   p.pool = w.pool, p.pool_meta = w.pool_meta;
   p.topk_keep = k <= 12 ? 16 : tc::TOPK_KEEP_MAX;
-  const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, tc::choose_cluster(N, M));
-  a.splits = 2 * p.g_splits;  // two column halves per gallery split
+  const int cluster = tc::choose_cluster(N, M);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
+  // Sample pass: the first ~1/16 of the gallery yields a per-row threshold that the k best of the
+  // WHOLE gallery provably beat, so the main pass appends a handful of candidates per row and
+  // (almost) never has to re-sort a buffer.
+  const int64_t g_tiles = ceil_div<int64_t>(M, tc::BN);
+  int64_t sample_tiles = g_tiles / 16;
+  if (sample_tiles > 64) sample_tiles = 64;
+  if (sample_tiles >= 8 && !getenv("VTC_TOPK_NO_SAMPLE")) {
+    tc::Params ps = p;
+    ps.M = sample_tiles * tc::BN;
+    const tc::Plan pls = tc::plan_tiles(ps, 1, cluster);
+    a.splits = 2 * ps.g_splits;
+    CUtensorMap tmS;
+    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, ps.M, o.Kp, o.Kp, tc::BN / pls.cluster, &tmS));
+    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_TOPK, ps.num_kb <= 8, pls, tmA, tmS, ps, s));
+    VTC_RETURN_IF_ERROR(launch_topk_tau(a, w.tau0, s));
+    p.tau_init = w.tau0;
+  }
+  const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, cluster);
+  a.splits = 2 * p.g_splits;  // two column halves per gallery split
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
   VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_TOPK, p.num_kb <= 8, pl, tmA, tmB, p, s));
   VTC_RETURN_IF_ERROR(launch_topk_select(a, s));

@@ -203,6 +203,64 @@ topk_select_kernel(TopkSelectArgs a) {
   }
 }
 
+// Threshold for the main top-k pass from a SAMPLE pass over the first gallery rows: the k-th
+// smallest approximate score a_k of the sample bounds the k-th smallest exact score of the whole
+// gallery (d_k(all) <= d_k(sample) <= a_k + delta), so every member of the exact top-k has
+// approximate score < a_k + 3 delta.  One warp per query row.
+template <typename T>
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+topk_tau_kernel(TopkSelectArgs a, float* __restrict__ tau0) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * SEL_WARPS + w;
+  if (t >= a.ex.N) return;
+  const T* q = (const T*)a.ex.Q + t * a.ex.ldq;
+  const int ncand = a.splits * a.pool;
+  float last_v = -INFINITY;
+  int last_c = -1, have = 0;
+  for (int r = 0; r < a.k; ++r) {
+    float bv = INFINITY;
+    int bc = 0x7fffffff;
+    for (int c = lane; c < ncand; c += 32) {
+      const int s = c / a.pool, i = c % a.pool;
+      const int64_t slot = (int64_t)s * a.ex.N + t;
+      if (i >= (int)a.pool_meta[slot].x) continue;
+      const float x = a.pool_buf[slot * a.pool + i].x;
+      if (x != x) continue;
+      const bool above = x > last_v || (x == last_v && c > last_c);
+      if (above && (x < bv || (x == bv && c < bc))) bv = x, bc = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (ov < bv || (ov == bv && oc < bc)) bv = ov, bc = oc;
+    }
+    if (bc == 0x7fffffff) break;
+    last_v = bv, last_c = bc;
+    ++have;
+  }
+  const double qq = sq_seq64(q, a.ex.D);
+  const double qn = sqrt(qq);
+  const double gmax_sq = (double)__uint_as_float(*a.max_sq_bits);
+  const double gn = sqrt(gmax_sq);
+  const double delta = a.ex.metric == VTC_METRIC_L2
+                           ? 2.0 * a.guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn)
+                           : (double)a.guard_rel * qn * gn + 1.2e-7 * qn * gn;
+  if (lane == 0)
+    tau0[t] = (have == a.k && qq == qq) ? __double2float_ru((double)last_v + 3.0 * delta) : INFINITY;
+}
+
+int launch_topk_tau(const TopkSelectArgs& a, float* tau0, cudaStream_t s) {
+  if (a.ex.N == 0) return VTC_OK;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(a.ex.N, SEL_WARPS);
+  if (a.ex.bf16)
+    topk_tau_kernel<__nv_bfloat16><<<grid, SEL_WARPS * 32, 0, s>>>(a, tau0);
+  else
+    topk_tau_kernel<float><<<grid, SEL_WARPS * 32, 0, s>>>(a, tau0);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
 constexpr int BRUTE_THREADS = 128;
 constexpr int BRUTE_KMAX = 16;
 

@@ -50,6 +50,7 @@ struct Params {
   float2* pool;       // [2 * g_splits, N, TOPK_POOL] (score, column index as int bits)
   float2* pool_meta;  // [2 * g_splits, N] (entries, tau): every column outside the pool scores >= tau
   int topk_keep;      // entries kept by a compaction (>= k, <= TOPK_KEEP_MAX)
+  const float* tau_init;  // optional [N]: initial per-row threshold (from a sample pass); NULL = +inf
 };
 
 // Row-major bf16 [rows, cols] with leading dimension ld (elements) -> 2-D TMA descriptor with a

@@ -304,7 +304,10 @@ struct TopkEpi {
     tau = INFINITY;
     cnt = 0;
     buf = buf_of(p, t < p.N ? t : 0, split);
-    if (t >= p.N) tau = -INFINITY;  // padded rows never append
+    if (t >= p.N)
+      tau = -INFINITY;  // padded rows never append
+    else if (p.tau_init)
+      tau = p.tau_init[t];  // threshold proven by a sample pass: appends are rare from column 0
   }
   // warp-cooperative: sort lane `r`'s buffer (`my_buf` / `my_cnt` are each lane's own), keep the
   // TOPK_KEEP smallest in place and return the new threshold to every lane.  Static with by-value
