@@ -214,6 +214,8 @@ def run_ours(a):
             hits, medr = ops.rank_finalize(rank0, gts, a.m, k_vals)
             return hits, medr
         res = sharded_rank_eval(q_local, g_local, a.n, a.m, k_vals, "l2", a.precision)
+        if res.get("phases_ms") and rank == 0:
+            print("phases_ms", json.dumps(res["phases_ms"]), file=sys.stderr)
         return res["hits"], res["medr"]
 
     def barrier():

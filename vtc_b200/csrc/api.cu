@@ -269,12 +269,13 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   const int cluster = tc::choose_cluster(N, M);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
-  // Sample pass: the first ~1/16 of the gallery yields a per-row threshold that the k best of the
+  // Sample pass: the first ~1/32 of the gallery (8..32 tiles) yields a per-row threshold that the k best of the
   // WHOLE gallery provably beat, so the main pass appends a handful of candidates per row and
   // (almost) never has to re-sort a buffer.
   const int64_t g_tiles = ceil_div<int64_t>(M, tc::BN);
-  int64_t sample_tiles = g_tiles / 16;
-  if (sample_tiles > 64) sample_tiles = 64;
+  int64_t sample_tiles = g_tiles / 32;  // >= 4 gallery tiles of main pass per sample tile
+  if (sample_tiles < 8) sample_tiles = g_tiles >= 128 ? 8 : 0;
+  if (sample_tiles > 32) sample_tiles = 32;
   if (sample_tiles >= 8 && !getenv("VTC_TOPK_NO_SAMPLE")) {
     tc::Params ps = p;
     ps.M = sample_tiles * tc::BN;

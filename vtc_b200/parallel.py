@@ -19,10 +19,33 @@ The compute backend is injectable so that the host logic is testable on CPU with
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+class _Phases:
+    """Optional CUDA-event phase timing (VTC_PHASE_TIMING=1): where a sharded step spends its time."""
+
+    def __init__(self, dev):
+        self.on = bool(os.environ.get("VTC_PHASE_TIMING")) and dev.type == "cuda"
+        self.marks = []
+        self.dev = dev
+        self.mark("start")
+
+    def mark(self, name):
+        if self.on:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.dev))
+            self.marks.append((name, ev))
+
+    def result(self):
+        if not self.on:
+            return None
+        torch.cuda.synchronize(self.dev)
+        return {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self.marks[:-1], self.marks[1:])}
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -93,6 +116,7 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     g_starts = [shard_bounds(M_total, world, r)[0] for r in range(world)]
     assert g_local.shape[0] == g_sizes[rank], "g_local does not match shard_bounds(M_total)"
     dev = q_local.device
+    ph = _Phases(dev)
     if precision == "bf16" and q_local.dtype == torch.float32 and g_local.dtype == torch.float32:
         # the bf16 mode ranks the RN-even bf16 roundings of the inputs: round BEFORE the exchange
         # (identical results, half the NVLink bytes and half the operand-prep reads)
@@ -113,6 +137,7 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
         gathered = torch.empty((world * mx, send.shape[1]), dtype=send.dtype, device=dev)
         work = dist.all_gather_into_tensor(gathered, send.contiguous(), group=group, async_op=True)
 
+    ph.mark("cast+gather_issue")
     # ground-truth scores: d(t, gt) lives in the chunk that owns gallery row t; start with ours
     n_local = qe - qs
     gs0, ge0 = g_starts[rank], g_starts[rank] + g_sizes[rank]
@@ -124,8 +149,10 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
         # every ground truth is in our own chunk: rank against it while the gather is in flight
         backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
         local_done = True
+    ph.mark("gt+local_rank")
     if work is not None:
         work.wait()
+        ph.mark("gather_wait")
         # remote row ranges as (start row in the global gallery, tensor)
         if equal:
             remote = [(0, gathered[:gs0]), (ge0, gathered[ge0:M_total])]
@@ -144,6 +171,7 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     elif not local_done and g_sizes[rank] > 0:
         backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
 
+    ph.mark("remote_rank")
     hits, _ = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), False)
     hits = hits.clone()
     medr = None
@@ -159,7 +187,9 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
             full = rank0
         _, m = backend.rank_finalize(full.clone(), None, M_total, [], True)
         medr = m
-    return {"hits": hits, "medr": medr, "rank0_local": rank0, "num_queries": N_total}
+    ph.mark("finalize+collectives")
+    return {"hits": hits, "medr": medr, "rank0_local": rank0, "num_queries": N_total,
+            "phases_ms": ph.result()}
 
 
 def _gt_all_local(qs: int, qe: int, g_start: int, g_size: int) -> bool:
