@@ -34,6 +34,8 @@ class OracleBackend:
         return torch.from_numpy(out)
 
     def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0):
+        if gt_score is None:
+            gt_score = self.gt_scores(q, g, row_offset, col_offset, metric, precision)
         full = self.O.scores64(q, g, self._m(metric))
         d0 = gt_score.numpy()
         for t in range(q.shape[0]):
@@ -41,6 +43,7 @@ class OracleBackend:
             jg = np.arange(g.shape[0]) + col_offset
             c = ((full[t] < d0[t]) & (jg != gt)).sum() + ((full[t] == d0[t]) & (jg < gt)).sum()
             rank0[t] += int(c)
+        return gt_score
 
     def rank_finalize(self, rank0, gt_score, M_total, k_vals, want_medr):
         if gt_score is not None:

@@ -67,8 +67,11 @@ class CudaBackend:
         return self.ops.gt_scores(q, g, None, row_offset, col_offset, metric, precision)
 
     def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0):
-        self.ops.sim_rank(q, g, None, row_offset, col_offset, metric, precision, gt_score, rank0,
-                          accumulate=True)
+        """Accumulates into rank0; gt_score None = every ground truth lies inside g (computed and
+        returned)."""
+        _, gs = self.ops.sim_rank(q, g, None, row_offset, col_offset, metric, precision, gt_score,
+                                  rank0, accumulate=True)
+        return gs
 
     def rank_finalize(self, rank0, gt_score, M_total, k_vals, want_medr):
         return self.ops.rank_finalize(rank0, gt_score, M_total, k_vals, want_medr)
@@ -141,14 +144,16 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     # ground-truth scores: d(t, gt) lives in the chunk that owns gallery row t; start with ours
     n_local = qe - qs
     gs0, ge0 = g_starts[rank], g_starts[rank] + g_sizes[rank]
-    gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
     rank0 = torch.zeros(n_local, dtype=torch.int32, device=dev)
-    gt_local = world == 1 or _gt_all_local(qs, qe, gs0, g_sizes[rank])
+    gt_local = (world == 1 or _gt_all_local(qs, qe, gs0, g_sizes[rank])) and g_sizes[rank] > 0
     local_done = False
-    if gt_local and g_sizes[rank] > 0:
-        # every ground truth is in our own chunk: rank against it while the gather is in flight
-        backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
+    if gt_local:
+        # every ground truth is in our own chunk: rank against it (the call also yields the
+        # ground-truth scores) while the gather is in flight
+        gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0)
         local_done = True
+    else:
+        gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
     ph.mark("gt+local_rank")
     if work is not None:
         work.wait()
@@ -172,21 +177,24 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
         backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
 
     ph.mark("remote_rank")
-    hits, _ = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), False)
-    hits = hits.clone()
     medr = None
-    if world > 1:
+    if world == 1:
+        hits, medr = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), want_medr)
+        hits = hits.clone()
+    elif want_medr:
+        # NaN ground truths -> M_total locally, then ONE exchange: gather the int32 ranks and count
+        # hits / select the median on the full vector (identical on every rank)
+        backend.rank_finalize(rank0, gt_score, M_total, [], False)
+        q_sizes = [shard_bounds(N_total, world, r)[1] - shard_bounds(N_total, world, r)[0]
+                   for r in range(world)]
+        allr, _ = _all_gather_padded(rank0, q_sizes, group)
+        full = torch.cat([allr[r][:q_sizes[r]] for r in range(world)])
+        hits, medr = backend.rank_finalize(full, None, M_total, list(k_vals), True)
+        hits = hits.clone()
+    else:
+        hits, _ = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), False)
+        hits = hits.clone()
         dist.all_reduce(hits, op=dist.ReduceOp.SUM, group=group)
-    if want_medr:
-        if world > 1:
-            q_sizes = [shard_bounds(N_total, world, r)[1] - shard_bounds(N_total, world, r)[0]
-                       for r in range(world)]
-            allr, _ = _all_gather_padded(rank0, q_sizes, group)
-            full = torch.cat([allr[r][:q_sizes[r]] for r in range(world)])
-        else:
-            full = rank0
-        _, m = backend.rank_finalize(full.clone(), None, M_total, [], True)
-        medr = m
     ph.mark("finalize+collectives")
     return {"hits": hits, "medr": medr, "rank0_local": rank0, "num_queries": N_total,
             "phases_ms": ph.result()}
