@@ -144,6 +144,73 @@ def config2():
         emit(bench="c2_cam_torch_cudagraph_fp32", error=str(e)[:200])
 
 
+def config2_train():
+    """One training step of the hot path at config-2 size: CAM forward + InfoNCE + backward through
+    both (precomputed CLIP features in, as in the reference's cached-feature branch)."""
+    b, D, nc = 256, 512, 5
+    vis, txt = make_batch_pair(b, D, seed=1023)
+    main, aux = make_cam_inputs(b, nc, D, seed=1023)
+    v, x = vis.to(dev), aux.to(dev).permute(1, 0, 2).contiguous()  # comments [b, nc, D]
+    for prec in ("exact", "bf16"):
+        model = PretrainedCLIP_finaltf(D, precision=prec).to(dev).train()
+        model.random_skip_adapter = False
+        for blk in model.final_transformer.resblocks:
+            torch.nn.init.normal_(blk.mlp.c_proj.weight, std=0.02)
+            torch.nn.init.normal_(blk.attn.out_proj.weight, std=0.02)
+        title = txt.to(dev).requires_grad_(True)
+
+        def step():
+            out = model(v, title, x)
+            loss = clip_loss(out, {})
+            loss.backward()
+            model.zero_grad(set_to_none=True)
+            title.grad = None
+
+        us, nl = timeit(step, iters=20)
+        emit(bench="c2_train_step_cam+infonce_fwd_bwd", precision=prec, us=us, launches=nl)
+
+    # stock torch: same computation, eager fp32
+    class Block(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attn = torch.nn.MultiheadAttention(D, 8)
+            self.ln_1 = torch.nn.LayerNorm(D)
+            self.c_fc = torch.nn.Linear(D, 4 * D)
+            self.c_proj = torch.nn.Linear(4 * D, D)
+            self.ln_2 = torch.nn.LayerNorm(D)
+
+        def forward(self, h):
+            y = self.ln_1(h)
+            h = h + self.attn(y, y, y, need_weights=False)[0]
+            y = self.c_fc(self.ln_2(h))
+            return h + self.c_proj(y * torch.sigmoid(1.702 * y))
+
+    blocks = torch.nn.Sequential(Block(), Block()).to(dev).train()
+    scale = torch.nn.Parameter(torch.tensor(math.log(1 / 0.07), device=dev))
+    title = txt.to(dev).requires_grad_(True)
+    comm = x.permute(1, 0, 2).contiguous()
+
+    def nrm(t):
+        return t / t.norm(dim=-1, keepdim=True)
+
+    def torch_step():
+        c = nrm(torch.stack([title, *comm], 0))
+        tf = blocks(c)
+        res = nrm(torch.mean(torch.stack([nrm(s_) for s_ in tf], 0), 0))
+        ft = nrm(nrm(nrm(title) + res))
+        fv = nrm(v)
+        sim = scale.exp() * fv @ ft.t()
+        labels = torch.arange(b, device=dev)
+        loss = 0.5 * (F.cross_entropy(sim, labels) + F.cross_entropy(sim.t(), labels))
+        loss.backward()
+        blocks.zero_grad(set_to_none=True)
+        title.grad = None
+        scale.grad = None
+
+    us, _ = timeit(torch_step, iters=20)
+    emit(bench="c2_train_step_torch_eager_fp32", us=us)
+
+
 def torch_rank(q, g, tile=8192):
     """Stock torch on the same GPU: bf16 cuBLAS GEMM tile + compare-count against the gt score."""
     qb, gb = q.bfloat16(), g.bfloat16()
@@ -201,5 +268,6 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c35"]
     if "c2" in which:
         config2()
+        config2_train()
     if "c35" in which:
         config3_and_5()
