@@ -222,8 +222,11 @@ int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D
  * (dX = dY W = linear(dY, W^T), dW = dY^T X = linear(dY^T, X^T)); the rest is here.
  * vtc_layernorm_bwd: dX = LN'(dY) + dres (dres nullable), dgamma / dbeta [D] overwritten.
  * vtc_cam_readout_bwd: residual activation NONE only; AVG writes dT [L,b,D], RESIDUAL_ONLY writes
- * dres [b,D]; dmain [b,D] is the part through normalize(main) at model.py:203.
+ * dres [b,D]; dmain [b,D] is the part through normalize(main) at model.py:203; UNIFORM (averaging
+ * fusion) writes dT only.
  * vtc_cam_stack_normalize_bwd: dX [L,b,D] -> dmain [b,D] (token 0), daux [L-1,b,D]. */
+int vtc_normalize_bwd(const float* X, const float* dY, int64_t rows, int D, float* dX,
+                      vtc_stream_t stream); /* dX of Y = X / |X| (model/model.py:26-27) */
 int vtc_transpose(const float* in, int64_t rows, int64_t cols, float* out, vtc_stream_t stream);
 int vtc_gelu_bwd(const float* dF, const float* U, int64_t n, float* dU, vtc_stream_t stream);
 int vtc_colsum(const float* X, int64_t rows, int64_t cols, float* out, vtc_stream_t stream);

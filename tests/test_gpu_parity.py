@@ -545,6 +545,55 @@ def test_cam_backward_matches_autograd_oracle(cuda_dev, avg):
     assert out2.requires_grad
 
 
+def test_training_step_gradients_through_the_model(cuda_dev):
+    """The whole training call chain of trainer/trainer.py:77-79 on precomputed features:
+    model(vis, title, comments) -> clip_loss -> backward, against torch autograd through the oracle."""
+    from vtc_b200.model import PretrainedCLIP, PretrainedCLIP_finaltf, clip_loss
+
+    b, nc, D, layers, heads = 32, 3, 128, 2, 4
+    params = O.make_cam_params(D, layers, heads, seed=21, rerandomise=True)
+    g = torch.Generator().manual_seed(5)
+    vis, title, comm = torch.randn(b, D, generator=g), torch.randn(b, D, generator=g), torch.randn(b, nc, D, generator=g)
+    ls0 = math.log(20.0)
+    # oracle
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    to, co, lo = title.clone().requires_grad_(True), comm.clone().requires_grad_(True), torch.tensor(ls0, requires_grad=True)
+    ft = O.normalize(O.adapt_feature(to, co.permute(1, 0, 2), po, layers, heads))
+    loss_o = O.clip_loss(O.sim_matrix(O.normalize(vis), ft, lo.exp()))
+    loss_o.backward()
+    # CUDA path (eval-mode routing, autograd on)
+    m = PretrainedCLIP_finaltf(D, n_layers=layers, n_heads=heads, logit_scale_init=ls0).to(cuda_dev)
+    m.final_transformer.load_state_dict(params, strict=True)
+    m.eval()
+    tg, cg = title.to(cuda_dev).requires_grad_(True), comm.to(cuda_dev).requires_grad_(True)
+    out = m(vis.to(cuda_dev), tg, cg)
+    loss = clip_loss(out, {})
+    np.testing.assert_allclose(loss.item(), loss_o.item(), rtol=1e-4)
+    loss.backward()
+
+    def close(got, want, name, tol=5e-3):
+        want = want.numpy()
+        err = np.abs(_np(got) - want).max() / (np.abs(want).max() + 1e-12)
+        assert err < tol, f"{name}: {err:.3e}"
+
+    close(tg.grad, to.grad, "dtitle")
+    close(cg.grad, co.grad, "dcomments")
+    close(m.logit_scale.grad, lo.grad, "dlogit_scale")
+    for n_, p in m.final_transformer.named_parameters():
+        close(p.grad, po[n_].grad, n_)
+    # averaging-fusion baseline (model/model.py:356-366) is differentiable too
+    m2 = PretrainedCLIP(D, comment_fusion="averaging", logit_scale_init=ls0).to(cuda_dev)
+    t2, c2 = title.to(cuda_dev).requires_grad_(True), comm.to(cuda_dev).requires_grad_(True)
+    loss2 = clip_loss(m2(vis.to(cuda_dev), t2, c2), {})
+    loss2.backward()
+    t3, c3 = title.clone().requires_grad_(True), comm.clone().requires_grad_(True)
+    l3 = O.clip_loss(O.sim_matrix(O.normalize(vis), O.averaging_fusion(t3, c3), torch.tensor(20.0)))
+    l3.backward()
+    np.testing.assert_allclose(loss2.item(), l3.item(), rtol=1e-4)
+    close(t2.grad, t3.grad, "avg dtitle")
+    close(c2.grad, c3.grad, "avg dcomments")
+
+
 def test_cam_transformer_module_forward(cuda_dev):
     """The op-by-op CAMTransformer.forward (LayerNorm / tcgen05 linears / attention core as separate
     C-ABI calls) against the oracle's clip.model.Transformer restatement."""

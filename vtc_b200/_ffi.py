@@ -73,6 +73,7 @@ SIGNATURES.update({
 
 
 SIGNATURES.update({
+    "vtc_normalize_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P]),
     "vtc_transpose": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "vtc_gelu_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
     "vtc_colsum": (c_int, [_P, c_int64, c_int64, _P, _P]),

@@ -203,6 +203,43 @@ __device__ __forceinline__ void normalize_bwd_row(const float* __restrict__ x,
   for (int k = lane; k < D; k += 32) dx[k] = (scale_in * dy[k] - (x[k] / nrm) * ydy) / nrm;
 }
 
+// backward of normalize (model/model.py:26-27): one warp per row
+__global__ void __launch_bounds__(256)
+normalize_bwd_kernel(const float* __restrict__ X, const float* __restrict__ dY, int64_t rows, int D,
+                     float* __restrict__ dX) {
+  const int64_t r = (int64_t)blockIdx.x * BW + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  normalize_bwd_row(X + r * D, dY + r * D, D, threadIdx.x & 31, dX + r * D, 1.f);
+}
+
+// backward of the averaging fusion normalize(mean_l T_l) (model/model.py:356-366): dT [L,b,D]
+__global__ void __launch_bounds__(256)
+uniform_readout_bwd_kernel(const float* __restrict__ T, const float* __restrict__ dout, int L,
+                           int64_t b, int D, float* __restrict__ dT) {
+  const int64_t bi = (int64_t)blockIdx.x * BW + (threadIdx.x >> 5);
+  if (bi >= b) return;
+  const int lane = threadIdx.x & 31;
+  // m = mean_l T_l is rebuilt on the fly; dm = (dout - y (y . dout)) / |m|, dT_l = dm / L
+  float mm = 0.f, md = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    float m = 0.f;
+    for (int l = 0; l < L; ++l) m += T[((int64_t)l * b + bi) * D + k];
+    m /= (float)L;
+    mm = fmaf(m, m, mm);
+    md = fmaf(m, dout[bi * D + k], md);
+  }
+  mm = warp_sum(mm);
+  md = warp_sum(md);
+  const float nrm = sqrtf(mm);
+  for (int k = lane; k < D; k += 32) {
+    float m = 0.f;
+    for (int l = 0; l < L; ++l) m += T[((int64_t)l * b + bi) * D + k];
+    m /= (float)L;
+    const float dm = (dout[bi * D + k] - (m / nrm) * (md / nrm)) / nrm / (float)L;
+    for (int l = 0; l < L; ++l) dT[((int64_t)l * b + bi) * D + k] = dm;
+  }
+}
+
 // backward of normalize(stack([main, *aux])) (model/model.py:150-151): dX [L,b,D] -> dmain, daux
 __global__ void __launch_bounds__(256)
 cam_stack_normalize_bwd_kernel(const float* __restrict__ main, const float* __restrict__ aux,
@@ -366,11 +403,24 @@ int launch_cam_stack_normalize_bwd(const float* main, const float* aux, const fl
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }
+int launch_normalize_bwd(const float* X, const float* dY, int64_t rows, int D, float* dX,
+                         cudaStream_t s) {
+  if (rows == 0) return VTC_OK;
+  normalize_bwd_kernel<<<(unsigned)ceil_div<int64_t>(rows, BW), 256, 0, s>>>(X, dY, rows, D, dX);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
 int launch_cam_readout_bwd(const float* T, const float* main, const float* res_in,
                            const uint8_t* skip_mask, const float* dout, int L, int64_t b, int D,
                            int mode, float* dT, float* dres, float* dmain, cudaStream_t s) {
   if (b == 0) return VTC_OK;
   if (D > 1024) return VTC_ERR_UNSUPPORTED_SHAPE;
+  if (mode == VTC_CAM_READOUT_UNIFORM) {
+    uniform_readout_bwd_kernel<<<(unsigned)ceil_div<int64_t>(b, BW), 256, 0, s>>>(T, dout, L, b, D, dT);
+    VTC_LAUNCH_CHECK();
+    return VTC_OK;
+  }
   const size_t smem = (size_t)BW * 3 * D * sizeof(float);
   auto* kern = &cam_readout_bwd_kernel;
   if (smem > 48 * 1024) {
@@ -418,9 +468,19 @@ int vtc_cam_stack_normalize_bwd(const float* main, const float* aux, const float
     return VTC_ERR_INVALID_ARG;
   return launch_cam_stack_normalize_bwd(main, aux, dX, L, b, D, dmain, daux, (cudaStream_t)stream);
 }
+int vtc_normalize_bwd(const float* X, const float* dY, int64_t rows, int D, float* dX,
+                      vtc_stream_t stream) {
+  if (!X || !dY || !dX || rows < 0 || D <= 0) return VTC_ERR_INVALID_ARG;
+  return launch_normalize_bwd(X, dY, rows, D, dX, (cudaStream_t)stream);
+}
 int vtc_cam_readout_bwd(const float* T, const float* main, const float* res_in,
                         const uint8_t* skip_mask, const float* dout, int L, int64_t b, int D,
                         int mode, float* dT, float* dres, float* dmain, vtc_stream_t stream) {
+  if (mode == VTC_CAM_READOUT_UNIFORM) {
+    if (!T || !dout || !dT || b < 0 || D <= 0 || L < 1) return VTC_ERR_INVALID_ARG;
+    return launch_cam_readout_bwd(T, nullptr, nullptr, nullptr, dout, L, b, D, mode, dT, nullptr,
+                                  nullptr, (cudaStream_t)stream);
+  }
   if (!main || !dout || !dmain || b < 0 || D <= 0 || L < 1) return VTC_ERR_INVALID_ARG;
   if (mode == VTC_CAM_READOUT_AVG ? (!T || !dT) : (mode != VTC_CAM_READOUT_RESIDUAL_ONLY || !res_in || !dres))
     return VTC_ERR_INVALID_ARG;

@@ -36,8 +36,37 @@ __all__ = [
 ]
 
 
+class _Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x.detach())
+        return ops.normalize(x.detach())
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.normalize_bwd(x, dy).to(x.dtype)
+
+
+class _UniformReadout(torch.autograd.Function):
+    """normalize(mean_l T_l): the averaging fusion of model/model.py:356-366."""
+
+    @staticmethod
+    def forward(ctx, stacked):
+        ctx.save_for_backward(stacked.detach())
+        return ops.cam_readout(stacked.detach(), None, _ffi.CAM_READOUT_UNIFORM)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (stacked,) = ctx.saved_tensors
+        return ops.cam_readout_bwd(stacked, None, dout, _ffi.CAM_READOUT_UNIFORM)[0]
+
+
 def normalize(x: torch.Tensor) -> torch.Tensor:
-    """x / x.norm(dim=-1, keepdim=True) -- model/model.py:26-27 (no eps; zero row -> NaN)."""
+    """x / x.norm(dim=-1, keepdim=True) -- model/model.py:26-27 (no eps; zero row -> NaN).
+    Differentiable (vtc_normalize / vtc_normalize_bwd)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _Normalize.apply(x)
     return ops.normalize(x)
 
 
@@ -434,7 +463,7 @@ class PretrainedCLIP(PretrainedCLIPBase):
         elif self.comment_fusion == "averaging":
             feats_comm = self._load_comment_features(comments)                   # [nc, b, D]
             stacked = torch.cat([feats_title.float().unsqueeze(0), feats_comm], 0)
-            feats_text = ops.cam_readout(stacked, None, _ffi.CAM_READOUT_UNIFORM)  # :356-362,:366
+            feats_text = _UniformReadout.apply(stacked)                          # :356-362,:366
         else:
             raise ValueError("Comment fusion method not specified.")
         feats_vis = normalize(feats_vis.float())                                 # :367

@@ -467,6 +467,18 @@ def _call(name, *args):
     _ffi.check(getattr(_ffi.load(), name)(*args), name)
 
 
+def normalize_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """dX of y = x / |x| over the last dim."""
+    dev = _req_cuda(x, dy)
+    shp = x.shape
+    x2 = x.float().reshape(-1, shp[-1]).contiguous()
+    d2 = dy.float().reshape(-1, shp[-1]).contiguous()
+    out = torch.empty_like(x2)
+    with torch.cuda.device(dev):
+        _call("vtc_normalize_bwd", _ptr(x2), _ptr(d2), x2.shape[0], x2.shape[1], _ptr(out), _stream(dev))
+    return out.reshape(shp)
+
+
 def transpose(x: torch.Tensor) -> torch.Tensor:
     """[R, C] fp32 -> [C, R] (materialised; operands of the backward GEMMs)."""
     dev = _req_cuda(x)
@@ -554,7 +566,16 @@ def cam_readout_bwd(T: Optional[torch.Tensor], main: torch.Tensor, dout: torch.T
                     L: int = 1):
     """-> (dT [L,b,D] or None, dres [b,D] or None, dmain [b,D])."""
     dev = _req_cuda(T, main, dout, res_in, skip_mask)
-    main, dout = main.float().contiguous(), dout.float().contiguous()
+    dout = dout.float().contiguous()
+    if mode == _ffi.CAM_READOUT_UNIFORM:
+        T = T.float().contiguous()
+        L, b, D = T.shape
+        dT = torch.empty_like(T)
+        with torch.cuda.device(dev):
+            _call("vtc_cam_readout_bwd", _ptr(T), None, None, None, _ptr(dout), L, b, D, mode, _ptr(dT),
+                  None, None, _stream(dev))
+        return dT, None, None
+    main = main.float().contiguous()
     b, D = main.shape
     dT = dres = None
     if mode == _ffi.CAM_READOUT_AVG:
