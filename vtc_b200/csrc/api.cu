@@ -24,7 +24,9 @@ namespace {
 
 // Bound on |tensor-core dot - exact dot| / (|q| |x|) for operands of padded depth Kp; see
 // DESIGN.md "guard band".  Each of the Kp/16 accumulation steps of the fp32 accumulator may lose
-// up to 2 ulp (2^-23) of |q||x| (measured total on B200: <= 1.8e-7 at K = 768).
+// up to 1 ulp (2^-24, i.e. truncation rather than round-to-nearest) of the FULL-SCALE value |q||x|
+// -- partial sums are bounded by it (Cauchy-Schwarz) -- plus 8 steps of slack for the epilogue's
+// own fp32 roundings (measured total on B200: <= 1.8e-7 at K = 768, 13x inside the bound).
 //   BF16 : products of bf16 are exact in fp32, so that is the whole error;
 //   EXACT: the 3-term bf16 split additionally drops <= 3 * 2^-18 (1.15e-5) of each product.
 float guard_rel_for(int precision, int Kp) {
@@ -33,7 +35,7 @@ float guard_rel_for(int precision, int Kp) {
     const float v = (float)atof(e);
     if (v > 0.f) return v;
   }
-  const float accum = (float)(Kp / 16 + 8) * 1.1920929e-07f;
+  const float accum = (float)(Kp / 16 + 8) * 5.9604645e-08f;
   return precision == VTC_PREC_BF16 ? accum : 1.2e-05f + accum;
 }
 
