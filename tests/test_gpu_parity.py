@@ -160,6 +160,51 @@ def test_rank_all_duplicates_and_overflow_fallback(cuda_dev, lib):
     np.testing.assert_array_equal(_np(rank0), want)
 
 
+@pytest.mark.parametrize("precision", ["brute", "exact", "bf16"])
+def test_rank_and_topk_degenerate_shapes(cuda_dev, precision):
+    """Empty / single-row / odd-D / M < k inputs (the ragged edges of every tile)."""
+    from vtc_b200 import ops
+
+    for (N, M, D) in ((1, 1, 8), (3, 2, 5), (1, 300, 37), (130, 1, 64), (257, 513, 1)):
+        g = torch.Generator().manual_seed(N * 1000 + M)
+        G = torch.randn(M, D, generator=g)
+        Q = torch.randn(N, D, generator=g)
+        gt = torch.randint(0, M, (N,), generator=g)
+        rank0, gts = ops.sim_rank(Q.to(cuda_dev), G.to(cuda_dev), gt=gt.to(cuda_dev), precision=precision)
+        hits, medr = ops.rank_finalize(rank0, gts, M, [1, 5])
+        Qo, Go = (O.bf16_round(Q), O.bf16_round(G)) if precision == "bf16" else (Q, G)
+        want = O.rank0_exact(Qo, Go, gt=gt.numpy())
+        np.testing.assert_array_equal(_np(rank0), want)
+        assert _np(medr)[0] == O.medr(want)
+        vals, idx = ops.sim_topk(Q.to(cuda_dev), G.to(cuda_dev), 5, precision=precision)
+        np.testing.assert_array_equal(_np(idx), O.topk_exact(Qo, Go, 5)[1])
+    # no queries at all: nothing to do, empty results
+    Q0 = torch.empty(0, 16, device=cuda_dev)
+    G0 = torch.randn(9, 16, device=cuda_dev)
+    r, gs = ops.sim_rank(Q0, G0, precision=precision)
+    assert r.shape == (0,) and gs.shape == (0,)
+    v, i = ops.sim_topk(Q0, G0, 3, precision=precision)
+    assert v.shape == (0, 3) and i.shape == (0, 3)
+
+
+def test_topk_full_size_1M_gallery(cuda_dev):
+    """BASELINE config 5 at full gallery size on one GPU (1M x 512, bf16): the tensor-core path
+    against the fp64 brute-force kernel on all rows and against the CPU oracle on a few."""
+    from vtc_b200 import ops
+
+    M, N, D, k = 1_000_000, 48, 512, 11
+    T, V = make_retrieval_pair(N, M, D, seed=1023)
+    q, g = T.to(cuda_dev), V.to(cuda_dev)
+    vals, idx = ops.sim_topk(q, g, k, precision="bf16")
+    qb, gb = q.bfloat16().float(), g.bfloat16().float()
+    bv, bi = ops.sim_topk(qb, gb, k, precision="brute")
+    np.testing.assert_array_equal(_np(idx), _np(bi))
+    np.testing.assert_allclose(_np(vals), _np(bv), rtol=1e-5, atol=1e-6)
+    wi = O.topk_exact(O.bf16_round(T[:8]), O.bf16_round(V), k)[1]
+    np.testing.assert_array_equal(_np(idx[:8]), wi)
+    assert (_np(idx[:, 0]) == np.arange(N)).mean() > 0.2  # queries are noisy copies of rows 0..N-1
+
+
 def test_rank_chunked_gallery_is_additive(cuda_dev):
     """rank counts add over gallery chunks (the multi-GPU decomposition)."""
     from vtc_b200 import ops
