@@ -64,6 +64,9 @@ def test_invalid_arguments_are_rejected_before_any_launch(lib):
     assert lib.vtc_row_norms(None, 4, 8, 8, _ffi.F32, None, None, None) == -1
     assert lib.vtc_sim_rank(None, None, 4, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
                             _ffi.PREC_EXACT, None, None, 0, None, None, 0, None) == -1
+    # zero queries is a valid no-op even with NULL pointers
+    assert lib.vtc_sim_rank(None, None, 0, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
+                            _ffi.PREC_EXACT, None, None, 0, None, None, 0, None) == 0
     assert lib.vtc_topk_merge(None, None, 2, 4, 3, None, None, None) == -1
     assert lib.vtc_cam_attn_core(None, 6, 4, 512, 8, None, None) == -1
     assert lib.vtc_launch_count() == before

@@ -108,11 +108,12 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
                   const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
                   int precision, const double* gt_score, double* gt_score_out, int accumulate,
                   int32_t* rank0, void* wsp, size_t ws_bytes, cudaStream_t s) {
-  if (!Q || !G || !rank0 || N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) ||
-      !valid_metric(metric) || !valid_prec(precision))
+  if (N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) || !valid_metric(metric) ||
+      !valid_prec(precision))
     return VTC_ERR_INVALID_ARG;
+  if (N == 0) return VTC_OK;  // no queries: nothing to rank (pointers may be NULL)
+  if (!Q || (!G && M > 0) || !rank0) return VTC_ERR_INVALID_ARG;
   if (N > kMaxRows || M > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
-  if (N == 0) return VTC_OK;
   Workspace ws(wsp, ws_bytes);
   RankWs w = carve_rank(ws, N, M, D, dtype, precision, false);
   if (!ws.ok() || !w.sq64 || !w.dgt || !w.scalars) return VTC_ERR_WORKSPACE;
@@ -218,11 +219,12 @@ TopkWs carve_topk(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
 int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype, int metric,
                   int precision, int k, int64_t col_offset, float* out_val, int64_t* out_idx,
                   void* wsp, size_t ws_bytes, cudaStream_t s) {
-  if (!Q || !G || !out_val || !out_idx || N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) ||
-      !valid_metric(metric) || !valid_prec(precision) || k < 1)
+  if (N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) || !valid_metric(metric) ||
+      !valid_prec(precision) || k < 1)
     return VTC_ERR_INVALID_ARG;
+  if (N == 0) return VTC_OK;  // no queries: nothing to search (pointers may be NULL)
+  if (!Q || (!G && M > 0) || !out_val || !out_idx) return VTC_ERR_INVALID_ARG;
   if (k > 16 || N > kMaxRows || M > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
-  if (N == 0) return VTC_OK;
   Workspace ws(wsp, ws_bytes);
   TopkWs w = carve_topk(ws, N, M, D, dtype, precision);
   if (!ws.ok()) return VTC_ERR_WORKSPACE;
