@@ -92,22 +92,30 @@ topk_select_kernel(TopkSelectArgs a) {
   const T* Q = (const T*)a.ex.Q;
   const T* G = (const T*)a.ex.G;
   const T* q = Q + t * a.ex.ldq;
-  const int ncand = a.splits * a.pool;
-  // 1. gather the pooled candidates (approximate score, column)
-  for (int c = lane; c < ncand; c += 32) {
-    const int s = c / a.pool, i = c % a.pool;
-    const int64_t slot = (int64_t)s * a.ex.N + t;
-    const int fill = (int)a.pool_meta[slot].x;
+  // 1. gather the pooled candidates (approximate score, column), dropping the empty slots
+  const int nslots = a.splits * a.pool;
+  int ncand = 0;
+  for (int c0 = 0; c0 < nslots; c0 += 32) {
+    const int c = c0 + lane;
     int j = -1;
     float ap = INFINITY;
-    if (i < fill) {
-      const float2 e = a.pool_buf[slot * a.pool + i];
-      j = __float_as_int(e.y);
-      ap = e.x;
-      if (j < 0 || j >= a.ex.M || ap != ap) j = -1;
+    if (c < nslots) {
+      const int s = c / a.pool, i = c % a.pool;
+      const int64_t slot = (int64_t)s * a.ex.N + t;
+      if (i < (int)a.pool_meta[slot].x) {
+        const float2 e = a.pool_buf[slot * a.pool + i];
+        j = __float_as_int(e.y);
+        ap = e.x;
+        if (j < 0 || j >= a.ex.M || ap != ap) j = -1;
+      }
     }
-    ca[w][c] = ap;
-    cj[w][c] = j;
+    const unsigned m = __ballot_sync(0xffffffffu, j >= 0);
+    if (j >= 0) {
+      const int o = ncand + __popc(m & ((1u << lane) - 1u));
+      ca[w][o] = ap;
+      cj[w][o] = j;
+    }
+    ncand += __popc(m);
   }
   __syncwarp();
   const double qq = sq_seq64(q, a.ex.D);  // every lane computes it (keeps the warp convergent)
@@ -125,7 +133,6 @@ topk_select_kernel(TopkSelectArgs a) {
     float bv = INFINITY;
     int bc = 0x7fffffff;
     for (int c = lane; c < ncand; c += 32) {
-      if (cj[w][c] < 0) continue;
       const float x = ca[w][c];
       const bool above = x > last_v || (x == last_v && c > last_c);
       if (above && (x < bv || (x == bv && c < bc))) bv = x, bc = c;
@@ -142,17 +149,26 @@ topk_select_kernel(TopkSelectArgs a) {
   }
   // every member of the exact top-k has approximate score <= a_k + 2 delta
   const double thr = have == a.k ? (double)last_v + 2.0 * delta : INFINITY;
-  // 3. exact re-scoring of the candidates that can still be in the top-k
-  for (int c = lane; c < ncand; c += 32) {
+  // 3. compact the candidates that can still be in the top-k to the front of the list (in place:
+  // a pass only writes slots it or an earlier pass has already read), so that the fp64 re-scoring
+  // below runs with full warps instead of once per 32-slot stripe with a few live lanes
+  int nsurv = 0;
+  for (int c0 = 0; c0 < ncand; c0 += 32) {
+    const int c = c0 + lane;
+    const int j = c < ncand ? cj[w][c] : -1;
+    const bool keep = j >= 0 && (double)ca[w][c] <= thr;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) cj[w][nsurv + __popc(m & ((1u << lane) - 1u))] = j;
+    nsurv += __popc(m);
+    __syncwarp();
+  }
+  // exact re-scoring, one survivor per lane
+  for (int c = lane; c < nsurv; c += 32) {
     int j = cj[w][c];
-    double d = 0.0;
-    if (j >= 0 && (double)ca[w][c] <= thr) {
-      d = exact_score(q, G + (int64_t)j * a.ex.ldg, a.ex.D, a.ex.metric,
-                      a.ex.metric == VTC_METRIC_L2 ? a.ex.sq64[j] : 0.0);
-      if (d != d) j = -1;  // NaN scores are never selected
-    } else {
-      j = -1;
-    }
+    const double d = exact_score(q, G + (int64_t)j * a.ex.ldg, a.ex.D, a.ex.metric,
+                                 a.ex.metric == VTC_METRIC_L2 ? a.ex.sq64[j] : 0.0);
+    if (d != d) j = -1;  // NaN scores are never selected
     cd[w][c] = d;
     cj[w][c] = j;
   }
@@ -163,7 +179,7 @@ topk_select_kernel(TopkSelectArgs a) {
   for (int r = 0; r < a.k; ++r) {
     double bd = 0.0;
     int bj = -1, bc = -1;
-    for (int c = lane; c < ncand; c += 32) {
+    for (int c = lane; c < nsurv; c += 32) {
       if (cand_less(cd[w][c], cj[w][c], bd, bj)) bd = cd[w][c], bj = cj[w][c], bc = c;
     }
 #pragma unroll
@@ -214,18 +230,29 @@ topk_tau_kernel(TopkSelectArgs a, float* __restrict__ tau0) {
   const int64_t t = (int64_t)blockIdx.x * SEL_WARPS + w;
   if (t >= a.ex.N) return;
   const T* q = (const T*)a.ex.Q + t * a.ex.ldq;
-  const int ncand = a.splits * a.pool;
+  __shared__ float ca[SEL_WARPS][SEL_MAX_CAND];
+  const int nslots = a.splits * a.pool;
+  int ncand = 0;
+  for (int c0 = 0; c0 < nslots; c0 += 32) {  // one pass over the pools, empty slots dropped
+    const int c = c0 + lane;
+    float x = NAN;
+    if (c < nslots) {
+      const int s = c / a.pool, i = c % a.pool;
+      const int64_t slot = (int64_t)s * a.ex.N + t;
+      if (i < (int)a.pool_meta[slot].x) x = a.pool_buf[slot * a.pool + i].x;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, x == x);
+    if (x == x) ca[w][ncand + __popc(m & ((1u << lane) - 1u))] = x;
+    ncand += __popc(m);
+  }
+  __syncwarp();
   float last_v = -INFINITY;
   int last_c = -1, have = 0;
   for (int r = 0; r < a.k; ++r) {
     float bv = INFINITY;
     int bc = 0x7fffffff;
     for (int c = lane; c < ncand; c += 32) {
-      const int s = c / a.pool, i = c % a.pool;
-      const int64_t slot = (int64_t)s * a.ex.N + t;
-      if (i >= (int)a.pool_meta[slot].x) continue;
-      const float x = a.pool_buf[slot * a.pool + i].x;
-      if (x != x) continue;
+      const float x = ca[w][c];
       const bool above = x > last_v || (x == last_v && c > last_c);
       if (above && (x < bv || (x == bv && c < bc))) bv = x, bc = c;
     }
