@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "exact", "brute"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="N > 1: launch the sharded step kernel by kernel instead of as a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline time")
     return ap.parse_args()
 
@@ -186,7 +188,7 @@ def run_ours(a):
 
     from vtc_b200 import _ffi, ops
     from vtc_b200.model.metric import RecallAtK
-    from vtc_b200.parallel import shard_bounds, sharded_rank_eval
+    from vtc_b200.parallel import GraphedRankEval, shard_bounds, sharded_rank_eval
     from vtc_b200.synthetic import make_retrieval_pair
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,12 +210,24 @@ def run_ours(a):
     q_local = T[qs:qe].contiguous().to(dev)
     g_local = V[gs:ge].contiguous().to(dev)
 
+    # N > 1: ~1 ms of GPU work per rank behind ~40 launches and 3 collectives is launch-bound from
+    # Python, so the whole sharded step is captured once and replayed as one CUDA graph
+    graphed = None
+    if world > 1 and not a.no_graph and not os.environ.get("VTC_PHASE_TIMING"):
+        graphed = GraphedRankEval(q_local, g_local, a.n, a.m, k_vals, "l2", a.precision)
+
+    def eager_step():
+        return sharded_rank_eval(q_local, g_local, a.n, a.m, k_vals, "l2", a.precision)
+
     def step():
         if world == 1:
             rank0, gts = ops.sim_rank(q_local, g_local, metric="l2", precision=a.precision)
             hits, medr = ops.rank_finalize(rank0, gts, a.m, k_vals)
             return hits, medr
-        res = sharded_rank_eval(q_local, g_local, a.n, a.m, k_vals, "l2", a.precision)
+        if graphed is not None:
+            res = graphed()
+            return res["hits"], res["medr"]
+        res = eager_step()
         if res.get("phases_ms") and rank == 0:
             print("phases_ms", json.dumps(res["phases_ms"]), file=sys.stderr)
         return res["hits"], res["medr"]
@@ -235,12 +249,24 @@ def run_ours(a):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    t_host = time.perf_counter()
     for _ in range(a.steps):
         hits, medr = step()
+    host_ms_per_step = (time.perf_counter() - t_host) / a.steps * 1e3  # CPU time to enqueue a step
     ev1.record()
     barrier()
     launches = _ffi.launch_count() - launches0
     tc_ms, tc_n = _ffi.kernel_timer_read()
+    tc_steps = a.steps
+    if graphed is not None:
+        # a replayed graph has no per-kernel events: count the captured launches, and time the
+        # dominant kernel on a few eager steps OUTSIDE the timed region (roofline only)
+        launches = graphed.launches_per_replay * a.steps
+        tc_steps = 3
+        for _ in range(tc_steps):
+            eager_step()
+        torch.cuda.synchronize()
+        tc_ms, tc_n = _ffi.kernel_timer_read()
     _ffi.kernel_timer_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -313,7 +339,7 @@ def run_ours(a):
         k_eff = a.d if a.precision == "bf16" else 3 * a.d
         n_rows = qe - qs
         flops_alg = 2.0 * n_rows * a.m * a.d            # algorithmic FLOPs of this rank's launches
-        launches_per_step = tc_n / a.steps
+        launches_per_step = tc_n / tc_steps
         ms_per_launch = tc_ms / tc_n
         achieved = flops_alg / launches_per_step / (ms_per_launch * 1e-3) / 1e12
         traffic = None
@@ -326,7 +352,7 @@ def run_ours(a):
                     "frac_vs_sustained": (achieved / peaks["bf16_tflops_sustained"]
                                           if peaks.get("bf16_tflops_sustained") else None),
                     "ms_per_launch": ms_per_launch, "launches_per_step": launches_per_step,
-                    "kernel_share_of_step": tc_ms / a.steps / ms_per_step,
+                    "kernel_share_of_step": tc_ms / tc_steps / ms_per_step,
                     "issued_tflops": achieved * k_eff / a.d,
                     "note": "achieved = algorithmic 2*N*M*D per launch / CUDA-event launch time; "
                             "the exact mode issues 3x the MMAs (bf16x3 split), see issued_tflops"}
@@ -346,9 +372,11 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "N": a.n, "M": a.m, "D": a.d,
                    "precision": a.precision, "metric": "l2", "k_vals": k_vals,
                    "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                   "cuda_graph": graphed is not None,
                    "l2_flush": "not needed: inputs + operands (>= 600 MB) exceed the 126 MB L2"},
         "hits": [int(x) for x in hits.cpu().tolist()], "medr": float(medr.cpu()[0]),
-        "e2e": e2e, "gpu_launches": int(tl.item()), "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(tl.item()), "host_enqueue_ms_per_step": host_ms_per_step,
+        "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

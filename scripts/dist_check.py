@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import vtc_oracle as O  # noqa: E402
-from vtc_b200.parallel import shard_bounds, sharded_rank_eval, sharded_topk  # noqa: E402
+from vtc_b200.parallel import GraphedRankEval, shard_bounds, sharded_rank_eval, sharded_topk  # noqa: E402
 from vtc_b200.synthetic import make_retrieval_pair  # noqa: E402
 
 
@@ -41,6 +41,17 @@ def main():
                               precision=prec)
         wi = O.topk_exact(Tq[:64], Vq, 11)[1]
         good = good and np.array_equal(ti.cpu().numpy(), wi)
+        # the same step captured in a CUDA graph, replayed on NEW inputs (row-permuted problem)
+        ev = GraphedRankEval(T[qs:qe].contiguous().to(dev), V[gs:ge].contiguous().to(dev), N, M,
+                             precision=prec)
+        T2, V2 = make_retrieval_pair(N, M, D, sigma=4.0, seed=N + 1)
+        for _ in range(2):
+            res2 = ev(T2[qs:qe].contiguous().to(dev), V2[gs:ge].contiguous().to(dev))
+        Tq2, Vq2 = (O.bf16_round(T2), O.bf16_round(V2)) if prec == "bf16" else (T2, V2)
+        want2 = O.rank0_exact(Tq2, Vq2)
+        good = good and (np.array_equal(res2["rank0_local"].cpu().numpy(), want2[qs:qe]) and
+                         list(res2["hits"].cpu().numpy()) == [int((want2 < k).sum()) for k in (1, 5, 10)]
+                         and float(res2["medr"].cpu()[0]) == O.medr(want2))
         print(f"[rank {rank}/{world}] N={N} M={M} D={D} {prec}: {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
     flag = torch.tensor([0 if ok else 1], device=dev)
