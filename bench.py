@@ -320,9 +320,11 @@ def run_ours(a):
                "d2h_bytes_per_step": 8 * len(k_vals) * world, "ms_per_step": dt.item() * 1e3,
                "api": "vtc_b200.parallel.sharded_rank_eval(pinned fp32 host shards)"}
 
+    if graphed is not None:
+        graphed.close()  # NCCL will not tear a communicator down under a live captured graph
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _teardown(dist)
         return
 
     # ---- roofline of the dominant kernel (the tcgen05 similarity + rank kernel)
@@ -381,7 +383,17 @@ def run_ours(a):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _teardown(dist)
+
+
+def _teardown(dist):
+    """destroy_process_group with a bounded wait: the measurement is already printed, a stuck
+    communicator teardown must not hold the launcher."""
+    t = threading.Timer(30.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
 
 
 def main():

@@ -52,6 +52,7 @@ def main():
         good = good and (np.array_equal(res2["rank0_local"].cpu().numpy(), want2[qs:qe]) and
                          list(res2["hits"].cpu().numpy()) == [int((want2 < k).sum()) for k in (1, 5, 10)]
                          and float(res2["medr"].cpu()[0]) == O.medr(want2))
+        ev.close()
         print(f"[rank {rank}/{world}] N={N} M={M} D={D} {prec}: {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
     flag = torch.tensor([0 if ok else 1], device=dev)
@@ -61,4 +62,15 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import faulthandler
+    import traceback
+
+    faulthandler.dump_traceback_later(int(os.environ.get("VTC_DIST_CHECK_TIMEOUT", "240")), exit=True)
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)  # a failed rank must not wait in the NCCL destructors for its peers

@@ -210,7 +210,8 @@ class GraphedRankEval:
     and median -- becomes a single graph launch.  Inputs live in static buffers: pass new shards
     to __call__ to have them copied in (device-to-device) before the replay.
 
-    All ranks must construct and call it collectively."""
+    All ranks must construct and call it collectively, and close() it before the process group is
+    destroyed."""
 
     def __init__(self, q_local: torch.Tensor, g_local: torch.Tensor, N_total: int, M_total: int,
                  k_vals: Sequence[int] = (1, 5, 10), metric: str = "l2", precision: str = "exact",
@@ -250,6 +251,16 @@ class GraphedRankEval:
             self.g.copy_(g_local, non_blocking=True)
         self.graph.replay()
         return self.out
+
+    def close(self) -> None:
+        """Destroy the graph.  NCCL keeps a communicator alive while a captured graph still refers
+        to it, so call this before dist.destroy_process_group() (which otherwise waits forever)."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.q.device)
+            self.graph.reset()
+            self.graph = None
+        self.out = None
+        self._held = []
 
 
 def _gt_all_local(qs: int, qe: int, g_start: int, g_size: int) -> bool:
