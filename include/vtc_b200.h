@@ -221,9 +221,10 @@ int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D
  * _adapt_feature).  Dense products of the backward are vtc_linear on transposed copies
  * (dX = dY W = linear(dY, W^T), dW = dY^T X = linear(dY^T, X^T)); the rest is here.
  * vtc_layernorm_bwd: dX = LN'(dY) + dres (dres nullable), dgamma / dbeta [D] overwritten.
- * vtc_cam_readout_bwd: residual activation NONE only; AVG writes dT [L,b,D], RESIDUAL_ONLY writes
- * dres [b,D]; dmain [b,D] is the part through normalize(main) at model.py:203; UNIFORM (averaging
- * fusion) writes dT only.
+ * vtc_cam_readout_bwd: same residual-activation arguments as vtc_cam_readout (the Jacobians of
+ * model/model.py:30-77; AFFINE = sub_mean / bn on running statistics, whose own parameters get no
+ * gradient here); AVG writes dT [L,b,D], RESIDUAL_ONLY writes dres [b,D]; dmain [b,D] is the part
+ * through normalize(main) at model.py:203; UNIFORM (averaging fusion) writes dT only.
  * vtc_cam_stack_normalize_bwd: dX [L,b,D] -> dmain [b,D] (token 0), daux [L-1,b,D]. */
 int vtc_normalize_bwd(const float* X, const float* dY, int64_t rows, int D, float* dX,
                       vtc_stream_t stream); /* dX of Y = X / |X| (model/model.py:26-27) */
@@ -239,7 +240,9 @@ int vtc_cam_stack_normalize_bwd(const float* main, const float* aux, const float
                                 int64_t b, int D, float* dmain, float* daux, vtc_stream_t stream);
 int vtc_cam_readout_bwd(const float* T, const float* main, const float* res_in,
                         const uint8_t* skip_mask, const float* dout, int L, int64_t b, int D,
-                        int mode, float* dT, float* dres, float* dmain, vtc_stream_t stream);
+                        int mode, int res_act, float res_scale, const float* res_shift,
+                        const float* res_mul, float* dT, float* dres, float* dmain,
+                        vtc_stream_t stream);
 
 /* number of kernels this library has launched since load (for bench.py's gpu_launches). */
 uint64_t vtc_launch_count(void);

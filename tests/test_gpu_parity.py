@@ -296,6 +296,31 @@ def test_recall_at_k_and_compute_recall_golden(cuda_dev, golden):
         np.testing.assert_array_equal(np.array([r for _, r in got]) * 100.0, g[key][:, 1])
 
 
+def test_eval_consumer_six_keys(cuda_dev, tmp_path):
+    """evaluation/eval.py:97-138: a loader of (vis, title, comments, meta) batches through a model,
+    features kept on the device, six floats keyed R{k}_{title_from_im,im_from_title}."""
+    import json
+
+    from vtc_b200.evaluation.eval import evaluate, recall_summary
+
+    T, V = make_retrieval_pair(700, 700, 128, sigma=5.0, seed=3)
+    batches = [(V[s:s + 96].unsqueeze(1), T[s:s + 96].unsqueeze(1), torch.zeros(min(96, 700 - s), 1),
+                {"id": torch.arange(s, min(s + 96, 700))}) for s in range(0, 700, 96)]
+
+    def model(vis, title, comments):  # stands in for the CLIP encoders: features pass through
+        return vis, title, None
+
+    out = evaluate(model, batches, cuda_dev, save_path=str(tmp_path / "r.json"))
+    want_ti = O.recall_at_k(V.numpy(), T.numpy(), [1, 5, 10])   # gallery = images, queries = titles
+    want_it = O.recall_at_k(T.numpy(), V.numpy(), [1, 5, 10])
+    assert list(out) == ["R1_title_from_im", "R5_title_from_im", "R10_title_from_im",
+                         "R1_im_from_title", "R5_im_from_title", "R10_im_from_title"]
+    assert [out[f"R{k}_title_from_im"] for k in (1, 5, 10)] == [r for _, r in want_ti]
+    assert [out[f"R{k}_im_from_title"] for k in (1, 5, 10)] == [r for _, r in want_it]
+    assert json.load(open(tmp_path / "r.json")) == out
+    assert recall_summary(V.numpy(), T.numpy()) == out          # numpy in, like the reference
+
+
 def test_recall_pipelined_host_staging(cuda_dev):
     """Large host inputs are staged chunk by chunk on a copy stream (H2D overlaps ranking); the
     result must not depend on the chunking."""
@@ -566,7 +591,7 @@ def test_cam_backward_matches_autograd_oracle(cuda_dev, avg):
     from vtc_b200.model.model import _CamAdaptFunction, _layer_params
 
     plist = [p for blk in m.final_transformer.resblocks for p in _layer_params(blk)]
-    cfg = (layers, heads, avg, "exact")
+    cfg = (layers, heads, avg, "exact", None)
     out = _CamAdaptFunction.apply(mg, ag, skip.to(cuda_dev), cfg, None if avg else m.final_linear.weight,
                                   *plist)
     np.testing.assert_allclose(_np(out), out_o.detach().numpy(), rtol=2e-4, atol=2e-5)
@@ -588,6 +613,57 @@ def test_cam_backward_matches_autograd_oracle(cuda_dev, avg):
     m.zero_grad()
     out2 = m._adapt_feature(mg, ag)
     assert out2.requires_grad
+
+
+@pytest.mark.parametrize("act,avg", [("normalize", True), ("squash", False), ("squash10", True),
+                                     ("tanh", False), ("tanh", True), ("sub_mean", True), ("bn", False)])
+def test_cam_backward_residual_activations(cuda_dev, act, avg):
+    """SURVEY.md §8f row 4, training side: the Jacobians of the residual-activation table
+    (model/model.py:30-77; sub_mean / bn on running statistics = frozen-finaltf form) inside
+    vtc_cam_readout_bwd, against torch autograd through the oracle."""
+    from vtc_b200.model import PretrainedCLIP_finaltf
+
+    b, nc, D, layers, heads = 16, 3, 64, 1, 2
+    params = O.make_cam_params(D, layers, heads, seed=13, rerandomise=True)
+    g = torch.Generator().manual_seed(4)
+    flw = torch.randn(D, D, generator=g) / D ** 0.5
+    run_mean, run_var = 0.05 * torch.randn(D, generator=g), 0.5 + torch.rand(D, generator=g)
+    main, aux = make_cam_inputs(b, nc, D, seed=2)
+    w = torch.randn(b, D, generator=g)
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    mo, ao, fo = main.clone().requires_grad_(True), aux.clone().requires_grad_(True), flw.clone().requires_grad_(True)
+    out_o = O.adapt_feature(mo, ao, po, layers, heads, init_from_avg=avg, final_linear_weight=fo,
+                            residual_activation=act, bn_state=(run_mean, run_var, 1e-5))
+    (out_o * w).sum().backward()
+
+    m = PretrainedCLIP_finaltf(D, n_layers=layers, n_heads=heads, init_from_avg=avg,
+                               residual_activation=act)
+    if act in ("sub_mean", "bn"):
+        m.branch_to_freeze = "finaltf"  # what _freeze("finaltf") records (model/model.py:268-269)
+    m.final_transformer.load_state_dict(params, strict=True)
+    with torch.no_grad():
+        m.final_linear.weight.copy_(flw)
+        if act in ("sub_mean", "bn"):
+            m.mean_center_bn.running_mean.copy_(run_mean)
+            m.mean_center_bn.running_var.copy_(run_var)
+    m = m.to(cuda_dev).train()
+    m.random_skip_adapter = False
+    mg, ag = main.to(cuda_dev).requires_grad_(True), aux.to(cuda_dev).requires_grad_(True)
+    out = m._adapt_feature(mg, ag)
+    np.testing.assert_allclose(_np(out), out_o.detach().numpy(), rtol=2e-4, atol=2e-5)
+    (out * w.to(cuda_dev)).sum().backward()
+
+    def close(got, want, name):
+        want = want.numpy()
+        err = np.abs(_np(got) - want).max() / (np.abs(want).max() + 1e-12)
+        assert err < 3e-3, f"{name}: max err / max |grad| = {err:.3e}"
+
+    close(mg.grad, mo.grad, "dmain")
+    close(ag.grad, ao.grad, "daux")
+    for n_, p in m.final_transformer.named_parameters():
+        close(p.grad, po[n_].grad, n_)
+    if not avg:
+        close(m.final_linear.weight.grad, fo.grad, "final_linear.weight")
 
 
 def test_training_step_gradients_through_the_model(cuda_dev):

@@ -80,7 +80,8 @@ SIGNATURES.update({
     "vtc_layernorm_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P, _P, _P, _P]),
     "vtc_cam_attn_core_bwd": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P, _P]),
     "vtc_cam_stack_normalize_bwd": (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P, _P]),
-    "vtc_cam_readout_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P]),
+    "vtc_cam_readout_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, c_float,
+                                    _P, _P, _P, _P, _P, _P]),
 })
 
 

@@ -263,15 +263,17 @@ __global__ void __launch_bounds__(256)
 cam_readout_bwd_kernel(const float* __restrict__ T, const float* __restrict__ main,
                        const float* __restrict__ res_in, const uint8_t* __restrict__ skip_mask,
                        const float* __restrict__ dout, int L, int64_t b, int D, int mode,
-                       float* __restrict__ dT, float* __restrict__ dres,
-                       float* __restrict__ dmain) {
-  extern __shared__ float smem[];  // per warp: r[D], z[D], dz[D]
+                       int res_act, float res_scale, const float* __restrict__ res_shift,
+                       const float* __restrict__ res_mul, float* __restrict__ dT,
+                       float* __restrict__ dres, float* __restrict__ dmain) {
+  extern __shared__ float smem[];  // per warp: r[D], z[D], dz[D], act aux[D]
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t bi = (int64_t)blockIdx.x * BW + wi;
   if (bi >= b) return;
-  float* rv = smem + (size_t)wi * 3 * D;
+  float* rv = smem + (size_t)wi * 4 * D;
   float* zv = rv + D;
   float* dz = zv + D;
+  float* av = dz + D;
   const bool skipped = skip_mask && skip_mask[bi];
   float mnorm = 1.f;
   // forward recompute: r
@@ -294,6 +296,28 @@ cam_readout_bwd_kernel(const float* __restrict__ T, const float* __restrict__ ma
   } else {
     for (int k = lane; k < D; k += 32) rv[k] = res_in[bi * D + k];
   }
+  // residual activation a = act(r) (model/model.py:30-77), kept in dz[] until dz is formed;
+  // av keeps what the activation's Jacobian needs: s = r + eps (normalize_eps / squash), a (tanh)
+  float act_mag = 1.f;
+  if (res_act == VTC_RESACT_NORMALIZE_EPS || res_act == VTC_RESACT_SQUASH) {
+    float q = 0.f;
+    for (int k = lane; k < D; k += 32) {
+      av[k] = rv[k] + 1e-9f;
+      q = fmaf(av[k], av[k], q);
+    }
+    const float mag_sq = warp_sum(q);
+    act_mag = sqrtf(mag_sq);
+    const float f = res_act == VTC_RESACT_NORMALIZE_EPS
+                        ? 1.f / act_mag
+                        : res_scale * (mag_sq / (1.f + mag_sq)) / act_mag;
+    for (int k = lane; k < D; k += 32) dz[k] = av[k] * f;
+  } else if (res_act == VTC_RESACT_TANH) {
+    for (int k = lane; k < D; k += 32) dz[k] = av[k] = tanhf(rv[k]);
+  } else if (res_act == VTC_RESACT_AFFINE) {
+    for (int k = lane; k < D; k += 32) dz[k] = (rv[k] - res_shift[k]) * (res_mul ? res_mul[k] : 1.f);
+  } else {
+    for (int k = lane; k < D; k += 32) dz[k] = rv[k];
+  }
   // u, z, out
   const float* mp = main + bi * D;
   float s = 0.f;
@@ -301,7 +325,7 @@ cam_readout_bwd_kernel(const float* __restrict__ T, const float* __restrict__ ma
   const float un = sqrtf(warp_sum(s));
   float zs = 0.f;
   for (int k = lane; k < D; k += 32) {
-    zv[k] = mp[k] / un + (skipped ? 0.f : rv[k]);
+    zv[k] = mp[k] / un + (skipped ? 0.f : dz[k]);
     zs = fmaf(zv[k], zv[k], zs);
   }
   const float zn = sqrtf(warp_sum(zs));
@@ -317,6 +341,29 @@ cam_readout_bwd_kernel(const float* __restrict__ T, const float* __restrict__ ma
   for (int k = lane; k < D; k += 32) cu = fmaf(mp[k] / un, dz[k], cu);
   cu = warp_sum(cu);
   for (int k = lane; k < D; k += 32) dmain[bi * D + k] = (dz[k] - (mp[k] / un) * cu) / un;
+  // d r = J_act(r)^T d a   (d a = dz)
+  if (res_act == VTC_RESACT_NORMALIZE_EPS) {
+    // a = s/|s|:  ds = (da - a (a . da)) / |s|
+    float c1 = 0.f;
+    for (int k = lane; k < D; k += 32) c1 = fmaf(av[k] / act_mag, dz[k], c1);
+    c1 = warp_sum(c1);
+    for (int k = lane; k < D; k += 32) dz[k] = (dz[k] - (av[k] / act_mag) * c1) / act_mag;
+  } else if (res_act == VTC_RESACT_SQUASH) {
+    // a = c f(m) s, f(m) = m / (1 + m^2):  ds = c (f da + f'(m)/m s (s . da)), f' = (1-m^2)/(1+m^2)^2
+    float c1 = 0.f;
+    for (int k = lane; k < D; k += 32) c1 = fmaf(av[k], dz[k], c1);
+    c1 = warp_sum(c1);
+    const float m2 = act_mag * act_mag, den = 1.f + m2;
+    const float f = act_mag / den, fp = (1.f - m2) / (den * den);
+    for (int k = lane; k < D; k += 32)
+      dz[k] = res_scale * (f * dz[k] + (fp / act_mag) * av[k] * c1);
+  } else if (res_act == VTC_RESACT_TANH) {
+    for (int k = lane; k < D; k += 32) dz[k] *= 1.f - av[k] * av[k];
+  } else if (res_act == VTC_RESACT_AFFINE) {
+    if (res_mul)
+      for (int k = lane; k < D; k += 32) dz[k] *= res_mul[k];
+  }
+  __syncwarp();
   // dr = dz (0 if skipped)
   if (mode != VTC_CAM_READOUT_AVG) {
     for (int k = lane; k < D; k += 32) dres[bi * D + k] = skipped ? 0.f : dz[k];
@@ -413,7 +460,9 @@ int launch_normalize_bwd(const float* X, const float* dY, int64_t rows, int D, f
 
 int launch_cam_readout_bwd(const float* T, const float* main, const float* res_in,
                            const uint8_t* skip_mask, const float* dout, int L, int64_t b, int D,
-                           int mode, float* dT, float* dres, float* dmain, cudaStream_t s) {
+                           int mode, int res_act, float res_scale, const float* res_shift,
+                           const float* res_mul, float* dT, float* dres, float* dmain,
+                           cudaStream_t s) {
   if (b == 0) return VTC_OK;
   if (D > 1024) return VTC_ERR_UNSUPPORTED_SHAPE;
   if (mode == VTC_CAM_READOUT_UNIFORM) {
@@ -421,14 +470,15 @@ int launch_cam_readout_bwd(const float* T, const float* main, const float* res_i
     VTC_LAUNCH_CHECK();
     return VTC_OK;
   }
-  const size_t smem = (size_t)BW * 3 * D * sizeof(float);
+  const size_t smem = (size_t)BW * 4 * D * sizeof(float);
   auto* kern = &cam_readout_bwd_kernel;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_err(e);
   }
   kern<<<(unsigned)ceil_div<int64_t>(b, BW), 256, smem, s>>>(T, main, res_in, skip_mask, dout, L, b, D,
-                                                            mode, dT, dres, dmain);
+                                                            mode, res_act, res_scale, res_shift,
+                                                            res_mul, dT, dres, dmain);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }
@@ -475,17 +525,23 @@ int vtc_normalize_bwd(const float* X, const float* dY, int64_t rows, int D, floa
 }
 int vtc_cam_readout_bwd(const float* T, const float* main, const float* res_in,
                         const uint8_t* skip_mask, const float* dout, int L, int64_t b, int D,
-                        int mode, float* dT, float* dres, float* dmain, vtc_stream_t stream) {
+                        int mode, int res_act, float res_scale, const float* res_shift,
+                        const float* res_mul, float* dT, float* dres, float* dmain,
+                        vtc_stream_t stream) {
   if (mode == VTC_CAM_READOUT_UNIFORM) {
     if (!T || !dout || !dT || b < 0 || D <= 0 || L < 1) return VTC_ERR_INVALID_ARG;
-    return launch_cam_readout_bwd(T, nullptr, nullptr, nullptr, dout, L, b, D, mode, dT, nullptr,
-                                  nullptr, (cudaStream_t)stream);
+    return launch_cam_readout_bwd(T, nullptr, nullptr, nullptr, dout, L, b, D, mode,
+                                  VTC_RESACT_NONE, 1.f, nullptr, nullptr, dT, nullptr, nullptr,
+                                  (cudaStream_t)stream);
   }
+  if (res_act < VTC_RESACT_NONE || res_act > VTC_RESACT_AFFINE ||
+      (res_act == VTC_RESACT_AFFINE && !res_shift))
+    return VTC_ERR_INVALID_ARG;
   if (!main || !dout || !dmain || b < 0 || D <= 0 || L < 1) return VTC_ERR_INVALID_ARG;
   if (mode == VTC_CAM_READOUT_AVG ? (!T || !dT) : (mode != VTC_CAM_READOUT_RESIDUAL_ONLY || !res_in || !dres))
     return VTC_ERR_INVALID_ARG;
-  return launch_cam_readout_bwd(T, main, res_in, skip_mask, dout, L, b, D, mode, dT, dres, dmain,
-                                (cudaStream_t)stream);
+  return launch_cam_readout_bwd(T, main, res_in, skip_mask, dout, L, b, D, mode, res_act, res_scale,
+                                res_shift, res_mul, dT, dres, dmain, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -196,7 +196,7 @@ class _CamAdaptFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, main, aux, skip_mask, cfg, flw, *params):
-        layers, heads, avg, prec = cfg
+        layers, heads, avg, prec, res_act = cfg
         main, aux = main.detach().float().contiguous(), aux.detach().float().contiguous()
         L, (b, D) = aux.shape[0] + 1, main.shape
         X = ops.cam_stack_normalize(main, aux).reshape(L * b, D)
@@ -217,11 +217,12 @@ class _CamAdaptFunction(torch.autograd.Function):
         T = X.reshape(L, b, D)
         res = None
         if avg:
-            out = ops.cam_readout(T, main, _ffi.CAM_READOUT_AVG, skip_mask=skip_mask)
+            out = ops.cam_readout(T, main, _ffi.CAM_READOUT_AVG, skip_mask=skip_mask,
+                                  res_act=res_act)
         else:
             res = ops.linear(T[0], flw.detach(), precision=prec)
             out = ops.cam_readout(None, main, _ffi.CAM_READOUT_RESIDUAL_ONLY, res_in=res,
-                                  skip_mask=skip_mask)
+                                  skip_mask=skip_mask, res_act=res_act)
         ctx.cfg = cfg
         ctx.skip_mask = skip_mask
         ctx.dims = (L, b, D)
@@ -233,7 +234,7 @@ class _CamAdaptFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        layers, heads, avg, prec = ctx.cfg
+        layers, heads, avg, prec, res_act = ctx.cfg
         L, b, D = ctx.dims
         sv = ctx.saved_tensors
         main, aux, T, res, flw = sv[:5]
@@ -244,10 +245,11 @@ class _CamAdaptFunction(torch.autograd.Function):
         dflw = None
         if avg:
             dT, _, dmain = ops.cam_readout_bwd(T, main, dout, _ffi.CAM_READOUT_AVG,
-                                               skip_mask=ctx.skip_mask)
+                                               skip_mask=ctx.skip_mask, res_act=res_act)
         else:
             _, dres, dmain = ops.cam_readout_bwd(None, main, dout, _ffi.CAM_READOUT_RESIDUAL_ONLY,
-                                                 res_in=res, skip_mask=ctx.skip_mask, L=L)
+                                                 res_in=res, skip_mask=ctx.skip_mask, L=L,
+                                                 res_act=res_act)
             dT = torch.zeros_like(T)
             dT[0] = lin(dres, tr(flw))                       # d token0 = dres @ W
             dflw = lin(tr(dres), tr(T[0].contiguous()))      # dW = dres^T @ token0
@@ -335,12 +337,10 @@ class PretrainedCLIPBase(nn.Module):
             or any(p.requires_grad for p in tfm.parameters())
             or (not self.init_from_avg and self.final_linear.weight.requires_grad))
         if needs_grad:
-            if res_act[0] != _ffi.RESACT_NONE:
-                raise NotImplementedError(
-                    f"residual_activation={self.residual_activation!r} has no backward yet; only "
-                    "None/'none' (what every shipped config uses) is differentiable")
             params = [p for blk in tfm.resblocks for p in _layer_params(blk)]
-            cfg = (len(tfm.resblocks), tfm.heads, bool(self.init_from_avg), self.precision)
+            act = None if res_act[0] == _ffi.RESACT_NONE else tuple(
+                t.detach() if isinstance(t, torch.Tensor) else t for t in res_act)
+            cfg = (len(tfm.resblocks), tfm.heads, bool(self.init_from_avg), self.precision, act)
             sm = None if skip_mask is None else skip_mask.to(feature_main.device)
             flw = None if self.init_from_avg else self.final_linear.weight
             return _CamAdaptFunction.apply(feature_main, features_aux, sm, cfg, flw, *params)

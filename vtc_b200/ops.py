@@ -563,8 +563,8 @@ def cam_stack_normalize_bwd(main: torch.Tensor, aux: torch.Tensor, dX: torch.Ten
 
 def cam_readout_bwd(T: Optional[torch.Tensor], main: torch.Tensor, dout: torch.Tensor, mode: int,
                     res_in: Optional[torch.Tensor] = None, skip_mask: Optional[torch.Tensor] = None,
-                    L: int = 1):
-    """-> (dT [L,b,D] or None, dres [b,D] or None, dmain [b,D])."""
+                    L: int = 1, res_act=None):
+    """-> (dT [L,b,D] or None, dres [b,D] or None, dmain [b,D]).  `res_act` as in cam_readout."""
     dev = _req_cuda(T, main, dout, res_in, skip_mask)
     dout = dout.float().contiguous()
     if mode == _ffi.CAM_READOUT_UNIFORM:
@@ -572,8 +572,8 @@ def cam_readout_bwd(T: Optional[torch.Tensor], main: torch.Tensor, dout: torch.T
         L, b, D = T.shape
         dT = torch.empty_like(T)
         with torch.cuda.device(dev):
-            _call("vtc_cam_readout_bwd", _ptr(T), None, None, None, _ptr(dout), L, b, D, mode, _ptr(dT),
-                  None, None, _stream(dev))
+            _call("vtc_cam_readout_bwd", _ptr(T), None, None, None, _ptr(dout), L, b, D, mode,
+                  _ffi.RESACT_NONE, 1.0, None, None, _ptr(dT), None, None, _stream(dev))
         return dT, None, None
     main = main.float().contiguous()
     b, D = main.shape
@@ -589,6 +589,8 @@ def cam_readout_bwd(T: Optional[torch.Tensor], main: torch.Tensor, dout: torch.T
         skip_mask = skip_mask.to(device=dev, dtype=torch.uint8).contiguous()
     dmain = torch.empty_like(main)
     with torch.cuda.device(dev):
+        act, scale, shift, mul = _res_act_args(res_act, dev)
         _call("vtc_cam_readout_bwd", _ptr(T), _ptr(main), _ptr(res_in), _ptr(skip_mask), _ptr(dout), L, b,
-              D, mode, _ptr(dT), _ptr(dres), _ptr(dmain), _stream(dev))
+              D, mode, act, scale, _ptr(shift), _ptr(mul), _ptr(dT), _ptr(dres), _ptr(dmain),
+              _stream(dev))
     return dT, dres, dmain
