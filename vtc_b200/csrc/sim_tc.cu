@@ -11,10 +11,10 @@
 namespace vtc {
 namespace tc {
 
-int launch_rank(bool a_resident, int cluster, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                const Params& p, int grid, cudaStream_t s);
-int launch_topk(bool a_resident, int cluster, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                const Params& p, int grid, cudaStream_t s);
+int launch_rank(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
+                const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
+int launch_topk(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
+                const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
 int launch_lse(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
                int grid, cudaStream_t s);
 int launch_store(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
@@ -81,9 +81,30 @@ int choose_cluster(int64_t N, int64_t M) {
   return want;
 }
 
+// A cluster of two can run as a CTA pair (tcgen05 cta_group::2, one M256 MMA issued by the leader):
+// each CTA stages and reads only ITS half of every gallery tile instead of receiving the full
+// tile by multicast and issuing its own M128 MMAs.  Measured on B200 (profiles/r01_summary.md):
+// +4.6 % on the streamed kernel (K' > 512: exact mode, D = 768), +4 % at K' <= 256, nothing on
+// the resident K' = 512 kernel, whose main loop already runs at the cuBLAS rate and is
+// power-limited by its epilogue.  VTC_PAIR=0/1 forces it off / on.
+static bool use_pair(int num_kb) {
+  static const int forced = []() {
+    const char* e = getenv("VTC_PAIR");
+    return e && *e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  if (forced >= 0) return forced != 0;
+  return num_kb > 8 || num_kb <= 4;
+}
+
 Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split) {
   Plan pl;
   pl.cluster = cluster < 1 ? 1 : cluster;
+  pl.pair = pl.cluster == 2 && use_pair(p.num_kb);
+  static const int skip_epi = []() {
+    const char* e = getenv("VTC_DBG_SKIP_EPILOGUE");
+    return e && *e ? atoi(e) : 0;
+  }();
+  p.dbg_skip_epilogue = skip_epi;
   p.q_tiles = (int)ceil_div<int64_t>(p.N, BM);
   p.g_tiles = (int)ceil_div<int64_t>(p.M, BN);
   const int units = pl.cluster > 1 ? active_clusters(pl.cluster) : kNumSMs;  // co-resident clusters
@@ -164,8 +185,8 @@ int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorM
   }
   int rc;
   switch (epilogue) {
-    case EPI_RANK: rc = launch_rank(a_resident, pl.cluster, tmA, tmB, p, pl.grid, s); break;
-    case EPI_TOPK: rc = launch_topk(a_resident, pl.cluster, tmA, tmB, p, pl.grid, s); break;
+    case EPI_RANK: rc = launch_rank(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
+    case EPI_TOPK: rc = launch_topk(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
     case EPI_LSE:
       rc = pl.cluster == 1 ? launch_lse(a_resident, tmA, tmB, p, pl.grid, s) : VTC_ERR_INVALID_ARG;
       break;

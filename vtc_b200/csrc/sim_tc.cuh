@@ -51,6 +51,7 @@ struct Params {
   float2* pool_meta;  // [2 * g_splits, N] (entries, tau): every column outside the pool scores >= tau
   int topk_keep;      // entries kept by a compaction (>= k, <= TOPK_KEEP_MAX)
   const float* tau_init;  // optional [N]: initial per-row threshold (from a sample pass); NULL = +inf
+  int dbg_skip_epilogue;  // profiling only (VTC_DBG_SKIP_EPILOGUE=1): drain TMEM but reduce nothing
 };
 
 // Row-major bf16 [rows, cols] with leading dimension ld (elements) -> 2-D TMA descriptor with a
@@ -64,6 +65,7 @@ int choose_cluster(int64_t N, int64_t M);
 struct Plan {
   int cluster;  // CTAs per cluster sharing each gallery tile
   int grid;     // CTAs to launch (multiple of cluster)
+  bool pair;    // cluster == 2 run as a CTA pair: one M256 cta_group::2 MMA instead of multicast
 };
 // fills q_tiles / g_tiles / g_splits / tiles_per_split for the given cluster size
 Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split = 8);

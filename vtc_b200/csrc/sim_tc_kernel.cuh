@@ -43,10 +43,13 @@ constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;      // two per scheduler: each TMEM lane quarter is split in two column halves
 constexpr int TMEM_COLS = 512;
 
-template <bool kRes>
+// kPair: the two CTAs of a cluster issue one M256 cta_group::2 MMA; each CTA stages only ITS half
+// of every gallery tile (16 KB), so the ring is twice as deep in the same shared memory.
+template <bool kRes, bool kPair = false>
 struct SmemLayout {
-  static constexpr int kStages = kRes ? 3 : 4;
-  static constexpr int kStageBytes = kRes ? B_TILE_BYTES : (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int kBBytes = kPair ? B_TILE_BYTES / 2 : B_TILE_BYTES;
+  static constexpr int kStages = kPair ? 6 : (kRes ? 3 : 4);
+  static constexpr int kStageBytes = kRes ? kBBytes : (A_TILE_BYTES + kBBytes);
   static constexpr int kResBytes = kRes ? MAX_RES_KB * A_TILE_BYTES : 0;
   static constexpr int kStagesOff = kResBytes;
   static constexpr int kBarOff = kStagesOff + kStages * kStageBytes;
@@ -394,11 +397,12 @@ struct TopkEpi {
 };
 
 // ------------------------------------------------------------------------------------- kernel
-template <typename Epi, bool kRes, int kC>
+template <typename Epi, bool kRes, int kC, bool kPair = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const Params p) {
-  using L = SmemLayout<kRes>;
+  static_assert(!kPair || kC == 2, "a CTA pair is a cluster of two");
+  using L = SmemLayout<kRes, kPair>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* res_a = smem;
   uint8_t* stages = smem + L::kStagesOff;
@@ -424,19 +428,26 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < L::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kC);  // one tcgen05.commit arrival from every CTA of the cluster
+      // one tcgen05.commit arrival from every MMA issuer of the cluster (a pair has one)
+      mbar_init(&empty[i], kPair ? 1 : kC);
     }
     for (int i = 0; i < MAX_RES_KB; ++i) mbar_init(&a_full[i], 1);
     mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], EPI_WARPS);  // one arrival per epilogue warp
+      // one arrival per epilogue warp; the leader of a pair collects both CTAs' warps
+      mbar_init(&tmem_empty[i], kPair ? 2 * EPI_WARPS : EPI_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -454,6 +465,9 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int num_items = q_groups * p.g_splits;
   const int num_kb = p.num_kb;
   constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
+  // CTA pair: rank 0 issues the MMAs and owns the `full` / `a_full` / `tmem_empty` barriers; both
+  // CTAs' TMA loads and epilogue warps signal ITS barriers (shared::cluster addresses)
+  const bool leader = !kPair || cta_rank == 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -466,6 +480,24 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (kRes) mbar_wait(a_empty, (it & 1) ^ 1);  // previous item's MMAs have drained
         for (int tile = t0; tile < t1; ++tile) {
           for (int kb = 0; kb < num_kb; ++kb) {
+            if (kPair) {
+              // each CTA loads its own query rows and its half of the gallery tile into its own
+              // shared memory; the bytes of both are expected on the leader's barrier
+              if (kRes && tile == t0) {
+                if (leader) mbar_arrive_expect_tx(&a_full[kb], 2 * A_TILE_BYTES);
+                tma_load_2d_pair(res_a + kb * A_TILE_BYTES, &tmA,
+                                 mapa_shared(smem_u32(&a_full[kb]), 0), kb * BK, qt * BM);
+              }
+              mbar_wait(&empty[stage], phase ^ 1);
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * L::kStageBytes);
+              const uint32_t fbar = mapa_shared(smem_u32(&full[stage]), 0);
+              uint8_t* st = stages + stage * L::kStageBytes;
+              if (!kRes) tma_load_2d_pair(st, &tmA, fbar, kb * BK, qt * BM);
+              tma_load_2d_pair(st + (kRes ? 0 : A_TILE_BYTES), &tmB, fbar, kb * BK,
+                               tile * BN + cta_rank * (BN / 2));
+              if (++stage == L::kStages) stage = 0, phase ^= 1;
+              continue;
+            }
             if (kRes && tile == t0) {
               mbar_arrive_expect_tx(&a_full[kb], A_TILE_BYTES);
               tma_load_2d(res_a + kb * A_TILE_BYTES, &tmA, &a_full[kb], kb * BK, qt * BM);
@@ -489,8 +521,8 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kPair ? 2 * BM : BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, it = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
         const int split = item / q_groups;
@@ -509,21 +541,37 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 make_smem_desc_sw128(smem_u32(kRes ? res_a + kb * A_TILE_BYTES : st));
             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(st + (kRes ? 0 : A_TILE_BYTES)));
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 16; ++k4)
-              umma_bf16(d_tmem, desc_advance(adesc, k4 * 32), desc_advance(bdesc, k4 * 32), idesc,
-                        (uint32_t)((kb | k4) != 0));
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              if (kPair)
+                umma_bf16_pair(d_tmem, desc_advance(adesc, k4 * 32), desc_advance(bdesc, k4 * 32),
+                               idesc, (uint32_t)((kb | k4) != 0));
+              else
+                umma_bf16(d_tmem, desc_advance(adesc, k4 * 32), desc_advance(bdesc, k4 * 32), idesc,
+                          (uint32_t)((kb | k4) != 0));
+            }
             // smem slot free (in every CTA of the cluster) once these MMAs retire
-            if (kC == 1)
+            if (kPair)
+              umma_commit_pair(&empty[stage], kMask);
+            else if (kC == 1)
               umma_commit(&empty[stage]);
             else
               umma_commit_multicast(&empty[stage], kMask);
             if (++stage == L::kStages) stage = 0, phase ^= 1;
           }
-          umma_commit(&tmem_full[as]);  // accumulator complete
+          // accumulator complete (in both CTAs of a pair)
+          if (kPair)
+            umma_commit_pair(&tmem_full[as], kMask);
+          else
+            umma_commit(&tmem_full[as]);
           as ^= 1;
           if (as == 0) aphase ^= 1;
         }
-        if (kRes) umma_commit(a_empty);
+        if (kRes) {
+          if (kPair)
+            umma_commit_pair(a_empty, kMask);
+          else
+            umma_commit(a_empty);
+        }
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -581,7 +629,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + nj) + lane);
           }
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-          epi.chunk(p, va, wbias, scale, j0 + c * 32, seg_count);
+          if (!p.dbg_skip_epilogue) epi.chunk(p, va, wbias, scale, j0 + c * 32, seg_count);
           tmem_ld_wait(vb);
           if (c + 2 < kHalfCols / 32) {
             tmem_ld_32x32(taddr + (c + 2) * 32, va);
@@ -590,9 +638,14 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) {
+              if (kPair)
+                mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+              else
+                mbar_arrive(&tmem_empty[as]);
+            }
           }
-          epi.chunk(p, vb, wbias + 32, scale, j0 + (c + 1) * 32, seg_count);
+          if (!p.dbg_skip_epilogue) epi.chunk(p, vb, wbias + 32, scale, j0 + (c + 1) * 32, seg_count);
           if (c + 2 < kHalfCols / 32) tmem_ld_wait(va);
         }
         as ^= 1;
@@ -608,18 +661,21 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (kC > 1) cluster_sync_all();  // no CTA leaves while peers may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (kPair)
+      tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 
 // ------------------------------------------------------------------------------ launch helper
 // Launches one instance with a thread-block-cluster dimension of kC (1 = plain launch).
-template <typename Epi, bool kRes, int kC>
+template <typename Epi, bool kRes, int kC, bool kPair = false>
 int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid,
                     cudaStream_t s) {
-  using L = SmemLayout<kRes>;
-  auto* kern = &sim_tc_kernel<Epi, kRes, kC>;
+  using L = SmemLayout<kRes, kPair>;
+  auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair>;
   // the attribute is per function and per device: cheap, so set it on every launch
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
   if (e != cudaSuccess) return cuda_err(e);
@@ -642,10 +698,10 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params
 }
 
 // how many clusters of kC CTAs of this kernel can be co-resident on the current device
-template <typename Epi, bool kRes, int kC>
+template <typename Epi, bool kRes, int kC, bool kPair = false>
 int max_active_clusters() {
-  using L = SmemLayout<kRes>;
-  auto* kern = &sim_tc_kernel<Epi, kRes, kC>;
+  using L = SmemLayout<kRes, kPair>;
+  auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess)
     return 0;
   cudaLaunchConfig_t cfg;
@@ -668,7 +724,10 @@ int max_active_clusters() {
 // dispatch over (resident, cluster) for one epilogue
 template <typename Epi>
 int launch_epilogue(bool a_resident, int cluster, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                    const Params& p, int grid, cudaStream_t s) {
+                    const Params& p, int grid, cudaStream_t s, bool pair = false) {
+  if (pair && cluster == 2)
+    return a_resident ? launch_instance<Epi, true, 2, true>(tmA, tmB, p, grid, s)
+                      : launch_instance<Epi, false, 2, true>(tmA, tmB, p, grid, s);
   if (a_resident) {
     if (cluster == 4) return launch_instance<Epi, true, 4>(tmA, tmB, p, grid, s);
     if (cluster == 2) return launch_instance<Epi, true, 2>(tmA, tmB, p, grid, s);

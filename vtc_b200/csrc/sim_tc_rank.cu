@@ -5,9 +5,9 @@
 namespace vtc {
 namespace tc {
 
-int launch_rank(bool a_resident, int cluster, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                 const Params& p, int grid, cudaStream_t s) {
-  return launch_epilogue<RankEpi>(a_resident, cluster, tmA, tmB, p, grid, s);
+int launch_rank(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
+                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s) {
+  return launch_epilogue<RankEpi>(a_resident, cluster, tmA, tmB, p, grid, s, pair);
 }
 
 int max_active_clusters_rank(int cluster) {

@@ -18,6 +18,7 @@ pinned host memory to the current CUDA device.  There is no CPU compute path.
 from __future__ import annotations
 
 import collections.abc
+import os
 import time
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -185,10 +186,17 @@ class RecallAtK(BaseMetric):
         hits, medr = ops.rank_finalize(rank0, gt_score, num_samples, self.k_vals)
         return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": num_samples}
 
-    # host inputs of at least this many bytes are staged in chunks on a copy stream so that the
-    # host->device transfer of query chunk i+1 overlaps the ranking of chunk i
+    # Host inputs of at least this many bytes are staged in chunks on a copy stream so that the
+    # host->device transfer overlaps the ranking.  When BOTH sides come from the host, gallery and
+    # queries are cut with the same bounds and copied interleaved (G0, Q0, G1, Q1, ...); when pair i
+    # lands, the new query rows are ranked against all gallery rows so far (gt(t) = t puts their
+    # ground truth among them) and the earlier query rows against the new gallery rows -- rank
+    # counts are additive over gallery chunks -- so the tensor cores start after 1/c of the
+    # transfer instead of after the whole gallery, with 2c - 1 library calls.
     PIPELINE_MIN_BYTES = 32 << 20
-    PIPELINE_CHUNKS = 4
+    PIPELINE_CHUNKS = 4      # query chunks against a device-resident gallery
+    # chunks per side when both sides are staged from the host
+    PIPELINE_CHUNKS_2D = int(os.environ.get("VTC_PIPELINE_CHUNKS_2D", "6"))
 
     def _compute_full_pipelined(self, features_a: ArrayLike, features_b: ArrayLike,
                                 device: torch.device) -> Dict[str, object]:
@@ -206,33 +214,68 @@ class RecallAtK(BaseMetric):
         hb = host(features_b)
         n = hb.shape[0]
         dtype = hb.dtype if (ha is None or ha.dtype == hb.dtype) else torch.float32
+        if a is not None and a.dtype != hb.dtype:
+            dtype = torch.float32
         main = torch.cuda.current_stream(device)
         copy = _copy_stream(device)
-        bounds = [n * i // self.PIPELINE_CHUNKS for i in range(self.PIPELINE_CHUNKS + 1)]
         rank0 = torch.empty(n, dtype=torch.int32, device=device)
         gt_score = torch.empty(n, dtype=torch.float64, device=device)
-        chunks, events = [], []
+
+        def stage(src, s, e):
+            t = src[s:e].to(device, non_blocking=True).to(dtype)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            return t, ev
+
+        if a is not None:
+            # gallery already on the device: stream the query chunks against all of it
+            c = self.PIPELINE_CHUNKS
+            bounds = [n * i // c for i in range(c + 1)]
+            with torch.cuda.stream(copy):
+                copy.wait_stream(main)
+                staged = [stage(hb, s, e) for s, e in zip(bounds[:-1], bounds[1:])]
+            a = a.to(dtype)
+            for (s, e), (qc, ev) in zip(zip(bounds[:-1], bounds[1:]), staged):
+                if e == s:
+                    continue
+                main.wait_event(ev)
+                qc.record_stream(main)
+                r, g = ops.sim_rank(qc, a, row_offset=s, metric=self.metric, precision=self.precision)
+                rank0[s:e] = r
+                gt_score[s:e] = g
+            hits, medr = ops.rank_finalize(rank0, gt_score, a.shape[0], self.k_vals)
+            return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": a.shape[0]}
+
+        c = self.PIPELINE_CHUNKS_2D
+        bounds = [n * i // c for i in range(c + 1)]
+        dq = torch.empty((n, hb.shape[1]), dtype=dtype, device=device)
+        dg = torch.empty((n, ha.shape[1]), dtype=dtype, device=device)
+        events = []
         with torch.cuda.stream(copy):
             copy.wait_stream(main)
-            if a is None:
-                a = ha.to(device, non_blocking=True).to(dtype)
             for s, e in zip(bounds[:-1], bounds[1:]):
-                chunks.append(hb[s:e].to(device, non_blocking=True).to(dtype))
+                dg[s:e].copy_(ha[s:e], non_blocking=True)
+                dq[s:e].copy_(hb[s:e], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
                 events.append(ev)
-        a = a.to(dtype)
-        for (s, e), qc, ev in zip(zip(bounds[:-1], bounds[1:]), chunks, events):
+        for (s, e), ev in zip(zip(bounds[:-1], bounds[1:]), events):
             if e == s:
                 continue
             main.wait_event(ev)
-            qc.record_stream(main)
-            r, g = ops.sim_rank(qc, a, row_offset=s, metric=self.metric, precision=self.precision)
-            rank0[s:e] = r
+            # new rows against everything that has arrived (their ground truth is among it) ...
+            _, g = ops.sim_rank(dq[s:e], dg[:e], row_offset=s, metric=self.metric,
+                                precision=self.precision, rank0=rank0[s:e], accumulate=False)
             gt_score[s:e] = g
-        a.record_stream(main)
-        hits, medr = ops.rank_finalize(rank0, gt_score, a.shape[0], self.k_vals)
-        return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": a.shape[0]}
+            # ... and the earlier rows against the new gallery rows
+            if s > 0:
+                ops.sim_rank(dq[:s], dg[s:e], row_offset=0, col_offset=s, metric=self.metric,
+                             precision=self.precision, gt_score=gt_score[:s], rank0=rank0[:s],
+                             accumulate=True)
+        dq.record_stream(copy)
+        dg.record_stream(copy)
+        hits, medr = ops.rank_finalize(rank0, gt_score, n, self.k_vals)
+        return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": n}
 
     def compute(self, features_a: ArrayLike, features_b: ArrayLike) -> List[Tuple[int, float]]:
         full = self.compute_full(features_a, features_b)
