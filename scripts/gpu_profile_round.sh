@@ -18,6 +18,18 @@ timeout 600 python bench.py --precision exact --steps 10 --no-cpu-baseline > gpu
 echo "bench exact exit=$?" >> $S
 timeout 900 python scripts/bench_extra.py c2 c35 > gpurun_out/${TAG}_bench_extra.jsonl 2> gpurun_out/${TAG}_bench_extra.err
 echo "bench_extra exit=$?" >> $S
+# what bounds the headline kernel: the same launch with the epilogue arithmetic switched off
+VTC_DBG_SKIP_EPILOGUE=1 timeout 200 python bench.py --steps 10 --no-cpu-baseline --no-e2e \
+    > gpurun_out/${TAG}_bench_skip_epilogue.json 2> gpurun_out/${TAG}_bench_skip_epilogue.err
+for d in 256 768; do
+  timeout 200 python bench.py --steps 10 --d $d --no-cpu-baseline --no-e2e \
+      > gpurun_out/${TAG}_bench_d$d.json 2> gpurun_out/${TAG}_bench_d$d.err
+done
+echo "bench variants exit=$?" >> $S
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/${TAG}_launches_topk.csv python scripts/topk_once.py \
+    > gpurun_out/${TAG}_ncu_launches_topk.log 2>&1
+echo "ncu topk launches exit=$?" >> $S
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e \
     > gpurun_out/${TAG}_ncu_launches.log 2>&1

@@ -196,8 +196,23 @@ struct TopkWs {
   float2* pool_meta;
   unsigned int* row_flag;
   float* tau0;
+  float* sample;  // [N, sample columns] approximate scores of the sample pass
 };
 constexpr int kTopkMaxSplits = 8;
+
+// Gallery tiles (of 256 rows) scored densely to seed the per-row top-k thresholds: ~1/32 of the
+// gallery, 8..32 tiles, capped so that the [N, columns] fp32 scratch stays below 512 MB; 0 = no
+// sample pass (small galleries are cheap to stream without a threshold).
+static int64_t topk_sample_tiles(int64_t N, int64_t M) {
+  const int64_t g_tiles = ceil_div<int64_t>(M, tc::BN);
+  if (g_tiles < 128 || N <= 0) return 0;
+  int64_t t = g_tiles / 32;
+  if (t < 8) t = 8;
+  if (t > 32) t = 32;
+  const int64_t cap = ((int64_t)512 << 20) / (N * tc::BN * 4);
+  if (t > cap) t = cap;
+  return t >= 4 ? t : 0;
+}
 
 TopkWs carve_topk(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int precision) {
   TopkWs t;
@@ -213,6 +228,8 @@ TopkWs carve_topk(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   t.pool = ws.take<float2>((size_t)2 * kTopkMaxSplits * N * tc::TOPK_POOL);
   t.pool_meta = ws.take<float2>((size_t)2 * kTopkMaxSplits * N);
   t.tau0 = ws.take<float>(N);
+  const int64_t st = precision == VTC_PREC_BRUTE ? 0 : topk_sample_tiles(N, M);
+  t.sample = st ? ws.take<float>((size_t)N * st * tc::BN) : nullptr;
   return t;
 }
 
@@ -273,22 +290,21 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   const int cluster = tc::choose_cluster(N, M);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
-  // Sample pass: the first ~1/32 of the gallery (8..32 tiles) yields a per-row threshold that the k best of the
-  // WHOLE gallery provably beat, so the main pass appends a handful of candidates per row and
-  // (almost) never has to re-sort a buffer.
-  const int64_t g_tiles = ceil_div<int64_t>(M, tc::BN);
-  int64_t sample_tiles = g_tiles / 32;  // >= 4 gallery tiles of main pass per sample tile
-  if (sample_tiles < 8) sample_tiles = g_tiles >= 128 ? 8 : 0;
-  if (sample_tiles > 32) sample_tiles = 32;
-  if (sample_tiles >= 8 && !getenv("VTC_TOPK_NO_SAMPLE")) {
+  // Sample pass: the first ~1/32 of the gallery is scored densely (plain tensor-core product into
+  // a scratch matrix) and reduced to a per-row threshold that the k best of the WHOLE gallery
+  // provably beat, so the main pass appends a handful of candidates per row and (almost) never
+  // has to re-sort a buffer.
+  const int64_t sample_tiles = topk_sample_tiles(N, M);
+  if (sample_tiles > 0 && w.sample && !getenv("VTC_TOPK_NO_SAMPLE")) {
     tc::Params ps = p;
     ps.M = sample_tiles * tc::BN;
-    const tc::Plan pls = tc::plan_tiles(ps, 1, cluster);
-    a.splits = 2 * ps.g_splits;
+    ps.pool = nullptr, ps.pool_meta = nullptr;
+    ps.out = w.sample, ps.ldo = ps.M;
+    const tc::Plan pls = tc::plan_tiles(ps, 64, 1, 1);
     CUtensorMap tmS;
-    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, ps.M, o.Kp, o.Kp, tc::BN / pls.cluster, &tmS));
-    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_TOPK, ps.num_kb <= 8, pls, tmA, tmS, ps, s));
-    VTC_RETURN_IF_ERROR(launch_topk_tau(a, w.tau0, s));
+    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, ps.M, o.Kp, o.Kp, tc::BN, &tmS));
+    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_STORE, ps.num_kb <= 8, pls, tmA, tmS, ps, s));
+    VTC_RETURN_IF_ERROR(launch_topk_tau(a, w.sample, (int)ps.M, ps.M, w.tau0, s));
     p.tau_init = w.tau0;
   }
   const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, cluster);

@@ -219,52 +219,62 @@ topk_select_kernel(TopkSelectArgs a) {
   }
 }
 
-// Threshold for the main top-k pass from a SAMPLE pass over the first gallery rows: the k-th
-// smallest approximate score a_k of the sample bounds the k-th smallest exact score of the whole
-// gallery (d_k(all) <= d_k(sample) <= a_k + delta), so every member of the exact top-k has
-// approximate score < a_k + 3 delta.  One warp per query row.
+// Threshold for the main top-k pass from a SAMPLE of the gallery: `scores` [N, cols] holds the
+// approximate scores of every query against the first `cols` gallery rows (a plain tensor-core
+// product, EPI_STORE).  The k-th smallest a_k of a row bounds the k-th smallest exact score of the
+// whole gallery (d_k(all) <= d_k(sample) <= a_k + delta), so every member of the exact top-k has
+// approximate score < a_k + 3 delta.  One warp per query row: every lane keeps the 16 smallest of
+// its share in sorted registers (branch-free bubble insert, taken only when a value beats the
+// lane's worst), then k rounds of warp-min pop the k-th smallest overall.
 template <typename T>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
-topk_tau_kernel(TopkSelectArgs a, float* __restrict__ tau0) {
+topk_tau_kernel(TopkSelectArgs a, const float* __restrict__ scores, int cols, int64_t ld,
+                float* __restrict__ tau0) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t t = (int64_t)blockIdx.x * SEL_WARPS + w;
+  (void)w;
+  const int64_t t = (int64_t)blockIdx.x * SEL_WARPS + (threadIdx.x >> 5);
   if (t >= a.ex.N) return;
   const T* q = (const T*)a.ex.Q + t * a.ex.ldq;
-  __shared__ float ca[SEL_WARPS][SEL_MAX_CAND];
-  const int nslots = a.splits * a.pool;
-  int ncand = 0;
-  for (int c0 = 0; c0 < nslots; c0 += 32) {  // one pass over the pools, empty slots dropped
-    const int c = c0 + lane;
-    float x = NAN;
-    if (c < nslots) {
-      const int s = c / a.pool, i = c % a.pool;
-      const int64_t slot = (int64_t)s * a.ex.N + t;
-      if (i < (int)a.pool_meta[slot].x) x = a.pool_buf[slot * a.pool + i].x;
+  constexpr int KEEP = 16;  // k <= 16
+  float best[KEEP];
+#pragma unroll
+  for (int i = 0; i < KEEP; ++i) best[i] = INFINITY;
+  const float4* row = reinterpret_cast<const float4*>(scores + t * ld);
+  for (int c = lane; c < cols / 4; c += 32) {
+    const float4 v4 = __ldg(row + c);
+    const float vs[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = vs[e];
+      if (v < best[KEEP - 1]) {  // NaN never enters
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+          const float lo = fminf(best[i], v);
+          v = fmaxf(best[i], v);
+          best[i] = lo;
+        }
+      }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, x == x);
-    if (x == x) ca[w][ncand + __popc(m & ((1u << lane) - 1u))] = x;
-    ncand += __popc(m);
   }
-  __syncwarp();
-  float last_v = -INFINITY;
-  int last_c = -1, have = 0;
+  float kth = INFINITY;
+  int have = 0;
   for (int r = 0; r < a.k; ++r) {
-    float bv = INFINITY;
-    int bc = 0x7fffffff;
-    for (int c = lane; c < ncand; c += 32) {
-      const float x = ca[w][c];
-      const bool above = x > last_v || (x == last_v && c > last_c);
-      if (above && (x < bv || (x == bv && c < bc))) bv = x, bc = c;
-    }
+    float m = best[0];
+    int src = lane;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-      if (ov < bv || (ov == bv && oc < bc)) bv = ov, bc = oc;
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int os = __shfl_xor_sync(0xffffffffu, src, o);
+      if (om < m || (om == m && os < src)) m = om, src = os;
     }
-    if (bc == 0x7fffffff) break;
-    last_v = bv, last_c = bc;
+    if (!(m < INFINITY)) break;
+    kth = m;
     ++have;
+    if (lane == src) {  // pop this lane's head
+#pragma unroll
+      for (int i = 0; i + 1 < KEEP; ++i) best[i] = best[i + 1];
+      best[KEEP - 1] = INFINITY;
+    }
   }
   const double qq = sq_seq64(q, a.ex.D);
   const double qn = sqrt(qq);
@@ -274,16 +284,18 @@ topk_tau_kernel(TopkSelectArgs a, float* __restrict__ tau0) {
                            ? 2.0 * a.guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn)
                            : (double)a.guard_rel * qn * gn + 1.2e-7 * qn * gn;
   if (lane == 0)
-    tau0[t] = (have == a.k && qq == qq) ? __double2float_ru((double)last_v + 3.0 * delta) : INFINITY;
+    tau0[t] = (have == a.k && qq == qq) ? __double2float_ru((double)kth + 3.0 * delta) : INFINITY;
 }
 
-int launch_topk_tau(const TopkSelectArgs& a, float* tau0, cudaStream_t s) {
+int launch_topk_tau(const TopkSelectArgs& a, const float* scores, int cols, int64_t ld, float* tau0,
+                    cudaStream_t s) {
   if (a.ex.N == 0) return VTC_OK;
+  if (a.k > 16 || cols % 4 || ld % 4) return VTC_ERR_UNSUPPORTED_SHAPE;
   const unsigned grid = (unsigned)ceil_div<int64_t>(a.ex.N, SEL_WARPS);
   if (a.ex.bf16)
-    topk_tau_kernel<__nv_bfloat16><<<grid, SEL_WARPS * 32, 0, s>>>(a, tau0);
+    topk_tau_kernel<__nv_bfloat16><<<grid, SEL_WARPS * 32, 0, s>>>(a, scores, cols, ld, tau0);
   else
-    topk_tau_kernel<float><<<grid, SEL_WARPS * 32, 0, s>>>(a, tau0);
+    topk_tau_kernel<float><<<grid, SEL_WARPS * 32, 0, s>>>(a, scores, cols, ld, tau0);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }

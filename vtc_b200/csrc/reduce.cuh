@@ -26,7 +26,8 @@ struct TopkSelectArgs {
 };
 int launch_topk_select(const TopkSelectArgs& a, cudaStream_t s);
 // tau0[t] = (k-th smallest approximate score in the pools) + 3 delta_t, +inf if fewer than k entries
-int launch_topk_tau(const TopkSelectArgs& a, float* tau0, cudaStream_t s);
+int launch_topk_tau(const TopkSelectArgs& a, const float* scores, int cols, int64_t ld, float* tau0,
+                    cudaStream_t s);
 int launch_topk_brute_rows(const TopkSelectArgs& a, cudaStream_t s);
 int launch_topk_merge(const float* vals, const int64_t* idx, int parts, int64_t N, int k,
                       float* out_val, int64_t* out_idx, cudaStream_t s);
