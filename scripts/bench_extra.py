@@ -168,6 +168,13 @@ def config2_train():
 
         us, nl = timeit(step, iters=20)
         emit(bench="c2_train_step_cam+infonce_fwd_bwd", precision=prec, us=us, launches=nl)
+        # the library never synchronises, so the whole step (forward, loss, backward) can be
+        # captured and replayed as one CUDA graph: GPU time without the Python launch overhead
+        try:
+            us, _ = timeit(graphed(step), iters=50)
+            emit(bench="c2_train_step_cam+infonce_fwd_bwd_cudagraph", precision=prec, us=us)
+        except Exception as e:  # noqa: BLE001
+            emit(bench="c2_train_step_cam+infonce_fwd_bwd_cudagraph", precision=prec, error=str(e)[:200])
 
     # stock torch: same computation, eager fp32
     class Block(torch.nn.Module):
@@ -209,6 +216,11 @@ def config2_train():
 
     us, _ = timeit(torch_step, iters=20)
     emit(bench="c2_train_step_torch_eager_fp32", us=us)
+    try:
+        us, _ = timeit(graphed(torch_step), iters=50)
+        emit(bench="c2_train_step_torch_cudagraph_fp32", us=us)
+    except Exception as e:  # noqa: BLE001
+        emit(bench="c2_train_step_torch_cudagraph_fp32", error=str(e)[:200])
 
 
 def torch_rank(q, g, tile=8192):
@@ -268,6 +280,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c35"]
     if "c2" in which:
         config2()
+    if "c2" in which or "train" in which:
         config2_train()
     if "c35" in which:
         config3_and_5()

@@ -23,6 +23,14 @@ for prec in ("brute", "exact", "bf16"):
     assert np.array_equal(r.cpu().numpy(), O.rank0_exact(Tq, Vq)), prec
     v, i = ops.sim_topk(q, g, 11, precision=prec)
     assert np.array_equal(i.cpu().numpy(), O.topk_exact(Tq, Vq, 11)[1]), prec
+# a gallery long enough for the top-k sample pass (dense scores + per-row threshold kernel)
+T2, V2 = make_retrieval_pair(200, 33000, 64, sigma=2.0, seed=4)
+v, i = ops.sim_topk(T2.to(dev), V2.to(dev), 11, precision="bf16")
+assert np.array_equal(i.cpu().numpy(), O.topk_exact(O.bf16_round(T2), O.bf16_round(V2), 11)[1])
+# streamed (K' > 512) CTA-pair kernel
+T3, V3 = make_retrieval_pair(300, 600, 768, sigma=2.0, seed=5)
+r, gs = ops.sim_rank(T3.to(dev), V3.to(dev), precision="bf16")
+assert np.array_equal(r.cpu().numpy(), O.rank0_exact(O.bf16_round(T3), O.bf16_round(V3)))
 vis, txt = make_batch_pair(96, 64, seed=1)
 a, t = vis.to(dev).requires_grad_(True), txt.to(dev).requires_grad_(True)
 for force in ("", "1"):

@@ -391,7 +391,7 @@ class PretrainedCLIPBase(nn.Module):
                 comm_masks = [torch.randint(low=0, high=2, size=(bs, 1), device=comm.device)
                               for comm in feats_comm]                             # :237-240
             else:
-                comm_masks = torch.ones(len(feats_comm)).to(feats_comm.device)
+                comm_masks = torch.ones(len(feats_comm), device=feats_comm.device)  # :241-242
             feats_comm = [comm * mask + self.mask_embedding.detach() * (1 - mask)
                           for comm, mask in zip(feats_comm, comm_masks)]          # :243-246
             branch_to_adapt = self.branch_to_adapt
