@@ -271,6 +271,24 @@ def test_full_size_properties_100k(cuda_dev):
     assert _np(medr)[0] == O.medr(r)
 
 
+@pytest.mark.parametrize("D", [64, 192, 100])
+def test_bf16_inputs_used_in_place(cuda_dev, D):
+    """bf16 rows of whole 128-byte atoms are the tensor-core operands themselves (no prep copy);
+    other widths go through the prep kernel.  Same ranks / top-k either way, also on row slices
+    (offset base pointers) as the pipelined staging and the multi-GPU gather hand them in."""
+    T, V = make_retrieval_pair(700, 900, D, sigma=3.0, seed=D)
+    Tq, Vq = O.bf16_round(T), O.bf16_round(V)
+    q16, g16 = T.to(cuda_dev).bfloat16(), V.to(cuda_dev).bfloat16()
+    for prec in ("bf16", "exact"):
+        r, _ = ops.sim_rank(q16, g16, precision=prec)
+        np.testing.assert_array_equal(_np(r), O.rank0_exact(Tq, Vq))
+        _, idx = ops.sim_topk(q16[:128], g16, 11, precision=prec)
+        np.testing.assert_array_equal(_np(idx), O.topk_exact(Tq[:128], Vq, 11)[1])
+    # slices: queries 300.., gallery rows 256..900 (ground truth shifted by the offsets)
+    r, _ = ops.sim_rank(q16[300:], g16[256:], row_offset=300, col_offset=256, precision="bf16")
+    np.testing.assert_array_equal(_np(r), O.rank0_exact(Tq[300:], Vq[256:], gt=np.arange(300, 700) - 256))
+
+
 # ------------------------------------------------------------- drop-in call sites (R1, R2, R4)
 def test_recall_at_k_and_compute_recall_golden(cuda_dev, golden):
     """The reference-facing calls on config-1 inputs against the fixtures produced by the

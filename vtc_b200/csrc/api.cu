@@ -58,6 +58,13 @@ OperandPlan plan_operands(int D, int dtype, int precision) {
 
 constexpr int64_t kMaxRows = (int64_t)1 << 30;
 
+// bf16 inputs whose rows already are whole 128-byte swizzle atoms ARE the tensor-core operands:
+// no prep launch, no copy (callers that keep bf16 embeddings, the multi-GPU gather and the
+// pipelined host staging hand such rows in).
+static bool operand_is_input(const void* X, int D, int dtype, const OperandPlan& o) {
+  return dtype == VTC_BF16 && !o.split && o.Kp == D && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+}
+
 // ------------------------------------------------------------------------------------ sim_rank
 struct RankWs {
   __nv_bfloat16 *opQ, *opG;
@@ -141,16 +148,24 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     return VTC_ERR_WORKSPACE;
   const OperandPlan o = plan_operands(D, dtype, precision);
   // 1. bf16 operands
-  VTC_RETURN_IF_ERROR(launch_prep_operand(Q, in_bf16, N, D, D, o.split ? PREP_SPLIT_A : PREP_PLAIN,
-                                          w.opQ, o.Kp, s));
-  VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D, o.split ? PREP_SPLIT_B : PREP_PLAIN,
-                                          w.opG, o.Kp, s));
-  // canonical values: fp32 inputs (split) or the bf16 roundings just written
+  const __nv_bfloat16* opQ = w.opQ;
+  const __nv_bfloat16* opG = w.opG;
+  if (operand_is_input(Q, D, dtype, o))
+    opQ = static_cast<const __nv_bfloat16*>(Q);
+  else
+    VTC_RETURN_IF_ERROR(launch_prep_operand(Q, in_bf16, N, D, D,
+                                            o.split ? PREP_SPLIT_A : PREP_PLAIN, w.opQ, o.Kp, s));
+  if (operand_is_input(G, D, dtype, o))
+    opG = static_cast<const __nv_bfloat16*>(G);
+  else
+    VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D,
+                                            o.split ? PREP_SPLIT_B : PREP_PLAIN, w.opG, o.Kp, s));
+  // canonical values: fp32 inputs (split) or the bf16 operands
   ExactArgs ex;
   if (o.split)
     ex = ExactArgs{Q, G, D, D, false, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
   else
-    ex = ExactArgs{w.opQ, w.opG, o.Kp, o.Kp, true, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
+    ex = ExactArgs{opQ, opG, o.Kp, o.Kp, true, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
   // 2. canonical norms, ground-truth scores, guard band
   VTC_RETURN_IF_ERROR(launch_sqnorm64(ex.G, ex.bf16, M, D, ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
   VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0],
@@ -175,8 +190,8 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   if (pl.grid > 256) return VTC_ERR_UNSUPPORTED_SHAPE;
   p.amb_seg_cap = (unsigned int)(w.amb_cap / (size_t)pl.grid);
   CUtensorMap tmA, tmB;
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
   VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
   // 4. exact re-check of the guard-band pairs; brute force if the list overflowed
   VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[64], pl.grid, p.amb_seg_cap, w.dgt,
@@ -254,10 +269,14 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
 
   TopkSelectArgs a;
   memset(&a, 0, sizeof(a));
+  const bool aliasQ = !brute && operand_is_input(Q, D, dtype, o);
+  const bool aliasG = !brute && operand_is_input(G, D, dtype, o);
+  const __nv_bfloat16* opQ = aliasQ ? static_cast<const __nv_bfloat16*>(Q) : w.opQ;
+  const __nv_bfloat16* opG = aliasG ? static_cast<const __nv_bfloat16*>(G) : w.opG;
   if (canon_inputs)
     a.ex = ExactArgs{Q, G, D, D, in_bf16, N, M, D, w.sq64, nullptr, 0, col_offset, metric};
   else
-    a.ex = ExactArgs{w.opQ, w.opG, o.Kp, o.Kp, true, N, M, D, w.sq64, nullptr, 0, col_offset, metric};
+    a.ex = ExactArgs{opQ, opG, o.Kp, o.Kp, true, N, M, D, w.sq64, nullptr, 0, col_offset, metric};
   a.pool_buf = w.pool, a.pool_meta = w.pool_meta;
   a.pool = tc::TOPK_POOL, a.k = k;
   a.guard_rel = guard_rel_for(precision, o.Kp);
@@ -272,10 +291,12 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     return launch_topk_brute_rows(a, s);
   }
 
-  VTC_RETURN_IF_ERROR(launch_prep_operand(Q, in_bf16, N, D, D, o.split ? PREP_SPLIT_A : PREP_PLAIN,
-                                          w.opQ, o.Kp, s));
-  VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D, o.split ? PREP_SPLIT_B : PREP_PLAIN,
-                                          w.opG, o.Kp, s));
+  if (!aliasQ)
+    VTC_RETURN_IF_ERROR(launch_prep_operand(Q, in_bf16, N, D, D,
+                                            o.split ? PREP_SPLIT_A : PREP_PLAIN, w.opQ, o.Kp, s));
+  if (!aliasG)
+    VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D,
+                                            o.split ? PREP_SPLIT_B : PREP_PLAIN, w.opG, o.Kp, s));
   VTC_RETURN_IF_ERROR(
       launch_sqnorm64(a.ex.G, a.ex.bf16, M, D, a.ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
   tc::Params p;
@@ -289,7 +310,7 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.topk_keep = k <= 12 ? 16 : tc::TOPK_KEEP_MAX;
   const int cluster = tc::choose_cluster(N, M);
   CUtensorMap tmA, tmB;
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
   // Sample pass: the first ~1/32 of the gallery is scored densely (plain tensor-core product into
   // a scratch matrix) and reduced to a per-row threshold that the k best of the WHOLE gallery
   // provably beat, so the main pass appends a handful of candidates per row and (almost) never
@@ -302,14 +323,14 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     ps.out = w.sample, ps.ldo = ps.M;
     const tc::Plan pls = tc::plan_tiles(ps, 64, 1, 1);
     CUtensorMap tmS;
-    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, ps.M, o.Kp, o.Kp, tc::BN, &tmS));
+    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opG, ps.M, o.Kp, o.Kp, tc::BN, &tmS));
     VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_STORE, ps.num_kb <= 8, pls, tmA, tmS, ps, s));
     VTC_RETURN_IF_ERROR(launch_topk_tau(a, w.sample, (int)ps.M, ps.M, w.tau0, s));
     p.tau_init = w.tau0;
   }
   const tc::Plan pl = tc::plan_tiles(p, kTopkMaxSplits, cluster);
   a.splits = 2 * p.g_splits;  // two column halves per gallery split
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
   VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_TOPK, p.num_kb <= 8, pl, tmA, tmB, p, s));
   VTC_RETURN_IF_ERROR(launch_topk_select(a, s));
   return launch_topk_brute_rows(a, s);

@@ -250,12 +250,23 @@ class RecallAtK(BaseMetric):
         bounds = [n * i // c for i in range(c + 1)]
         dq = torch.empty((n, hb.shape[1]), dtype=dtype, device=device)
         dg = torch.empty((n, ha.shape[1]), dtype=dtype, device=device)
+        # the bf16 mode ranks the RN-even bf16 roundings of the inputs: round each chunk on the copy
+        # stream as it lands (identical results); bf16 rows of whole swizzle atoms are used by the
+        # library as tensor-core operands in place, so no call re-converts the rows it is handed
+        to16 = self.precision == "bf16" and dtype == torch.float32
+        sq, sg = dq, dg
+        if to16:
+            dq = torch.empty_like(sq, dtype=torch.bfloat16)
+            dg = torch.empty_like(sg, dtype=torch.bfloat16)
         events = []
         with torch.cuda.stream(copy):
             copy.wait_stream(main)
             for s, e in zip(bounds[:-1], bounds[1:]):
-                dg[s:e].copy_(ha[s:e], non_blocking=True)
-                dq[s:e].copy_(hb[s:e], non_blocking=True)
+                sg[s:e].copy_(ha[s:e], non_blocking=True)
+                sq[s:e].copy_(hb[s:e], non_blocking=True)
+                if to16:
+                    dg[s:e].copy_(sg[s:e])
+                    dq[s:e].copy_(sq[s:e])
                 ev = torch.cuda.Event()
                 ev.record(copy)
                 events.append(ev)
@@ -272,8 +283,8 @@ class RecallAtK(BaseMetric):
                 ops.sim_rank(dq[:s], dg[s:e], row_offset=0, col_offset=s, metric=self.metric,
                              precision=self.precision, gt_score=gt_score[:s], rank0=rank0[:s],
                              accumulate=True)
-        dq.record_stream(copy)
-        dg.record_stream(copy)
+        for t in (dq, dg, sq, sg):
+            t.record_stream(copy)
         hits, medr = ops.rank_finalize(rank0, gt_score, n, self.k_vals)
         return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": n}
 
