@@ -276,6 +276,8 @@ def test_bf16_inputs_used_in_place(cuda_dev, D):
     """bf16 rows of whole 128-byte atoms are the tensor-core operands themselves (no prep copy);
     other widths go through the prep kernel.  Same ranks / top-k either way, also on row slices
     (offset base pointers) as the pipelined staging and the multi-GPU gather hand them in."""
+    from vtc_b200 import ops
+
     T, V = make_retrieval_pair(700, 900, D, sigma=3.0, seed=D)
     Tq, Vq = O.bf16_round(T), O.bf16_round(V)
     q16, g16 = T.to(cuda_dev).bfloat16(), V.to(cuda_dev).bfloat16()
