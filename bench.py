@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=100_000, help="queries")
     ap.add_argument("--m", type=int, default=100_000, help="gallery rows")
-    ap.add_argument("--d", type=int, default=512)
+    ap.add_argument("--d", "--dim", dest="d", type=int, default=512,
+                    help="embedding width (use --dim under torchrun: its parser rejects --d as ambiguous)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "exact", "brute"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

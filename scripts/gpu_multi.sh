@@ -32,7 +32,7 @@ timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --ma
     --master-port 29533 scripts/dist_topk_bench.py > gpurun_out/c5_topk_n$NG.json 2> gpurun_out/c5_topk_n$NG.err
 echo "c5 topk n=$NG exit=$?" >> $S
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
-    --master-port 29534 bench.py --gpus $NG --steps 20 --warmup 3 --d 768 --no-cpu-baseline --no-e2e \
+    --master-port 29534 bench.py --gpus $NG --steps 20 --warmup 3 --dim 768 --no-cpu-baseline --no-e2e \
     > gpurun_out/c4_d768_n$NG.json 2> gpurun_out/c4_d768_n$NG.err
 echo "c4 d768 n=$NG exit=$?" >> $S
 cat $S
