@@ -89,12 +89,67 @@ template <typename T>
 __device__ __forceinline__ bool aligned16(const T* p) {
   return (reinterpret_cast<uintptr_t>(p) & 15) == 0;
 }
-// fp64-sequential dot product: acc = fma(q[k], x[k], acc) for k = 0..D-1, in that order.
+// 8 consecutive elements as loaded (16-byte aligned p); widened later, so that several loads can be
+// in flight before the first dependent FMA
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<float> {
+  float4 a, b;
+};
+template <>
+struct Raw8<__nv_bfloat16> {
+  uint4 u;
+};
+__device__ __forceinline__ Raw8<float> load8_raw(const float* p) {
+  Raw8<float> r;
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  return r;
+}
+__device__ __forceinline__ Raw8<__nv_bfloat16> load8_raw(const __nv_bfloat16* p) {
+  Raw8<__nv_bfloat16> r;
+  r.u = __ldg(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+__device__ __forceinline__ void widen8(const Raw8<float>& r, double (&v)[8]) {
+  v[0] = r.a.x, v[1] = r.a.y, v[2] = r.a.z, v[3] = r.a.w;
+  v[4] = r.b.x, v[5] = r.b.y, v[6] = r.b.z, v[7] = r.b.w;
+}
+__device__ __forceinline__ void widen8(const Raw8<__nv_bfloat16>& r, double (&v)[8]) {
+  const uint32_t w[4] = {r.u.x, r.u.y, r.u.z, r.u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = (double)__uint_as_float(w[i] << 16);
+    v[2 * i + 1] = (double)__uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// fp64-sequential dot product: acc = fma(q[k], x[k], acc) for k = 0..D-1, in that order.  The
+// FMA chain is serial by definition; the loads are not, so the main loop keeps 64 bytes per operand
+// in flight (these kernels are latency-bound: one thread walks two rows).
 template <typename T>
 __device__ __forceinline__ double dot_seq64(const T* __restrict__ q, const T* __restrict__ x, int D) {
   double acc = 0.0;
   int k = 0;
   if (aligned16(q) && aligned16(x)) {
+    constexpr int U = sizeof(T) == 2 ? 4 : 2;  // groups of 8 elements per step
+    for (; k + 8 * U <= D; k += 8 * U) {
+      Raw8<T> ra[U], rb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ra[u] = load8_raw(q + k + 8 * u);
+        rb[u] = load8_raw(x + k + 8 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double a[8], b[8];
+        widen8(ra[u], a);
+        widen8(rb[u], b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fma(a[i], b[i], acc);
+      }
+    }
     for (; k + 8 <= D; k += 8) {
       double a[8], b[8];
       load8_f64(q + k, a);
@@ -111,6 +166,19 @@ __device__ __forceinline__ double sq_seq64(const T* __restrict__ x, int D) {
   double acc = 0.0;
   int k = 0;
   if (aligned16(x)) {
+    constexpr int U = sizeof(T) == 2 ? 4 : 2;
+    for (; k + 8 * U <= D; k += 8 * U) {
+      Raw8<T> ra[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ra[u] = load8_raw(x + k + 8 * u);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double a[8];
+        widen8(ra[u], a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fma(a[i], a[i], acc);
+      }
+    }
     for (; k + 8 <= D; k += 8) {
       double a[8];
       load8_f64(x + k, a);

@@ -64,7 +64,9 @@ int launch_infonce_loss(const float* row_lse, const float* col_lse, const float*
 
 // --------------------------------------------------------------------------------------- top-k
 constexpr int SEL_WARPS = 2;
-constexpr int SEL_MAX_CAND = 16 * 64;  // 2 column halves x 8 splits, pool = 64
+constexpr int SEL_MAX_PARTS = 16;                  // 2 column halves x 8 gallery splits
+constexpr int SEL_MAX_CAND = SEL_MAX_PARTS * 64;   // pool = 64 entries per part
+constexpr int SEL_MAX_SURV = 256;  // candidates re-scored in fp64 per row; more -> brute-force row
 
 template <typename T>
 __device__ __forceinline__ double exact_score(const T* __restrict__ q, const T* __restrict__ x, int D,
@@ -83,7 +85,7 @@ __device__ __forceinline__ bool cand_less(double d1, int j1, double d2, int j2) 
 template <typename T>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 topk_select_kernel(TopkSelectArgs a) {
-  __shared__ double cd[SEL_WARPS][SEL_MAX_CAND];
+  __shared__ double cd[SEL_WARPS][SEL_MAX_SURV];
   __shared__ float ca[SEL_WARPS][SEL_MAX_CAND];
   __shared__ int cj[SEL_WARPS][SEL_MAX_CAND];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,30 +94,42 @@ topk_select_kernel(TopkSelectArgs a) {
   const T* Q = (const T*)a.ex.Q;
   const T* G = (const T*)a.ex.G;
   const T* q = Q + t * a.ex.ldq;
-  // 1. gather the pooled candidates (approximate score, column), dropping the empty slots
-  const int nslots = a.splits * a.pool;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // 1. gather the pooled candidates (approximate score, column).  Lane l walks part l % 16 from
+  // entry l / 16 in steps of 2: the fill counts are read once, only filled entries are touched and
+  // four independent loads are in flight per lane (this phase is pure latency).
+  const int part = lane & (SEL_MAX_PARTS - 1), half = lane / SEL_MAX_PARTS;
+  int fill = 0;
+  int64_t slot = 0;
+  if (part < a.splits) {
+    slot = (int64_t)part * a.ex.N + t;
+    fill = min((int)a.pool_meta[slot].x, a.pool);
+  }
+  int maxfill = fill;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxfill = max(maxfill, __shfl_xor_sync(0xffffffffu, maxfill, o));
+  const float2* __restrict__ pb = a.pool_buf + slot * a.pool;
   int ncand = 0;
-  for (int c0 = 0; c0 < nslots; c0 += 32) {
-    const int c = c0 + lane;
-    int j = -1;
-    float ap = INFINITY;
-    if (c < nslots) {
-      const int s = c / a.pool, i = c % a.pool;
-      const int64_t slot = (int64_t)s * a.ex.N + t;
-      if (i < (int)a.pool_meta[slot].x) {
-        const float2 e = a.pool_buf[slot * a.pool + i];
-        j = __float_as_int(e.y);
-        ap = e.x;
-        if (j < 0 || j >= a.ex.M || ap != ap) j = -1;
+  for (int i0 = 0; i0 < maxfill; i0 += 8) {
+    float2 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + half + 2 * u;
+      e[u] = i < fill ? pb[i] : make_float2(NAN, __int_as_float(-1));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = __float_as_int(e[u].y);
+      const float ap = e[u].x;
+      const bool ok = (i0 + half + 2 * u) < fill && j >= 0 && j < a.ex.M && ap == ap;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int o = ncand + __popc(m & lt_mask);
+        ca[w][o] = ap;
+        cj[w][o] = j;
       }
+      ncand += __popc(m);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, j >= 0);
-    if (j >= 0) {
-      const int o = ncand + __popc(m & ((1u << lane) - 1u));
-      ca[w][o] = ap;
-      cj[w][o] = j;
-    }
-    ncand += __popc(m);
   }
   __syncwarp();
   const double qq = sq_seq64(q, a.ex.D);  // every lane computes it (keeps the warp convergent)
@@ -159,9 +173,13 @@ topk_select_kernel(TopkSelectArgs a) {
     const bool keep = j >= 0 && (double)ca[w][c] <= thr;
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     __syncwarp();
-    if (keep) cj[w][nsurv + __popc(m & ((1u << lane) - 1u))] = j;
+    if (keep) cj[w][nsurv + __popc(m & lt_mask)] = j;
     nsurv += __popc(m);
     __syncwarp();
+  }
+  if (nsurv > SEL_MAX_SURV) {  // pathological ties: let the brute-force kernel do this row
+    if (lane == 0) a.row_flag[t] = 1u;
+    return;
   }
   // exact re-scoring, one survivor per lane
   for (int c = lane; c < nsurv; c += 32) {
@@ -240,18 +258,27 @@ topk_tau_kernel(TopkSelectArgs a, const float* __restrict__ scores, int cols, in
 #pragma unroll
   for (int i = 0; i < KEEP; ++i) best[i] = INFINITY;
   const float4* row = reinterpret_cast<const float4*>(scores + t * ld);
-  for (int c = lane; c < cols / 4; c += 32) {
-    const float4 v4 = __ldg(row + c);
-    const float vs[4] = {v4.x, v4.y, v4.z, v4.w};
+  const int nv = cols / 4;
+  for (int c0 = lane; c0 < nv; c0 += 128) {  // four independent 16-byte loads in flight per lane
+    float4 v4[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float v = vs[e];
-      if (v < best[KEEP - 1]) {  // NaN never enters
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 32 * u;
+      v4[u] = c < nv ? __ldg(row + c) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    }
 #pragma unroll
-        for (int i = 0; i < KEEP; ++i) {
-          const float lo = fminf(best[i], v);
-          v = fmaxf(best[i], v);
-          best[i] = lo;
+    for (int u = 0; u < 4; ++u) {
+      const float vs[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = vs[e];
+        if (v < best[KEEP - 1]) {  // NaN never enters
+#pragma unroll
+          for (int i = 0; i < KEEP; ++i) {
+            const float lo = fminf(best[i], v);
+            v = fmaxf(best[i], v);
+            best[i] = lo;
+          }
         }
       }
     }
@@ -394,7 +421,7 @@ __global__ void topk_merge_kernel(const float* __restrict__ vals, const int64_t*
 
 int launch_topk_select(const TopkSelectArgs& a, cudaStream_t s) {
   if (a.ex.N == 0) return VTC_OK;
-  if (a.splits * a.pool > SEL_MAX_CAND || a.k > BRUTE_KMAX) return VTC_ERR_UNSUPPORTED_SHAPE;
+  if (a.splits > SEL_MAX_PARTS || a.pool > 64 || a.k > BRUTE_KMAX) return VTC_ERR_UNSUPPORTED_SHAPE;
   const unsigned grid = (unsigned)ceil_div<int64_t>(a.ex.N, SEL_WARPS);
   if (a.ex.bf16)
     topk_select_kernel<__nv_bfloat16><<<grid, SEL_WARPS * 32, 0, s>>>(a);
