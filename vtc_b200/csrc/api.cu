@@ -183,6 +183,7 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   tc::Params p;
   memset(&p, 0, sizeof(p));
   p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
+  p.gt = gt, p.gt_row_offset = row_offset, p.gt_col_offset = col_offset;
   p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
   p.thr = w.thr, p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_seg_count = &w.scalars[64];

@@ -34,6 +34,11 @@ struct Params {
                       // one segment of amb_seg_cap entries per CTA
   unsigned int* amb_seg_count;  // [grid] entries each CTA wanted to push (may exceed the capacity)
   unsigned int amb_seg_cap;
+  // ground-truth column of row t in THIS launch's column numbering:
+  // (gt ? gt[t] : t + gt_row_offset) - gt_col_offset.  Its own score is inside the guard band by
+  // construction; a group whose only in-band column is that one needs no re-check.
+  const int64_t* gt;
+  int64_t gt_row_offset, gt_col_offset;
   // EPI_LSE  (score is the logit in log2 units: scale already includes log2(e))
   float2* lse_part;     // [2 * g_splits, N] running (max, sum) in log2 domain (part = 2*split + half)
   float* diag;          // [N] raw accumulator of column t + diag_offset (nullable)

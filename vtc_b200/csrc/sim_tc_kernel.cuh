@@ -25,6 +25,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <climits>
 #include <cstring>
 
 #include "ptx.cuh"
@@ -85,15 +86,19 @@ constexpr int RANK_GROUP = 8;  // columns re-checked together when any of them i
 struct RankEpi {
   float lo, hi;
   int cnt;
+  int gtc;  // ground-truth column of this row (launch-local), or a value no group can contain
   int64_t t;
   __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int) {
     t = t_;
     cnt = 0;
     lo = hi = nanf("");
+    gtc = INT_MIN / 2;
     if (t < p.N) {
       const float2 th = p.thr[t];
       lo = th.x;
       hi = th.y;
+      const int64_t g = (p.gt ? p.gt[t] : t + p.gt_row_offset) - p.gt_col_offset;
+      if (g >= 0 && g < p.M) gtc = (int)g;
     }
   }
   // rare: this row has a score inside the guard band among columns [j, j+8): hand the whole group
@@ -131,11 +136,18 @@ struct RankEpi {
                        ((d2 <= hi ? 1.f : 0.f) + (d3 <= hi ? 1.f : 0.f)) +
                        ((d4 <= hi ? 1.f : 0.f) + (d5 <= hi ? 1.f : 0.f)) +
                        ((d6 <= hi ? 1.f : 0.f) + (d7 <= hi ? 1.f : 0.f));
-      if (le != lt)
-        push_group(p.amb_list + (size_t)blockIdx.x * p.amb_seg_cap, p.amb_seg_cap, seg_count,
-                   (int)t, (int)(jbase + RANK_GROUP * g));
-      else
+      if (le != lt) {
+        // the ground truth's own score is in the band by construction: a group whose ONLY in-band
+        // column is that one is decided (the column is skipped by index in the count anyway)
+        const int j0 = (int)jbase + RANK_GROUP * g;
+        if (le - lt == 1.f && (unsigned)(gtc - j0) < (unsigned)RANK_GROUP)
+          csum += lt;
+        else
+          push_group(p.amb_list + (size_t)blockIdx.x * p.amb_seg_cap, p.amb_seg_cap, seg_count,
+                     (int)t, j0);
+      } else {
         csum += lt;
+      }
     }
     cnt += (int)csum;
   }
