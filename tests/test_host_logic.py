@@ -109,3 +109,30 @@ def test_cached_embedding_reader_and_alignment(tmp_path):
     torch.save({"reddit_ids": ids_a.int(), "embeddings": ea}, pa)
     with pytest.raises(AssertionError):
         load_cached_embeddings(str(pa), pin=False)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line with the contract's keys,
+    no GPU needed, no work on ranks other than 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--n", "1500",
+           "--m", "1500", "--steps", "1", "--warmup", "0", "--cpu-seconds", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
+    # under torchrun only rank 0 works and prints
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
