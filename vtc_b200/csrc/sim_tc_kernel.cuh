@@ -11,11 +11,13 @@
 //   EPI_TOPK   streaming top-k candidate pool per row                      -> faiss-style search
 //   EPI_STORE  materialise (bias / QuickGELU / residual)                   -> sim tensor, linears
 //
-// Structure (one CTA per SM, persistent over work items, 256 threads):
-//   warp 0   TMA producer  : cp.async.bulk.tensor 2-D loads, 128B-swizzled K-major tiles
-//   warp 1   MMA issuer    : one thread issues tcgen05.mma (M128 x N256 x K16, bf16 -> fp32 TMEM)
-//   warp 2   TMEM allocator: 512 columns = 2 accumulator stages of 256
-//   warp 4-7 epilogue      : tcgen05.ld 32x32b (thread = tile row), fused reduction
+// Structure (one CTA per SM, persistent over work items, 384 threads):
+//   warp 0    TMA producer  : cp.async.bulk.tensor 2-D loads, 128B-swizzled K-major tiles
+//   warp 1    MMA issuer    : one thread issues tcgen05.mma (M128 x N256 x K16 per CTA, or one
+//                             M256 cta_group::2 MMA per CTA pair; bf16 -> fp32 in TMEM)
+//   warp 2    TMEM allocator: 512 columns = 2 accumulator stages of 256
+//   warp 4-11 epilogue      : tcgen05.ld 32x32b (thread = tile row; two warps per scheduler, each
+//                             one column half of the tile), fused reduction
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 // With `kRes` the 128 x K' query tile stays resident in shared memory for a whole work item
 // (K' <= 512), so only gallery tiles stream from L2: 64 B/clk/SM instead of 96.
