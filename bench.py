@@ -215,7 +215,19 @@ def run_ours(a):
     # Python, so the whole sharded step is captured once and replayed as one CUDA graph
     graphed = None
     if world > 1 and not a.no_graph and not os.environ.get("VTC_PHASE_TIMING"):
-        graphed = GraphedRankEval(q_local, g_local, a.n, a.m, k_vals, "l2", a.precision)
+        try:
+            graphed = GraphedRankEval(q_local, g_local, a.n, a.m, k_vals, "l2", a.precision)
+        except Exception as exc:  # noqa: BLE001  (capture refused: measure kernel by kernel, say so)
+            print(f"[bench] CUDA-graph capture of the sharded step failed on rank {rank}: {exc!r}; "
+                  "falling back to per-kernel launches", file=sys.stderr, flush=True)
+            graphed = None
+            torch.cuda.synchronize()
+        # every rank must take the same path: the collectives inside differ otherwise
+        ok = torch.tensor([1 if graphed is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0 and graphed is not None:
+            graphed.close()
+            graphed = None
 
     def eager_step():
         return sharded_rank_eval(q_local, g_local, a.n, a.m, k_vals, "l2", a.precision)
