@@ -113,7 +113,8 @@ def normalize(x: torch.Tensor) -> torch.Tensor:
 
 
 def row_norms(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(1/||x_r||, ||x_r||^2) per row, fp32."""
+    """(1/||x_r||, ||x_r||^2) per row, fp32: the norms behind model/model.py:26-27 and the
+    ||x||^2 term of faiss' L2 distance (model/metric.py:144-146)."""
     dev = _req_cuda(x)
     x = _mat(x, "x")
     inv = torch.empty(x.shape[0], dtype=torch.float32, device=dev)
@@ -153,7 +154,9 @@ def sim_matrix(a: torch.Tensor, b: torch.Tensor, scale=1.0, precision="exact") -
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, act: int = 0, precision="exact") -> torch.Tensor:
-    """act(x @ w.t() + bias) + residual on the tensor cores; x [rows, in], w [out, in], fp32."""
+    """act(x @ w.t() + bias) + residual on the tensor cores; x [rows, in], w [out, in], fp32.
+    The CAM transformer's linears (in_proj / out_proj / c_fc / c_proj of clip.model.Transformer,
+    structure per model/timesformer_clip_alt.py:43-67,112-124) and final_linear (model/model.py:161)."""
     dev = _req_cuda(x, w, bias, residual)
     x, w = _mat(x.float(), "x"), _mat(w.float(), "w")
     rows, in_f = x.shape
@@ -181,7 +184,9 @@ def sim_rank(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None
              row_offset: int = 0, col_offset: int = 0, metric="l2", precision="exact",
              gt_score: Optional[torch.Tensor] = None, rank0: Optional[torch.Tensor] = None,
              accumulate: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Fused similarity + rank of ground truth.  Returns (rank0 int32 [N], gt_score fp64 [N]).
+    """Fused similarity + rank of ground truth: replaces faiss GpuIndexFlatL2.add/search + the Python
+    hit loop of RecallAtK.compute (model/metric.py:140-160).  Returns (rank0 int32 [N], gt_score
+    fp64 [N]).
 
     rank0 is NOT finalised (NaN ground truths still hold their partial count): call
     :func:`rank_finalize` once every gallery chunk has been accumulated."""
@@ -238,7 +243,8 @@ def gt_scores(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = Non
 def rank_finalize(rank0: torch.Tensor, gt_score: Optional[torch.Tensor], M_total: int,
                   k_vals: Sequence[int], want_medr: bool = True
                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """In place: rank0 = M_total where gt_score is NaN.  Returns (hits int64 [nk], medr fp64 [1])."""
+    """In place: rank0 = M_total where gt_score is NaN.  Returns (hits int64 [nk], medr fp64 [1]):
+    the hit counts behind recall@k (model/metric.py:148-160) and MedR."""
     dev = _req_cuda(rank0, gt_score)
     k_vals = [int(k) for k in k_vals]
     if len(k_vals) > 8:
@@ -258,7 +264,8 @@ def rank_finalize(rank0: torch.Tensor, gt_score: Optional[torch.Tensor], M_total
 # ------------------------------------------------------------------------------------------ K7
 def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int, metric="l2", precision="exact",
              col_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Fused similarity + streaming top-k: (vals fp32 [N,k] ascending, idx int64 [N,k])."""
+    """Fused similarity + streaming top-k: (vals fp32 [N,k] ascending, idx int64 [N,k]) -- what
+    faiss_search_index.search(features_b, max(k_vals) + 1) returns (model/metric.py:144-146)."""
     dev = _req_cuda(q, g)
     q, g = _mat(q, "q"), _mat(g, "g")
     if q.shape[1] != g.shape[1] or q.dtype != g.dtype:
@@ -293,7 +300,9 @@ def topk_merge(vals: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, tor
 # ------------------------------------------------------------------------------------- H2 + H3
 def infonce_fwd(a: torch.Tensor, b: torch.Tensor, scale, precision="exact"
                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Fused symmetric InfoNCE forward: (loss [1], row_lse [n], col_lse [n], diag [n])."""
+    """Fused symmetric InfoNCE forward, 0.5 * (CE(sim, arange) + CE(sim.t(), arange)) with
+    sim = scale * a @ b.t() never materialised (model/loss.py:18-22, model/model.py:369):
+    (loss [1], row_lse [n], col_lse [n], diag [n])."""
     dev = _req_cuda(a, b)
     a, b = _mat(a, "a"), _mat(b, "b")
     if a.shape != b.shape or a.dtype != b.dtype:
@@ -317,7 +326,8 @@ def infonce_fwd(a: torch.Tensor, b: torch.Tensor, scale, precision="exact"
 def infonce_bwd(a: torch.Tensor, b: torch.Tensor, scale, row_lse: torch.Tensor,
                 col_lse: torch.Tensor, grad_loss: torch.Tensor
                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(dA [n,D], dB [n,D], dscale [1]) fp32."""
+    """Backward of infonce_fwd w.r.t. both feature matrices and the logit scale (the autograd of
+    model/loss.py:18-22 through model/model.py:369): (dA [n,D], dB [n,D], dscale [1]) fp32."""
     dev = _req_cuda(a, b, row_lse, col_lse, grad_loss)
     a, b = _mat(a, "a"), _mat(b, "b")
     n, D = a.shape
@@ -354,6 +364,8 @@ def cam_stack_normalize(main: torch.Tensor, aux: torch.Tensor) -> torch.Tensor:
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5
               ) -> torch.Tensor:
+    """LayerNorm over the last dim in fp32 (ln_1 / ln_2 of clip.model.Transformer's blocks, the
+    fp32-upcast LayerNorm of model/timesformer_clip_alt.py:22-33)."""
     dev = _req_cuda(x, gamma, beta)
     shp = x.shape
     x2 = x.float().reshape(-1, shp[-1]).contiguous()
@@ -367,7 +379,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def cam_attn_core(qkv: torch.Tensor, heads: int) -> torch.Tensor:
-    """softmax(q k^T / sqrt(hd)) v per (sample, head); qkv [L, b, 3D] -> [L, b, D]."""
+    """softmax(q k^T / sqrt(hd)) v per (sample, head); qkv [L, b, 3D] -> [L, b, D]: the attention
+    core of nn.MultiheadAttention inside clip.model.Transformer (model/model.py:155; structure per
+    model/timesformer_clip_alt.py:43-67), seq-first, no mask."""
     dev = _req_cuda(qkv)
     qkv = qkv.float().contiguous()
     L, b, D3 = qkv.shape
@@ -391,6 +405,10 @@ def _res_act_args(res_act, dev):
 def cam_readout(T: Optional[torch.Tensor], main: Optional[torch.Tensor], mode: int,
                 res_in: Optional[torch.Tensor] = None, skip_mask: Optional[torch.Tensor] = None,
                 res_act=None) -> torch.Tensor:
+    """Read-out of the CAM in one kernel (model/model.py:156-161, 168-171, 199-203): AVG =
+    normalize(mean_l normalize(T_l)), RESIDUAL_ONLY = a caller-computed residual (final_linear of
+    token 0), then the residual activation of model/model.py:30-77, the random adapter skip and
+    normalize(normalize(main) + res); UNIFORM = the averaging fusion of model/model.py:356-366."""
     dev = _req_cuda(T, main, res_in, skip_mask)
     if T is not None:
         T = T.float().contiguous()
