@@ -612,3 +612,34 @@ def cam_readout_bwd(T: Optional[torch.Tensor], main: torch.Tensor, dout: torch.T
               D, mode, act, scale, _ptr(shift), _ptr(mul), _ptr(dT), _ptr(dres), _ptr(dmain),
               _stream(dev))
     return dT, dres, dmain
+
+
+# ----------------------------------------------------------------------------------- tracing
+def _install_nvtx_ranges() -> None:
+    """VTC_NVTX=1: wrap every public op in an NVTX range `vtc.<name>` so that ncu / nsys can filter
+    and group by library call (`ncu --nvtx --nvtx-include "vtc.sim_rank/"`).  The reference's only
+    timing around this path is a wall-clock print in RecallAtK.result (model/metric.py:167-185)."""
+    import functools
+    import types
+
+    def wrap(fn):
+        @functools.wraps(fn)
+        def ranged(*args, **kwargs):
+            torch.cuda.nvtx.range_push("vtc." + fn.__name__)
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return ranged
+
+    g = globals()
+    for name, fn in list(g.items()):
+        if (isinstance(fn, types.FunctionType) and not name.startswith("_")
+                and fn.__module__ == __name__ and name != "release_workspaces"):
+            g[name] = wrap(fn)
+
+
+import os as _os  # noqa: E402
+
+if _os.environ.get("VTC_NVTX"):
+    _install_nvtx_ranges()
