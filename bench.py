@@ -11,8 +11,10 @@ vtc_rank_finalize), 1e10 pairs per step at the default size.
 N > 1 is launched by the driver as
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 one rank per GPU over NCCL: query rows and gallery rows are sharded, gallery shards are
-all-gathered over NVLink, ranks are additive over gallery chunks, hit counts are all-reduced
-(vtc_b200/parallel.py).  Total work is fixed as N grows => "scaling": "strong".
+all-gathered over NVLink, ranks are additive over gallery chunks, the int32 ranks are gathered for
+the hit counts and the median (vtc_b200/parallel.py); the whole sharded step is captured once and
+replayed as a CUDA graph (--no-graph: kernel by kernel).  Total work is fixed as N grows =>
+"scaling": "strong".
 
 One JSON line is printed by rank 0 (see the contract in the task description): `value` is the
 device-resident throughput, `e2e` the same metric through the reference-facing call
