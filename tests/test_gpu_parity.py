@@ -341,6 +341,29 @@ def test_eval_consumer_six_keys(cuda_dev, tmp_path):
     assert recall_summary(V.numpy(), T.numpy()) == out          # numpy in, like the reference
 
 
+def test_eval_tail_on_device(cuda_dev):
+    """R5 (evaluation/retrieval_evaluation.py:238-260): lists of per-video frame features and
+    per-video caption features -> [N, D] means (not renormalised) and [N, maxcap, D] with -inf
+    padding, built on the device in O(1) launches; then ranked like the reference does."""
+    from vtc_b200.evaluation.retrieval_evaluation import compute_recall, eval_tail
+
+    g = torch.Generator().manual_seed(5)
+    T, V = make_retrieval_pair(300, 300, 64, sigma=2.0, seed=9)
+    vids = [V[i:i + 1] + 0.01 * torch.randn(int(n), 64, generator=g)
+            for i, n in enumerate(torch.randint(1, 9, (300,), generator=g))]
+    caps = [T[i:i + 1].repeat(int(n), 1) for i, n in enumerate(torch.randint(1, 4, (300,), generator=g))]
+    v, c = eval_tail(vids, caps, cuda_dev)
+    vo, co = O.eval_tail(vids, caps)
+    assert v.is_cuda and c.is_cuda
+    np.testing.assert_array_equal(_np(c), co.numpy())
+    np.testing.assert_allclose(_np(v), vo.numpy(), rtol=1e-6, atol=1e-7)
+    # one caption per video -> the reference's compute_recall call on the tail's outputs
+    v1, c1 = eval_tail(vids, [x[:1] for x in caps], cuda_dev)
+    df = compute_recall(v1, c1)
+    want = O.compute_recall(v1.cpu(), c1.cpu())
+    np.testing.assert_array_equal(df.values, want.values)
+
+
 def test_recall_pipelined_host_staging(cuda_dev):
     """Large host inputs are staged chunk by chunk on a copy stream (H2D overlaps ranking); the
     result must not depend on the chunking."""

@@ -136,3 +136,24 @@ def test_bench_reference_arm_contract():
     # under torchrun only rank 0 works and prints
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_eval_tail_vectorised_matches_the_oracle_on_cpu():
+    """evaluation/retrieval_evaluation.py:238-260: -inf caption padding (exact) and per-video frame
+    mean (fp32 reduction order may differ: allclose), via the device-agnostic core of eval_tail."""
+    import torch
+
+    from oracle import vtc_oracle as O
+    from vtc_b200.evaluation.retrieval_evaluation import _eval_tail_on
+
+    g = torch.Generator().manual_seed(0)
+    vids = [torch.randn(int(n), 32, generator=g) for n in torch.randint(1, 40, (150,), generator=g)]
+    caps = [torch.randn(int(n), 32, generator=g) for n in torch.randint(1, 6, (150,), generator=g)]
+    v, c = _eval_tail_on(vids, caps, torch.device("cpu"))
+    vo, co = O.eval_tail(vids, caps)
+    assert torch.equal(c, co)
+    assert v.shape == vo.shape and torch.allclose(v, vo, rtol=1e-6, atol=1e-7)
+    # the single-frame / single-caption case degenerates to plain stacking
+    v1, c1 = _eval_tail_on([x[:1] for x in vids], [x[:1] for x in caps], torch.device("cpu"))
+    assert torch.equal(v1, torch.cat([x[:1] for x in vids]))
+    assert torch.equal(c1[:, 0], torch.cat([x[:1] for x in caps]))

@@ -63,15 +63,50 @@ def compute_recall(tensor_v: torch.Tensor, tensor_t: torch.Tensor, split: str = 
     return df
 
 
+def _gather_rows(items: List[torch.Tensor], device: torch.device) -> torch.Tensor:
+    """All rows of a list of [n_i, D] tensors as one fp32 [sum n_i, D] tensor on `device`: a single
+    concatenation and (for host inputs) a single transfer instead of one per video."""
+    if all(t.device == items[0].device for t in items):
+        return torch.cat(items).to(device=device, dtype=torch.float32)
+    return torch.cat([t.to(device=device, dtype=torch.float32) for t in items])
+
+
+def _eval_tail_on(video_joint_embeddings: List[torch.Tensor],
+                  caption_joint_embeddings: List[torch.Tensor],
+                  device: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The arithmetic of eval_tail on an explicit device (device-agnostic so that the host logic is
+    testable without a GPU): O(1) launches instead of O(#videos)."""
+    n = len(caption_joint_embeddings)
+    D = caption_joint_embeddings[0].shape[1]
+    lens_c = np.array([k.shape[0] for k in caption_joint_embeddings], dtype=np.int64)
+    max_length = int(lens_c.max())
+    # captions (:238-252): a buffer of -inf rows, one indexed copy of every caption row into it
+    caps = torch.full((n * max_length, D), float("-inf"), dtype=torch.float32, device=device)
+    if lens_c.sum() > 0:
+        first = np.concatenate([[0], np.cumsum(lens_c)[:-1]])
+        row = (np.arange(int(lens_c.sum())) - np.repeat(first, lens_c)
+               + np.repeat(np.arange(n, dtype=np.int64) * max_length, lens_c))
+        caps.index_copy_(0, torch.from_numpy(row).to(device),
+                         _gather_rows([k.reshape(-1, D) for k in caption_joint_embeddings], device))
+    caps = caps.view(n, max_length, D)
+    # videos (:254-259): mean over each video's frame / chunk features, NOT renormalised
+    lens_v = torch.tensor([k.shape[0] for k in video_joint_embeddings], dtype=torch.int64)
+    vids = None
+    if int(lens_v.min()) > 0:
+        try:
+            vids = torch.segment_reduce(_gather_rows(list(video_joint_embeddings), device), "mean",
+                                        lengths=lens_v.to(device), axis=0)
+        except (RuntimeError, NotImplementedError):
+            vids = None  # same arithmetic, one reduction per video
+    if vids is None:
+        vids = torch.cat([k.to(device=device, dtype=torch.float32).mean(dim=0, keepdim=True)
+                          for k in video_joint_embeddings])
+    return vids, caps
+
+
 def eval_tail(video_joint_embeddings: List[torch.Tensor], caption_joint_embeddings: List[torch.Tensor],
               device: Optional[torch.device] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """evaluation/retrieval_evaluation.py:238-260 on the device: -inf padding of caption lists to
     the max count, per-video mean over frame / chunk features (NOT renormalised), stack."""
     device = device or _default_device()
-    max_length = max(s.shape[0] for s in caption_joint_embeddings)
-    D = caption_joint_embeddings[0].shape[1]
-    caps = torch.full((len(caption_joint_embeddings), max_length, D), float("-inf"), device=device)
-    for i, k in enumerate(caption_joint_embeddings):
-        caps[i, :k.shape[0]] = _to_device(k, device)
-    vids = torch.cat([_to_device(k, device).mean(dim=0, keepdim=True) for k in video_joint_embeddings])
-    return vids, caps
+    return _eval_tail_on(video_joint_embeddings, caption_joint_embeddings, device)
