@@ -23,14 +23,20 @@ What is restated here (citations are ``path:line`` in /root/reference):
                                      implemented in fp64-sequential arithmetic by
                                      ``oracle/vtc_oracle.c``.
 
-PARITY STATUS: **parity unpinned** at the ``faiss`` and ``clip.model.Transformer``
-boundaries (both are un-vendored, un-pinned third-party packages absent from this image and
-from /root/reference; the reference's own tests hold no golden vector for this path --
-SURVEY.md §4, §8c).  What *is* pinned: ``tests/golden/generate_golden.py`` executes the
-reference's own function bodies (``clip_loss``, ``RecallAtK.compute``, ``compute_recall``,
-``_adapt_feature``, ``_encode_with_comments``) in this container through the shims in
-``oracle/reference_shims.py`` and commits their outputs; ``tests/test_oracle_golden.py``
-checks this restatement against those fixtures.
+PARITY STATUS.  Pinned to the reference's OWN code: ``tests/golden/generate_golden.py`` imports
+the reference from /root/reference and executes its function bodies unmodified (``clip_loss``,
+``RecallAtK.compute``, ``compute_recall``, ``_adapt_feature``, ``_encode_with_comments``); the
+outputs are committed under ``tests/golden/`` and ``tests/test_oracle_golden.py`` checks this
+restatement against them (``tests/test_oracle_vs_reference.py`` repeats the comparison live
+wherever /root/reference exists).  Two third-party packages the reference calls are absent from
+this image and from /root/reference, are not version-pinned by the reference itself
+(``environment.yml:12,30``), and are therefore RESTATED from their published definitions in
+``oracle/reference_shims.py``: ``faiss.GpuIndexFlatL2(useFloat16=False)`` = exact fp32 brute-force
+L2 search, and ``clip.model.Transformer`` = openai/CLIP's ResidualAttentionBlock stack (the in-repo
+mirror model/timesformer_clip_alt.py has the same structure).  At exactly those two boundaries
+**parity is unpinned**: faiss' internal accumulation / tie order and the CLIP commit are not
+observable here, and the reference's own tests hold no golden vector for this path (SURVEY.md §4,
+§8c).
 """
 from __future__ import annotations
 
