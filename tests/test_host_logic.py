@@ -157,3 +157,34 @@ def test_eval_tail_vectorised_matches_the_oracle_on_cpu():
     v1, c1 = _eval_tail_on([x[:1] for x in vids], [x[:1] for x in caps], torch.device("cpu"))
     assert torch.equal(v1, torch.cat([x[:1] for x in vids]))
     assert torch.equal(c1[:, 0], torch.cat([x[:1] for x in caps]))
+
+
+def test_models_construct_from_the_reference_config_args():
+    """`config.init_obj("arch", module_arch)` (train.py:67, utils/parse_config.py:97-112) calls
+    the class with the `args` dict of the reference's configs: same keyword names must work."""
+    import pytest
+
+    from vtc_b200.model.model import PretrainedCLIP, PretrainedCLIP_finaltf
+
+    args = {"model_type": "ViT-B/32", "branch_to_adapt": "text", "branch_to_adapt_val": "text",
+            "n_layers": 2, "n_heads": 8, "init_from_avg": True, "random_comment_masking": False,
+            "random_skip_adapter": True}          # configs/pretrained_clip_comments_attention.jsonc:7-17
+    m = PretrainedCLIP_finaltf(**args)
+    assert m.feature_dim == 512 and len(m.final_transformer.resblocks) == 2
+    assert m.branch_to_freeze is False
+    assert PretrainedCLIP_finaltf("ViT-L/14").feature_dim == 768
+    assert PretrainedCLIP_finaltf(64, n_layers=1, n_heads=2).feature_dim == 64   # int shorthand
+    # freeze="finaltf" (experiments freeze the adapter, model/model.py:290-299)
+    f = PretrainedCLIP_finaltf(model_type="ViT-B/32", freeze="finaltf")
+    assert f.branch_to_freeze == "finaltf"
+    assert not any(p.requires_grad for p in f.final_transformer.parameters())
+    assert not f.final_linear.weight.requires_grad and not f.mask_embedding.requires_grad
+    with pytest.raises(Exception, match="Unknown branch_to_freeze"):
+        PretrainedCLIP_finaltf(freeze="bogus")
+    with pytest.raises(NotImplementedError):
+        PretrainedCLIP_finaltf(init_audio_model=True)
+    p = PretrainedCLIP(model_type="ViT-B/32", freeze=False, residual_activation=None,
+                       comment_fusion="averaging")                  # model/model.py:309-315
+    assert p.feature_dim == 512 and p.comment_fusion == "averaging"
+    with pytest.raises(ValueError):
+        PretrainedCLIP("no-such-clip")

@@ -296,6 +296,65 @@ class PretrainedCLIPBase(nn.Module):
     branch_to_adapt_val = "text"
     precision = "exact"
 
+    # embedding width of the CLIP checkpoints `clip.load` knows (model_type strings of the
+    # reference's configs, e.g. configs/pretrained_clip_comments_attention.jsonc:9)
+    CLIP_FEATURE_DIMS = {"ViT-B/32": 512, "ViT-B/16": 512, "ViT-L/14": 768, "ViT-L/14@336px": 768,
+                         "RN50": 1024, "RN101": 512, "RN50x4": 640, "RN50x16": 768, "RN50x64": 1024}
+
+    @classmethod
+    def _resolve_feature_dim(cls, model_type, feature_dim, backbone) -> int:
+        """The reference reads the width off the loaded CLIP model (model/model.py:320,395); here
+        the backbone is optional (precomputed features), so the width comes from, in order: the
+        backbone's `ln_final`, an explicit `feature_dim`, an int passed where the reference takes
+        `model_type`, or the model_type string."""
+        if backbone is not None and hasattr(backbone, "ln_final"):
+            return int(backbone.ln_final.normalized_shape[0])
+        if feature_dim is not None:
+            return int(feature_dim)
+        if isinstance(model_type, int):
+            return int(model_type)
+        if model_type in cls.CLIP_FEATURE_DIMS:
+            return cls.CLIP_FEATURE_DIMS[model_type]
+        raise ValueError(f"unknown model_type {model_type!r}: pass feature_dim=")
+
+    def _freeze(self, branch_to_freeze):
+        """model/model.py:268-305.  Without a backbone there is nothing to freeze for "visual" /
+        "text" / "all"; "finaltf" freezes the CAM exactly as the reference does."""
+        self.branch_to_freeze = branch_to_freeze
+        if branch_to_freeze is False or branch_to_freeze == "none":
+            return
+        did_freeze = False
+        backbone = getattr(self, "model", None)
+        if "visual" in branch_to_freeze:
+            did_freeze = True
+            if backbone is not None and hasattr(backbone, "visual"):
+                for param in backbone.visual.parameters():
+                    param.requires_grad = False
+        if "text" in branch_to_freeze:
+            did_freeze = True
+            if backbone is not None and hasattr(backbone, "transformer"):
+                for param in backbone.transformer.parameters():
+                    param.requires_grad = False
+        if "all" in branch_to_freeze:
+            did_freeze = True
+            if backbone is not None:
+                for param in backbone.parameters():
+                    param.requires_grad = False
+        if "finaltf" in branch_to_freeze:
+            did_freeze = True
+            if hasattr(self, "final_transformer"):
+                for param in self.final_transformer.parameters():
+                    param.requires_grad = False
+                for param in self.final_linear.parameters():
+                    param.requires_grad = False
+                self.mask_embedding.requires_grad = False
+            else:
+                import warnings
+
+                warnings.warn("Tried to freeze finaltf but model has no final transformer, ignoring!")
+        if not did_freeze:
+            raise Exception("Unknown branch_to_freeze")
+
     def _common_init(self):
         """model/model.py:133-139: a BatchNorm1d holds the running stats of sub_mean / bn."""
         if getattr(self, "residual_activation", None) in NEEDS_STATE:
@@ -307,7 +366,7 @@ class PretrainedCLIPBase(nn.Module):
             raise KeyError(f"unknown residual_activation {name!r}")
         act, scale = RESIDUAL_ACTIVATIONS[name]
         if name in NEEDS_STATE:
-            if self.training and "finaltf" not in getattr(self, "branch_to_freeze", ""):
+            if self.training and "finaltf" not in (getattr(self, "branch_to_freeze", "") or ""):
                 raise NotImplementedError(
                     f"residual_activation={name!r} in training mode updates batch statistics "
                     "(model/model.py:41-60); only the eval-mode form is built")
@@ -443,18 +502,25 @@ class PretrainedCLIPBase(nn.Module):
 class PretrainedCLIP(PretrainedCLIPBase):
     """model/model.py:308-371 with the backbone made pluggable."""
 
-    def __init__(self, feature_dim: int = 512, backbone=None, residual_activation=None,
-                 comment_fusion=None, logit_scale_init: float = math.log(1 / 0.07),
-                 precision: str = "exact", lazy_sim: bool = True):
+    def __init__(self, model_type="ViT-B/32", freeze=False, residual_activation=None,
+                 comment_fusion=None, *, feature_dim: Optional[int] = None, backbone=None,
+                 logit_scale_init: float = math.log(1 / 0.07), precision: str = "exact",
+                 lazy_sim: bool = True):
+        """Positional / keyword arguments as the reference's (model/model.py:309-324), so that
+        `config.init_obj("arch", module_arch)` works with its configs; `model_type` may also be an
+        int = the embedding width.  Keyword-only extras: `backbone` (an object with encode_image /
+        encode_text / logit_scale; None = precomputed features in), `feature_dim`, `precision`."""
         super().__init__()
         self.model = backbone
-        self.feature_dim = feature_dim
+        self.feature_dim = self._resolve_feature_dim(model_type, feature_dim, backbone)
         self.residual_activation = residual_activation
         self.comment_fusion = comment_fusion
         self.precision = precision
         self.lazy_sim = lazy_sim
+        self._common_init()
         if backbone is None or not hasattr(backbone, "logit_scale"):
             self.logit_scale = nn.Parameter(torch.ones([]) * logit_scale_init)
+        self._freeze(freeze)
 
     def forward(self, vis, title, comments=None):
         feats_vis, feats_title = self._features(vis, title)
@@ -474,13 +540,22 @@ class PretrainedCLIP(PretrainedCLIPBase):
 class PretrainedCLIP_finaltf(PretrainedCLIPBase):
     """model/model.py:374-480 with the backbone made pluggable (audio branch out of scope)."""
 
-    def __init__(self, feature_dim: int = 512, backbone=None, branch_to_adapt="text",
+    def __init__(self, model_type="ViT-B/32", freeze=False, branch_to_adapt="text",
                  branch_to_adapt_val="text", residual_activation=None, n_layers=2, n_heads=8,
                  init_from_avg=True, random_comment_masking=False, random_skip_adapter=True,
+                 init_audio_model=False, audio_model_ckpt=None, clip_audio_ckpt=None, *,
+                 feature_dim: Optional[int] = None, backbone=None,
                  logit_scale_init: float = math.log(1 / 0.07), precision: str = "exact",
                  lazy_sim: bool = True):
+        """Positional / keyword arguments as the reference's (model/model.py:375-390), so that its
+        configs construct this class unchanged (configs/pretrained_clip_comments_attention.jsonc:
+        7-17); `model_type` may also be an int = the embedding width.  Keyword-only extras as in
+        PretrainedCLIP."""
         super().__init__()
+        if init_audio_model or audio_model_ckpt or clip_audio_ckpt:
+            raise NotImplementedError("the audio branch (model/model.py:405-437) is out of scope")
         self.model = backbone
+        feature_dim = self._resolve_feature_dim(model_type, feature_dim, backbone)
         self.feature_dim = feature_dim
         self.final_transformer = CAMTransformer(feature_dim, int(n_layers), int(n_heads), precision)
         self.final_linear = nn.Linear(feature_dim, feature_dim, bias=False)
@@ -493,7 +568,6 @@ class PretrainedCLIP_finaltf(PretrainedCLIPBase):
         self.random_skip_adapter = random_skip_adapter
         self.precision = precision
         self.lazy_sim = lazy_sim
-        self.branch_to_freeze = ""
         self._common_init()
         if backbone is None or not hasattr(backbone, "logit_scale"):
             self.logit_scale = nn.Parameter(torch.ones([]) * logit_scale_init)
@@ -503,6 +577,7 @@ class PretrainedCLIP_finaltf(PretrainedCLIPBase):
                 blk.mlp.c_proj.bias.data.zero_()
                 blk.attn.out_proj.weight.data.zero_()
         nn.init.constant_(self.final_linear.weight, 0.0)                         # :452
+        self._freeze(freeze)                                                     # :454
 
     def forward(self, vis, title, comments):
         feats_vis, feats_title = self._features(vis, title)
