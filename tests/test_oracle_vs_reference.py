@@ -95,3 +95,41 @@ def test_encode_with_comments_routing_matches_reference():
         else:
             torch.testing.assert_close(fv, O.normalize(vis))
             torch.testing.assert_close(ft, O.normalize(main))
+
+
+def test_constructor_and_call_signatures_match_the_reference():
+    """The drop-in boundary is name lookup + keyword construction (train.py:67,85-89): the
+    reference's parameter names must be accepted, in the reference's order, by the product."""
+    import inspect
+
+    from vtc_b200.evaluation import retrieval_evaluation as our_reval
+    from vtc_b200.model import loss as our_loss
+    from vtc_b200.model import metric as our_metric
+    from vtc_b200.model import model as our_model
+
+    ref_model, ref_metric = RS.ref_model_module(), RS.ref_metric_module()
+    ref_loss, ref_reval = RS.ref_loss_module(), RS.ref_retrieval_evaluation_module()
+
+    def leading(fn):
+        return [p.name for p in inspect.signature(fn).parameters.values()
+                if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+
+    def defaults(fn):
+        return {p.name: p.default for p in inspect.signature(fn).parameters.values()
+                if p.default is not p.empty}
+
+    for cls in ("PretrainedCLIP", "PretrainedCLIP_finaltf"):
+        ref, ours = getattr(ref_model, cls).__init__, getattr(our_model, cls).__init__
+        assert leading(ours)[:len(leading(ref))] == leading(ref), cls
+        rd, od = defaults(ref), defaults(ours)
+        assert all(od[k] == v for k, v in rd.items()), cls
+        assert leading(getattr(our_model, cls).forward) == leading(getattr(ref_model, cls).forward), cls
+    for name in ("_adapt_feature", "_encode_with_comments"):
+        ours_m, ref_m = getattr(our_model.PretrainedCLIPBase, name), getattr(ref_model.PretrainedCLIPBase, name)
+        assert leading(ours_m) == leading(ref_m), name
+    assert leading(our_metric.RecallAtK.__init__)[:4] == leading(ref_metric.RecallAtK.__init__)
+    for meth in ("update", "compute", "reset", "result", "avg", "set_writer"):
+        assert leading(getattr(our_metric.RecallAtK, meth)) == leading(getattr(ref_metric.RecallAtK, meth)), meth
+    assert leading(our_loss.clip_loss)[:2] == leading(ref_loss.clip_loss)
+    assert leading(our_reval.compute_recall)[:4] == leading(ref_reval.compute_recall)
+    assert defaults(ref_reval.compute_recall).items() <= defaults(our_reval.compute_recall).items()
