@@ -188,3 +188,11 @@ def test_models_construct_from_the_reference_config_args():
     assert p.feature_dim == 512 and p.comment_fusion == "averaging"
     with pytest.raises(ValueError):
         PretrainedCLIP("no-such-clip")
+    # the TimeSformer variants share the hot path; their towers come in as `backbone`
+    from vtc_b200.model.model import PretrainedCLIP_TimeSformer, PretrainedCLIP_TimeSformer_finaltf
+
+    t = PretrainedCLIP_TimeSformer_finaltf(model_type="ViT-B/32", freeze=False, visual_device=None,
+                                           n_layers=2, n_heads=8)     # configs/..timesformer..jsonc
+    assert t.feature_dim == 512 and t.multigpu is False
+    assert {n for n, _ in t.named_parameters()} == {n for n, _ in m.named_parameters()}
+    assert PretrainedCLIP_TimeSformer("ViT-B/32").comment_fusion is None

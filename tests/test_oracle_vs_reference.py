@@ -118,7 +118,8 @@ def test_constructor_and_call_signatures_match_the_reference():
         return {p.name: p.default for p in inspect.signature(fn).parameters.values()
                 if p.default is not p.empty}
 
-    for cls in ("PretrainedCLIP", "PretrainedCLIP_finaltf"):
+    for cls in ("PretrainedCLIP", "PretrainedCLIP_finaltf", "PretrainedCLIP_TimeSformer",
+                "PretrainedCLIP_TimeSformer_finaltf"):
         ref, ours = getattr(ref_model, cls).__init__, getattr(our_model, cls).__init__
         assert leading(ours)[:len(leading(ref))] == leading(ref), cls
         rd, od = defaults(ref), defaults(ours)

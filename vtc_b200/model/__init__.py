@@ -2,4 +2,5 @@ from .lazy import LazySim  # noqa: F401
 from .loss import clip_loss  # noqa: F401
 from .metric import MetricTracker, RecallAtK  # noqa: F401
 from .model import (CAMTransformer, PretrainedCLIP, PretrainedCLIP_finaltf,  # noqa: F401
+                    PretrainedCLIP_TimeSformer, PretrainedCLIP_TimeSformer_finaltf,
                     PretrainedCLIPBase, normalize)

@@ -32,6 +32,8 @@ __all__ = [
     "PretrainedCLIPBase",
     "PretrainedCLIP",
     "PretrainedCLIP_finaltf",
+    "PretrainedCLIP_TimeSformer",
+    "PretrainedCLIP_TimeSformer_finaltf",
     "RESIDUAL_ACTIVATIONS",
 ]
 
@@ -585,3 +587,70 @@ class PretrainedCLIP_finaltf(PretrainedCLIPBase):
                                                            comments)
         sim = LazySim(feats_vis, feats_text, self._logit_scale_exp(feats_vis.device), self.precision)
         return feats_vis, feats_text, (sim if self.lazy_sim else sim.materialize())
+
+
+class _TimeSformerFeatures:
+    """Feature extraction of the reference's TimeSformer variants (model/model.py:494-498,
+    598-613): the visual tower is `self.model.visual` applied to the whole [b, t, c, h, w] clip
+    (not per-frame `encode_image`), optionally living on its own device.  The tower itself
+    (model/timesformer_clip_alt.py) is a backbone and out of scope: it comes in as `backbone`."""
+
+    def _features(self, vis, title):
+        shp = vis.shape
+        if len(shp) == 2 and shp[1] == self.feature_dim:
+            feats_vis = vis                                                      # precomputed
+        else:
+            if getattr(self, "model", None) is None:
+                raise ops.VtcError("raw clips need a backbone with a `visual` tower")
+            vdev = getattr(self, "visual_device", None)
+            if vdev is not None:                                                 # :598-609
+                if getattr(self, "text_device", None) is None:
+                    self.text_device = title.device
+                    self.model.visual.to(vdev)
+                feats_vis = self.model.visual(vis.to(vdev)).to(self.text_device)
+            else:
+                feats_vis = self.model.visual(vis)
+        if title.dim() == 2 and title.dtype.is_floating_point and title.shape[1] == self.feature_dim:
+            feats_title = title
+        else:
+            if getattr(self, "model", None) is None:
+                raise ops.VtcError("token-id titles need a backbone with encode_text")
+            feats_title = self.model.encode_text(title)
+        return feats_vis, feats_title
+
+
+class PretrainedCLIP_TimeSformer(_TimeSformerFeatures, PretrainedCLIP):
+    """model/model.py:483-507: normalise both towers' features, similarity -- the hot path of
+    PretrainedCLIP without comment fusion."""
+
+    def __init__(self, model_type="ViT-B/32", freeze=False, residual_activation=None, *,
+                 feature_dim: Optional[int] = None, backbone=None,
+                 logit_scale_init: float = math.log(1 / 0.07), precision: str = "exact",
+                 lazy_sim: bool = True):
+        super().__init__(model_type, freeze, residual_activation, None, feature_dim=feature_dim,
+                         backbone=backbone, logit_scale_init=logit_scale_init, precision=precision,
+                         lazy_sim=lazy_sim)
+
+    def forward(self, im, text, comments=None):
+        return super().forward(im, text, None)           # comments are ignored (:494-507)
+
+
+class PretrainedCLIP_TimeSformer_finaltf(_TimeSformerFeatures, PretrainedCLIP_finaltf):
+    """model/model.py:537-621: the CAM over a TimeSformer visual tower; `visual_device` places
+    that tower on a second GPU as the reference does (:588-609)."""
+
+    def __init__(self, model_type="ViT-B/32", freeze=False, branch_to_adapt="text",
+                 branch_to_adapt_val="text", residual_activation=None, visual_device=None,
+                 n_layers=2, n_heads=8, init_from_avg=True, random_comment_masking=False,
+                 random_skip_adapter=True, *, feature_dim: Optional[int] = None, backbone=None,
+                 logit_scale_init: float = math.log(1 / 0.07), precision: str = "exact",
+                 lazy_sim: bool = True):
+        super().__init__(model_type, freeze, branch_to_adapt, branch_to_adapt_val,
+                         residual_activation, n_layers, n_heads, init_from_avg,
+                         random_comment_masking, random_skip_adapter, feature_dim=feature_dim,
+                         backbone=backbone, logit_scale_init=logit_scale_init, precision=precision,
+                         lazy_sim=lazy_sim)
+        self.multigpu = visual_device is not None
+        if self.multigpu:
+            self.visual_device = torch.device(visual_device)
+            self.text_device = None
