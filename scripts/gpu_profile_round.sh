@@ -30,6 +30,10 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches_topk.csv python scripts/topk_once.py \
     > gpurun_out/${TAG}_ncu_launches_topk.log 2>&1
 echo "ncu topk launches exit=$?" >> $S
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/${TAG}_launches_cam.csv python scripts/cam_once.py \
+    > gpurun_out/${TAG}_ncu_launches_cam.log 2>&1
+echo "ncu cam launches exit=$?" >> $S
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e \
     > gpurun_out/${TAG}_ncu_launches.log 2>&1
