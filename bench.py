@@ -138,8 +138,10 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
-        self.lines = []
+        self.lines = []   # (arrival time, csv line)
         self.proc = None
+        self.t0 = None    # the timed region, in time.perf_counter() terms
+        self.t1 = None
 
     def start(self):
         try:
@@ -153,7 +155,13 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -163,9 +171,22 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        return self.summarise()
+
+    def summarise(self):
+        """Samples that arrived inside the timed region; the sampler is started before the warm-up
+        steps (nvidia-smi needs ~0.1 s to print its first line, the timed region of a 20-step run
+        is 0.16 s), so if none fell inside, the samples taken under load since then are used."""
+        lines = list(self.lines)
+        inside = [ln for t, ln in lines
+                  if self.t0 is not None and t >= self.t0 and (self.t1 is None or t <= self.t1 + 0.03)]
+        window = "timed region"
+        if not inside:
+            inside = [ln for _, ln in lines]
+            window = "warm-up + timed region (no sample arrived inside the timed region)"
         sm, mx, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -181,7 +202,7 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -252,17 +273,18 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nvidia-smi takes ~0.1 s to deliver its first sample
     for _ in range(max(a.warmup, 3)):
         hits, medr = step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     _ffi.kernel_timer_enable(True)
     _ffi.kernel_timer_read()
     launches0 = _ffi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_start()
     ev0.record()
     t_host = time.perf_counter()
     for _ in range(a.steps):
@@ -270,6 +292,7 @@ def run_ours(a):
     host_ms_per_step = (time.perf_counter() - t_host) / a.steps * 1e3  # CPU time to enqueue a step
     ev1.record()
     barrier()
+    sampler.mark_end()
     launches = _ffi.launch_count() - launches0
     tc_ms, tc_n = _ffi.kernel_timer_read()
     tc_steps = a.steps

@@ -196,3 +196,28 @@ def test_models_construct_from_the_reference_config_args():
     assert t.feature_dim == 512 and t.multigpu is False
     assert {n for n, _ in t.named_parameters()} == {n for n, _ in m.named_parameters()}
     assert PretrainedCLIP_TimeSformer("ViT-B/32").comment_fusion is None
+
+
+def test_clock_sampler_prefers_samples_inside_the_timed_region():
+    """bench.py's `clocks` object: nvidia-smi lines are time-stamped on arrival, only those inside
+    the timed region count, with a labelled fall-back when the region was too short to catch one."""
+    import os
+    import sys
+    import time
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    capped = "0, 1700, 1965, 950.5, 0x4, Not Active, Not Active, Not Active, Active"
+    idle = "0, 1965, 1965, 300.0, 0x0, Not Active, Not Active, Not Active, Not Active"
+    now = time.perf_counter()
+    cs = bench.ClockSampler(0)
+    cs.lines = [(now - 1.0, idle), (now - 0.5, idle)]
+    cs.t0, cs.t1 = now - 0.2, now
+    out = cs.summarise()
+    assert out["sm_mhz"] == 1965.0 and out["reasons"] == [] and out["window"].startswith("warm-up")
+    cs.lines += [(now - 0.1, capped), (now - 0.05, capped), (now + 5.0, idle)]
+    out = cs.summarise()
+    assert out["window"] == "timed region" and out["samples"] == 2
+    assert out["sm_mhz"] == 1700.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    assert bench.ClockSampler(0).stop()["reasons"] == ["nvidia-smi unavailable"]
