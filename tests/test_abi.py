@@ -101,3 +101,39 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "vtc_oracle" not in src.replace("oracle/vtc_oracle", ""), f
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/vtc_b200.h must compile as C11 (no torch / C++ types) and a
+    plain C translation unit must link against libvtc_b200.so and call it."""
+    import shutil
+    import subprocess
+
+    from vtc_b200 import build as vbuild
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "vtc_b200.h")], check=True)
+    lib = vbuild.build()
+    src = tmp_path / "abi.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include "vtc_b200.h"
+int main(void) {
+  size_t ws = vtc_workspace_bytes(VTC_OP_SIM_RANK, 1000, 1000, 512, VTC_PREC_BF16);
+  printf("%d %zu %s\n", vtc_abi_version(), ws, vtc_strerror(VTC_ERR_INVALID_ARG));
+  /* argument validation happens before any CUDA call: no GPU needed */
+  return vtc_sim_rank(0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) == VTC_ERR_INVALID_ARG ? 0 : 1;
+}
+""")
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c11", "-I", inc, str(src), "-o", str(exe), lib,
+                    "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ver, ws, msg = r.stdout.split(None, 2)
+    assert int(ver) >= 1 and int(ws) > 0 and "invalid" in msg
