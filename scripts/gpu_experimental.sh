@@ -1,0 +1,28 @@
+#!/bin/bash
+# First GPU call of a round that inherits opt-in kernel variants (DESIGN.md §8 "pending
+# validation"): parity of every variant against the oracle, then the headline bench with and
+# without it on the SAME box (boxes differ in how hard sw_power_cap bites), plus the shapes where the
+# variant should matter most.  usage: gpu_experimental.sh [tag]; ~6 GPU-minutes.
+set -u
+TAG=${1:-exp}
+mkdir -p gpurun_out
+S=gpurun_out/summary_$TAG.txt
+: > $S
+VTC_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -m gpu -q --tb=short \
+    --maxfail=8 > gpurun_out/${TAG}_pytest.log 2>&1
+echo "experimental parity exit=$?" >> $S; tail -n 12 gpurun_out/${TAG}_pytest.log >> $S
+for fold in 0 1; do
+  for args in "" "--d 256" "--d 768" "--precision exact"; do
+    name=$(echo "fold${fold}${args}" | tr -d ' -')
+    VTC_RANK_FOLD=$fold timeout 200 python bench.py --steps 10 --no-cpu-baseline $args \
+        > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
+    echo "bench fold=$fold $args exit=$?" >> $S
+  done
+done
+python scripts/show_bench.py gpurun_out/${TAG}_fold*.json 2>&1 | cut -c1-200 >> $S
+# SASS-level proof of what the fold epilogue issues per logit goes with the ncu capture of the round
+VTC_RANK_FOLD=1 timeout 600 ncu --set full --clock-control none --import-source on \
+    -k regex:sim_tc_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof_rank_fold -f \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_fold.log 2>&1
+echo "ncu fold exit=$?" >> $S
+cat $S

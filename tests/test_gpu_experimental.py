@@ -1,0 +1,150 @@
+"""Parity tests of the OPT-IN kernel variants that have been written but not yet run on a B200
+(DESIGN.md §8 "pending validation").  They are skipped unless VTC_TEST_EXPERIMENTAL=1, so that the
+default `pytest -m gpu` run only exercises code that has been measured; the first GPU call of the next
+round is `VTC_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q`
+(scripts/gpu_experimental.sh), after which a variant is either made the default or removed.
+
+VTC_RANK_FOLD=1 -- EPI_RANK_FOLD (csrc/fold.cu, RankFoldEpi in csrc/sim_tc_kernel.cuh): the
+per-column bias and the per-row ground-truth score enter the accumulator through one extra K16 MMA
+step, the epilogue counts sign bits.  Same contract as the default path: ranks bit-exact against the
+fp64-sequential oracle (replacing the faiss search + hit loop of model/metric.py:137-161).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vtc_oracle as O
+from vtc_b200.synthetic import make_retrieval_pair
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("VTC_TEST_EXPERIMENTAL") != "1",
+                       reason="opt-in variants: set VTC_TEST_EXPERIMENTAL=1"),
+]
+
+METRICS = {"l2": O.METRIC_L2, "dot": O.METRIC_DOT}
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _oracle_ranks(Q, G, metric, precision, gt=None, row_offset=0):
+    if precision == "bf16":
+        Q, G = O.bf16_round(Q), O.bf16_round(G)
+    return O.rank0_exact(Q, G, gt=gt, metric=METRICS[metric], row_offset=row_offset)
+
+
+@pytest.fixture
+def fold(monkeypatch):
+    monkeypatch.setenv("VTC_RANK_FOLD", "1")  # read by the library on every vtc_sim_rank call
+
+
+# resident query tile (K' <= 512) and streamed (D = 768; every exact-mode K' = 3D), ragged edges
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+@pytest.mark.parametrize("metric", ["l2", "dot"])
+@pytest.mark.parametrize("N,M,D,sigma", [(1000, 1000, 512, 6.0), (333, 1201, 96, 2.0),
+                                         (129, 257, 768, 7.0), (300, 3000, 64, 1.5),
+                                         (2000, 5000, 256, 5.0)])
+def test_fold_rank_bit_exact(cuda_dev, fold, precision, metric, N, M, D, sigma):
+    from vtc_b200 import ops
+
+    T, V = make_retrieval_pair(min(N, M), M, D, sigma=sigma, seed=N + M)
+    T = T[:N].contiguous()
+    rank0, gts = ops.sim_rank(T.to(cuda_dev), V.to(cuda_dev), metric=metric, precision=precision)
+    hits, medr = ops.rank_finalize(rank0, gts, M, [1, 5, 10])
+    want = _oracle_ranks(T, V, metric, precision)
+    np.testing.assert_array_equal(_np(rank0), want)
+    np.testing.assert_array_equal(_np(hits), [np.sum(want < k) for k in (1, 5, 10)])
+    assert _np(medr)[0] == O.medr(want)
+
+
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+def test_fold_same_ranks_as_default_path(cuda_dev, monkeypatch, precision):
+    """Mixed-difficulty queries, shuffled gallery (explicit gt), non-unit gallery rows."""
+    from vtc_b200 import ops
+
+    T, V = make_retrieval_pair(1500, 2500, 512, seed=11, mixed=True)
+    V = V * (0.5 + torch.rand(2500, 1, generator=torch.Generator().manual_seed(5)))  # norms 0.5..1.5
+    perm = torch.randperm(2500, generator=torch.Generator().manual_seed(3))
+    Vp = V[perm].contiguous()
+    inv = torch.empty(2500, dtype=torch.int64)
+    inv[perm] = torch.arange(2500)
+    gt = inv[:1500].contiguous()
+    q, g, gtd = T.to(cuda_dev), Vp.to(cuda_dev), gt.to(cuda_dev)
+    monkeypatch.delenv("VTC_RANK_FOLD", raising=False)
+    base, _ = ops.sim_rank(q, g, gt=gtd, precision=precision)
+    monkeypatch.setenv("VTC_RANK_FOLD", "1")
+    got, _ = ops.sim_rank(q, g, gt=gtd, precision=precision)
+    np.testing.assert_array_equal(_np(got), _np(base))
+    np.testing.assert_array_equal(_np(got), _oracle_ranks(T, Vp, "l2", precision, gt=gt.numpy()))
+
+
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+def test_fold_adversarial_golden(cuda_dev, fold, golden, precision):
+    """Duplicated gallery rows (exact ties), a zero row, a non-unit row, a NaN query."""
+    from vtc_b200 import ops
+
+    g = golden("retrieval_small.npz")
+    Q, G = torch.from_numpy(g["queries"]), torch.from_numpy(g["gallery"])
+    for metric, key in (("l2", "rank0"), ("dot", "rank0_dot")):
+        rank0, gts = ops.sim_rank(Q.to(cuda_dev), G.to(cuda_dev), metric=metric, precision=precision)
+        ops.rank_finalize(rank0, gts, G.shape[0], [1])
+        want = _oracle_ranks(Q, G, metric, precision) if precision == "bf16" else g[key]
+        np.testing.assert_array_equal(_np(rank0), want)
+
+
+def test_fold_duplicates_nan_gallery_row_and_chunks(cuda_dev, fold):
+    from vtc_b200 import ops
+
+    # every pair ties: everything goes through the re-check list
+    row = torch.randn(1, 128)
+    G = row.repeat(600, 1).contiguous()
+    Q = row.repeat(400, 1).contiguous()
+    for precision in ("exact", "bf16"):
+        rank0, _ = ops.sim_rank(Q.to(cuda_dev), G.to(cuda_dev), precision=precision)
+        np.testing.assert_array_equal(_np(rank0), np.arange(400))
+    # a gallery row with a NaN / an inf element: the fold operands cannot carry it, the call must
+    # fall back to the canonical brute-force kernel and still agree with the oracle
+    T, V = make_retrieval_pair(300, 900, 256, sigma=3.0, seed=8)
+    V[17, 5] = float("nan")
+    V[400, 0] = float("inf")
+    for precision in ("exact", "bf16"):
+        rank0, gts = ops.sim_rank(T.to(cuda_dev), V.to(cuda_dev), precision=precision)
+        ops.rank_finalize(rank0, gts, 900, [1])
+        np.testing.assert_array_equal(_np(rank0), _oracle_ranks(T, V, "l2", precision))
+    # additive over gallery chunks (ground truth outside the chunk, col_offset, accumulate)
+    T, V = make_retrieval_pair(500, 2000, 256, sigma=4.0, seed=21)
+    q, g = T.to(cuda_dev), V.to(cuda_dev)
+    for precision in ("exact", "bf16"):
+        whole, gts = ops.sim_rank(q, g, precision=precision)
+        acc = torch.zeros(500, dtype=torch.int32, device=cuda_dev)
+        bounds = [0, 700, 701, 1500, 2000]
+        for s, e in zip(bounds[:-1], bounds[1:]):
+            ops.sim_rank(q, g[s:e].contiguous(), col_offset=s, precision=precision, gt_score=gts,
+                         rank0=acc, accumulate=True)
+        np.testing.assert_array_equal(_np(acc), _np(whole))
+        np.testing.assert_array_equal(_np(whole), _oracle_ranks(T, V, "l2", precision))
+
+
+def test_fold_10k_and_100k_slice(cuda_dev, fold):
+    from vtc_b200 import ops
+
+    T, V = make_retrieval_pair(10000, 10000, 512, seed=1023)
+    q, g = T.to(cuda_dev), V.to(cuda_dev)
+    for precision in ("exact", "bf16"):
+        rank0, _ = ops.sim_rank(q, g, precision=precision)
+        np.testing.assert_array_equal(_np(rank0), _oracle_ranks(T, V, "l2", precision))
+    N = M = 100_000
+    T, V = make_retrieval_pair(N, M, 512, seed=1023)
+    q, g = T.to(cuda_dev), V.to(cuda_dev)
+    rank_bf16, gts = ops.sim_rank(q, g, precision="bf16")
+    sl = slice(50_000, 50_256)
+    want = _oracle_ranks(T[sl], V, "l2", "bf16", row_offset=50_000)
+    np.testing.assert_array_equal(_np(rank_bf16[sl]), want)
+    os.environ.pop("VTC_RANK_FOLD")
+    base, _ = ops.sim_rank(q, g, precision="bf16")
+    os.environ["VTC_RANK_FOLD"] = "1"
+    np.testing.assert_array_equal(_np(rank_bf16), _np(base))

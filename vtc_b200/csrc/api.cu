@@ -7,6 +7,7 @@
 
 #include "cam.cuh"
 #include "exact.cuh"
+#include "fold.cuh"
 #include "prep.cuh"
 #include "reduce.cuh"
 #include "sim_tc.cuh"
@@ -73,9 +74,18 @@ struct RankWs {
   unsigned int* scalars;  // [0] max_sq_bits, [2] overflow, [64..] per-CTA list segment counts
   float2* thr;
   int* rank_tmp;
+  __nv_bfloat16 *foldQ, *foldG;  // EPI_RANK_FOLD operands [N, 64], [round_up(M, 256), 64]
+  float* foldW;                  // [N] guard band around acc' = 0
   int2* amb;
   size_t amb_cap;
 };
+
+// EPI_RANK_FOLD (bias and ground-truth score folded into the MMA, sign-bit epilogue) is opt-in
+// until it has been validated and measured on a B200: VTC_RANK_FOLD=1.
+bool rank_fold_enabled() {
+  const char* e = getenv("VTC_RANK_FOLD");
+  return e && *e && atoi(e) != 0;
+}
 
 size_t amb_entries_wanted(int64_t N) {
   const int64_t want = 64 * N;
@@ -96,6 +106,9 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
     r.sq32 = ws.take<float>(round_up<int64_t>(M, tc::BN));
     r.thr = ws.take<float2>(N);
     r.rank_tmp = ws.take<int>(N);
+    r.foldQ = ws.take<__nv_bfloat16>((size_t)N * FOLD_COLS);
+    r.foldG = ws.take<__nv_bfloat16>((size_t)round_up<int64_t>(M, tc::BN) * FOLD_COLS);
+    r.foldW = ws.take<float>(N);
     if (sizing) {
       r.amb_cap = amb_entries_wanted(N);
       ws.take<int2>(r.amb_cap);
@@ -187,13 +200,29 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
   p.thr = w.thr, p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_seg_count = &w.scalars[64];
-  const tc::Plan pl = tc::plan_tiles(p, 64, tc::choose_cluster(N, M));
+  tc::Plan pl = tc::plan_tiles(p, 64, tc::choose_cluster(N, M));
   if (pl.grid > 256) return VTC_ERR_UNSUPPORTED_SHAPE;
   p.amb_seg_cap = (unsigned int)(w.amb_cap / (size_t)pl.grid);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
-  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
+  if (rank_fold_enabled() && pl.cluster == 2 && w.foldQ && w.foldG && w.foldW) {
+    // fold pass: the bias and d(t,gt) enter through one extra K16 step (fold.cu); always a CTA pair
+    const int64_t Mpad = round_up<int64_t>(M, tc::BN);
+    VTC_RETURN_IF_ERROR(launch_fold_g(w.sq64, M, Mpad, metric, w.foldG, &w.scalars[2], s));
+    VTC_RETURN_IF_ERROR(launch_fold_q(w.thr, w.dgt, &w.scalars[0], N, metric,
+                                      guard_rel_for(precision, o.Kp), w.foldQ, w.foldW, s));
+    CUtensorMap tmAx, tmBx;
+    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.foldQ, N, FOLD_COLS, FOLD_COLS, tc::BM, &tmAx));
+    VTC_RETURN_IF_ERROR(
+        tc::make_operand_tmap(w.foldG, Mpad, FOLD_COLS, FOLD_COLS, tc::BN / 2, &tmBx));
+    p.fold_w = w.foldW;
+    pl.pair = true;
+    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK_FOLD, p.num_kb <= 8, pl, tmA, tmB, p, s,
+                                          &tmAx, &tmBx));
+  } else {
+    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
+  }
   // 4. exact re-check of the guard-band pairs; brute force if the list overflowed
   VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[64], pl.grid, p.amb_seg_cap, w.dgt,
                                      w.rank_tmp, &w.scalars[2], s));

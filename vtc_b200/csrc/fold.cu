@@ -1,0 +1,113 @@
+// fold.cu -- builds the fold operands of the EPI_RANK_FOLD pass (opt-in, VTC_RANK_FOLD=1).
+//
+// RankEpi spends FFMA + 2 FSET + 2 FADD per logit on "scale * acc + ||x_j||^2, compare with the two
+// guard-band thresholds of row t" (model/metric.py:144-160 is the faiss search + hit loop this
+// replaces).  Both the per-column term and the per-row term are rank-1, so they can ride in the
+// MMA: with
+//     Qx[t] = [ m'_t | 1 ],  Gx[j] = [ 1 | h_j ]      (each scalar as three bf16 pieces = 24 bits)
+// one extra K16 step makes the accumulator acc' = q.x + h_j + m'_t, and
+//     L2 : h_j = -||x_j||^2 / 2, m'_t = d(t,gt) / 2   =>  d(t,j) < d(t,gt)  <=>  acc' > 0
+//     DOT: h_j = 0,              m'_t = d(t,gt)       =>  -q.x   < d(t,gt)  <=>  acc' > 0
+// The decision that matters is still taken in canonical fp64 arithmetic: |acc'| <= w_t sends the
+// column group to the same re-check as before.
+#include "fold.cuh"
+
+namespace vtc {
+namespace {
+
+// v ~ p[0] + p[1] + p[2], each a bf16; the remainder is below 2^-24 |v|
+__device__ __forceinline__ void split3(double v, unsigned short (&p)[3]) {
+  double rem = v;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const __nv_bfloat16 b = __float2bfloat16_rn((float)rem);
+    p[i] = __bfloat16_as_ushort(b);
+    rem -= (double)__bfloat162float(b);
+  }
+}
+
+constexpr unsigned short kOne = 0x3f80;  // bf16 1.0
+constexpr double kFar = -1.0e30;         // "never closer, never in the band"
+
+__device__ __forceinline__ void store_fold_row(__nv_bfloat16* row, const unsigned short (&e)[6]) {
+  uint4* o = reinterpret_cast<uint4*>(row);
+  o[0] = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16),
+                    (uint32_t)e[4] | ((uint32_t)e[5] << 16), 0u);
+#pragma unroll
+  for (int i = 1; i < FOLD_COLS / 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void fold_q_kernel(const float2* __restrict__ thr, const double* __restrict__ dgt,
+                              const unsigned int* __restrict__ max_sq_bits, int64_t N, int metric,
+                              float guard_rel, __nv_bfloat16* __restrict__ Qx,
+                              float* __restrict__ fold_w) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  const float2 th = thr[t];
+  const double d0 = dgt[t];
+  double m = kFar;
+  float w = -1.f;
+  if (d0 == d0 && fabs(d0) < 1.0e30 && th.x == th.x && th.y == th.y) {
+    // (hi - lo) / 2 >= the delta RankEpi's thresholds were built from (they are rounded outwards)
+    const double delta = 0.5 * ((double)th.y - (double)th.x);
+    const double gmax_sq = (double)__uint_as_float(*max_sq_bits);
+    double wd;
+    if (metric == VTC_METRIC_L2) {
+      m = 0.5 * d0;
+      // delta >= 2 g |q| max|x|; the fold step adds three more products per scalar to an
+      // accumulator whose magnitude is bounded by S: 8 ulp (2^-24 each) of slack on top
+      const double S = delta / (2.0 * (double)guard_rel) + 0.5 * gmax_sq + fabs(m);
+      wd = 0.5 * delta + 4.8e-7 * S;
+    } else {
+      m = d0;
+      const double S = delta / (double)guard_rel + fabs(m);
+      wd = delta + 4.8e-7 * S;
+    }
+    w = __double2float_ru(wd * (1.0 + 1.0e-6));
+  }
+  unsigned short p[3];
+  split3(m, p);
+  const unsigned short e[6] = {p[0], p[1], p[2], kOne, kOne, kOne};
+  store_fold_row(Qx + t * FOLD_COLS, e);
+  fold_w[t] = w;
+}
+
+__global__ void fold_g_kernel(const double* __restrict__ sq64, int64_t M, int64_t Mpad, int metric,
+                              __nv_bfloat16* __restrict__ Gx, unsigned int* __restrict__ invalid) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Mpad) return;
+  double h = kFar;
+  if (j < M) {
+    const double sq = sq64[j];
+    if (fabs(sq) < 1.0e30)  // false for NaN and inf
+      h = metric == VTC_METRIC_L2 ? -0.5 * sq : 0.0;
+    else
+      *invalid = 1u;
+  }
+  unsigned short p[3];
+  split3(h, p);
+  const unsigned short e[6] = {kOne, kOne, kOne, p[0], p[1], p[2]};
+  store_fold_row(Gx + j * FOLD_COLS, e);
+}
+
+}  // namespace
+
+int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_sq_bits, int64_t N,
+                  int metric, float guard_rel, __nv_bfloat16* Qx, float* fold_w, cudaStream_t s) {
+  if (N == 0) return VTC_OK;
+  fold_q_kernel<<<(unsigned)ceil_div<int64_t>(N, 128), 128, 0, s>>>(thr, dgt, max_sq_bits, N, metric,
+                                                                  guard_rel, Qx, fold_w);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_fold_g(const double* sq64, int64_t M, int64_t Mpad, int metric, __nv_bfloat16* Gx,
+                  unsigned int* invalid, cudaStream_t s) {
+  if (Mpad == 0) return VTC_OK;
+  fold_g_kernel<<<(unsigned)ceil_div<int64_t>(Mpad, 128), 128, 0, s>>>(sq64, M, Mpad, metric, Gx,
+                                                                     invalid);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+}  // namespace vtc

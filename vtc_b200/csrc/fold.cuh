@@ -1,0 +1,25 @@
+// fold.cuh -- operands of the EPI_RANK_FOLD tensor-core pass (fold.cu; see RankFoldEpi in
+// sim_tc_kernel.cuh): the per-column bias and the per-row ground-truth score as one extra K16 step
+// of the MMA.
+#pragma once
+#include "common.cuh"
+
+namespace vtc {
+
+constexpr int FOLD_COLS = 64;  // bf16 per fold-operand row: one 128-byte swizzle atom, like a k-block
+
+// Qx [N, 64] bf16 = [ m'_t (three bf16 pieces) | 1 1 1 | 0 ... ] and fold_w [N]: half-width of the
+// guard band around acc' = 0, derived from the (lo, hi) thresholds and d(t,gt) that
+// launch_gt_score produced.  Rows whose ground-truth score is NaN get m' = -1e30, w = -1 (they count
+// nothing and never push; vtc_rank_finalize gives them rank M).
+int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_sq_bits, int64_t N,
+                  int metric, float guard_rel, __nv_bfloat16* Qx, float* fold_w, cudaStream_t s);
+
+// Gx [Mpad, 64] bf16 = [ 1 1 1 | h_j (three bf16 pieces) | 0 ... ], h_j = -||x_j||^2 / 2 (L2) or 0
+// (DOT); padding rows j >= M carry h = -1e30 (never closer, never inside the band).  A gallery row
+// whose squared norm is not finite sets *invalid = 1: the caller's brute-force fallback then
+// recomputes the whole call in canonical arithmetic.
+int launch_fold_g(const double* sq64, int64_t M, int64_t Mpad, int metric, __nv_bfloat16* Gx,
+                  unsigned int* invalid, cudaStream_t s);
+
+}  // namespace vtc

@@ -13,6 +13,9 @@ namespace tc {
 
 int launch_rank(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
+int launch_rank_fold(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                     const CUtensorMap& tmAx, const CUtensorMap& tmBx, const Params& p, int grid,
+                     cudaStream_t s);
 int launch_topk(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
 int launch_lse(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
@@ -169,7 +172,8 @@ int kernel_timer_read(double* total_ms, int* count) {
 }
 
 int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorMap& tmA,
-                  const CUtensorMap& tmB, const Params& p, cudaStream_t s) {
+                  const CUtensorMap& tmB, const Params& p, cudaStream_t s, const CUtensorMap* tmAx,
+                  const CUtensorMap* tmBx) {
   if (pl.grid <= 0) return VTC_OK;
   if (a_resident && p.num_kb > 8) return VTC_ERR_UNSUPPORTED_SHAPE;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -186,6 +190,11 @@ int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorM
   int rc;
   switch (epilogue) {
     case EPI_RANK: rc = launch_rank(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
+    case EPI_RANK_FOLD:
+      rc = (pl.cluster == 2 && pl.pair && tmAx && tmBx)
+               ? launch_rank_fold(a_resident, tmA, tmB, *tmAx, *tmBx, p, pl.grid, s)
+               : VTC_ERR_INVALID_ARG;
+      break;
     case EPI_TOPK: rc = launch_topk(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
     case EPI_LSE:
       rc = pl.cluster == 1 ? launch_lse(a_resident, tmA, tmB, p, pl.grid, s) : VTC_ERR_INVALID_ARG;

@@ -11,7 +11,7 @@ constexpr int BM = 128;  // query rows per CTA tile  (UMMA M, TMEM lanes)
 constexpr int BN = 256;  // gallery rows per tile    (UMMA N, TMEM columns per accumulator stage)
 constexpr int BK = 64;   // bf16 per k-block = one 128-byte swizzle atom
 
-enum Epilogue { EPI_RANK = 0, EPI_LSE = 1, EPI_STORE = 2, EPI_TOPK = 3 };
+enum Epilogue { EPI_RANK = 0, EPI_LSE = 1, EPI_STORE = 2, EPI_TOPK = 3, EPI_RANK_FOLD = 4 };
 
 constexpr int TOPK_POOL = 64;  // buffer entries per (row, gallery split)
 constexpr int TOPK_KEEP_MAX = 32;  // entries kept when a buffer is compacted: 16 for k <= 12, else 32
@@ -57,6 +57,12 @@ struct Params {
   int topk_keep;      // entries kept by a compaction (>= k, <= TOPK_KEEP_MAX)
   const float* tau_init;  // optional [N]: initial per-row threshold (from a sample pass); NULL = +inf
   int dbg_skip_epilogue;  // profiling only (VTC_DBG_SKIP_EPILOGUE=1): drain TMEM but reduce nothing
+  // EPI_RANK_FOLD (new fields go at the END: the other kernels' parameter offsets stay put).
+  // The per-column bias and the per-row ground-truth score ride in one extra K16 step of the MMA
+  // (operands tmAx / tmBx), so the accumulator IS acc' = q.x - ||x||^2/2 + d(t,gt)/2 and a column
+  // is closer than the ground truth iff acc' > 0; fold_w[t] is the half-width of the guard band
+  // around 0 (negative: the row never pushes).
+  const float* fold_w;
 };
 
 // Row-major bf16 [rows, cols] with leading dimension ld (elements) -> 2-D TMA descriptor with a
@@ -77,8 +83,11 @@ Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split 
 
 // a_resident: keep the whole 128 x K' query tile in shared memory (needs num_kb <= 8).
 // tmB must have been built with box_rows = BN / pl.cluster.
+// EPI_RANK_FOLD additionally takes the tensor maps of the [rows, 64] bf16 fold operands (tmBx with
+// box_rows = BN / 2: it always runs as a CTA pair).
 int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorMap& tmA,
-                  const CUtensorMap& tmB, const Params& p, cudaStream_t s);
+                  const CUtensorMap& tmB, const Params& p, cudaStream_t s,
+                  const CUtensorMap* tmAx = nullptr, const CUtensorMap* tmBx = nullptr);
 
 // opt-in CUDA-event timing of the tensor-core launches (bench.py roofline)
 void kernel_timer_enable(bool on);
