@@ -424,6 +424,10 @@ def run_ours(a):
                    "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                    "cuda_graph": graphed is not None,
                    "rank_epilogue": "fold (VTC_RANK_FOLD=1, opt-in)" if rank_fold else "default",
+                   "sharded_step": ("n/a" if world == 1 else
+                                    "single pass (VTC_SHARD_SINGLE_PASS=1, opt-in)"
+                                    if os.environ.get("VTC_SHARD_SINGLE_PASS", "0") not in ("", "0")
+                                    else "local chunk overlapped with the gather + remote ranges"),
                    "l2_flush": "not needed: inputs + operands (>= 600 MB) exceed the 126 MB L2"},
         "hits": [int(x) for x in hits.cpu().tolist()], "medr": float(medr.cpu()[0]),
         "e2e": e2e, "gpu_launches": int(tl.item()), "host_enqueue_ms_per_step": host_ms_per_step,

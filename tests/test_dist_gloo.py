@@ -78,7 +78,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, N, M, out_q):
+def _worker(rank, world, port, N, M, out_q, single_pass=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -91,7 +91,8 @@ def _worker(rank, world, port, N, M, out_q):
         qs, qe = shard_bounds(N, world, rank)
         gs, ge = shard_bounds(M, world, rank)
         be = OracleBackend()
-        res = sharded_rank_eval(T[qs:qe].contiguous(), V[gs:ge].contiguous(), N, M, backend=be)
+        res = sharded_rank_eval(T[qs:qe].contiguous(), V[gs:ge].contiguous(), N, M, backend=be,
+                                single_pass=single_pass)
         tv, ti = sharded_topk(T[:16].contiguous(), V[gs:ge].contiguous(), M, 5, backend=be)
         out_q.put((rank, res["hits"].numpy(), float(res["medr"][0]), res["rank0_local"].numpy(),
                    ti.numpy()))
@@ -99,7 +100,7 @@ def _worker(rank, world, port, N, M, out_q):
         dist.destroy_process_group()
 
 
-def _run(N, M, world=2):
+def _run(N, M, world=2, single_pass=False):
     from oracle import vtc_oracle as O
     from vtc_b200.parallel import shard_bounds
     from vtc_b200.synthetic import make_retrieval_pair
@@ -107,7 +108,7 @@ def _run(N, M, world=2):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, N, M, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, M, q, single_pass)) for r in range(world)]
     for p in procs:
         p.start()
     got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
@@ -138,3 +139,10 @@ def test_row_sharded_eval_rectangular_world2():
 def test_row_sharded_eval_equal_shards_world2():
     """Equal shards: the gathered gallery is used as two contiguous remote ranges."""
     _run(100, 100)
+
+
+def test_row_sharded_eval_single_pass_world2():
+    """Opt-in variant: one library call over the whole gathered gallery (equal shards); with unequal
+    shards the flag is ignored and the chunked path runs."""
+    _run(100, 100, single_pass=True)
+    _run(90, 151, single_pass=True)

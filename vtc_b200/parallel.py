@@ -104,9 +104,16 @@ def _all_gather_padded(x: torch.Tensor, sizes: Sequence[int], group, async_op: b
 def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int, M_total: int,
                       k_vals: Sequence[int] = (1, 5, 10), metric: str = "l2",
                       precision: str = "exact", group=None, backend=None,
-                      want_medr: bool = True) -> Dict[str, object]:
+                      want_medr: bool = True, single_pass: Optional[bool] = None
+                      ) -> Dict[str, object]:
     """Row-sharded similarity + rank + R@K (+MedR).  q_local / g_local are this rank's
     shard_bounds() rows of the global query / gallery matrices; gt(t) = t (global row index).
+
+    single_pass (default: VTC_SHARD_SINGLE_PASS=1, else off; needs equal gallery shards): wait for
+    the gather and rank against the whole gathered gallery in ONE library call instead of
+    local chunk + up to two remote ranges -- a third of the small launches and one tensor-core
+    launch without intermediate tails, at the price of not overlapping the gather (opt-in until both
+    have been timed side by side at 8 GPUs).
 
     Returns {"hits": int64 [nk] (global), "medr": float or None, "rank0_local": int32 [n_r],
              "num_queries": N_total}.  hits / medr are identical on every rank."""
@@ -132,6 +139,9 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     gathered = None
     mx = max(g_sizes)
     equal = all(sz == mx for sz in g_sizes)
+    if single_pass is None:
+        single_pass = os.environ.get("VTC_SHARD_SINGLE_PASS", "0") not in ("", "0")
+    single_pass = bool(single_pass) and world > 1 and equal and mx > 0
     if world > 1:
         send = g_local
         if send.shape[0] < mx:
@@ -147,7 +157,15 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     rank0 = torch.zeros(n_local, dtype=torch.int32, device=dev)
     gt_local = (world == 1 or _gt_all_local(qs, qe, gs0, g_sizes[rank])) and g_sizes[rank] > 0
     local_done = False
-    if gt_local:
+    if single_pass:
+        # equal shards: the gathered buffer IS the gallery in global row order, every ground truth
+        # lies inside it, so one call yields the ground-truth scores and the complete ranks
+        work.wait()
+        ph.mark("gather_wait")
+        work = None
+        gt_score = backend.sim_rank(q_local, gathered[:M_total], qs, 0, metric, precision, None, rank0)
+        local_done = True
+    elif gt_local:
         # every ground truth is in our own chunk: rank against it (the call also yields the
         # ground-truth scores) while the gather is in flight
         gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0)
