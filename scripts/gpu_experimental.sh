@@ -19,6 +19,14 @@ for fold in 0 1; do
     echo "bench fold=$fold $args exit=$?" >> $S
   done
 done
+# host staging schedule of RecallAtK.compute (the e2e number): equal chunks vs the balanced schedule
+for sch in equal balanced; do
+  for c in 6 8; do
+    VTC_PIPELINE_SCHEDULE=$sch VTC_PIPELINE_CHUNKS_2D=$c timeout 200 python bench.py --steps 10 \
+        --no-cpu-baseline > gpurun_out/${TAG}_fold0_e2e_${sch}_c$c.json 2> gpurun_out/${TAG}_e2e_${sch}_c$c.err
+    echo "bench e2e schedule=$sch c=$c exit=$?" >> $S
+  done
+done
 python scripts/show_bench.py gpurun_out/${TAG}_fold*.json 2>&1 | cut -c1-200 >> $S
 # SASS-level proof of what the fold epilogue issues per logit goes with the ncu capture of the round
 VTC_RANK_FOLD=1 timeout 600 ncu --set full --clock-control none --import-source on \
