@@ -211,7 +211,8 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     const int64_t Mpad = round_up<int64_t>(M, tc::BN);
     VTC_RETURN_IF_ERROR(launch_fold_g(w.sq64, M, Mpad, metric, w.foldG, &w.scalars[2], s));
     VTC_RETURN_IF_ERROR(launch_fold_q(w.thr, w.dgt, &w.scalars[0], N, metric,
-                                      guard_rel_for(precision, o.Kp), w.foldQ, w.foldW, s));
+                                      guard_rel_for(precision, o.Kp), w.foldQ, w.foldW,
+                                      &w.scalars[2], s));
     CUtensorMap tmAx, tmBx;
     VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.foldQ, N, FOLD_COLS, FOLD_COLS, tc::BM, &tmAx));
     VTC_RETURN_IF_ERROR(

@@ -40,7 +40,7 @@ __device__ __forceinline__ void store_fold_row(__nv_bfloat16* row, const unsigne
 __global__ void fold_q_kernel(const float2* __restrict__ thr, const double* __restrict__ dgt,
                               const unsigned int* __restrict__ max_sq_bits, int64_t N, int metric,
                               float guard_rel, __nv_bfloat16* __restrict__ Qx,
-                              float* __restrict__ fold_w) {
+                              float* __restrict__ fold_w, unsigned int* __restrict__ invalid) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N) return;
   const float2 th = thr[t];
@@ -64,6 +64,10 @@ __global__ void fold_q_kernel(const float2* __restrict__ thr, const double* __re
       wd = delta + 4.8e-7 * S;
     }
     w = __double2float_ru(wd * (1.0 + 1.0e-6));
+  } else if (d0 == d0) {
+    // an infinite (or absurdly large) ground-truth score still orders against finite scores in
+    // canonical arithmetic, but cannot ride in a bf16 operand: let the brute-force fallback decide
+    *invalid = 1u;
   }
   unsigned short p[3];
   split3(m, p);
@@ -93,10 +97,11 @@ __global__ void fold_g_kernel(const double* __restrict__ sq64, int64_t M, int64_
 }  // namespace
 
 int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_sq_bits, int64_t N,
-                  int metric, float guard_rel, __nv_bfloat16* Qx, float* fold_w, cudaStream_t s) {
+                  int metric, float guard_rel, __nv_bfloat16* Qx, float* fold_w,
+                  unsigned int* invalid, cudaStream_t s) {
   if (N == 0) return VTC_OK;
-  fold_q_kernel<<<(unsigned)ceil_div<int64_t>(N, 128), 128, 0, s>>>(thr, dgt, max_sq_bits, N, metric,
-                                                                  guard_rel, Qx, fold_w);
+  fold_q_kernel<<<(unsigned)ceil_div<int64_t>(N, 128), 128, 0, s>>>(
+      thr, dgt, max_sq_bits, N, metric, guard_rel, Qx, fold_w, invalid);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }

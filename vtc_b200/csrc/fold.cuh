@@ -11,9 +11,11 @@ constexpr int FOLD_COLS = 64;  // bf16 per fold-operand row: one 128-byte swizzl
 // Qx [N, 64] bf16 = [ m'_t (three bf16 pieces) | 1 1 1 | 0 ... ] and fold_w [N]: half-width of the
 // guard band around acc' = 0, derived from the (lo, hi) thresholds and d(t,gt) that
 // launch_gt_score produced.  Rows whose ground-truth score is NaN get m' = -1e30, w = -1 (they count
-// nothing and never push; vtc_rank_finalize gives them rank M).
+// nothing and never push; vtc_rank_finalize gives them rank M); an infinite score sets *invalid = 1
+// (brute-force fallback, as for launch_fold_g).
 int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_sq_bits, int64_t N,
-                  int metric, float guard_rel, __nv_bfloat16* Qx, float* fold_w, cudaStream_t s);
+                  int metric, float guard_rel, __nv_bfloat16* Qx, float* fold_w,
+                  unsigned int* invalid, cudaStream_t s);
 
 // Gx [Mpad, 64] bf16 = [ 1 1 1 | h_j (three bf16 pieces) | 0 ... ], h_j = -||x_j||^2 / 2 (L2) or 0
 // (DOT); padding rows j >= M carry h = -1e30 (never closer, never inside the band).  A gallery row
