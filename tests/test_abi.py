@@ -137,3 +137,41 @@ int main(void) {
     assert r.returncode == 0, r.stdout + r.stderr
     ver, ws, msg = r.stdout.split(None, 2)
     assert int(ver) >= 1 and int(ws) > 0 and "invalid" in msg
+
+
+def test_integration_md_ctypes_stub_matches_the_library(lib):
+    """INTEGRATION.md shows the ctypes binding a maintainer of the reference would write for the
+    evaluation path (the replacement of model/metric.py:137-161): its argtypes must have the arity
+    and kinds of the real entry points, and the enum literals it passes must be the header's."""
+    import ctypes
+
+    from vtc_b200 import _ffi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = text[text.index("import ctypes, torch"):]
+    block = block[:block.index("```")]
+    ns = {}
+    stub = "\n".join(ln for ln in block.splitlines()
+                     if ln.startswith(("P, i64", "lib.vtc_")) and "CDLL" not in ln)
+
+    class FakeFn:
+        pass
+
+    class FakeLib:
+        def __getattr__(self, name):
+            fn = FakeFn()
+            object.__setattr__(self, name, fn)
+            return fn
+
+    fake = FakeLib()
+    exec("import ctypes\n" + stub, {"lib": fake, "ctypes": ctypes}, ns)
+    for name in ("vtc_workspace_bytes", "vtc_sim_rank", "vtc_rank_finalize"):
+        want = _ffi.SIGNATURES[name][1]
+        got = getattr(fake, name).argtypes
+        assert len(got) == len(want), name
+        for g, w in zip(got, want):
+            assert ctypes.sizeof(g) == ctypes.sizeof(w), (name, g, w)
+    # the literals in the example call: F32 = 0, L2 = 1, EXACT = 0, OP_SIM_RANK = 0
+    assert (_ffi.F32, _ffi.METRIC_L2, _ffi.PREC_EXACT, _ffi.OP_SIM_RANK) == (0, 1, 0, 0)
+    assert "N, M, D, 0, None, 0, 0, 1, 0," in block
