@@ -245,6 +245,18 @@ def config3_and_5():
         us, nl = timeit(lambda: ops.rank_finalize(*ops.sim_rank(q, g, precision=prec), 10000, [1, 5, 10]),
                         iters=20)
         emit(bench="c3_rank_10kx10k", precision=prec, us=us, launches=nl, pairs_per_s=1e8 / (us * 1e-6))
+        # the same step replayed as one CUDA graph (17 dependent launches around a ~70 us
+        # tensor-core kernel: the gaps between them are a third of the eager step)
+        try:
+            from vtc_b200.parallel import GraphedRankEval
+
+            ge = GraphedRankEval(q, g, 10000, 10000, [1, 5, 10], "l2", prec)
+            us, _ = timeit(lambda: ge(), iters=50)
+            emit(bench="c3_rank_10kx10k_cudagraph", precision=prec, us=us,
+                 launches=ge.launches_per_replay, pairs_per_s=1e8 / (us * 1e-6))
+            ge.close()
+        except Exception as e:  # noqa: BLE001
+            emit(bench="c3_rank_10kx10k_cudagraph", precision=prec, error=str(e)[:200])
     us, _ = timeit(lambda: torch_rank(q, g), iters=10)
     emit(bench="c3_rank_10kx10k_torch_bf16_eager", us=us, pairs_per_s=1e8 / (us * 1e-6))
 
