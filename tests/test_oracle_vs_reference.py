@@ -134,3 +134,53 @@ def test_constructor_and_call_signatures_match_the_reference():
     assert leading(our_loss.clip_loss)[:2] == leading(ref_loss.clip_loss)
     assert leading(our_reval.compute_recall)[:4] == leading(ref_reval.compute_recall)
     assert defaults(ref_reval.compute_recall).items() <= defaults(our_reval.compute_recall).items()
+
+
+@pytest.mark.parametrize("random_masking", [False, True])
+def test_mask_embedding_is_trained_like_in_the_reference(random_masking, monkeypatch):
+    """model/model.py:212 and :243-246 route `mask_embedding` into the comment features through
+    autograd-visible operations, so the parameter receives gradients.  The glue of
+    `_encode_with_comments` is compared with the reference's own method, live, with the CAM itself
+    (a CUDA op here) replaced on both sides by the same differentiable stand-in."""
+    import vtc_b200.model.model as our_model
+    from vtc_b200.model import PretrainedCLIP_finaltf
+
+    # the final normalisation (:263-264) is a CUDA kernel on our side: same formula in torch here
+    monkeypatch.setattr(our_model, "normalize", O.normalize)
+    b, nc, D = 6, 4, 32
+    g = torch.Generator().manual_seed(3)
+    vis, title = torch.randn(b, D, generator=g), torch.randn(b, D, generator=g)
+    comm = torch.randn(b, nc, D, generator=g)
+    empty = torch.rand(b, nc, generator=g) < 0.3
+    me = torch.randn(1, D, generator=g)
+
+    def stand_in(main, aux):  # differentiable in both arguments, like the CAM
+        aux = torch.stack(list(aux), 0) if not isinstance(aux, torch.Tensor) else aux
+        return main + aux.mean(0) * 0.5 + (aux ** 2).sum(0) * 0.1
+
+    ref = RS.make_ref_cam(D, 1, 2, mask_embedding=me)
+    ref.random_comment_masking = random_masking
+    ref._adapt_feature = stand_in
+
+    def ref_load(comments):  # model/model.py:207-214 without the text encoder (out of scope)
+        feats, mask = comments
+        feats = feats.clone().float()
+        feats[mask] = ref.mask_embedding
+        return feats.permute(1, 0, 2)
+
+    ref._load_comment_features = ref_load
+    ours = PretrainedCLIP_finaltf(D, n_layers=1, n_heads=2, random_comment_masking=random_masking)
+    with torch.no_grad():
+        ours.mask_embedding.copy_(me)
+    ours._adapt_feature = stand_in
+    outs = []
+    for m in (ref, ours):
+        m.train()
+        torch.manual_seed(11)  # the Bernoulli comment masks come from the global generator
+        fv, ft = m._encode_with_comments(vis, title, (comm, empty))
+        (fv.sum() + (ft * torch.arange(D)).sum()).backward()
+        outs.append((fv.detach(), ft.detach(), m.mask_embedding.grad.clone()))
+    torch.testing.assert_close(outs[1][0], outs[0][0])
+    torch.testing.assert_close(outs[1][1], outs[0][1])
+    assert outs[0][2].abs().max() > 0
+    torch.testing.assert_close(outs[1][2], outs[0][2])

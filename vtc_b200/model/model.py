@@ -440,7 +440,8 @@ class PretrainedCLIPBase(nn.Module):
         else:
             feats_comm = comments.float().clone()
         if empty_mask is not None:
-            feats_comm[empty_mask] = self.mask_embedding.detach().to(feats_comm.dtype)  # :212
+            # :212 -- an autograd-visible assignment: mask_embedding is a trained parameter
+            feats_comm[empty_mask] = self.mask_embedding.to(feats_comm.dtype)
         return feats_comm.permute(1, 0, 2)                                       # :213
 
     def _encode_with_comments(self, feats_vis, feats_title, comments):
@@ -453,7 +454,7 @@ class PretrainedCLIPBase(nn.Module):
                               for comm in feats_comm]                             # :237-240
             else:
                 comm_masks = torch.ones(len(feats_comm), device=feats_comm.device)  # :241-242
-            feats_comm = [comm * mask + self.mask_embedding.detach() * (1 - mask)
+            feats_comm = [comm * mask + self.mask_embedding * (1 - mask)
                           for comm, mask in zip(feats_comm, comm_masks)]          # :243-246
             branch_to_adapt = self.branch_to_adapt
         else:
