@@ -184,3 +184,130 @@ def test_mask_embedding_is_trained_like_in_the_reference(random_masking, monkeyp
     torch.testing.assert_close(outs[1][1], outs[0][1])
     assert outs[0][2].abs().max() > 0
     torch.testing.assert_close(outs[1][2], outs[0][2])
+
+
+def test_averaging_fusion_forward_glue_matches_reference(monkeypatch):
+    """PretrainedCLIP.forward with comment_fusion="averaging" (model/model.py:326-371) through a
+    stand-in backbone and TOKEN-ID inputs: the comments are averaged in as the encoder sees them
+    (no mask_embedding in this class), both outputs are normalised, sim = exp(logit_scale) * v t^T.
+    The two CUDA ops on our side (normalize, the fused mean + normalise read-out) are replaced by
+    their torch formulas; everything else is the code that runs on the box."""
+    import torch.nn as nn
+
+    import vtc_b200.model.model as our_model
+
+    D, b, nc, ntok = 16, 5, 3, 7
+
+    class FakeClip(nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(2)
+            self.emb = nn.Parameter(torch.randn(50000, D, generator=g))
+            self.proj = nn.Parameter(torch.randn(3 * 4 * 4, D, generator=g))
+            self.logit_scale = nn.Parameter(torch.tensor(2.5))
+            self.ln_final = nn.LayerNorm(D)
+
+        def encode_text(self, tok):
+            return self.emb[tok].mean(1)
+
+        def encode_image(self, x):
+            return x.flatten(1) @ self.proj
+
+    backbone = FakeClip()
+    mm = RS.ref_model_module()
+
+    class RefClip(mm.PretrainedCLIP):
+        def __init__(self):
+            nn.Module.__init__(self)
+            self.model = backbone
+            self.feature_dim = D
+            self.residual_activation = None
+            self.comment_fusion = "averaging"
+
+    monkeypatch.setattr(our_model, "normalize", O.normalize)
+    monkeypatch.setattr(our_model._UniformReadout, "apply",
+                        staticmethod(lambda stacked: O.normalize(stacked.mean(0))))
+    ours = our_model.PretrainedCLIP("ViT-B/32", comment_fusion="averaging", backbone=backbone,
+                                    lazy_sim=False)
+    monkeypatch.setattr(our_model.LazySim, "materialize",
+                        lambda self: self.scale * self.feats_a @ self.feats_b.t())
+    g = torch.Generator().manual_seed(9)
+    vis = torch.randn(b, 2, 3, 4, 4, generator=g)              # [b, t, c, h, w]: mean over time
+    title = torch.randint(0, 49000, (b, ntok), generator=g)
+    comments = torch.randint(0, 49000, (b, nc, ntok), generator=g)
+    comments[1, 2, 1] = 49407                                   # an empty comment
+    with torch.no_grad():
+        want = RefClip().eval()(vis, title, comments)
+        got = ours.eval()(vis, title, comments)
+    for g_, w_ in zip(got, want):
+        torch.testing.assert_close(g_, w_, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("branch", ["text", "image", "skip"])
+def test_finaltf_forward_glue_with_token_ids_matches_reference(monkeypatch, branch):
+    """PretrainedCLIP_finaltf.forward (model/model.py:456-480) with TOKEN-ID titles / comments and
+    raw frames through a stand-in backbone: the reference's own _load_comment_features (:207-214,
+    empty comment = end-of-text token 49407 in position 1 -> mask_embedding) and
+    _encode_with_comments run unmodified; the CAM is the same differentiable stand-in on both sides."""
+    import torch.nn as nn
+
+    import vtc_b200.model.model as our_model
+
+    D, b, nc, ntok = 16, 5, 3, 7
+
+    class FakeClip(nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(4)
+            self.emb = nn.Parameter(torch.randn(50000, D, generator=g))
+            self.proj = nn.Parameter(torch.randn(3 * 4 * 4, D, generator=g))
+            self.logit_scale = nn.Parameter(torch.tensor(2.0))
+            self.ln_final = nn.LayerNorm(D)
+
+        def encode_text(self, tok):
+            return self.emb[tok].mean(1)
+
+        def encode_image(self, x):
+            return x.flatten(1) @ self.proj
+
+    backbone = FakeClip()
+    me = torch.randn(1, D, generator=torch.Generator().manual_seed(6))
+
+    def stand_in(main, aux):
+        aux = torch.stack(list(aux), 0) if not isinstance(aux, torch.Tensor) else aux
+        return main * 0.7 + aux.mean(0)
+
+    mm = RS.ref_model_module()
+
+    class RefFinal(mm.PretrainedCLIP_finaltf):
+        def __init__(self):
+            nn.Module.__init__(self)
+            self.model = backbone
+            self.feature_dim = D
+            self.mask_embedding = nn.Parameter(me.clone())
+            self.random_comment_masking = False
+            self.branch_to_adapt = self.branch_to_adapt_val = branch
+            self.init_audio_model = False
+
+    ref = RefFinal().eval()
+    ref._adapt_feature = stand_in
+    monkeypatch.setattr(our_model, "normalize", O.normalize)
+    monkeypatch.setattr(our_model.LazySim, "materialize",
+                        lambda self: self.scale * self.feats_a @ self.feats_b.t())
+    ours = our_model.PretrainedCLIP_finaltf("ViT-B/32", branch_to_adapt=branch,
+                                            branch_to_adapt_val=branch, n_layers=1, n_heads=2,
+                                            backbone=backbone, lazy_sim=False).eval()
+    with torch.no_grad():
+        ours.mask_embedding.copy_(me)
+    ours._adapt_feature = stand_in
+    g = torch.Generator().manual_seed(9)
+    vis = torch.randn(b, 3, 4, 4, generator=g)                  # [b, c, h, w]
+    title = torch.randint(0, 49000, (b, ntok), generator=g)
+    comments = torch.randint(0, 49000, (b, nc, ntok), generator=g)
+    comments[1, 2, 1] = 49407
+    comments[3, 0, 1] = 49407
+    with torch.no_grad():
+        want = ref(vis, title, comments)
+        got = ours(vis, title, comments)
+    for g_, w_ in zip(got, want):
+        torch.testing.assert_close(g_, w_, rtol=1e-5, atol=1e-6)

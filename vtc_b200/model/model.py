@@ -423,10 +423,10 @@ class PretrainedCLIPBase(nn.Module):
                                final_linear=final, skip_mask=skip_mask, precision=self.precision,
                                res_act=res_act)
 
-    def _load_comment_features(self, comments) -> torch.Tensor:
-        """model/model.py:207-214.  `comments` is either precomputed comment embeddings
-        [b, nc, D] (optionally a tuple (embeddings, empty_mask [b, nc])) or token ids
-        [b, nc, ntoks] when a backbone with `encode_text` is attached."""
+    def _comment_embeddings(self, comments):
+        """-> (comment embeddings [b, nc, D] fp32, empty-string mask [b, nc] or None).  `comments`
+        is either precomputed comment embeddings [b, nc, D] (optionally a tuple (embeddings,
+        empty_mask)) or token ids [b, nc, ntoks] when a backbone with `encode_text` is attached."""
         empty_mask = None
         if isinstance(comments, (tuple, list)):
             comments, empty_mask = comments
@@ -439,6 +439,12 @@ class PretrainedCLIPBase(nn.Module):
             feats_comm = feats_comm.reshape(b, ncomms, self.feature_dim).float()
         else:
             feats_comm = comments.float().clone()
+        return feats_comm, empty_mask
+
+    def _load_comment_features(self, comments) -> torch.Tensor:
+        """model/model.py:207-214: comment embeddings with `mask_embedding` in place of empty
+        comments, sequence-first [nc, b, D]."""
+        feats_comm, empty_mask = self._comment_embeddings(comments)
         if empty_mask is not None:
             # :212 -- an autograd-visible assignment: mask_embedding is a trained parameter
             feats_comm[empty_mask] = self.mask_embedding.to(feats_comm.dtype)
@@ -530,7 +536,9 @@ class PretrainedCLIP(PretrainedCLIPBase):
         if comments is None or self.comment_fusion is None or self.comment_fusion == "None":
             feats_text = normalize(feats_title.float())
         elif self.comment_fusion == "averaging":
-            feats_comm = self._load_comment_features(comments)                   # [nc, b, D]
+            # :346-351 -- plain comment embeddings: this class has no mask_embedding, empty
+            # comments are averaged in as the encoder sees them
+            feats_comm = self._comment_embeddings(comments)[0].permute(1, 0, 2)  # [nc, b, D]
             stacked = torch.cat([feats_title.float().unsqueeze(0), feats_comm], 0)
             feats_text = _UniformReadout.apply(stacked)                          # :356-362,:366
         else:
