@@ -243,3 +243,32 @@ def test_pipelined_staging_chunk_bounds(monkeypatch):
     bal = [x / 100_000 for x in RecallAtK._pipeline_bounds_2d(100_000, 6)]
     assert bound(bal) < bound([i / 6 for i in range(7)]) - 0.05
     assert RecallAtK._pipeline_bounds_2d(100, 2) == [0, 50, 100]  # too few chunks to balance
+
+
+def test_metric_tracker_and_loss_metric_follow_the_trainer_protocol():
+    """trainer/trainer.py:49-54,78-81,118-121: MetricTracker(*metrics) + add_metric(LossMetric()) +
+    set_writer(writer); update(loss.item(), output, meta); result() merges the metrics' dicts;
+    avg() maps every metric name to its running average (None for RecallAtK)."""
+    from vtc_b200.model.metric import LossMetric, MetricTracker, RecallAtK
+
+    class Writer:
+        def __init__(self):
+            self.scalars = []
+
+        def add_scalar(self, name, value):
+            self.scalars.append((name, value))
+
+    rec = RecallAtK("visual", "titles", k_vals=[1])
+    tr = MetricTracker(*[m for m in [rec] if m.is_val])
+    tr.add_metric(LossMetric())
+    w = Writer()
+    tr.set_writer(w)
+    assert list(tr.metrics) == ["recall@k", "loss"] and rec.writer is w
+    loss_metric = tr.metrics["loss"]
+    for v in (2.0, 4.0, 6.0):
+        loss_metric.update(v, None, None)
+    assert tr.avg() == {"recall@k": None, "loss": 4.0}
+    assert loss_metric.result() == {"loss": 4.0}
+    assert w.scalars == [("loss", 2.0), ("loss", 4.0), ("loss", 6.0)]
+    tr.reset()
+    assert loss_metric.avg() == 0 and rec.insert_index == 0

@@ -131,6 +131,15 @@ def test_constructor_and_call_signatures_match_the_reference():
     assert leading(our_metric.RecallAtK.__init__)[:4] == leading(ref_metric.RecallAtK.__init__)
     for meth in ("update", "compute", "reset", "result", "avg", "set_writer"):
         assert leading(getattr(our_metric.RecallAtK, meth)) == leading(getattr(ref_metric.RecallAtK, meth)), meth
+    # the trainer imports these two from the same module and drives them through this API
+    # (trainer/trainer.py:9,49-54,78-81)
+    for cls in ("MetricTracker", "BaseMetric", "ScalarPerBatchMetric", "LossMetric"):
+        rc, oc = getattr(ref_metric, cls), getattr(our_metric, cls)
+        assert leading(oc.__init__) == leading(rc.__init__), cls
+        ref_api = {n for n, v in vars(rc).items() if callable(v) and not n.startswith("_")}
+        assert ref_api <= {n for n in dir(oc) if callable(getattr(oc, n))}, (cls, ref_api)
+        for meth in ref_api:
+            assert leading(getattr(oc, meth)) == leading(getattr(rc, meth)), (cls, meth)
     assert leading(our_loss.clip_loss)[:2] == leading(ref_loss.clip_loss)
     assert leading(our_reval.compute_recall)[:4] == leading(ref_reval.compute_recall)
     assert defaults(ref_reval.compute_recall).items() <= defaults(our_reval.compute_recall).items()

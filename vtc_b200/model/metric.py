@@ -29,64 +29,108 @@ from .. import ops
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
-__all__ = ["BaseMetric", "RecallAtK", "MetricTracker"]
+__all__ = ["BaseMetric", "ScalarPerBatchMetric", "LossMetric", "RecallAtK", "MetricTracker"]
+
+
+class MetricTracker:
+    """model/metric.py:10-42, API kept as the trainer uses it (trainer/trainer.py:49-54):
+    `MetricTracker(*metrics)`, `add_metric`, `set_writer`, `reset`, `update`, `avg`, `result`."""
+
+    def __init__(self, *metrics):
+        self.metrics = {}
+        for m in metrics:
+            self.add_metric(m)
+        self.reset()
+
+    def add_metric(self, metric):
+        self.metrics[metric.name] = metric
+
+    def set_writer(self, writer):
+        for m in self.metrics.values():
+            m.set_writer(writer)
+
+    def reset(self):
+        for m in self.metrics.values():
+            m.reset()
+
+    def update(self, loss, output, meta):
+        for m in self.metrics.values():
+            m.update(loss, output, meta)
+
+    def avg(self):
+        res = {}
+        for m in self.metrics.values():
+            res[m.name] = m.avg()
+        return res
+
+    def result(self):
+        res = {}
+        for m in self.metrics.values():
+            res.update(m.result())
+        return res
 
 
 class BaseMetric:
     """model/metric.py:45-65."""
 
-    def __init__(self, name, is_train=True, is_val=True):
+    def __init__(self, name):
         self.name = name
         self.writer = None
-        self.is_train = is_train
-        self.is_val = is_val
+        self.is_train = True
+        self.is_val = True
 
     def set_writer(self, writer):
         self.writer = writer
 
     def reset(self):
-        raise NotImplementedError
+        raise NotImplementedError()
 
     def update(self, loss, output, meta):
-        raise NotImplementedError
+        raise NotImplementedError()
 
     def avg(self):
-        raise NotImplementedError
+        raise NotImplementedError()
 
     def result(self):
-        raise NotImplementedError
+        raise NotImplementedError()
 
 
-class MetricTracker:
-    """model/metric.py:10-42 (thin host glue, kept as is)."""
+class ScalarPerBatchMetric(BaseMetric):
+    """model/metric.py:68-95: running total / count / average of a per-batch scalar.  Host glue
+    (the trainer feeds it `loss.item()`); the reference keeps the three numbers in a one-row
+    DataFrame and zeroes it through `.values[:] = 0`, which pandas >= 3 rejects (copy-on-write), so
+    they are plain floats here -- same values, same `avg()` / `result()`."""
 
-    def __init__(self, *metrics, writer=None):
-        self.writer = writer
-        self.metrics = metrics
-        for met in self.metrics:
-            met.set_writer(writer)
+    def __init__(self, name, metric_fun):
+        super().__init__(name)
+        self.fun = metric_fun
         self.reset()
 
     def reset(self):
-        for met in self.metrics:
-            met.reset()
+        self.total = 0
+        self.counts = 0
+        self.average = 0
 
-    def update(self, loss, output, meta):
-        for met in self.metrics:
-            met.update(loss, output, meta)
+    def update(self, loss, output, meta, n=1):
+        value = self.fun(loss, output, meta)
+        if self.writer is not None:
+            self.writer.add_scalar(self.name, value)
+        self.total += value * n
+        self.counts += n
+        self.average = self.total / self.counts
 
     def avg(self):
-        return {met.name: met.avg() for met in self.metrics if met.avg() is not None}
+        return self.average
 
     def result(self):
-        res = {}
-        for met in self.metrics:
-            r = met.result()
-            if isinstance(r, dict):
-                res.update(r)
-            else:
-                res[met.name] = r
-        return res
+        return {self.name: self.average}
+
+
+class LossMetric(ScalarPerBatchMetric):
+    """model/metric.py:98-100."""
+
+    def __init__(self):
+        super().__init__("loss", lambda loss, o, m: loss)
 
 
 def _to_device(x: ArrayLike, device: torch.device) -> torch.Tensor:
