@@ -11,11 +11,13 @@ S=gpurun_out/summary_$TAG.txt
 VTC_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -m gpu -q --tb=short \
     --maxfail=8 > gpurun_out/${TAG}_pytest.log 2>&1
 echo "experimental parity exit=$?" >> $S; tail -n 12 gpurun_out/${TAG}_pytest.log >> $S
-for fold in 0 1; do
+# fold = 0: default epilogue; 1: fold operands 64 columns wide; 2: 16 columns wide (VTC_FOLD_COLS=16)
+for fold in 0 1 2; do
   for args in "" "--d 256" "--d 768" "--precision exact"; do
     name=$(echo "fold${fold}${args}" | tr -d ' -')
-    VTC_RANK_FOLD=$fold timeout 200 python bench.py --steps 10 --no-cpu-baseline $args \
-        > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
+    cols=64; [ $fold -eq 2 ] && cols=16
+    VTC_RANK_FOLD=$(( fold > 0 )) VTC_FOLD_COLS=$cols timeout 200 python bench.py --steps 10 \
+        --no-cpu-baseline $args > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
     echo "bench fold=$fold $args exit=$?" >> $S
   done
 done

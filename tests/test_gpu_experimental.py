@@ -37,9 +37,13 @@ def _oracle_ranks(Q, G, metric, precision, gt=None, row_offset=0):
     return O.rank0_exact(Q, G, gt=gt, metric=METRICS[metric], row_offset=row_offset)
 
 
-@pytest.fixture
-def fold(monkeypatch):
-    monkeypatch.setenv("VTC_RANK_FOLD", "1")  # read by the library on every vtc_sim_rank call
+@pytest.fixture(params=[64, 16])
+def fold(monkeypatch, request):
+    """VTC_RANK_FOLD / VTC_FOLD_COLS are read by the library on every vtc_sim_rank call.  64-column
+    fold operands are laid out like any other k-block; 16-column ones rely on TMA zero-filling the
+    out-of-range part of the {64, rows} box (4 KB instead of 16 KB of L2 traffic per tile)."""
+    monkeypatch.setenv("VTC_RANK_FOLD", "1")
+    monkeypatch.setenv("VTC_FOLD_COLS", str(request.param))
 
 
 # resident query tile (K' <= 512) and streamed (D = 768; every exact-mode K' = 3D), ragged edges

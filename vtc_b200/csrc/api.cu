@@ -86,6 +86,11 @@ bool rank_fold_enabled() {
   const char* e = getenv("VTC_RANK_FOLD");
   return e && *e && atoi(e) != 0;
 }
+// columns of the fold operands in global memory (fold.cuh): 64 (default) or 16
+int fold_cols() {
+  const char* e = getenv("VTC_FOLD_COLS");
+  return e && atoi(e) == 16 ? 16 : FOLD_COLS_MAX;
+}
 
 size_t amb_entries_wanted(int64_t N) {
   const int64_t want = 64 * N;
@@ -106,8 +111,8 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
     r.sq32 = ws.take<float>(round_up<int64_t>(M, tc::BN));
     r.thr = ws.take<float2>(N);
     r.rank_tmp = ws.take<int>(N);
-    r.foldQ = ws.take<__nv_bfloat16>((size_t)N * FOLD_COLS);
-    r.foldG = ws.take<__nv_bfloat16>((size_t)round_up<int64_t>(M, tc::BN) * FOLD_COLS);
+    r.foldQ = ws.take<__nv_bfloat16>((size_t)N * FOLD_COLS_MAX);
+    r.foldG = ws.take<__nv_bfloat16>((size_t)round_up<int64_t>(M, tc::BN) * FOLD_COLS_MAX);
     r.foldW = ws.take<float>(N);
     if (sizing) {
       r.amb_cap = amb_entries_wanted(N);
@@ -209,14 +214,16 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   if (rank_fold_enabled() && pl.cluster == 2 && w.foldQ && w.foldG && w.foldW) {
     // fold pass: the bias and d(t,gt) enter through one extra K16 step (fold.cu); always a CTA pair
     const int64_t Mpad = round_up<int64_t>(M, tc::BN);
-    VTC_RETURN_IF_ERROR(launch_fold_g(w.sq64, M, Mpad, metric, w.foldG, &w.scalars[2], s));
+    const int fc = fold_cols();
+    VTC_RETURN_IF_ERROR(launch_fold_g(w.sq64, M, Mpad, metric, w.foldG, fc, &w.scalars[2], s));
     VTC_RETURN_IF_ERROR(launch_fold_q(w.thr, w.dgt, &w.scalars[0], N, metric,
-                                      guard_rel_for(precision, o.Kp), w.foldQ, w.foldW,
+                                      guard_rel_for(precision, o.Kp), w.foldQ, fc, w.foldW,
                                       &w.scalars[2], s));
+    // the box is {64, rows} either way: with 16-column operands the rest of each 128-byte row is
+    // out of range and zero-filled by TMA, exactly like a K tail
     CUtensorMap tmAx, tmBx;
-    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.foldQ, N, FOLD_COLS, FOLD_COLS, tc::BM, &tmAx));
-    VTC_RETURN_IF_ERROR(
-        tc::make_operand_tmap(w.foldG, Mpad, FOLD_COLS, FOLD_COLS, tc::BN / 2, &tmBx));
+    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.foldQ, N, fc, fc, tc::BM, &tmAx));
+    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.foldG, Mpad, fc, fc, tc::BN / 2, &tmBx));
     p.fold_w = w.foldW;
     pl.pair = true;
     VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK_FOLD, p.num_kb <= 8, pl, tmA, tmB, p, s,

@@ -29,17 +29,17 @@ __device__ __forceinline__ void split3(double v, unsigned short (&p)[3]) {
 constexpr unsigned short kOne = 0x3f80;  // bf16 1.0
 constexpr double kFar = -1.0e30;         // "never closer, never in the band"
 
-__device__ __forceinline__ void store_fold_row(__nv_bfloat16* row, const unsigned short (&e)[6]) {
+__device__ __forceinline__ void store_fold_row(__nv_bfloat16* row, int cols,
+                                               const unsigned short (&e)[6]) {
   uint4* o = reinterpret_cast<uint4*>(row);
   o[0] = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16),
                     (uint32_t)e[4] | ((uint32_t)e[5] << 16), 0u);
-#pragma unroll
-  for (int i = 1; i < FOLD_COLS / 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = 1; i < cols / 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __global__ void fold_q_kernel(const float2* __restrict__ thr, const double* __restrict__ dgt,
                               const unsigned int* __restrict__ max_sq_bits, int64_t N, int metric,
-                              float guard_rel, __nv_bfloat16* __restrict__ Qx,
+                              float guard_rel, __nv_bfloat16* __restrict__ Qx, int cols,
                               float* __restrict__ fold_w, unsigned int* __restrict__ invalid) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N) return;
@@ -72,12 +72,13 @@ __global__ void fold_q_kernel(const float2* __restrict__ thr, const double* __re
   unsigned short p[3];
   split3(m, p);
   const unsigned short e[6] = {p[0], p[1], p[2], kOne, kOne, kOne};
-  store_fold_row(Qx + t * FOLD_COLS, e);
+  store_fold_row(Qx + t * cols, cols, e);
   fold_w[t] = w;
 }
 
 __global__ void fold_g_kernel(const double* __restrict__ sq64, int64_t M, int64_t Mpad, int metric,
-                              __nv_bfloat16* __restrict__ Gx, unsigned int* __restrict__ invalid) {
+                              __nv_bfloat16* __restrict__ Gx, int cols,
+                              unsigned int* __restrict__ invalid) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Mpad) return;
   double h = kFar;
@@ -91,26 +92,28 @@ __global__ void fold_g_kernel(const double* __restrict__ sq64, int64_t M, int64_
   unsigned short p[3];
   split3(h, p);
   const unsigned short e[6] = {kOne, kOne, kOne, p[0], p[1], p[2]};
-  store_fold_row(Gx + j * FOLD_COLS, e);
+  store_fold_row(Gx + j * cols, cols, e);
 }
 
 }  // namespace
 
 int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_sq_bits, int64_t N,
-                  int metric, float guard_rel, __nv_bfloat16* Qx, float* fold_w,
+                  int metric, float guard_rel, __nv_bfloat16* Qx, int cols, float* fold_w,
                   unsigned int* invalid, cudaStream_t s) {
   if (N == 0) return VTC_OK;
+  if (cols != 16 && cols != 64) return VTC_ERR_INVALID_ARG;
   fold_q_kernel<<<(unsigned)ceil_div<int64_t>(N, 128), 128, 0, s>>>(
-      thr, dgt, max_sq_bits, N, metric, guard_rel, Qx, fold_w, invalid);
+      thr, dgt, max_sq_bits, N, metric, guard_rel, Qx, cols, fold_w, invalid);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }
 
 int launch_fold_g(const double* sq64, int64_t M, int64_t Mpad, int metric, __nv_bfloat16* Gx,
-                  unsigned int* invalid, cudaStream_t s) {
+                  int cols, unsigned int* invalid, cudaStream_t s) {
   if (Mpad == 0) return VTC_OK;
+  if (cols != 16 && cols != 64) return VTC_ERR_INVALID_ARG;
   fold_g_kernel<<<(unsigned)ceil_div<int64_t>(Mpad, 128), 128, 0, s>>>(sq64, M, Mpad, metric, Gx,
-                                                                     invalid);
+                                                                     cols, invalid);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }

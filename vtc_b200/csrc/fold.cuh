@@ -6,22 +6,26 @@
 
 namespace vtc {
 
-constexpr int FOLD_COLS = 64;  // bf16 per fold-operand row: one 128-byte swizzle atom, like a k-block
+// bf16 per fold-operand row in global memory.  64 = one whole 128-byte swizzle atom, laid out like
+// any other k-block.  16 = only the K16 slice that is multiplied: the TMA box stays {64, rows} and
+// the 48 out-of-range columns are zero-filled (as for a K tail), so a tile's fold block costs 4 KB of
+// L2 -> shared-memory traffic instead of 16 KB.  VTC_FOLD_COLS selects (default 64).
+constexpr int FOLD_COLS_MAX = 64;
 
-// Qx [N, 64] bf16 = [ m'_t (three bf16 pieces) | 1 1 1 | 0 ... ] and fold_w [N]: half-width of the
+// Qx [N, cols] bf16 (cols = 16 or 64) = [ m'_t (three bf16 pieces) | 1 1 1 | 0 ... ] and fold_w [N]: half-width of the
 // guard band around acc' = 0, derived from the (lo, hi) thresholds and d(t,gt) that
 // launch_gt_score produced.  Rows whose ground-truth score is NaN get m' = -1e30, w = -1 (they count
 // nothing and never push; vtc_rank_finalize gives them rank M); an infinite score sets *invalid = 1
 // (brute-force fallback, as for launch_fold_g).
 int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_sq_bits, int64_t N,
-                  int metric, float guard_rel, __nv_bfloat16* Qx, float* fold_w,
+                  int metric, float guard_rel, __nv_bfloat16* Qx, int cols, float* fold_w,
                   unsigned int* invalid, cudaStream_t s);
 
-// Gx [Mpad, 64] bf16 = [ 1 1 1 | h_j (three bf16 pieces) | 0 ... ], h_j = -||x_j||^2 / 2 (L2) or 0
+// Gx [Mpad, cols] bf16 = [ 1 1 1 | h_j (three bf16 pieces) | 0 ... ], h_j = -||x_j||^2 / 2 (L2) or 0
 // (DOT); padding rows j >= M carry h = -1e30 (never closer, never inside the band).  A gallery row
 // whose squared norm is not finite sets *invalid = 1: the caller's brute-force fallback then
 // recomputes the whole call in canonical arithmetic.
 int launch_fold_g(const double* sq64, int64_t M, int64_t Mpad, int metric, __nv_bfloat16* Gx,
-                  unsigned int* invalid, cudaStream_t s);
+                  int cols, unsigned int* invalid, cudaStream_t s);
 
 }  // namespace vtc
