@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check, launched under torchrun (one rank per GPU, NCCL):
-row-sharded rank eval and gallery-sharded top-k against the CPU oracle."""
+"""Multi-GPU parity check, launched under torchrun by tests/test_multigpu.py (one rank per GPU,
+NCCL): row-sharded rank eval and gallery-sharded top-k against the CPU oracle.  Lives under tests/
+because it is a checker: nothing outside tests/, smoke() and bench.py's CPU baseline touches oracle/."""
 import os
 import sys
 

@@ -93,14 +93,20 @@ def test_product_path_fails_loudly_without_cuda():
 
 
 def test_product_never_imports_the_oracle():
-    """The oracle is test infrastructure: nothing under vtc_b200/ may import or call it."""
-    pkg = os.path.join(ROOT, "vtc_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
-                assert "vtc_oracle" not in src.replace("oracle/vtc_oracle", ""), f
+    """The oracle is test infrastructure: nothing under vtc_b200/ or scripts/ may import or call
+    it; the only users are tests/, __graft_entry__.smoke() and the CPU-baseline leg of bench.py."""
+    for top in ("vtc_b200", "scripts"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".sh")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                    assert "vtc_oracle" not in src.replace("oracle/vtc_oracle", ""), f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"^\s*(from|import)\s+oracle\b", bench, flags=re.M)]
+    assert len(uses) == 1  # inside cpu_reference_pairs_per_s only
+    fn = bench.index("def cpu_reference_pairs_per_s")
+    assert fn < uses[0] < bench.index("def run_reference")
 
 
 def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):

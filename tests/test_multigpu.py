@@ -18,7 +18,7 @@ def test_sharded_eval_nccl(cuda_dev):
     n = 2 if n < 4 else (4 if n < 8 else 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29517",
-           os.path.join(ROOT, "scripts", "dist_check.py")]
+           os.path.join(ROOT, "tests", "nccl_parity_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MISMATCH" not in r.stdout
