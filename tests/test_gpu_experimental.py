@@ -152,3 +152,16 @@ def test_fold_10k_and_100k_slice(cuda_dev, fold):
     base, _ = ops.sim_rank(q, g, precision="bf16")
     os.environ["VTC_RANK_FOLD"] = "1"
     np.testing.assert_array_equal(_np(rank_bf16), _np(base))
+
+
+def test_more_than_eight_k_values(cuda_dev):
+    """RecallAtK accepts any number of k values like the reference (model/metric.py:104-108); the C
+    entry point counts 8 per call."""
+    from vtc_b200.model.metric import RecallAtK
+
+    T, V = make_retrieval_pair(400, 400, 64, sigma=3.0, seed=4)
+    ks = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 20, 50]
+    got = RecallAtK("v", "t", ks).compute(V.to(cuda_dev), T.to(cuda_dev))
+    want = O.recall_at_k(V.numpy(), T.numpy(), ks)
+    assert [k for k, _ in got] == ks
+    assert [r for _, r in got] == [r for _, r in want]

@@ -248,7 +248,11 @@ def rank_finalize(rank0: torch.Tensor, gt_score: Optional[torch.Tensor], M_total
     dev = _req_cuda(rank0, gt_score)
     k_vals = [int(k) for k in k_vals]
     if len(k_vals) > 8:
-        raise ValueError("at most 8 k values")
+        # the entry point takes up to 8 thresholds per call (the reference's configs use 2-3,
+        # model/metric.py:104); more are counted 8 at a time -- the NaN -> M_total pass is idempotent
+        parts = [rank_finalize(rank0, gt_score, M_total, k_vals[i:i + 8], want_medr and i == 0)
+                 for i in range(0, len(k_vals), 8)]
+        return torch.cat([h for h, _ in parts]), parts[0][1]
     hits = torch.zeros(max(1, len(k_vals)), dtype=torch.int64, device=dev)
     medr = torch.empty(1, dtype=torch.float64, device=dev) if want_medr else None
     karr = (ctypes.c_int * max(1, len(k_vals)))(*k_vals)
