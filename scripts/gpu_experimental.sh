@@ -21,6 +21,13 @@ for fold in 0 1 2; do
     echo "bench fold=$fold $args exit=$?" >> $S
   done
 done
+# guard-band thresholds from a coalesced fp32 norm (fewer fp64 row walks per library call): the e2e
+# number has 11 calls per evaluation, the device-resident step one
+for ft in 0 1; do
+  VTC_FAST_THR=$ft timeout 200 python bench.py --steps 10 --no-cpu-baseline \
+      > gpurun_out/${TAG}_fold0_fastthr$ft.json 2> gpurun_out/${TAG}_fastthr$ft.err
+  echo "bench fast_thr=$ft exit=$?" >> $S
+done
 # host staging schedule of RecallAtK.compute (the e2e number): equal chunks vs the balanced schedule
 for sch in equal balanced; do
   for c in 6 8; do

@@ -165,3 +165,35 @@ def test_more_than_eight_k_values(cuda_dev):
     want = O.recall_at_k(V.numpy(), T.numpy(), ks)
     assert [k for k, _ in got] == ks
     assert [r for _, r in got] == [r for _, r in want]
+
+
+# VTC_FAST_THR=1 -- the guard-band thresholds from a coalesced fp32 norm of the query rows (an upper
+# bound of ||q|| is all the band needs) instead of gt_score_kernel's second fp64 walk; alone and
+# together with the fold epilogue, incl. the chunked (gt_score given) calls it helps most
+@pytest.mark.parametrize("fold_on", [False, True])
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+def test_fast_thresholds_same_ranks(cuda_dev, monkeypatch, golden, precision, fold_on):
+    from vtc_b200 import ops
+
+    monkeypatch.setenv("VTC_FAST_THR", "1")
+    monkeypatch.setenv("VTC_RANK_FOLD", "1" if fold_on else "0")
+    for N, M, D, metric in ((1000, 1000, 512, "l2"), (333, 1201, 96, "dot"), (129, 257, 768, "l2")):
+        T, V = make_retrieval_pair(N, M, D, sigma=4.0, seed=N + M)
+        rank0, gts = ops.sim_rank(T.to(cuda_dev), V.to(cuda_dev), metric=metric, precision=precision)
+        ops.rank_finalize(rank0, gts, M, [1])
+        np.testing.assert_array_equal(_np(rank0), _oracle_ranks(T, V, metric, precision))
+    g = golden("retrieval_small.npz")           # ties, zero row, non-unit row, NaN query
+    Q, G = torch.from_numpy(g["queries"]), torch.from_numpy(g["gallery"])
+    rank0, gts = ops.sim_rank(Q.to(cuda_dev), G.to(cuda_dev), precision=precision)
+    ops.rank_finalize(rank0, gts, G.shape[0], [1])
+    want = _oracle_ranks(Q, G, "l2", precision) if precision == "bf16" else g["rank0"]
+    np.testing.assert_array_equal(_np(rank0), want)
+    T, V = make_retrieval_pair(500, 2000, 256, sigma=4.0, seed=21)
+    q, gal = T.to(cuda_dev), V.to(cuda_dev)
+    whole, gts = ops.sim_rank(q, gal, precision=precision)
+    acc = torch.zeros(500, dtype=torch.int32, device=cuda_dev)
+    for s, e in ((0, 700), (700, 701), (701, 2000)):
+        ops.sim_rank(q, gal[s:e].contiguous(), col_offset=s, precision=precision, gt_score=gts,
+                     rank0=acc, accumulate=True)
+    np.testing.assert_array_equal(_np(acc), _np(whole))
+    np.testing.assert_array_equal(_np(whole), _oracle_ranks(T, V, "l2", precision))

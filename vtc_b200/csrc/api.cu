@@ -86,6 +86,12 @@ bool rank_fold_enabled() {
   const char* e = getenv("VTC_RANK_FOLD");
   return e && *e && atoi(e) != 0;
 }
+// Opt-in until timed on a B200 (VTC_FAST_THR=1): guard-band thresholds from a coalesced fp32 norm
+// of the query rows (launch_thr_fast) instead of gt_score_kernel's second fp64 walk over them.
+bool fast_thr_enabled() {
+  const char* e = getenv("VTC_FAST_THR");
+  return e && *e && atoi(e) != 0;
+}
 // columns of the fold operands in global memory (fold.cuh): 64 (default) or 16
 int fold_cols() {
   const char* e = getenv("VTC_FOLD_COLS");
@@ -186,8 +192,14 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     ex = ExactArgs{opQ, opG, o.Kp, o.Kp, true, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
   // 2. canonical norms, ground-truth scores, guard band
   VTC_RETURN_IF_ERROR(launch_sqnorm64(ex.G, ex.bf16, M, D, ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
-  VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0],
-                                      guard_rel_for(precision, o.Kp), s));
+  if (fast_thr_enabled()) {
+    VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, nullptr, nullptr, 0.f, s));
+    VTC_RETURN_IF_ERROR(launch_thr_fast(ex.Q, ex.bf16, ex.ldq, N, D, w.dgt, &w.scalars[0], metric,
+                                        guard_rel_for(precision, o.Kp), w.thr, s));
+  } else {
+    VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0],
+                                        guard_rel_for(precision, o.Kp), s));
+  }
   // per-column epilogue bias: ||x_j||^2 (L2) or 0 (DOT); padding columns are +inf (never counted)
   VTC_RETURN_IF_ERROR(launch_fill_bias(w.sq32, metric == VTC_METRIC_L2 ? w.sq32 : nullptr, M,
                                        round_up<int64_t>(M, tc::BN), INFINITY, s));

@@ -95,7 +95,56 @@ __global__ void fold_g_kernel(const double* __restrict__ sq64, int64_t M, int64_
   store_fold_row(Gx + j * cols, cols, e);
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+thr_fast_kernel(const T* __restrict__ Q, int64_t ldq, int64_t N, int D,
+                const double* __restrict__ dgt, const unsigned int* __restrict__ max_sq_bits,
+                int metric, float guard_rel, float2* __restrict__ thr) {
+  const int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= N) return;
+  const int lane = threadIdx.x & 31;
+  const T* q = Q + t * ldq;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float v = to_f32(q[k]);
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane != 0) return;
+  const double d0 = dgt[t];
+  // fp32 accumulation of D non-negative terms is within (D/32 + 5) ulp of the exact sum: 1e-4 covers
+  // every D the library accepts (<= 8192)
+  const double qq = (double)s * (1.0 + 1.0e-4);
+  const double qn = sqrt(qq);
+  const double gmax_sq = (double)__uint_as_float(*max_sq_bits);
+  const double gn = sqrt(gmax_sq);
+  double delta;  // exact.cu::gt_score_kernel
+  if (metric == VTC_METRIC_L2)
+    delta = 2.0 * guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn);
+  else
+    delta = (double)guard_rel * qn * gn + 1.2e-7 * qn * gn;
+  float lo = __double2float_rd(d0 - delta);
+  float hi = __double2float_ru(d0 + delta);
+  if (!(s == s) || !(d0 == d0)) lo = hi = nanf("");
+  thr[t] = make_float2(lo, hi);
+}
+
 }  // namespace
+
+int launch_thr_fast(const void* Q, bool bf16, int64_t ldq, int64_t N, int D, const double* dgt,
+                    const unsigned int* max_sq_bits, int metric, float guard_rel, float2* thr,
+                    cudaStream_t s) {
+  if (N == 0) return VTC_OK;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(N, 8);
+  if (bf16)
+    thr_fast_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)Q, ldq, N, D, dgt,
+                                                       max_sq_bits, metric, guard_rel, thr);
+  else
+    thr_fast_kernel<float><<<grid, 256, 0, s>>>((const float*)Q, ldq, N, D, dgt, max_sq_bits, metric,
+                                                guard_rel, thr);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
 
 int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_sq_bits, int64_t N,
                   int metric, float guard_rel, __nv_bfloat16* Qx, int cols, float* fold_w,

@@ -28,4 +28,13 @@ int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_
 int launch_fold_g(const double* sq64, int64_t M, int64_t Mpad, int metric, __nv_bfloat16* Gx,
                   int cols, unsigned int* invalid, cudaStream_t s);
 
+// Opt-in (VTC_FAST_THR=1): the (lo, hi) guard-band thresholds of launch_gt_score from a coalesced
+// fp32 row norm instead of a second fp64-sequential walk over every query row.  The band only needs
+// an UPPER bound of ||q_t|| (the scores themselves stay canonical), so ||q||^2 is summed in fp32 by a
+// warp and inflated by 1e-4; everything else is gt_score_kernel's formula.  Q / ldq / bf16 / D are
+// the canonical query rows (ExactArgs), dgt the canonical d(t,gt).
+int launch_thr_fast(const void* Q, bool bf16, int64_t ldq, int64_t N, int D, const double* dgt,
+                    const unsigned int* max_sq_bits, int metric, float guard_rel, float2* thr,
+                    cudaStream_t s);
+
 }  // namespace vtc
