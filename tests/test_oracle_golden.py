@@ -156,3 +156,52 @@ def test_eval_tail_matches_reference_semantics():
     assert v.shape == (3, 8) and c.shape == (3, 2, 8)
     assert torch.isinf(c[0, 1]).all() and (c[0, 1] < 0).all()
     torch.testing.assert_close(v[1], vids[1].mean(0))
+
+
+def test_c_oracle_against_a_pure_python_restatement_of_the_canonical_arithmetic():
+    """The C oracle is the anchor every CUDA rank / top-k is compared with, so it is itself pinned to
+    the definition written out in plain Python: dot = fold_k acc + q_k * x_k in k
+    order (the product of two floats is exact in a double, so `acc + a * b` IS the fused
+    multiply-add), d = sq(x) - 2 dot (L2) or -dot (DOT), rank0 = #{j != gt: d_j < d_gt} +
+    #{j < gt: d_j == d_gt}, NaN comparisons false, top-k by (score, index).  Values come from a
+    small grid so that exact ties, duplicates, zero rows and a NaN are all present."""
+    rng = np.random.default_rng(7)
+    grid = np.array([-1.5, -0.5, 0.0, 0.25, 0.5, 1.0, 3.0], dtype=np.float32)
+    N, M, D = 23, 41, 9
+    Q = rng.choice(grid, size=(N, D)).astype(np.float32)
+    G = rng.choice(grid, size=(M, D)).astype(np.float32)
+    G[5] = G[30]                      # duplicate rows -> exact ties
+    G[7] = 0.0                        # zero row
+    Q[:10] = G[:10] + rng.choice(np.array([0.0, 0.25], dtype=np.float32), size=(10, D))
+    Q[3, 2] = np.nan
+    gt = rng.integers(0, M, size=N)
+
+    def dot(a, b):
+        acc = 0.0
+        for x, y in zip(a.tolist(), b.tolist()):
+            acc = acc + x * y
+        return acc
+
+    for metric in (O.METRIC_L2, O.METRIC_DOT):
+        d = np.empty((N, M))
+        for t in range(N):
+            for j in range(M):
+                d[t, j] = (dot(G[j], G[j]) - 2.0 * dot(Q[t], G[j])) if metric == O.METRIC_L2 \
+                    else -dot(Q[t], G[j])
+        np.testing.assert_array_equal(O.scores64(Q, G, metric), d)
+        want = np.zeros(N, dtype=np.int64)
+        for t in range(N):
+            d0 = d[t, gt[t]]
+            for j in range(M):
+                if j != gt[t] and (d[t, j] < d0 or (d[t, j] == d0 and j < gt[t])):
+                    want[t] += 1
+        got = O.rank0_exact(Q, G, gt=gt, metric=metric)
+        ok = ~np.isnan(d[np.arange(N), gt])   # a NaN score: vtc_rank_finalize's business (rank = M)
+        np.testing.assert_array_equal(got[ok], want[ok])
+        vals, idx = O.topk_exact(Q, G, 6, metric=metric)
+        for t in range(N):
+            if np.isnan(d[t]).any():
+                continue
+            order = sorted(range(M), key=lambda j: (d[t, j], j))[:6]
+            np.testing.assert_array_equal(idx[t], order)
+            np.testing.assert_array_equal(vals[t], d[t, order])
