@@ -12,8 +12,8 @@ namespace vtc {
 // L2 -> shared-memory traffic instead of 16 KB.  VTC_FOLD_COLS selects (default 64).
 constexpr int FOLD_COLS_MAX = 64;
 
-// Qx [N, cols] bf16 (cols = 16 or 64) = [ m'_t (three bf16 pieces) | 1 1 1 | 0 ... ] and fold_w [N]: half-width of the
-// guard band around acc' = 0, derived from the (lo, hi) thresholds and d(t,gt) that
+// Qx [N, cols] bf16 (cols = 16 or 64) = [ m'_t (three bf16 pieces) | 1 1 1 | 0 ... ] and
+// fold_w [N]: half-width of the guard band around acc' = 0, derived from the (lo, hi) thresholds and d(t,gt) that
 // launch_gt_score produced.  Rows whose ground-truth score is NaN get m' = -1e30, w = -1 (they count
 // nothing and never push; vtc_rank_finalize gives them rank M); an infinite score sets *invalid = 1
 // (brute-force fallback, as for launch_fold_g).

@@ -166,8 +166,9 @@ struct RankEpi {
 // RankEpi with the per-column bias and the per-row ground-truth score FOLDED INTO THE MMA
 // (EPI_RANK_FOLD; opt-in, VTC_RANK_FOLD=1).  One extra K16 step per tile multiplies the fold
 // operands
-//     Qx[t] = [ m'_t in three bf16 pieces | 1 1 1 | 0 ... ],  Gx[j] = [ 1 1 1 | h_j in three pieces | 0 ... ]
-// (m'_t = d(t,gt)/2, h_j = -||x_j||^2/2 for L2; m'_t = d(t,gt), h_j = 0 for DOT; exact.cu), so the
+//     Qx[t] = [ m'_t in three bf16 pieces | 1 1 1 | 0 ... ]
+//     Gx[j] = [ 1 1 1 | h_j in three bf16 pieces | 0 ... ]
+// (m'_t = d(t,gt)/2, h_j = -||x_j||^2/2 for L2; m'_t = d(t,gt), h_j = 0 for DOT; fold.cu), so the
 // accumulator is acc' = q.x + h_j + m'_t and "column j is closer than the ground truth" is
 // acc' > 0.  Per logit the epilogue is then one sign-bit add (LEA.HI) and half a three-input
 // |min| (FMNMX3) instead of FFMA + 2 FSET + 2 FADD + the bias staging: a group of 8 columns is
