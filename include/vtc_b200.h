@@ -124,6 +124,24 @@ int vtc_sim_rank(const void* Q, const void* G, int64_t N, int64_t M, int D, int 
                  int precision, const double* gt_score, double* gt_score_out, int accumulate,
                  int32_t* rank0, void* ws, size_t ws_bytes, vtc_stream_t stream);
 
+/* ---- prepared ranking: per-row quantities computed once per chunk, reused by every call ----------
+ * A chunked evaluation (host staging pipelined against the ranking, gallery shards gathered over
+ * NVLink) calls vtc_sim_rank many times on the same rows; each call re-walks its gallery rows for
+ * ||x||^2 and its query rows for the guard band.  vtc_rank_prepare computes, for a block of rows,
+ *   sq64  [rows] fp64 : canonical ||x_r||^2 (what vtc_sim_rank computes internally; gallery side)
+ *   qq_up [rows] fp32 : an upper bound of ||x_r||^2 (query side; the guard band needs no more)
+ * (either may be NULL).  vtc_sim_rank_prepared is vtc_sim_rank with gt_score, the sq64 of THIS G
+ * and the qq_up of THIS Q given: no row is read outside the tensor-core pass and the re-check.
+ * The rows must already be the canonical values: bf16 rows with VTC_PREC_BF16, fp32 rows with
+ * VTC_PREC_EXACT (VTC_ERR_UNSUPPORTED_SHAPE otherwise).  Same results as vtc_sim_rank. */
+int vtc_rank_prepare(const void* X, int64_t rows, int D, int dtype, int precision, double* sq64,
+                     float* qq_up, vtc_stream_t stream);
+int vtc_sim_rank_prepared(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                          const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
+                          int precision, const double* gt_score, const double* sq64,
+                          const float* qq_up, int accumulate, int32_t* rank0, void* ws,
+                          size_t ws_bytes, vtc_stream_t stream);
+
 /* fp64-sequential d(t,gt) for each query (also the pre-pass of vtc_sim_rank). */
 int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
                   const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,

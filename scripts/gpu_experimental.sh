@@ -28,12 +28,16 @@ for ft in 0 1; do
       > gpurun_out/${TAG}_fold0_fastthr$ft.json 2> gpurun_out/${TAG}_fastthr$ft.err
   echo "bench fast_thr=$ft exit=$?" >> $S
 done
-# host staging schedule of RecallAtK.compute (the e2e number): equal chunks vs the balanced schedule
-for sch in equal balanced; do
-  for c in 6 8; do
-    VTC_PIPELINE_SCHEDULE=$sch VTC_PIPELINE_CHUNKS_2D=$c timeout 200 python bench.py --steps 10 \
-        --no-cpu-baseline > gpurun_out/${TAG}_fold0_e2e_${sch}_c$c.json 2> gpurun_out/${TAG}_e2e_${sch}_c$c.err
-    echo "bench e2e schedule=$sch c=$c exit=$?" >> $S
+# host staging of RecallAtK.compute (the e2e number): equal chunks vs the balanced schedule, per-call
+# row walks vs per-chunk prepared quantities (vtc_sim_rank_prepared)
+for prep in 0 1; do
+  for sch in equal balanced; do
+    for c in 6 8; do
+      VTC_RANK_PREPARED=$prep VTC_PIPELINE_SCHEDULE=$sch VTC_PIPELINE_CHUNKS_2D=$c timeout 200 \
+          python bench.py --steps 10 --no-cpu-baseline \
+          > gpurun_out/${TAG}_fold0_e2e_prep${prep}_${sch}_c$c.json 2> gpurun_out/${TAG}_e2e_prep${prep}_${sch}_c$c.err
+      echo "bench e2e prepared=$prep schedule=$sch c=$c exit=$?" >> $S
+    done
   done
 done
 python scripts/show_bench.py gpurun_out/${TAG}_fold*.json 2>&1 | cut -c1-200 >> $S

@@ -29,7 +29,7 @@ for n in 1 2 4 8; do
 done
 # opt-in variants of the sharded step on all GPUs, same box as the default above: one library call
 # over the whole gathered gallery (VTC_SHARD_SINGLE_PASS=1), the fold epilogue (VTC_RANK_FOLD=1), both
-for v in "VTC_SHARD_SINGLE_PASS=1" "VTC_RANK_FOLD=1" "VTC_SHARD_SINGLE_PASS=1 VTC_RANK_FOLD=1"; do
+for v in "VTC_RANK_PREPARED=1" "VTC_SHARD_SINGLE_PASS=1" "VTC_RANK_FOLD=1" "VTC_RANK_PREPARED=1 VTC_RANK_FOLD=1"; do
   name=$(echo "$v" | tr -d ' =' | tr 'A-Z' 'a-z')
   env $v timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
       --master-port 29535 bench.py --gpus $NG --steps 20 --warmup 3 --no-cpu-baseline --no-e2e \

@@ -197,3 +197,69 @@ def test_fast_thresholds_same_ranks(cuda_dev, monkeypatch, golden, precision, fo
                      rank0=acc, accumulate=True)
     np.testing.assert_array_equal(_np(acc), _np(whole))
     np.testing.assert_array_equal(_np(whole), _oracle_ranks(T, V, "l2", precision))
+
+
+# vtc_rank_prepare / vtc_sim_rank_prepared -- norms, norm bounds and ground-truth scores computed
+# once per chunk and handed to every call that touches the chunk (new entry points; used by the
+# host-staging pipeline and the sharded step when VTC_RANK_PREPARED=1)
+@pytest.mark.parametrize("fold_on", [False, True])
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+def test_prepared_ranking_same_ranks(cuda_dev, monkeypatch, golden, precision, fold_on):
+    from vtc_b200 import ops
+
+    monkeypatch.setenv("VTC_RANK_FOLD", "1" if fold_on else "0")
+
+    def canon(x):  # the rows must already be the canonical values of the mode
+        return x.to(cuda_dev).bfloat16() if precision == "bf16" else x.to(cuda_dev)
+
+    cases = [make_retrieval_pair(1000, 1000, 512, sigma=4.0, seed=3) + ("l2",),
+             make_retrieval_pair(333, 1201, 96, sigma=2.0, seed=4) + ("dot",),
+             make_retrieval_pair(129, 257, 768, sigma=7.0, seed=5) + ("l2",)]
+    g = golden("retrieval_small.npz")           # ties, zero row, non-unit row, NaN query
+    cases.append((torch.from_numpy(g["queries"]), torch.from_numpy(g["gallery"]), "l2"))
+    for T, V, metric in cases:
+        q, gal = canon(T), canon(V)
+        N, M = q.shape[0], gal.shape[0]
+        want = _oracle_ranks(T, V, metric, precision)
+        gts = ops.gt_scores(q, gal, metric=metric, precision=precision)
+        sq64, _ = ops.rank_prepare(gal, precision, want_qq=False)
+        _, qq = ops.rank_prepare(q, precision, want_sq64=False)
+        np.testing.assert_array_equal(_np(sq64), O.sqnorm64(_np(gal.float())))
+        assert (_np(qq) >= O.sqnorm64(_np(q.float())))[~np.isnan(_np(qq))].all()
+        # whole gallery in one prepared call
+        rank0 = torch.full((N,), -5, dtype=torch.int32, device=cuda_dev)
+        ops.sim_rank(q, gal, metric=metric, precision=precision, gt_score=gts, rank0=rank0,
+                     accumulate=False, sq64=sq64, qq=qq)
+        ops.rank_finalize(rank0, gts, M, [1])
+        np.testing.assert_array_equal(_np(rank0), want)
+        # ... and accumulated over ragged gallery chunks with slices of the same arrays
+        acc = torch.zeros(N, dtype=torch.int32, device=cuda_dev)
+        bounds = [0, M // 3, M // 3 + 1, M]
+        for s, e in zip(bounds[:-1], bounds[1:]):
+            ops.sim_rank(q, gal[s:e].contiguous(), col_offset=s, metric=metric, precision=precision,
+                         gt_score=gts, rank0=acc, accumulate=True, sq64=sq64[s:e].contiguous(), qq=qq)
+        ops.rank_finalize(acc, gts, M, [1])
+        np.testing.assert_array_equal(_np(acc), want)
+
+
+@pytest.mark.parametrize("schedule", ["equal", "balanced"])
+def test_prepared_host_staging_pipeline(cuda_dev, monkeypatch, schedule):
+    """RecallAtK.compute from host arrays with VTC_RANK_PREPARED=1 (and the balanced chunk schedule):
+    same recalls and ranks as the oracle."""
+    from vtc_b200.model.metric import RecallAtK
+
+    monkeypatch.setenv("VTC_RANK_PREPARED", "1")
+    monkeypatch.setenv("VTC_PIPELINE_SCHEDULE", schedule)
+    N, D = 40_000, 256                           # 41 MB per side: above PIPELINE_MIN_BYTES
+    T, V = make_retrieval_pair(N, N, D, sigma=5.0, seed=12)
+    for precision in ("bf16", "exact"):
+        m = RecallAtK("v", "t", [1, 5, 10], precision=precision)
+        full = m.compute_full(V.numpy(), T.numpy())
+        sl = slice(20_000, 20_200)
+        want = _oracle_ranks(T[sl], V, "l2", precision, row_offset=20_000)
+        np.testing.assert_array_equal(_np(full["rank0"][sl]), want)
+        monkeypatch.setenv("VTC_RANK_PREPARED", "0")
+        base = m.compute_full(V.numpy(), T.numpy())
+        monkeypatch.setenv("VTC_RANK_PREPARED", "1")
+        np.testing.assert_array_equal(_np(full["rank0"]), _np(base["rank0"]))
+        np.testing.assert_array_equal(_np(full["hits"]), _np(base["hits"]))

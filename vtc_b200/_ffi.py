@@ -33,6 +33,9 @@ SIGNATURES = {
                                c_size_t, _P]),
     "vtc_sim_rank": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int,
                              c_int, _P, _P, c_int, _P, _P, c_size_t, _P]),
+    "vtc_rank_prepare": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    "vtc_sim_rank_prepared": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64,
+                                      c_int, c_int, _P, _P, _P, c_int, _P, _P, c_size_t, _P]),
     "vtc_gt_scores": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int,
                               c_int, _P, _P, c_size_t, _P]),
     "vtc_rank_finalize": (c_int, [_P, _P, c_int64, c_int64, POINTER(c_int), c_int, _P, _P, _P,

@@ -135,12 +135,19 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   return r;
 }
 
+// sq64_in / qq_in (both or neither; vtc_sim_rank_prepared): canonical ||x_j||^2 of THIS gallery
+// chunk and an upper bound of ||q_t||^2, computed once by vtc_rank_prepare.  With them (and a given
+// gt_score) the call walks no row outside the tensor-core pass and the re-check.
 int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
                   const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
                   int precision, const double* gt_score, double* gt_score_out, int accumulate,
-                  int32_t* rank0, void* wsp, size_t ws_bytes, cudaStream_t s) {
+                  int32_t* rank0, void* wsp, size_t ws_bytes, cudaStream_t s,
+                  const double* sq64_in = nullptr, const float* qq_in = nullptr) {
   if (N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) || !valid_metric(metric) ||
       !valid_prec(precision))
+    return VTC_ERR_INVALID_ARG;
+  const bool prepared = sq64_in != nullptr;
+  if (prepared && (!qq_in || !gt_score || precision == VTC_PREC_BRUTE || M == 0))
     return VTC_ERR_INVALID_ARG;
   if (N == 0) return VTC_OK;  // no queries: nothing to rank (pointers may be NULL)
   if (!Q || (!G && M > 0) || !rank0) return VTC_ERR_INVALID_ARG;
@@ -185,26 +192,38 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D,
                                             o.split ? PREP_SPLIT_B : PREP_PLAIN, w.opG, o.Kp, s));
   // canonical values: fp32 inputs (split) or the bf16 operands
+  const double* sq64 = prepared ? sq64_in : w.sq64;
+  const double* dgt = prepared ? gt_score : w.dgt;
   ExactArgs ex;
   if (o.split)
-    ex = ExactArgs{Q, G, D, D, false, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
+    ex = ExactArgs{Q, G, D, D, false, N, M, D, sq64, gt, row_offset, col_offset, metric};
   else
-    ex = ExactArgs{opQ, opG, o.Kp, o.Kp, true, N, M, D, w.sq64, gt, row_offset, col_offset, metric};
+    ex = ExactArgs{opQ, opG, o.Kp, o.Kp, true, N, M, D, sq64, gt, row_offset, col_offset, metric};
   // 2. canonical norms, ground-truth scores, guard band
-  VTC_RETURN_IF_ERROR(launch_sqnorm64(ex.G, ex.bf16, M, D, ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
-  if (fast_thr_enabled()) {
-    VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, nullptr, nullptr, 0.f, s));
-    VTC_RETURN_IF_ERROR(launch_thr_fast(ex.Q, ex.bf16, ex.ldq, N, D, w.dgt, &w.scalars[0], metric,
-                                        guard_rel_for(precision, o.Kp), w.thr, s));
+  if (prepared) {
+    // everything per-row is cached: padded fp32 bias + max norm from sq64, thresholds from
+    // (d(t,gt), ||q_t||^2 bound) -- three small launches, no row is read
+    VTC_RETURN_IF_ERROR(launch_bias_max(sq64, M, round_up<int64_t>(M, tc::BN), metric, w.sq32,
+                                        &w.scalars[0], s));
+    VTC_RETURN_IF_ERROR(launch_thr_cached(qq_in, dgt, &w.scalars[0], N, metric,
+                                          guard_rel_for(precision, o.Kp), w.thr, s));
   } else {
-    VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0],
-                                        guard_rel_for(precision, o.Kp), s));
+    VTC_RETURN_IF_ERROR(
+        launch_sqnorm64(ex.G, ex.bf16, M, D, ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
+    if (fast_thr_enabled()) {
+      VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, nullptr, nullptr, 0.f, s));
+      VTC_RETURN_IF_ERROR(launch_thr_fast(ex.Q, ex.bf16, ex.ldq, N, D, w.dgt, &w.scalars[0], metric,
+                                          guard_rel_for(precision, o.Kp), w.thr, s));
+    } else {
+      VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0],
+                                          guard_rel_for(precision, o.Kp), s));
+    }
+    // per-column epilogue bias: ||x_j||^2 (L2) or 0 (DOT); padding columns are +inf (never counted)
+    VTC_RETURN_IF_ERROR(launch_fill_bias(w.sq32, metric == VTC_METRIC_L2 ? w.sq32 : nullptr, M,
+                                         round_up<int64_t>(M, tc::BN), INFINITY, s));
   }
-  // per-column epilogue bias: ||x_j||^2 (L2) or 0 (DOT); padding columns are +inf (never counted)
-  VTC_RETURN_IF_ERROR(launch_fill_bias(w.sq32, metric == VTC_METRIC_L2 ? w.sq32 : nullptr, M,
-                                       round_up<int64_t>(M, tc::BN), INFINITY, s));
-  if (gt_score_out) {
-    e = cudaMemcpyAsync(gt_score_out, w.dgt, sizeof(double) * N, cudaMemcpyDeviceToDevice, s);
+  if (gt_score_out && gt_score_out != dgt) {
+    e = cudaMemcpyAsync(gt_score_out, dgt, sizeof(double) * N, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return cuda_err(e);
   }
   e = cudaMemsetAsync(w.rank_tmp, 0, sizeof(int) * N, s);
@@ -227,8 +246,8 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     // fold pass: the bias and d(t,gt) enter through one extra K16 step (fold.cu); always a CTA pair
     const int64_t Mpad = round_up<int64_t>(M, tc::BN);
     const int fc = fold_cols();
-    VTC_RETURN_IF_ERROR(launch_fold_g(w.sq64, M, Mpad, metric, w.foldG, fc, &w.scalars[2], s));
-    VTC_RETURN_IF_ERROR(launch_fold_q(w.thr, w.dgt, &w.scalars[0], N, metric,
+    VTC_RETURN_IF_ERROR(launch_fold_g(sq64, M, Mpad, metric, w.foldG, fc, &w.scalars[2], s));
+    VTC_RETURN_IF_ERROR(launch_fold_q(w.thr, dgt, &w.scalars[0], N, metric,
                                       guard_rel_for(precision, o.Kp), w.foldQ, fc, w.foldW,
                                       &w.scalars[2], s));
     // the box is {64, rows} either way: with 16-column operands the rest of each 128-byte row is
@@ -244,10 +263,10 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
   }
   // 4. exact re-check of the guard-band pairs; brute force if the list overflowed
-  VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[64], pl.grid, p.amb_seg_cap, w.dgt,
+  VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[64], pl.grid, p.amb_seg_cap, dgt,
                                      w.rank_tmp, &w.scalars[2], s));
   VTC_RETURN_IF_ERROR(launch_zero_if_flag(w.rank_tmp, N, &w.scalars[2], s));
-  VTC_RETURN_IF_ERROR(launch_rank_brute(ex, w.dgt, w.rank_tmp, &w.scalars[2], s));
+  VTC_RETURN_IF_ERROR(launch_rank_brute(ex, dgt, w.rank_tmp, &w.scalars[2], s));
   return launch_rank_commit(w.rank_tmp, rank0, N, accumulate, s);
 }
 
@@ -661,6 +680,37 @@ int vtc_sim_rank(const void* Q, const void* G, int64_t N, int64_t M, int D, int 
   return sim_rank_impl(Q, G, N, M, D, dtype, gt, row_offset, col_offset, metric, precision,
                        gt_score, gt_score_out, accumulate, rank0, ws, ws_bytes,
                        (cudaStream_t)stream);
+}
+
+int vtc_rank_prepare(const void* X, int64_t rows, int D, int dtype, int precision, double* sq64,
+                     float* qq_up, vtc_stream_t stream) {
+  if (!X || rows < 0 || D <= 0 || !valid_dtype(dtype) || !valid_prec(precision) || (!sq64 && !qq_up))
+    return VTC_ERR_INVALID_ARG;
+  // the canonical values must be the rows as handed in: bf16 rows in the bf16 mode, fp32 rows
+  // otherwise (fp32 rows in the bf16 mode would have to be rounded first -- hand in the rounded rows)
+  if ((precision == VTC_PREC_BF16) != (dtype == VTC_BF16)) return VTC_ERR_UNSUPPORTED_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool in_bf16 = dtype == VTC_BF16;
+  if (sq64) VTC_RETURN_IF_ERROR(launch_sqnorm64(X, in_bf16, rows, D, D, sq64, nullptr, nullptr, s));
+  if (qq_up) VTC_RETURN_IF_ERROR(launch_qnorm_up(X, in_bf16, D, rows, D, qq_up, s));
+  return VTC_OK;
+}
+
+int vtc_sim_rank_prepared(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                          const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
+                          int precision, const double* gt_score, const double* sq64,
+                          const float* qq_up, int accumulate, int32_t* rank0, void* ws,
+                          size_t ws_bytes, vtc_stream_t stream) {
+  if (!gt_score || !sq64 || !qq_up) return VTC_ERR_INVALID_ARG;
+  if ((precision == VTC_PREC_BF16) != (dtype == VTC_BF16)) return VTC_ERR_UNSUPPORTED_SHAPE;
+  if (N > 0 && M == 0) {  // an empty gallery chunk adds nothing
+    if (accumulate) return VTC_OK;
+    return sim_rank_impl(Q, G, N, M, D, dtype, gt, row_offset, col_offset, metric, precision,
+                         gt_score, nullptr, accumulate, rank0, ws, ws_bytes, (cudaStream_t)stream);
+  }
+  return sim_rank_impl(Q, G, N, M, D, dtype, gt, row_offset, col_offset, metric, precision,
+                       gt_score, nullptr, accumulate, rank0, ws, ws_bytes, (cudaStream_t)stream,
+                       sq64, qq_up);
 }
 
 int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,

@@ -129,7 +129,96 @@ thr_fast_kernel(const T* __restrict__ Q, int64_t ldq, int64_t N, int D,
   thr[t] = make_float2(lo, hi);
 }
 
+// (lo, hi) of exact.cu::gt_score_kernel from d(t,gt) and an upper bound qq of ||q_t||^2
+__device__ __forceinline__ float2 thresholds_from(double d0, double qq, double gmax_sq, int metric,
+                                                  float guard_rel) {
+  const double qn = sqrt(qq), gn = sqrt(gmax_sq);
+  double delta;
+  if (metric == VTC_METRIC_L2)
+    delta = 2.0 * guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn);
+  else
+    delta = (double)guard_rel * qn * gn + 1.2e-7 * qn * gn;
+  float lo = __double2float_rd(d0 - delta);
+  float hi = __double2float_ru(d0 + delta);
+  if (!(qq == qq) || !(d0 == d0)) lo = hi = nanf("");
+  return make_float2(lo, hi);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+qnorm_up_kernel(const T* __restrict__ X, int64_t ldx, int64_t rows, int D,
+                float* __restrict__ qq_up) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const T* x = X + r * ldx;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float v = to_f32(x[k]);
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  // (D/32 + 5) ulp of fp32 accumulation error at most: 1e-4 covers every D the library accepts
+  if (lane == 0) qq_up[r] = s * (1.0f + 1.0e-4f);
+}
+
+__global__ void bias_max_kernel(const double* __restrict__ sq64, int64_t M, int64_t Mpad, int metric,
+                                float* __restrict__ bias, unsigned int* __restrict__ max_sq_bits) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float mine = 0.f;
+  if (j < Mpad) {
+    float b = INFINITY;
+    if (j < M) {
+      const float f = (float)sq64[j];
+      b = metric == VTC_METRIC_L2 ? f : 0.f;
+      if (f == f && f < 3.0e38f) mine = f;  // as sqnorm64_kernel: NaN / inf rows do not scale the band
+    }
+    bias[j] = b;
+  }
+  mine = warp_max(mine);
+  if ((threadIdx.x & 31) == 0 && mine > 0.f) atomicMax(max_sq_bits, __float_as_uint(mine));
+}
+
+__global__ void thr_cached_kernel(const float* __restrict__ qq_up, const double* __restrict__ dgt,
+                                  const unsigned int* __restrict__ max_sq_bits, int64_t N, int metric,
+                                  float guard_rel, float2* __restrict__ thr) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  thr[t] = thresholds_from(dgt[t], (double)qq_up[t], (double)__uint_as_float(*max_sq_bits), metric,
+                           guard_rel);
+}
+
 }  // namespace
+
+int launch_qnorm_up(const void* X, bool bf16, int64_t ldx, int64_t rows, int D, float* qq_up,
+                    cudaStream_t s) {
+  if (rows == 0) return VTC_OK;
+  const unsigned grid = (unsigned)ceil_div<int64_t>(rows, 8);
+  if (bf16)
+    qnorm_up_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)X, ldx, rows, D, qq_up);
+  else
+    qnorm_up_kernel<float><<<grid, 256, 0, s>>>((const float*)X, ldx, rows, D, qq_up);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_bias_max(const double* sq64, int64_t M, int64_t Mpad, int metric, float* bias,
+                    unsigned int* max_sq_bits, cudaStream_t s) {
+  if (Mpad == 0) return VTC_OK;
+  bias_max_kernel<<<(unsigned)ceil_div<int64_t>(Mpad, 256), 256, 0, s>>>(sq64, M, Mpad, metric, bias,
+                                                                       max_sq_bits);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_thr_cached(const float* qq_up, const double* dgt, const unsigned int* max_sq_bits,
+                      int64_t N, int metric, float guard_rel, float2* thr, cudaStream_t s) {
+  if (N == 0) return VTC_OK;
+  thr_cached_kernel<<<(unsigned)ceil_div<int64_t>(N, 256), 256, 0, s>>>(qq_up, dgt, max_sq_bits, N,
+                                                                      metric, guard_rel, thr);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
 
 int launch_thr_fast(const void* Q, bool bf16, int64_t ldq, int64_t N, int D, const double* dgt,
                     const unsigned int* max_sq_bits, int metric, float guard_rel, float2* thr,

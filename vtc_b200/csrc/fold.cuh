@@ -28,6 +28,19 @@ int launch_fold_q(const float2* thr, const double* dgt, const unsigned int* max_
 int launch_fold_g(const double* sq64, int64_t M, int64_t Mpad, int metric, __nv_bfloat16* Gx,
                   int cols, unsigned int* invalid, cudaStream_t s);
 
+// ---- prepared ranking (vtc_rank_prepare / vtc_sim_rank_prepared): per-row quantities computed once
+// per gallery / query chunk and reused by every library call that touches the chunk.
+// qq_up[r] = fp32 upper bound of ||x_r||^2 (coalesced warp-per-row sum, inflated by 1e-4).
+int launch_qnorm_up(const void* X, bool bf16, int64_t ldx, int64_t rows, int D, float* qq_up,
+                    cudaStream_t s);
+// bias[j] = (float)sq64[j] (L2) or 0 (DOT) for j < M, +inf for M <= j < Mpad, and
+// *max_sq_bits = max over the finite (float)sq64[j]  (what sqnorm64 + fill_bias produce together)
+int launch_bias_max(const double* sq64, int64_t M, int64_t Mpad, int metric, float* bias,
+                    unsigned int* max_sq_bits, cudaStream_t s);
+// thresholds from cached quantities: d(t,gt) and the upper bound of ||q_t||^2 (no row walks)
+int launch_thr_cached(const float* qq_up, const double* dgt, const unsigned int* max_sq_bits,
+                      int64_t N, int metric, float guard_rel, float2* thr, cudaStream_t s);
+
 // Opt-in (VTC_FAST_THR=1): the (lo, hi) guard-band thresholds of launch_gt_score from a coalesced
 // fp32 row norm instead of a second fp64-sequential walk over every query row.  The band only needs
 // an UPPER bound of ||q_t|| (the scores themselves stay canonical), so ||q||^2 is summed in fp32 by a

@@ -345,10 +345,31 @@ class RecallAtK(BaseMetric):
                 ev = torch.cuda.Event()
                 ev.record(copy)
                 events.append(ev)
+        # VTC_RANK_PREPARED=1 (opt-in until timed on the box): norms and ground-truth scores are
+        # computed once per chunk as it lands and handed to every call that touches the chunk
+        # (vtc_sim_rank_prepared), instead of each of the 2c - 1 calls re-walking all its rows
+        prepared = (os.environ.get("VTC_RANK_PREPARED", "0") not in ("", "0")
+                    and (self.precision == "bf16") == (dq.dtype == torch.bfloat16)
+                    and self.precision in ("bf16", "exact"))
+        if prepared:
+            sq64 = torch.empty(n, dtype=torch.float64, device=device)
+            qq = torch.empty(n, dtype=torch.float32, device=device)
         for (s, e), ev in zip(zip(bounds[:-1], bounds[1:]), events):
             if e == s:
                 continue
             main.wait_event(ev)
+            if prepared:
+                ops.rank_prepare(dg[s:e], self.precision, want_qq=False, sq64_out=sq64[s:e])
+                ops.rank_prepare(dq[s:e], self.precision, want_sq64=False, qq_out=qq[s:e])
+                gt_score[s:e] = ops.gt_scores(dq[s:e], dg[s:e], None, s, s, self.metric, self.precision)
+                ops.sim_rank(dq[s:e], dg[:e], row_offset=s, metric=self.metric,
+                             precision=self.precision, gt_score=gt_score[s:e], rank0=rank0[s:e],
+                             accumulate=False, sq64=sq64[:e], qq=qq[s:e])
+                if s > 0:
+                    ops.sim_rank(dq[:s], dg[s:e], row_offset=0, col_offset=s, metric=self.metric,
+                                 precision=self.precision, gt_score=gt_score[:s], rank0=rank0[:s],
+                                 accumulate=True, sq64=sq64[s:e], qq=qq[:s])
+                continue
             # new rows against everything that has arrived (their ground truth is among it) ...
             _, g = ops.sim_rank(dq[s:e], dg[:e], row_offset=s, metric=self.metric,
                                 precision=self.precision, rank0=rank0[s:e], accumulate=False)

@@ -180,17 +180,48 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 # ------------------------------------------------------------------------------------ R1 / R3
+def rank_prepare(x: torch.Tensor, precision="exact", want_sq64: bool = True, want_qq: bool = True,
+                 sq64_out: Optional[torch.Tensor] = None, qq_out: Optional[torch.Tensor] = None
+                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Per-row quantities of a block of gallery / query rows, computed once and handed to every
+    :func:`sim_rank` call that touches the block (`sq64=` for its gallery rows, `qq=` for its query
+    rows): canonical fp64 ||x||^2 (what faiss' L2 distance adds per gallery row,
+    model/metric.py:140-146) and an fp32 upper bound of ||x||^2 for the guard band.  The rows must be
+    the canonical values: bf16 rows in the bf16 mode, fp32 rows in the exact mode."""
+    dev = _req_cuda(x)
+    x = _mat(x, "x")
+    rows, D = x.shape
+    sq64, qq = sq64_out, qq_out  # optional caller-owned outputs (e.g. slices of per-gallery arrays)
+    for t, dt in ((sq64, torch.float64), (qq, torch.float32)):
+        if t is not None and (t.dtype != dt or t.shape != (rows,) or not t.is_contiguous()
+                              or t.device != dev):
+            raise ValueError("rank_prepare outputs must be contiguous [rows] tensors on x's device")
+    if sq64 is None and want_sq64:
+        sq64 = torch.empty(rows, dtype=torch.float64, device=dev)
+    if qq is None and want_qq:
+        qq = torch.empty(rows, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_rank_prepare(_ptr(x), rows, D, _dtype_code(x), _prec(precision),
+                                                _ptr(sq64), _ptr(qq), _stream(dev)),
+                   "vtc_rank_prepare")
+    return sq64, qq
+
+
 def sim_rank(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None,
              row_offset: int = 0, col_offset: int = 0, metric="l2", precision="exact",
              gt_score: Optional[torch.Tensor] = None, rank0: Optional[torch.Tensor] = None,
-             accumulate: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+             accumulate: bool = False, sq64: Optional[torch.Tensor] = None,
+             qq: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused similarity + rank of ground truth: replaces faiss GpuIndexFlatL2.add/search + the Python
     hit loop of RecallAtK.compute (model/metric.py:140-160).  Returns (rank0 int32 [N], gt_score
     fp64 [N]).
 
     rank0 is NOT finalised (NaN ground truths still hold their partial count): call
-    :func:`rank_finalize` once every gallery chunk has been accumulated."""
-    dev = _req_cuda(q, g, gt, gt_score, rank0)
+    :func:`rank_finalize` once every gallery chunk has been accumulated.
+
+    `sq64` (of these gallery rows) and `qq` (of these query rows) from :func:`rank_prepare`, together
+    with a given `gt_score`, select vtc_sim_rank_prepared: same result, no per-call row walks."""
+    dev = _req_cuda(q, g, gt, gt_score, rank0, sq64, qq)
     q, g = _mat(q, "q"), _mat(g, "g")
     if q.shape[1] != g.shape[1] or q.dtype != g.dtype:
         raise ValueError("queries and gallery must share D and dtype")
@@ -211,6 +242,20 @@ def sim_rank(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None
         gs_out = torch.empty(N, dtype=torch.float64, device=dev)
     elif gt_score.dtype != torch.float64 or gt_score.shape != (N,):
         raise ValueError("gt_score must be float64 [N]")
+    if sq64 is not None or qq is not None:
+        if sq64 is None or qq is None or gt_score is None:
+            raise ValueError("prepared ranking needs sq64, qq and gt_score together")
+        if sq64.dtype != torch.float64 or sq64.shape != (M,) or not sq64.is_contiguous():
+            raise ValueError("sq64 must be a contiguous float64 [M] tensor")
+        if qq.dtype != torch.float32 or qq.shape != (N,) or not qq.is_contiguous():
+            raise ValueError("qq must be a contiguous float32 [N] tensor")
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, _ws_bytes(_ffi.OP_SIM_RANK, N, M, D, prec))
+            _ffi.check(_ffi.load().vtc_sim_rank_prepared(
+                _ptr(q), _ptr(g), N, M, D, _dtype_code(q), _ptr(gt), row_offset, col_offset, met,
+                prec, _ptr(gt_score), _ptr(sq64), _ptr(qq), 1 if accumulate else 0, _ptr(rank0),
+                _ptr(ws), ws.numel(), _stream(dev)), "vtc_sim_rank_prepared")
+        return rank0, gt_score
     with torch.cuda.device(dev):
         ws = _workspace(dev, _ws_bytes(_ffi.OP_SIM_RANK, N, M, D, prec))
         _ffi.check(_ffi.load().vtc_sim_rank(

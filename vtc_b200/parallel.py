@@ -66,12 +66,16 @@ class CudaBackend:
     def gt_scores(self, q, g, row_offset, col_offset, metric, precision):
         return self.ops.gt_scores(q, g, None, row_offset, col_offset, metric, precision)
 
-    def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0):
+    def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0,
+                 sq64=None, qq=None):
         """Accumulates into rank0; gt_score None = every ground truth lies inside g (computed and
-        returned)."""
+        returned).  sq64 / qq (from rank_prepare) select the prepared entry point."""
         _, gs = self.ops.sim_rank(q, g, None, row_offset, col_offset, metric, precision, gt_score,
-                                  rank0, accumulate=True)
+                                  rank0, accumulate=True, sq64=sq64, qq=qq)
         return gs
+
+    def rank_prepare(self, x, precision, want_sq64, want_qq):
+        return self.ops.rank_prepare(x, precision, want_sq64, want_qq)
 
     def rank_finalize(self, rank0, gt_score, M_total, k_vals, want_medr):
         return self.ops.rank_finalize(rank0, gt_score, M_total, k_vals, want_medr)
@@ -157,6 +161,19 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     rank0 = torch.zeros(n_local, dtype=torch.int32, device=dev)
     gt_local = (world == 1 or _gt_all_local(qs, qe, gs0, g_sizes[rank])) and g_sizes[rank] > 0
     local_done = False
+    # VTC_RANK_PREPARED=1 (opt-in until timed at 8 GPUs): query-norm bounds once per step, gallery
+    # norms once per (local / gathered) buffer, ground-truth scores from the pre-pass; the two or
+    # three ranking calls of the step then walk no rows of their own (vtc_sim_rank_prepared)
+    prepared = (os.environ.get("VTC_RANK_PREPARED", "0") not in ("", "0")
+                and hasattr(backend, "rank_prepare") and not single_pass and world > 1
+                and precision in ("bf16", "exact") and n_local > 0
+                and (precision == "bf16") == (q_local.dtype == torch.bfloat16)
+                and q_local.dtype == g_local.dtype)
+    if prepared:
+        return _sharded_rank_eval_prepared(backend, q_local, g_local, gathered, work, equal, mx,
+                                           g_sizes, g_starts, rank, world, qs, gt_local, N_total,
+                                           M_total, k_vals, metric, precision, group, want_medr,
+                                           rank0, ph)
     if single_pass:
         # equal shards: the gathered buffer IS the gallery in global row order, every ground truth
         # lies inside it, so one call yields the ground-truth scores and the complete ranks
@@ -216,6 +233,67 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     ph.mark("finalize+collectives")
     return {"hits": hits, "medr": medr, "rank0_local": rank0, "num_queries": N_total,
             "phases_ms": ph.result()}
+
+
+def _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group, want_medr, ph):
+    """The exchange at the end of a sharded step (shared by the default and the prepared path)."""
+    medr = None
+    if want_medr:
+        backend.rank_finalize(rank0, gt_score, M_total, [], False)
+        q_sizes = [shard_bounds(N_total, world, r)[1] - shard_bounds(N_total, world, r)[0]
+                   for r in range(world)]
+        allr, _ = _all_gather_padded(rank0, q_sizes, group)
+        full = torch.cat([allr[r][:q_sizes[r]] for r in range(world)])
+        hits, medr = backend.rank_finalize(full, None, M_total, list(k_vals), True)
+        hits = hits.clone()
+    else:
+        hits, _ = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), False)
+        hits = hits.clone()
+        dist.all_reduce(hits, op=dist.ReduceOp.SUM, group=group)
+    ph.mark("finalize+collectives")
+    return {"hits": hits, "medr": medr, "rank0_local": rank0, "num_queries": N_total,
+            "phases_ms": ph.result()}
+
+
+def _sharded_rank_eval_prepared(backend, q_local, g_local, gathered, work, equal, mx, g_sizes,
+                                g_starts, rank, world, qs, gt_local, N_total, M_total, k_vals,
+                                metric, precision, group, want_medr, rank0, ph):
+    """sharded_rank_eval with per-step prepared quantities (world > 1): the query-norm bounds and the
+    ground-truth scores once, the gallery norms once per buffer; the ranking calls walk no rows."""
+    gs0, ge0 = g_starts[rank], g_starts[rank] + g_sizes[rank]
+    have_local = g_sizes[rank] > 0
+    _, qq = backend.rank_prepare(q_local, precision, False, True)
+    gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
+    sq_local = backend.rank_prepare(g_local, precision, True, False)[0] if have_local else None
+    local_done = False
+    if gt_local and have_local:
+        # every ground truth is in our own chunk: rank against it while the gather is in flight
+        backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0,
+                         sq64=sq_local, qq=qq)
+        local_done = True
+    ph.mark("prepare+gt+local_rank")
+    work.wait()
+    ph.mark("gather_wait")
+    sq_all, _ = backend.rank_prepare(gathered, precision, True, False)   # [world * mx], incl. padding
+    if equal:
+        remote = [(0, 0, gs0), (ge0, ge0, M_total)]       # (global start row, buffer start, buffer end)
+    else:
+        remote = [(g_starts[r], r * mx, r * mx + g_sizes[r]) for r in range(world) if r != rank]
+    remote = [(st, b0, b1) for st, b0, b1 in remote if b1 > b0]
+    if not gt_local:
+        # ground truths that live in another rank's shard (N != M splits): fill in where still NaN
+        for st, b0, b1 in remote:
+            other = backend.gt_scores(q_local, gathered[b0:b1], qs, st, metric, precision)
+            gt_score = torch.where(torch.isnan(gt_score), other, gt_score)
+    if have_local and not local_done:
+        backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0,
+                         sq64=sq_local, qq=qq)
+    for st, b0, b1 in remote:
+        backend.sim_rank(q_local, gathered[b0:b1], qs, st, metric, precision, gt_score, rank0,
+                         sq64=sq_all[b0:b1], qq=qq)
+    ph.mark("remote_rank")
+    return _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group,
+                           want_medr, ph)
 
 
 class GraphedRankEval:
