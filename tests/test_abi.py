@@ -68,6 +68,19 @@ def test_invalid_arguments_are_rejected_before_any_launch(lib):
     assert lib.vtc_sim_rank(None, None, 0, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
                             _ffi.PREC_EXACT, None, None, 0, None, None, 0, None) == 0
     assert lib.vtc_topk_merge(None, None, 2, 4, 3, None, None, None) == -1
+    # prepared ranking: outputs / prepared inputs are required, and the rows must be the canonical
+    # values of the mode (bf16 rows <-> bf16 mode), VTC_ERR_UNSUPPORTED_SHAPE otherwise
+    import ctypes
+    buf = (ctypes.c_double * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.vtc_rank_prepare(None, 4, 8, _ffi.F32, _ffi.PREC_EXACT, p, None, None) == -1
+    assert lib.vtc_rank_prepare(p, 4, 8, _ffi.F32, _ffi.PREC_EXACT, None, None, None) == -1
+    assert lib.vtc_rank_prepare(p, 4, 8, _ffi.F32, _ffi.PREC_BF16, p, None, None) == -2
+    assert lib.vtc_rank_prepare(p, 4, 8, _ffi.BF16, _ffi.PREC_EXACT, p, None, None) == -2
+    assert lib.vtc_sim_rank_prepared(p, p, 4, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
+                                     _ffi.PREC_EXACT, p, None, p, 0, p, None, 0, None) == -1
+    assert lib.vtc_sim_rank_prepared(p, p, 4, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
+                                     _ffi.PREC_BF16, p, p, p, 0, p, None, 0, None) == -2
     assert lib.vtc_cam_attn_core(None, 6, 4, 512, 8, None, None) == -1
     assert lib.vtc_launch_count() == before
 
