@@ -242,8 +242,13 @@ def _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, g
         backend.rank_finalize(rank0, gt_score, M_total, [], False)
         q_sizes = [shard_bounds(N_total, world, r)[1] - shard_bounds(N_total, world, r)[0]
                    for r in range(world)]
-        allr, _ = _all_gather_padded(rank0, q_sizes, group)
-        full = torch.cat([allr[r][:q_sizes[r]] for r in range(world)])
+        if all(sz == q_sizes[0] for sz in q_sizes):
+            # equal shards: one collective straight into the full vector (no per-rank copies, no cat)
+            full = torch.empty(N_total, dtype=rank0.dtype, device=rank0.device)
+            dist.all_gather_into_tensor(full, rank0.contiguous(), group=group)
+        else:
+            allr, _ = _all_gather_padded(rank0, q_sizes, group)
+            full = torch.cat([allr[r][:q_sizes[r]] for r in range(world)])
         hits, medr = backend.rank_finalize(full, None, M_total, list(k_vals), True)
         hits = hits.clone()
     else:
