@@ -4,6 +4,10 @@ default `pytest -m gpu` run only exercises code that has been measured; the firs
 round is `VTC_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q`
 (scripts/gpu_experimental.sh), after which a variant is either made the default or removed.
 
+Variants covered: VTC_RANK_FOLD / VTC_FOLD_COLS (fold epilogue), VTC_FAST_THR (thresholds from a
+coalesced norm), vtc_rank_prepare + vtc_sim_rank_prepared / VTC_RANK_PREPARED (per-chunk prepared
+quantities), VTC_PIPELINE_SCHEDULE (host-staging chunk sizes), plus > 8 k values.
+
 VTC_RANK_FOLD=1 -- EPI_RANK_FOLD (csrc/fold.cu, RankFoldEpi in csrc/sim_tc_kernel.cuh): the
 per-column bias and the per-row ground-truth score enter the accumulator through one extra K16 MMA
 step, the epilogue counts sign bits.  Same contract as the default path: ranks bit-exact against the
