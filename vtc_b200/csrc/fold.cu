@@ -95,6 +95,21 @@ __global__ void fold_g_kernel(const double* __restrict__ sq64, int64_t M, int64_
   store_fold_row(Gx + j * cols, cols, e);
 }
 
+// (lo, hi) of exact.cu::gt_score_kernel from d(t,gt) and an upper bound qq of ||q_t||^2
+__device__ __forceinline__ float2 thresholds_from(double d0, double qq, double gmax_sq, int metric,
+                                                  float guard_rel) {
+  const double qn = sqrt(qq), gn = sqrt(gmax_sq);
+  double delta;
+  if (metric == VTC_METRIC_L2)
+    delta = 2.0 * guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn);
+  else
+    delta = (double)guard_rel * qn * gn + 1.2e-7 * qn * gn;
+  float lo = __double2float_rd(d0 - delta);
+  float hi = __double2float_ru(d0 + delta);
+  if (!(qq == qq) || !(d0 == d0)) lo = hi = nanf("");
+  return make_float2(lo, hi);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 thr_fast_kernel(const T* __restrict__ Q, int64_t ldq, int64_t N, int D,
@@ -111,37 +126,10 @@ thr_fast_kernel(const T* __restrict__ Q, int64_t ldq, int64_t N, int D,
   }
   s = warp_sum(s);
   if (lane != 0) return;
-  const double d0 = dgt[t];
   // fp32 accumulation of D non-negative terms is within (D/32 + 5) ulp of the exact sum: 1e-4 covers
   // every D the library accepts (<= 8192)
-  const double qq = (double)s * (1.0 + 1.0e-4);
-  const double qn = sqrt(qq);
-  const double gmax_sq = (double)__uint_as_float(*max_sq_bits);
-  const double gn = sqrt(gmax_sq);
-  double delta;  // exact.cu::gt_score_kernel
-  if (metric == VTC_METRIC_L2)
-    delta = 2.0 * guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn);
-  else
-    delta = (double)guard_rel * qn * gn + 1.2e-7 * qn * gn;
-  float lo = __double2float_rd(d0 - delta);
-  float hi = __double2float_ru(d0 + delta);
-  if (!(s == s) || !(d0 == d0)) lo = hi = nanf("");
-  thr[t] = make_float2(lo, hi);
-}
-
-// (lo, hi) of exact.cu::gt_score_kernel from d(t,gt) and an upper bound qq of ||q_t||^2
-__device__ __forceinline__ float2 thresholds_from(double d0, double qq, double gmax_sq, int metric,
-                                                  float guard_rel) {
-  const double qn = sqrt(qq), gn = sqrt(gmax_sq);
-  double delta;
-  if (metric == VTC_METRIC_L2)
-    delta = 2.0 * guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn);
-  else
-    delta = (double)guard_rel * qn * gn + 1.2e-7 * qn * gn;
-  float lo = __double2float_rd(d0 - delta);
-  float hi = __double2float_ru(d0 + delta);
-  if (!(qq == qq) || !(d0 == d0)) lo = hi = nanf("");
-  return make_float2(lo, hi);
+  thr[t] = thresholds_from(dgt[t], (double)s * (1.0 + 1.0e-4),
+                           (double)__uint_as_float(*max_sq_bits), metric, guard_rel);
 }
 
 template <typename T>
