@@ -40,6 +40,14 @@ for prep in 0 1; do
     done
   done
 done
+# top-k sample pass size (default: 1/32 of the gallery, 8..32 tiles): config-5 share of one GPU
+for st in 6 8 12 24; do
+  VTC_TOPK_SAMPLE_TILES=$st timeout 200 python scripts/bench_extra.py c35 2>/dev/null | grep c5_topk \
+      | sed "s/^/sample_tiles=$st /" >> gpurun_out/${TAG}_topk_sample_tiles.txt
+done
+timeout 200 python scripts/bench_extra.py c35 2>/dev/null | grep c5_topk | sed "s/^/sample_tiles=default /" \
+    >> gpurun_out/${TAG}_topk_sample_tiles.txt
+cat gpurun_out/${TAG}_topk_sample_tiles.txt | cut -c1-200 >> $S
 python scripts/show_bench.py gpurun_out/${TAG}_fold*.json 2>&1 | cut -c1-200 >> $S
 # SASS-level proof of what the fold epilogue issues per logit goes with the ncu capture of the round
 VTC_RANK_FOLD=1 timeout 600 ncu --set full --clock-control none --import-source on \

@@ -293,6 +293,12 @@ static int64_t topk_sample_tiles(int64_t N, int64_t M) {
   int64_t t = g_tiles / 32;
   if (t < 8) t = 8;
   if (t > 32) t = 32;
+  // tuning knob (VTC_TOPK_SAMPLE_TILES=4..64): fewer tiles = a cheaper sample pass (its dense scores
+  // are written and read back once) but looser thresholds, i.e. more candidates in the main pass
+  if (const char* e = getenv("VTC_TOPK_SAMPLE_TILES")) {
+    const int64_t v = atoll(e);
+    if (v >= 4 && v <= 64 && v < g_tiles) t = v;
+  }
   const int64_t cap = ((int64_t)512 << 20) / (N * tc::BN * 4);
   if (t > cap) t = cap;
   return t >= 4 ? t : 0;
