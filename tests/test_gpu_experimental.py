@@ -41,7 +41,7 @@ def _oracle_ranks(Q, G, metric, precision, gt=None, row_offset=0):
     return O.rank0_exact(Q, G, gt=gt, metric=METRICS[metric], row_offset=row_offset)
 
 
-@pytest.fixture(params=[64, 16])
+@pytest.fixture(params=[64, 16], ids=["cols64", "cols16"])
 def fold(monkeypatch, request):
     """VTC_RANK_FOLD / VTC_FOLD_COLS are read by the library on every vtc_sim_rank call.  64-column
     fold operands are laid out like any other k-block; 16-column ones rely on TMA zero-filling the
