@@ -2,7 +2,7 @@
 # First GPU call of a round that inherits opt-in kernel variants (DESIGN.md §8 "pending
 # validation"): parity of every variant against the oracle, then the headline bench with and
 # without it on the SAME box (boxes differ in how hard sw_power_cap bites), plus the shapes where the
-# variant should matter most.  usage: gpu_experimental.sh [tag]; ~6 GPU-minutes.
+# variant should matter most.  usage: gpurun --timeout 1800 -- 'bash scripts/gpu_experimental.sh [tag]'; ~15 GPU-minutes.
 set -u
 TAG=${1:-exp}
 mkdir -p gpurun_out
@@ -18,8 +18,8 @@ for grp in "fold and cols64" "fold and cols16" "fold and not cols64 and not cols
 done
 # fold = 0: default epilogue; 1: fold operands 64 columns wide; 2: 16 columns wide (VTC_FOLD_COLS=16)
 for fold in 0 1 2; do
-  for args in "" "--d 256" "--d 768" "--precision exact"; do
-    name=$(echo "fold${fold}${args}" | tr -d ' -')
+  for args in "" "--d 256 --no-e2e" "--d 768 --no-e2e" "--precision exact --no-e2e"; do
+    name=$(echo "fold${fold}${args}" | sed 's/--no-e2e//' | tr -d ' -')
     cols=64; [ $fold -eq 2 ] && cols=16
     VTC_RANK_FOLD=$(( fold > 0 )) VTC_FOLD_COLS=$cols timeout 200 python bench.py --steps 10 \
         --no-cpu-baseline $args > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
