@@ -33,66 +33,69 @@ __all__ = ["BaseMetric", "ScalarPerBatchMetric", "LossMetric", "RecallAtK", "Met
 
 
 class MetricTracker:
-    """model/metric.py:10-42, API kept as the trainer uses it (trainer/trainer.py:49-54):
-    `MetricTracker(*metrics)`, `add_metric`, `set_writer`, `reset`, `update`, `avg`, `result`."""
+    """model/metric.py:10-42, with the API the trainer drives it through (trainer/trainer.py:49-54):
+    `MetricTracker(*metrics)`, `add_metric`, `set_writer`, `reset`, `update`, `avg`, `result`;
+    `metrics` maps metric name -> metric, in insertion order."""
 
     def __init__(self, *metrics):
         self.metrics = {}
-        for m in metrics:
-            self.add_metric(m)
+        for metric in metrics:
+            self.add_metric(metric)
         self.reset()
 
     def add_metric(self, metric):
         self.metrics[metric.name] = metric
 
+    def _each(self):
+        return list(self.metrics.values())
+
     def set_writer(self, writer):
-        for m in self.metrics.values():
-            m.set_writer(writer)
+        for metric in self._each():
+            metric.set_writer(writer)
 
     def reset(self):
-        for m in self.metrics.values():
-            m.reset()
+        for metric in self._each():
+            metric.reset()
 
     def update(self, loss, output, meta):
-        for m in self.metrics.values():
-            m.update(loss, output, meta)
+        for metric in self._each():
+            metric.update(loss, output, meta)
 
     def avg(self):
-        res = {}
-        for m in self.metrics.values():
-            res[m.name] = m.avg()
-        return res
+        return {metric.name: metric.avg() for metric in self._each()}
 
     def result(self):
-        res = {}
-        for m in self.metrics.values():
-            res.update(m.result())
-        return res
+        merged = {}
+        for metric in self._each():
+            merged.update(metric.result())
+        return merged
 
 
 class BaseMetric:
-    """model/metric.py:45-65."""
+    """model/metric.py:45-65: name, writer, the two phase flags, and the four methods a metric has to
+    provide."""
 
     def __init__(self, name):
-        self.name = name
-        self.writer = None
-        self.is_train = True
-        self.is_val = True
+        self.name, self.writer = name, None
+        self.is_train = self.is_val = True
 
     def set_writer(self, writer):
         self.writer = writer
 
+    def _abstract(self, what):
+        raise NotImplementedError(f"{type(self).__name__}.{what}")
+
     def reset(self):
-        raise NotImplementedError()
+        self._abstract("reset")
 
     def update(self, loss, output, meta):
-        raise NotImplementedError()
+        self._abstract("update")
 
     def avg(self):
-        raise NotImplementedError()
+        self._abstract("avg")
 
     def result(self):
-        raise NotImplementedError()
+        self._abstract("result")
 
 
 class ScalarPerBatchMetric(BaseMetric):
@@ -394,24 +397,19 @@ class RecallAtK(BaseMetric):
         return None
 
     def result(self):
-        tic = time.time()
+        started = time.time()
         print("RecallAtK: result()...", end=" ", flush=True)
-
-        features_a = torch.cat(self.features_a_list)
-        features_b = torch.cat(self.features_b_list)
-
-        assert self.insert_index == len(features_a)
-
+        side_a = (self.name_a, torch.cat(self.features_a_list))
+        side_b = (self.name_b, torch.cat(self.features_b_list))
+        assert self.insert_index == len(side_a[1])
+        # both retrieval directions, keyed and ordered as model/metric.py:175-179: queries b against
+        # gallery a first ("{b}_from_{a}-recall_at_{k}"), then the roles swapped
         res = {}
-        for k, recall in self.compute(features_a, features_b):
-            res[f"{self.name_b}_from_{self.name_a}-recall_at_{k}"] = recall
-        for k, recall in self.compute(features_b, features_a):
-            res[f"{self.name_a}_from_{self.name_b}-recall_at_{k}"] = recall
-
+        for (g_name, gallery), (q_name, queries) in ((side_a, side_b), (side_b, side_a)):
+            for k, recall in self.compute(gallery, queries):
+                res[f"{q_name}_from_{g_name}-recall_at_{k}"] = recall
         if self.writer:
-            for name, recall in res.items():
-                self.writer.add_scalar(name, recall)
-
-        print("RecallAtK: result() took %.3fs" % (time.time() - tic))
-
+            for key, recall in res.items():
+                self.writer.add_scalar(key, recall)
+        print("RecallAtK: result() took %.3fs" % (time.time() - started))
         return res
