@@ -12,6 +12,18 @@ VTC_RANK_FOLD=1 -- EPI_RANK_FOLD (csrc/fold.cu, RankFoldEpi in csrc/sim_tc_kerne
 per-column bias and the per-row ground-truth score enter the accumulator through one extra K16 MMA
 step, the epilogue counts sign bits.  Same contract as the default path: ranks bit-exact against the
 fp64-sequential oracle (replacing the faiss search + hit loop of model/metric.py:137-161).
+
+Reading a failure (nothing here has run on a GPU yet):
+* cols16 fails, cols64 passes -> the assumption that a {64, rows} TMA box may exceed a 16-column
+  tensor along the inner dimension (zero fill, as for a K tail) is wrong: drop VTC_FOLD_COLS=16.
+* every fold test dies after ~4 s with a CUDA error -> an mbarrier wait hit its 4 s trap: the fold
+  kernel differs from the measured pair kernel only in (a) nkb = num_kb + 1 k-blocks per tile in the
+  producer and MMA loops, (b) 9 resident query blocks / a_full barriers, (c) a 5-stage ring when
+  resident, (d) the last block issuing one K16 step -- check those four in sim_tc_kernel.cuh.
+* ranks off by small counts on a few rows -> guard band: VTC_GUARD_REL_BF16 / _EXACT widen it; the
+  fold step's own slack is the 4.8e-7 * S term of fold.cu::fold_q_kernel.
+* ranks wildly off -> sign convention / operand layout: tests/test_fold_math.py is the numpy
+  transcription the CUDA code must match (Qx = [m' pieces | 1 1 1], Gx = [1 1 1 | h pieces]).
 """
 import os
 
