@@ -39,7 +39,8 @@ def _includes(path: str, seen=None):
 def _unit_hash(src: str) -> str:
     h = hashlib.sha256()
     for f in sorted(_includes(os.path.join(CSRC, src))):
-        h.update(f.encode())
+        # relative names: the stamp must survive the move of the tree to the GPU box's scratch path
+        h.update(os.path.relpath(f, HERE).encode())
         h.update(open(f, "rb").read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
