@@ -10,7 +10,7 @@ S=gpurun_out/summary_$TAG.txt
 : > $S
 # one pytest process per variant: a trap in one kernel poisons its CUDA context, not the other groups
 for grp in "fold and cols64" "fold and cols16" "fold and not cols64 and not cols16" \
-           "fast_thresholds" "prepared" "more_than_eight"; do
+           "fast_thresholds" "prepared" "more_than_eight" "infinite_rows"; do
   name=$(echo "$grp" | tr -d ' ' | cut -c1-24)
   VTC_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -m gpu -q \
       --tb=short --maxfail=6 -k "$grp" > gpurun_out/${TAG}_pytest_$name.log 2>&1
