@@ -268,8 +268,13 @@ def _sharded_rank_eval_prepared(backend, q_local, g_local, gathered, work, equal
     gs0, ge0 = g_starts[rank], g_starts[rank] + g_sizes[rank]
     have_local = g_sizes[rank] > 0
     _, qq = backend.rank_prepare(q_local, precision, False, True)
-    gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
-    sq_local = backend.rank_prepare(g_local, precision, True, False)[0] if have_local else None
+    if have_local:
+        gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
+        sq_local, _ = backend.rank_prepare(g_local, precision, True, False)
+    else:  # more ranks than gallery rows: every ground truth lives elsewhere
+        gt_score = torch.full((q_local.shape[0],), float("nan"), dtype=torch.float64,
+                              device=q_local.device)
+        sq_local = None
     local_done = False
     if gt_local and have_local:
         # every ground truth is in our own chunk: rank against it while the gather is in flight
