@@ -320,3 +320,32 @@ def test_finaltf_forward_glue_with_token_ids_matches_reference(monkeypatch, bran
         got = ours(vis, title, comments)
     for g_, w_ in zip(got, want):
         torch.testing.assert_close(g_, w_, rtol=1e-5, atol=1e-6)
+
+
+def test_committed_goldens_are_reproduced_by_the_generator(tmp_path, monkeypatch):
+    """tests/golden/*.npz are what the GPU box checks against (the reference does not exist there),
+    so they must be exactly what tests/golden/generate_golden.py -- i.e. the reference's own code --
+    produces today: regenerate into a scratch directory and compare every array."""
+    import importlib.util
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location(
+        "generate_golden", os.path.join(here, "golden", "generate_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    monkeypatch.setattr(gen, "OUT", str(tmp_path))
+    gen.main()
+    made = sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz"))
+    committed = sorted(f for f in os.listdir(os.path.join(here, "golden")) if f.endswith(".npz"))
+    assert made == committed
+    for name in made:
+        new = np.load(os.path.join(tmp_path, name), allow_pickle=True)
+        old = np.load(os.path.join(here, "golden", name), allow_pickle=True)
+        assert sorted(new.files) == sorted(old.files), name
+        for key in new.files:
+            a, b = new[key], old[key]
+            if a.dtype.kind in "fc":
+                np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-7, err_msg=f"{name}:{key}")
+            else:
+                np.testing.assert_array_equal(a, b, err_msg=f"{name}:{key}")
