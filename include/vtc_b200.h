@@ -28,7 +28,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define VTC_ABI_VERSION 1
+#define VTC_ABI_VERSION 2
 
 typedef void* vtc_stream_t; /* a cudaStream_t */
 
@@ -124,23 +124,39 @@ int vtc_sim_rank(const void* Q, const void* G, int64_t N, int64_t M, int D, int 
                  int precision, const double* gt_score, double* gt_score_out, int accumulate,
                  int32_t* rank0, void* ws, size_t ws_bytes, vtc_stream_t stream);
 
-/* ---- prepared ranking: per-row quantities computed once per chunk, reused by every call ----------
+/* ---- R1 + R3 in one call: similarity + rank + R@K hit counts + median rank -----------------------
+ * The whole of RecallAtK.compute (model/metric.py:137-161) for one (queries, gallery) pair that is
+ * resident on the device: vtc_sim_rank over the full gallery followed by vtc_rank_finalize, as
+ * memset + 3 kernels (row prologue, tensor-core pass, cooperative epilogue).  hits [nk] int64 and
+ * medr (fp64, nullable) are device pointers; gt_score_out [N] (nullable) receives d(t,gt).
+ * The workspace is that of VTC_OP_SIM_RANK. */
+int vtc_rank_eval(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                  const int64_t* gt, int metric, int precision, const int* k_vals, int nk,
+                  int32_t* rank0, int64_t* hits, double* medr, double* gt_score_out, void* ws,
+                  size_t ws_bytes, vtc_stream_t stream);
+
+/* ---- chunked ranking: per-row quantities computed once, reused by every call ---------------------
  * A chunked evaluation (host staging pipelined against the ranking, gallery shards gathered over
- * NVLink) calls vtc_sim_rank many times on the same rows; each call re-walks its gallery rows for
- * ||x||^2 and its query rows for the guard band.  vtc_rank_prepare computes, for a block of rows,
- *   sq64  [rows] fp64 : canonical ||x_r||^2 (what vtc_sim_rank computes internally; gallery side)
- *   qq_up [rows] fp32 : an upper bound of ||x_r||^2 (query side; the guard band needs no more)
- * (either may be NULL).  vtc_sim_rank_prepared is vtc_sim_rank with gt_score, the sq64 of THIS G
- * and the qq_up of THIS Q given: no row is read outside the tensor-core pass and the re-check.
- * The rows must already be the canonical values: bf16 rows with VTC_PREC_BF16, fp32 rows with
- * VTC_PREC_EXACT (VTC_ERR_UNSUPPORTED_SHAPE otherwise).  Same results as vtc_sim_rank. */
+ * NVLink) calls the ranking many times on the same rows.  Three per-row quantities can be cached
+ * across those calls, each either handed IN or computed by this call and stored OUT:
+ *   sq64 [M] fp64  canonical ||x_j||^2 of THIS G            (sq64     in | sq64_out     out)
+ *   qq   [N] fp32  upper bound of ||q_t||^2 (guard band)   (qq_up    in | qq_out       out)
+ *   d(t,gt) [N] fp64                                        (gt_score in | gt_score_out out; when
+ *           computed, rows whose ground truth lies outside this G receive NaN)
+ * (exactly one of each pair must be non-NULL).  With all three handed in and bf16 rows of whole
+ * 128-byte swizzle atoms (D % 64 == 0), no row is read outside the tensor-core pass and the re-check.
+ * The cached values are tied to the canonical rows: the bf16 roundings with VTC_PREC_BF16, the fp32
+ * values with VTC_PREC_EXACT.  Same results as vtc_sim_rank.  vtc_rank_prepare computes sq64 and / or
+ * qq_up for a block of rows on its own (either may be NULL); its rows must already be the canonical
+ * values (bf16 rows with VTC_PREC_BF16, fp32 rows otherwise: VTC_ERR_UNSUPPORTED_SHAPE if not). */
 int vtc_rank_prepare(const void* X, int64_t rows, int D, int dtype, int precision, double* sq64,
                      float* qq_up, vtc_stream_t stream);
 int vtc_sim_rank_prepared(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
                           const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
-                          int precision, const double* gt_score, const double* sq64,
-                          const float* qq_up, int accumulate, int32_t* rank0, void* ws,
-                          size_t ws_bytes, vtc_stream_t stream);
+                          int precision, const double* gt_score, double* gt_score_out,
+                          const double* sq64, double* sq64_out, const float* qq_up, float* qq_out,
+                          int accumulate, int32_t* rank0, void* ws, size_t ws_bytes,
+                          vtc_stream_t stream);
 
 /* fp64-sequential d(t,gt) for each query (also the pre-pass of vtc_sim_rank). */
 int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
@@ -270,6 +286,14 @@ uint64_t vtc_launch_count(void);
  * duration (HOST pointers: total_ms, count) and clears the list.  Off by default. */
 int vtc_kernel_timer_enable(int on);
 int vtc_kernel_timer_read(double* total_ms, int* count);
+
+/* Profiling only (VTC_DBG_PROF=1 in the environment when the library is loaded): the tensor-core
+ * kernel's MMA issuer and first epilogue warp record, per CTA, 8 x uint64 {clock64 ticks,
+ * globaltimer ns, ticks the issuer waited for a free accumulator, ticks it waited for operand
+ * stages, tiles, ticks the epilogue waited for a full accumulator, epilogue ticks, 0}.
+ * Synchronises the device, copies the words of the LAST launch to the HOST buffer and clears them.
+ * VTC_ERR_INVALID_ARG when profiling is off. */
+int vtc_debug_prof_read(unsigned long long* out, int max_words);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -242,8 +242,7 @@ def config3_and_5():
     T, V = make_retrieval_pair(10000, 10000, 512, seed=1023)
     q, g = T.to(dev), V.to(dev)
     for prec in ("bf16", "exact"):
-        us, nl = timeit(lambda: ops.rank_finalize(*ops.sim_rank(q, g, precision=prec), 10000, [1, 5, 10]),
-                        iters=20)
+        us, nl = timeit(lambda: ops.rank_eval(q, g, [1, 5, 10], precision=prec), iters=20)
         emit(bench="c3_rank_10kx10k", precision=prec, us=us, launches=nl, pairs_per_s=1e8 / (us * 1e-6))
         # the same step replayed as one CUDA graph (17 dependent launches around a ~70 us
         # tensor-core kernel: the gaps between them are a third of the eager step)

@@ -27,15 +27,6 @@ for n in 1 2 4 8; do
   fi
   echo "bench n=$n exit=$?" >> $S
 done
-# opt-in variants of the sharded step on all GPUs, same box as the default above: one library call
-# over the whole gathered gallery (VTC_SHARD_SINGLE_PASS=1), the fold epilogue (VTC_RANK_FOLD=1), both
-for v in "VTC_RANK_PREPARED=1" "VTC_SHARD_SINGLE_PASS=1" "VTC_RANK_FOLD=1" "VTC_RANK_PREPARED=1 VTC_RANK_FOLD=1"; do
-  name=$(echo "$v" | tr -d ' =' | tr 'A-Z' 'a-z')
-  env $v timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
-      --master-port 29535 bench.py --gpus $NG --steps 20 --warmup 3 --no-cpu-baseline --no-e2e \
-      > gpurun_out/scale_n${NG}_$name.json 2> gpurun_out/scale_n${NG}_$name.err
-  echo "bench n=$NG $v exit=$?" >> $S
-done
 # BASELINE config 5 (10k x 1M x 512 top-k, gallery-sharded) and config 4 (D = 768) on all GPUs
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
     --master-port 29533 scripts/dist_topk_bench.py > gpurun_out/c5_topk_n$NG.json 2> gpurun_out/c5_topk_n$NG.err

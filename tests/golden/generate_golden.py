@@ -73,6 +73,8 @@ def gen_retrieval_small(metric_mod):
     V[20] = 0.5 * (V[20] + V[21])   # non-unit gallery row (mean of unit vectors, reval.py:254-259)
     V[30] = 0.0             # zero row
     T[40] = float("nan")    # a NaN query (normalising a zero row, model.py:26-27)
+    V[50] = float("-inf")   # a -inf padding row (retrieval_evaluation.py:238-252), also a ground truth
+    V[51, :3] = float("inf")   # a row with +inf elements: +-inf / NaN scores depending on the query
     k_vals = [1, 5, 10]
     m = metric_mod.RecallAtK("a", "b", k_vals)
     r_ab = np.array([r for _, r in m.compute(V.numpy(), T.numpy())])

@@ -25,7 +25,7 @@ def test_header_declares_what_the_binding_binds():
 def test_library_exports_every_declared_symbol(lib):
     for name in _declared_symbols():
         assert hasattr(lib, name), f"{name} not exported by libvtc_b200.so"
-    assert lib.vtc_abi_version() == 1
+    assert lib.vtc_abi_version() == 2
     assert lib.vtc_strerror(0) == b"ok"
     assert b"workspace" in lib.vtc_strerror(-3)
 
@@ -77,10 +77,21 @@ def test_invalid_arguments_are_rejected_before_any_launch(lib):
     assert lib.vtc_rank_prepare(p, 4, 8, _ffi.F32, _ffi.PREC_EXACT, None, None, None) == -1
     assert lib.vtc_rank_prepare(p, 4, 8, _ffi.F32, _ffi.PREC_BF16, p, None, None) == -2
     assert lib.vtc_rank_prepare(p, 4, 8, _ffi.BF16, _ffi.PREC_EXACT, p, None, None) == -2
+    # chunked ranking: each cached quantity is handed in or asked for (never neither), and the
+    # brute-force mode has nothing to cache
     assert lib.vtc_sim_rank_prepared(p, p, 4, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
-                                     _ffi.PREC_EXACT, p, None, p, 0, p, None, 0, None) == -1
+                                     _ffi.PREC_EXACT, p, None, None, None, p, None, 0, p, None, 0,
+                                     None) == -1
     assert lib.vtc_sim_rank_prepared(p, p, 4, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
-                                     _ffi.PREC_BF16, p, p, p, 0, p, None, 0, None) == -2
+                                     _ffi.PREC_EXACT, None, None, p, None, p, None, 0, p, None, 0,
+                                     None) == -1
+    assert lib.vtc_sim_rank_prepared(p, p, 4, 4, 8, _ffi.F32, None, 0, 0, _ffi.METRIC_L2,
+                                     _ffi.PREC_BRUTE, p, None, p, None, p, None, 0, p, None, 0,
+                                     None) == -2
+    assert lib.vtc_rank_eval(None, None, 4, 4, 8, _ffi.F32, None, _ffi.METRIC_L2, _ffi.PREC_EXACT,
+                             None, 0, None, None, None, None, None, 0, None) == -1
+    assert lib.vtc_rank_eval(p, p, 4, 4, 8, _ffi.F32, None, _ffi.METRIC_L2, _ffi.PREC_EXACT, None, 9,
+                             p, p, None, None, None, 0, None) == -1
     assert lib.vtc_cam_attn_core(None, 6, 4, 512, 8, None, None) == -1
     assert lib.vtc_launch_count() == before
 

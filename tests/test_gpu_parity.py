@@ -46,7 +46,7 @@ def test_normalize_matches_reference_semantics(cuda_dev):
 def test_sim_matrix_tensor_core_gemm(cuda_dev, N, M, D, precision):
     """The tcgen05 GEMM core (EPI_STORE) against fp64; also the evidence for the guard band:
     |tc - exact| / (|a||b|) must stay well inside the library's guard_rel (csrc/api.cu
-    guard_rel_for: (K'/16 + 8) * 2^-24, plus 1.2e-5 for the bf16x3 split)."""
+    guard_rel_for: (K'/16 + 8) * 2^-24, plus 4.62e-5 for the bf16x3 split)."""
     from vtc_b200 import ops
 
     g = torch.Generator().manual_seed(N * 7 + M)
@@ -63,7 +63,7 @@ def test_sim_matrix_tensor_core_gemm(cuda_dev, N, M, D, precision):
     norms = (a_ref.norm(dim=-1, keepdim=True) * b_ref.norm(dim=-1, keepdim=True).t()).double().numpy()
     rel = np.abs(out - want) / (scale * norms)
     kp = -(-(D if precision == "bf16" else 3 * D) // 64) * 64
-    guard = (kp // 16 + 8) * 2.0 ** -24 + (0.0 if precision == "bf16" else 1.2e-5)
+    guard = (kp // 16 + 8) * 2.0 ** -24 + (0.0 if precision == "bf16" else 4.62e-5)
     print(f"\n[guard-band evidence] {precision} N={N} M={M} D={D}: max rel err {rel.max():.3e} "
           f"(guard {guard:.3e}, margin x{guard / max(rel.max(), 1e-30):.1f})")
     assert rel.max() < guard / 3
@@ -97,6 +97,32 @@ def test_rank_bit_exact(cuda_dev, precision, metric, N, M, D, sigma):
     np.testing.assert_array_equal(_np(rank0), want)
     np.testing.assert_array_equal(_np(hits), [np.sum(want < k) for k in (1, 5, 10)])
     assert _np(medr)[0] == O.medr(want)
+
+
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+@pytest.mark.parametrize("D", [64, 512])
+def test_rank_structured_embeddings_ties_stay_exact(cuda_dev, precision, D):
+    """Constant-magnitude sign embeddings whose elements sit just below a bf16 rounding midpoint
+    (the inputs on which the bf16x3 split loses the most: 2.4e-5 of |q||x|, tests/test_guard_band.py)
+    with duplicated gallery rows, so that exactly tied columns abound.  A tie must reach the fp64
+    re-check (index tie-break), which it only does if the guard band really bounds the tensor-core
+    error -- the round-1 constant (1.2e-5) did not."""
+    from vtc_b200 import ops
+
+    rng = np.random.default_rng(D)
+    base = np.sign(rng.standard_normal(D)).astype(np.float32)
+    M, N = 900, 400
+    flip = rng.random((M, D)) < 0.1
+    V = (np.where(flip, -base, base) * np.float32(1.00385 / 32)).astype(np.float32)
+    V[300:600] = V[0:300]          # every row of [0, 300) has an exact duplicate further down
+    V[700] = V[5]
+    T = V[:N].copy()               # queries identical to their ground truth: d(t, gt) ties with the copies
+    T[350:] = V[350:N] * np.float32(0.5)
+    Vt, Tt = torch.from_numpy(V), torch.from_numpy(T)
+    for metric in ("l2", "dot"):
+        rank0, gts = ops.sim_rank(Tt.to(cuda_dev), Vt.to(cuda_dev), metric=metric, precision=precision)
+        ops.rank_finalize(rank0, gts, M, [1])
+        np.testing.assert_array_equal(_np(rank0), _oracle_ranks(Tt, Vt, metric, precision))
 
 
 @pytest.mark.parametrize("precision", ["brute", "exact", "bf16"])
@@ -833,3 +859,161 @@ def test_sharded_eval_single_process_equals_whole(cuda_dev):
     assert _np(res["medr"])[0] == O.medr(want)
     v, i = sharded_topk(q, g, 600, 5, precision="exact")
     np.testing.assert_array_equal(_np(i), O.topk_exact(T, V, 5)[1])
+
+
+# ----------------------------------------------------------- variants promoted in round 2
+def test_more_than_eight_k_values(cuda_dev):
+    """RecallAtK accepts any number of k values like the reference (model/metric.py:104-108); the C
+    entry point counts 8 per call."""
+    from vtc_b200.model.metric import RecallAtK
+
+    T, V = make_retrieval_pair(400, 400, 64, sigma=3.0, seed=4)
+    ks = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 20, 50]
+    got = RecallAtK("v", "t", ks).compute(V.to(cuda_dev), T.to(cuda_dev))
+    want = O.recall_at_k(V.numpy(), T.numpy(), ks)
+    assert [k for k, _ in got] == ks
+    assert [r for _, r in got] == [r for _, r in want]
+
+
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+def test_cached_ranking_same_ranks(cuda_dev, golden, precision):
+    """vtc_rank_prepare / vtc_sim_rank_prepared: norms, norm bounds and ground-truth scores computed
+    once (by vtc_rank_prepare or by the first ranking call that sees the rows) and handed to every
+    later call as slices of per-gallery arrays -- the host-staging pipeline and the sharded step run
+    on this.  Same ranks as the oracle, whichever call produced the cached values."""
+    from vtc_b200 import ops
+
+    def canon(x):  # cached values are tied to the canonical rows of the mode
+        return x.to(cuda_dev).bfloat16() if precision == "bf16" else x.to(cuda_dev)
+
+    cases = [make_retrieval_pair(1000, 1000, 512, sigma=4.0, seed=3) + ("l2",),
+             make_retrieval_pair(333, 1201, 96, sigma=2.0, seed=4) + ("dot",),
+             make_retrieval_pair(129, 257, 768, sigma=7.0, seed=5) + ("l2",)]
+    g = golden("retrieval_small.npz")           # ties, zero row, non-unit row, NaN query, inf rows
+    cases.append((torch.from_numpy(g["queries"]), torch.from_numpy(g["gallery"]), "l2"))
+    for T, V, metric in cases:
+        q, gal = canon(T), canon(V)
+        N, M = q.shape[0], gal.shape[0]
+        want = _oracle_ranks(T, V, metric, precision)
+        gts = ops.gt_scores(q, gal, metric=metric, precision=precision)
+        sq64, _ = ops.rank_prepare(gal, precision, want_qq=False)
+        _, qq = ops.rank_prepare(q, precision, want_sq64=False)
+        np.testing.assert_array_equal(_np(sq64), O.sqnorm64(_np(gal.float())))
+        assert (_np(qq) >= O.sqnorm64(_np(q.float())))[~np.isnan(_np(qq))].all()
+        # whole gallery in one call, everything handed in
+        rank0 = torch.full((N,), -5, dtype=torch.int32, device=cuda_dev)
+        ops.sim_rank(q, gal, metric=metric, precision=precision, gt_score=gts, rank0=rank0,
+                     accumulate=False, sq64=sq64, qq=qq)
+        ops.rank_finalize(rank0, gts, M, [1])
+        np.testing.assert_array_equal(_np(rank0), want)
+        # the ranking call itself produces the cached values: same bits as vtc_rank_prepare's
+        sq_o = torch.empty(M, dtype=torch.float64, device=cuda_dev)
+        qq_o = torch.empty(N, dtype=torch.float32, device=cuda_dev)
+        gs_o = torch.empty(N, dtype=torch.float64, device=cuda_dev)
+        r2, _ = ops.sim_rank(q, gal, metric=metric, precision=precision, gt_score_out=gs_o,
+                             sq64_out=sq_o, qq_out=qq_o)
+        ops.rank_finalize(r2, gs_o, M, [1])
+        np.testing.assert_array_equal(_np(r2), want)
+        np.testing.assert_array_equal(_np(sq_o), _np(sq64))
+        np.testing.assert_array_equal(_np(gs_o), _np(gts))
+        # ... and accumulated over ragged gallery chunks with slices of the same arrays
+        acc = torch.zeros(N, dtype=torch.int32, device=cuda_dev)
+        bounds = [0, M // 3, M // 3 + 1, M]
+        for s, e in zip(bounds[:-1], bounds[1:]):
+            ops.sim_rank(q, gal[s:e].contiguous(), col_offset=s, metric=metric, precision=precision,
+                         gt_score=gts, rank0=acc, accumulate=True, sq64=sq64[s:e].contiguous(), qq=qq)
+        ops.rank_finalize(acc, gts, M, [1])
+        np.testing.assert_array_equal(_np(acc), want)
+
+
+def test_host_staging_pipeline_matches_device_path(cuda_dev):
+    """RecallAtK.compute from host arrays (interleaved chunk pairs, cached per-row quantities): the
+    same ranks and hits as the single device-resident call, and as the oracle on a slice."""
+    from vtc_b200.model.metric import RecallAtK
+
+    N, D = 40_000, 256                           # 41 MB per side: above PIPELINE_MIN_BYTES
+    T, V = make_retrieval_pair(N, N, D, sigma=5.0, seed=12)
+    for precision in ("bf16", "exact"):
+        m = RecallAtK("v", "t", [1, 5, 10], precision=precision)
+        full = m.compute_full(V.numpy(), T.numpy())
+        sl = slice(20_000, 20_200)
+        want = O.rank0_exact(O.bf16_round(T[sl]) if precision == "bf16" else T[sl],
+                             O.bf16_round(V) if precision == "bf16" else V, row_offset=20_000)
+        np.testing.assert_array_equal(_np(full["rank0"][sl]), want)
+        base = m.compute_full(V.to(cuda_dev), T.to(cuda_dev))
+        np.testing.assert_array_equal(_np(full["rank0"]), _np(base["rank0"]))
+        np.testing.assert_array_equal(_np(full["hits"]), _np(base["hits"]))
+        assert _np(full["medr"])[0] == _np(base["medr"])[0]
+
+
+@pytest.mark.parametrize("precision", ["brute", "exact", "bf16"])
+def test_infinite_gallery_rows(cuda_dev, precision):
+    """Gallery rows of -inf (the padding rows evaluation/retrieval_evaluation.py:238-252 creates for
+    missing captions) and +inf, also as ground truth.  Canonical arithmetic gives such a column an
+    infinite or NaN score (NaN comparisons false; -inf closer than everything).  The 3-term bf16
+    split cannot carry inf (x - bf16(x) is NaN), so the exact mode must notice and recount in
+    canonical arithmetic (round 1 silently lost the -inf scores of the DOT metric here)."""
+    from vtc_b200 import ops
+
+    T, V = make_retrieval_pair(300, 900, 128, sigma=3.0, seed=31)
+    V[7] = float("-inf")          # ground truth of query 7
+    V[400] = float("-inf")
+    V[401, :5] = float("inf")
+    V[20] = V[7]
+    for metric in ("l2", "dot"):
+        rank0, gts = ops.sim_rank(T.to(cuda_dev), V.to(cuda_dev), metric=metric, precision=precision)
+        ops.rank_finalize(rank0, gts, 900, [1])
+        want = _oracle_ranks(T, V, metric, "bf16" if precision == "bf16" else "exact")
+        d0 = O.scores64(O.bf16_round(T) if precision == "bf16" else T,
+                        O.bf16_round(V) if precision == "bf16" else V, METRICS[metric])[
+            np.arange(300), np.arange(300)]
+        want = np.where(np.isnan(d0), 900, want)     # vtc_rank_finalize: NaN score -> rank M
+        np.testing.assert_array_equal(_np(rank0), want)
+        # the one-call evaluation takes the same fallback
+        full = ops.rank_eval(T.to(cuda_dev), V.to(cuda_dev), [1, 5, 10], metric=metric,
+                             precision=precision)
+        np.testing.assert_array_equal(_np(full["rank0"]), want)
+        np.testing.assert_array_equal(_np(full["hits"]), [np.sum(want < k) for k in (1, 5, 10)])
+        assert _np(full["medr"])[0] == O.medr(want)
+
+
+@pytest.mark.parametrize("precision", ["brute", "exact", "bf16"])
+@pytest.mark.parametrize("N,M,D", [(1000, 1000, 512), (333, 1201, 96), (5, 3000, 64), (700, 700, 100),
+                                   (2500, 2500, 768)])
+def test_rank_eval_one_call(cuda_dev, precision, N, M, D):
+    """vtc_rank_eval (memset + prologue + tensor-core pass + cooperative epilogue) == vtc_sim_rank +
+    vtc_rank_finalize == oracle: ranks, hit counts, median, ground-truth scores."""
+    from vtc_b200 import ops
+
+    T, V = make_retrieval_pair(min(N, M), M, D, sigma=3.0, seed=N + D, mixed=True)
+    T = T[:N].contiguous()
+    q, g = T.to(cuda_dev), V.to(cuda_dev)
+    ks = [1, 5, 10]
+    full = ops.rank_eval(q, g, ks, precision=precision)
+    want = _oracle_ranks(T, V, "l2", precision)
+    np.testing.assert_array_equal(_np(full["rank0"]), want)
+    np.testing.assert_array_equal(_np(full["hits"]), [np.sum(want < k) for k in ks])
+    assert _np(full["medr"])[0] == O.medr(want)
+    r2, gts = ops.sim_rank(q, g, precision=precision)
+    h2, m2 = ops.rank_finalize(r2, gts, M, ks)
+    np.testing.assert_array_equal(_np(r2), want)
+    np.testing.assert_array_equal(_np(h2), _np(full["hits"]))
+    np.testing.assert_array_equal(_np(gts), _np(full["gt_score"]))
+    assert _np(m2)[0] == _np(full["medr"])[0]
+
+
+def test_rank_finalize_median_wide_ranks(cuda_dev):
+    """The radix-select median over the full int32 range (three 11/11/10-bit levels), odd and even
+    N, the two middle order statistics in different bins."""
+    from vtc_b200 import ops
+
+    rng = np.random.default_rng(5)
+    for n, hi in ((1, 10), (2, 5_000_000), (1001, 3_000_000), (4096, 900), (50_000, 2**30)):
+        r = rng.integers(0, hi, size=n).astype(np.int32)
+        if n == 4096:
+            r[:2048] = 3            # median straddles two far-apart values
+            r[2048:] = 800
+        t = torch.from_numpy(r).to(cuda_dev)
+        hits, medr = ops.rank_finalize(t, None, int(hi), [1, 5, 10])
+        np.testing.assert_array_equal(_np(hits), [np.sum(r < k) for k in (1, 5, 10)])
+        assert _np(medr)[0] == O.medr(r)

@@ -18,7 +18,7 @@ PREC_EXACT, PREC_BF16, PREC_BRUTE = 0, 1, 2
 OP_SIM_RANK, OP_SIM_TOPK, OP_INFONCE_FWD, OP_SIM_MATRIX, OP_INFONCE_BWD, OP_GT_SCORES, OP_LINEAR = range(7)
 CAM_READOUT_AVG, CAM_READOUT_RESIDUAL_ONLY, CAM_READOUT_UNIFORM = 0, 1, 2
 RESACT_NONE, RESACT_NORMALIZE_EPS, RESACT_SQUASH, RESACT_TANH, RESACT_AFFINE = range(5)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _P = c_void_p
 
@@ -33,9 +33,12 @@ SIGNATURES = {
                                c_size_t, _P]),
     "vtc_sim_rank": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int,
                              c_int, _P, _P, c_int, _P, _P, c_size_t, _P]),
+    "vtc_rank_eval": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, c_int, c_int, POINTER(c_int),
+                              c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "vtc_rank_prepare": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
     "vtc_sim_rank_prepared": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64,
-                                      c_int, c_int, _P, _P, _P, c_int, _P, _P, c_size_t, _P]),
+                                      c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, c_size_t,
+                                      _P]),
     "vtc_gt_scores": (c_int, [_P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int,
                               c_int, _P, _P, c_size_t, _P]),
     "vtc_rank_finalize": (c_int, [_P, _P, c_int64, c_int64, POINTER(c_int), c_int, _P, _P, _P,
@@ -58,6 +61,7 @@ SIGNATURES = {
     "vtc_launch_count": (c_uint64, []),
     "vtc_kernel_timer_enable": (c_int, [c_int]),
     "vtc_kernel_timer_read": (c_int, [POINTER(c_double), POINTER(c_int)]),
+    "vtc_debug_prof_read": (c_int, [POINTER(c_uint64), c_int]),
 }
 
 
@@ -136,3 +140,11 @@ def kernel_timer_read():
     n = c_int(0)
     check(load().vtc_kernel_timer_read(ctypes.byref(ms), ctypes.byref(n)), "vtc_kernel_timer_read")
     return ms.value, n.value
+
+
+def debug_prof_read(n_ctas: int = 148):
+    """VTC_DBG_PROF=1 only: per-CTA wait counters of the last tensor-core launch, as a list of
+    8-tuples (see include/vtc_b200.h::vtc_debug_prof_read); synchronises the device."""
+    buf = (c_uint64 * (8 * n_ctas))()
+    check(load().vtc_debug_prof_read(buf, 8 * n_ctas), "vtc_debug_prof_read")
+    return [tuple(int(buf[8 * i + j]) for j in range(8)) for i in range(n_ctas)]

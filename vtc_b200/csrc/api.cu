@@ -7,8 +7,8 @@
 
 #include "cam.cuh"
 #include "exact.cuh"
-#include "fold.cuh"
 #include "prep.cuh"
+#include "rank_stage.cuh"
 #include "reduce.cuh"
 #include "sim_tc.cuh"
 
@@ -29,7 +29,11 @@ namespace {
 // -- partial sums are bounded by it (Cauchy-Schwarz) -- plus 8 steps of slack for the epilogue's
 // own fp32 roundings (measured total on B200: <= 1.8e-7 at K = 768, 13x inside the bound).
 //   BF16 : products of bf16 are exact in fp32, so that is the whole error;
-//   EXACT: the 3-term bf16 split additionally drops <= 3 * 2^-18 (1.15e-5) of each product.
+//   EXACT: x = hi + lo + e with hi = bf16(x), lo = bf16(x - hi).  bf16 carries 8 significand bits,
+//          so its unit roundoff is 2^-8: |x - hi| <= 2^-8 |x|, |e| <= 2^-16 |x|, |lo| <= 2^-8 |x|.
+//          hi*hi + hi*lo + lo*hi drops lo_q*lo_x + e_q*x + q*e_x (+ third-order terms), i.e. at most
+//          3 * 2^-16 (1 + 2^-7) < 4.62e-5 of |q_k||x_k| per product, and by Cauchy-Schwarz of
+//          |q||x| per row.
 float guard_rel_for(int precision, int Kp) {
   const char* e = getenv(precision == VTC_PREC_BF16 ? "VTC_GUARD_REL_BF16" : "VTC_GUARD_REL_EXACT");
   if (e && *e) {
@@ -37,7 +41,7 @@ float guard_rel_for(int precision, int Kp) {
     if (v > 0.f) return v;
   }
   const float accum = (float)(Kp / 16 + 8) * 5.9604645e-08f;
-  return precision == VTC_PREC_BF16 ? accum : 1.2e-05f + accum;
+  return precision == VTC_PREC_BF16 ? accum : 4.62e-05f + accum;
 }
 
 bool valid_dtype(int d) { return d == VTC_F32 || d == VTC_BF16; }
@@ -70,33 +74,14 @@ static bool operand_is_input(const void* X, int D, int dtype, const OperandPlan&
 struct RankWs {
   __nv_bfloat16 *opQ, *opG;
   double *sq64, *dgt;
-  float* sq32;
-  unsigned int* scalars;  // [0] max_sq_bits, [2] overflow, [64..] per-CTA list segment counts
-  float2* thr;
-  int* rank_tmp;
-  __nv_bfloat16 *foldQ, *foldG;  // EPI_RANK_FOLD operands [N, 64], [round_up(M, 256), 64]
-  float* foldW;                  // [N] guard band around acc' = 0
+  float *sq32, *qq;
+  unsigned int* scalars;  // [0] max_sq_bits, [2] fallback flag, [64..] per-CTA list segment counts
+  int* rank_tmp;          // directly behind `scalars`: one memset clears both
+  unsigned int* hist;     // scratch of the fused finalisation (vtc_rank_eval)
   int2* amb;
   size_t amb_cap;
 };
-
-// EPI_RANK_FOLD (bias and ground-truth score folded into the MMA, sign-bit epilogue) is opt-in
-// until it has been validated and measured on a B200: VTC_RANK_FOLD=1.
-bool rank_fold_enabled() {
-  const char* e = getenv("VTC_RANK_FOLD");
-  return e && *e && atoi(e) != 0;
-}
-// Opt-in until timed on a B200 (VTC_FAST_THR=1): guard-band thresholds from a coalesced fp32 norm
-// of the query rows (launch_thr_fast) instead of gt_score_kernel's second fp64 walk over them.
-bool fast_thr_enabled() {
-  const char* e = getenv("VTC_FAST_THR");
-  return e && *e && atoi(e) != 0;
-}
-// columns of the fold operands in global memory (fold.cuh): 64 (default) or 16
-int fold_cols() {
-  const char* e = getenv("VTC_FOLD_COLS");
-  return e && atoi(e) == 16 ? 16 : FOLD_COLS_MAX;
-}
+constexpr size_t kRankScalars = 64 + 256;
 
 size_t amb_entries_wanted(int64_t N) {
   const int64_t want = 64 * N;
@@ -107,19 +92,17 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
                   bool sizing) {
   RankWs r;
   memset(&r, 0, sizeof(r));
+  r.scalars = ws.take<unsigned int>(kRankScalars);  // 1280 bytes: a whole number of 256-byte granules
+  r.rank_tmp = ws.take<int>(N);
   r.sq64 = ws.take<double>(M);
   r.dgt = ws.take<double>(N);
-  r.scalars = ws.take<unsigned int>(64 + 256);
+  r.hist = ws.take<unsigned int>(rank_epilogue_hist_words());
   if (precision != VTC_PREC_BRUTE) {
     const OperandPlan o = plan_operands(D, dtype, precision);
     r.opQ = ws.take<__nv_bfloat16>((size_t)N * o.Kp);
     r.opG = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
     r.sq32 = ws.take<float>(round_up<int64_t>(M, tc::BN));
-    r.thr = ws.take<float2>(N);
-    r.rank_tmp = ws.take<int>(N);
-    r.foldQ = ws.take<__nv_bfloat16>((size_t)N * FOLD_COLS_MAX);
-    r.foldG = ws.take<__nv_bfloat16>((size_t)round_up<int64_t>(M, tc::BN) * FOLD_COLS_MAX);
-    r.foldW = ws.take<float>(N);
+    r.qq = ws.take<float>(N);
     if (sizing) {
       r.amb_cap = amb_entries_wanted(N);
       ws.take<int2>(r.amb_cap);
@@ -135,28 +118,54 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   return r;
 }
 
-// sq64_in / qq_in (both or neither; vtc_sim_rank_prepared): canonical ||x_j||^2 of THIS gallery
-// chunk and an upper bound of ||q_t||^2, computed once by vtc_rank_prepare.  With them (and a given
-// gt_score) the call walks no row outside the tensor-core pass and the re-check.
+// What the fused finalisation of vtc_rank_eval needs (NULL for plain vtc_sim_rank calls).
+struct RankFinalize {
+  int64_t M_total;
+  const int* k_vals;
+  int nk;
+  int64_t* hits;
+  double* medr;
+};
+
+// One retrieval evaluation (or one gallery chunk of it) = memset + prologue + tensor-core pass +
+// cooperative epilogue.
+// Cached per-row quantities (vtc_sim_rank_prepared): canonical ||x_j||^2 of THIS gallery chunk
+// (sq64_in, or computed into sq64_out), an upper bound of ||q_t||^2 (qq_in, or computed into
+// qq_out) and d(t,gt) (gt_score, or computed into gt_score_out).  With all three given (and bf16 rows
+// that are the operands) the prologue touches no row at all.
+struct RankCache {
+  const double* sq64_in;
+  double* sq64_out;
+  const float* qq_in;
+  float* qq_out;
+};
 int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
                   const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
                   int precision, const double* gt_score, double* gt_score_out, int accumulate,
                   int32_t* rank0, void* wsp, size_t ws_bytes, cudaStream_t s,
-                  const double* sq64_in = nullptr, const float* qq_in = nullptr) {
+                  const RankCache* cache = nullptr, const RankFinalize* fin = nullptr) {
+  const double* sq64_in = cache ? cache->sq64_in : nullptr;
+  const float* qq_in = cache ? cache->qq_in : nullptr;
   if (N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) || !valid_metric(metric) ||
       !valid_prec(precision))
     return VTC_ERR_INVALID_ARG;
-  const bool prepared = sq64_in != nullptr;
-  if (prepared && (!qq_in || !gt_score || precision == VTC_PREC_BRUTE || M == 0))
+  if (cache && (precision == VTC_PREC_BRUTE || M == 0)) return VTC_ERR_INVALID_ARG;
+  if (fin && (fin->nk < 0 || fin->nk > 8 || (fin->nk > 0 && (!fin->k_vals || !fin->hits))))
     return VTC_ERR_INVALID_ARG;
-  if (N == 0) return VTC_OK;  // no queries: nothing to rank (pointers may be NULL)
+  if (N == 0) {  // no queries: nothing to rank (pointers may be NULL)
+    if (fin)
+      return launch_rank_finalize(rank0, nullptr, 0, fin->M_total, fin->k_vals, fin->nk, fin->hits,
+                                  fin->medr, nullptr, s);
+    return VTC_OK;
+  }
   if (!Q || (!G && M > 0) || !rank0) return VTC_ERR_INVALID_ARG;
   if (N > kMaxRows || M > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
   Workspace ws(wsp, ws_bytes);
   RankWs w = carve_rank(ws, N, M, D, dtype, precision, false);
-  if (!ws.ok() || !w.sq64 || !w.dgt || !w.scalars) return VTC_ERR_WORKSPACE;
+  if (!ws.ok() || !w.sq64 || !w.dgt || !w.scalars || !w.rank_tmp || !w.hist) return VTC_ERR_WORKSPACE;
   const bool in_bf16 = dtype == VTC_BF16;
-  cudaError_t e = cudaMemsetAsync(w.scalars, 0, (64 + 256) * sizeof(unsigned int), s);
+  cudaError_t e = cudaMemsetAsync(
+      w.scalars, 0, kRankScalars * sizeof(unsigned int) + round_up<size_t>(sizeof(int) * N, 256), s);
   if (e != cudaSuccess) return cuda_err(e);
 
   if (precision == VTC_PREC_BRUTE || M == 0) {
@@ -172,102 +181,82 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
       e = cudaMemsetAsync(rank0, 0, sizeof(int32_t) * N, s);
       if (e != cudaSuccess) return cuda_err(e);
     }
-    return launch_rank_brute(ex, w.dgt, rank0, nullptr, s);
+    VTC_RETURN_IF_ERROR(launch_rank_brute(ex, w.dgt, rank0, nullptr, s));
+    if (fin)
+      return launch_rank_finalize(rank0, w.dgt, N, fin->M_total, fin->k_vals, fin->nk, fin->hits,
+                                  fin->medr, w.hist, s);
+    return VTC_OK;
   }
 
-  if (!w.opQ || !w.opG || !w.thr || !w.rank_tmp || !w.amb || w.amb_cap < 1024)
-    return VTC_ERR_WORKSPACE;
+  if (!w.opQ || !w.opG || !w.sq32 || !w.qq || !w.amb || w.amb_cap < 1024) return VTC_ERR_WORKSPACE;
   const OperandPlan o = plan_operands(D, dtype, precision);
-  // 1. bf16 operands
-  const __nv_bfloat16* opQ = w.opQ;
-  const __nv_bfloat16* opG = w.opG;
-  if (operand_is_input(Q, D, dtype, o))
-    opQ = static_cast<const __nv_bfloat16*>(Q);
-  else
-    VTC_RETURN_IF_ERROR(launch_prep_operand(Q, in_bf16, N, D, D,
-                                            o.split ? PREP_SPLIT_A : PREP_PLAIN, w.opQ, o.Kp, s));
-  if (operand_is_input(G, D, dtype, o))
-    opG = static_cast<const __nv_bfloat16*>(G);
-  else
-    VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D,
-                                            o.split ? PREP_SPLIT_B : PREP_PLAIN, w.opG, o.Kp, s));
-  // canonical values: fp32 inputs (split) or the bf16 operands
-  const double* sq64 = prepared ? sq64_in : w.sq64;
-  const double* dgt = prepared ? gt_score : w.dgt;
+  const bool aliasQ = operand_is_input(Q, D, dtype, o), aliasG = operand_is_input(G, D, dtype, o);
+  const __nv_bfloat16* opQ = aliasQ ? static_cast<const __nv_bfloat16*>(Q) : w.opQ;
+  const __nv_bfloat16* opG = aliasG ? static_cast<const __nv_bfloat16*>(G) : w.opG;
+  // computed quantities land where the caller wants them
+  double* sq64_w = (cache && cache->sq64_out) ? cache->sq64_out : w.sq64;
+  float* qq_w = (cache && cache->qq_out) ? cache->qq_out : w.qq;
+  double* dgt_w = (!gt_score && gt_score_out) ? gt_score_out : w.dgt;
+  const double* sq64 = sq64_in ? sq64_in : sq64_w;
+  const double* dgt = gt_score ? gt_score : dgt_w;
+  const float* qq = qq_in ? qq_in : qq_w;
+  // canonical values: the fp32 inputs (split) or the bf16 operands
   ExactArgs ex;
   if (o.split)
     ex = ExactArgs{Q, G, D, D, false, N, M, D, sq64, gt, row_offset, col_offset, metric};
   else
     ex = ExactArgs{opQ, opG, o.Kp, o.Kp, true, N, M, D, sq64, gt, row_offset, col_offset, metric};
-  // 2. canonical norms, ground-truth scores, guard band
-  if (prepared) {
-    // everything per-row is cached: padded fp32 bias + max norm from sq64, thresholds from
-    // (d(t,gt), ||q_t||^2 bound) -- three small launches, no row is read
-    VTC_RETURN_IF_ERROR(launch_bias_max(sq64, M, round_up<int64_t>(M, tc::BN), metric, w.sq32,
-                                        &w.scalars[0], s));
-    VTC_RETURN_IF_ERROR(launch_thr_cached(qq_in, dgt, &w.scalars[0], N, metric,
-                                          guard_rel_for(precision, o.Kp), w.thr, s));
-  } else {
-    VTC_RETURN_IF_ERROR(
-        launch_sqnorm64(ex.G, ex.bf16, M, D, ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
-    if (fast_thr_enabled()) {
-      VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, nullptr, nullptr, 0.f, s));
-      VTC_RETURN_IF_ERROR(launch_thr_fast(ex.Q, ex.bf16, ex.ldq, N, D, w.dgt, &w.scalars[0], metric,
-                                          guard_rel_for(precision, o.Kp), w.thr, s));
-    } else {
-      VTC_RETURN_IF_ERROR(launch_gt_score(ex, gt_score, w.dgt, w.thr, &w.scalars[0],
-                                          guard_rel_for(precision, o.Kp), s));
-    }
-    // per-column epilogue bias: ||x_j||^2 (L2) or 0 (DOT); padding columns are +inf (never counted)
-    VTC_RETURN_IF_ERROR(launch_fill_bias(w.sq32, metric == VTC_METRIC_L2 ? w.sq32 : nullptr, M,
-                                         round_up<int64_t>(M, tc::BN), INFINITY, s));
-  }
-  if (gt_score_out && gt_score_out != dgt) {
-    e = cudaMemcpyAsync(gt_score_out, dgt, sizeof(double) * N, cudaMemcpyDeviceToDevice, s);
+  // 1. prologue: operands, canonical norms, ground-truth scores, bias, guard-band inputs
+  const int64_t Mpad = round_up<int64_t>(M, tc::BN);
+  RankPrologueArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.Q = Q, pa.G = G, pa.in_bf16 = in_bf16 ? 1 : 0, pa.N = N, pa.M = M, pa.D = D;
+  pa.ldq = D, pa.ldg = D;
+  pa.mode_q = aliasQ ? STAGE_NONE : (o.split ? PREP_SPLIT_A : PREP_PLAIN);
+  pa.mode_g = aliasG ? STAGE_NONE : (o.split ? PREP_SPLIT_B : PREP_PLAIN);
+  pa.round_bf16 = (!o.split && !in_bf16) ? 1 : 0;
+  pa.opQ = w.opQ, pa.opG = w.opG, pa.Kp = o.Kp, pa.metric = metric;
+  pa.sq64_in = sq64_in, pa.sq64 = sq64_w, pa.bias = w.sq32, pa.Mpad = Mpad;
+  pa.max_sq_bits = &w.scalars[0];
+  pa.gt_in = gt_score, pa.dgt = dgt_w, pa.qq_in = qq_in, pa.qq = qq_w;
+  pa.gt = gt, pa.row_offset = row_offset, pa.col_offset = col_offset;
+  pa.fallback = &w.scalars[2];
+  VTC_RETURN_IF_ERROR(launch_rank_prologue(pa, s));
+  if (gt_score && gt_score_out && gt_score_out != gt_score) {
+    e = cudaMemcpyAsync(gt_score_out, gt_score, sizeof(double) * N, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return cuda_err(e);
   }
-  e = cudaMemsetAsync(w.rank_tmp, 0, sizeof(int) * N, s);
-  if (e != cudaSuccess) return cuda_err(e);
-  // 3. tensor-core pass
+  // 2. tensor-core pass
   tc::Params p;
   memset(&p, 0, sizeof(p));
   p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
   p.gt = gt, p.gt_row_offset = row_offset, p.gt_col_offset = col_offset;
   p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
-  p.thr = w.thr, p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_seg_count = &w.scalars[64];
+  p.dgt = dgt, p.qq = qq, p.max_sq_bits = &w.scalars[0];
+  p.guard_rel = guard_rel_for(precision, o.Kp), p.metric_l2 = metric == VTC_METRIC_L2 ? 1 : 0;
+  p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_seg_count = &w.scalars[64];
   tc::Plan pl = tc::plan_tiles(p, 64, tc::choose_cluster(N, M));
   if (pl.grid > 256) return VTC_ERR_UNSUPPORTED_SHAPE;
   p.amb_seg_cap = (unsigned int)(w.amb_cap / (size_t)pl.grid);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
-  if (rank_fold_enabled() && pl.cluster == 2 && w.foldQ && w.foldG && w.foldW) {
-    // fold pass: the bias and d(t,gt) enter through one extra K16 step (fold.cu); always a CTA pair
-    const int64_t Mpad = round_up<int64_t>(M, tc::BN);
-    const int fc = fold_cols();
-    VTC_RETURN_IF_ERROR(launch_fold_g(sq64, M, Mpad, metric, w.foldG, fc, &w.scalars[2], s));
-    VTC_RETURN_IF_ERROR(launch_fold_q(w.thr, dgt, &w.scalars[0], N, metric,
-                                      guard_rel_for(precision, o.Kp), w.foldQ, fc, w.foldW,
-                                      &w.scalars[2], s));
-    // the box is {64, rows} either way: with 16-column operands the rest of each 128-byte row is
-    // out of range and zero-filled by TMA, exactly like a K tail
-    CUtensorMap tmAx, tmBx;
-    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.foldQ, N, fc, fc, tc::BM, &tmAx));
-    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.foldG, Mpad, fc, fc, tc::BN / 2, &tmBx));
-    p.fold_w = w.foldW;
-    pl.pair = true;
-    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK_FOLD, p.num_kb <= 8, pl, tmA, tmB, p, s,
-                                          &tmAx, &tmBx));
-  } else {
-    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
+  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
+  // 3. epilogue: exact re-check of the guard-band groups (brute force if the list overflowed),
+  //    commit, and -- for vtc_rank_eval -- hit counts and the median rank
+  RankEpilogueArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.ex = ex, ea.amb_list = w.amb, ea.seg_count = &w.scalars[64], ea.nseg = pl.grid;
+  ea.seg_cap = p.amb_seg_cap, ea.dgt = dgt, ea.rank_tmp = w.rank_tmp, ea.fallback = &w.scalars[2];
+  ea.rank0 = rank0, ea.accumulate = accumulate;
+  if (fin) {
+    ea.finalize = 1, ea.M_total = fin->M_total, ea.nk = fin->nk;
+    for (int i = 0; i < fin->nk; ++i) ea.k_vals[i] = fin->k_vals[i];
+    ea.hits = reinterpret_cast<unsigned long long*>(fin->hits), ea.medr = fin->medr;
+    ea.hist = w.hist;
   }
-  // 4. exact re-check of the guard-band pairs; brute force if the list overflowed
-  VTC_RETURN_IF_ERROR(launch_recheck(ex, w.amb, &w.scalars[64], pl.grid, p.amb_seg_cap, dgt,
-                                     w.rank_tmp, &w.scalars[2], s));
-  VTC_RETURN_IF_ERROR(launch_zero_if_flag(w.rank_tmp, N, &w.scalars[2], s));
-  VTC_RETURN_IF_ERROR(launch_rank_brute(ex, dgt, w.rank_tmp, &w.scalars[2], s));
-  return launch_rank_commit(w.rank_tmp, rank0, N, accumulate, s);
+  return launch_rank_epilogue(ea, s);
 }
 
 // ------------------------------------------------------------------------------------ sim_topk
@@ -620,6 +609,10 @@ int vtc_kernel_timer_read(double* total_ms, int* count) {
   return tc::kernel_timer_read(total_ms, count);
 }
 
+int vtc_debug_prof_read(unsigned long long* out, int max_words) {
+  return tc::debug_prof_read(out, max_words);
+}
+
 size_t vtc_workspace_bytes(int op, int64_t N, int64_t M, int D, int precision) {
   if (N < 0 || M < 0 || D <= 0 || !valid_prec(precision)) return 0;
   Workspace ws(nullptr, 0);
@@ -688,6 +681,16 @@ int vtc_sim_rank(const void* Q, const void* G, int64_t N, int64_t M, int D, int 
                        (cudaStream_t)stream);
 }
 
+int vtc_rank_eval(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
+                  const int64_t* gt, int metric, int precision, const int* k_vals, int nk,
+                  int32_t* rank0, int64_t* hits, double* medr, double* gt_score_out, void* ws,
+                  size_t ws_bytes, vtc_stream_t stream) {
+  if (nk < 0 || nk > 8 || (nk > 0 && (!k_vals || !hits))) return VTC_ERR_INVALID_ARG;
+  RankFinalize fin{M, k_vals, nk, hits, medr};
+  return sim_rank_impl(Q, G, N, M, D, dtype, gt, 0, 0, metric, precision, nullptr, gt_score_out, 0,
+                       rank0, ws, ws_bytes, (cudaStream_t)stream, nullptr, &fin);
+}
+
 int vtc_rank_prepare(const void* X, int64_t rows, int D, int dtype, int precision, double* sq64,
                      float* qq_up, vtc_stream_t stream) {
   if (!X || rows < 0 || D <= 0 || !valid_dtype(dtype) || !valid_prec(precision) || (!sq64 && !qq_up))
@@ -695,28 +698,36 @@ int vtc_rank_prepare(const void* X, int64_t rows, int D, int dtype, int precisio
   // the canonical values must be the rows as handed in: bf16 rows in the bf16 mode, fp32 rows
   // otherwise (fp32 rows in the bf16 mode would have to be rounded first -- hand in the rounded rows)
   if ((precision == VTC_PREC_BF16) != (dtype == VTC_BF16)) return VTC_ERR_UNSUPPORTED_SHAPE;
-  cudaStream_t s = (cudaStream_t)stream;
-  const bool in_bf16 = dtype == VTC_BF16;
-  if (sq64) VTC_RETURN_IF_ERROR(launch_sqnorm64(X, in_bf16, rows, D, D, sq64, nullptr, nullptr, s));
-  if (qq_up) VTC_RETURN_IF_ERROR(launch_qnorm_up(X, in_bf16, D, rows, D, qq_up, s));
-  return VTC_OK;
+  // one staged pass over the rows (rank_stage.cu): as gallery rows for the canonical norms, as
+  // query rows for the norm bounds
+  RankPrologueArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.in_bf16 = dtype == VTC_BF16 ? 1 : 0, pa.D = D, pa.ldq = D, pa.ldg = D;
+  pa.mode_q = STAGE_NONE, pa.mode_g = STAGE_NONE, pa.metric = VTC_METRIC_L2;
+  if (sq64) pa.G = X, pa.M = rows, pa.Mpad = rows, pa.sq64 = sq64;
+  if (qq_up) pa.Q = X, pa.N = rows, pa.qq = qq_up;
+  return launch_rank_prologue(pa, (cudaStream_t)stream);
 }
 
 int vtc_sim_rank_prepared(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
                           const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
-                          int precision, const double* gt_score, const double* sq64,
-                          const float* qq_up, int accumulate, int32_t* rank0, void* ws,
-                          size_t ws_bytes, vtc_stream_t stream) {
-  if (!gt_score || !sq64 || !qq_up) return VTC_ERR_INVALID_ARG;
-  if ((precision == VTC_PREC_BF16) != (dtype == VTC_BF16)) return VTC_ERR_UNSUPPORTED_SHAPE;
+                          int precision, const double* gt_score, double* gt_score_out,
+                          const double* sq64, double* sq64_out, const float* qq_up, float* qq_out,
+                          int accumulate, int32_t* rank0, void* ws, size_t ws_bytes,
+                          vtc_stream_t stream) {
+  if ((!sq64 && !sq64_out) || (!qq_up && !qq_out) || (!gt_score && !gt_score_out))
+    return VTC_ERR_INVALID_ARG;
+  if (precision == VTC_PREC_BRUTE) return VTC_ERR_UNSUPPORTED_SHAPE;
   if (N > 0 && M == 0) {  // an empty gallery chunk adds nothing
     if (accumulate) return VTC_OK;
     return sim_rank_impl(Q, G, N, M, D, dtype, gt, row_offset, col_offset, metric, precision,
-                         gt_score, nullptr, accumulate, rank0, ws, ws_bytes, (cudaStream_t)stream);
+                         gt_score, gt_score_out, accumulate, rank0, ws, ws_bytes,
+                         (cudaStream_t)stream);
   }
+  const RankCache cache{sq64, sq64_out, qq_up, qq_out};
   return sim_rank_impl(Q, G, N, M, D, dtype, gt, row_offset, col_offset, metric, precision,
-                       gt_score, nullptr, accumulate, rank0, ws, ws_bytes, (cudaStream_t)stream,
-                       sq64, qq_up);
+                       gt_score, gt_score_out, accumulate, rank0, ws, ws_bytes, (cudaStream_t)stream,
+                       &cache);
 }
 
 int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
@@ -760,8 +771,19 @@ int vtc_rank_finalize(int32_t* rank0, const double* gt_score, int64_t N, int64_t
     return VTC_ERR_INVALID_ARG;
   if (medr && (!hist_ws || hist_ws_bytes < (3 * 65536 + 8) * sizeof(unsigned int)))
     return VTC_ERR_WORKSPACE;
-  return launch_rank_finalize(rank0, gt_score, N, M_total, k_vals, nk, hits, medr, hist_ws,
-                              (cudaStream_t)stream);
+  if (N == 0 || !hist_ws)  // no scratch: the stand-alone kernels (hit counts only)
+    return launch_rank_finalize(rank0, gt_score, N, M_total, k_vals, nk, hits, medr, hist_ws,
+                                (cudaStream_t)stream);
+  // one cooperative launch: NaN ground truth -> M_total, hit counts, radix-select median
+  RankEpilogueArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.ex.N = N, ea.ex.bf16 = false;
+  ea.dgt = gt_score, ea.rank0 = rank0, ea.accumulate = 1;
+  ea.finalize = 1, ea.M_total = M_total, ea.nk = nk;
+  for (int i = 0; i < nk; ++i) ea.k_vals[i] = k_vals[i];
+  ea.hits = reinterpret_cast<unsigned long long*>(hits), ea.medr = medr;
+  ea.hist = static_cast<unsigned int*>(hist_ws);
+  return launch_rank_epilogue(ea, (cudaStream_t)stream);
 }
 
 int vtc_sim_topk(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype, int metric,

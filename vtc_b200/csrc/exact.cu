@@ -11,6 +11,8 @@
 // Replaces faiss.GpuIndexFlatL2.search + the host loop at model/metric.py:140-160.
 #include "exact.cuh"
 
+#include "exact_dev.cuh"
+
 namespace vtc {
 
 // ------------------------------------------------------------------------------------------------
@@ -83,12 +85,8 @@ __global__ void gt_score_kernel(const T* __restrict__ Q, int64_t ldq, const T* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// brute-force rank: register-tiled fp64 "GEMM" whose accumulators run sequentially in k
+// brute-force rank and re-check of the guard-band column groups (bodies: exact_dev.cuh)
 // ------------------------------------------------------------------------------------------------
-constexpr int BR_T = 64;   // block tile (queries x gallery rows)
-constexpr int BR_K = 16;   // k chunk
-constexpr int BR_PAD = 2;  // doubles of padding per smem row
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 rank_brute_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ G, int64_t ldg,
@@ -97,77 +95,10 @@ rank_brute_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ G,
                   int64_t col_offset, int metric, int* __restrict__ rank,
                   const unsigned int* __restrict__ run_flag) {
   if (run_flag && *run_flag == 0) return;
-  __shared__ double Qs[BR_K][BR_T + BR_PAD];
-  __shared__ double Gs[BR_K][BR_T + BR_PAD];
-  __shared__ int cnt_s[BR_T];
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int64_t q_tiles = ceil_div<int64_t>(N, BR_T), g_tiles = ceil_div<int64_t>(M, BR_T);
-  const int lrow = tid >> 2, lk = (tid & 3) * 4;  // loader mapping: 64 rows x 16 k
-  for (int64_t tile = blockIdx.x; tile < q_tiles * g_tiles; tile += gridDim.x) {
-    // consecutive blocks share the gallery tile (L2 reuse), queries vary fastest
-    const int64_t q0 = (tile % q_tiles) * BR_T, g0 = (tile / q_tiles) * BR_T;
-    double acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    if (tid < BR_T) cnt_s[tid] = 0;
-    for (int k0 = 0; k0 < D; k0 += BR_K) {
-      __syncthreads();
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = k0 + lk + e;
-        const int64_t qr = q0 + lrow, gr = g0 + lrow;
-        Qs[lk + e][lrow] = (qr < N && k < D) ? to_f64(Q[qr * ldq + k]) : 0.0;
-        Gs[lk + e][lrow] = (gr < M && k < D) ? to_f64(G[gr * ldg + k]) : 0.0;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < BR_K; ++kk) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = Qs[kk][ty * 4 + i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Gs[kk][tx * 4 + j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t t = q0 + ty * 4 + i;
-      if (t >= N) continue;
-      const double d0 = dgt[t];
-      const int64_t g = gt ? gt[t] : t + row_offset;
-      int c = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t jl = g0 + tx * 4 + j;
-        if (jl >= M) continue;
-        const int64_t jg = jl + col_offset;
-        if (jg == g) continue;
-        const double d = metric == VTC_METRIC_L2 ? sq64[jl] - 2.0 * acc[i][j] : -acc[i][j];
-        c += (d < d0) || (d == d0 && jg < g);
-      }
-      if (c) atomicAdd(&cnt_s[ty * 4 + i], c);
-    }
-    __syncthreads();
-    if (tid < BR_T && cnt_s[tid] && q0 + tid < N) atomicAdd(&rank[q0 + tid], cnt_s[tid]);
-    __syncthreads();
-  }
+  __shared__ BruteSmem sm;
+  rank_brute_tiles<T>(sm, Q, ldq, G, ldg, sq64, dgt, N, M, D, gt, row_offset, col_offset, metric,
+                      rank, blockIdx.x, gridDim.x);
 }
-
-// ------------------------------------------------------------------------------------------------
-// re-check of the ambiguous column groups emitted by the tensor-core pass
-// ------------------------------------------------------------------------------------------------
-// The list has one segment per CTA of the tensor-core launch; entry (t, j0) means "row t has a
-// score inside the guard band among gallery columns [j0, j0 + 8)": the tensor-core pass added
-// nothing for that group, so all 8 columns are decided here in canonical arithmetic.
-constexpr int RECHECK_GROUP = 8;
-constexpr int RECHECK_PARTS = 4;  // blocks per segment
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -177,26 +108,8 @@ recheck_kernel(const int2* __restrict__ list, const unsigned int* __restrict__ s
                const double* __restrict__ dgt, int64_t N, int64_t M, int D,
                const int64_t* __restrict__ gt, int64_t row_offset, int64_t col_offset, int metric,
                int* __restrict__ rank, unsigned int* __restrict__ overflow) {
-  const int seg = blockIdx.x / RECHECK_PARTS, part = blockIdx.x % RECHECK_PARTS;
-  const unsigned int n = seg_count[seg];
-  if (n > seg_cap) {
-    if (part == 0 && threadIdx.x == 0) *overflow = 1u;
-    return;  // the brute-force fallback recomputes everything
-  }
-  const int2* seg_list = list + (size_t)seg * seg_cap;
-  for (unsigned int u = part * blockDim.x + threadIdx.x; u < n * RECHECK_GROUP;
-       u += RECHECK_PARTS * blockDim.x) {
-    const int2 e = seg_list[u / RECHECK_GROUP];
-    const int64_t t = e.x, jl = (int64_t)e.y + (u % RECHECK_GROUP);
-    if (t >= N || jl >= M) continue;  // zero-padded tile rows / columns
-    const int64_t g = gt ? gt[t] : t + row_offset;
-    const int64_t jg = jl + col_offset;
-    if (jg == g) continue;
-    const double acc = dot_seq64(Q + t * ldq, G + jl * ldg, D);
-    const double d = metric == VTC_METRIC_L2 ? sq64[jl] - 2.0 * acc : -acc;
-    const double d0 = dgt[t];
-    if ((d < d0) || (d == d0 && jg < g)) atomicAdd(&rank[t], 1);
-  }
+  recheck_part<T>(blockIdx.x, list, seg_count, seg_cap, Q, ldq, G, ldg, sq64, dgt, N, M, D, gt,
+                  row_offset, col_offset, metric, rank, overflow);
 }
 
 // dst[j] = j < M ? (src ? src[j] : 0) : pad   for j in [0, Mpad)   (in place allowed)

@@ -13,9 +13,6 @@ namespace tc {
 
 int launch_rank(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
-int launch_rank_fold(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                     const CUtensorMap& tmAx, const CUtensorMap& tmBx, const Params& p, int grid,
-                     cudaStream_t s);
 int launch_topk(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
 int launch_lse(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
@@ -99,6 +96,31 @@ static bool use_pair(int num_kb) {
   return num_kb > 8 || num_kb <= 4;
 }
 
+// VTC_DBG_PROF=1 (profiling only): a small device buffer the kernel's MMA issuer and first epilogue
+// warp write their wait counters to; allocated once, on first use.  The library allocates nothing
+// otherwise.
+constexpr int kProfWords = 256 * 8;
+static unsigned long long* dbg_prof_buffer() {
+  static unsigned long long* buf = []() -> unsigned long long* {
+    const char* e = getenv("VTC_DBG_PROF");
+    if (!e || !*e || atoi(e) == 0) return nullptr;
+    unsigned long long* p = nullptr;
+    if (cudaMalloc(&p, kProfWords * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, kProfWords * sizeof(unsigned long long));
+    return p;
+  }();
+  return buf;
+}
+int debug_prof_read(unsigned long long* out, int max_words) {
+  unsigned long long* buf = dbg_prof_buffer();
+  if (!buf || !out || max_words <= 0) return VTC_ERR_INVALID_ARG;
+  const int n = max_words < kProfWords ? max_words : kProfWords;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, buf, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(buf, 0, kProfWords * sizeof(unsigned long long));
+  return cuda_err(e);
+}
+
 Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split) {
   Plan pl;
   pl.cluster = cluster < 1 ? 1 : cluster;
@@ -108,6 +130,7 @@ Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split)
     return e && *e ? atoi(e) : 0;
   }();
   p.dbg_skip_epilogue = skip_epi;
+  p.dbg_prof = dbg_prof_buffer();
   p.q_tiles = (int)ceil_div<int64_t>(p.N, BM);
   p.g_tiles = (int)ceil_div<int64_t>(p.M, BN);
   const int units = pl.cluster > 1 ? active_clusters(pl.cluster) : kNumSMs;  // co-resident clusters
@@ -172,8 +195,7 @@ int kernel_timer_read(double* total_ms, int* count) {
 }
 
 int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorMap& tmA,
-                  const CUtensorMap& tmB, const Params& p, cudaStream_t s, const CUtensorMap* tmAx,
-                  const CUtensorMap* tmBx) {
+                  const CUtensorMap& tmB, const Params& p, cudaStream_t s) {
   if (pl.grid <= 0) return VTC_OK;
   if (a_resident && p.num_kb > 8) return VTC_ERR_UNSUPPORTED_SHAPE;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -190,11 +212,6 @@ int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorM
   int rc;
   switch (epilogue) {
     case EPI_RANK: rc = launch_rank(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
-    case EPI_RANK_FOLD:
-      rc = (pl.cluster == 2 && pl.pair && tmAx && tmBx)
-               ? launch_rank_fold(a_resident, tmA, tmB, *tmAx, *tmBx, p, pl.grid, s)
-               : VTC_ERR_INVALID_ARG;
-      break;
     case EPI_TOPK: rc = launch_topk(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
     case EPI_LSE:
       rc = pl.cluster == 1 ? launch_lse(a_resident, tmA, tmB, p, pl.grid, s) : VTC_ERR_INVALID_ARG;

@@ -11,7 +11,7 @@ constexpr int BM = 128;  // query rows per CTA tile  (UMMA M, TMEM lanes)
 constexpr int BN = 256;  // gallery rows per tile    (UMMA N, TMEM columns per accumulator stage)
 constexpr int BK = 64;   // bf16 per k-block = one 128-byte swizzle atom
 
-enum Epilogue { EPI_RANK = 0, EPI_LSE = 1, EPI_STORE = 2, EPI_TOPK = 3, EPI_RANK_FOLD = 4 };
+enum Epilogue { EPI_RANK = 0, EPI_LSE = 1, EPI_STORE = 2, EPI_TOPK = 3 };
 
 constexpr int TOPK_POOL = 64;  // buffer entries per (row, gallery split)
 constexpr int TOPK_KEEP_MAX = 32;  // entries kept when a buffer is compacted: 16 for k <= 12, else 32
@@ -27,8 +27,13 @@ struct Params {
   const float* col_bias;
   const float* scale_ptr;  // optional device scalar multiplied into `scale`
   float scale;
-  // EPI_RANK
-  const float2* thr;  // [N] (lo, hi) guard band around d(t, gt)
+  // EPI_RANK: the guard band (lo, hi) around d(t, gt) is derived per work item from the canonical
+  // ground-truth score, an upper bound of ||q_t||^2 and the largest gallery norm (rank_band())
+  const double* dgt;                 // [N] canonical d(t, gt); NaN = no ground truth in this call
+  const float* qq;                   // [N] upper bound of ||q_t||^2
+  const unsigned int* max_sq_bits;   // float bits of max_j ||x_j||^2 over the finite gallery rows
+  float guard_rel;                   // bound of |tensor-core dot - exact dot| / (|q||x|)
+  int metric_l2;                     // 1: score = ||x||^2 - 2 q.x, 0: score = -q.x
   int* rank;          // [N] += #{j : score < lo}
   int2* amb_list;     // (t, j0): row t has a score in [lo, hi] among columns [j0, j0 + 8);
                       // one segment of amb_seg_cap entries per CTA
@@ -57,12 +62,10 @@ struct Params {
   int topk_keep;      // entries kept by a compaction (>= k, <= TOPK_KEEP_MAX)
   const float* tau_init;  // optional [N]: initial per-row threshold (from a sample pass); NULL = +inf
   int dbg_skip_epilogue;  // profiling only (VTC_DBG_SKIP_EPILOGUE=1): drain TMEM but reduce nothing
-  // EPI_RANK_FOLD (new fields go at the END: the other kernels' parameter offsets stay put).
-  // The per-column bias and the per-row ground-truth score ride in one extra K16 step of the MMA
-  // (operands tmAx / tmBx), so the accumulator IS acc' = q.x - ||x||^2/2 + d(t,gt)/2 and a column
-  // is closer than the ground truth iff acc' > 0; fold_w[t] is the half-width of the guard band
-  // around 0 (negative: the row never pushes).
-  const float* fold_w;
+  // profiling only (VTC_DBG_PROF=1): per CTA 8 x u64 {clock64 ticks, globaltimer ns, MMA-issuer
+  // ticks waiting for a free accumulator (epilogue-bound), ticks waiting for operand stages
+  // (load-bound), tiles, epilogue-warp ticks waiting for a full accumulator, ...}
+  unsigned long long* dbg_prof;
 };
 
 // Row-major bf16 [rows, cols] with leading dimension ld (elements) -> 2-D TMA descriptor with a
@@ -83,15 +86,37 @@ Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split 
 
 // a_resident: keep the whole 128 x K' query tile in shared memory (needs num_kb <= 8).
 // tmB must have been built with box_rows = BN / pl.cluster.
-// EPI_RANK_FOLD additionally takes the tensor maps of the [rows, 64] bf16 fold operands (tmBx with
-// box_rows = BN / 2: it always runs as a CTA pair).
 int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorMap& tmA,
-                  const CUtensorMap& tmB, const Params& p, cudaStream_t s,
-                  const CUtensorMap* tmAx = nullptr, const CUtensorMap* tmBx = nullptr);
+                  const CUtensorMap& tmB, const Params& p, cudaStream_t s);
 
 // opt-in CUDA-event timing of the tensor-core launches (bench.py roofline)
 void kernel_timer_enable(bool on);
 int kernel_timer_read(double* total_ms, int* count);
+// VTC_DBG_PROF=1: copies the per-CTA profile words of the LAST launch to the host (synchronises)
+int debug_prof_read(unsigned long long* out, int max_words);
+
+// The guard band of the rank epilogue: every tensor-core score of query t is within delta of the
+// canonical one (DESIGN.md "guard band"), so a column is certainly closer than the ground truth
+// below lo = d(t,gt) - delta and certainly not above hi = d(t,gt) + delta.
+//   dot error <= guard_rel * |q| * max|x|;  L2: d = sq32 - 2 acc in fp32 adds the roundings of sq32
+//   and of the FMA.  qq is an upper bound of |q|^2, gmax_sq the largest finite gallery norm^2.
+__host__ __device__ inline void rank_band(double d0, double qq, double gmax_sq, int metric_l2,
+                                          float guard_rel, float* lo, float* hi) {
+  const double qn = sqrt(qq), gn = sqrt(gmax_sq);
+  double delta;
+  if (metric_l2)
+    delta = 2.0 * guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn);
+  else
+    delta = (double)guard_rel * qn * gn + 1.2e-7 * qn * gn;
+#ifdef __CUDA_ARCH__
+  *lo = __double2float_rd(d0 - delta);
+  *hi = __double2float_ru(d0 + delta);
+#else
+  *lo = (float)(d0 - delta);
+  *hi = (float)(d0 + delta);
+#endif
+  if (!(qq == qq) || !(d0 == d0)) *lo = *hi = nanf("");
+}
 
 }  // namespace tc
 }  // namespace vtc

@@ -48,14 +48,11 @@ constexpr int TMEM_COLS = 512;
 
 // kPair: the two CTAs of a cluster issue one M256 cta_group::2 MMA; each CTA stages only ITS half
 // of every gallery tile (16 KB), so the ring is twice as deep in the same shared memory.
-// kFold: one more k-block per tile (the fold operands, see RankFoldEpi): the resident query tile
-// grows to 9 blocks (144 KB) and the ring of a resident pair kernel shrinks to 5 stages.
-template <bool kRes, bool kPair = false, bool kFold = false>
+template <bool kRes, bool kPair = false>
 struct SmemLayout {
-  static_assert(!kFold || kPair, "the fold kernel runs as a CTA pair");
-  static constexpr int kResKb = kFold ? MAX_RES_KB + 1 : MAX_RES_KB;
+  static constexpr int kResKb = MAX_RES_KB;
   static constexpr int kBBytes = kPair ? B_TILE_BYTES / 2 : B_TILE_BYTES;
-  static constexpr int kStages = kPair ? ((kFold && kRes) ? 5 : 6) : (kRes ? 3 : 4);
+  static constexpr int kStages = kPair ? 6 : (kRes ? 3 : 4);
   static constexpr int kStageBytes = kRes ? kBBytes : (A_TILE_BYTES + kBBytes);
   static constexpr int kResBytes = kRes ? kResKb * A_TILE_BYTES : 0;
   static constexpr int kStagesOff = kResBytes;
@@ -90,7 +87,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 constexpr int RANK_GROUP = 8;  // columns re-checked together when any of them is in the guard band
 
 struct RankEpi {
-  static constexpr bool kFold = false;
   float lo, hi;
   int cnt;
   int gtc;  // ground-truth column of this row (launch-local), or a value no group can contain
@@ -101,12 +97,16 @@ struct RankEpi {
     lo = hi = nanf("");
     gtc = INT_MIN / 2;
     if (t < p.N) {
-      const float2 th = p.thr[t];
-      lo = th.x;
-      hi = th.y;
+      band(p.dgt[t], p.qq[t], p.max_sq_bits, p.metric_l2, p.guard_rel, &lo, &hi);
       const int64_t g = (p.gt ? p.gt[t] : t + p.gt_row_offset) - p.gt_col_offset;
       if (g >= 0 && g < p.M) gtc = (int)g;
     }
+  }
+  // once per row and work item (dozens of tiles): out of line, so that the double-precision square
+  // roots stay out of the instruction-cache footprint of the per-column loop
+  static __device__ __noinline__ void band(double d0, float qq, const unsigned int* max_sq_bits,
+                                           int metric_l2, float guard_rel, float* lo, float* hi) {
+    rank_band(d0, (double)qq, (double)__uint_as_float(*max_sq_bits), metric_l2, guard_rel, lo, hi);
   }
   // rare: this row has a score inside the guard band among columns [j, j+8): hand the whole group
   // to the fp64 re-check (its definite count is NOT added here).  List segments are per CTA, slots
@@ -163,102 +163,7 @@ struct RankEpi {
   }
 };
 
-// RankEpi with the per-column bias and the per-row ground-truth score FOLDED INTO THE MMA
-// (EPI_RANK_FOLD; opt-in, VTC_RANK_FOLD=1).  One extra K16 step per tile multiplies the fold
-// operands
-//     Qx[t] = [ m'_t in three bf16 pieces | 1 1 1 | 0 ... ]
-//     Gx[j] = [ 1 1 1 | h_j in three bf16 pieces | 0 ... ]
-// (m'_t = d(t,gt)/2, h_j = -||x_j||^2/2 for L2; m'_t = d(t,gt), h_j = 0 for DOT; fold.cu), so the
-// accumulator is acc' = q.x + h_j + m'_t and "column j is closer than the ground truth" is
-// acc' > 0.  Per logit the epilogue is then one sign-bit add (LEA.HI) and half a three-input
-// |min| (FMNMX3) instead of FFMA + 2 FSET + 2 FADD + the bias staging: a group of 8 columns is
-// counted by its sign bits unless min |acc'| <= w_t (the guard band, now around 0), in which case
-// it takes the same rare path as RankEpi.  Padding columns carry h = -1e30 (never closer, never in
-// the band), padding rows and NaN rows w = -1 (never push).
-struct RankFoldEpi {
-  static constexpr bool kFold = true;
-  float w;
-  int cnt;
-  int gtc;
-  int64_t t;
-  __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int) {
-    t = t_;
-    cnt = 0;
-    w = -1.f;
-    gtc = INT_MIN / 2;
-    if (t < p.N) {
-      w = p.fold_w[t];
-      const int64_t g = (p.gt ? p.gt[t] : t + p.gt_row_offset) - p.gt_col_offset;
-      if (g >= 0 && g < p.M) gtc = (int)g;
-    }
-  }
-  // rare: some |acc'| of the group is inside the band.  If the only such column is the ground
-  // truth itself the group is decided (that column is excluded from the count by index); else the
-  // whole group goes to the fp64 re-check and contributes nothing here.
-  static __device__ __noinline__ int slow_group(int2* __restrict__ seg_list, unsigned int seg_cap,
-                                                unsigned int* seg_count, int t, int j0, int gtc,
-                                                float w, uint4 xa, uint4 xb) {
-    const uint32_t x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-    const unsigned int gi = (unsigned int)(gtc - j0);
-    int in_band = 0, pos_others = 0;
-    bool gt_in_band = false;
-#pragma unroll
-    for (int i = 0; i < RANK_GROUP; ++i) {
-      const bool ib = fabsf(__uint_as_float(x[i])) <= w;
-      in_band += ib ? 1 : 0;
-      if ((unsigned int)i == gi)
-        gt_in_band = ib;
-      else
-        pos_others += (int)((x[i] >> 31) ^ 1u);
-    }
-    if (in_band == 1 && gt_in_band) return pos_others;
-    const unsigned int slot = atomicAdd(seg_count, 1u);
-    if (slot < seg_cap) seg_list[slot] = make_int2(t, j0);
-    return 0;
-  }
-  __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32], const float*,
-                                        float, int64_t jbase, unsigned int* seg_count) {
-    // per group of 8 columns: min |acc'| (three-input minima) and the number of negative
-    // accumulators (sign-bit adds); the four groups are independent dependency chains
-    constexpr int G = 32 / RANK_GROUP;
-    float mn[G];
-    unsigned int neg[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const uint32_t* x = v + RANK_GROUP * g;
-      float m = fminf(fminf(fabsf(__uint_as_float(x[0])), fabsf(__uint_as_float(x[1]))),
-                      fabsf(__uint_as_float(x[2])));
-      m = fminf(fminf(m, fabsf(__uint_as_float(x[3]))), fabsf(__uint_as_float(x[4])));
-      m = fminf(fminf(m, fabsf(__uint_as_float(x[5]))), fabsf(__uint_as_float(x[6])));
-      mn[g] = fminf(m, fabsf(__uint_as_float(x[7])));
-      unsigned int n = x[0] >> 31;
-#pragma unroll
-      for (int i = 1; i < RANK_GROUP; ++i) n += x[i] >> 31;
-      neg[g] = n;
-    }
-    const float mall = fminf(fminf(fminf(mn[0], mn[1]), mn[2]), mn[3]);
-    if (mall > w) {  // the common case: nothing of these 32 columns is near the ground truth
-      cnt += 32 - (int)((neg[0] + neg[1]) + (neg[2] + neg[3]));
-    } else {
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const uint32_t* x = v + RANK_GROUP * g;
-        if (mn[g] <= w)
-          cnt += slow_group(p.amb_list + (size_t)blockIdx.x * p.amb_seg_cap, p.amb_seg_cap,
-                            seg_count, (int)t, (int)jbase + RANK_GROUP * g, gtc, w,
-                            make_uint4(x[0], x[1], x[2], x[3]), make_uint4(x[4], x[5], x[6], x[7]));
-        else
-          cnt += RANK_GROUP - (int)neg[g];
-      }
-    }
-  }
-  __device__ __forceinline__ void end_item(const Params& p, int) {
-    if (t < p.N && cnt) atomicAdd(&p.rank[t], cnt);
-  }
-};
-
 struct LseEpi {
-  static constexpr bool kFold = false;
   float m, l, dv;
   int64_t t, jd;
   __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int) {
@@ -306,7 +211,6 @@ struct LseEpi {
 };
 
 struct StoreEpi {
-  static constexpr bool kFold = false;
   int64_t t;
   __device__ __forceinline__ void begin_item(const Params&, int64_t t_, int) { t = t_; }
   // 8 floats -> 8 bf16 (RN) packed in a uint4; with `lo` the residuals x - bf16(x) instead
@@ -409,7 +313,6 @@ struct StoreEpi {
 // score >= tau, which is what topk_select_kernel's completeness proof needs.  A row compacts only
 // O(log(M / 64)) times, so the per-column cost stays at one FFMA + one compare.
 struct TopkEpi {
-  static constexpr bool kFold = false;
   float tau;
   int cnt;
   int64_t t;
@@ -516,15 +419,9 @@ struct TopkEpi {
 template <typename Epi, bool kRes, int kC, bool kPair = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const Params p, const __grid_constant__ CUtensorMap tmAx,
-              const __grid_constant__ CUtensorMap tmBx) {
+              const Params p) {
   static_assert(!kPair || kC == 2, "a CTA pair is a cluster of two");
-  // kFold: every tile gets one more k-block, read through tmAx / tmBx (the fold operands of
-  // RankFoldEpi; [rows, 64] bf16, only their first 16 columns are multiplied).  The maps trail the
-  // other parameters and are not referenced otherwise.
-  constexpr bool kFold = Epi::kFold;
-  static_assert(!kFold || kPair, "the fold kernel runs as a CTA pair");
-  using L = SmemLayout<kRes, kPair, kFold>;
+  using L = SmemLayout<kRes, kPair>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* res_a = smem;
   uint8_t* stages = smem + L::kStagesOff;
@@ -546,10 +443,6 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
-    if (kFold) {
-      prefetch_tensormap(&tmAx);
-      prefetch_tensormap(&tmBx);
-    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < L::kStages; ++i) {
@@ -589,8 +482,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int num_clusters = gridDim.x / kC;
   const int q_groups = (p.q_tiles + kC - 1) / kC;
   const int num_items = q_groups * p.g_splits;
-  const int num_kb = p.num_kb;
-  const int nkb = num_kb + (kFold ? 1 : 0);  // k-blocks per tile incl. the fold block (the last)
+  const int nkb = p.num_kb;
   constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
   // CTA pair: rank 0 issues the MMAs and owns the `full` / `a_full` / `tmem_empty` barriers; both
   // CTAs' TMA loads and epilogue warps signal ITS barriers (shared::cluster addresses)
@@ -610,24 +502,18 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (kPair) {
               // each CTA loads its own query rows and its half of the gallery tile into its own
               // shared memory; the bytes of both are expected on the leader's barrier
-              // (the fold block is column 0 of tmAx / tmBx; FOLD_COL is spelled out at every use so
-              // that the kernels without a fold block compile to the code they had before)
-#define VTC_FOLD_KB (kFold && kb == num_kb)
-#define VTC_FOLD_COL (VTC_FOLD_KB ? 0 : kb * BK)
               if (kRes && tile == t0) {
                 if (leader) mbar_arrive_expect_tx(&a_full[kb], 2 * A_TILE_BYTES);
-                tma_load_2d_pair(res_a + kb * A_TILE_BYTES, VTC_FOLD_KB ? &tmAx : &tmA,
-                                 mapa_shared(smem_u32(&a_full[kb]), 0), VTC_FOLD_COL, qt * BM);
+                tma_load_2d_pair(res_a + kb * A_TILE_BYTES, &tmA,
+                                 mapa_shared(smem_u32(&a_full[kb]), 0), kb * BK, qt * BM);
               }
               mbar_wait(&empty[stage], phase ^ 1);
               if (leader) mbar_arrive_expect_tx(&full[stage], 2 * L::kStageBytes);
               const uint32_t fbar = mapa_shared(smem_u32(&full[stage]), 0);
               uint8_t* st = stages + stage * L::kStageBytes;
-              if (!kRes) tma_load_2d_pair(st, VTC_FOLD_KB ? &tmAx : &tmA, fbar, VTC_FOLD_COL, qt * BM);
-              tma_load_2d_pair(st + (kRes ? 0 : A_TILE_BYTES), VTC_FOLD_KB ? &tmBx : &tmB, fbar,
-                               VTC_FOLD_COL, tile * BN + cta_rank * (BN / 2));
-#undef VTC_FOLD_COL
-#undef VTC_FOLD_KB
+              if (!kRes) tma_load_2d_pair(st, &tmA, fbar, kb * BK, qt * BM);
+              tma_load_2d_pair(st + (kRes ? 0 : A_TILE_BYTES), &tmB, fbar, kb * BK,
+                               tile * BN + cta_rank * (BN / 2));
               if (++stage == L::kStages) stage = 0, phase ^= 1;
               continue;
             }
@@ -657,17 +543,35 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(kPair ? 2 * BM : BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, it = 0;
+      // VTC_DBG_PROF: where the issuer waits (one thread; two clock reads per wait when enabled)
+      const bool prof = p.dbg_prof != nullptr;
+      unsigned long long w_acc = 0, w_ld = 0, n_tiles = 0;
+      const long long c_begin = prof ? clock64() : 0;
+      const uint64_t g_begin = prof ? globaltimer_ns() : 0;
       for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
         const int split = item / q_groups;
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
         for (int tile = t0; tile < t1; ++tile) {
-          mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
+          if (prof) {
+            const long long c0 = clock64();
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            w_acc += (unsigned long long)(clock64() - c0);
+            ++n_tiles;
+          } else {
+            mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
+          }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BN;
           for (int kb = 0; kb < nkb; ++kb) {
             if (kRes && tile == t0) mbar_wait(&a_full[kb], it & 1);
-            mbar_wait(&full[stage], phase);
+            if (prof) {
+              const long long c0 = clock64();
+              mbar_wait(&full[stage], phase);
+              w_ld += (unsigned long long)(clock64() - c0);
+            } else {
+              mbar_wait(&full[stage], phase);
+            }
             tc_fence_after();
             uint8_t* st = stages + stage * L::kStageBytes;
             const uint64_t adesc =
@@ -675,7 +579,6 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(st + (kRes ? 0 : A_TILE_BYTES)));
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
-              if (kFold && kb == num_kb && k4 > 0) break;  // the fold block is one K16 step wide
               if (kPair)
                 umma_bf16_pair(d_tmem, desc_advance(adesc, k4 * 32), desc_advance(bdesc, k4 * 32),
                                idesc, (uint32_t)((kb | k4) != 0));
@@ -707,6 +610,14 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             umma_commit(a_empty);
         }
       }
+      if (prof) {
+        unsigned long long* o = p.dbg_prof + (size_t)blockIdx.x * 8;
+        o[0] = (unsigned long long)(clock64() - c_begin);
+        o[1] = globaltimer_ns() - g_begin;
+        o[2] = w_acc;
+        o[3] = w_ld;
+        o[4] = n_tiles;
+      }
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------------ epilogue
@@ -726,11 +637,14 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // column bias, staged 64 columns at a time in this warp's private buffer; lanes 0..15 carry the
     // next 64 values in registers (prefetched one step ahead so the L2 latency is never exposed)
     float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!kFold && cluster_id < num_items && lane < 16)
+    if (cluster_id < num_items && lane < 16)
       bias_pre = __ldg(reinterpret_cast<const float4*>(
                            p.col_bias + (int64_t)(cluster_id / q_groups) * p.tiles_per_split * BN +
                            half * kHalfCols) +
                        lane);
+    const bool eprof = p.dbg_prof != nullptr;
+    unsigned long long e_wait = 0;
+    const long long e_begin = eprof ? clock64() : 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int qt = (item % q_groups) * kC + cta_rank, split = item / q_groups;
       const int t0 = split * p.tiles_per_split;
@@ -746,7 +660,13 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         ? (int64_t)(nitem / q_groups) * p.tiles_per_split * BN + half * kHalfCols
                         : 0;
         }
-        mbar_wait(&tmem_full[as], aphase);
+        if (eprof) {
+          const long long c0 = clock64();
+          mbar_wait(&tmem_full[as], aphase);
+          e_wait += (unsigned long long)(clock64() - c0);
+        } else {
+          mbar_wait(&tmem_full[as], aphase);
+        }
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_off + as * BN + half * kHalfCols;
         uint32_t va[32], vb[32];
@@ -755,15 +675,12 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll 1
         for (int c = 0; c < kHalfCols / 32; c += 2) {
           // stage the bias of columns [32c, 32c + 64) and start fetching the following 64
-          // (the fold epilogue has no per-column bias: it is inside the accumulator)
-          if (!kFold) {
-            __syncwarp();
-            if (lane < 16) reinterpret_cast<float4*>(wbias)[lane] = bias_pre;
-            __syncwarp();
-            if (lane < 16) {
-              const int64_t nj = c == 0 ? j0 + 64 : next_j0;
-              bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + nj) + lane);
-            }
+          __syncwarp();
+          if (lane < 16) reinterpret_cast<float4*>(wbias)[lane] = bias_pre;
+          __syncwarp();
+          if (lane < 16) {
+            const int64_t nj = c == 0 ? j0 + 64 : next_j0;
+            bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + nj) + lane);
           }
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
           if (!p.dbg_skip_epilogue) epi.chunk(p, va, wbias, scale, j0 + c * 32, seg_count);
@@ -790,6 +707,10 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       epi.end_item(p, 2 * split + half);
     }
+    if (eprof && warp == EPI_WARP0 && lane == 0) {
+      p.dbg_prof[(size_t)blockIdx.x * 8 + 5] = e_wait;
+      p.dbg_prof[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - e_begin);
+    }
   }
 
   tc_fence_before();
@@ -810,10 +731,8 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // Launches one instance with a thread-block-cluster dimension of kC (1 = plain launch).
 template <typename Epi, bool kRes, int kC, bool kPair = false>
 int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid,
-                    cudaStream_t s, const CUtensorMap* tmAx = nullptr,
-                    const CUtensorMap* tmBx = nullptr) {
-  using L = SmemLayout<kRes, kPair, Epi::kFold>;
-  if (Epi::kFold && (!tmAx || !tmBx)) return VTC_ERR_INVALID_ARG;
+                    cudaStream_t s) {
+  using L = SmemLayout<kRes, kPair>;
   auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair>;
   // the attribute is per function and per device: cheap, so set it on every launch
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -831,8 +750,7 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = kC > 1 ? 1 : 0;
-  // kernels without a fold block never touch the two trailing maps
-  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, tmAx ? *tmAx : tmA, tmBx ? *tmBx : tmB);
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
   if (e != cudaSuccess) return cuda_err(e);
   return VTC_OK;
 }
@@ -840,7 +758,7 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params
 // how many clusters of kC CTAs of this kernel can be co-resident on the current device
 template <typename Epi, bool kRes, int kC, bool kPair = false>
 int max_active_clusters() {
-  using L = SmemLayout<kRes, kPair, Epi::kFold>;
+  using L = SmemLayout<kRes, kPair>;
   auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess)
     return 0;

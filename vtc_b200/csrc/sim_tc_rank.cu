@@ -1,6 +1,5 @@
 // sim_tc_rank.cu -- instantiates the similarity GEMM with the RankEpi epilogue for every
-// (resident query tile, cluster size) combination, and with RankFoldEpi (bias and ground-truth
-// score folded into the MMA; always a CTA pair).  See sim_tc_kernel.cuh.
+// (resident query tile, cluster size) combination.  See sim_tc_kernel.cuh.
 #include "sim_tc_kernel.cuh"
 
 namespace vtc {
@@ -9,13 +8,6 @@ namespace tc {
 int launch_rank(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                  const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s) {
   return launch_epilogue<RankEpi>(a_resident, cluster, tmA, tmB, p, grid, s, pair);
-}
-
-int launch_rank_fold(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                     const CUtensorMap& tmAx, const CUtensorMap& tmBx, const Params& p, int grid,
-                     cudaStream_t s) {
-  return a_resident ? launch_instance<RankFoldEpi, true, 2, true>(tmA, tmB, p, grid, s, &tmAx, &tmBx)
-                    : launch_instance<RankFoldEpi, false, 2, true>(tmA, tmB, p, grid, s, &tmAx, &tmBx);
 }
 
 int max_active_clusters_rank(int cluster) {

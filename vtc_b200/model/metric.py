@@ -229,9 +229,11 @@ class RecallAtK(BaseMetric):
         b = _to_device(features_b, device)
         if a.dtype != b.dtype:
             a, b = a.float(), b.float()
-        rank0, gt_score = ops.sim_rank(b, a, metric=self.metric, precision=self.precision)
-        hits, medr = ops.rank_finalize(rank0, gt_score, num_samples, self.k_vals)
-        return {"rank0": rank0, "hits": hits, "medr": medr, "num_samples": num_samples}
+        # one library call: row prologue + tensor-core pass + cooperative epilogue (re-check, hit
+        # counts, median)
+        full = ops.rank_eval(b, a, self.k_vals, metric=self.metric, precision=self.precision)
+        return {"rank0": full["rank0"], "hits": full["hits"], "medr": full["medr"],
+                "num_samples": num_samples}
 
     # Host inputs of at least this many bytes are staged in chunks on a copy stream so that the
     # host->device transfer overlaps the ranking.  When BOTH sides come from the host, gallery and
@@ -242,39 +244,17 @@ class RecallAtK(BaseMetric):
     # transfer instead of after the whole gallery, with 2c - 1 library calls.
     PIPELINE_MIN_BYTES = 32 << 20
     PIPELINE_CHUNKS = 4      # query chunks against a device-resident gallery
-    # chunks per side when both sides are staged from the host
-    PIPELINE_CHUNKS_2D = int(os.environ.get("VTC_PIPELINE_CHUNKS_2D", "6"))
+    # Chunk pairs when both sides are staged from the host.  Once the last pair has landed, the
+    # blocks it enables -- (2 r_last N - r_last^2) of the N^2 pairs for r_last rows -- are all that is
+    # left, so the evaluation cannot end before T + that share of the ranking time W: equal chunks
+    # give (2c - 1) / c^2 (c = 6: 0.31 W, c = 12: 0.16 W), and every call is memset + 3 kernels
+    # (rank_stage.cu), so a dozen pairs are affordable.
+    PIPELINE_CHUNKS_2D = 10
 
     @staticmethod
     def _pipeline_bounds_2d(n: int, c: int) -> List[int]:
-        """Row bounds of the c interleaved chunk pairs.  Default: equal chunks.
-
-        VTC_PIPELINE_SCHEDULE=balanced (opt-in until timed on the box): when pair i has landed, a
-        fraction f_i of the transfer (time f_i * T) is over and only the f_{i-1}^2 of the pairs
-        that were rankable before it can be done, so the evaluation ends no earlier than
-        max_i [f_i * T + (1 - f_{i-1}^2) * W] (T transfer, W ranking time; T ~ W at 100k x 100k x
-        512 over PCIe 5).  Equal chunks peak in the middle (c = 6: 1.42 T); the schedule
-        f_i = m + f_{i-1}^2 with the smallest m that reaches 1 in c steps levels every term
-        (c = 6: m = 0.35, 1.35 T) with the same 2c - 1 library calls."""
-        if os.environ.get("VTC_PIPELINE_SCHEDULE", "equal") != "balanced" or c < 3:
-            return [n * i // c for i in range(c + 1)]
-
-        def reach(m: float) -> float:
-            f = 0.0
-            for _ in range(c):
-                f = m + f * f
-            return f
-
-        lo, hi = 0.0, 1.0
-        for _ in range(50):  # bisection on m: reach(m) is increasing
-            mid = 0.5 * (lo + hi)
-            lo, hi = (lo, mid) if reach(mid) >= 1.0 else (mid, hi)
-        fr, f = [0.0], 0.0
-        for _ in range(c):
-            f = min(1.0, hi + f * f)
-            fr.append(f)
-        fr[-1] = 1.0
-        return [min(n, int(round(n * x))) for x in fr]
+        """Row bounds of the c interleaved chunk pairs (equal chunks)."""
+        return [n * i // c for i in range(c + 1)]
 
     def _compute_full_pipelined(self, features_a: ArrayLike, features_b: ArrayLike,
                                 device: torch.device) -> Dict[str, object]:
@@ -348,36 +328,32 @@ class RecallAtK(BaseMetric):
                 ev = torch.cuda.Event()
                 ev.record(copy)
                 events.append(ev)
-        # VTC_RANK_PREPARED=1 (opt-in until timed on the box): norms and ground-truth scores are
-        # computed once per chunk as it lands and handed to every call that touches the chunk
-        # (vtc_sim_rank_prepared), instead of each of the 2c - 1 calls re-walking all its rows
-        prepared = (os.environ.get("VTC_RANK_PREPARED", "0") not in ("", "0")
-                    and (self.precision == "bf16") == (dq.dtype == torch.bfloat16)
-                    and self.precision in ("bf16", "exact"))
-        if prepared:
-            sq64 = torch.empty(n, dtype=torch.float64, device=device)
-            qq = torch.empty(n, dtype=torch.float32, device=device)
+        # per-row quantities are computed once, by the first call that sees the rows, and handed to
+        # every later call that touches them (vtc_sim_rank_prepared): canonical ||x||^2 per gallery
+        # row, the ||q||^2 bound and d(t,gt) per query row -- no call re-walks rows it was given
+        cached = self.precision in ("bf16", "exact")
+        sq64 = torch.empty(n, dtype=torch.float64, device=device) if cached else None
+        qq = torch.empty(n, dtype=torch.float32, device=device) if cached else None
         for (s, e), ev in zip(zip(bounds[:-1], bounds[1:]), events):
             if e == s:
                 continue
             main.wait_event(ev)
-            if prepared:
-                ops.rank_prepare(dg[s:e], self.precision, want_qq=False, sq64_out=sq64[s:e])
-                ops.rank_prepare(dq[s:e], self.precision, want_sq64=False, qq_out=qq[s:e])
-                gt_score[s:e] = ops.gt_scores(dq[s:e], dg[s:e], None, s, s, self.metric, self.precision)
-                ops.sim_rank(dq[s:e], dg[:e], row_offset=s, metric=self.metric,
-                             precision=self.precision, gt_score=gt_score[s:e], rank0=rank0[s:e],
-                             accumulate=False, sq64=sq64[:e], qq=qq[s:e])
+            if cached:
+                # the earlier rows against the new gallery rows (computes the new rows' norms) ...
                 if s > 0:
                     ops.sim_rank(dq[:s], dg[s:e], row_offset=0, col_offset=s, metric=self.metric,
                                  precision=self.precision, gt_score=gt_score[:s], rank0=rank0[:s],
-                                 accumulate=True, sq64=sq64[s:e], qq=qq[:s])
+                                 accumulate=True, sq64_out=sq64[s:e], qq=qq[:s])
+                # ... and the new rows against everything that has arrived (their ground truth is
+                # among it: computes their d(t,gt) and norm bounds)
+                ops.sim_rank(dq[s:e], dg[:e], row_offset=s, metric=self.metric,
+                             precision=self.precision, gt_score_out=gt_score[s:e], rank0=rank0[s:e],
+                             accumulate=False, qq_out=qq[s:e],
+                             **({"sq64": sq64[:e]} if s > 0 else {"sq64_out": sq64[:e]}))
                 continue
-            # new rows against everything that has arrived (their ground truth is among it) ...
             _, g = ops.sim_rank(dq[s:e], dg[:e], row_offset=s, metric=self.metric,
                                 precision=self.precision, rank0=rank0[s:e], accumulate=False)
             gt_score[s:e] = g
-            # ... and the earlier rows against the new gallery rows
             if s > 0:
                 ops.sim_rank(dq[:s], dg[s:e], row_offset=0, col_offset=s, metric=self.metric,
                              precision=self.precision, gt_score=gt_score[:s], rank0=rank0[:s],

@@ -211,7 +211,9 @@ def sim_rank(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None
              row_offset: int = 0, col_offset: int = 0, metric="l2", precision="exact",
              gt_score: Optional[torch.Tensor] = None, rank0: Optional[torch.Tensor] = None,
              accumulate: bool = False, sq64: Optional[torch.Tensor] = None,
-             qq: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+             qq: Optional[torch.Tensor] = None, sq64_out: Optional[torch.Tensor] = None,
+             qq_out: Optional[torch.Tensor] = None, gt_score_out: Optional[torch.Tensor] = None
+             ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused similarity + rank of ground truth: replaces faiss GpuIndexFlatL2.add/search + the Python
     hit loop of RecallAtK.compute (model/metric.py:140-160).  Returns (rank0 int32 [N], gt_score
     fp64 [N]).
@@ -219,9 +221,12 @@ def sim_rank(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None
     rank0 is NOT finalised (NaN ground truths still hold their partial count): call
     :func:`rank_finalize` once every gallery chunk has been accumulated.
 
-    `sq64` (of these gallery rows) and `qq` (of these query rows) from :func:`rank_prepare`, together
-    with a given `gt_score`, select vtc_sim_rank_prepared: same result, no per-call row walks."""
-    dev = _req_cuda(q, g, gt, gt_score, rank0, sq64, qq)
+    Chunked evaluations cache three per-row quantities across calls (vtc_sim_rank_prepared): the
+    canonical ||x||^2 of these gallery rows (`sq64` in, or `sq64_out` to have this call compute and
+    store them), an upper bound of ||q||^2 of these query rows (`qq` / `qq_out`) and d(t,gt)
+    (`gt_score` / `gt_score_out`).  Same result as the plain call; rows that are handed in with all
+    three cached are not walked again."""
+    dev = _req_cuda(q, g, gt, gt_score, rank0, sq64, qq, sq64_out, qq_out, gt_score_out)
     q, g = _mat(q, "q"), _mat(g, "g")
     if q.shape[1] != g.shape[1] or q.dtype != g.dtype:
         raise ValueError("queries and gallery must share D and dtype")
@@ -233,29 +238,40 @@ def sim_rank(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None
         if gt.shape != (N,):
             raise ValueError("gt must be [N]")
     if rank0 is None:
-        rank0 = torch.zeros(N, dtype=torch.int32, device=dev)
+        rank0 = torch.empty(N, dtype=torch.int32, device=dev)  # every entry is written
         accumulate = False
     elif rank0.dtype != torch.int32 or rank0.shape != (N,) or not rank0.is_contiguous():
         raise ValueError("rank0 must be a contiguous int32 [N] tensor")
-    gs_out = None
-    if gt_score is None:
+
+    def vec(t, dt, n, name):
+        if t is not None and (t.dtype != dt or t.shape != (n,) or not t.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous {dt} [{n}] tensor")
+        return t
+
+    gt_score = vec(gt_score, torch.float64, N, "gt_score")
+    gs_out = vec(gt_score_out, torch.float64, N, "gt_score_out")
+    if gt_score is None and gs_out is None:
         gs_out = torch.empty(N, dtype=torch.float64, device=dev)
-    elif gt_score.dtype != torch.float64 or gt_score.shape != (N,):
-        raise ValueError("gt_score must be float64 [N]")
-    if sq64 is not None or qq is not None:
-        if sq64 is None or qq is None or gt_score is None:
-            raise ValueError("prepared ranking needs sq64, qq and gt_score together")
-        if sq64.dtype != torch.float64 or sq64.shape != (M,) or not sq64.is_contiguous():
-            raise ValueError("sq64 must be a contiguous float64 [M] tensor")
-        if qq.dtype != torch.float32 or qq.shape != (N,) or not qq.is_contiguous():
-            raise ValueError("qq must be a contiguous float32 [N] tensor")
+    cached = any(t is not None for t in (sq64, qq, sq64_out, qq_out))
+    if cached and prec != _ffi.PREC_BRUTE:
+        sq64 = vec(sq64, torch.float64, M, "sq64")
+        qq = vec(qq, torch.float32, N, "qq")
+        sq64_out = vec(sq64_out, torch.float64, M, "sq64_out")
+        qq_out = vec(qq_out, torch.float32, N, "qq_out")
+        if sq64 is None and sq64_out is None:
+            sq64_out = torch.empty(M, dtype=torch.float64, device=dev)
+        if qq is None and qq_out is None:
+            qq_out = torch.empty(N, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             ws = _workspace(dev, _ws_bytes(_ffi.OP_SIM_RANK, N, M, D, prec))
             _ffi.check(_ffi.load().vtc_sim_rank_prepared(
                 _ptr(q), _ptr(g), N, M, D, _dtype_code(q), _ptr(gt), row_offset, col_offset, met,
-                prec, _ptr(gt_score), _ptr(sq64), _ptr(qq), 1 if accumulate else 0, _ptr(rank0),
-                _ptr(ws), ws.numel(), _stream(dev)), "vtc_sim_rank_prepared")
-        return rank0, gt_score
+                prec, _ptr(gt_score), _ptr(None if gt_score is not None else gs_out),
+                _ptr(sq64), _ptr(None if sq64 is not None else sq64_out),
+                _ptr(qq), _ptr(None if qq is not None else qq_out),
+                1 if accumulate else 0, _ptr(rank0), _ptr(ws), ws.numel(), _stream(dev)),
+                "vtc_sim_rank_prepared")
+        return rank0, (gt_score if gt_score is not None else gs_out)
     with torch.cuda.device(dev):
         ws = _workspace(dev, _ws_bytes(_ffi.OP_SIM_RANK, N, M, D, prec))
         _ffi.check(_ffi.load().vtc_sim_rank(
@@ -263,6 +279,43 @@ def sim_rank(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None
             _ptr(gt_score), _ptr(gs_out), 1 if accumulate else 0, _ptr(rank0), _ptr(ws), ws.numel(),
             _stream(dev)), "vtc_sim_rank")
     return rank0, (gt_score if gt_score is not None else gs_out)
+
+
+def rank_eval(q: torch.Tensor, g: torch.Tensor, k_vals: Sequence[int],
+              gt: Optional[torch.Tensor] = None, metric="l2", precision="exact",
+              want_medr: bool = True) -> Dict[str, Optional[torch.Tensor]]:
+    """The whole of RecallAtK.compute (model/metric.py:137-161) for device-resident embeddings in
+    one library call -- memset + 3 kernels: similarity + rank of ground truth over the full gallery,
+    NaN ground truths -> rank M, hit counts for every k, median rank.  Returns
+    {"rank0": int32 [N], "hits": int64 [nk], "medr": fp64 [1] | None, "gt_score": fp64 [N]}."""
+    k_vals = [int(k) for k in k_vals]
+    if len(k_vals) > 8:  # the fused finalisation counts up to 8 thresholds (the reference uses 2-3)
+        rank0, gts = sim_rank(q, g, gt=gt, metric=metric, precision=precision)
+        hits, medr = rank_finalize(rank0, gts, g.shape[0], k_vals, want_medr)
+        return {"rank0": rank0, "hits": hits, "medr": medr, "gt_score": gts}
+    dev = _req_cuda(q, g, gt)
+    q, g = _mat(q, "q"), _mat(g, "g")
+    if q.shape[1] != g.shape[1] or q.dtype != g.dtype:
+        raise ValueError("queries and gallery must share D and dtype")
+    N, D = q.shape
+    M = g.shape[0]
+    prec, met = _prec(precision), _metric(metric)
+    if gt is not None:
+        gt = gt.to(torch.int64).contiguous()
+        if gt.shape != (N,):
+            raise ValueError("gt must be [N]")
+    rank0 = torch.empty(N, dtype=torch.int32, device=dev)
+    gts = torch.empty(N, dtype=torch.float64, device=dev)
+    hits = torch.empty(max(1, len(k_vals)), dtype=torch.int64, device=dev)
+    medr = torch.empty(1, dtype=torch.float64, device=dev) if want_medr else None
+    karr = (ctypes.c_int * max(1, len(k_vals)))(*k_vals)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_SIM_RANK, N, M, D, prec))
+        _ffi.check(_ffi.load().vtc_rank_eval(
+            _ptr(q), _ptr(g), N, M, D, _dtype_code(q), _ptr(gt), met, prec, karr, len(k_vals),
+            _ptr(rank0), _ptr(hits), _ptr(medr), _ptr(gts), _ptr(ws), ws.numel(), _stream(dev)),
+            "vtc_rank_eval")
+    return {"rank0": rank0, "hits": hits[:len(k_vals)], "medr": medr, "gt_score": gts}
 
 
 def gt_scores(q: torch.Tensor, g: torch.Tensor, gt: Optional[torch.Tensor] = None,

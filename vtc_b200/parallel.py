@@ -67,15 +67,17 @@ class CudaBackend:
         return self.ops.gt_scores(q, g, None, row_offset, col_offset, metric, precision)
 
     def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0,
-                 sq64=None, qq=None):
+                 sq64=None, qq=None, sq64_out=None, qq_out=None):
         """Accumulates into rank0; gt_score None = every ground truth lies inside g (computed and
-        returned).  sq64 / qq (from rank_prepare) select the prepared entry point."""
+        returned).  sq64 / qq hand cached per-row quantities in, sq64_out / qq_out have this call
+        compute and store them (vtc_sim_rank_prepared)."""
         _, gs = self.ops.sim_rank(q, g, None, row_offset, col_offset, metric, precision, gt_score,
-                                  rank0, accumulate=True, sq64=sq64, qq=qq)
+                                  rank0, accumulate=True, sq64=sq64, qq=qq, sq64_out=sq64_out,
+                                  qq_out=qq_out)
         return gs
 
-    def rank_prepare(self, x, precision, want_sq64, want_qq):
-        return self.ops.rank_prepare(x, precision, want_sq64, want_qq)
+    def rank_prepare(self, x, precision, want_sq64, want_qq, sq64_out=None, qq_out=None):
+        return self.ops.rank_prepare(x, precision, want_sq64, want_qq, sq64_out, qq_out)
 
     def rank_finalize(self, rank0, gt_score, M_total, k_vals, want_medr):
         return self.ops.rank_finalize(rank0, gt_score, M_total, k_vals, want_medr)
@@ -108,16 +110,13 @@ def _all_gather_padded(x: torch.Tensor, sizes: Sequence[int], group, async_op: b
 def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int, M_total: int,
                       k_vals: Sequence[int] = (1, 5, 10), metric: str = "l2",
                       precision: str = "exact", group=None, backend=None,
-                      want_medr: bool = True, single_pass: Optional[bool] = None
-                      ) -> Dict[str, object]:
+                      want_medr: bool = True) -> Dict[str, object]:
     """Row-sharded similarity + rank + R@K (+MedR).  q_local / g_local are this rank's
     shard_bounds() rows of the global query / gallery matrices; gt(t) = t (global row index).
 
-    single_pass (default: VTC_SHARD_SINGLE_PASS=1, else off; needs equal gallery shards): wait for
-    the gather and rank against the whole gathered gallery in ONE library call instead of
-    local chunk + up to two remote ranges -- a third of the small launches and one tensor-core
-    launch without intermediate tails, at the price of not overlapping the gather (opt-in until both
-    have been timed side by side at 8 GPUs).
+    Per-row quantities are computed once, by the rank that owns the rows: the canonical ||x||^2 of a
+    gallery shard come out of its owner's local ranking call and ride a second (800 KB) all_gather,
+    so the calls against the gathered rows walk no row at all (vtc_sim_rank_prepared).
 
     Returns {"hits": int64 [nk] (global), "medr": float or None, "rank0_local": int32 [n_r],
              "num_queries": N_total}.  hits / medr are identical on every rank."""
@@ -133,7 +132,8 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     ph = _Phases(dev)
     if precision == "bf16" and q_local.dtype == torch.float32 and g_local.dtype == torch.float32:
         # the bf16 mode ranks the RN-even bf16 roundings of the inputs: round BEFORE the exchange
-        # (identical results, half the NVLink bytes and half the operand-prep reads)
+        # (identical results, half the NVLink bytes; bf16 rows of whole swizzle atoms are the
+        # tensor-core operands in place)
         q_local = q_local.to(torch.bfloat16)
         g_local = g_local.to(torch.bfloat16)
 
@@ -143,9 +143,6 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
     gathered = None
     mx = max(g_sizes)
     equal = all(sz == mx for sz in g_sizes)
-    if single_pass is None:
-        single_pass = os.environ.get("VTC_SHARD_SINGLE_PASS", "0") not in ("", "0")
-    single_pass = bool(single_pass) and world > 1 and equal and mx > 0
     if world > 1:
         send = g_local
         if send.shape[0] < mx:
@@ -153,86 +150,90 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
             send = torch.cat([send, pad])
         gathered = torch.empty((world * mx, send.shape[1]), dtype=send.dtype, device=dev)
         work = dist.all_gather_into_tensor(gathered, send.contiguous(), group=group, async_op=True)
-
     ph.mark("cast+gather_issue")
-    # ground-truth scores: d(t, gt) lives in the chunk that owns gallery row t; start with ours
+
     n_local = qe - qs
     gs0, ge0 = g_starts[rank], g_starts[rank] + g_sizes[rank]
+    have_local = g_sizes[rank] > 0
     rank0 = torch.zeros(n_local, dtype=torch.int32, device=dev)
-    gt_local = (world == 1 or _gt_all_local(qs, qe, gs0, g_sizes[rank])) and g_sizes[rank] > 0
+    if n_local == 0:
+        # more ranks than query rows: take part in the collectives, rank nothing
+        if work is not None:
+            work.wait()
+            if hasattr(backend, "rank_prepare") and precision in ("bf16", "exact"):
+                _exchange_norms(backend, g_local, mx, world, precision, group, dev, have_local)
+        gt_score = torch.empty(0, dtype=torch.float64, device=dev)
+        return _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group,
+                               want_medr, ph)
+    gt_local = (world == 1 or _gt_all_local(qs, qe, gs0, g_sizes[rank])) and have_local
+    cached = hasattr(backend, "rank_prepare") and precision in ("bf16", "exact") and world > 1
+    sq_local = qq = None
+    if cached:
+        sq_local = torch.zeros(mx, dtype=torch.float64, device=dev)   # padded like the shard
+        qq = torch.empty(n_local, dtype=torch.float32, device=dev)
     local_done = False
-    # VTC_RANK_PREPARED=1 (opt-in until timed at 8 GPUs): query-norm bounds once per step, gallery
-    # norms once per (local / gathered) buffer, ground-truth scores from the pre-pass; the two or
-    # three ranking calls of the step then walk no rows of their own (vtc_sim_rank_prepared)
-    prepared = (os.environ.get("VTC_RANK_PREPARED", "0") not in ("", "0")
-                and hasattr(backend, "rank_prepare") and not single_pass and world > 1
-                and precision in ("bf16", "exact") and n_local > 0
-                and (precision == "bf16") == (q_local.dtype == torch.bfloat16)
-                and q_local.dtype == g_local.dtype)
-    if prepared:
-        return _sharded_rank_eval_prepared(backend, q_local, g_local, gathered, work, equal, mx,
-                                           g_sizes, g_starts, rank, world, qs, gt_local, N_total,
-                                           M_total, k_vals, metric, precision, group, want_medr,
-                                           rank0, ph)
-    if single_pass:
-        # equal shards: the gathered buffer IS the gallery in global row order, every ground truth
-        # lies inside it, so one call yields the ground-truth scores and the complete ranks
-        work.wait()
-        ph.mark("gather_wait")
-        work = None
-        gt_score = backend.sim_rank(q_local, gathered[:M_total], qs, 0, metric, precision, None, rank0)
-        local_done = True
-    elif gt_local:
-        # every ground truth is in our own chunk: rank against it (the call also yields the
-        # ground-truth scores) while the gather is in flight
-        gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0)
+    if gt_local:
+        # every ground truth is in our own chunk: rank against it while the gather is in flight;
+        # the call also yields the ground-truth scores, the shard's norms and the query-norm bounds
+        gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0,
+                                    **({"sq64_out": sq_local[:g_sizes[rank]], "qq_out": qq}
+                                       if cached else {}))
         local_done = True
     else:
-        gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
+        if have_local:
+            gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
+        else:  # more ranks than gallery rows: every ground truth lives elsewhere
+            gt_score = torch.full((n_local,), float("nan"), dtype=torch.float64, device=dev)
+        if cached:
+            if have_local:
+                backend.rank_prepare(g_local, precision, True, False,
+                                     sq64_out=sq_local[:g_sizes[rank]])
+            backend.rank_prepare(q_local, precision, False, True, qq_out=qq)
     ph.mark("gt+local_rank")
     if work is not None:
+        sq_all = None
+        if cached:
+            # the owners' norms: [world * mx] fp64, laid out like the gathered rows
+            sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(sq_all, sq_local, group=group)
         work.wait()
         ph.mark("gather_wait")
-        # remote row ranges as (start row in the global gallery, tensor)
+        # remote row ranges as (start row in the global gallery, buffer start, buffer end)
         if equal:
-            remote = [(0, gathered[:gs0]), (ge0, gathered[ge0:M_total])]
+            remote = [(0, 0, gs0), (ge0, ge0, M_total)]
         else:
-            remote = [(g_starts[r], gathered[r * mx:r * mx + g_sizes[r]])
-                      for r in range(world) if r != rank]
-        remote = [(st, t) for st, t in remote if t.shape[0] > 0]
+            remote = [(g_starts[r], r * mx, r * mx + g_sizes[r]) for r in range(world) if r != rank]
+        remote = [(st, b0, b1) for st, b0, b1 in remote if b1 > b0]
         if not gt_local:
-            for st, t in remote:
-                other = backend.gt_scores(q_local, t, qs, st, metric, precision)
+            # ground truths that live in another rank's shard (N != M splits): fill in where still NaN
+            for st, b0, b1 in remote:
+                other = backend.gt_scores(q_local, gathered[b0:b1], qs, st, metric, precision)
                 gt_score = torch.where(torch.isnan(gt_score), other, gt_score)
-        if not local_done and g_sizes[rank] > 0:
-            backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
-        for st, t in remote:
-            backend.sim_rank(q_local, t, qs, st, metric, precision, gt_score, rank0)
-    elif not local_done and g_sizes[rank] > 0:
+        kw = (lambda b0, b1: {"sq64": sq_all[b0:b1], "qq": qq}) if cached else (lambda b0, b1: {})
+        if not local_done and have_local:
+            backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0,
+                             **({"sq64": sq_local[:g_sizes[rank]], "qq": qq} if cached else {}))
+        for st, b0, b1 in remote:
+            backend.sim_rank(q_local, gathered[b0:b1], qs, st, metric, precision, gt_score, rank0,
+                             **kw(b0, b1))
+    elif not local_done and have_local:
         backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
-
     ph.mark("remote_rank")
-    medr = None
     if world == 1:
         hits, medr = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), want_medr)
-        hits = hits.clone()
-    elif want_medr:
-        # NaN ground truths -> M_total locally, then ONE exchange: gather the int32 ranks and count
-        # hits / select the median on the full vector (identical on every rank)
-        backend.rank_finalize(rank0, gt_score, M_total, [], False)
-        q_sizes = [shard_bounds(N_total, world, r)[1] - shard_bounds(N_total, world, r)[0]
-                   for r in range(world)]
-        allr, _ = _all_gather_padded(rank0, q_sizes, group)
-        full = torch.cat([allr[r][:q_sizes[r]] for r in range(world)])
-        hits, medr = backend.rank_finalize(full, None, M_total, list(k_vals), True)
-        hits = hits.clone()
-    else:
-        hits, _ = backend.rank_finalize(rank0, gt_score, M_total, list(k_vals), False)
-        hits = hits.clone()
-        dist.all_reduce(hits, op=dist.ReduceOp.SUM, group=group)
-    ph.mark("finalize+collectives")
-    return {"hits": hits, "medr": medr, "rank0_local": rank0, "num_queries": N_total,
-            "phases_ms": ph.result()}
+        return {"hits": hits.clone(), "medr": medr, "rank0_local": rank0, "num_queries": N_total,
+                "phases_ms": ph.result()}
+    return _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group,
+                           want_medr, ph)
+
+
+def _exchange_norms(backend, g_local, mx, world, precision, group, dev, have_local):
+    """A rank without query rows still owns gallery rows: contribute their norms to the exchange."""
+    sq_local = torch.zeros(mx, dtype=torch.float64, device=dev)
+    if have_local:
+        backend.rank_prepare(g_local, precision, True, False, sq64_out=sq_local[:g_local.shape[0]])
+    sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(sq_all, sq_local, group=group)
 
 
 def _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group, want_medr, ph):
@@ -258,52 +259,6 @@ def _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, g
     ph.mark("finalize+collectives")
     return {"hits": hits, "medr": medr, "rank0_local": rank0, "num_queries": N_total,
             "phases_ms": ph.result()}
-
-
-def _sharded_rank_eval_prepared(backend, q_local, g_local, gathered, work, equal, mx, g_sizes,
-                                g_starts, rank, world, qs, gt_local, N_total, M_total, k_vals,
-                                metric, precision, group, want_medr, rank0, ph):
-    """sharded_rank_eval with per-step prepared quantities (world > 1): the query-norm bounds and the
-    ground-truth scores once, the gallery norms once per buffer; the ranking calls walk no rows."""
-    gs0, ge0 = g_starts[rank], g_starts[rank] + g_sizes[rank]
-    have_local = g_sizes[rank] > 0
-    _, qq = backend.rank_prepare(q_local, precision, False, True)
-    if have_local:
-        gt_score = backend.gt_scores(q_local, g_local, qs, gs0, metric, precision)
-        sq_local, _ = backend.rank_prepare(g_local, precision, True, False)
-    else:  # more ranks than gallery rows: every ground truth lives elsewhere
-        gt_score = torch.full((q_local.shape[0],), float("nan"), dtype=torch.float64,
-                              device=q_local.device)
-        sq_local = None
-    local_done = False
-    if gt_local and have_local:
-        # every ground truth is in our own chunk: rank against it while the gather is in flight
-        backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0,
-                         sq64=sq_local, qq=qq)
-        local_done = True
-    ph.mark("prepare+gt+local_rank")
-    work.wait()
-    ph.mark("gather_wait")
-    sq_all, _ = backend.rank_prepare(gathered, precision, True, False)   # [world * mx], incl. padding
-    if equal:
-        remote = [(0, 0, gs0), (ge0, ge0, M_total)]       # (global start row, buffer start, buffer end)
-    else:
-        remote = [(g_starts[r], r * mx, r * mx + g_sizes[r]) for r in range(world) if r != rank]
-    remote = [(st, b0, b1) for st, b0, b1 in remote if b1 > b0]
-    if not gt_local:
-        # ground truths that live in another rank's shard (N != M splits): fill in where still NaN
-        for st, b0, b1 in remote:
-            other = backend.gt_scores(q_local, gathered[b0:b1], qs, st, metric, precision)
-            gt_score = torch.where(torch.isnan(gt_score), other, gt_score)
-    if have_local and not local_done:
-        backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0,
-                         sq64=sq_local, qq=qq)
-    for st, b0, b1 in remote:
-        backend.sim_rank(q_local, gathered[b0:b1], qs, st, metric, precision, gt_score, rank0,
-                         sq64=sq_all[b0:b1], qq=qq)
-    ph.mark("remote_rank")
-    return _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group,
-                           want_medr, ph)
 
 
 class GraphedRankEval:
