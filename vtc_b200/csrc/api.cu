@@ -734,10 +734,11 @@ int vtc_gt_scores(const void* Q, const void* G, int64_t N, int64_t M, int D, int
                   const int64_t* gt, int64_t row_offset, int64_t col_offset, int metric,
                   int precision, double* gt_score, void* wsp, size_t ws_bytes,
                   vtc_stream_t stream) {
-  if (!Q || !G || !gt_score || N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) ||
-      !valid_metric(metric) || !valid_prec(precision))
+  if (N < 0 || M < 0 || D <= 0 || !valid_dtype(dtype) || !valid_metric(metric) ||
+      !valid_prec(precision))
     return VTC_ERR_INVALID_ARG;
-  if (N == 0) return VTC_OK;
+  if (N == 0) return VTC_OK;  // no queries (pointers may be NULL, e.g. an empty shard)
+  if (!Q || (!G && M > 0) || !gt_score) return VTC_ERR_INVALID_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   Workspace ws(wsp, ws_bytes);
   double* sq64 = ws.take<double>(M);

@@ -14,6 +14,35 @@ import torch
 from .. import ops
 
 
+class _SimMatrixFunction(torch.autograd.Function):
+    """sim = (s * A) @ B^T with gradients to A, B and s (dA = s g B, dB = s g^T A,
+    ds = sum(g * A B^T)), every product on the library's tensor-core GEMM."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale, precision):
+        sim = ops.sim_matrix(a, b, scale, precision)
+        ctx.save_for_backward(a, b, scale if isinstance(scale, torch.Tensor) else torch.tensor(float(scale)))
+        ctx.precision = precision
+        ctx.sim = sim
+        return sim
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, scale = ctx.saved_tensors
+        s = scale.detach().to(device=g.device, dtype=torch.float32).reshape(())
+        g = g.contiguous().float()
+        da = db = ds = None
+        if ctx.needs_input_grad[0]:
+            da = (s * ops.linear(g, b.detach().float().t().contiguous(), None, None, 0, ctx.precision)
+                  ).to(a.dtype)
+        if ctx.needs_input_grad[1]:
+            db = (s * ops.linear(g.t().contiguous(), a.detach().float().t().contiguous(), None, None, 0,
+                                 ctx.precision)).to(b.dtype)
+        if ctx.needs_input_grad[2]:
+            ds = ((g * ctx.sim).sum() / s).reshape(scale.shape).to(scale.dtype)
+        return da, db, ds, None
+
+
 class LazySim:
     def __init__(self, feats_a: torch.Tensor, feats_b: torch.Tensor, scale, precision: str = "exact"):
         self.feats_a = feats_a
@@ -42,7 +71,17 @@ class LazySim:
         return 2
 
     def materialize(self) -> torch.Tensor:
-        """(scale * A) @ B.t() as a real fp32 CUDA tensor (no autograd graph)."""
+        """(scale * A) @ B.t() as a real fp32 CUDA tensor.  Like the reference's `sim`
+        (model/model.py:369) it is differentiable: when autograd is recording and the features or
+        the scale require grad, the tensor carries a graph back to them."""
+        wants_grad = torch.is_grad_enabled() and any(
+            isinstance(t, torch.Tensor) and t.requires_grad
+            for t in (self.feats_a, self.feats_b, self.scale))
+        if wants_grad:
+            if self._dense is None or not self._dense.requires_grad:
+                self._dense = _SimMatrixFunction.apply(self.feats_a, self.feats_b, self.scale,
+                                                       self.precision)
+            return self._dense
         if self._dense is None:
             self._dense = ops.sim_matrix(self.feats_a.detach(), self.feats_b.detach(), self.scale,
                                          self.precision)

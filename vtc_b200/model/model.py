@@ -11,8 +11,10 @@ reference (`final_transformer.resblocks.{i}.attn.in_proj_weight`, ..., `final_li
 `mask_embedding`) so its checkpoints load and `train.py:105`'s substring grouping keeps working.
 
 The CAM forward runs on the CUDA kernels of csrc/cam.cu + csrc/sim_tc.cu (dense projections on
-the tensor cores).  It is inference-only in this round: calling it with autograd enabled on
-parameters that require grad raises (the CAM backward is listed as "next" in DESIGN.md).
+the tensor cores) as one C call (vtc_cam_forward).  Under autograd (`_adapt_feature` with
+parameters or inputs that require grad) it goes through `_CamAdaptFunction`, whose backward runs
+on csrc/cam_bwd.cu + the same tensor-core GEMMs; gradients are checked against torch autograd
+through the oracle (tests/test_gpu_parity.py::test_cam_backward_*).
 """
 from __future__ import annotations
 
@@ -73,7 +75,8 @@ def normalize(x: torch.Tensor) -> torch.Tensor:
 
 
 # residual activations (model/model.py:30-77) -> (VTC_RESACT_*, scale); "sub_mean" / "bn" use the
-# BatchNorm1d running statistics (eval mode only: the CAM is forward-only this round)
+# BatchNorm1d running statistics (their frozen form; training-mode batch statistics are out of scope,
+# no shipped config uses them)
 RESIDUAL_ACTIVATIONS = {
     None: (_ffi.RESACT_NONE, 1.0), "none": (_ffi.RESACT_NONE, 1.0),
     "normalize": (_ffi.RESACT_NORMALIZE_EPS, 1.0),
@@ -126,11 +129,24 @@ class CAMTransformer(nn.Module):
         self.heads = heads
         self.precision = precision
         self.resblocks = nn.Sequential(*[_ResBlock(width, heads) for _ in range(layers)])
+        self._prepared_cache = None
+        self.register_load_state_dict_post_hook(lambda module, _keys: module.invalidate_prepared())
 
     # ---- prepared weights: bf16 tensor-core operands + padded biases, rebuilt only when a
-    # parameter changes (torch bumps `_version` on every in-place update / optimizer step)
+    # parameter changes.  torch bumps `_version` on every in-place update / optimizer step and a
+    # `.to()` / `.cuda()` moves the storage, so (data_ptr, _version) catches those; writes through
+    # `.data` (p.data.copy_(), EMA weight swaps) bump nothing, so load_state_dict() and train() /
+    # eval() drop the cache as well, and invalidate_prepared() is there for everything else.
     def _param_key(self, extra=()):
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple(extra)
+
+    def invalidate_prepared(self) -> None:
+        """Forget the prepared tensor-core operands (call after writing weights through `.data`)."""
+        self._prepared_cache = None
+
+    def train(self, mode: bool = True):
+        self.invalidate_prepared()
+        return super().train(mode)
 
     def prepared(self):
         """(ctypes array of vtc_cam_layer, keep-alive list) for vtc_cam_forward."""
@@ -302,6 +318,26 @@ class PretrainedCLIPBase(nn.Module):
     # reference's configs, e.g. configs/pretrained_clip_comments_attention.jsonc:9)
     CLIP_FEATURE_DIMS = {"ViT-B/32": 512, "ViT-B/16": 512, "ViT-L/14": 768, "ViT-L/14@336px": 768,
                          "RN50": 1024, "RN101": 512, "RN50x4": 640, "RN50x16": 768, "RN50x64": 1024}
+
+    _final_prepared = None
+
+    def invalidate_prepared(self) -> None:
+        """Forget every prepared tensor-core operand of the CAM (final_linear's and the
+        transformer's).  train() / eval() and load_state_dict() do this on their own; call it after
+        writing weights through `.data`."""
+        self._final_prepared = None
+        tfm = getattr(self, "final_transformer", None)
+        if tfm is not None and hasattr(tfm, "invalidate_prepared"):
+            tfm.invalidate_prepared()
+
+    def train(self, mode: bool = True):
+        self.invalidate_prepared()
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_prepared()
+        return out
 
     @classmethod
     def _resolve_feature_dim(cls, model_type, feature_dim, backbone) -> int:
