@@ -236,12 +236,15 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.dgt = dgt, p.qq = qq, p.max_sq_bits = &w.scalars[0];
   p.guard_rel = guard_rel_for(precision, o.Kp), p.metric_l2 = metric == VTC_METRIC_L2 ? 1 : 0;
   p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_seg_count = &w.scalars[64];
-  tc::Plan pl = tc::plan_tiles(p, 64, tc::choose_cluster(N, M));
+  // K' <= 512: the query tile lives in tensor memory (one CTA per SM, 128-column tiles)
+  const bool ts = p.num_kb <= 8 && tc::rank_ts_enabled();
+  tc::Plan pl = ts ? tc::plan_tiles(p, 64, 1, 8, 128) : tc::plan_tiles(p, 64, tc::choose_cluster(N, M));
+  pl.ts = ts;
   if (pl.grid > 256) return VTC_ERR_UNSUPPORTED_SHAPE;
   p.amb_seg_cap = (unsigned int)(w.amb_cap / (size_t)pl.grid);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opQ, N, o.Kp, o.Kp, tc::BM, &tmA));
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opG, M, o.Kp, o.Kp, tc::BN / pl.cluster, &tmB));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opG, M, o.Kp, o.Kp, pl.bn / pl.cluster, &tmB));
   VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_RANK, p.num_kb <= 8, pl, tmA, tmB, p, s));
   // 3. epilogue: exact re-check of the guard-band groups (brute force if the list overflowed),
   //    commit, and -- for vtc_rank_eval -- hit counts and the median rank

@@ -13,12 +13,14 @@ namespace tc {
 
 int launch_rank(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
+int launch_rank_ts(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid,
+                   cudaStream_t s);
 int launch_topk(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
 int launch_lse(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
                int grid, cudaStream_t s);
-int launch_store(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
-                 int grid, cudaStream_t s);
+int launch_store(bool a_resident, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                 const Params& p, int grid, cudaStream_t s);
 int max_active_clusters_rank(int cluster);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -121,10 +123,23 @@ int debug_prof_read(unsigned long long* out, int max_words) {
   return cuda_err(e);
 }
 
-Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split) {
+// Experiment switch of round 2 (VTC_TS=0 turns it off): the rank kernel with the query tile in
+// tensor memory.
+bool rank_ts_enabled() {
+  static const int on = []() {
+    const char* e = getenv("VTC_TS");
+    return e && *e ? atoi(e) : 1;
+  }();
+  return on != 0;
+}
+
+Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split, int bn) {
   Plan pl;
   pl.cluster = cluster < 1 ? 1 : cluster;
   pl.pair = pl.cluster == 2 && use_pair(p.num_kb);
+  pl.bn = bn == 128 ? 128 : BN;
+  pl.ts = false;
+  min_tiles_per_split *= BN / pl.bn;
   static const int skip_epi = []() {
     const char* e = getenv("VTC_DBG_SKIP_EPILOGUE");
     return e && *e ? atoi(e) : 0;
@@ -132,7 +147,7 @@ Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split)
   p.dbg_skip_epilogue = skip_epi;
   p.dbg_prof = dbg_prof_buffer();
   p.q_tiles = (int)ceil_div<int64_t>(p.N, BM);
-  p.g_tiles = (int)ceil_div<int64_t>(p.M, BN);
+  p.g_tiles = (int)ceil_div<int64_t>(p.M, pl.bn);
   const int units = pl.cluster > 1 ? active_clusters(pl.cluster) : kNumSMs;  // co-resident clusters
   const int q_groups = ceil_div(p.q_tiles, pl.cluster);
   // Items are dealt round-robin to the co-resident clusters, so the cost is ceil(items / units)
@@ -211,13 +226,21 @@ int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorM
   }
   int rc;
   switch (epilogue) {
-    case EPI_RANK: rc = launch_rank(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
+    case EPI_RANK:
+      if (pl.ts)
+        rc = (a_resident && pl.cluster == 1 && pl.bn == 128) ? launch_rank_ts(tmA, tmB, p, pl.grid, s)
+                                                            : VTC_ERR_INVALID_ARG;
+      else
+        rc = pl.bn == BN ? launch_rank(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s)
+                         : VTC_ERR_INVALID_ARG;
+      break;
     case EPI_TOPK: rc = launch_topk(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
     case EPI_LSE:
       rc = pl.cluster == 1 ? launch_lse(a_resident, tmA, tmB, p, pl.grid, s) : VTC_ERR_INVALID_ARG;
       break;
     case EPI_STORE:
-      rc = pl.cluster == 1 ? launch_store(a_resident, tmA, tmB, p, pl.grid, s) : VTC_ERR_INVALID_ARG;
+      rc = pl.cluster == 1 ? launch_store(a_resident, pl.bn, tmA, tmB, p, pl.grid, s)
+                           : VTC_ERR_INVALID_ARG;
       break;
     default: rc = VTC_ERR_INVALID_ARG;
   }

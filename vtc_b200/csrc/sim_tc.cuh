@@ -80,12 +80,17 @@ struct Plan {
   int cluster;  // CTAs per cluster sharing each gallery tile
   int grid;     // CTAs to launch (multiple of cluster)
   bool pair;    // cluster == 2 run as a CTA pair: one M256 cta_group::2 MMA instead of multicast
+  int bn;       // gallery rows per tile: BN (256) or 128
+  bool ts;      // query tile in tensor memory (EPI_RANK, num_kb <= 8, cluster 1, bn 128)
 };
-// fills q_tiles / g_tiles / g_splits / tiles_per_split for the given cluster size
-Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split = 8);
+// fills q_tiles / g_tiles / g_splits / tiles_per_split for the given cluster size and tile width;
+// min_tiles_per_split is in 256-row tiles
+Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split = 8, int bn = BN);
+// EPI_RANK with the resident query tile in tensor memory instead of shared memory
+bool rank_ts_enabled();
 
 // a_resident: keep the whole 128 x K' query tile in shared memory (needs num_kb <= 8).
-// tmB must have been built with box_rows = BN / pl.cluster.
+// tmB must have been built with box_rows = pl.bn / pl.cluster.
 int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorMap& tmA,
                   const CUtensorMap& tmB, const Params& p, cudaStream_t s);
 

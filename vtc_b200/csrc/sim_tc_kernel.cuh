@@ -39,7 +39,8 @@ namespace tc {
 using namespace ptx;
 
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int EPI_WARPS_C = 8;
+constexpr int SMEM_LIMIT = 232448;         // 227 KB per CTA
 constexpr int MAX_RES_KB = 8;              // resident A: up to K' = 512
 constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
@@ -48,20 +49,25 @@ constexpr int TMEM_COLS = 512;
 
 // kPair: the two CTAs of a cluster issue one M256 cta_group::2 MMA; each CTA stages only ITS half
 // of every gallery tile (16 KB), so the ring is twice as deep in the same shared memory.
-template <bool kRes, bool kPair = false>
+// kBN: gallery rows per tile (UMMA N, TMEM columns per accumulator stage): 256, or 128 for the
+// kernels that keep the query tile in TMEM (kTS) and for small dense products that need more CTAs.
+// The ring takes what the resident query tile leaves of the 227 KB (at most 8 stages).
+template <bool kRes, bool kPair = false, int kBN = BN>
 struct SmemLayout {
   static constexpr int kResKb = MAX_RES_KB;
-  static constexpr int kBBytes = kPair ? B_TILE_BYTES / 2 : B_TILE_BYTES;
-  static constexpr int kStages = kPair ? 6 : (kRes ? 3 : 4);
+  static constexpr int kBBytes = (kBN * BK * 2) / (kPair ? 2 : 1);
   static constexpr int kStageBytes = kRes ? kBBytes : (A_TILE_BYTES + kBBytes);
   static constexpr int kResBytes = kRes ? kResKb * A_TILE_BYTES : 0;
+  static constexpr int kFit = (SMEM_LIMIT - 256 - EPI_WARPS_C * 64 * 4 - kResBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kStagesOff = kResBytes;
   static constexpr int kBarOff = kStagesOff + kStages * kStageBytes;
   static constexpr int kBiasOff = kBarOff + 256;  // 8 epilogue warps x 64 floats
   static constexpr int kNumBars = 2 * kStages + kResKb + 1 + 2 + 2;
   static constexpr int kTotal = kBiasOff + EPI_WARPS * 64 * 4;
+  static_assert(kStages >= 3, "ring too shallow");
   static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
-  static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(kTotal <= SMEM_LIMIT, "exceeds 227 KB of shared memory");
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -416,12 +422,24 @@ struct TopkEpi {
 };
 
 // ------------------------------------------------------------------------------------- kernel
-template <typename Epi, bool kRes, int kC, bool kPair = false>
+// kTS: the resident query tile lives in TENSOR MEMORY.  Per work item its k-blocks are staged in
+// shared memory by TMA (as for kRes) and moved to TMEM columns [0, 4 K'/64 * 8) by tcgen05.cp; the
+// MMAs then read A from TMEM (tcgen05.mma [d], [a], b-desc) and shared memory only serves the gallery
+// stream: 4 KB instead of 12 KB of operand reads per 128 x 256 x 16 step, which is what the
+// shared-memory pipe (128 B/clk) was short of -- the SS kernel issues one M128 N256 K16 MMA per
+// ~150-175 clk instead of 128 (scripts/tc_prof.py).  The staging area is free again as soon as the
+// copies have retired, so the NEXT item's query tile is prefetched during the whole item.  TMEM:
+// 256 columns of A + two accumulator stages of kBN = 128 columns.
+template <typename Epi, bool kRes, int kC, bool kPair = false, int kBN = BN, bool kTS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const Params p) {
   static_assert(!kPair || kC == 2, "a CTA pair is a cluster of two");
-  using L = SmemLayout<kRes, kPair>;
+  static_assert(kBN == 256 || kBN == 128, "tile widths built: 256 and 128 gallery rows");
+  static_assert(!kTS || (kRes && kBN == 128 && !kPair && kC == 1),
+                "A in TMEM: resident query tile, 128-column accumulators, one CTA");
+  using L = SmemLayout<kRes, kPair, kBN>;
+  constexpr uint32_t kAccCol0 = kTS ? 4 * MAX_RES_KB * 8 : 0;  // first accumulator column
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* res_a = smem;
   uint8_t* stages = smem + L::kStagesOff;
@@ -513,7 +531,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               uint8_t* st = stages + stage * L::kStageBytes;
               if (!kRes) tma_load_2d_pair(st, &tmA, fbar, kb * BK, qt * BM);
               tma_load_2d_pair(st + (kRes ? 0 : A_TILE_BYTES), &tmB, fbar, kb * BK,
-                               tile * BN + cta_rank * (BN / 2));
+                               tile * kBN + cta_rank * (kBN / 2));
               if (++stage == L::kStages) stage = 0, phase ^= 1;
               continue;
             }
@@ -527,11 +545,11 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (!kRes) tma_load_2d(st, &tmA, &full[stage], kb * BK, qt * BM);
             uint8_t* bdst = st + (kRes ? 0 : A_TILE_BYTES);
             if (kC == 1) {
-              tma_load_2d(bdst, &tmB, &full[stage], kb * BK, tile * BN);
+              tma_load_2d(bdst, &tmB, &full[stage], kb * BK, tile * kBN);
             } else {
-              constexpr int kSliceRows = BN / kC;
+              constexpr int kSliceRows = kBN / kC;
               tma_load_2d_multicast(bdst + cta_rank * kSliceRows * (BK * 2), &tmB, &full[stage],
-                                    kb * BK, tile * BN + cta_rank * kSliceRows, kMask);
+                                    kb * BK, tile * kBN + cta_rank * kSliceRows, kMask);
             }
             if (++stage == L::kStages) stage = 0, phase ^= 1;
           }
@@ -541,7 +559,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(kPair ? 2 * BM : BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kPair ? 2 * BM : BM, kBN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0, it = 0;
       // VTC_DBG_PROF: where the issuer waits (one thread; two clock reads per wait when enabled)
       const bool prof = p.dbg_prof != nullptr;
@@ -562,9 +580,26 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
           }
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * BN;
+          const uint32_t d_tmem = tmem_base + kAccCol0 + as * kBN;
+          if (kTS && tile == t0) {
+            // this item's query tile: shared memory -> TMEM, K16 slice by K16 slice (the same
+            // descriptors the SS kernel hands to the MMA as A).  tcgen05.cp and tcgen05.mma execute in
+            // issue order, so the previous item's MMAs have read the old tile before it is
+            // overwritten and this item's MMAs see the new one; the commit frees the staging area
+            // for the producer's prefetch of the next item's tile.
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(&a_full[kb], it & 1);
+              tc_fence_after();
+              const uint64_t adesc = make_smem_desc_sw128(smem_u32(res_a + kb * A_TILE_BYTES));
+#pragma unroll
+              for (int k4 = 0; k4 < BK / 16; ++k4)
+                tmem_cp_128x256b(tmem_base + (uint32_t)((kb * 4 + k4) * 8),
+                                 desc_advance(adesc, k4 * 32));
+            }
+            umma_commit(a_empty);
+          }
           for (int kb = 0; kb < nkb; ++kb) {
-            if (kRes && tile == t0) mbar_wait(&a_full[kb], it & 1);
+            if (kRes && !kTS && tile == t0) mbar_wait(&a_full[kb], it & 1);
             if (prof) {
               const long long c0 = clock64();
               mbar_wait(&full[stage], phase);
@@ -579,7 +614,10 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(st + (kRes ? 0 : A_TILE_BYTES)));
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
-              if (kPair)
+              if (kTS)
+                umma_bf16_ts(d_tmem, tmem_base + (uint32_t)((kb * 4 + k4) * 8),
+                             desc_advance(bdesc, k4 * 32), idesc, (uint32_t)((kb | k4) != 0));
+              else if (kPair)
                 umma_bf16_pair(d_tmem, desc_advance(adesc, k4 * 32), desc_advance(bdesc, k4 * 32),
                                idesc, (uint32_t)((kb | k4) != 0));
               else
@@ -603,7 +641,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           as ^= 1;
           if (as == 0) aphase ^= 1;
         }
-        if (kRes) {
+        if (kRes && !kTS) {
           if (kPair)
             umma_commit_pair(a_empty, kMask);
           else
@@ -630,7 +668,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int row = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float scale = p.scale * (p.scale_ptr ? *p.scale_ptr : 1.0f);
-    constexpr int kHalfCols = BN / 2;  // 128 columns = 4 chunks of 32
+    constexpr int kHalfCols = kBN / 2;  // 128 (64) columns = 4 (2) chunks of 32
     uint32_t as = 0, aphase = 0;
     Epi epi;
     float* wbias = reinterpret_cast<float*>(smem + L::kBiasOff) + (warp - EPI_WARP0) * 64;
@@ -639,7 +677,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cluster_id < num_items && lane < 16)
       bias_pre = __ldg(reinterpret_cast<const float4*>(
-                           p.col_bias + (int64_t)(cluster_id / q_groups) * p.tiles_per_split * BN +
+                           p.col_bias + (int64_t)(cluster_id / q_groups) * p.tiles_per_split * kBN +
                            half * kHalfCols) +
                        lane);
     const bool eprof = p.dbg_prof != nullptr;
@@ -651,13 +689,13 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
       epi.begin_item(p, (int64_t)qt * BM + row, 2 * split + half);
       for (int tile = t0; tile < t1; ++tile) {
-        const int64_t j0 = (int64_t)tile * BN + half * kHalfCols;
+        const int64_t j0 = (int64_t)tile * kBN + half * kHalfCols;
         // first column this warp will process in its next tile (for the bias prefetch)
-        int64_t next_j0 = j0 + BN;
+        int64_t next_j0 = j0 + kBN;
         if (tile + 1 >= t1) {
           const int nitem = item + num_clusters;
           next_j0 = nitem < num_items
-                        ? (int64_t)(nitem / q_groups) * p.tiles_per_split * BN + half * kHalfCols
+                        ? (int64_t)(nitem / q_groups) * p.tiles_per_split * kBN + half * kHalfCols
                         : 0;
         }
         if (eprof) {
@@ -668,7 +706,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           mbar_wait(&tmem_full[as], aphase);
         }
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_off + as * BN + half * kHalfCols;
+        const uint32_t taddr = tmem_base + lane_off + kAccCol0 + as * kBN + half * kHalfCols;
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
         tmem_ld_wait(va);
@@ -679,7 +717,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (lane < 16) reinterpret_cast<float4*>(wbias)[lane] = bias_pre;
           __syncwarp();
           if (lane < 16) {
-            const int64_t nj = c == 0 ? j0 + 64 : next_j0;
+            const int64_t nj = c + 2 < kHalfCols / 32 ? j0 + (c + 2) * 32 : next_j0;
             bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + nj) + lane);
           }
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
@@ -729,11 +767,11 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 // ------------------------------------------------------------------------------ launch helper
 // Launches one instance with a thread-block-cluster dimension of kC (1 = plain launch).
-template <typename Epi, bool kRes, int kC, bool kPair = false>
+template <typename Epi, bool kRes, int kC, bool kPair = false, int kBN = BN, bool kTS = false>
 int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid,
                     cudaStream_t s) {
-  using L = SmemLayout<kRes, kPair>;
-  auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair>;
+  using L = SmemLayout<kRes, kPair, kBN>;
+  auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair, kBN, kTS>;
   // the attribute is per function and per device: cheap, so set it on every launch
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
   if (e != cudaSuccess) return cuda_err(e);
@@ -779,7 +817,7 @@ int max_active_clusters() {
   return n;
 }
 
-// dispatch over (resident, cluster) for one epilogue
+// dispatch over (resident, cluster) for one epilogue (256-column tiles)
 template <typename Epi>
 int launch_epilogue(bool a_resident, int cluster, const CUtensorMap& tmA, const CUtensorMap& tmB,
                     const Params& p, int grid, cudaStream_t s, bool pair = false) {
