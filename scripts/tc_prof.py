@@ -75,7 +75,7 @@ def main():
     med = {k: statistics.median(r[k] for r in rows) for k in rows[0]} if rows else {}
     out = {"cfg": {"n": a.n, "m": m, "d": a.d, "precision": a.precision,
                    "skip_epilogue": os.environ.get("VTC_DBG_SKIP_EPILOGUE", "0"),
-                   "pair": os.environ.get("VTC_PAIR", "auto"), "ts": os.environ.get("VTC_TS", "1"),
+                   "pair": os.environ.get("VTC_PAIR", "auto"),
                    "cluster": os.environ.get("VTC_CLUSTER", "2")},
            "step_ms": statistics.median(ms), "floor_clk_per_tile": kp // 16 * 128, **med}
     if med:

@@ -546,6 +546,51 @@ def test_clip_loss_large_batch_tcgen05(cuda_dev):
         np.testing.assert_allclose(_np(col), p64["col_lse"], atol=tol * 50, rtol=0)
 
 
+def test_clip_loss_one_pass_column_sums_and_overflow_fallback(cuda_dev):
+    """The tcgen05 InfoNCE forward is ONE pass over the logits (row log-sum-exp online, column sums
+    against each column's positive logit).  A negative that beats its column's positive by more than
+    88 nats overflows that reference: the merge kernel notices and gates the transposed pass on --
+    results must still match fp64.  Also n = 16384 (64 row tiles x 64 column tiles) against an fp64
+    computation on the device."""
+    from vtc_b200 import _ffi, ops
+
+    # (a) launch count: one tensor-core pass does rows AND columns; the gated second pass exits at once
+    vis, txt = make_batch_pair(3000, 256, seed=5)
+    a, t = vis.to(cuda_dev), txt.to(cuda_dev)
+    loss, row, col, diag = ops.infonce_fwd(a, t, 50.0, "bf16")
+    p64 = O.clip_loss_parts64(O.bf16_round(vis), O.bf16_round(txt), 50.0)
+    np.testing.assert_allclose(_np(col), p64["col_lse"], atol=2e-3, rtol=0)
+    np.testing.assert_allclose(_np(row), p64["row_lse"], atol=2e-3, rtol=0)
+    # (b) overflow of the column reference -> device-side fallback
+    n, D, s = 2200, 128, 300.0
+    g = torch.Generator().manual_seed(3)
+    u = torch.nn.functional.normalize(torch.randn(1, D, generator=g), dim=1)
+    txt2 = torch.nn.functional.normalize(u + 0.05 * torch.randn(n, D, generator=g), dim=1)
+    vis2 = torch.nn.functional.normalize(u + 0.05 * torch.randn(n, D, generator=g), dim=1)
+    w = torch.nn.functional.normalize(torch.randn(1, D, generator=g), dim=1)
+    vis2[0] = torch.nn.functional.normalize(w - (w @ txt2[0]) * txt2[0:1], dim=1)  # positive logit ~ 0
+    for precision, tol in (("exact", 1e-4), ("bf16", 2e-2)):
+        loss, row, col, diag = ops.infonce_fwd(vis2.to(cuda_dev), txt2.to(cuda_dev), s, precision)
+        p64 = O.clip_loss_parts64(vis2, txt2, s)
+        assert np.isfinite(_np(col)).all() and np.isfinite(loss.item())
+        np.testing.assert_allclose(_np(col), p64["col_lse"], atol=tol * s, rtol=0)
+        np.testing.assert_allclose(_np(row), p64["row_lse"], atol=tol * s, rtol=0)
+        np.testing.assert_allclose(loss.item(), p64["loss"], rtol=tol, atol=tol)
+    # (c) n = 16384: forward (+ the saved statistics) against fp64 on the device
+    n, D, s = 16384, 512, 100.0
+    gen = torch.Generator(device=cuda_dev).manual_seed(11)
+    V = torch.nn.functional.normalize(torch.randn(n, D, generator=gen, device=cuda_dev), dim=1)
+    T = torch.nn.functional.normalize(V + 8.0 * torch.randn(n, D, generator=gen, device=cuda_dev) / D ** 0.5, dim=1)
+    loss, row, col, diag = ops.infonce_fwd(V, T, s, "exact")
+    sim = s * (V.double() @ T.double().t())
+    want_row = torch.logsumexp(sim, dim=1)
+    want_col = torch.logsumexp(sim, dim=0)
+    want = 0.5 * ((want_row - sim.diag()).mean() + (want_col - sim.diag()).mean())
+    np.testing.assert_allclose(_np(row), _np(want_row), atol=1e-4 * s, rtol=0)
+    np.testing.assert_allclose(_np(col), _np(want_col), atol=1e-4 * s, rtol=0)
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=1e-4)
+
+
 def test_clip_loss_backward_and_dense_sim(cuda_dev, golden):
     from vtc_b200.model import LazySim, clip_loss
 

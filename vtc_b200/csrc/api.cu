@@ -236,10 +236,8 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.dgt = dgt, p.qq = qq, p.max_sq_bits = &w.scalars[0];
   p.guard_rel = guard_rel_for(precision, o.Kp), p.metric_l2 = metric == VTC_METRIC_L2 ? 1 : 0;
   p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_seg_count = &w.scalars[64];
-  // K' <= 512: the query tile lives in tensor memory (one CTA per SM, 128-column tiles)
-  const bool ts = p.num_kb <= 8 && tc::rank_ts_enabled();
-  tc::Plan pl = ts ? tc::plan_tiles(p, 64, 1, 8, 128) : tc::plan_tiles(p, 64, tc::choose_cluster(N, M));
-  pl.ts = ts;
+  // (rank counts are additive over gallery ranges: the last round of work items is balanced)
+  tc::Plan pl = tc::plan_tiles(p, 64, tc::choose_cluster(N, M), 8, tc::BN, true);
   if (pl.grid > 256) return VTC_ERR_UNSUPPORTED_SHAPE;
   p.amb_seg_cap = (unsigned int)(w.amb_cap / (size_t)pl.grid);
   CUtensorMap tmA, tmB;
@@ -403,6 +401,13 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   return launch_topk_brute_rows(a, s);
 }
 
+// Tile width of a dense product: 256 gallery rows per tile unless that leaves more than half of
+// the SMs without a tile (the skinny projections of the CAM: 1536 x 512 outputs = 24 tiles).
+int store_tile_width(int64_t rows, int64_t cols) {
+  const int64_t tiles = ceil_div<int64_t>(rows, tc::BM) * ceil_div<int64_t>(cols, tc::BN);
+  return tiles * 2 <= kNumSMs ? 128 : tc::BN;
+}
+
 // --------------------------------------------------------------------------- dense TC products
 // out[N,M] = act(scale * A B^T + bias) + residual, fp32 in/out.
 struct GemmWs {
@@ -442,39 +447,39 @@ int gemm_store_impl(const void* A, const void* B, int64_t N, int64_t M, int D, i
   VTC_RETURN_IF_ERROR(launch_fill_bias(g.bias, bias, M, round_up<int64_t>(M, tc::BN), 0.f, s));
   p.col_bias = g.bias, p.scale_ptr = scale_ptr, p.scale = 1.f;
   p.out = out, p.ldo = ldo, p.residual = residual, p.act = act;
-  const tc::Plan pl = tc::plan_tiles(p, 64, 1, 1);
+  const tc::Plan pl = tc::plan_tiles(p, 64, 1, 1, store_tile_width(N, M));
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opA, N, o.Kp, o.Kp, tc::BM, &tmA));
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opB, M, o.Kp, o.Kp, tc::BN, &tmB));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(g.opB, M, o.Kp, o.Kp, pl.bn, &tmB));
   return tc::launch_sim_tc(tc::EPI_STORE, p.num_kb <= 8, pl, tmA, tmB, p, s);
 }
 
 // ------------------------------------------------------------------------------------- InfoNCE
 struct NceWs {
-  __nv_bfloat16 *a_as_a, *b_as_b, *b_as_a, *a_as_b;
+  __nv_bfloat16 *opA, *opB;  // A as query-side operand, B as gallery-side operand
   float2 *part_row, *part_col;
   float* diag_raw;
-  float* bias;  // zeros, -inf padding
+  float* bias;     // zeros, -inf padding
+  float* col_ref;  // per-column reference of the one-pass column sums (+inf padding)
+  float* col_part; // [q_tiles * 4, npad] partial column sums
+  unsigned int* flag;
 };
 constexpr int kNceMaxSplits = 8;
 constexpr int64_t kNceSmallMax = 2048;
 NceWs carve_nce(Workspace& ws, int64_t n, int D, int dtype, int precision) {
   const OperandPlan o = plan_operands(D, dtype, precision);
+  const int64_t npad = round_up<int64_t>(n, tc::BN);
   NceWs w;
   memset(&w, 0, sizeof(w));
-  w.a_as_a = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
-  w.b_as_b = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
-  if (o.split) {
-    w.b_as_a = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
-    w.a_as_b = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
-  } else {
-    w.b_as_a = w.b_as_b;
-    w.a_as_b = w.a_as_a;
-  }
+  w.opA = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
+  w.opB = ws.take<__nv_bfloat16>((size_t)n * o.Kp);
   w.part_row = ws.take<float2>((size_t)2 * kNceMaxSplits * n);
   w.part_col = ws.take<float2>((size_t)2 * kNceMaxSplits * n);
   w.diag_raw = ws.take<float>(n);
-  w.bias = ws.take<float>(round_up<int64_t>(n, tc::BN));
+  w.bias = ws.take<float>(npad);
+  w.col_ref = ws.take<float>(npad);
+  w.col_part = ws.take<float>((size_t)ceil_div<int64_t>(n, tc::BM) * 4 * npad);
+  w.flag = ws.take<unsigned int>(64);
   return w;
 }
 
@@ -487,7 +492,8 @@ int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, 
   if (n > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
   // training-sized batches are launch-latency bound: one fused SIMT launch (infonce_small.cu);
   // larger ones stream through the tcgen05 kernel with the online-LSE epilogue
-  if (n <= kNceSmallMax && !getenv("VTC_INFONCE_FORCE_TC"))
+  const bool force_tc = getenv("VTC_INFONCE_FORCE_TC") != nullptr;  // test knob (tests/ only)
+  if (n <= kNceSmallMax && !force_tc)
     return launch_infonce_small(A, B, n, D, dtype == VTC_BF16, precision == VTC_PREC_BF16, scale,
                                 loss, row_lse, col_lse, diag, wsp, ws_bytes, s);
   Workspace ws(wsp, ws_bytes);
@@ -495,32 +501,49 @@ int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, 
   if (!ws.ok()) return VTC_ERR_WORKSPACE;
   const OperandPlan o = plan_operands(D, dtype, precision);
   const bool in_bf16 = dtype == VTC_BF16;
-  const int ma = o.split ? PREP_SPLIT_A : PREP_PLAIN, mb = o.split ? PREP_SPLIT_B : PREP_PLAIN;
-  VTC_RETURN_IF_ERROR(launch_prep_operand(A, in_bf16, n, D, D, ma, w.a_as_a, o.Kp, s));
-  VTC_RETURN_IF_ERROR(launch_prep_operand(B, in_bf16, n, D, D, mb, w.b_as_b, o.Kp, s));
-  if (o.split) {
-    VTC_RETURN_IF_ERROR(launch_prep_operand(B, in_bf16, n, D, D, ma, w.b_as_a, o.Kp, s));
-    VTC_RETURN_IF_ERROR(launch_prep_operand(A, in_bf16, n, D, D, mb, w.a_as_b, o.Kp, s));
-  }
-  VTC_RETURN_IF_ERROR(launch_fill_bias(w.bias, nullptr, n, round_up<int64_t>(n, tc::BN), -INFINITY, s));
-  for (int dir = 0; dir < 2; ++dir) {
-    tc::Params p;
-    memset(&p, 0, sizeof(p));
-    p.N = n, p.M = n, p.num_kb = o.Kp / tc::BK;
-    p.scale_ptr = scale, p.scale = 1.4426950408889634f;  // logits in log2 units
-    p.col_bias = w.bias;
-    p.lse_part = dir == 0 ? w.part_row : w.part_col;
-    p.diag = dir == 0 ? w.diag_raw : nullptr;
-    p.diag_offset = 0;
-    const tc::Plan pl = tc::plan_tiles(p, kNceMaxSplits, 1);
-    CUtensorMap tmA, tmB;
-    VTC_RETURN_IF_ERROR(
-        tc::make_operand_tmap(dir == 0 ? w.a_as_a : w.b_as_a, n, o.Kp, o.Kp, tc::BM, &tmA));
-    VTC_RETURN_IF_ERROR(
-        tc::make_operand_tmap(dir == 0 ? w.b_as_b : w.a_as_b, n, o.Kp, o.Kp, tc::BN, &tmB));
-    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_LSE, p.num_kb <= 8, pl, tmA, tmB, p, s));
-    VTC_RETURN_IF_ERROR(
-        launch_lse_merge(p.lse_part, 2 * p.g_splits, n, dir == 0 ? row_lse : col_lse, s));
+  const int64_t npad = round_up<int64_t>(n, tc::BN);
+  cudaError_t e = cudaMemsetAsync(w.flag, 0, 64 * sizeof(unsigned int), s);
+  if (e != cudaSuccess) return cuda_err(e);
+  VTC_RETURN_IF_ERROR(launch_prep_operand(A, in_bf16, n, D, D, o.split ? PREP_SPLIT_A : PREP_PLAIN,
+                                          w.opA, o.Kp, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(B, in_bf16, n, D, D, o.split ? PREP_SPLIT_B : PREP_PLAIN,
+                                          w.opB, o.Kp, s));
+  VTC_RETURN_IF_ERROR(launch_fill_bias(w.bias, nullptr, n, npad, -INFINITY, s));
+  VTC_RETURN_IF_ERROR(launch_nce_colref(w.opA, w.opB, n, npad, o.Kp, scale, w.col_ref, s));
+  // ONE pass over the logits: online row log-sum-exp, diagonal, and the column sums against the
+  // per-column reference (model/loss.py:21 evaluates cross_entropy on sim and on sim.t())
+  tc::Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = n, p.M = n, p.num_kb = o.Kp / tc::BK;
+  p.scale_ptr = scale, p.scale = 1.4426950408889634f;  // logits in log2 units
+  p.col_bias = w.bias;
+  p.lse_part = w.part_row, p.diag = w.diag_raw, p.diag_offset = 0;
+  p.col_ref = w.col_ref, p.col_part = w.col_part, p.col_ld = npad;
+  tc::Plan pl = tc::plan_tiles(p, kNceMaxSplits, 1);
+  CUtensorMap tmA, tmB;
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opA, n, o.Kp, o.Kp, tc::BM, &tmA));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opB, n, o.Kp, o.Kp, tc::BN, &tmB));
+  VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_LSE, p.num_kb <= 8, pl, tmA, tmB, p, s));
+  VTC_RETURN_IF_ERROR(launch_lse_merge(w.part_row, 2 * p.g_splits, n, row_lse, s));
+  VTC_RETURN_IF_ERROR(launch_nce_col_merge(w.col_part, p.q_tiles * 4, npad, w.col_ref, n, col_lse,
+                                           &w.flag[0], s));
+  // fallback, gated on the device (launches that exit at once unless a column sum overflowed): the
+  // transposed product with the online row statistics.  The split operands need no second
+  // preparation: [hi|lo|hi] . [hi|hi|lo] multiplies the same three term pairs with the roles swapped.
+  {
+    tc::Params q;
+    memset(&q, 0, sizeof(q));
+    q.N = n, q.M = n, q.num_kb = o.Kp / tc::BK;
+    q.scale_ptr = scale, q.scale = 1.4426950408889634f;
+    q.col_bias = w.bias;
+    q.lse_part = w.part_col;
+    q.run_flag = &w.flag[0];
+    tc::Plan pl2 = tc::plan_tiles(q, kNceMaxSplits, 1);
+    CUtensorMap tmA2, tmB2;
+    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opB, n, o.Kp, o.Kp, tc::BM, &tmA2));
+    VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.opA, n, o.Kp, o.Kp, tc::BN, &tmB2));
+    VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_LSE, q.num_kb <= 8, pl2, tmA2, tmB2, q, s));
+    VTC_RETURN_IF_ERROR(launch_lse_merge(w.part_col, 2 * q.g_splits, n, col_lse, s, &w.flag[0]));
   }
   return launch_infonce_loss(row_lse, col_lse, w.diag_raw, scale, n, diag, loss, s);
 }
@@ -553,10 +576,12 @@ int linear_prepared(const __nv_bfloat16* Xop, const void* prepared, const float*
   p.scale = 1.f;
   p.out = Y, p.ldo = out_f, p.residual = residual, p.act = act;
   p.out_op = Yop, p.out_op_kp = Yop_kp, p.out_op_split = o.split ? 1 : 0;
-  const tc::Plan pl = tc::plan_tiles(p, 64, 1, 1);
+  // skinny products (few output columns): 128-column tiles put twice as many SMs to work
+  const int bn = store_tile_width(rows, out_f);
+  const tc::Plan pl = tc::plan_tiles(p, 64, 1, 1, bn);
   CUtensorMap tmA, tmB;
   VTC_RETURN_IF_ERROR(tc::make_operand_tmap(Xop, rows, o.Kp, o.Kp, tc::BM, &tmA));
-  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(prepared, out_f, o.Kp, o.Kp, tc::BN, &tmB));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(prepared, out_f, o.Kp, o.Kp, pl.bn, &tmB));
   return tc::launch_sim_tc(tc::EPI_STORE, p.num_kb <= 8, pl, tmA, tmB, p, s);
 }
 

@@ -168,26 +168,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc]: A is read from tensor memory (lane = row, 8 columns of packed
-// bf16 pairs per K16 step); issued by ONE thread.
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n"
-      :
-      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// shared memory (matrix descriptor, 128 rows x 32 bytes) -> tensor memory (128 lanes x 8 columns);
-// issued by ONE thread, ordered with the tcgen05.mma / tcgen05.cp issued before and after it.
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t desc_src) {
-  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(desc_src)
-               : "memory");
-}
 // mbarrier arrives when all tcgen05 ops issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

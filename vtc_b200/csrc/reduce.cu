@@ -10,8 +10,10 @@
 namespace vtc {
 
 // ------------------------------------------------------------------------------------- InfoNCE
+// run_flag (nullable): the launch does nothing unless *run_flag != 0 (fallback pass)
 __global__ void lse_merge_kernel(const float2* __restrict__ part, int splits, int64_t n,
-                                 float* __restrict__ lse) {
+                                 float* __restrict__ lse, const unsigned int* __restrict__ run_flag) {
+  if (run_flag && *run_flag == 0u) return;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   float m = -INFINITY;
@@ -22,6 +24,58 @@ __global__ void lse_merge_kernel(const float2* __restrict__ part, int splits, in
     if (p.x > -INFINITY) l += p.y * exp2f(p.x - m);
   }
   lse[t] = 0.6931471805599453f * (m + log2f(l));
+}
+
+// Reference of column j for the one-pass column sums: its own positive logit in log2 units,
+// ref[j] = scale * log2(e) * <opA_j, opB_j> over the bf16 operand rows (plain, or the 3-term split
+// [hi|hi|lo].[hi|lo|hi]); +inf on the padding columns j >= n.  One warp per row.
+__global__ void __launch_bounds__(256)
+nce_colref_kernel(const __nv_bfloat16* __restrict__ opA, const __nv_bfloat16* __restrict__ opB,
+                  int64_t n, int64_t npad, int Kp, const float* __restrict__ scale_ptr,
+                  float* __restrict__ ref) {
+  const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= npad) return;
+  const int lane = threadIdx.x & 31;
+  if (j >= n) {
+    if (lane == 0) ref[j] = INFINITY;
+    return;
+  }
+  const uint4* a = reinterpret_cast<const uint4*>(opA + j * Kp);
+  const uint4* b = reinterpret_cast<const uint4*>(opB + j * Kp);
+  float acc = 0.f;
+  for (int k = lane; k < Kp / 8; k += 32) {  // Kp % 64 == 0: whole 16-byte groups
+    const uint4 ua = __ldg(a + k), ub = __ldg(b + k);
+    const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc = fmaf(__uint_as_float(wa[i] << 16), __uint_as_float(wb[i] << 16), acc);
+      acc = fmaf(__uint_as_float(wa[i] & 0xffff0000u), __uint_as_float(wb[i] & 0xffff0000u), acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) ref[j] = *scale_ptr * 1.4426950408889634f * acc;
+}
+
+// col_lse[j] = ln2 * (ref[j] + log2(sum over the partial rows of col_part)); a column whose sum is
+// not a positive finite number (a negative pair beat the positive one by more than 2^127) raises
+// *flag, which gates the second pass on.
+__global__ void nce_col_merge_kernel(const float* __restrict__ col_part, int parts, int64_t ld,
+                                     const float* __restrict__ ref, int64_t n,
+                                     float* __restrict__ col_lse, unsigned int* __restrict__ flag) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // fixed order, four independent chains
+  int p = 0;
+  for (; p + 4 <= parts; p += 4) {
+    s0 += col_part[(int64_t)p * ld + j];
+    s1 += col_part[(int64_t)(p + 1) * ld + j];
+    s2 += col_part[(int64_t)(p + 2) * ld + j];
+    s3 += col_part[(int64_t)(p + 3) * ld + j];
+  }
+  for (; p < parts; ++p) s0 += col_part[(int64_t)p * ld + j];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (!(s > 0.f && s < INFINITY)) *flag = 1u;
+  col_lse[j] = 0.6931471805599453f * (ref[j] + log2f(s));
 }
 
 __global__ void __launch_bounds__(1024)
@@ -47,9 +101,28 @@ infonce_loss_kernel(const float* __restrict__ row_lse, const float* __restrict__
   }
 }
 
-int launch_lse_merge(const float2* part, int splits, int64_t n, float* lse, cudaStream_t s) {
+int launch_lse_merge(const float2* part, int splits, int64_t n, float* lse, cudaStream_t s,
+                     const unsigned int* run_flag) {
   if (n == 0) return VTC_OK;
-  lse_merge_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, s>>>(part, splits, n, lse);
+  lse_merge_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, s>>>(part, splits, n, lse, run_flag);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_nce_colref(const __nv_bfloat16* opA, const __nv_bfloat16* opB, int64_t n, int64_t npad,
+                      int Kp, const float* scale_ptr, float* ref, cudaStream_t s) {
+  if (npad == 0) return VTC_OK;
+  nce_colref_kernel<<<(unsigned)ceil_div<int64_t>(npad, 8), 256, 0, s>>>(opA, opB, n, npad, Kp,
+                                                                        scale_ptr, ref);
+  VTC_LAUNCH_CHECK();
+  return VTC_OK;
+}
+
+int launch_nce_col_merge(const float* col_part, int parts, int64_t ld, const float* ref, int64_t n,
+                         float* col_lse, unsigned int* flag, cudaStream_t s) {
+  if (n == 0) return VTC_OK;
+  nce_col_merge_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, s>>>(col_part, parts, ld, ref, n,
+                                                                          col_lse, flag);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }

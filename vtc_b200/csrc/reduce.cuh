@@ -7,7 +7,15 @@
 namespace vtc {
 
 // row_lse[t] = ln2 * (max + log2(sum)) merged over `splits` partials [splits, n]
-int launch_lse_merge(const float2* part, int splits, int64_t n, float* lse, cudaStream_t s);
+// (run_flag != NULL: the launch does nothing unless *run_flag != 0)
+int launch_lse_merge(const float2* part, int splits, int64_t n, float* lse, cudaStream_t s,
+                     const unsigned int* run_flag = nullptr);
+// one-pass column log-sum-exp of the symmetric loss (LseEpi in sim_tc_kernel.cuh): per-column
+// reference = the positive logit, and the merge of the per-(query tile, lane quarter) partial sums
+int launch_nce_colref(const __nv_bfloat16* opA, const __nv_bfloat16* opB, int64_t n, int64_t npad,
+                      int Kp, const float* scale_ptr, float* ref, cudaStream_t s);
+int launch_nce_col_merge(const float* col_part, int parts, int64_t ld, const float* ref, int64_t n,
+                         float* col_lse, unsigned int* flag, cudaStream_t s);
 // loss = 0.5 * (mean(row_lse - diag) + mean(col_lse - diag)); diag = scale * diag_raw (written back)
 int launch_infonce_loss(const float* row_lse, const float* col_lse, const float* diag_raw,
                         const float* scale_ptr, int64_t n, float* diag_out, float* loss,

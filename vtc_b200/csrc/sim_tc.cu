@@ -13,8 +13,6 @@ namespace tc {
 
 int launch_rank(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
-int launch_rank_ts(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid,
-                   cudaStream_t s);
 int launch_topk(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
                 const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t s);
 int launch_lse(bool a_resident, const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p,
@@ -123,22 +121,21 @@ int debug_prof_read(unsigned long long* out, int max_words) {
   return cuda_err(e);
 }
 
-// Experiment switch of round 2 (VTC_TS=0 turns it off): the rank kernel with the query tile in
-// tensor memory.
-bool rank_ts_enabled() {
-  static const int on = []() {
-    const char* e = getenv("VTC_TS");
-    return e && *e ? atoi(e) : 1;
-  }();
-  return on != 0;
+// Sub-ranges the items of the last (partial) round are cut into: one per idle cluster, at least two
+// tiles each (every sub-range pays ~1 tile-time to swap the resident query tile).
+static int tail_parts_for(int rem, int units, int tps, bool balance) {
+  if (!balance || rem <= 0) return 1;
+  int parts = units / rem;
+  if (parts > tps / 2) parts = tps / 2;
+  return parts < 1 ? 1 : parts;
 }
 
-Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split, int bn) {
+Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split, int bn,
+                bool balance_tail) {
   Plan pl;
   pl.cluster = cluster < 1 ? 1 : cluster;
   pl.pair = pl.cluster == 2 && use_pair(p.num_kb);
   pl.bn = bn == 128 ? 128 : BN;
-  pl.ts = false;
   min_tiles_per_split *= BN / pl.bn;
   static const int skip_epi = []() {
     const char* e = getenv("VTC_DBG_SKIP_EPILOGUE");
@@ -150,26 +147,32 @@ Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split,
   p.g_tiles = (int)ceil_div<int64_t>(p.M, pl.bn);
   const int units = pl.cluster > 1 ? active_clusters(pl.cluster) : kNumSMs;  // co-resident clusters
   const int q_groups = ceil_div(p.q_tiles, pl.cluster);
-  // Items are dealt round-robin to the co-resident clusters, so the cost is ceil(items / units)
-  // rounds of tiles_per_split tiles (+ ~1 tile-time to swap the resident query tile).  Pick the
-  // split count with the best useful / occupied tile-slot ratio, keeping >= min_tiles_per_split
-  // tiles per item (8 for the streaming epilogues, 1 for small dense products).
+  // Items are dealt round-robin to the co-resident clusters: items / units full rounds of
+  // tiles_per_split tiles (+ ~1 tile-time to swap the resident query tile) and, if items are left,
+  // one more round -- of whole items, or (balance_tail) of sub-ranges that give every cluster a share.
+  // Pick the split count with the lowest cost, keeping >= min_tiles_per_split tiles per item (8 for
+  // the streaming epilogues, 1 for small dense products).
   const int g_tiles = p.g_tiles > 0 ? p.g_tiles : 1;
   int best = 1;
-  double best_eff = 0.0;
+  double best_cost = 0.0;
   for (int s = 1; s <= max_splits && s <= g_tiles; ++s) {
     const int tps = ceil_div(g_tiles, s);
     if (s > 1 && tps < min_tiles_per_split) break;
     const int64_t items = (int64_t)q_groups * ceil_div(g_tiles, tps);
-    const int64_t rounds = ceil_div<int64_t>(items, units);
-    const double eff =
-        (double)p.q_tiles * g_tiles / ((double)rounds * units * pl.cluster * (tps + 1));
-    if (eff > best_eff + 1e-9) best_eff = eff, best = s;
+    const int64_t full = items / units;
+    const int rem = (int)(items % units);
+    double cost = (double)full * (tps + 1);
+    if (rem) cost += ceil_div(tps, tail_parts_for(rem, units, tps, balance_tail)) + 1;
+    if (s == 1 || cost < best_cost - 1e-9) best_cost = cost, best = s;
   }
   p.tiles_per_split = ceil_div(g_tiles, best);
   p.g_splits = ceil_div(g_tiles, p.tiles_per_split);
   const int64_t items = (int64_t)q_groups * p.g_splits;
-  pl.grid = (int)(items < units ? items : units) * pl.cluster;
+  const int rem = (int)(items % units);
+  p.tail_parts = tail_parts_for(rem, units, p.tiles_per_split, balance_tail);
+  p.tail_first = p.tail_parts > 1 ? (int)(items - rem) : (int)items;
+  p.num_items = p.tail_first + (p.tail_parts > 1 ? rem * p.tail_parts : 0);
+  pl.grid = (int)(p.num_items < units ? p.num_items : units) * pl.cluster;
   return pl;
 }
 
@@ -227,12 +230,8 @@ int launch_sim_tc(int epilogue, bool a_resident, const Plan& pl, const CUtensorM
   int rc;
   switch (epilogue) {
     case EPI_RANK:
-      if (pl.ts)
-        rc = (a_resident && pl.cluster == 1 && pl.bn == 128) ? launch_rank_ts(tmA, tmB, p, pl.grid, s)
-                                                            : VTC_ERR_INVALID_ARG;
-      else
-        rc = pl.bn == BN ? launch_rank(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s)
-                         : VTC_ERR_INVALID_ARG;
+      rc = pl.bn == BN ? launch_rank(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s)
+                       : VTC_ERR_INVALID_ARG;
       break;
     case EPI_TOPK: rc = launch_topk(a_resident, pl.cluster, pl.pair, tmA, tmB, p, pl.grid, s); break;
     case EPI_LSE:

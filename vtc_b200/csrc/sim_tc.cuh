@@ -22,6 +22,9 @@ struct Params {
   int q_tiles, g_tiles;  // ceil(N/128), ceil(M/256)
   int g_splits;          // gallery is cut into g_splits contiguous tile ranges
   int tiles_per_split;
+  // work items: q_groups * g_splits, of which those from tail_first on (the last, partial round of
+  // the round-robin deal) are cut into tail_parts gallery sub-ranges each (1 = not cut)
+  int num_items, tail_first, tail_parts;
   // score = scale * acc + col_bias[j].  col_bias is REQUIRED and padded to a multiple of BN
   // entries; the padding holds the epilogue's neutral value (+inf rank/top-k, -inf LSE, 0 store).
   const float* col_bias;
@@ -48,6 +51,16 @@ struct Params {
   float2* lse_part;     // [2 * g_splits, N] running (max, sum) in log2 domain (part = 2*split + half)
   float* diag;          // [N] raw accumulator of column t + diag_offset (nullable)
   int64_t diag_offset;
+  // column log-sum-exp of the SAME pass (symmetric InfoNCE): per column j a reference col_ref[j]
+  // (log2 units; its own positive logit, +inf on padding columns) and, per (query tile, TMEM lane
+  // quarter), the partial sum over its 32 rows of 2^(logit - col_ref[j]) at
+  // col_part[(qt * 4 + quarter) * col_ld + j]   (nullable: row statistics only)
+  const float* col_ref;
+  float* col_part;
+  int64_t col_ld;
+  // any epilogue: when non-NULL and *run_flag == 0 the whole launch exits at once (device-side
+  // gating of a fallback pass, no host synchronisation)
+  const unsigned int* run_flag;
   // EPI_STORE
   float* out;  // [N, ldo] (nullable when only out_op is wanted)
   int64_t ldo;
@@ -80,14 +93,15 @@ struct Plan {
   int cluster;  // CTAs per cluster sharing each gallery tile
   int grid;     // CTAs to launch (multiple of cluster)
   bool pair;    // cluster == 2 run as a CTA pair: one M256 cta_group::2 MMA instead of multicast
-  int bn;       // gallery rows per tile: BN (256) or 128
-  bool ts;      // query tile in tensor memory (EPI_RANK, num_kb <= 8, cluster 1, bn 128)
+  int bn;       // gallery rows per tile: BN (256) or 128 (EPI_STORE only)
 };
 // fills q_tiles / g_tiles / g_splits / tiles_per_split for the given cluster size and tile width;
 // min_tiles_per_split is in 256-row tiles
-Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split = 8, int bn = BN);
-// EPI_RANK with the resident query tile in tensor memory instead of shared memory
-bool rank_ts_enabled();
+// balance_tail: cut the items of the last round so that every cluster gets a share (epilogues whose
+// results are additive over gallery ranges, i.e. EPI_RANK)
+Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split = 8, int bn = BN,
+                bool balance_tail = false);
+
 
 // a_resident: keep the whole 128 x K' query tile in shared memory (needs num_kb <= 8).
 // tmB must have been built with box_rows = pl.bn / pl.cluster.

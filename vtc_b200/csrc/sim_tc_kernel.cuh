@@ -49,22 +49,26 @@ constexpr int TMEM_COLS = 512;
 
 // kPair: the two CTAs of a cluster issue one M256 cta_group::2 MMA; each CTA stages only ITS half
 // of every gallery tile (16 KB), so the ring is twice as deep in the same shared memory.
-// kBN: gallery rows per tile (UMMA N, TMEM columns per accumulator stage): 256, or 128 for the
-// kernels that keep the query tile in TMEM (kTS) and for small dense products that need more CTAs.
+// kBN: gallery rows per tile (UMMA N, TMEM columns per accumulator stage): 256, or 128 for small
+// dense products that need more CTAs.
 // The ring takes what the resident query tile leaves of the 227 KB (at most 8 stages).
-template <bool kRes, bool kPair = false, int kBN = BN>
+// kEpiStage: bytes of warp-private staging each epilogue warp gets behind the bias buffers (StoreEpi
+// transposes its 32 x 32 blocks there so that global stores and residual loads are whole 128-byte rows).
+template <bool kRes, bool kPair = false, int kBN = BN, int kEpiStage = 0>
 struct SmemLayout {
   static constexpr int kResKb = MAX_RES_KB;
   static constexpr int kBBytes = (kBN * BK * 2) / (kPair ? 2 : 1);
   static constexpr int kStageBytes = kRes ? kBBytes : (A_TILE_BYTES + kBBytes);
   static constexpr int kResBytes = kRes ? kResKb * A_TILE_BYTES : 0;
-  static constexpr int kFit = (SMEM_LIMIT - 256 - EPI_WARPS_C * 64 * 4 - kResBytes) / kStageBytes;
+  static constexpr int kFit =
+      (SMEM_LIMIT - 256 - EPI_WARPS_C * (64 * 4 + kEpiStage) - kResBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kStagesOff = kResBytes;
   static constexpr int kBarOff = kStagesOff + kStages * kStageBytes;
   static constexpr int kBiasOff = kBarOff + 256;  // 8 epilogue warps x 64 floats
   static constexpr int kNumBars = 2 * kStages + kResKb + 1 + 2 + 2;
-  static constexpr int kTotal = kBiasOff + EPI_WARPS * 64 * 4;
+  static constexpr int kEpiStageOff = kBiasOff + EPI_WARPS * 64 * 4;
+  static constexpr int kTotal = kEpiStageOff + EPI_WARPS * kEpiStage;
   static_assert(kStages >= 3, "ring too shallow");
   static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
   static_assert(kTotal <= SMEM_LIMIT, "exceeds 227 KB of shared memory");
@@ -93,6 +97,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 constexpr int RANK_GROUP = 8;  // columns re-checked together when any of them is in the guard band
 
 struct RankEpi {
+  static constexpr int kStageBytes = 0;
+  __device__ __forceinline__ void bind_stage(float*) {}
   float lo, hi;
   int cnt;
   int gtc;  // ground-truth column of this row (launch-local), or a value no group can contain
@@ -169,15 +175,30 @@ struct RankEpi {
   }
 };
 
+// Online row log-sum-exp (running max + rescaled sum, log2 domain) and -- in the SAME pass -- the
+// column sums of the symmetric loss: sim^T is never formed and the product is not run a second time
+// (model/loss.py:21 calls cross_entropy on sim and on sim.t()).  Columns cannot keep a running max
+// across the row tiles of different CTAs, so every column j is summed against a fixed reference, its
+// own positive logit col_ref[j]: the positive pair contributes 2^~0, so the sum cannot underflow, and
+// it overflows only if some negative beats the positive by > 88 nats (caught by the merge kernel,
+// which then gates a second pass on).  A warp holds a 32 x 32 block of 2^(x - ref): a butterfly
+// transpose-reduce (31 shuffles) leaves lane i with the block's sum of column i, written once per
+// (query tile, lane quarter, column) -- deterministic, no atomics.
 struct LseEpi {
+  static constexpr int kStageBytes = 0;
+  __device__ __forceinline__ void bind_stage(float*) {}
   float m, l, dv;
   int64_t t, jd;
+  float* cpart;  // this (query tile, lane quarter)'s row of col_part, or NULL
+  bool rowvalid;
   __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int) {
     t = t_;
     m = -INFINITY;
     l = 0.f;
     dv = nanf("");
     jd = p.diag ? t + p.diag_offset : -1;
+    rowvalid = t < p.N;
+    cpart = p.col_part ? p.col_part + ((t / BM) * 4 + ((t % BM) >> 5)) * p.col_ld : nullptr;
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
@@ -207,6 +228,30 @@ struct LseEpi {
       for (int i = 0; i < 32; ++i)
         if (i == sel) dv = __uint_as_float(v[i]);
     }
+    if (cpart) {
+      float e[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(p.col_ref + jbase) + i);
+        // zero-filled tile rows beyond N must not count; padding columns have x = -inf, ref = +inf
+        e[4 * i + 0] = rowvalid ? ex2_approx(x[4 * i + 0] - r.x) : 0.f;
+        e[4 * i + 1] = rowvalid ? ex2_approx(x[4 * i + 1] - r.y) : 0.f;
+        e[4 * i + 2] = rowvalid ? ex2_approx(x[4 * i + 2] - r.z) : 0.f;
+        e[4 * i + 3] = rowvalid ? ex2_approx(x[4 * i + 3] - r.w) : 0.f;
+      }
+      const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;  // this lane keeps the upper half of its values
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+          const float send = up ? e[k] : e[k + o];
+          const float keep = up ? e[k + o] : e[k];
+          e[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      cpart[jbase + lane] = e[0];  // lane i: column jbase + i, summed over this warp's 32 rows
+    }
   }
   __device__ __forceinline__ void end_item(const Params& p, int split) {
     if (t < p.N) {
@@ -216,32 +261,37 @@ struct LseEpi {
   }
 };
 
+// Materialising epilogue.  A thread owns one tile ROW, so a warp's registers hold a 32 x 32 block
+// row-per-lane, while memory wants whole 128-byte rows per instruction: the block goes through a
+// warp-private 4 KB shared-memory tile (128-bit accesses, XOR-swizzled by row so that both the
+// row-per-lane and the transposed accesses are bank-conflict free) on its way out -- and the residual
+// on its way in.  Straight from registers a float4 store touched 32 different rows, i.e. 32
+// transactions per instruction instead of 4.
 struct StoreEpi {
-  int64_t t;
-  __device__ __forceinline__ void begin_item(const Params&, int64_t t_, int) { t = t_; }
-  // 8 floats -> 8 bf16 (RN) packed in a uint4; with `lo` the residuals x - bf16(x) instead
-  static __device__ __forceinline__ uint4 pack8(const float* y, bool lo) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat16 a = __float2bfloat16_rn(y[2 * i]), b = __float2bfloat16_rn(y[2 * i + 1]);
-      if (lo) {
-        a = __float2bfloat16_rn(y[2 * i] - __bfloat162float(a));
-        b = __float2bfloat16_rn(y[2 * i + 1] - __bfloat162float(b));
-      }
-      w[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+  static constexpr int kStageBytes = 32 * 32 * 4;
+  int64_t t, t0w;  // this thread's row, first row of the warp's 32-row block
+  float* st;       // warp-private 32 x 32 fp32 staging tile
+  __device__ __forceinline__ void bind_stage(float* s) { st = s; }
+  __device__ __forceinline__ void begin_item(const Params&, int64_t t_, int) {
+    t = t_;
+    t0w = t_ - (threadIdx.x & 31);
+  }
+  // float4 slot q (0..7) of staged row r lives at r * 32 + 4 * (q ^ (r & 7))
+  static __device__ __forceinline__ int slot(int r, int q) { return r * 32 + 4 * (q ^ (r & 7)); }
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) |
+           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
                                         unsigned int*) {
-    if (t >= p.N) return;
-    const float* r = p.residual ? p.residual + t * p.ldo + jbase : nullptr;
-    const bool full = jbase + 32 <= p.M;
+    const int lane = threadIdx.x & 31;
+    if (t0w >= p.N || jbase >= p.M) return;  // warp-uniform: nothing of this block is in range
+    const bool full = jbase + 32 <= p.M && t0w + 32 <= p.N;
     const bool vec = full && ((p.ldo & 3) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
-                     (!r || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+                     (!p.out || (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                     (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    const int rr = lane >> 3, q = lane & 7;  // transposed view: 4 rows x 8 float4 per instruction
     float y[32];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -254,26 +304,49 @@ struct StoreEpi {
         y[4 * i + e] = z;
       }
     }
-    if (r) {
+    if (p.residual) {
       if (vec) {
+        // whole 128-byte rows in, four rows per instruction; each lane then reads its own row
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 q = reinterpret_cast<const float4*>(r)[i];
-          y[4 * i] += q.x, y[4 * i + 1] += q.y, y[4 * i + 2] += q.z, y[4 * i + 3] += q.w;
+          const int r = 4 * i + rr;
+          const float4 x4 = __ldg(reinterpret_cast<const float4*>(p.residual + (t0w + r) * p.ldo + jbase) + q);
+          *reinterpret_cast<float4*>(st + slot(r, q)) = x4;
         }
-      } else {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x4 = *reinterpret_cast<const float4*>(st + slot(lane, i));
+          y[4 * i] += x4.x, y[4 * i + 1] += x4.y, y[4 * i + 2] += x4.z, y[4 * i + 3] += x4.w;
+        }
+      } else if (t < p.N) {
+        const float* r = p.residual + t * p.ldo + jbase;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (jbase + i < p.M) y[i] += r[i];
       }
     }
+    const bool ovec = p.out_op && full && ((p.M & 7) == 0) && ((p.out_op_kp & 7) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.out_op) & 15) == 0);
+    if ((p.out && vec) || ovec) {
+      __syncwarp();  // the residual reads of the staging tile are complete
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(st + slot(lane, i)) =
+            make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      __syncwarp();
+    }
     if (p.out) {
-      float* o = p.out + t * p.ldo + jbase;
       if (vec) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          reinterpret_cast<float4*>(o)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-      } else {
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + rr;
+          *reinterpret_cast<float4*>(p.out + (t0w + r) * p.ldo + jbase + 4 * q) =
+              *reinterpret_cast<const float4*>(st + slot(r, q));
+        }
+      } else if (t < p.N) {
+        float* o = p.out + t * p.ldo + jbase;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (jbase + i < p.M) o[i] = y[i];
@@ -281,20 +354,30 @@ struct StoreEpi {
     }
     if (p.out_op) {
       // the result as the query-side bf16 operand of the NEXT GEMM: [x] or the split [hi|hi|lo]
-      __nv_bfloat16* oo = p.out_op + t * (int64_t)p.out_op_kp + jbase;
-      const bool ovec = full && ((p.M & 7) == 0) && ((p.out_op_kp & 7) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.out_op) & 15) == 0);
       if (ovec) {
+        // 64-byte operand rows: 8 rows x 4 groups of 8 bf16 per instruction
+        const int r8 = lane >> 2, g8 = lane & 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint4 hi = pack8(y + 8 * i, false);
-          reinterpret_cast<uint4*>(oo)[i] = hi;
+          const int r = 8 * i + r8;
+          const float4 a4 = *reinterpret_cast<const float4*>(st + slot(r, 2 * g8));
+          const float4 b4 = *reinterpret_cast<const float4*>(st + slot(r, 2 * g8 + 1));
+          const float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+          const uint4 hi = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]),
+                                      pack2(f[6], f[7]));
+          __nv_bfloat16* oo = p.out_op + (t0w + r) * (int64_t)p.out_op_kp + jbase + 8 * g8;
+          *reinterpret_cast<uint4*>(oo) = hi;
           if (p.out_op_split) {
-            reinterpret_cast<uint4*>(oo + p.M)[i] = hi;
-            reinterpret_cast<uint4*>(oo + 2 * p.M)[i] = pack8(y + 8 * i, true);
+            float l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) l[e] = f[e] - __bfloat162float(__float2bfloat16_rn(f[e]));
+            *reinterpret_cast<uint4*>(oo + p.M) = hi;
+            *reinterpret_cast<uint4*>(oo + 2 * p.M) =
+                make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
           }
         }
-      } else {
+      } else if (t < p.N) {
+        __nv_bfloat16* oo = p.out_op + t * (int64_t)p.out_op_kp + jbase;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (jbase + i < p.M) {
@@ -319,6 +402,8 @@ struct StoreEpi {
 // score >= tau, which is what topk_select_kernel's completeness proof needs.  A row compacts only
 // O(log(M / 64)) times, so the per-column cost stays at one FFMA + one compare.
 struct TopkEpi {
+  static constexpr int kStageBytes = 0;
+  __device__ __forceinline__ void bind_stage(float*) {}
   float tau;
   int cnt;
   int64_t t;
@@ -422,24 +507,42 @@ struct TopkEpi {
 };
 
 // ------------------------------------------------------------------------------------- kernel
-// kTS: the resident query tile lives in TENSOR MEMORY.  Per work item its k-blocks are staged in
-// shared memory by TMA (as for kRes) and moved to TMEM columns [0, 4 K'/64 * 8) by tcgen05.cp; the
-// MMAs then read A from TMEM (tcgen05.mma [d], [a], b-desc) and shared memory only serves the gallery
-// stream: 4 KB instead of 12 KB of operand reads per 128 x 256 x 16 step, which is what the
-// shared-memory pipe (128 B/clk) was short of -- the SS kernel issues one M128 N256 K16 MMA per
-// ~150-175 clk instead of 128 (scripts/tc_prof.py).  The staging area is free again as soon as the
-// copies have retired, so the NEXT item's query tile is prefetched during the whole item.  TMEM:
-// 256 columns of A + two accumulator stages of kBN = 128 columns.
-template <typename Epi, bool kRes, int kC, bool kPair = false, int kBN = BN, bool kTS = false>
+// Work items.  Item i < tail_first is (query-tile group i % q_groups, gallery split i / q_groups):
+// tiles_per_split consecutive gallery tiles.  Items are dealt round-robin to the co-resident
+// clusters, so the last round would keep only (items mod clusters) of them busy for a whole item;
+// instead each item of that round is cut into tail_parts sub-ranges (Params::tail_first /
+// tail_parts, EPI_RANK only: its counts are additive over gallery ranges), one per idle cluster.
+struct Work {
+  int qg, split, t0, t1;
+};
+__device__ __forceinline__ Work decode_work(const Params& p, int item, int q_groups) {
+  int base = item, part = 0, parts = 1;
+  if (item >= p.tail_first) {
+    const int u = item - p.tail_first;
+    base = p.tail_first + u / p.tail_parts;
+    part = u % p.tail_parts;
+    parts = p.tail_parts;
+  }
+  Work w;
+  w.qg = base % q_groups;
+  w.split = base / q_groups;
+  w.t0 = w.split * p.tiles_per_split;
+  w.t1 = min(p.g_tiles, w.t0 + p.tiles_per_split);
+  if (parts > 1) {
+    const int len = w.t1 - w.t0, lo = w.t0;
+    w.t0 = lo + (int)(((long long)len * part) / parts);
+    w.t1 = lo + (int)(((long long)len * (part + 1)) / parts);
+  }
+  return w;
+}
+
+template <typename Epi, bool kRes, int kC, bool kPair = false, int kBN = BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const Params p) {
   static_assert(!kPair || kC == 2, "a CTA pair is a cluster of two");
   static_assert(kBN == 256 || kBN == 128, "tile widths built: 256 and 128 gallery rows");
-  static_assert(!kTS || (kRes && kBN == 128 && !kPair && kC == 1),
-                "A in TMEM: resident query tile, 128-column accumulators, one CTA");
-  using L = SmemLayout<kRes, kPair, kBN>;
-  constexpr uint32_t kAccCol0 = kTS ? 4 * MAX_RES_KB * 8 : 0;  // first accumulator column
+  using L = SmemLayout<kRes, kPair, kBN, Epi::kStageBytes>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* res_a = smem;
   uint8_t* stages = smem + L::kStagesOff;
@@ -455,6 +558,9 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // a gated fallback pass that is not needed: every CTA sees the same flag and leaves before any
+  // barrier, cluster or tensor-memory state exists
+  if (p.run_flag && *p.run_flag == 0u) return;
 
   if (threadIdx.x == 0) {
     *seg_count = 0;
@@ -499,7 +605,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int cluster_id = blockIdx.x / kC;
   const int num_clusters = gridDim.x / kC;
   const int q_groups = (p.q_tiles + kC - 1) / kC;
-  const int num_items = q_groups * p.g_splits;
+  const int num_items = p.num_items;  // incl. the sub-items of the balanced last round
   const int nkb = p.num_kb;
   constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
   // CTA pair: rank 0 issues the MMAs and owns the `full` / `a_full` / `tmem_empty` barriers; both
@@ -510,11 +616,12 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
-        const int qt = (item % q_groups) * kC + cta_rank, split = item / q_groups;
-        const int t0 = split * p.tiles_per_split;
-        const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const Work wk = decode_work(p, item, q_groups);
+        const int qt = wk.qg * kC + cta_rank, t0 = wk.t0, t1 = wk.t1;
+        if (t0 >= t1) continue;  // an empty sub-range: skipped by every role alike
         if (kRes) mbar_wait(a_empty, (it & 1) ^ 1);  // previous item's MMAs have drained
+        ++it;
         for (int tile = t0; tile < t1; ++tile) {
           for (int kb = 0; kb < nkb; ++kb) {
             if (kPair) {
@@ -566,10 +673,10 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       unsigned long long w_acc = 0, w_ld = 0, n_tiles = 0;
       const long long c_begin = prof ? clock64() : 0;
       const uint64_t g_begin = prof ? globaltimer_ns() : 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
-        const int split = item / q_groups;
-        const int t0 = split * p.tiles_per_split;
-        const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const Work wk = decode_work(p, item, q_groups);
+        const int t0 = wk.t0, t1 = wk.t1;
+        if (t0 >= t1) continue;
         for (int tile = t0; tile < t1; ++tile) {
           if (prof) {
             const long long c0 = clock64();
@@ -580,26 +687,9 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
           }
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + kAccCol0 + as * kBN;
-          if (kTS && tile == t0) {
-            // this item's query tile: shared memory -> TMEM, K16 slice by K16 slice (the same
-            // descriptors the SS kernel hands to the MMA as A).  tcgen05.cp and tcgen05.mma execute in
-            // issue order, so the previous item's MMAs have read the old tile before it is
-            // overwritten and this item's MMAs see the new one; the commit frees the staging area
-            // for the producer's prefetch of the next item's tile.
-            for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(&a_full[kb], it & 1);
-              tc_fence_after();
-              const uint64_t adesc = make_smem_desc_sw128(smem_u32(res_a + kb * A_TILE_BYTES));
-#pragma unroll
-              for (int k4 = 0; k4 < BK / 16; ++k4)
-                tmem_cp_128x256b(tmem_base + (uint32_t)((kb * 4 + k4) * 8),
-                                 desc_advance(adesc, k4 * 32));
-            }
-            umma_commit(a_empty);
-          }
+          const uint32_t d_tmem = tmem_base + as * kBN;
           for (int kb = 0; kb < nkb; ++kb) {
-            if (kRes && !kTS && tile == t0) mbar_wait(&a_full[kb], it & 1);
+            if (kRes && tile == t0) mbar_wait(&a_full[kb], it & 1);
             if (prof) {
               const long long c0 = clock64();
               mbar_wait(&full[stage], phase);
@@ -614,10 +704,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint64_t bdesc = make_smem_desc_sw128(smem_u32(st + (kRes ? 0 : A_TILE_BYTES)));
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
-              if (kTS)
-                umma_bf16_ts(d_tmem, tmem_base + (uint32_t)((kb * 4 + k4) * 8),
-                             desc_advance(bdesc, k4 * 32), idesc, (uint32_t)((kb | k4) != 0));
-              else if (kPair)
+              if (kPair)
                 umma_bf16_pair(d_tmem, desc_advance(adesc, k4 * 32), desc_advance(bdesc, k4 * 32),
                                idesc, (uint32_t)((kb | k4) != 0));
               else
@@ -641,12 +728,13 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           as ^= 1;
           if (as == 0) aphase ^= 1;
         }
-        if (kRes && !kTS) {
+        if (kRes) {
           if (kPair)
             umma_commit_pair(a_empty, kMask);
           else
             umma_commit(a_empty);
         }
+        ++it;
       }
       if (prof) {
         unsigned long long* o = p.dbg_prof + (size_t)blockIdx.x * 8;
@@ -672,21 +760,20 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     uint32_t as = 0, aphase = 0;
     Epi epi;
     float* wbias = reinterpret_cast<float*>(smem + L::kBiasOff) + (warp - EPI_WARP0) * 64;
+    epi.bind_stage(reinterpret_cast<float*>(smem + L::kEpiStageOff +
+                                            (warp - EPI_WARP0) * Epi::kStageBytes));
     // column bias, staged 64 columns at a time in this warp's private buffer; lanes 0..15 carry the
     // next 64 values in registers (prefetched one step ahead so the L2 latency is never exposed)
+    // (pre_j: the column bias_pre was fetched for; a wrong guess at an item boundary is re-fetched)
     float4 bias_pre = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cluster_id < num_items && lane < 16)
-      bias_pre = __ldg(reinterpret_cast<const float4*>(
-                           p.col_bias + (int64_t)(cluster_id / q_groups) * p.tiles_per_split * kBN +
-                           half * kHalfCols) +
-                       lane);
+    int64_t pre_j = -1;
     const bool eprof = p.dbg_prof != nullptr;
     unsigned long long e_wait = 0;
     const long long e_begin = eprof ? clock64() : 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
-      const int qt = (item % q_groups) * kC + cta_rank, split = item / q_groups;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(p.g_tiles, t0 + p.tiles_per_split);
+      const Work wk = decode_work(p, item, q_groups);
+      const int qt = wk.qg * kC + cta_rank, split = wk.split, t0 = wk.t0, t1 = wk.t1;
+      if (t0 >= t1) continue;
       epi.begin_item(p, (int64_t)qt * BM + row, 2 * split + half);
       for (int tile = t0; tile < t1; ++tile) {
         const int64_t j0 = (int64_t)tile * kBN + half * kHalfCols;
@@ -695,7 +782,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (tile + 1 >= t1) {
           const int nitem = item + num_clusters;
           next_j0 = nitem < num_items
-                        ? (int64_t)(nitem / q_groups) * p.tiles_per_split * kBN + half * kHalfCols
+                        ? (int64_t)decode_work(p, nitem, q_groups).t0 * kBN + half * kHalfCols
                         : 0;
         }
         if (eprof) {
@@ -706,7 +793,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           mbar_wait(&tmem_full[as], aphase);
         }
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_off + kAccCol0 + as * kBN + half * kHalfCols;
+        const uint32_t taddr = tmem_base + lane_off + as * kBN + half * kHalfCols;
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
         tmem_ld_wait(va);
@@ -714,12 +801,12 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int c = 0; c < kHalfCols / 32; c += 2) {
           // stage the bias of columns [32c, 32c + 64) and start fetching the following 64
           __syncwarp();
+          if (pre_j != j0 + c * 32 && lane < 16)  // first chunk of the launch, or a skipped item
+            bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + j0 + c * 32) + lane);
           if (lane < 16) reinterpret_cast<float4*>(wbias)[lane] = bias_pre;
           __syncwarp();
-          if (lane < 16) {
-            const int64_t nj = c + 2 < kHalfCols / 32 ? j0 + (c + 2) * 32 : next_j0;
-            bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + nj) + lane);
-          }
+          pre_j = c + 2 < kHalfCols / 32 ? j0 + (c + 2) * 32 : next_j0;
+          if (lane < 16) bias_pre = __ldg(reinterpret_cast<const float4*>(p.col_bias + pre_j) + lane);
           tmem_ld_32x32(taddr + (c + 1) * 32, vb);
           if (!p.dbg_skip_epilogue) epi.chunk(p, va, wbias, scale, j0 + c * 32, seg_count);
           tmem_ld_wait(vb);
@@ -767,11 +854,11 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 // ------------------------------------------------------------------------------ launch helper
 // Launches one instance with a thread-block-cluster dimension of kC (1 = plain launch).
-template <typename Epi, bool kRes, int kC, bool kPair = false, int kBN = BN, bool kTS = false>
+template <typename Epi, bool kRes, int kC, bool kPair = false, int kBN = BN>
 int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid,
                     cudaStream_t s) {
-  using L = SmemLayout<kRes, kPair, kBN>;
-  auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair, kBN, kTS>;
+  using L = SmemLayout<kRes, kPair, kBN, Epi::kStageBytes>;
+  auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair, kBN>;
   // the attribute is per function and per device: cheap, so set it on every launch
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
   if (e != cudaSuccess) return cuda_err(e);
@@ -796,7 +883,7 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params
 // how many clusters of kC CTAs of this kernel can be co-resident on the current device
 template <typename Epi, bool kRes, int kC, bool kPair = false>
 int max_active_clusters() {
-  using L = SmemLayout<kRes, kPair>;
+  using L = SmemLayout<kRes, kPair, BN, Epi::kStageBytes>;
   auto* kern = &sim_tc_kernel<Epi, kRes, kC, kPair>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess)
     return 0;

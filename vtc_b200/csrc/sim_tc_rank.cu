@@ -10,12 +10,6 @@ int launch_rank(bool a_resident, int cluster, bool pair, const CUtensorMap& tmA,
   return launch_epilogue<RankEpi>(a_resident, cluster, tmA, tmB, p, grid, s, pair);
 }
 
-// query tile in tensor memory: resident, one CTA per cluster, 128-column accumulators
-int launch_rank_ts(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid,
-                   cudaStream_t s) {
-  return launch_instance<RankEpi, true, 1, false, 128, true>(tmA, tmB, p, grid, s);
-}
-
 int max_active_clusters_rank(int cluster) {
   if (cluster == 4) return max_active_clusters<RankEpi, true, 4>();
   if (cluster == 2) return max_active_clusters<RankEpi, true, 2>();

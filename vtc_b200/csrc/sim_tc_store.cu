@@ -7,10 +7,12 @@ namespace tc {
 
 int launch_store(bool a_resident, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const Params& p, int grid, cudaStream_t s) {
+  // always the streamed kernel: these products have a tile or two per CTA, so a resident query tile
+  // buys nothing, and its shared memory is what holds the epilogue's transposing tiles
+  (void)a_resident;
   if (bn == 128)  // narrow tiles: twice the CTAs for the skinny products of the CAM
-    return a_resident ? launch_instance<StoreEpi, true, 1, false, 128>(tmA, tmB, p, grid, s)
-                      : launch_instance<StoreEpi, false, 1, false, 128>(tmA, tmB, p, grid, s);
-  return launch_epilogue_c1<StoreEpi>(a_resident, tmA, tmB, p, grid, s);
+    return launch_instance<StoreEpi, false, 1, false, 128>(tmA, tmB, p, grid, s);
+  return launch_instance<StoreEpi, false, 1>(tmA, tmB, p, grid, s);
 }
 
 }  // namespace tc
