@@ -158,7 +158,8 @@ def run_reference(a):
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "enforced.power.limit")
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
@@ -202,7 +203,7 @@ class ClockSampler:
         if not inside:
             inside = [ln for _, ln in lines]
             window = "warm-up + timed blocks (no sample arrived inside a timed block)"
-        sm, mx, power, reasons = [], [], [], set()
+        sm, mx, power, limit, reasons = [], [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in inside:
             f = [x.strip() for x in ln.split(",")]
@@ -217,9 +218,15 @@ class ClockSampler:
             for name, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+            try:
+                limit.append(float(f[9]))
+            except (IndexError, ValueError):
+                pass
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None,
+                "power_w_median": statistics.median(power) if power else None,
+                "power_limit_w": max(limit) if limit else None,
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 

@@ -295,6 +295,15 @@ int vtc_kernel_timer_read(double* total_ms, int* count);
  * VTC_ERR_INVALID_ARG when profiling is off. */
 int vtc_debug_prof_read(unsigned long long* out, int max_words);
 
+/* Profiling only: launch trace.  Between vtc_trace_begin(stream) and vtc_trace_end the library
+ * records one CUDA event on `stream` after every kernel it launches; vtc_trace_end synchronises,
+ * writes one line "<source file>:<line> <microseconds>" per launch into the HOST buffer (the gap
+ * to the previous event: the launch as it ran back to back in the stream, warm caches -- unlike
+ * ncu's serialised cold-cache times) and returns the number of launches (< 0: error).  Single
+ * stream, not thread-safe against concurrent library calls; off by default. */
+int vtc_trace_begin(vtc_stream_t stream);
+int vtc_trace_end(char* buf, size_t cap);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -81,3 +81,52 @@ def test_split_error_random_search_never_exceeds_the_band():
             x = q + np.float32(1e-4) * scale * rng.standard_normal((16, D)).astype(np.float32)
         worst = max(worst, rel_err(q, x).max())
     assert worst <= SPLIT_TERM
+
+
+# ---- the per-row bound the rank path uses since round 2 (csrc/sim_tc.cuh::rank_split_bound) -------
+def split_pieces(x):
+    """hi = bf16(x), lo = bf16(x - hi), e = x - hi - lo (each difference is exact in fp32)."""
+    hi = O.bf16_round(x)
+    r = (x - hi).astype(np.float32)
+    lo = O.bf16_round(r)
+    e = (r - lo).astype(np.float32)
+    return hi, lo, e
+
+
+def row_bound(q, x):
+    """|q| max|ex| + |lq| max|lx| + |eq| (max|x| + max|ex|) for every query row, in float64 from the
+    pieces themselves (the kernel computes the same norms in fp32 and rounds them up)."""
+    _, lq, eq = split_pieces(q)
+    _, lx, ex = split_pieces(x)
+    n = lambda a: np.linalg.norm(a.astype(np.float64), axis=1)  # noqa: E731
+    return n(q) * n(ex).max() + n(lq) * n(lx).max() + n(eq) * (n(x).max() + n(ex).max())
+
+
+@pytest.mark.parametrize("D", [64, 512, 768])
+def test_per_row_split_bound_holds_on_adversarial_and_random_rows(D):
+    rng = np.random.default_rng(100 + D)
+    cases = []
+    for value in (1.00385, 1.0038, 1.00389, 1.0116, 0.50192, 1.99):
+        base = np.sign(rng.standard_normal(D)).astype(np.float32)
+        q = adversarial_rows(rng, 24, D, value, base)
+        x = adversarial_rows(rng, 24, D, value, base)
+        x[0] = q[0]
+        cases.append((q, x))
+    for scale in (2.0 ** -5, 1.0, 37.0):
+        q = (rng.standard_normal((24, D)) * scale).astype(np.float32)
+        x = (rng.standard_normal((24, D)) * scale).astype(np.float32)
+        cases.append((q / np.linalg.norm(q, axis=1, keepdims=True).astype(np.float32), x))
+    tightest = np.inf
+    for q, x in cases:
+        exact = q.astype(np.float64) @ x.astype(np.float64).T
+        err = np.abs(split3_dot(q, x) - exact)
+        bound = row_bound(q, x)[:, None]
+        assert (err <= bound * (1 + 1e-12)).all()
+        norms = np.linalg.norm(q.astype(np.float64), axis=1)[:, None] * \
+            np.linalg.norm(x.astype(np.float64), axis=1).max()
+        tightest = min(tightest, (bound / norms).min())
+    # on ordinary rows the bound is an order of magnitude below the worst-case constant: that is
+    # what cuts the fp64 re-check of the exact mode
+    print(f"\n[guard band] D={D}: smallest per-row split bound {tightest:.2e} of |q| max|x| "
+          f"(constant {SPLIT_TERM:.2e})")
+    assert tightest < SPLIT_TERM / 5

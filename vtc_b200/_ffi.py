@@ -62,6 +62,8 @@ SIGNATURES = {
     "vtc_kernel_timer_enable": (c_int, [c_int]),
     "vtc_kernel_timer_read": (c_int, [POINTER(c_double), POINTER(c_int)]),
     "vtc_debug_prof_read": (c_int, [POINTER(c_uint64), c_int]),
+    "vtc_trace_begin": (c_int, [_P]),
+    "vtc_trace_end": (c_int, [ctypes.c_char_p, c_size_t]),
 }
 
 
@@ -148,3 +150,21 @@ def debug_prof_read(n_ctas: int = 148):
     buf = (c_uint64 * (8 * n_ctas))()
     check(load().vtc_debug_prof_read(buf, 8 * n_ctas), "vtc_debug_prof_read")
     return [tuple(int(buf[8 * i + j]) for j in range(8)) for i in range(n_ctas)]
+
+
+def trace_begin(stream: int = 0) -> None:
+    """Profiling aid: start recording one CUDA event per library launch on `stream` (a raw handle)."""
+    check(load().vtc_trace_begin(stream), "vtc_trace_begin")
+
+
+def trace_end(cap: int = 1 << 18):
+    """Stop the launch trace; returns [(source "file:line", microseconds)] in launch order."""
+    buf = ctypes.create_string_buffer(cap)
+    n = load().vtc_trace_end(buf, cap)
+    if n < 0:
+        check(n, "vtc_trace_end")
+    out = []
+    for ln in buf.value.decode().splitlines():
+        where, us = ln.rsplit(" ", 1)
+        out.append((where, float(us)))
+    return out

@@ -2,8 +2,12 @@
 //
 // Each entry point validates its arguments, carves the caller's workspace, and enqueues kernels on
 // the caller's stream.  Nothing here allocates device memory or synchronises.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "cam.cuh"
 #include "exact.cuh"
@@ -14,6 +18,37 @@
 
 namespace vtc {
 std::atomic<uint64_t> g_launch_count{0};
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("VTC_PDL");
+    return !(e && *e && atoi(e) == 0);
+  }();
+  return on;
+}
+
+// ---- launch trace: a CUDA event on the traced stream after every launch of the library, so that
+// the gaps between consecutive events are the launches' durations as they run back to back in the
+// caller's stream (ncu's per-launch times are serialised and cold-cache).  Debug aid, off by default.
+std::atomic<int> g_trace_on{0};
+namespace {
+struct LaunchTrace {
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> events;           // events[0] = begin
+  std::vector<std::pair<const char*, int>> where;
+};
+LaunchTrace g_trace;
+}  // namespace
+void trace_mark(const char* file, int line) {
+  std::lock_guard<std::mutex> lk(g_trace.mu);
+  if (g_trace.events.empty() || g_trace.events.size() > 4096) return;
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, g_trace.stream);
+  g_trace.events.push_back(e);
+  g_trace.where.emplace_back(file, line);
+}
 
 // infonce_small.cu
 size_t infonce_small_ws_bytes(int64_t n);
@@ -34,6 +69,9 @@ namespace {
 //          hi*hi + hi*lo + lo*hi drops lo_q*lo_x + e_q*x + q*e_x (+ third-order terms), i.e. at most
 //          3 * 2^-16 (1 + 2^-7) < 4.62e-5 of |q_k||x_k| per product, and by Cauchy-Schwarz of
 //          |q||x| per row.
+// (the rank path bounds the split term per row instead -- sim_tc.cuh::rank_split_bound -- and keeps
+// only the accumulation term: guard_accum_rel)
+float guard_accum_rel(int Kp) { return (float)(Kp / 16 + 8) * 5.9604645e-08f; }
 float guard_rel_for(int precision, int Kp) {
   const char* e = getenv(precision == VTC_PREC_BF16 ? "VTC_GUARD_REL_BF16" : "VTC_GUARD_REL_EXACT");
   if (e && *e) {
@@ -75,6 +113,7 @@ struct RankWs {
   __nv_bfloat16 *opQ, *opG;
   double *sq64, *dgt;
   float *sq32, *qq;
+  float2* qsplit;  // exact mode: norms of the split pieces of the query rows
   unsigned int* scalars;  // [0] max_sq_bits, [2] fallback flag, [64..] per-CTA list segment counts
   int* rank_tmp;          // directly behind `scalars`: one memset clears both
   unsigned int* hist;     // scratch of the fused finalisation (vtc_rank_eval)
@@ -103,6 +142,7 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
     r.opG = ws.take<__nv_bfloat16>((size_t)M * o.Kp);
     r.sq32 = ws.take<float>(round_up<int64_t>(M, tc::BN));
     r.qq = ws.take<float>(N);
+    r.qsplit = ws.take<float2>(N);
     if (sizing) {
       r.amb_cap = amb_entries_wanted(N);
       ws.take<int2>(r.amb_cap);
@@ -128,7 +168,7 @@ struct RankFinalize {
 };
 
 // One retrieval evaluation (or one gallery chunk of it) = memset + prologue + tensor-core pass +
-// cooperative epilogue.
+// epilogue (+ its device-gated fallback launch), chained by programmatic dependent launch.
 // Cached per-row quantities (vtc_sim_rank_prepared): canonical ||x_j||^2 of THIS gallery chunk
 // (sq64_in, or computed into sq64_out), an upper bound of ||q_t||^2 (qq_in, or computed into
 // qq_out) and d(t,gt) (gt_score, or computed into gt_score_out).  With all three given (and bf16 rows
@@ -221,6 +261,7 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   pa.gt_in = gt_score, pa.dgt = dgt_w, pa.qq_in = qq_in, pa.qq = qq_w;
   pa.gt = gt, pa.row_offset = row_offset, pa.col_offset = col_offset;
   pa.fallback = &w.scalars[2];
+  pa.qsplit = o.split ? w.qsplit : nullptr, pa.split_max_bits = &w.scalars[4];
   VTC_RETURN_IF_ERROR(launch_rank_prologue(pa, s));
   if (gt_score && gt_score_out && gt_score_out != gt_score) {
     e = cudaMemcpyAsync(gt_score_out, gt_score, sizeof(double) * N, cudaMemcpyDeviceToDevice, s);
@@ -234,7 +275,11 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
   p.dgt = dgt, p.qq = qq, p.max_sq_bits = &w.scalars[0];
-  p.guard_rel = guard_rel_for(precision, o.Kp), p.metric_l2 = metric == VTC_METRIC_L2 ? 1 : 0;
+  // (an override from the environment is a constant relative bound, as in round 1)
+  const bool row_split = o.split && !getenv("VTC_GUARD_REL_EXACT");
+  p.guard_rel = row_split ? guard_accum_rel(o.Kp) : guard_rel_for(precision, o.Kp);
+  p.qsplit = row_split ? w.qsplit : nullptr, p.split_max_bits = &w.scalars[4];
+  p.metric_l2 = metric == VTC_METRIC_L2 ? 1 : 0;
   p.rank = w.rank_tmp, p.amb_list = w.amb, p.amb_seg_count = &w.scalars[64];
   // (rank counts are additive over gallery ranges: the last round of work items is balanced)
   tc::Plan pl = tc::plan_tiles(p, 64, tc::choose_cluster(N, M), 8, tc::BN, true);
@@ -250,6 +295,7 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   memset(&ea, 0, sizeof(ea));
   ea.ex = ex, ea.amb_list = w.amb, ea.seg_count = &w.scalars[64], ea.nseg = pl.grid;
   ea.seg_cap = p.amb_seg_cap, ea.dgt = dgt, ea.rank_tmp = w.rank_tmp, ea.fallback = &w.scalars[2];
+  ea.ticket = &w.scalars[6];
   ea.rank0 = rank0, ea.accumulate = accumulate;
   if (fin) {
     ea.finalize = 1, ea.M_total = fin->M_total, ea.nk = fin->nk;
@@ -401,11 +447,14 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   return launch_topk_brute_rows(a, s);
 }
 
-// Tile width of a dense product: 256 gallery rows per tile unless that leaves more than half of
-// the SMs without a tile (the skinny projections of the CAM: 1536 x 512 outputs = 24 tiles).
+// Tile width of a dense product: the widest of 256 / 128 / 64 gallery rows per tile that still gives
+// two thirds of the SMs a tile (the skinny projections of the CAM: 1536 x 512 outputs are 24 tiles of
+// 256 columns but 96 of 64).  These launches are bound by the operand bytes each CTA pulls from L2.
 int store_tile_width(int64_t rows, int64_t cols) {
-  const int64_t tiles = ceil_div<int64_t>(rows, tc::BM) * ceil_div<int64_t>(cols, tc::BN);
-  return tiles * 2 <= kNumSMs ? 128 : tc::BN;
+  const int64_t q_tiles = ceil_div<int64_t>(rows, tc::BM);
+  for (int bn = tc::BN; bn > 64; bn /= 2)
+    if (q_tiles * ceil_div<int64_t>(cols, bn) * 3 >= kNumSMs * 2) return bn;
+  return 64;
 }
 
 // --------------------------------------------------------------------------- dense TC products
@@ -641,6 +690,47 @@ int vtc_debug_prof_read(unsigned long long* out, int max_words) {
   return tc::debug_prof_read(out, max_words);
 }
 
+int vtc_trace_begin(vtc_stream_t stream) {
+  std::lock_guard<std::mutex> lk(g_trace.mu);
+  for (cudaEvent_t e : g_trace.events) cudaEventDestroy(e);
+  g_trace.events.clear();
+  g_trace.where.clear();
+  g_trace.stream = (cudaStream_t)stream;
+  cudaEvent_t e = nullptr;
+  cudaError_t rc = cudaEventCreate(&e);
+  if (rc == cudaSuccess) rc = cudaEventRecord(e, g_trace.stream);
+  if (rc != cudaSuccess) return cuda_err(rc);
+  g_trace.events.push_back(e);
+  g_trace_on.store(1);
+  return VTC_OK;
+}
+
+int vtc_trace_end(char* buf, size_t cap) {
+  g_trace_on.store(0);
+  std::lock_guard<std::mutex> lk(g_trace.mu);
+  size_t off = 0;
+  int n = 0;
+  cudaError_t rc = cudaSuccess;
+  if (!g_trace.events.empty()) rc = cudaEventSynchronize(g_trace.events.back());
+  for (size_t i = 1; i < g_trace.events.size() && rc == cudaSuccess; ++i) {
+    float ms = 0.f;
+    rc = cudaEventElapsedTime(&ms, g_trace.events[i - 1], g_trace.events[i]);
+    const char* f = g_trace.where[i - 1].first;
+    const char* slash = strrchr(f, '/');
+    if (buf && off < cap) {
+      const int w = snprintf(buf + off, cap - off, "%s:%d %.3f\n", slash ? slash + 1 : f,
+                             g_trace.where[i - 1].second, ms * 1e3f);
+      if (w > 0) off += (size_t)w;
+    }
+    ++n;
+  }
+  for (cudaEvent_t e : g_trace.events) cudaEventDestroy(e);
+  g_trace.events.clear();
+  g_trace.where.clear();
+  if (buf && cap) buf[off < cap ? off : cap - 1] = 0;
+  return rc == cudaSuccess ? n : cuda_err(rc);
+}
+
 size_t vtc_workspace_bytes(int op, int64_t N, int64_t M, int D, int precision) {
   if (N < 0 || M < 0 || D <= 0 || !valid_prec(precision)) return 0;
   Workspace ws(nullptr, 0);
@@ -803,7 +893,7 @@ int vtc_rank_finalize(int32_t* rank0, const double* gt_score, int64_t N, int64_t
   if (N == 0 || !hist_ws)  // no scratch: the stand-alone kernels (hit counts only)
     return launch_rank_finalize(rank0, gt_score, N, M_total, k_vals, nk, hits, medr, hist_ws,
                                 (cudaStream_t)stream);
-  // one cooperative launch: NaN ground truth -> M_total, hit counts, radix-select median
+  // one block: NaN ground truth -> M_total, hit counts, radix-select median
   RankEpilogueArgs ea;
   memset(&ea, 0, sizeof(ea));
   ea.ex.N = N, ea.ex.bf16 = false;

@@ -14,6 +14,8 @@ constexpr int MAX_VEC = 8;  // float4 per lane: rows up to D = 1024
 __global__ void __launch_bounds__(256)
 cam_stack_normalize_kernel(const float* __restrict__ main, const float* __restrict__ aux, int L,
                            int64_t b, int D, float* __restrict__ X) {
+  griddep_launch();
+  griddep_wait();
   const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (r >= (int64_t)L * b) return;
   const int lane = threadIdx.x & 31;
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(256)
 layernorm_prep_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int64_t rows, int D, float eps, int split,
                       __nv_bfloat16* __restrict__ out, int Kp) {
+  griddep_launch();
+  griddep_wait();
   const int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -92,6 +96,8 @@ template <int MAXL, int LPH>
 __global__ void __launch_bounds__(256)
 cam_attn_core_kernel(const float* __restrict__ QKV, int L, int64_t b, int D, int heads,
                      float* __restrict__ out, __nv_bfloat16* __restrict__ out_op, int Kp, int split) {
+  griddep_launch();
+  griddep_wait();
   constexpr int HPW = 32 / LPH;  // heads per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPH, li = lane % LPH;
@@ -194,6 +200,8 @@ cam_readout_kernel(const float* __restrict__ T, const float* __restrict__ main,
                    int64_t b, int D, int mode, int res_act, float res_scale,
                    const float* __restrict__ res_shift, const float* __restrict__ res_mul,
                    float* __restrict__ out) {
+  griddep_launch();
+  griddep_wait();
   __shared__ __align__(16) float part[WARPS][RO_MAX_D];
   const int64_t bi = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -345,8 +353,8 @@ int launch_cam_stack_normalize(const float* main, const float* aux, int L, int64
                                float* X, cudaStream_t s) {
   const int64_t rows = (int64_t)L * b;
   if (rows == 0) return VTC_OK;
-  cam_stack_normalize_kernel<<<(unsigned)ceil_div<int64_t>(rows, WARPS), 256, 0, s>>>(main, aux, L,
-                                                                                      b, D, X);
+  launch_pdl(cam_stack_normalize_kernel, dim3((unsigned)ceil_div<int64_t>(rows, WARPS)), dim3(256), 0, s,
+             main, aux, L, b, D, X);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }
@@ -367,14 +375,14 @@ static void launch_attn_t(int lph, unsigned blocks_for, const float* QKV, int L,
   (void)blocks_for;
   const int64_t units = b * heads;
   if (lph == 8)
-    cam_attn_core_kernel<MAXL, 8><<<(unsigned)ceil_div<int64_t>(units, WARPS * 4), 256, 0, s>>>(
-        QKV, L, b, D, heads, out, out_op, Kp, split);
+    launch_pdl(cam_attn_core_kernel<MAXL, 8>, dim3((unsigned)ceil_div<int64_t>(units, WARPS * 4)),
+               dim3(256), 0, s, QKV, L, b, D, heads, out, out_op, Kp, split);
   else if (lph == 16)
-    cam_attn_core_kernel<MAXL, 16><<<(unsigned)ceil_div<int64_t>(units, WARPS * 2), 256, 0, s>>>(
-        QKV, L, b, D, heads, out, out_op, Kp, split);
+    launch_pdl(cam_attn_core_kernel<MAXL, 16>, dim3((unsigned)ceil_div<int64_t>(units, WARPS * 2)),
+               dim3(256), 0, s, QKV, L, b, D, heads, out, out_op, Kp, split);
   else
-    cam_attn_core_kernel<MAXL, 32><<<(unsigned)ceil_div<int64_t>(units, WARPS), 256, 0, s>>>(
-        QKV, L, b, D, heads, out, out_op, Kp, split);
+    launch_pdl(cam_attn_core_kernel<MAXL, 32>, dim3((unsigned)ceil_div<int64_t>(units, WARPS)),
+               dim3(256), 0, s, QKV, L, b, D, heads, out, out_op, Kp, split);
 }
 
 int launch_cam_attn_core(const float* QKV, int L, int64_t b, int D, int heads, float* out,
@@ -398,8 +406,8 @@ int launch_cam_attn_core(const float* QKV, int L, int64_t b, int D, int heads, f
 int launch_layernorm_prep(const float* X, const float* gamma, const float* beta, int64_t rows, int D,
                           float eps, int split, __nv_bfloat16* out, int Kp, cudaStream_t s) {
   if (rows == 0) return VTC_OK;
-  layernorm_prep_kernel<<<(unsigned)ceil_div<int64_t>(rows, WARPS), 256, 0, s>>>(X, gamma, beta, rows,
-                                                                                D, eps, split, out, Kp);
+  launch_pdl(layernorm_prep_kernel, dim3((unsigned)ceil_div<int64_t>(rows, WARPS)), dim3(256), 0, s, X,
+             gamma, beta, rows, D, eps, split, out, Kp);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }
@@ -424,8 +432,8 @@ int launch_cam_readout(const float* T, const float* main, const float* res_in,
   if (res_act < VTC_RESACT_NONE || res_act > VTC_RESACT_AFFINE ||
       (res_act == VTC_RESACT_AFFINE && !res_shift))
     return VTC_ERR_INVALID_ARG;
-  cam_readout_kernel<<<(unsigned)b, 256, 0, s>>>(T, main, res_in, skip_mask, L, b, D, mode, res_act,
-                                                 res_scale, res_shift, res_mul, out);
+  launch_pdl(cam_readout_kernel, dim3((unsigned)b), dim3(256), 0, s, T, main, res_in, skip_mask, L, b,
+             D, mode, res_act, res_scale, res_shift, res_mul, out);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }

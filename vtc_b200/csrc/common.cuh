@@ -6,12 +6,16 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstring>
 
 #include "../../include/vtc_b200.h"
 
 namespace vtc {
 
 extern std::atomic<uint64_t> g_launch_count;
+// opt-in launch trace (vtc_trace_begin / vtc_trace_end): one CUDA event after every launch
+extern std::atomic<int> g_trace_on;
+void trace_mark(const char* file, int line);
 
 inline int cuda_err(cudaError_t e) { return e == cudaSuccess ? VTC_OK : VTC_ERR_CUDA_BASE - (int)e; }
 
@@ -19,6 +23,8 @@ inline int cuda_err(cudaError_t e) { return e == cudaSuccess ? VTC_OK : VTC_ERR_
 #define VTC_LAUNCH_CHECK()                                   \
   do {                                                       \
     ::vtc::g_launch_count.fetch_add(1);                      \
+    if (::vtc::g_trace_on.load(std::memory_order_relaxed))   \
+      ::vtc::trace_mark(__FILE__, __LINE__);                 \
     cudaError_t e__ = cudaGetLastError();                    \
     if (e__ != cudaSuccess) return ::vtc::cuda_err(e__);     \
   } while (0)
@@ -30,6 +36,42 @@ inline int cuda_err(cudaError_t e) { return e == cudaSuccess ? VTC_OK : VTC_ERR_
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- programmatic dependent launch (PDL).  The paths of this library are chains of short kernels
+// on one stream (CAM forward: 16, a chunked evaluation: 4 per call): launched back to back, each
+// pays its launch latency and its own set-up (barrier init, tensor-memory allocation, descriptor
+// prefetch) after the previous kernel has drained.  With PDL a kernel is scheduled as soon as every
+// CTA of its predecessor has STARTED (griddep_launch at the top of each kernel), does its set-up,
+// and blocks in griddep_wait until the predecessor has completed and flushed its writes.
+// Rules kept by every kernel launched through launch_pdl: (1) all threads execute griddep_wait()
+// before the first access to global memory and before any early return -- so a grid never completes
+// before its predecessor, which makes the ordering transitive along the chain; (2) nothing but
+// shared-memory / tensor-memory set-up and kernel-parameter reads happens above it.
+// VTC_PDL=0 launches everything fully serialised (profiling / debugging).
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_launch() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();  // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) {

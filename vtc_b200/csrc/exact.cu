@@ -100,18 +100,6 @@ rank_brute_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ G,
                       rank, blockIdx.x, gridDim.x);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-recheck_kernel(const int2* __restrict__ list, const unsigned int* __restrict__ seg_count,
-               unsigned int seg_cap, const T* __restrict__ Q, int64_t ldq,
-               const T* __restrict__ G, int64_t ldg, const double* __restrict__ sq64,
-               const double* __restrict__ dgt, int64_t N, int64_t M, int D,
-               const int64_t* __restrict__ gt, int64_t row_offset, int64_t col_offset, int metric,
-               int* __restrict__ rank, unsigned int* __restrict__ overflow) {
-  recheck_part<T>(blockIdx.x, list, seg_count, seg_cap, Q, ldq, G, ldg, sq64, dgt, N, M, D, gt,
-                  row_offset, col_offset, metric, rank, overflow);
-}
-
 // dst[j] = j < M ? (src ? src[j] : 0) : pad   for j in [0, Mpad)   (in place allowed)
 __global__ void fill_bias_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t M,
                                  int64_t Mpad, float pad) {
@@ -320,26 +308,6 @@ int launch_rank_brute(const ExactArgs& a, const double* dgt, int* rank,
                       const unsigned int* run_flag, cudaStream_t s) {
   return a.bf16 ? launch_rank_brute_t<__nv_bfloat16>(a, dgt, rank, run_flag, s)
                 : launch_rank_brute_t<float>(a, dgt, rank, run_flag, s);
-}
-
-template <typename T>
-static int launch_recheck_t(const ExactArgs& a, const int2* list, const unsigned int* seg_count,
-                            int nseg, unsigned int seg_cap, const double* dgt, int* rank,
-                            unsigned int* overflow, cudaStream_t s) {
-  if (nseg <= 0) return VTC_OK;
-  recheck_kernel<T><<<nseg * RECHECK_PARTS, 256, 0, s>>>(list, seg_count, seg_cap, (const T*)a.Q,
-                                                        a.ldq, (const T*)a.G, a.ldg, a.sq64, dgt,
-                                                        a.N, a.M, a.D, a.gt, a.row_offset,
-                                                        a.col_offset, a.metric, rank, overflow);
-  VTC_LAUNCH_CHECK();
-  return VTC_OK;
-}
-int launch_recheck(const ExactArgs& a, const int2* list, const unsigned int* seg_count, int nseg,
-                   unsigned int seg_cap, const double* dgt, int* rank, unsigned int* overflow,
-                   cudaStream_t s) {
-  return a.bf16 ? launch_recheck_t<__nv_bfloat16>(a, list, seg_count, nseg, seg_cap, dgt, rank,
-                                                  overflow, s)
-                : launch_recheck_t<float>(a, list, seg_count, nseg, seg_cap, dgt, rank, overflow, s);
 }
 
 int launch_fill_bias(float* dst, const float* src, int64_t M, int64_t Mpad, float pad,

@@ -25,9 +25,6 @@ int launch_gt_score(const ExactArgs& a, const double* gt_in, double* gt_out, flo
                     const unsigned int* max_sq_bits, float guard_rel, cudaStream_t s);
 int launch_rank_brute(const ExactArgs& a, const double* dgt, int* rank,
                       const unsigned int* run_flag, cudaStream_t s);
-int launch_recheck(const ExactArgs& a, const int2* list, const unsigned int* seg_count, int nseg,
-                   unsigned int seg_cap, const double* dgt, int* rank, unsigned int* overflow,
-                   cudaStream_t s);
 int launch_fill_bias(float* dst, const float* src, int64_t M, int64_t Mpad, float pad,
                      cudaStream_t s);
 int launch_zero_if_flag(int* buf, int64_t n, const unsigned int* flag, cudaStream_t s);

@@ -13,17 +13,13 @@
 //   dot product, the memory system needs a warp per row; the staging gives both.  HBM-bound:
 //   rows * D * sizeof(in) read + rows * K' * 2 written.
 //
-// rank_epilogue_kernel -- cooperative (grid-wide barriers), persistent:
+// rank_epilogue_kernel (+ rank_fallback_kernel, device-gated) -- see "epilogue" below:
 //   re-check of the guard-band groups -> [flag: zero + brute-force] -> commit into rank0 ->
 //   [NaN ground truth -> M, R@K hit counts, median rank by radix select].
 #include "rank_stage.cuh"
 
-#include <cooperative_groups.h>
-
 #include "exact_dev.cuh"
 #include "prep.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace vtc {
 
@@ -38,28 +34,9 @@ __device__ __forceinline__ float bf16_rn(float v) {
   return __bfloat162float(__float2bfloat16_rn(v));
 }
 
-// four consecutive elements [k, k + 4) of a row as floats; zero beyond D or for an invalid row
-__device__ __forceinline__ void load_quad(const float* row, int k, int D, bool vec, float (&v)[4]) {
-  if (row != nullptr && vec && k + 4 <= D) {
-    const float4 f = __ldg(reinterpret_cast<const float4*>(row + k));
-    v[0] = f.x, v[1] = f.y, v[2] = f.z, v[3] = f.w;
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = (row != nullptr && k + e < D) ? __ldg(row + k + e) : 0.f;
-  }
-}
-__device__ __forceinline__ void load_quad(const __nv_bfloat16* row, int k, int D, bool vec,
-                                          float (&v)[4]) {
-  if (row != nullptr && vec && k + 4 <= D) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(row + k));
-    v[0] = __uint_as_float(u.x << 16), v[1] = __uint_as_float(u.x & 0xffff0000u);
-    v[2] = __uint_as_float(u.y << 16), v[3] = __uint_as_float(u.y & 0xffff0000u);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      v[e] = (row != nullptr && k + e < D) ? __bfloat162float(row[k + e]) : 0.f;
-  }
-}
+// an upper bound of a sum of squares accumulated in fp32 in any order (D <= 8192 terms: the
+// relative rounding error is below 8192 * 2^-24 = 4.9e-4)
+__device__ __forceinline__ float piece_up(float s) { return s * 1.001f; }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) |
@@ -68,8 +45,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // the operand columns of four consecutive input elements (canonical values v, already rounded in the
 // plain mode): mode PREP_PLAIN [x], PREP_SPLIT_A [hi | hi | lo], PREP_SPLIT_B [hi | lo | hi]
+// (split modes: *s_lo / *s_e gain the squared pieces lo = bf16(x - hi) and e = x - hi - lo)
 __device__ __forceinline__ void emit_quad(__nv_bfloat16* o, int k, int D, int mode,
-                                          const float (&v)[4], unsigned int* fallback) {
+                                          const float (&v)[4], unsigned int* fallback,
+                                          float* s_lo = nullptr, float* s_e = nullptr) {
   if (k >= D) return;
   if (mode == PREP_PLAIN) {
     if (k + 4 <= D) {
@@ -87,6 +66,11 @@ __device__ __forceinline__ void emit_quad(__nv_bfloat16* o, int k, int D, int mo
     lo[e] = v[e] - hi[e];
     // inf / NaN (or an fp32 value that rounds to inf) has no 3-term split: x - hi is NaN
     bad |= !(fabsf(hi[e]) <= 3.0e38f);
+    if (s_lo && k + e < D) {
+      const float lb = bf16_rn(lo[e]), ee = lo[e] - lb;  // (x - hi and lo - bf16(lo) are exact in fp32)
+      *s_lo = fmaf(lb, lb, *s_lo);
+      *s_e = fmaf(ee, ee, *s_e);
+    }
   }
   if (bad && fallback) *fallback = 1u;
   const int o1 = mode == PREP_SPLIT_A ? D : 2 * D;  // second copy of hi
@@ -104,12 +88,6 @@ __device__ __forceinline__ void emit_quad(__nv_bfloat16* o, int k, int D, int mo
       o[o2 + k + e] = __float2bfloat16_rn(lo[e]);
     }
   }
-}
-
-template <typename T>
-__device__ __forceinline__ bool rows_vectorisable(const T* base, int64_t ld) {
-  constexpr uintptr_t kAlign = sizeof(T) == 4 ? 15 : 7;  // 4 elements
-  return (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & kAlign) == 0;
 }
 
 // zero the padding columns [used, Kp) of the 32 operand rows of this block
@@ -131,6 +109,8 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
   __shared__ __align__(16) float tile_b[PR_ROWS * PR_LD];  // ground-truth gallery rows of the queries
   __shared__ int64_t srow_a[PR_ROWS], srow_b[PR_ROWS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  griddep_launch();
+  griddep_wait();
   const T* Qb = static_cast<const T*>(a.Q);
   const T* Gb = static_cast<const T*>(a.G);
   const bool round = a.round_bf16 != 0;
@@ -159,6 +139,8 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
     __syncthreads();
     const bool walk = a.sq64_in == nullptr;
     const bool emit = a.mode_g != STAGE_NONE;
+    const bool pieces = emit && a.mode_g != PREP_PLAIN && a.split_max_bits != nullptr;
+    float s_lo[4] = {0.f, 0.f, 0.f, 0.f}, s_e[4] = {0.f, 0.f, 0.f, 0.f};
     double sq = 0.0;
     if ((walk || emit) && r0 < a.M) {
       const bool vec = rows_vectorisable(Gb, a.ldg);
@@ -185,7 +167,7 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
               make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
           if (emit && rp[j])
             emit_quad(a.opG + srow_a[row] * (int64_t)a.Kp, k0 + 4 * lane, a.D, a.mode_g, v[j],
-                      a.fallback);
+                      a.fallback, pieces ? &s_lo[j] : nullptr, pieces ? &s_e[j] : nullptr);
         }
         __syncthreads();
         if (c + 1 < nchunks) {
@@ -206,6 +188,24 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
         }
       }
       if (emit) zero_pad_columns(a.opG, a.Kp, a.mode_g == PREP_PLAIN ? a.D : 3 * a.D, srow_a);
+      if (pieces) {
+        // largest piece norms of this block's rows: one pair of global atomics per block
+        float m_lo = 0.f, m_e = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float l = piece_up(warp_sum(s_lo[j])), e = piece_up(warp_sum(s_e[j]));
+          if (l < 3.0e38f) m_lo = fmaxf(m_lo, l);  // (NaN / inf rows raise the fallback flag instead)
+          if (e < 3.0e38f) m_e = fmaxf(m_e, e);
+        }
+        float* blk = tile_b;  // (unused by gallery blocks)
+        if (lane == 0) blk[2 * warp] = m_lo, blk[2 * warp + 1] = m_e;
+        __syncthreads();
+        if (tid < 2) {
+          float m = 0.f;
+          for (int w = 0; w < PR_THREADS / 32; ++w) m = fmaxf(m, blk[2 * w + tid]);
+          if (m > 0.f) atomicMax(a.split_max_bits + tid, __float_as_uint(m));
+        }
+      }
     }
     if (warp == 0) {
       const int64_t j = r0 + lane;
@@ -234,6 +234,8 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
   const bool need_gt = a.gt_in == nullptr && a.dgt != nullptr;
   const bool need_qq = a.qq_in == nullptr && a.qq != nullptr;
   const bool emit = a.mode_q != STAGE_NONE;
+  const bool pieces = emit && a.mode_q != PREP_PLAIN && a.qsplit != nullptr;
+  float s_lo[4] = {0.f, 0.f, 0.f, 0.f}, s_e[4] = {0.f, 0.f, 0.f, 0.f};
   if (tid < PR_ROWS) {
     const int64_t t = t0 + tid;
     srow_a[tid] = t < a.N ? t : -1;
@@ -279,7 +281,7 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
               make_float4(w[j][0], w[j][1], w[j][2], w[j][3]);
         if (emit && qp[j])
           emit_quad(a.opQ + srow_a[row] * (int64_t)a.Kp, k0 + 4 * lane, a.D, a.mode_q, v[j],
-                    a.fallback);
+                    a.fallback, pieces ? &s_lo[j] : nullptr, pieces ? &s_e[j] : nullptr);
       }
       __syncthreads();
       if (c + 1 < nchunks) {
@@ -314,6 +316,14 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
       }
     }
     if (emit) zero_pad_columns(a.opQ, a.Kp, a.mode_q == PREP_PLAIN ? a.D : 3 * a.D, srow_a);
+    if (pieces) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float l = piece_up(warp_sum(s_lo[j])), e = piece_up(warp_sum(s_e[j]));
+        const int64_t t = srow_a[warp + 8 * j];
+        if (lane == 0 && t >= 0) a.qsplit[t] = make_float2(sqrtf(l) * 1.000001f, sqrtf(e) * 1.000001f);
+      }
+    }
   }
   if (warp == 0 && t0 + lane < a.N) {
     const int64_t t = t0 + lane;
@@ -339,31 +349,50 @@ int launch_rank_prologue(const RankPrologueArgs& a, cudaStream_t s) {
   if (g_blocks + q_blocks > 0x7fffffff) return VTC_ERR_UNSUPPORTED_SHAPE;
   const unsigned grid = (unsigned)(g_blocks + q_blocks);
   if (a.in_bf16)
-    rank_prologue_kernel<__nv_bfloat16><<<grid, PR_THREADS, 0, s>>>(a, (int)g_blocks, g_light);
+    launch_pdl(rank_prologue_kernel<__nv_bfloat16>, dim3(grid), dim3(PR_THREADS), 0, s, a,
+               (int)g_blocks, g_light);
   else
-    rank_prologue_kernel<float><<<grid, PR_THREADS, 0, s>>>(a, (int)g_blocks, g_light);
+    launch_pdl(rank_prologue_kernel<float>, dim3(grid), dim3(PR_THREADS), 0, s, a, (int)g_blocks,
+               g_light);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }
 
 // ------------------------------------------------------------------------------------ epilogue
+// A chain of short plain launches under programmatic dependent launch (round 2a used one cooperative
+// launch with grid-wide barriers; a kernel boundary under PDL is cheaper than a grid barrier plus the
+// cooperative launch, and every stage gets the grid size that suits it):
+//   rank_recheck_kernel   zero the finalisation scratch; every warp re-checks its share of the
+//                         guard-band groups in canonical arithmetic
+//   rank_fallback_kernel  gated on the device-side flag (list overflow, or split operands that could
+//                         not carry inf / NaN): exits at once in the normal case, otherwise the whole
+//                         grid recounts in canonical arithmetic
+//   rank_commit_kernel    rank0 = (accumulate ? rank0 : 0) + counts; with `finalize`: NaN ground truth
+//                         -> M_total, R@K hit counts, histogram of the first radix digit
+//   rank_select_kernel    (per further digit) pick the digit(s) of the two middle order statistics,
+//                         histogram of the next digit among the ranks that match; the LAST block of
+//                         the last level writes median(rank0) + 1 (numpy semantics).
 constexpr int EP_THREADS = 256;
 constexpr int MED_BINS = 2048;
 constexpr int MED_LEVELS = 3;  // bits [21,32), [10,21), [0,10)
+constexpr int EP_ITEMS = 4;    // ranks per thread in the commit / select passes
 size_t rank_epilogue_hist_words() { return (size_t)MED_LEVELS * 2 * MED_BINS + 8; }
 
 __device__ __forceinline__ int med_shift(int level) { return level == 0 ? 21 : (level == 1 ? 10 : 0); }
 __device__ __forceinline__ unsigned int med_mask(int level) { return level == 2 ? 1023u : 2047u; }
+__host__ __device__ inline int med_level0(int64_t M_total) {
+  return (M_total >> 21) == 0 ? ((M_total >> 10) == 0 ? 2 : 1) : 0;
+}
 
-union EpilogueSmem {
+union __align__(16) EpilogueSmem {
   BruteSmem brute;
   unsigned int hist[2][MED_BINS];
+  float recheck[EP_THREADS / 32][RC_WARP_FLOATS];  // one staging tile per warp
 };
 
 // the bin (and the remainder inside it) that holds order statistic `target` of a 2048-bin
-// histogram; every thread of the block returns the same pair
-// (h was filled by other blocks' atomics in this same launch: read it through L2, not the
-// non-coherent path)
+// histogram in global memory (filled by other blocks' atomics: read through L2); every thread of
+// the block returns the same pair
 __device__ __forceinline__ uint2 med_pick(const unsigned int* h, unsigned int target,
                                           unsigned int* sh_warp, unsigned int* sh_out) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -400,140 +429,208 @@ __device__ __forceinline__ uint2 med_pick(const unsigned int* h, unsigned int ta
   return make_uint2(sh_out[0], sh_out[1]);
 }
 
+// true in every thread of exactly one block of the grid: the last one to get here.  All global
+// writes of the other blocks made before their call are visible to it afterwards.
+__device__ __forceinline__ bool last_block_here(unsigned int* ticket, unsigned int* sh_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *sh_flag = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  const bool last = *sh_flag != 0u;
+  if (last) __threadfence();
+  return last;
+}
+
+// hist layout: [level][2][MED_BINS] counters, then 8 words: tickets of the select levels
+__device__ __forceinline__ unsigned int* hist_ticket(unsigned int* hist, int level) {
+  return hist + (size_t)MED_LEVELS * 2 * MED_BINS + level;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(EP_THREADS)
-rank_epilogue_kernel(const RankEpilogueArgs a) {
-  cg::grid_group grid = cg::this_grid();
+rank_recheck_kernel(const RankEpilogueArgs a) {
   __shared__ EpilogueSmem sm;
-  __shared__ unsigned int sh_warp[EP_THREADS / 32], sh_out[2];
-  __shared__ int sh_hits[8];
+  __shared__ unsigned int sh_flag;
+  griddep_launch();
+  griddep_wait();
   const int tid = threadIdx.x;
-  const int64_t gtid = (int64_t)blockIdx.x * EP_THREADS + tid;
-  const int64_t gthreads = (int64_t)gridDim.x * EP_THREADS;
-  const T* Q = static_cast<const T*>(a.ex.Q);
-  const T* G = static_cast<const T*>(a.ex.G);
-  const int64_t N = a.ex.N;
-
-  // ---- phase 1: scratch of the finalisation + re-check of the guard-band groups
   if (a.finalize) {
-    const int64_t words = (int64_t)MED_LEVELS * 2 * MED_BINS + 8;
-    for (int64_t i = gtid; i < words; i += gthreads) a.hist[i] = 0u;
+    const int64_t words = (int64_t)(MED_LEVELS * 2 * MED_BINS + 8);
+    for (int64_t i = (int64_t)blockIdx.x * EP_THREADS + tid; i < words; i += (int64_t)gridDim.x * EP_THREADS)
+      a.hist[i] = 0u;
     if (blockIdx.x == 0 && tid < a.nk) a.hits[tid] = 0ull;
   }
-  // (rank_tmp == NULL: finalisation only -- vtc_rank_finalize on ranks that are already complete)
-  if (a.rank_tmp)
-    for (int vb = blockIdx.x; vb < a.nseg * RECHECK_PARTS; vb += gridDim.x)
-      recheck_part<T>(vb, a.amb_list, a.seg_count, a.seg_cap, Q, a.ex.ldq, G, a.ex.ldg, a.ex.sq64,
-                      a.dgt, N, a.ex.M, a.ex.D, a.ex.gt, a.ex.row_offset, a.ex.col_offset,
-                      a.ex.metric, a.rank_tmp, a.fallback);
-  grid.sync();
+  if (!a.rank_tmp) return;  // finalisation only (vtc_rank_finalize): nothing to re-check
+  recheck_all<T>(sm.recheck[tid >> 5], (int)blockIdx.x * (EP_THREADS / 32) + (tid >> 5),
+                 (int)gridDim.x * (EP_THREADS / 32), a.amb_list, a.seg_count, a.nseg, a.seg_cap,
+                 static_cast<const T*>(a.ex.Q), a.ex.ldq, static_cast<const T*>(a.ex.G), a.ex.ldg,
+                 a.ex.sq64, a.dgt, a.ex.N, a.ex.M, a.ex.D, a.ex.gt, a.ex.row_offset,
+                 a.ex.col_offset, a.ex.metric, a.rank_tmp, a.fallback);
+  // the fallback kernel recounts everything: the last block hands it zeroed counts
+  if (!last_block_here(a.ticket, &sh_flag)) return;
+  if (__ldcg(a.fallback) != 0u)
+    for (int64_t i = tid; i < a.ex.N; i += EP_THREADS) a.rank_tmp[i] = 0;
+}
 
-  // ---- phase 2 (rare): the list overflowed, or the split operands could not carry the inputs:
-  // recount everything in canonical arithmetic
-  if (a.rank_tmp && *reinterpret_cast<volatile unsigned int*>(a.fallback) != 0u) {
-    for (int64_t i = gtid; i < N; i += gthreads) a.rank_tmp[i] = 0;
-    grid.sync();
-    rank_brute_tiles<T>(sm.brute, Q, a.ex.ldq, G, a.ex.ldg, a.ex.sq64, a.dgt, N, a.ex.M, a.ex.D,
-                        a.ex.gt, a.ex.row_offset, a.ex.col_offset, a.ex.metric, a.rank_tmp,
-                        blockIdx.x, gridDim.x);
-    grid.sync();
+template <typename T>
+__global__ void __launch_bounds__(EP_THREADS)
+rank_fallback_kernel(const RankEpilogueArgs a) {
+  __shared__ BruteSmem sm;
+  griddep_launch();
+  griddep_wait();
+  if (__ldcg(a.fallback) == 0u) return;  // the normal case: nothing to do
+  rank_brute_tiles<T>(sm, static_cast<const T*>(a.ex.Q), a.ex.ldq, static_cast<const T*>(a.ex.G),
+                      a.ex.ldg, a.ex.sq64, a.dgt, a.ex.N, a.ex.M, a.ex.D, a.ex.gt, a.ex.row_offset,
+                      a.ex.col_offset, a.ex.metric, a.rank_tmp, blockIdx.x, gridDim.x);
+}
+
+// the median's radix-select state after the levels before `level`: prefixes (pa, pb) and remaining
+// order statistics (ra, rb) of the lower and upper middle element
+struct MedState {
+  unsigned int pa, pb, ra, rb;
+};
+__device__ __forceinline__ MedState med_state_before(const unsigned int* hist, int level0, int level,
+                                                     int64_t N, unsigned int* sh_warp,
+                                                     unsigned int* sh_out) {
+  MedState m{0u, 0u, (unsigned int)((N - 1) / 2), (unsigned int)(N / 2)};
+  for (int l = level0; l < level; ++l) {
+    const unsigned int* h = hist + (size_t)l * 2 * MED_BINS;
+    const bool same = m.pa == m.pb;
+    const uint2 sa = med_pick(h, m.ra, sh_warp, sh_out);
+    const uint2 sb = med_pick(same ? h : h + MED_BINS, m.rb, sh_warp, sh_out);
+    const int bits = l == 2 ? 10 : 11;
+    m.pa = (m.pa << bits) | sa.x, m.ra = sa.y;
+    m.pb = (m.pb << bits) | sb.x, m.rb = sb.y;
   }
+  return m;
+}
 
-  // ---- phase 3: commit (+ NaN ground truth -> M_total, R@K hit counts, first histogram level)
+__global__ void __launch_bounds__(EP_THREADS)
+rank_commit_kernel(const RankEpilogueArgs a) {
+  __shared__ unsigned int hist[MED_BINS];
+  __shared__ unsigned int sh_warp[EP_THREADS / 32], sh_out[2], sh_flag;
+  __shared__ int sh_hits[8];
+  griddep_launch();
+  griddep_wait();
+  const int tid = threadIdx.x;
+  const int64_t N = a.ex.N;
+  const int64_t i0 = ((int64_t)blockIdx.x * EP_THREADS + tid) * EP_ITEMS;
   if (!a.finalize) {
-    for (int64_t i = gtid; i < N; i += gthreads)
-      a.rank0[i] = (a.accumulate ? a.rank0[i] : 0) + a.rank_tmp[i];
+#pragma unroll
+    for (int e = 0; e < EP_ITEMS; ++e)
+      if (i0 + e < N) a.rank0[i0 + e] = (a.accumulate ? a.rank0[i0 + e] : 0) + __ldcg(a.rank_tmp + i0 + e);
     return;
   }
   const bool want_med = a.medr != nullptr;
-  const int level0 = (a.M_total >> 21) == 0 ? ((a.M_total >> 10) == 0 ? 2 : 1) : 0;
-  for (int i = tid; i < 2 * MED_BINS; i += EP_THREADS) (&sm.hist[0][0])[i] = 0u;
+  const int level0 = med_level0(a.M_total);
+  if (want_med)
+    for (int i = tid; i < MED_BINS; i += EP_THREADS) hist[i] = 0u;
   if (tid < 8) sh_hits[tid] = 0;
   __syncthreads();
-  {
-    int local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int shift = med_shift(level0);
-    const unsigned int mask = med_mask(level0);
-    for (int64_t i = gtid; i < N; i += gthreads) {
-      int r = (a.accumulate ? a.rank0[i] : 0) + (a.rank_tmp ? a.rank_tmp[i] : 0);
+  int r[EP_ITEMS];
+#pragma unroll
+  for (int e = 0; e < EP_ITEMS; ++e) {
+    r[e] = -1;
+    if (i0 + e < N) {
+      r[e] = (a.accumulate ? a.rank0[i0 + e] : 0) + (a.rank_tmp ? __ldcg(a.rank_tmp + i0 + e) : 0);
       if (a.dgt) {
-        const double d0 = a.dgt[i];
-        if (d0 != d0) r = (int)a.M_total;  // no ground truth: never retrieved
+        const double d0 = a.dgt[i0 + e];
+        if (d0 != d0) r[e] = (int)a.M_total;  // no ground truth: never retrieved
       }
-      a.rank0[i] = r;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (k < a.nk) local[k] += r < a.k_vals[k];
-      if (want_med) atomicAdd(&sm.hist[0][((unsigned int)r >> shift) & mask], 1u);
     }
+  }
+  int local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int shift = med_shift(level0);
+  const unsigned int mask = med_mask(level0);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (k < a.nk) {
-        int v = local[k];
+  for (int e = 0; e < EP_ITEMS; ++e) {
+    if (i0 + e >= N) continue;
+    a.rank0[i0 + e] = r[e];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0 && v) atomicAdd(&sh_hits[k], v);
-      }
+    for (int k = 0; k < 8; ++k)
+      if (k < a.nk) local[k] += r[e] < a.k_vals[k];
+    if (want_med) atomicAdd(&hist[((unsigned int)r[e] >> shift) & mask], 1u);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < a.nk) {
+      int v = local[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0 && v) atomicAdd(&sh_hits[k], v);
     }
   }
   __syncthreads();
   if (tid < a.nk && sh_hits[tid]) atomicAdd(&a.hits[tid], (unsigned long long)sh_hits[tid]);
   if (!want_med) return;
-  if (N <= 0) {
-    if (gtid == 0) *a.medr = nan("");
-    return;
+  unsigned int* h = a.hist + (size_t)level0 * 2 * MED_BINS;
+  for (int i = tid; i < MED_BINS; i += EP_THREADS)
+    if (hist[i]) atomicAdd(&h[i], hist[i]);
+  if (level0 < MED_LEVELS - 1) return;  // further digits: rank_select_kernel
+  // a single digit (M_total < 1024): the last block picks the median here
+  if (!last_block_here(hist_ticket(a.hist, level0), &sh_flag)) return;
+  const MedState m = med_state_before(a.hist, level0, MED_LEVELS, N, sh_warp, sh_out);
+  if (tid == 0) *a.medr = 0.5 * ((double)m.pa + (double)m.pb) + 1.0;
+}
+
+// one further radix digit (`level` > level0)
+__global__ void __launch_bounds__(EP_THREADS)
+rank_select_kernel(const RankEpilogueArgs a, int level) {
+  __shared__ unsigned int hist[2][MED_BINS];
+  __shared__ unsigned int sh_warp[EP_THREADS / 32], sh_out[2], sh_flag;
+  griddep_launch();
+  griddep_wait();
+  const int tid = threadIdx.x;
+  const int64_t N = a.ex.N;
+  const int level0 = med_level0(a.M_total);
+  for (int i = tid; i < 2 * MED_BINS; i += EP_THREADS) (&hist[0][0])[i] = 0u;
+  const MedState m = med_state_before(a.hist, level0, level, N, sh_warp, sh_out);  // (syncs inside)
+  const int64_t i0 = ((int64_t)blockIdx.x * EP_THREADS + tid) * EP_ITEMS;
+  const int shift = med_shift(level), up = med_shift(level - 1);
+  const unsigned int mask = med_mask(level);
+#pragma unroll
+  for (int e = 0; e < EP_ITEMS; ++e) {
+    if (i0 + e >= N) continue;
+    const unsigned int r = (unsigned int)a.rank0[i0 + e];
+    const unsigned int hi = r >> up, bin = (r >> shift) & mask;
+    if (hi == m.pa) atomicAdd(&hist[0][bin], 1u);
+    if (hi == m.pb && m.pb != m.pa) atomicAdd(&hist[1][bin], 1u);
   }
-  // ---- median(rank0) + 1 with numpy semantics: radix select over 11/11/10-bit digits, both middle
-  // order statistics at once (they may part ways at any level).  Every block derives the same
-  // (prefix, remainder) state from the global histogram, so one grid barrier per level suffices.
-  unsigned int pa = 0, pb = 0, ra = (unsigned int)((N - 1) / 2), rb = (unsigned int)(N / 2);
-  for (int level = level0; level < MED_LEVELS; ++level) {
-    unsigned int* h = a.hist + (size_t)level * 2 * MED_BINS;
-    if (level > level0) {
-      // histogram of this level's digit among the ranks that match the prefix selected so far
-      for (int i = tid; i < 2 * MED_BINS; i += EP_THREADS) (&sm.hist[0][0])[i] = 0u;
-      __syncthreads();
-      const int shift = med_shift(level), up = med_shift(level - 1);
-      const unsigned int mask = med_mask(level);
-      for (int64_t i = gtid; i < N; i += gthreads) {
-        const unsigned int r = (unsigned int)a.rank0[i];
-        const unsigned int hi = r >> up, bin = (r >> shift) & mask;
-        if (hi == pa) atomicAdd(&sm.hist[0][bin], 1u);
-        if (hi == pb && pb != pa) atomicAdd(&sm.hist[1][bin], 1u);
-      }
-      __syncthreads();
-    }
-    for (int i = tid; i < 2 * MED_BINS; i += EP_THREADS) {
-      const unsigned int v = (&sm.hist[0][0])[i];
-      if (v) atomicAdd(&h[i], v);
-    }
-    grid.sync();
-    const bool same = pa == pb;
-    const uint2 sa = med_pick(h, ra, sh_warp, sh_out);
-    const uint2 sb = med_pick(same ? h : h + MED_BINS, rb, sh_warp, sh_out);
-    const int bits = level == 2 ? 10 : 11;
-    pa = (pa << bits) | sa.x, ra = sa.y;
-    pb = (pb << bits) | sb.x, rb = sb.y;
+  __syncthreads();
+  unsigned int* h = a.hist + (size_t)level * 2 * MED_BINS;
+  for (int i = tid; i < 2 * MED_BINS; i += EP_THREADS) {
+    const unsigned int v = (&hist[0][0])[i];
+    if (v) atomicAdd(&h[i], v);
   }
-  if (gtid == 0) *a.medr = 0.5 * ((double)pa + (double)pb) + 1.0;
+  if (level < MED_LEVELS - 1) return;
+  if (!last_block_here(hist_ticket(a.hist, level), &sh_flag)) return;
+  const MedState f = med_state_before(a.hist, level0, MED_LEVELS, N, sh_warp, sh_out);
+  if (tid == 0) *a.medr = 0.5 * ((double)f.pa + (double)f.pb) + 1.0;
 }
 
 template <typename T>
 static int launch_rank_epilogue_t(const RankEpilogueArgs& a, cudaStream_t s) {
-  static int blocks_per_sm = []() {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rank_epilogue_kernel<T>, EP_THREADS, 0) !=
-        cudaSuccess)
-      return 0;
-    return n;
-  }();
-  if (blocks_per_sm <= 0) return VTC_ERR_NO_DEVICE;
-  const int grid = kNumSMs * (blocks_per_sm < 2 ? blocks_per_sm : 2);
-  void* args[] = {const_cast<RankEpilogueArgs*>(&a)};
-  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)rank_epilogue_kernel<T>, dim3(grid),
-                                                    dim3(EP_THREADS), args, 0, s);
-  if (e != cudaSuccess) return cuda_err(e);
+  const int64_t N = a.ex.N;
+  if (a.finalize && !a.hist) return VTC_ERR_WORKSPACE;
+  if (a.rank_tmp && !a.ticket) return VTC_ERR_INVALID_ARG;
+  if (a.rank_tmp || a.finalize) {
+    // finalisation only: the scratch is 12 K words -- a handful of blocks zero it
+    launch_pdl(rank_recheck_kernel<T>, dim3(a.rank_tmp ? 2 * kNumSMs : 8), dim3(EP_THREADS), 0, s, a);
+    VTC_LAUNCH_CHECK();
+  }
+  if (a.rank_tmp) {
+    launch_pdl(rank_fallback_kernel<T>, dim3(2 * kNumSMs), dim3(EP_THREADS), 0, s, a);
+    VTC_LAUNCH_CHECK();
+  }
+  const unsigned blocks = (unsigned)ceil_div<int64_t>(N, EP_THREADS * EP_ITEMS);
+  launch_pdl(rank_commit_kernel, dim3(blocks), dim3(EP_THREADS), 0, s, a);
   VTC_LAUNCH_CHECK();
+  if (a.finalize && a.medr) {
+    for (int level = med_level0(a.M_total) + 1; level < MED_LEVELS; ++level) {
+      launch_pdl(rank_select_kernel, dim3(blocks), dim3(EP_THREADS), 0, s, a, level);
+      VTC_LAUNCH_CHECK();
+    }
+  }
   return VTC_OK;
 }
 

@@ -1,8 +1,9 @@
 // rank_stage.cuh -- the two kernels around the tensor-core pass of vtc_sim_rank / vtc_rank_eval
 // (rank_stage.cu): ONE prologue launch (bf16 operands, canonical norms, ground-truth scores, epilogue
-// bias, guard-band inputs) and ONE cooperative epilogue launch (fp64 re-check of the guard-band
-// groups, brute-force fallback, commit, R@K hit counts, median rank).  A retrieval evaluation is
-// memset + prologue + tensor-core pass + epilogue: 3 kernels instead of the 17 launches of round 1.
+// bias, guard-band inputs) and the epilogue chain (fp64 re-check of the guard-band groups, device-gated
+// brute-force fallback, commit + R@K hit counts, radix-select median), short launches chained by
+// programmatic dependent launch.  A retrieval evaluation is memset + prologue + tensor-core pass +
+// 5 epilogue launches instead of the 17 launches of round 1.
 #pragma once
 #include "common.cuh"
 #include "exact.cuh"
@@ -39,6 +40,11 @@ struct RankPrologueArgs {
   float* qq;                  // nullable: no norm bounds wanted
   const int64_t* gt;
   int64_t row_offset, col_offset;
+  // split modes only (nullable): the norms of the split's pieces for the per-row guard band
+  // (sim_tc.cuh::rank_split_bound) -- per query upper bounds of (|lo(q_t)|, |e(q_t)|), over the
+  // gallery the float bits of max_j |lo(x_j)|^2 and max_j |e(x_j)|^2 (atomicMax; zeroed by the caller)
+  float2* qsplit;
+  unsigned int* split_max_bits;
   // set to 1 when a 3-term split operand would have to carry inf / NaN (x - bf16(x) is NaN there):
   // the epilogue then recomputes the call with the canonical brute-force kernel
   unsigned int* fallback;
@@ -54,6 +60,7 @@ struct RankEpilogueArgs {
   const double* dgt;
   int* rank_tmp;           // [N] counts of this call (tensor-core pass + re-check)
   unsigned int* fallback;  // in/out: list overflow or non-finite split operands -> brute force
+  unsigned int* ticket;    // zeroed by the caller: arrival counter of the re-check launch
   int32_t* rank0;          // [N] result
   int accumulate;
   // optional finalisation (vtc_rank_eval): NaN ground truth -> rank M_total, hits, median
@@ -63,7 +70,7 @@ struct RankEpilogueArgs {
   int nk;
   unsigned long long* hits;  // [nk]
   double* medr;              // nullable
-  unsigned int* hist;        // [3 * 2 * 2048 + 8] scratch (zeroed here)
+  unsigned int* hist;        // [3 * 2 * 2048 + 8] scratch (zeroed by the first launch)
 };
 int launch_rank_epilogue(const RankEpilogueArgs& a, cudaStream_t s);
 size_t rank_epilogue_hist_words();

@@ -81,19 +81,22 @@ int choose_cluster(int64_t N, int64_t M) {
   return want;
 }
 
-// A cluster of two can run as a CTA pair (tcgen05 cta_group::2, one M256 MMA issued by the leader):
+// A cluster of two runs as a CTA pair (tcgen05 cta_group::2, one M256 MMA issued by the leader):
 // each CTA stages and reads only ITS half of every gallery tile instead of receiving the full
-// tile by multicast and issuing its own M128 MMAs.  Measured on B200 (profiles/r01_summary.md):
-// +4.6 % on the streamed kernel (K' > 512: exact mode, D = 768), +4 % at K' <= 256, nothing on
-// the resident K' = 512 kernel, whose main loop already runs at the cuBLAS rate and is
-// power-limited by its epilogue.  VTC_PAIR=0/1 forces it off / on.
+// tile by multicast and issuing its own M128 MMAs -- a third less shared-memory operand traffic and
+// half the L2 -> SM gallery bytes per SM.  Measured on B200: +4.6 % on the streamed kernel (K' > 512:
+// exact mode, D = 768), +4 % at K' <= 256 (profiles/r01_summary.md); on the resident K' = 512 kernel,
+// which is limited by board power, +1 % in the sustained bench loop against the multicast flavour and
+// +4 % against unclustered CTAs (profiles/r02_summary.md) -- the cheaper data movement is what counts
+// under the power cap.  VTC_PAIR=0/1 forces it off / on (profiling).
 static bool use_pair(int num_kb) {
   static const int forced = []() {
     const char* e = getenv("VTC_PAIR");
     return e && *e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }();
+  (void)num_kb;
   if (forced >= 0) return forced != 0;
-  return num_kb > 8 || num_kb <= 4;
+  return true;
 }
 
 // VTC_DBG_PROF=1 (profiling only): a small device buffer the kernel's MMA issuer and first epilogue
@@ -135,8 +138,7 @@ Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split,
   Plan pl;
   pl.cluster = cluster < 1 ? 1 : cluster;
   pl.pair = pl.cluster == 2 && use_pair(p.num_kb);
-  pl.bn = bn == 128 ? 128 : BN;
-  min_tiles_per_split *= BN / pl.bn;
+  pl.bn = bn == 128 || bn == 64 ? bn : BN;
   static const int skip_epi = []() {
     const char* e = getenv("VTC_DBG_SKIP_EPILOGUE");
     return e && *e ? atoi(e) : 0;

@@ -36,6 +36,10 @@ struct Params {
   const float* qq;                   // [N] upper bound of ||q_t||^2
   const unsigned int* max_sq_bits;   // float bits of max_j ||x_j||^2 over the finite gallery rows
   float guard_rel;                   // bound of |tensor-core dot - exact dot| / (|q||x|)
+  // VTC_PREC_EXACT: what the 3-term bf16 split drops, bounded per ROW from the norms of the split's
+  // own pieces (rank_split_bound()) instead of the worst-case constant folded into guard_rel
+  const float2* qsplit;                 // [N] upper bounds of (|lo(q_t)|, |e(q_t)|); nullable
+  const unsigned int* split_max_bits;   // float bits of max_j |lo(x_j)|^2, max_j |e(x_j)|^2
   int metric_l2;                     // 1: score = ||x||^2 - 2 q.x, 0: score = -q.x
   int* rank;          // [N] += #{j : score < lo}
   int2* amb_list;     // (t, j0): row t has a score in [lo, hi] among columns [j0, j0 + 8);
@@ -119,14 +123,26 @@ int debug_prof_read(unsigned long long* out, int max_words);
 // below lo = d(t,gt) - delta and certainly not above hi = d(t,gt) + delta.
 //   dot error <= guard_rel * |q| * max|x|;  L2: d = sq32 - 2 acc in fp32 adds the roundings of sq32
 //   and of the FMA.  qq is an upper bound of |q|^2, gmax_sq the largest finite gallery norm^2.
+// What hi*hi + hi*lo + lo*hi drops of q.x, with q = hi + lo + e per element (hi = bf16(q),
+// lo = bf16(q - hi), e = q - hi - lo, all exact in fp32):  q.x - (hq.hx + hq.lx + lq.hx) =
+// q.ex + lq.lx + eq.(x - ex), so by Cauchy-Schwarz
+//   |dropped| <= |q| max|ex| + |lq| max|lx| + |eq| (max|x| + max|ex|).
+// The worst case over all inputs is 3 * 2^-16 |q||x| (tests/test_guard_band.py); the norms of real
+// rows' pieces give a bound ~10x smaller (|lo| ~ 1.1e-3 |x|, |e| ~ 1e-6 |x|), i.e. ~10x fewer column
+// groups in the fp64 re-check, and it is just as rigorous: it uses the pieces actually fed to the MMA.
+__host__ __device__ inline double rank_split_bound(double qn, double lqn, double eqn, double gn,
+                                                   double lxn, double exn) {
+  return qn * exn + lqn * lxn + eqn * (gn + exn);
+}
+
 __host__ __device__ inline void rank_band(double d0, double qq, double gmax_sq, int metric_l2,
-                                          float guard_rel, float* lo, float* hi) {
+                                          float guard_rel, double split_abs, float* lo, float* hi) {
   const double qn = sqrt(qq), gn = sqrt(gmax_sq);
   double delta;
   if (metric_l2)
-    delta = 2.0 * guard_rel * qn * gn + 2.4e-7 * (gmax_sq + 2.0 * qn * gn);
+    delta = 2.0 * (guard_rel * qn * gn + split_abs) + 2.4e-7 * (gmax_sq + 2.0 * qn * gn);
   else
-    delta = (double)guard_rel * qn * gn + 1.2e-7 * qn * gn;
+    delta = (double)guard_rel * qn * gn + split_abs + 1.2e-7 * qn * gn;
 #ifdef __CUDA_ARCH__
   *lo = __double2float_rd(d0 - delta);
   *hi = __double2float_ru(d0 + delta);
@@ -134,7 +150,7 @@ __host__ __device__ inline void rank_band(double d0, double qq, double gmax_sq, 
   *lo = (float)(d0 - delta);
   *hi = (float)(d0 + delta);
 #endif
-  if (!(qq == qq) || !(d0 == d0)) *lo = *hi = nanf("");
+  if (!(qq == qq) || !(d0 == d0) || !(delta == delta)) *lo = *hi = nanf("");
 }
 
 }  // namespace tc

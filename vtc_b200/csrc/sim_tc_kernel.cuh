@@ -109,7 +109,8 @@ struct RankEpi {
     lo = hi = nanf("");
     gtc = INT_MIN / 2;
     if (t < p.N) {
-      band(p.dgt[t], p.qq[t], p.max_sq_bits, p.metric_l2, p.guard_rel, &lo, &hi);
+      band(p.dgt[t], p.qq[t], p.max_sq_bits, p.metric_l2, p.guard_rel,
+           p.qsplit ? p.qsplit + t : nullptr, p.split_max_bits, &lo, &hi);
       const int64_t g = (p.gt ? p.gt[t] : t + p.gt_row_offset) - p.gt_col_offset;
       if (g >= 0 && g < p.M) gtc = (int)g;
     }
@@ -117,8 +118,17 @@ struct RankEpi {
   // once per row and work item (dozens of tiles): out of line, so that the double-precision square
   // roots stay out of the instruction-cache footprint of the per-column loop
   static __device__ __noinline__ void band(double d0, float qq, const unsigned int* max_sq_bits,
-                                           int metric_l2, float guard_rel, float* lo, float* hi) {
-    rank_band(d0, (double)qq, (double)__uint_as_float(*max_sq_bits), metric_l2, guard_rel, lo, hi);
+                                           int metric_l2, float guard_rel, const float2* qsplit,
+                                           const unsigned int* split_max_bits, float* lo, float* hi) {
+    const double gmax_sq = (double)__uint_as_float(*max_sq_bits);
+    double split_abs = 0.0;
+    if (qsplit) {
+      const float2 qs = *qsplit;
+      split_abs = rank_split_bound(sqrt((double)qq), (double)qs.x, (double)qs.y, sqrt(gmax_sq),
+                                   sqrt((double)__uint_as_float(split_max_bits[0])),
+                                   sqrt((double)__uint_as_float(split_max_bits[1])));
+    }
+    rank_band(d0, (double)qq, gmax_sq, metric_l2, guard_rel, split_abs, lo, hi);
   }
   // rare: this row has a score inside the guard band among columns [j, j+8): hand the whole group
   // to the fp64 re-check (its definite count is NOT added here).  List segments are per CTA, slots
@@ -541,7 +551,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const Params p) {
   static_assert(!kPair || kC == 2, "a CTA pair is a cluster of two");
-  static_assert(kBN == 256 || kBN == 128, "tile widths built: 256 and 128 gallery rows");
+  static_assert(kBN == 256 || kBN == 128 || kBN == 64, "tile widths built: 256, 128, 64 gallery rows");
   using L = SmemLayout<kRes, kPair, kBN, Epi::kStageBytes>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* res_a = smem;
@@ -558,9 +568,15 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // programmatic dependent launch (common.cuh): the next kernel of the stream may be scheduled once
+  // every CTA of this one is running; this one touches global memory only below griddep_wait()
+  griddep_launch();
   // a gated fallback pass that is not needed: every CTA sees the same flag and leaves before any
   // barrier, cluster or tensor-memory state exists
-  if (p.run_flag && *p.run_flag == 0u) return;
+  if (p.run_flag) {
+    griddep_wait();
+    if (*p.run_flag == 0u) return;
+  }
 
   if (threadIdx.x == 0) {
     *seg_count = 0;
@@ -597,6 +613,9 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (kC > 1) cluster_sync_all();  // peers' barriers are initialised before anything crosses CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // set-up done (shared memory, tensor memory, descriptor prefetch only): from here on the kernel
+  // reads what its predecessors wrote
+  griddep_wait();
 
   // Work items are dealt to CLUSTERS: the kC CTAs of a cluster take kC consecutive query tiles
   // against the same gallery tiles, so every gallery stage is fetched from L2 once per cluster
@@ -797,6 +816,23 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
         tmem_ld_wait(va);
+        if constexpr (kHalfCols == 32) {
+          // 64-column tiles (small dense products): one chunk per warp and tile
+          (void)vb, (void)next_j0;
+          __syncwarp();
+          if (lane < 8)
+            reinterpret_cast<float4*>(wbias)[lane] =
+                __ldg(reinterpret_cast<const float4*>(p.col_bias + j0) + lane);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair)
+              mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+            else
+              mbar_arrive(&tmem_empty[as]);
+          }
+          if (!p.dbg_skip_epilogue) epi.chunk(p, va, wbias, scale, j0, seg_count);
+        } else {
 #pragma unroll 1
         for (int c = 0; c < kHalfCols / 32; c += 2) {
           // stage the bias of columns [32c, 32c + 64) and start fetching the following 64
@@ -826,6 +862,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
           if (!p.dbg_skip_epilogue) epi.chunk(p, vb, wbias + 32, scale, j0 + (c + 1) * 32, seg_count);
           if (c + 2 < kHalfCols / 32) tmem_ld_wait(va);
+        }
         }
         as ^= 1;
         if (as == 0) aphase ^= 1;
@@ -868,13 +905,22 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kC;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (kC > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = kC;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = kC > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
   if (e != cudaSuccess) return cuda_err(e);
   return VTC_OK;

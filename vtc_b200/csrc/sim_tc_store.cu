@@ -10,8 +10,10 @@ int launch_store(bool a_resident, int bn, const CUtensorMap& tmA, const CUtensor
   // always the streamed kernel: these products have a tile or two per CTA, so a resident query tile
   // buys nothing, and its shared memory is what holds the epilogue's transposing tiles
   (void)a_resident;
-  if (bn == 128)  // narrow tiles: twice the CTAs for the skinny products of the CAM
-    return launch_instance<StoreEpi, false, 1, false, 128>(tmA, tmB, p, grid, s);
+  // narrow tiles put more SMs to work on the skinny products of the CAM (a CTA pulls ~50 B/clk from
+  // L2, so the operand bytes per CTA bound these launches, not the MMAs)
+  if (bn == 128) return launch_instance<StoreEpi, false, 1, false, 128>(tmA, tmB, p, grid, s);
+  if (bn == 64) return launch_instance<StoreEpi, false, 1, false, 64>(tmA, tmB, p, grid, s);
   return launch_instance<StoreEpi, false, 1>(tmA, tmB, p, grid, s);
 }
 
