@@ -28,7 +28,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define VTC_ABI_VERSION 2
+#define VTC_ABI_VERSION 3
 
 typedef void* vtc_stream_t; /* a cudaStream_t */
 
@@ -192,10 +192,15 @@ int vtc_infonce_fwd(const void* A, const void* B, int64_t n, int D, int dtype, i
                     const float* scale, float* loss, float* row_lse, float* col_lse, float* diag,
                     void* ws, size_t ws_bytes, vtc_stream_t stream);
 
-/* backward of vtc_infonce_fwd: dA, dB fp32 [n,D], dscale (device float); grad_loss device float. */
-int vtc_infonce_bwd(const void* A, const void* B, int64_t n, int D, int dtype, const float* scale,
-                    const float* row_lse, const float* col_lse, const float* grad_loss, float* dA,
-                    float* dB, float* dscale, void* ws, size_t ws_bytes, vtc_stream_t stream);
+/* backward of vtc_infonce_fwd (loss.backward() of model/loss.py:18-22, trainer/trainer.py:79):
+ * dA, dB fp32 [n,D], dscale (device float); grad_loss device float; `precision` as in the forward
+ * (the logits are recomputed from the same operands the saved log-sum-exps were reduced from).
+ * n <= 2048: fp32 SIMT tiles; larger: tcgen05 -- logit tiles recomputed, gradient weights handed on
+ * as bf16 operand strips of <= 64 MB, no n x n array (fp32 features only). */
+int vtc_infonce_bwd(const void* A, const void* B, int64_t n, int D, int dtype, int precision,
+                    const float* scale, const float* row_lse, const float* col_lse,
+                    const float* grad_loss, float* dA, float* dB, float* dscale, void* ws,
+                    size_t ws_bytes, vtc_stream_t stream);
 
 /* ---- H4: Context Adapter Module pieces (model/model.py:141-205) --------------------------------
  * vtc_cam_stack_normalize: X[l] = normalize(l == 0 ? main : aux[l-1]) -> X [L,b,D]   (:150-151)

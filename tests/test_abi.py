@@ -25,7 +25,7 @@ def test_header_declares_what_the_binding_binds():
 def test_library_exports_every_declared_symbol(lib):
     for name in _declared_symbols():
         assert hasattr(lib, name), f"{name} not exported by libvtc_b200.so"
-    assert lib.vtc_abi_version() == 2
+    assert lib.vtc_abi_version() == 3
     assert lib.vtc_strerror(0) == b"ok"
     assert b"workspace" in lib.vtc_strerror(-3)
 

@@ -624,6 +624,64 @@ def test_clip_loss_backward_and_dense_sim(cuda_dev, golden):
     np.testing.assert_allclose(_np(torch.diagonal(lz)), np.diag(g["small_sim"]), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("n,D,precision", [(2100, 64, "exact"), (2100, 64, "bf16"),
+                                           (2304, 200, "exact"), (4096, 512, "bf16")])
+def test_clip_loss_backward_tensor_cores(cuda_dev, n, D, precision):
+    """loss.backward() of model/loss.py:18-22 (trainer/trainer.py:79) for n > 2048: the tcgen05 path of
+    vtc_infonce_bwd (logit tiles recomputed, gradient weights as bf16 operand strips) against torch
+    autograd through the reference formula in fp64 on the device (oracle.clip_loss is that formula;
+    n x n in fp64 is too slow for the CPU at these sizes)."""
+    from vtc_b200.model import LazySim, clip_loss
+
+    s = 30.0
+    vis, txt = make_batch_pair(n, D, seed=21)
+    if precision == "bf16":  # the bf16 mode differentiates the loss of the bf16-rounded features
+        vis, txt = torch.from_numpy(O.bf16_round(vis.numpy())), torch.from_numpy(O.bf16_round(txt.numpy()))
+    a0 = vis.to(cuda_dev).double().requires_grad_(True)
+    t0 = txt.to(cuda_dev).double().requires_grad_(True)
+    ls0 = torch.tensor(math.log(s), device=cuda_dev, dtype=torch.float64, requires_grad=True)
+    sim = ls0.exp() * a0 @ t0.t()
+    lab = torch.arange(n, device=cuda_dev)
+    want = 0.5 * (torch.nn.functional.cross_entropy(sim, lab) + torch.nn.functional.cross_entropy(sim.t(), lab))
+    want.backward()
+    a = vis.to(cuda_dev).requires_grad_(True)
+    t = txt.to(cuda_dev).requires_grad_(True)
+    ls = torch.tensor(math.log(s), device=cuda_dev, requires_grad=True)
+    loss = clip_loss((a, t, LazySim(a, t, ls.exp(), precision)), {})
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=1e-4 if precision == "exact" else 2e-2)
+    # gradient rows are sums of n weighted unit vectors: compare against the largest entry
+    rtol = 1e-3 if precision == "exact" else 2e-2
+    for got, ref in ((a.grad, a0.grad), (t.grad, t0.grad)):
+        ref = ref.float()
+        err = (got - ref).abs().max().item()
+        assert err <= rtol * ref.abs().max().item(), (err, ref.abs().max().item())
+    np.testing.assert_allclose(ls.grad.item(), ls0.grad.item(), rtol=5 * rtol, atol=1e-6)
+
+
+def test_clip_loss_forward_backward_n16384(cuda_dev):
+    """n = 16384: beyond the n <= 8192 cap of round 1 (an n x n fp32 matrix in the workspace); the
+    strips keep the scratch at O(R n).  Checked on a slice of rows against fp64."""
+    from vtc_b200.model import LazySim, clip_loss
+
+    n, D, s = 16384, 512, 100.0
+    gen = torch.Generator(device=cuda_dev).manual_seed(11)
+    V = torch.nn.functional.normalize(torch.randn(n, D, generator=gen, device=cuda_dev), dim=1)
+    T = torch.nn.functional.normalize(V + 8.0 * torch.randn(n, D, generator=gen, device=cuda_dev) / D ** 0.5, dim=1)
+    a, t = V.clone().requires_grad_(True), T.clone().requires_grad_(True)
+    loss = clip_loss((a, t, LazySim(a, t, torch.tensor(s, device=cuda_dev), "exact")), {})
+    loss.backward()
+    sim = s * (V.double() @ T.double().t())
+    row, col = torch.logsumexp(sim, dim=1), torch.logsumexp(sim, dim=0)
+    W = (torch.exp(sim - row[:, None]) + torch.exp(sim - col[None, :])) / (2 * n)
+    W -= torch.eye(n, device=cuda_dev, dtype=torch.float64) / n
+    wantA = (s * W[:256] @ T.double()).float()
+    wantB = (s * W[:, :256].t() @ V.double()).float()
+    for got, ref in ((a.grad[:256], wantA), (t.grad[:256], wantB)):
+        err = (got - ref).abs().max().item()
+        assert err <= 1e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------ H4
 def _make_cam(D, layers, heads, params, init_from_avg, flw, dev, precision="exact"):
     from vtc_b200.model import PretrainedCLIP_finaltf

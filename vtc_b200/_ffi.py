@@ -18,7 +18,7 @@ PREC_EXACT, PREC_BF16, PREC_BRUTE = 0, 1, 2
 OP_SIM_RANK, OP_SIM_TOPK, OP_INFONCE_FWD, OP_SIM_MATRIX, OP_INFONCE_BWD, OP_GT_SCORES, OP_LINEAR = range(7)
 CAM_READOUT_AVG, CAM_READOUT_RESIDUAL_ONLY, CAM_READOUT_UNIFORM = 0, 1, 2
 RESACT_NONE, RESACT_NORMALIZE_EPS, RESACT_SQUASH, RESACT_TANH, RESACT_AFFINE = range(5)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _P = c_void_p
 
@@ -48,7 +48,7 @@ SIGNATURES = {
     "vtc_topk_merge": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P]),
     "vtc_infonce_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P,
                                 c_size_t, _P]),
-    "vtc_infonce_bwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
+    "vtc_infonce_bwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                 c_size_t, _P]),
     "vtc_cam_stack_normalize": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P]),
     "vtc_layernorm": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P]),

@@ -597,6 +597,121 @@ int infonce_fwd_impl(const void* A, const void* B, int64_t n, int D, int dtype, 
   return launch_infonce_loss(row_lse, col_lse, w.diag_raw, scale, n, diag, loss, s);
 }
 
+// Backward of the symmetric InfoNCE on the tensor cores (n > kNceSmallMax; smaller batches take the
+// single SIMT path of infonce_bwd.cu):  W = g/2n (softmax_row + softmax_col - 2I),  dA = s W B,
+// dB = s W^T A,  ds = sum W .* (A B^T)   (the autograd of model/loss.py:18-22 through
+// model/model.py:369).  W is never formed as an n x n matrix: for a block of R query rows
+//   (1) the logit tiles are RECOMPUTED by the tcgen05 GEMM (same operands and precision as the
+//       forward, so the exponentials meet the saved log-sum-exps they were reduced from) and leave
+//       the epilogue as gradient weights in bf16 OPERAND form (StoreEpi act = 2): an R x n strip,
+//   (2) a second tcgen05 GEMM multiplies the strip with B^T-as-operand: dA[block] = s W_blk B.
+// dB is the same computation with the roles of A and B swapped (W^T of (A, B) is W of (B, A) with
+// the log-sum-exps exchanged), so no transposed strip and no accumulation across blocks is needed:
+// 4 n^2 D tensor-core FLOPs instead of the minimal 3, and scratch O(R n) (<= 64 MB) for any n.
+constexpr size_t kNceBwdStripBytes = (size_t)64 << 20;
+struct NceBwdWs {
+  __nv_bfloat16 *opA, *opB, *opAt, *opBt, *strip;
+  float *tA, *tB, *colb, *rowb, *zb, *dsp;
+  int64_t R;
+  int KpD, KpN;
+};
+NceBwdWs carve_nce_bwd(Workspace& ws, int64_t n, int D, int precision) {
+  NceBwdWs w;
+  memset(&w, 0, sizeof(w));
+  const OperandPlan od = plan_operands(D, VTC_F32, precision);
+  const int64_t kn = round_up<int64_t>((od.split ? 3 : 1) * n, tc::BK);
+  w.KpD = od.Kp, w.KpN = (int)kn;
+  int64_t R = (int64_t)(kNceBwdStripBytes / ((size_t)kn * 2)) / tc::BM * tc::BM;
+  if (R < tc::BM) R = tc::BM;
+  if (R > n) R = n;
+  w.R = R;
+  const int64_t npad = round_up<int64_t>(n, tc::BN);
+  w.opA = ws.take<__nv_bfloat16>((size_t)n * od.Kp);
+  w.opB = ws.take<__nv_bfloat16>((size_t)n * od.Kp);
+  w.tA = ws.take<float>((size_t)D * n);
+  w.tB = ws.take<float>((size_t)D * n);
+  w.opAt = ws.take<__nv_bfloat16>((size_t)D * kn);
+  w.opBt = ws.take<__nv_bfloat16>((size_t)D * kn);
+  w.strip = ws.take<__nv_bfloat16>((size_t)R * kn);
+  w.colb = ws.take<float>(npad);
+  w.rowb = ws.take<float>(npad);
+  w.zb = ws.take<float>(round_up<int64_t>(D, tc::BN));
+  w.dsp = ws.take<float>((size_t)128 * R);
+  return w;
+}
+
+}  // namespace
+
+// cam_bwd.cu / infonce_bwd.cu
+int launch_transpose(const float* in, int64_t R, int64_t C, float* out, cudaStream_t s);
+int launch_nce_ds_reduce(const float* part, int64_t count, float* out, cudaStream_t s);
+
+int infonce_bwd_tc_impl(const float* A, const float* B, int64_t n, int D, int precision,
+                        const float* scale, const float* row_lse, const float* col_lse,
+                        const float* grad_loss, float* dA, float* dB, float* dscale, void* wsp,
+                        size_t ws_bytes, cudaStream_t s) {
+  if (n > kMaxRows || D > 8192 || 3 * n > 0x7ffffff0) return VTC_ERR_UNSUPPORTED_SHAPE;
+  Workspace ws(wsp, ws_bytes);
+  NceBwdWs w = carve_nce_bwd(ws, n, D, precision);
+  if (!ws.ok()) return VTC_ERR_WORKSPACE;
+  const OperandPlan od = plan_operands(D, VTC_F32, precision);
+  const int split = od.split ? 1 : 0;
+  const int64_t npad = round_up<int64_t>(n, tc::BN);
+  VTC_RETURN_IF_ERROR(launch_prep_operand(A, false, n, D, D, split ? PREP_SPLIT_A : PREP_PLAIN, w.opA, w.KpD, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(B, false, n, D, D, split ? PREP_SPLIT_B : PREP_PLAIN, w.opB, w.KpD, s));
+  // A^T, B^T as gallery-side operands [D, K' = n]: the right-hand sides of the gradient products
+  VTC_RETURN_IF_ERROR(launch_transpose(A, n, D, w.tA, s));
+  VTC_RETURN_IF_ERROR(launch_transpose(B, n, D, w.tB, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(w.tA, false, D, (int)n, n, split ? PREP_SPLIT_B : PREP_PLAIN, w.opAt, w.KpN, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(w.tB, false, D, (int)n, n, split ? PREP_SPLIT_B : PREP_PLAIN, w.opBt, w.KpN, s));
+  VTC_RETURN_IF_ERROR(launch_fill_bias(w.colb, col_lse, n, npad, INFINITY, s));
+  VTC_RETURN_IF_ERROR(launch_fill_bias(w.rowb, row_lse, n, npad, INFINITY, s));
+  VTC_RETURN_IF_ERROR(launch_fill_bias(w.zb, nullptr, D, round_up<int64_t>(D, tc::BN), 0.f, s));
+  // padding columns of the strip stay zero for the whole call (the epilogue never writes them)
+  cudaError_t e = cudaMemsetAsync(w.strip, 0, (size_t)w.R * w.KpN * sizeof(__nv_bfloat16), s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dscale, 0, sizeof(float), s);
+  if (e != cudaSuccess) return cuda_err(e);
+  for (int dir = 0; dir < 2; ++dir) {
+    // dir 0: rows of A against B -> dA (and ds);  dir 1: rows of B against A -> dB
+    const __nv_bfloat16* opX = dir == 0 ? w.opA : w.opB;
+    const __nv_bfloat16* opY = dir == 0 ? w.opB : w.opA;
+    const __nv_bfloat16* opYt = dir == 0 ? w.opBt : w.opAt;
+    const float* rstat = dir == 0 ? row_lse : col_lse;
+    const float* cbias = dir == 0 ? w.colb : w.rowb;
+    float* dX = dir == 0 ? dA : dB;
+    for (int64_t r0 = 0; r0 < n; r0 += w.R) {
+      const int64_t rows = n - r0 < w.R ? n - r0 : w.R;
+      tc::Params p;
+      memset(&p, 0, sizeof(p));
+      p.N = rows, p.M = n, p.num_kb = w.KpD / tc::BK;
+      p.col_bias = cbias, p.scale_ptr = scale, p.scale = 1.f;
+      p.act = 2, p.row_stat = rstat + r0, p.coef_ptr = grad_loss, p.coef_scale = 0.5f / (float)n;
+      p.diag_offset = r0, p.ds_part = dir == 0 ? w.dsp : nullptr;
+      p.out_op = w.strip, p.out_op_kp = w.KpN, p.out_op_split = split;
+      const tc::Plan pl = tc::plan_tiles(p, 64, 1, 1, store_tile_width(rows, n));
+      CUtensorMap tmA, tmB;
+      VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opX + (size_t)r0 * w.KpD, rows, w.KpD, w.KpD, tc::BM, &tmA));
+      VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opY, n, w.KpD, w.KpD, pl.bn, &tmB));
+      VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_STORE, false, pl, tmA, tmB, p, s));
+      if (dir == 0)
+        VTC_RETURN_IF_ERROR(launch_nce_ds_reduce(w.dsp, (int64_t)2 * p.g_splits * rows, dscale, s));
+      tc::Params q;
+      memset(&q, 0, sizeof(q));
+      q.N = rows, q.M = D, q.num_kb = w.KpN / tc::BK;
+      q.col_bias = w.zb, q.scale_ptr = scale, q.scale = 1.f;
+      q.out = dX + (size_t)r0 * D, q.ldo = D;
+      const tc::Plan pl2 = tc::plan_tiles(q, 64, 1, 1, store_tile_width(rows, D));
+      CUtensorMap tmW, tmY;
+      VTC_RETURN_IF_ERROR(tc::make_operand_tmap(w.strip, rows, w.KpN, w.KpN, tc::BM, &tmW));
+      VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opYt, D, w.KpN, w.KpN, pl2.bn, &tmY));
+      VTC_RETURN_IF_ERROR(tc::launch_sim_tc(tc::EPI_STORE, false, pl2, tmW, tmY, q, s));
+    }
+  }
+  return VTC_OK;
+}
+
+namespace {
+
 
 // ----------------------------------------------------------------------- prepared linears / CAM
 // A "prepared" linear holds its weight as the gallery-side bf16 operand [out_f, Kp] followed by the
@@ -750,7 +865,12 @@ size_t vtc_workspace_bytes(int op, int64_t N, int64_t M, int D, int precision) {
     case VTC_OP_LINEAR:
       carve_gemm(ws, N, M, D, VTC_F32, precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision);
       break;
-    case VTC_OP_INFONCE_BWD: ws.take<float>((size_t)N * N); break;
+    case VTC_OP_INFONCE_BWD: {
+      carve_nce_bwd(ws, N, D, precision == VTC_PREC_BRUTE ? VTC_PREC_EXACT : precision);
+      const size_t small = N <= kNceSmallMax ? (size_t)N * N * sizeof(float) + 256 : 0;
+      if (small > ws.used) ws.used = small;
+      break;
+    }
     case VTC_OP_GT_SCORES:
       ws.take<double>(M);
       ws.take<__nv_bfloat16>((size_t)N * round_up(D, tc::BK));

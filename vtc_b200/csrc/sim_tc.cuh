@@ -72,7 +72,17 @@ struct Params {
   int out_op_kp;
   int out_op_split;       // 0: [x], 1: [hi | hi | lo] (VTC_PREC_EXACT)
   const float* residual;  // optional [N, ldo]
-  int act;                // 0 none, 1 QuickGELU (applied after bias, before residual)
+  int act;                // 0 none, 1 QuickGELU (applied after bias, before residual),
+                          // 2 InfoNCE gradient weight (below)
+  // act == 2 (backward of the symmetric InfoNCE, model/loss.py:18-22): with x = scale * acc the logit,
+  //   z = coef * (exp(x - row_stat[t]) + exp(x - col_bias[j]) - 2 [t + diag_offset == j]),
+  // coef = *coef_ptr * coef_scale (= grad_loss / 2n); col_bias holds the other side's log-sum-exp
+  // (+inf on padding columns).  z leaves as the bf16 operand of the gradient product (out_op);
+  // ds_part[part * N + t] = sum_j z * acc for the gradient of the logit scale.
+  const float* row_stat;
+  const float* coef_ptr;
+  float coef_scale;
+  float* ds_part;
   // EPI_TOPK
   float2* pool;       // [2 * g_splits, N, TOPK_POOL] (score, column index as int bits)
   float2* pool_meta;  // [2 * g_splits, N] (entries, tau): every column outside the pool scores >= tau

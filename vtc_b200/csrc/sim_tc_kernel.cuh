@@ -281,10 +281,18 @@ struct StoreEpi {
   static constexpr int kStageBytes = 32 * 32 * 4;
   int64_t t, t0w;  // this thread's row, first row of the warp's 32-row block
   float* st;       // warp-private 32 x 32 fp32 staging tile
+  float rstat, coef, dsum;  // act == 2: this row's log-sum-exp, grad_loss / 2n, sum_j z * acc
   __device__ __forceinline__ void bind_stage(float* s) { st = s; }
-  __device__ __forceinline__ void begin_item(const Params&, int64_t t_, int) {
+  __device__ __forceinline__ void begin_item(const Params& p, int64_t t_, int) {
     t = t_;
     t0w = t_ - (threadIdx.x & 31);
+    dsum = 0.f;
+    rstat = INFINITY;
+    coef = 0.f;
+    if (p.act == 2) {
+      if (t < p.N) rstat = p.row_stat[t];  // (rows of the tile padding: exp(x - inf) = 0)
+      coef = *p.coef_ptr * p.coef_scale;
+    }
   }
   // float4 slot q (0..7) of staged row r lives at r * 32 + 4 * (q ^ (r & 7))
   static __device__ __forceinline__ int slot(int r, int q) { return r * 32 + 4 * (q ^ (r & 7)); }
@@ -311,6 +319,15 @@ struct StoreEpi {
       for (int e = 0; e < 4; ++e) {
         float z = fmaf(scale, __uint_as_float(v[4 * i + e]), bb[e]);
         if (p.act == 1) z = z / (1.f + __expf(-1.702f * z));  // QuickGELU: z * sigmoid(1.702 z)
+        if (p.act == 2) {
+          const float acc = __uint_as_float(v[4 * i + e]), x = scale * acc;
+          // (the split operands carry fp32 logits: accurate exponentials there)
+          const float er = p.out_op_split ? expf(x - rstat) : __expf(x - rstat);
+          const float ec = p.out_op_split ? expf(x - bb[e]) : __expf(x - bb[e]);
+          z = coef * (er + ec);
+          if (t + p.diag_offset == jbase + 4 * i + e) z -= 2.f * coef;
+          dsum = fmaf(z, acc, dsum);
+        }
         y[4 * i + e] = z;
       }
     }
@@ -402,7 +419,9 @@ struct StoreEpi {
       }
     }
   }
-  __device__ __forceinline__ void end_item(const Params&, int) {}
+  __device__ __forceinline__ void end_item(const Params& p, int part) {
+    if (p.act == 2 && p.ds_part && t < p.N) p.ds_part[(int64_t)part * p.N + t] = dsum;
+  }
 };
 
 // Streaming top-k: every row appends the scores that beat its threshold `tau` to a 64-entry

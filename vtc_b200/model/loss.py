@@ -26,12 +26,13 @@ class _FusedClipLoss(torch.autograd.Function):
         ctx.save_for_backward(a, b, scale.detach() if isinstance(scale, torch.Tensor) else
                               torch.tensor(float(scale), device=a.device), row, col)
         ctx.scale_is_tensor = isinstance(scale, torch.Tensor)
+        ctx.precision = precision
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
         a, b, scale, row, col = ctx.saved_tensors
-        dA, dB, ds = ops.infonce_bwd(a, b, scale, row, col, grad_out)
+        dA, dB, ds = ops.infonce_bwd(a, b, scale, row, col, grad_out, ctx.precision)
         dscale = ds.reshape(scale.shape).to(scale.dtype) if ctx.scale_is_tensor else None
         return dA.to(a.dtype), dB.to(b.dtype), dscale, None
 

@@ -426,10 +426,11 @@ def infonce_fwd(a: torch.Tensor, b: torch.Tensor, scale, precision="exact"
 
 
 def infonce_bwd(a: torch.Tensor, b: torch.Tensor, scale, row_lse: torch.Tensor,
-                col_lse: torch.Tensor, grad_loss: torch.Tensor
+                col_lse: torch.Tensor, grad_loss: torch.Tensor, precision="exact"
                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Backward of infonce_fwd w.r.t. both feature matrices and the logit scale (the autograd of
-    model/loss.py:18-22 through model/model.py:369): (dA [n,D], dB [n,D], dscale [1]) fp32."""
+    model/loss.py:18-22 through model/model.py:369): (dA [n,D], dB [n,D], dscale [1]) fp32.
+    `precision` must be the forward's: the logits are recomputed from the same operands."""
     dev = _req_cuda(a, b, row_lse, col_lse, grad_loss)
     a, b = _mat(a, "a"), _mat(b, "b")
     n, D = a.shape
@@ -439,8 +440,9 @@ def infonce_bwd(a: torch.Tensor, b: torch.Tensor, scale, row_lse: torch.Tensor,
     dB = torch.empty_like(dA)
     ds = torch.empty(1, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        ws = _workspace(dev, _ws_bytes(_ffi.OP_INFONCE_BWD, n, n, D, _ffi.PREC_EXACT))
-        _ffi.check(_ffi.load().vtc_infonce_bwd(_ptr(a), _ptr(b), n, D, _dtype_code(a), _ptr(sc),
+        prec = _prec(precision)
+        ws = _workspace(dev, _ws_bytes(_ffi.OP_INFONCE_BWD, n, n, D, prec))
+        _ffi.check(_ffi.load().vtc_infonce_bwd(_ptr(a), _ptr(b), n, D, _dtype_code(a), prec, _ptr(sc),
                                                _ptr(row_lse), _ptr(col_lse), _ptr(g), _ptr(dA),
                                                _ptr(dB), _ptr(ds), _ptr(ws), ws.numel(),
                                                _stream(dev)), "vtc_infonce_bwd")
