@@ -202,6 +202,15 @@ int vtc_infonce_bwd(const void* A, const void* B, int64_t n, int D, int dtype, i
                     const float* grad_loss, float* dA, float* dB, float* dscale, void* ws,
                     size_t ws_bytes, vtc_stream_t stream);
 
+/* clip_loss on a MATERIALISED sim [n, n] fp32 (what the reference's own forward returns,
+ * model/model.py:369 -> model/loss.py:19): row / column log-sum-exp + diagonal in one pass over the
+ * matrix, then the scalar; the backward is elementwise (d loss / d sim). */
+int vtc_infonce_dense_fwd(const float* sim, int64_t n, int64_t ld, float* loss, float* row_lse,
+                          float* col_lse, float* diag, vtc_stream_t stream);
+int vtc_infonce_dense_bwd(const float* sim, int64_t n, int64_t ld, const float* row_lse,
+                          const float* col_lse, const float* grad_loss, float* dsim, int64_t ldd,
+                          vtc_stream_t stream);
+
 /* ---- H4: Context Adapter Module pieces (model/model.py:141-205) --------------------------------
  * vtc_cam_stack_normalize: X[l] = normalize(l == 0 ? main : aux[l-1]) -> X [L,b,D]   (:150-151)
  * vtc_layernorm          : fp32 LayerNorm over the last dim, eps 1e-5 (clip.model.LayerNorm)

@@ -624,6 +624,25 @@ def test_clip_loss_backward_and_dense_sim(cuda_dev, golden):
     np.testing.assert_allclose(_np(torch.diagonal(lz)), np.diag(g["small_sim"]), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("n,s", [(300, 100.0), (1000, 14.29), (33, 1.0)])
+def test_clip_loss_on_a_materialised_sim(cuda_dev, n, s):
+    """model/loss.py:18-22 handed a real tensor (the reference's own forward returns one,
+    model/model.py:369): reductions over the matrix itself (csrc/infonce_dense.cu), loss and
+    d loss / d sim against the reference formula in fp64."""
+    from vtc_b200.model import clip_loss
+
+    vis, txt = make_batch_pair(n, 128, seed=9)
+    sim0 = (s * vis.double() @ txt.double().t()).requires_grad_(True)
+    want = O.clip_loss(sim0)
+    want.backward()
+    sim = sim0.detach().float().to(cuda_dev).requires_grad_(True)
+    loss = clip_loss((None, None, sim), {})
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=1e-4, atol=1e-6)
+    # (entries are <= 1/n; the diagonal ones cancel against -1/n, so bound them absolutely)
+    np.testing.assert_allclose(_np(sim.grad), sim0.grad.numpy(), rtol=2e-3, atol=3e-5 / n)
+
+
 @pytest.mark.parametrize("n,D,precision", [(2100, 64, "exact"), (2100, 64, "bf16"),
                                            (2304, 200, "exact"), (4096, 512, "bf16")])
 def test_clip_loss_backward_tensor_cores(cuda_dev, n, D, precision):

@@ -50,6 +50,8 @@ SIGNATURES = {
                                 c_size_t, _P]),
     "vtc_infonce_bwd": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                                 c_size_t, _P]),
+    "vtc_infonce_dense_fwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "vtc_infonce_dense_bwd": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P]),
     "vtc_cam_stack_normalize": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P]),
     "vtc_layernorm": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P]),
     "vtc_cam_attn_core": (c_int, [_P, c_int, c_int64, c_int, c_int, _P, _P]),

@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libvtc_b200.so")
 SOURCES = ["api.cu", "sim_tc.cu", "sim_tc_rank.cu", "sim_tc_topk.cu", "sim_tc_lse.cu", "sim_tc_store.cu",
-           "exact.cu", "rank_stage.cu", "prep.cu", "reduce.cu", "cam.cu", "infonce_bwd.cu", "infonce_small.cu", "cam_bwd.cu"]
+           "exact.cu", "rank_stage.cu", "prep.cu", "reduce.cu", "cam.cu", "infonce_bwd.cu", "infonce_small.cu", "infonce_dense.cu", "cam_bwd.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -5,7 +5,7 @@ three losses there are unused by every shipped config -- SURVEY.md §2 row 1).
 `input[2]`.  When that is a :class:`LazySim` (what this package's model forward returns) the
 N x N logit matrix is never formed: one fused tcgen05 pass per direction yields the row / column
 log-sum-exp and the diagonal (csrc/sim_tc.cu, EPI_LSE).  When it is a materialised CUDA tensor the
-same reductions run over that tensor.  Both are differentiable.
+same reductions run over that tensor (csrc/infonce_dense.cu).  Both are differentiable.
 """
 from __future__ import annotations
 
@@ -37,6 +37,22 @@ class _FusedClipLoss(torch.autograd.Function):
         return dA.to(a.dtype), dB.to(b.dtype), dscale, None
 
 
+class _DenseClipLoss(torch.autograd.Function):
+    """clip_loss of a materialised sim: three reductions of the matrix, elementwise backward."""
+
+    @staticmethod
+    def forward(ctx, sim):
+        s = sim.detach().float().contiguous()
+        loss, row, col, _diag = ops.infonce_dense_fwd(s)
+        ctx.save_for_backward(s, row, col)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        s, row, col = ctx.saved_tensors
+        return ops.infonce_dense_bwd(s, row, col, grad_out)
+
+
 def clip_loss(input, meta=None, precision: str = None, **loss_args):
     """0.5 * (CE(sim, arange) + CE(sim.t(), arange)) -- model/loss.py:18-22."""
     sim = input[2]
@@ -51,8 +67,5 @@ def clip_loss(input, meta=None, precision: str = None, **loss_args):
         raise ops.VtcError("clip_loss: vtc_b200 has no CPU path; move `sim` to a CUDA device")
     if sim.dim() != 2 or sim.shape[0] != sim.shape[1]:
         raise ValueError("clip_loss requires a square similarity matrix")
-    # A materialised sim is the product (s*A) @ B.t() of *some* features we no longer see; treat
-    # it as features A = sim, B = I with unit scale:  (1 * sim) @ I.t() == sim.
-    eye = torch.eye(sim.shape[0], device=sim.device, dtype=torch.float32)
-    one = torch.ones((), device=sim.device)
-    return _FusedClipLoss.apply(sim.float(), eye, one, "exact")
+    # a materialised sim (what the reference's forward hands over): reduce the matrix itself
+    return _DenseClipLoss.apply(sim).to(sim.dtype)

@@ -449,6 +449,35 @@ def infonce_bwd(a: torch.Tensor, b: torch.Tensor, scale, row_lse: torch.Tensor,
     return dA, dB, ds
 
 
+def infonce_dense_fwd(sim: torch.Tensor):
+    """clip_loss of a materialised fp32 [n, n] sim: (loss [1], row_lse, col_lse, diag)."""
+    dev = _req_cuda(sim)
+    sim = _mat(sim, "sim")
+    n = sim.shape[0]
+    if sim.shape[1] != n or sim.dtype != torch.float32:
+        raise ValueError("sim must be a square fp32 matrix")
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    row, col, diag = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_infonce_dense_fwd(_ptr(sim), n, n, _ptr(loss), _ptr(row), _ptr(col),
+                                                     _ptr(diag), _stream(dev)), "vtc_infonce_dense_fwd")
+    return loss, row, col, diag
+
+
+def infonce_dense_bwd(sim: torch.Tensor, row_lse: torch.Tensor, col_lse: torch.Tensor,
+                      grad_loss: torch.Tensor) -> torch.Tensor:
+    dev = _req_cuda(sim, row_lse, col_lse, grad_loss)
+    sim = _mat(sim, "sim")
+    n = sim.shape[0]
+    g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+    dsim = torch.empty_like(sim)
+    with torch.cuda.device(dev):
+        _ffi.check(_ffi.load().vtc_infonce_dense_bwd(_ptr(sim), n, n, _ptr(row_lse), _ptr(col_lse),
+                                                     _ptr(g), _ptr(dsim), n, _stream(dev)),
+                   "vtc_infonce_dense_bwd")
+    return dsim
+
+
 # ------------------------------------------------------------------------------------------ H4
 def cam_stack_normalize(main: torch.Tensor, aux: torch.Tensor) -> torch.Tensor:
     """normalize(stack([main, *aux])) -> [1+nc, b, D] (model/model.py:150-151)."""
