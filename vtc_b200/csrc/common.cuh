@@ -168,14 +168,14 @@ __device__ __forceinline__ void widen8(const Raw8<__nv_bfloat16>& r, double (&v)
 }
 
 // fp64-sequential dot product: acc = fma(q[k], x[k], acc) for k = 0..D-1, in that order.  The
-// FMA chain is serial by definition; the loads are not, so the main loop keeps 64 bytes per operand
+// FMA chain is serial by definition; the loads are not, so the main loop keeps 128 bytes per operand
 // in flight (these kernels are latency-bound: one thread walks two rows).
 template <typename T>
 __device__ __forceinline__ double dot_seq64(const T* __restrict__ q, const T* __restrict__ x, int D) {
   double acc = 0.0;
   int k = 0;
   if (aligned16(q) && aligned16(x)) {
-    constexpr int U = sizeof(T) == 2 ? 4 : 2;  // groups of 8 elements per step
+    constexpr int U = sizeof(T) == 2 ? 8 : 4;  // groups of 8 elements per step: 128 bytes per operand
     for (; k + 8 * U <= D; k += 8 * U) {
       Raw8<T> ra[U], rb[U];
 #pragma unroll
@@ -232,6 +232,21 @@ __device__ __forceinline__ double sq_seq64(const T* __restrict__ x, int D) {
     const double v = to_f64(x[k]);
     acc = fma(v, v, acc);
   }
+  return acc;
+}
+
+// ||x||^2 in fp64 by a whole warp: lane-strided partial sums, then a butterfly -- a fixed order, so
+// deterministic, but NOT the fp64-sequential canonical value (differs in the last bits): for guard
+// bands and reported distances, never for a comparison that decides a rank.  All lanes return it.
+template <typename T>
+__device__ __forceinline__ double warp_sq64(const T* __restrict__ x, int D) {
+  double acc = 0.0;
+  for (int k = threadIdx.x & 31; k < D; k += 32) {
+    const double v = to_f64(x[k]);
+    acc = fma(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   return acc;
 }
 

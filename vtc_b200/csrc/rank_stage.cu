@@ -7,10 +7,12 @@
 //   * canonical ||x_j||^2 (fp64-sequential, exact.cu), the fp32 epilogue bias padded with +inf, the
 //     largest finite norm (guard band),
 //   * canonical d(t, gt) and an upper bound of ||q_t||^2 (guard band).
-//   Rows are staged through shared memory 32 rows x 128 columns at a time: the whole block loads
-//   (128-bit, coalesced), converts and stores the operands, while ONE warp walks the 32 staged rows,
-//   a lane per row, accumulating in k order -- the fp64-sequential definition needs one thread per
-//   dot product, the memory system needs a warp per row; the staging gives both.  HBM-bound:
+//   Rows are staged through shared memory 128 rows x 32 columns at a time: the whole block loads
+//   (128-bit; the 8 lanes of a row segment read 128 contiguous bytes), converts and stores the
+//   operands, and 128 threads walk one staged row each, accumulating in k order -- the
+//   fp64-sequential definition needs one thread per dot product, the memory system needs several
+//   lanes per row; the staging gives both, and every row of the block has its own walker (round 2a
+//   walked 32 rows per block with one warp: 2.8x off the HBM bound).  HBM-bound:
 //   rows * D * sizeof(in) read + rows * K' * 2 written.
 //
 // rank_epilogue_kernel (+ rank_fallback_kernel, device-gated) -- see "epilogue" below:
@@ -24,10 +26,12 @@
 namespace vtc {
 
 // ------------------------------------------------------------------------------------ prologue
-constexpr int PR_ROWS = 32;
-constexpr int PR_KC = 128;
-constexpr int PR_LD = PR_KC + 4;  // floats per staged row: 16-byte aligned rows, conflict-free LDS.128
+constexpr int PR_ROWS = 128;      // rows per block: one walker thread per row
+constexpr int PR_KC = 32;         // staged columns per step
+constexpr int PR_LD = PR_KC + 4;  // floats per staged row: 16-byte aligned rows, and 8 consecutive rows
+                                  // cover all 32 banks (conflict-free LDS.128 for the walkers)
 constexpr int PR_THREADS = 256;
+constexpr int PR_Q = PR_ROWS * (PR_KC / 4) / PR_THREADS;  // quads a thread loads per tile and step (4)
 constexpr int PR_LIGHT_ROWS = 256;
 
 __device__ __forceinline__ float bf16_rn(float v) {
@@ -108,12 +112,17 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
   __shared__ __align__(16) float tile_a[PR_ROWS * PR_LD];  // gallery rows / query rows
   __shared__ __align__(16) float tile_b[PR_ROWS * PR_LD];  // ground-truth gallery rows of the queries
   __shared__ int64_t srow_a[PR_ROWS], srow_b[PR_ROWS];
+  __shared__ float blk_max[PR_THREADS / 32][3];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   griddep_launch();
   griddep_wait();
   const T* Qb = static_cast<const T*>(a.Q);
   const T* Gb = static_cast<const T*>(a.G);
   const bool round = a.round_bf16 != 0;
+  // loader view: thread owns column quad (tid % 8) of staged rows tid / 8 + 32 i, i = 0..3 -- the 8
+  // lanes of a row segment read 128 contiguous bytes (fp32) per step
+  const int lrow = tid >> 3, kq = 4 * (tid & 7);
+  const int nchunks = ceil_div(a.D, PR_KC);
 
   if ((int)blockIdx.x < g_blocks) {
     // ------------------------------------------------------------------------ gallery rows
@@ -140,43 +149,44 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
     const bool walk = a.sq64_in == nullptr;
     const bool emit = a.mode_g != STAGE_NONE;
     const bool pieces = emit && a.mode_g != PREP_PLAIN && a.split_max_bits != nullptr;
-    float s_lo[4] = {0.f, 0.f, 0.f, 0.f}, s_e[4] = {0.f, 0.f, 0.f, 0.f};
+    float s_lo[PR_Q], s_e[PR_Q];
+#pragma unroll
+    for (int i = 0; i < PR_Q; ++i) s_lo[i] = s_e[i] = 0.f;
     double sq = 0.0;
     if ((walk || emit) && r0 < a.M) {
       const bool vec = rows_vectorisable(Gb, a.ldg);
-      const int nchunks = ceil_div(a.D, PR_KC);
-      float v[4][4];
-      const T* rp[4];
+      float v[PR_Q][4];
+      const T* rp[PR_Q];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t r = srow_a[warp + 8 * j];
-        rp[j] = r >= 0 ? Gb + r * a.ldg : nullptr;
-        load_quad(rp[j], 4 * lane, a.D, vec, v[j]);
+      for (int i = 0; i < PR_Q; ++i) {
+        const int64_t r = srow_a[lrow + 32 * i];
+        rp[i] = r >= 0 ? Gb + r * a.ldg : nullptr;
+        load_quad(rp[i], kq, a.D, vec, v[i]);
       }
       for (int c = 0; c < nchunks; ++c) {
         const int k0 = c * PR_KC;
-        __syncthreads();  // the walker warp has finished the previous chunk
+        __syncthreads();  // the walkers have finished the previous chunk
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int row = warp + 8 * j;
+        for (int i = 0; i < PR_Q; ++i) {
+          const int row = lrow + 32 * i;
           if (round) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[j][e] = bf16_rn(v[j][e]);
+            for (int e = 0; e < 4; ++e) v[i][e] = bf16_rn(v[i][e]);
           }
-          *reinterpret_cast<float4*>(&tile_a[row * PR_LD + 4 * lane]) =
-              make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
-          if (emit && rp[j])
-            emit_quad(a.opG + srow_a[row] * (int64_t)a.Kp, k0 + 4 * lane, a.D, a.mode_g, v[j],
-                      a.fallback, pieces ? &s_lo[j] : nullptr, pieces ? &s_e[j] : nullptr);
+          *reinterpret_cast<float4*>(&tile_a[row * PR_LD + kq]) =
+              make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+          if (emit && rp[i])
+            emit_quad(a.opG + srow_a[row] * (int64_t)a.Kp, k0 + kq, a.D, a.mode_g, v[i], a.fallback,
+                      pieces ? &s_lo[i] : nullptr, pieces ? &s_e[i] : nullptr);
         }
         __syncthreads();
         if (c + 1 < nchunks) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) load_quad(rp[j], k0 + PR_KC + 4 * lane, a.D, vec, v[j]);
+          for (int i = 0; i < PR_Q; ++i) load_quad(rp[i], k0 + PR_KC + kq, a.D, vec, v[i]);
         }
-        if (walk && warp == 0) {
+        if (walk && tid < PR_ROWS) {
           const int kn = min(PR_KC, a.D - k0);
-          const float* row = &tile_a[lane * PR_LD];
+          const float* row = &tile_a[tid * PR_LD];
           for (int k = 0; k < kn; k += 4) {
             const float4 x = *reinterpret_cast<const float4*>(row + k);
             const double x0 = x.x, x1 = x.y, x2 = x.z, x3 = x.w;
@@ -188,28 +198,11 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
         }
       }
       if (emit) zero_pad_columns(a.opG, a.Kp, a.mode_g == PREP_PLAIN ? a.D : 3 * a.D, srow_a);
-      if (pieces) {
-        // largest piece norms of this block's rows: one pair of global atomics per block
-        float m_lo = 0.f, m_e = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float l = piece_up(warp_sum(s_lo[j])), e = piece_up(warp_sum(s_e[j]));
-          if (l < 3.0e38f) m_lo = fmaxf(m_lo, l);  // (NaN / inf rows raise the fallback flag instead)
-          if (e < 3.0e38f) m_e = fmaxf(m_e, e);
-        }
-        float* blk = tile_b;  // (unused by gallery blocks)
-        if (lane == 0) blk[2 * warp] = m_lo, blk[2 * warp + 1] = m_e;
-        __syncthreads();
-        if (tid < 2) {
-          float m = 0.f;
-          for (int w = 0; w < PR_THREADS / 32; ++w) m = fmaxf(m, blk[2 * w + tid]);
-          if (m > 0.f) atomicMax(a.split_max_bits + tid, __float_as_uint(m));
-        }
-      }
     }
-    if (warp == 0) {
-      const int64_t j = r0 + lane;
-      float mine = 0.f;
+    // per-row results (walker threads) and the block's maxima: one set of global atomics per block
+    float m_sq = 0.f, m_lo = 0.f, m_e = 0.f;
+    if (tid < PR_ROWS) {
+      const int64_t j = r0 + tid;
       if (j < a.Mpad) {
         float b = INFINITY;
         if (j < a.M) {
@@ -217,14 +210,34 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
           if (walk && a.sq64) a.sq64[j] = s64;
           const float f = (float)s64;
           b = a.metric == VTC_METRIC_L2 ? f : 0.f;
-          if (f == f && f < 3.0e38f) mine = f;
+          if (f == f && f < 3.0e38f) m_sq = f;
         }
         if (a.bias) a.bias[j] = b;
       }
-      if (a.max_sq_bits) {
-        mine = warp_max(mine);
-        if (lane == 0 && mine > 0.f) atomicMax(a.max_sq_bits, __float_as_uint(mine));
+    }
+    if (pieces) {
+#pragma unroll
+      for (int i = 0; i < PR_Q; ++i) {
+        // a row's 8 quads per step live in 8 consecutive lanes
+        float l = s_lo[i], e = s_e[i];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          l += __shfl_xor_sync(0xffffffffu, l, o);
+          e += __shfl_xor_sync(0xffffffffu, e, o);
+        }
+        l = piece_up(l), e = piece_up(e);
+        if (l < 3.0e38f) m_lo = fmaxf(m_lo, l);  // (NaN / inf rows raise the fallback flag instead)
+        if (e < 3.0e38f) m_e = fmaxf(m_e, e);
       }
+    }
+    m_sq = warp_max(m_sq), m_lo = warp_max(m_lo), m_e = warp_max(m_e);
+    if (lane == 0) blk_max[warp][0] = m_sq, blk_max[warp][1] = m_lo, blk_max[warp][2] = m_e;
+    __syncthreads();
+    if (tid < 3) {
+      float m = 0.f;
+      for (int w = 0; w < PR_THREADS / 32; ++w) m = fmaxf(m, blk_max[w][tid]);
+      unsigned int* dst = tid == 0 ? a.max_sq_bits : (pieces ? a.split_max_bits + (tid - 1) : nullptr);
+      if (dst && m > 0.f) atomicMax(dst, __float_as_uint(m));
     }
     return;
   }
@@ -235,7 +248,9 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
   const bool need_qq = a.qq_in == nullptr && a.qq != nullptr;
   const bool emit = a.mode_q != STAGE_NONE;
   const bool pieces = emit && a.mode_q != PREP_PLAIN && a.qsplit != nullptr;
-  float s_lo[4] = {0.f, 0.f, 0.f, 0.f}, s_e[4] = {0.f, 0.f, 0.f, 0.f};
+  float s_lo[PR_Q], s_e[PR_Q];
+#pragma unroll
+  for (int i = 0; i < PR_Q; ++i) s_lo[i] = s_e[i] = 0.f;
   if (tid < PR_ROWS) {
     const int64_t t = t0 + tid;
     srow_a[tid] = t < a.N ? t : -1;
@@ -250,51 +265,50 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
   double dot = 0.0, sqx = 0.0, qq = 0.0;
   {
     const bool vq = rows_vectorisable(Qb, a.ldq), vg = rows_vectorisable(Gb, a.ldg);
-    const int nchunks = ceil_div(a.D, PR_KC);
-    float v[4][4], w[4][4];
-    const T *qp[4], *gp[4];
+    float v[PR_Q][4], w[PR_Q][4];
+    const T *qp[PR_Q], *gp[PR_Q];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t t = srow_a[warp + 8 * j], g = srow_b[warp + 8 * j];
-      qp[j] = t >= 0 ? Qb + t * a.ldq : nullptr;
-      gp[j] = g >= 0 ? Gb + g * a.ldg : nullptr;
-      load_quad(qp[j], 4 * lane, a.D, vq, v[j]);
-      if (need_gt) load_quad(gp[j], 4 * lane, a.D, vg, w[j]);
+    for (int i = 0; i < PR_Q; ++i) {
+      const int64_t t = srow_a[lrow + 32 * i], g = srow_b[lrow + 32 * i];
+      qp[i] = t >= 0 ? Qb + t * a.ldq : nullptr;
+      gp[i] = g >= 0 ? Gb + g * a.ldg : nullptr;
+      load_quad(qp[i], kq, a.D, vq, v[i]);
+      if (need_gt) load_quad(gp[i], kq, a.D, vg, w[i]);
     }
     for (int c = 0; c < nchunks; ++c) {
       const int k0 = c * PR_KC;
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int row = warp + 8 * j;
+      for (int i = 0; i < PR_Q; ++i) {
+        const int row = lrow + 32 * i;
         if (round) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            v[j][e] = bf16_rn(v[j][e]);
-            if (need_gt) w[j][e] = bf16_rn(w[j][e]);
+            v[i][e] = bf16_rn(v[i][e]);
+            if (need_gt) w[i][e] = bf16_rn(w[i][e]);
           }
         }
-        *reinterpret_cast<float4*>(&tile_a[row * PR_LD + 4 * lane]) =
-            make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+        *reinterpret_cast<float4*>(&tile_a[row * PR_LD + kq]) =
+            make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
         if (need_gt)
-          *reinterpret_cast<float4*>(&tile_b[row * PR_LD + 4 * lane]) =
-              make_float4(w[j][0], w[j][1], w[j][2], w[j][3]);
-        if (emit && qp[j])
-          emit_quad(a.opQ + srow_a[row] * (int64_t)a.Kp, k0 + 4 * lane, a.D, a.mode_q, v[j],
-                    a.fallback, pieces ? &s_lo[j] : nullptr, pieces ? &s_e[j] : nullptr);
+          *reinterpret_cast<float4*>(&tile_b[row * PR_LD + kq]) =
+              make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
+        if (emit && qp[i])
+          emit_quad(a.opQ + srow_a[row] * (int64_t)a.Kp, k0 + kq, a.D, a.mode_q, v[i], a.fallback,
+                    pieces ? &s_lo[i] : nullptr, pieces ? &s_e[i] : nullptr);
       }
       __syncthreads();
       if (c + 1 < nchunks) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          load_quad(qp[j], k0 + PR_KC + 4 * lane, a.D, vq, v[j]);
-          if (need_gt) load_quad(gp[j], k0 + PR_KC + 4 * lane, a.D, vg, w[j]);
+        for (int i = 0; i < PR_Q; ++i) {
+          load_quad(qp[i], k0 + PR_KC + kq, a.D, vq, v[i]);
+          if (need_gt) load_quad(gp[i], k0 + PR_KC + kq, a.D, vg, w[i]);
         }
       }
-      if (warp == 0 && (need_gt || need_qq)) {
+      if (tid < PR_ROWS && (need_gt || need_qq)) {
         const int kn = min(PR_KC, a.D - k0);
-        const float* qr = &tile_a[lane * PR_LD];
-        const float* xr = &tile_b[lane * PR_LD];
+        const float* qr = &tile_a[tid * PR_LD];
+        const float* xr = &tile_b[tid * PR_LD];
         if (need_gt) {
           for (int k = 0; k < kn; k += 4) {
             const float4 q4 = *reinterpret_cast<const float4*>(qr + k);
@@ -318,18 +332,24 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
     if (emit) zero_pad_columns(a.opQ, a.Kp, a.mode_q == PREP_PLAIN ? a.D : 3 * a.D, srow_a);
     if (pieces) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float l = piece_up(warp_sum(s_lo[j])), e = piece_up(warp_sum(s_e[j]));
-        const int64_t t = srow_a[warp + 8 * j];
-        if (lane == 0 && t >= 0) a.qsplit[t] = make_float2(sqrtf(l) * 1.000001f, sqrtf(e) * 1.000001f);
+      for (int i = 0; i < PR_Q; ++i) {
+        float l = s_lo[i], e = s_e[i];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          l += __shfl_xor_sync(0xffffffffu, l, o);
+          e += __shfl_xor_sync(0xffffffffu, e, o);
+        }
+        const int64_t t = srow_a[lrow + 32 * i];
+        if ((tid & 7) == 0 && t >= 0)
+          a.qsplit[t] = make_float2(sqrtf(piece_up(l)) * 1.000001f, sqrtf(piece_up(e)) * 1.000001f);
       }
     }
   }
-  if (warp == 0 && t0 + lane < a.N) {
-    const int64_t t = t0 + lane;
+  if (tid < PR_ROWS && t0 + tid < a.N) {
+    const int64_t t = t0 + tid;
     if (need_gt) {
       double d0 = nan("");
-      if (srow_b[lane] >= 0) d0 = a.metric == VTC_METRIC_L2 ? sqx - 2.0 * dot : -dot;
+      if (srow_b[tid] >= 0) d0 = a.metric == VTC_METRIC_L2 ? sqx - 2.0 * dot : -dot;
       a.dgt[t] = d0;
     }
     // the guard band only needs an UPPER bound of ||q||^2: round up, one part in 10^6 of slack
