@@ -292,6 +292,29 @@ int vtc_cam_readout_bwd(const float* T, const float* main, const float* res_in,
                         const float* res_mul, float* dT, float* dres, float* dmain,
                         vtc_stream_t stream);
 
+/* The whole backward of _adapt_feature in ONE call (the chain round 1 drove from Python with ~156
+ * launches): read-out backward -> layers (reversed) x [c_proj, QuickGELU, c_fc, LN2, out_proj,
+ * attention core, in_proj, LN1] -> stacked-input normalisation.  Per layer the caller hands in the
+ * activations its forward kept (fp32 [L*b, .]: X the layer input, H1 = LN1(X), QKV, A the attention
+ * output, X2, H2 = LN2(X2), U = c_fc(H2), Fa = QuickGELU(U)), the LayerNorm weights, the prepared
+ * linears of the TRANSPOSED weights (vtc_linear_prepare on W^T, no bias) and the buffers that receive
+ * the parameter gradients.  T [L,b,D] is the transformer output, res_in the final_linear output
+ * (RESIDUAL_ONLY).  dmain [b,D], daux [L-1,b,D], dflw [D,D] (nullable).  HOST array of structs
+ * holding DEVICE pointers. */
+typedef struct {
+  const float *X, *H1, *QKV, *A, *X2, *H2, *U, *Fa;
+  const float *ln1_g, *ln2_g;
+  const void *qkv_t, *out_t, *fc_t, *proj_t;
+  float *dWqkv, *dbqkv, *dWo, *dbo, *dg1, *db1, *dWfc, *dbfc, *dWpr, *dbpr, *dg2, *db2;
+} vtc_cam_layer_bwd;
+size_t vtc_cam_backward_workspace_bytes(int L, int64_t b, int D, int precision);
+int vtc_cam_backward(const float* dout, const float* main, const float* aux, const float* T,
+                     const float* res_in, const uint8_t* skip_mask, int L, int64_t b, int D,
+                     int heads, int layers, const vtc_cam_layer_bwd* layers_params,
+                     int readout_mode, const void* final_linear_t, int res_act, float res_scale,
+                     const float* res_shift, const float* res_mul, int precision, float* dmain,
+                     float* daux, float* dflw, void* ws, size_t ws_bytes, vtc_stream_t stream);
+
 /* number of kernels this library has launched since load (for bench.py's gpu_launches). */
 uint64_t vtc_launch_count(void);
 

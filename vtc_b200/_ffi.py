@@ -60,6 +60,9 @@ SIGNATURES = {
                                 _P]),
     "vtc_linear": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_size_t,
                            _P]),
+    "vtc_cam_backward_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
+    "vtc_cam_backward": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P, c_int,
+                                 _P, c_int, c_float, _P, _P, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "vtc_launch_count": (c_uint64, []),
     "vtc_kernel_timer_enable": (c_int, [c_int]),
     "vtc_kernel_timer_read": (c_int, [POINTER(c_double), POINTER(c_int)]),
@@ -67,6 +70,14 @@ SIGNATURES = {
     "vtc_trace_begin": (c_int, [_P]),
     "vtc_trace_end": (c_int, [ctypes.c_char_p, c_size_t]),
 }
+
+
+class CamLayerBwd(ctypes.Structure):
+    """vtc_cam_layer_bwd of include/vtc_b200.h (device pointers)."""
+    _fields_ = [(n, c_void_p) for n in (
+        "X", "H1", "QKV", "A", "X2", "H2", "U", "Fa", "ln1_g", "ln2_g", "qkv_t", "out_t", "fc_t",
+        "proj_t", "dWqkv", "dbqkv", "dWo", "dbo", "dg1", "db1", "dWfc", "dbfc", "dWpr", "dbpr",
+        "dg2", "db2")]
 
 
 class CamLayer(ctypes.Structure):

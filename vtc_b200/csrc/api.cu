@@ -767,6 +767,146 @@ CamWs carve_cam(Workspace& ws, int L, int64_t b, int D, int precision) {
   return w;
 }
 
+// ---- CAM backward in one call (autograd through _adapt_feature, model/model.py:141-205 under
+// loss.backward(), trainer/trainer.py:79).  Round 1 drove ~156 launches from Python; here the same
+// chain is enqueued from C: per layer 8 tensor-core products (dX = dY W through the prepared
+// TRANSPOSED weights, dW = dY^T X on transposed operand copies), the fp32 row kernels of cam_bwd.cu
+// between them.  Operand preparation is the only extra traffic: every product reads bf16 operands.
+struct CamBwdWs {
+  float *dXa, *dXb, *dA, *dQKV, *dF, *dU, *tX, *tY, *zb, *dres, *dT;
+  __nv_bfloat16 *opX, *opT1, *opT2;
+};
+CamBwdWs carve_cam_bwd(Workspace& ws, int L, int64_t b, int D, int precision) {
+  const int64_t rows = (int64_t)L * b;
+  const OperandPlan of = plan_operands(4 * D, VTC_F32, precision);
+  const OperandPlan orow = plan_operands((int)rows, VTC_F32, precision);
+  CamBwdWs w;
+  w.dXa = ws.take<float>((size_t)rows * D);
+  w.dXb = ws.take<float>((size_t)rows * D);
+  w.dA = ws.take<float>((size_t)rows * D);
+  w.dQKV = ws.take<float>((size_t)rows * 3 * D);
+  w.dF = ws.take<float>((size_t)rows * 4 * D);
+  w.dU = ws.take<float>((size_t)rows * 4 * D);
+  w.tX = ws.take<float>((size_t)rows * 4 * D);
+  w.tY = ws.take<float>((size_t)rows * 4 * D);
+  w.zb = ws.take<float>(round_up<int64_t>(4 * D, tc::BN));
+  w.dres = ws.take<float>((size_t)b * D);
+  w.dT = ws.take<float>((size_t)rows * D);
+  w.opX = ws.take<__nv_bfloat16>((size_t)rows * of.Kp);
+  w.opT1 = ws.take<__nv_bfloat16>((size_t)4 * D * orow.Kp);
+  w.opT2 = ws.take<__nv_bfloat16>((size_t)4 * D * orow.Kp);
+  return w;
+}
+
+// out[N, M] = X[N, K] Y[M, K]^T from fp32 row-major matrices: operands prepared here (X as the
+// query side, Y as the gallery side), no bias
+int gemm_f32(const float* X, const float* Y, int64_t N, int64_t M, int K, int precision,
+             __nv_bfloat16* opX, __nv_bfloat16* opY, const float* zero_bias, float* out,
+             cudaStream_t s) {
+  const OperandPlan o = plan_operands(K, VTC_F32, precision);
+  VTC_RETURN_IF_ERROR(launch_prep_operand(X, false, N, K, K, o.split ? PREP_SPLIT_A : PREP_PLAIN, opX, o.Kp, s));
+  VTC_RETURN_IF_ERROR(launch_prep_operand(Y, false, M, K, K, o.split ? PREP_SPLIT_B : PREP_PLAIN, opY, o.Kp, s));
+  tc::Params p;
+  memset(&p, 0, sizeof(p));
+  p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
+  p.col_bias = zero_bias, p.scale = 1.f, p.out = out, p.ldo = M;
+  const tc::Plan pl = tc::plan_tiles(p, 64, 1, 1, store_tile_width(N, M));
+  CUtensorMap tmA, tmB;
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opX, N, o.Kp, o.Kp, tc::BM, &tmA));
+  VTC_RETURN_IF_ERROR(tc::make_operand_tmap(opY, M, o.Kp, o.Kp, pl.bn, &tmB));
+  return tc::launch_sim_tc(tc::EPI_STORE, false, pl, tmA, tmB, p, s);
+}
+
+}  // namespace
+int launch_transpose(const float* in, int64_t R, int64_t C, float* out, cudaStream_t s);
+int launch_gelu_bwd(const float* dF, const float* U, int64_t n, float* dU, cudaStream_t s);
+int launch_colsum(const float* X, int64_t R, int64_t C, float* out, cudaStream_t s);
+int launch_layernorm_bwd(const float* dY, const float* X, const float* gamma, int64_t rows, int D,
+                         float eps, const float* dres, float* dX, float* dgamma, float* dbeta,
+                         cudaStream_t s);
+int launch_cam_attn_core_bwd(const float* QKV, const float* dO, int L, int64_t b, int D, int heads,
+                             float* dQKV, cudaStream_t s);
+int launch_cam_stack_normalize_bwd(const float* main, const float* aux, const float* dX, int L,
+                                   int64_t b, int D, float* dmain, float* daux, cudaStream_t s);
+int launch_cam_readout_bwd(const float* T, const float* main, const float* res_in,
+                           const uint8_t* skip_mask, const float* dout, int L, int64_t b, int D,
+                           int mode, int res_act, float res_scale, const float* res_shift,
+                           const float* res_mul, float* dT, float* dres, float* dmain,
+                           cudaStream_t s);
+namespace {
+
+// dX = dY W (through the prepared transposed weight) and dW = dY^T Act, db = colsum(dY)
+int linear_bwd(const float* dY, const float* Act, const void* Wt_prepared, int64_t rows, int in_f,
+               int out_f, int precision, const CamBwdWs& w, float* dX, float* dW, float* db,
+               cudaStream_t s) {
+  const OperandPlan oo = plan_operands(out_f, VTC_F32, precision);
+  // dX [rows, in_f] = dY [rows, out_f] . (W^T)[in_f, out_f]^T
+  VTC_RETURN_IF_ERROR(launch_prep_operand(dY, false, rows, out_f, out_f,
+                                          oo.split ? PREP_SPLIT_A : PREP_PLAIN, w.opX, oo.Kp, s));
+  VTC_RETURN_IF_ERROR(linear_prepared(w.opX, Wt_prepared, nullptr, rows, out_f, in_f, 0, precision,
+                                      dX, nullptr, 0, s));
+  // dW [out_f, in_f] = (dY^T)[out_f, rows] . (Act^T)[in_f, rows]^T
+  VTC_RETURN_IF_ERROR(launch_transpose(dY, rows, out_f, w.tX, s));
+  VTC_RETURN_IF_ERROR(launch_transpose(Act, rows, in_f, w.tY, s));
+  VTC_RETURN_IF_ERROR(gemm_f32(w.tX, w.tY, out_f, in_f, (int)rows, precision, w.opT1, w.opT2, w.zb,
+                               dW, s));
+  return launch_colsum(dY, rows, out_f, db, s);
+}
+
+int cam_backward_impl(const float* dout, const float* main, const float* aux, const float* T,
+                      const float* res_in, const uint8_t* skip_mask, int L, int64_t b, int D,
+                      int heads, int layers, const vtc_cam_layer_bwd* lp, int readout_mode,
+                      const void* flw_t, int res_act, float res_scale, const float* res_shift,
+                      const float* res_mul, int precision, float* dmain, float* daux, float* dflw,
+                      void* wsp, size_t ws_bytes, cudaStream_t s) {
+  Workspace ws(wsp, ws_bytes);
+  CamBwdWs w = carve_cam_bwd(ws, L, b, D, precision);
+  if (!ws.ok()) return VTC_ERR_WORKSPACE;
+  const int64_t rows = (int64_t)L * b;
+  VTC_RETURN_IF_ERROR(launch_fill_bias(w.zb, nullptr, 4 * D, round_up<int64_t>(4 * D, tc::BN), 0.f, s));
+  // read-out (model/model.py:156-161, 168-171, 199-203): dmain first receives the part through
+  // normalize(main) at :203; the stacked-input part is added at the end
+  float* dX = w.dXa;
+  if (readout_mode == VTC_CAM_READOUT_AVG) {
+    VTC_RETURN_IF_ERROR(launch_cam_readout_bwd(T, main, nullptr, skip_mask, dout, L, b, D,
+                                               VTC_CAM_READOUT_AVG, res_act, res_scale, res_shift,
+                                               res_mul, dX, nullptr, dmain, s));
+  } else {
+    VTC_RETURN_IF_ERROR(launch_cam_readout_bwd(nullptr, main, res_in, skip_mask, dout, L, b, D,
+                                               VTC_CAM_READOUT_RESIDUAL_ONLY, res_act, res_scale,
+                                               res_shift, res_mul, nullptr, w.dres, dmain, s));
+    // final_linear(token 0) (model/model.py:161): d token0 = dres W, dW = dres^T token0
+    cudaError_t e = cudaMemsetAsync(dX, 0, (size_t)rows * D * sizeof(float), s);
+    if (e != cudaSuccess) return cuda_err(e);
+    const OperandPlan od = plan_operands(D, VTC_F32, precision);
+    VTC_RETURN_IF_ERROR(launch_prep_operand(w.dres, false, b, D, D,
+                                            od.split ? PREP_SPLIT_A : PREP_PLAIN, w.opX, od.Kp, s));
+    VTC_RETURN_IF_ERROR(linear_prepared(w.opX, flw_t, nullptr, b, D, D, 0, precision, dX, nullptr, 0, s));
+    if (dflw) {
+      VTC_RETURN_IF_ERROR(launch_transpose(w.dres, b, D, w.tX, s));
+      VTC_RETURN_IF_ERROR(launch_transpose(T, b, D, w.tY, s));
+      VTC_RETURN_IF_ERROR(gemm_f32(w.tX, w.tY, D, D, (int)b, precision, w.opT1, w.opT2, w.zb, dflw, s));
+    }
+  }
+  float* dX2 = w.dXb;
+  for (int i = layers - 1; i >= 0; --i) {  // timesformer_clip_alt.py:112-124, backwards
+    const vtc_cam_layer_bwd& l = lp[i];
+    // x = x2 + c_proj(gelu(c_fc(ln_2(x2))))
+    VTC_RETURN_IF_ERROR(linear_bwd(dX, l.Fa, l.proj_t, rows, 4 * D, D, precision, w, w.dF, l.dWpr, l.dbpr, s));
+    VTC_RETURN_IF_ERROR(launch_gelu_bwd(w.dF, l.U, rows * 4 * D, w.dU, s));
+    VTC_RETURN_IF_ERROR(linear_bwd(w.dU, l.H2, l.fc_t, rows, D, 4 * D, precision, w, w.dA, l.dWfc, l.dbfc, s));
+    VTC_RETURN_IF_ERROR(launch_layernorm_bwd(w.dA, l.X2, l.ln2_g, rows, D, 1e-5f, dX, dX2, l.dg2, l.db2, s));
+    // x2 = x + out_proj(attn(in_proj(ln_1(x))))
+    VTC_RETURN_IF_ERROR(linear_bwd(dX2, l.A, l.out_t, rows, D, D, precision, w, w.dA, l.dWo, l.dbo, s));
+    VTC_RETURN_IF_ERROR(launch_cam_attn_core_bwd(l.QKV, w.dA, L, b, D, heads, w.dQKV, s));
+    VTC_RETURN_IF_ERROR(linear_bwd(w.dQKV, l.H1, l.qkv_t, rows, D, 3 * D, precision, w, w.dA, l.dWqkv, l.dbqkv, s));
+    VTC_RETURN_IF_ERROR(launch_layernorm_bwd(w.dA, l.X, l.ln1_g, rows, D, 1e-5f, dX2, dX, l.dg1, l.db1, s));
+  }
+  // X = normalize(stack([main, *aux])) (model/model.py:150-151): dmain += the token-0 part
+  VTC_RETURN_IF_ERROR(launch_cam_stack_normalize_bwd(main, aux, dX, L, b, D, w.dres, daux, s));
+  return launch_bias_act(dmain, nullptr, w.dres, b, D, 0, dmain, s);
+}
+
 }  // namespace
 }  // namespace vtc
 
@@ -1155,6 +1295,31 @@ int vtc_cam_forward(const float* main, const float* aux, int L, int64_t b, int D
                                       nullptr, 0, s));
   return launch_cam_readout(nullptr, main, w.res, skip_mask, L, b, D, VTC_CAM_READOUT_RESIDUAL_ONLY,
                             res_act, res_scale, res_shift, res_mul, out, s);
+}
+
+size_t vtc_cam_backward_workspace_bytes(int L, int64_t b, int D, int precision) {
+  if (L < 1 || b < 0 || D <= 0 || (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16)) return 0;
+  Workspace ws(nullptr, 0);
+  carve_cam_bwd(ws, L, b, D, precision);
+  return ws.used + 512;
+}
+
+int vtc_cam_backward(const float* dout, const float* main, const float* aux, const float* T,
+                     const float* res_in, const uint8_t* skip_mask, int L, int64_t b, int D,
+                     int heads, int layers, const vtc_cam_layer_bwd* lp, int readout_mode,
+                     const void* final_linear_t, int res_act, float res_scale,
+                     const float* res_shift, const float* res_mul, int precision, float* dmain,
+                     float* daux, float* dflw, void* ws, size_t ws_bytes, vtc_stream_t stream) {
+  if (!dout || !main || !T || !dmain || L < 1 || (L > 1 && (!aux || !daux)) || b < 0 || D <= 0 ||
+      heads < 1 || layers < 0 || (layers > 0 && !lp) ||
+      (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16) ||
+      (readout_mode != VTC_CAM_READOUT_AVG && readout_mode != VTC_CAM_READOUT_RESIDUAL_ONLY) ||
+      (readout_mode == VTC_CAM_READOUT_RESIDUAL_ONLY && (!final_linear_t || !res_in)))
+    return VTC_ERR_INVALID_ARG;
+  if (b == 0) return VTC_OK;
+  return cam_backward_impl(dout, main, aux, T, res_in, skip_mask, L, b, D, heads, layers, lp,
+                           readout_mode, final_linear_t, res_act, res_scale, res_shift, res_mul,
+                           precision, dmain, daux, dflw, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -179,8 +179,9 @@ class CAMTransformer(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "CAMTransformer is forward-only in this round (wrap the call in torch.no_grad(); "
-                "the CAM backward kernels are listed as next in DESIGN.md)")
+                "calling the bare CAMTransformer under autograd is not supported: training goes "
+                "through PretrainedCLIPBase._adapt_feature (differentiable, _CamAdaptFunction); "
+                "wrap a stand-alone call in torch.no_grad()")
         L, b, D = x.shape
         prec = self.precision
         x2 = x.float().contiguous().reshape(L * b, D)
@@ -209,8 +210,9 @@ def _layer_params(blk) -> list:
 
 class _CamAdaptFunction(torch.autograd.Function):
     """Differentiable `_adapt_feature` (model/model.py:141-205) for training: the forward runs the
-    CUDA ops one by one and keeps the activations, the backward is built from the kernels of
-    csrc/cam_bwd.cu plus tensor-core GEMMs on transposed copies (dX = dY W, dW = dY^T X)."""
+    CUDA ops one by one and keeps the activations; the backward is ONE C call (vtc_cam_backward): the
+    kernels of csrc/cam_bwd.cu plus tensor-core products through the prepared transposed weights
+    (dX = dY W) and on transposed operand copies (dW = dY^T X)."""
 
     @staticmethod
     def forward(ctx, main, aux, skip_mask, cfg, flw, *params):
@@ -258,46 +260,40 @@ class _CamAdaptFunction(torch.autograd.Function):
         main, aux, T, res, flw = sv[:5]
         params = sv[5:5 + _PARAMS_PER_LAYER * layers]
         acts = sv[5 + _PARAMS_PER_LAYER * layers:]
-        lin = lambda x, w: ops.linear(x, w, precision=prec)  # noqa: E731  x @ w.t()
-        tr = ops.transpose
-        dflw = None
-        if avg:
-            dT, _, dmain = ops.cam_readout_bwd(T, main, dout, _ffi.CAM_READOUT_AVG,
-                                               skip_mask=ctx.skip_mask, res_act=res_act)
-        else:
-            _, dres, dmain = ops.cam_readout_bwd(None, main, dout, _ffi.CAM_READOUT_RESIDUAL_ONLY,
-                                                 res_in=res, skip_mask=ctx.skip_mask, L=L,
-                                                 res_act=res_act)
-            dT = torch.zeros_like(T)
-            dT[0] = lin(dres, tr(flw))                       # d token0 = dres @ W
-            dflw = lin(tr(dres), tr(T[0].contiguous()))      # dW = dres^T @ token0
-        dX = dT.reshape(L * b, D)
-        grads = [None] * len(params)
-        for i in reversed(range(layers)):
+        dev = main.device
+        keep = []
+
+        def wt(w):  # the weight transposed, as a prepared gallery-side operand: dX = dY W
+            buf = ops.linear_prepare(w.t().contiguous(), None, prec)
+            keep.append(buf)
+            return buf.data_ptr()
+
+        grads = []
+        arr = (_ffi.CamLayerBwd * layers)()
+        for i in range(layers):
             wqkv, bqkv, wo, bo, g1, b1, wfc, bfc, wpr, bpr, g2, b2 = params[
                 _PARAMS_PER_LAYER * i:_PARAMS_PER_LAYER * (i + 1)]
             X, H1, QKV, A, X2, H2, U, Fa = acts[8 * i:8 * (i + 1)]
-            o = _PARAMS_PER_LAYER * i
-            dXt = tr(dX)
-            dF = lin(dX, tr(wpr))                            # [rows, 4D]
-            grads[o + 8] = lin(dXt, tr(Fa))                  # dW_proj [D, 4D]
-            grads[o + 9] = ops.colsum(dX)
-            dU = ops.gelu_bwd(dF, U)
-            dH2 = lin(dU, tr(wfc))                           # [rows, D]
-            grads[o + 6] = lin(tr(dU), tr(H2))               # dW_fc [4D, D]
-            grads[o + 7] = ops.colsum(dU)
-            dX2, grads[o + 10], grads[o + 11] = ops.layernorm_bwd(dH2, X2, g2, dres=dX)
-            dA = lin(dX2, tr(wo))
-            grads[o + 2] = lin(tr(dX2), tr(A))
-            grads[o + 3] = ops.colsum(dX2)
-            dQKV = ops.cam_attn_core_bwd(QKV.reshape(L, b, 3 * D), dA.reshape(L, b, D),
-                                         heads).reshape(L * b, 3 * D)
-            dH1 = lin(dQKV, tr(wqkv))
-            grads[o + 0] = lin(tr(dQKV), tr(H1))
-            grads[o + 1] = ops.colsum(dQKV)
-            dX, grads[o + 4], grads[o + 5] = ops.layernorm_bwd(dH1, X, g1, dres=dX2)
-        dmain2, daux = ops.cam_stack_normalize_bwd(main, aux, dX.reshape(L, b, D))
-        dmain = ops.bias_act(dmain, residual=dmain2)
+            a = arr[i]
+            a.X, a.H1, a.QKV, a.A = X.data_ptr(), H1.data_ptr(), QKV.data_ptr(), A.data_ptr()
+            a.X2, a.H2, a.U, a.Fa = X2.data_ptr(), H2.data_ptr(), U.data_ptr(), Fa.data_ptr()
+            g1c, g2c = g1.float().contiguous(), g2.float().contiguous()
+            keep += [g1c, g2c]
+            a.ln1_g, a.ln2_g = g1c.data_ptr(), g2c.data_ptr()
+            a.qkv_t, a.out_t, a.fc_t, a.proj_t = wt(wqkv), wt(wo), wt(wfc), wt(wpr)
+            gl = [torch.empty(p.shape, dtype=torch.float32, device=dev)
+                  for p in (wqkv, bqkv, wo, bo, g1, b1, wfc, bfc, wpr, bpr, g2, b2)]
+            (a.dWqkv, a.dbqkv, a.dWo, a.dbo, a.dg1, a.db1, a.dWfc, a.dbfc, a.dWpr, a.dbpr, a.dg2,
+             a.db2) = (t.data_ptr() for t in gl)
+            grads += gl
+        flw_t = None
+        if not avg:
+            flw_t = ops.linear_prepare(flw.t().contiguous(), None, prec)
+        dmain, daux, dflw = ops.cam_backward(
+            dout, main, aux, T, None if avg else res, arr, heads,
+            _ffi.CAM_READOUT_AVG if avg else _ffi.CAM_READOUT_RESIDUAL_ONLY, flw_t, ctx.skip_mask,
+            prec, res_act, want_dflw=not avg)
+        del keep
         return (dmain, daux, None, None, dflw if ctx.has_flw else None, *grads)
 
 

@@ -748,6 +748,35 @@ def cam_readout_bwd(T: Optional[torch.Tensor], main: torch.Tensor, dout: torch.T
 
 
 # ----------------------------------------------------------------------------------- tracing
+def cam_backward(dout: torch.Tensor, main: torch.Tensor, aux: torch.Tensor, T: torch.Tensor,
+                 res_in: Optional[torch.Tensor], layers, heads: int, readout_mode: int,
+                 final_linear_t: Optional[torch.Tensor] = None,
+                 skip_mask: Optional[torch.Tensor] = None, precision="exact", res_act=None,
+                 want_dflw: bool = False):
+    """The whole backward of `_adapt_feature` in one C call (vtc_cam_backward).  `layers` is a ctypes
+    array of _ffi.CamLayerBwd whose gradient buffers the call fills.  Returns (dmain, daux, dflw)."""
+    dev = _req_cuda(dout, main, aux, T)
+    dout = dout.float().contiguous()
+    b, D = main.shape
+    L = aux.shape[0] + 1
+    prec = _prec(precision)
+    dmain = torch.empty(b, D, dtype=torch.float32, device=dev)
+    daux = torch.empty_like(aux, dtype=torch.float32)
+    dflw = torch.empty(D, D, dtype=torch.float32, device=dev) if want_dflw else None
+    if skip_mask is not None:
+        skip_mask = skip_mask.to(device=dev, dtype=torch.uint8).contiguous()
+    lib = _ffi.load()
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, int(lib.vtc_cam_backward_workspace_bytes(L, b, D, prec)))
+        act, scale, shift, mul = _res_act_args(res_act, dev)
+        _ffi.check(lib.vtc_cam_backward(_ptr(dout), _ptr(main), _ptr(aux), _ptr(T), _ptr(res_in),
+                                        _ptr(skip_mask), L, b, D, heads, len(layers), layers,
+                                        readout_mode, _ptr(final_linear_t), act, scale, _ptr(shift),
+                                        _ptr(mul), prec, _ptr(dmain), _ptr(daux), _ptr(dflw), _ptr(ws),
+                                        ws.numel(), _stream(dev)), "vtc_cam_backward")
+    return dmain, daux, dflw
+
+
 def _install_nvtx_ranges() -> None:
     """VTC_NVTX=1: wrap every public op in an NVTX range `vtc.<name>` so that ncu / nsys can filter
     and group by library call (`ncu --nvtx --nvtx-include "vtc.sim_rank/"`).  The reference's only
