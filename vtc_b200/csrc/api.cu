@@ -99,7 +99,7 @@ OperandPlan plan_operands(int D, int dtype, int precision) {
   return o;
 }
 
-constexpr int64_t kMaxRows = (int64_t)1 << 30;
+constexpr int64_t kMaxRows = (int64_t)1 << 29;  // (guard-band list entries pack row, column group and a mask)
 
 // bf16 inputs whose rows already are whole 128-byte swizzle atoms ARE the tensor-core operands:
 // no prep launch, no copy (callers that keep bf16 embeddings, the multi-GPU gather and the

@@ -4,6 +4,7 @@
 // Arithmetic: see exact.cu ("fp64-sequential", identical to oracle/vtc_oracle.c).
 #pragma once
 #include "common.cuh"
+#include "sim_tc.cuh"
 
 namespace vtc {
 
@@ -115,9 +116,11 @@ __device__ __forceinline__ bool rows_vectorisable(const T* base, int64_t ld) {
   return (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & kAlign) == 0;
 }
 
-// The tensor-core pass lists (t, j0): "row t has a score inside the guard band among gallery columns
-// [j0, j0 + 8)" in one segment per CTA and adds nothing for such a group; all 8 columns are decided
-// here in canonical arithmetic.
+// The tensor-core pass lists (t, j0, mask): "row t scores inside the guard band at the columns j0 + i
+// of [j0, j0 + 8) whose mask bit i is set" in one segment per CTA; it has already counted the
+// group's columns that are certainly below the band, the masked ones are decided here in canonical
+// arithmetic (round 2a re-decided all 8 columns of a group: 4.5x the L2 traffic for typically one
+// in-band column).
 //
 // One warp decides FOUR groups at a time, a lane per column: the 4 x (query row + 8 gallery rows) are
 // staged 32 columns at a time in a warp-private shared-memory tile by the whole warp (128-bit loads,
@@ -134,17 +137,27 @@ constexpr int RC_GROUP_ROWS = RECHECK_GROUP + 1;   // the query row + the group'
 constexpr int RC_ROWS = RC_GROUPS * RC_GROUP_ROWS; // 36
 constexpr int RC_WARP_FLOATS = RC_ROWS * RC_LD;       // 1296 floats
 
-// `e`: the entry of this lane's group (lanes 8g .. 8g+7 hold group g), e.x < 0 = no group.
+// `e`: the packed entry of this lane's group (lanes 8g .. 8g+7 hold group g), if `has`.
 template <typename T>
 __device__ __forceinline__ void recheck_groups_warp(
-    float* __restrict__ st, int2 e, const T* __restrict__ Q, int64_t ldq, const T* __restrict__ G,
+    float* __restrict__ st, int2 e, bool has, const T* __restrict__ Q, int64_t ldq, const T* __restrict__ G,
     int64_t ldg, const double* __restrict__ sq64, const double* __restrict__ dgt, int64_t N,
     int64_t M, int D, const int64_t* __restrict__ gt, int64_t row_offset, int64_t col_offset,
     int metric, int* __restrict__ rank) {
   const int lane = threadIdx.x & 31;
+  unsigned int cmask = 0;  // the group's columns that need the canonical decision
+  if (has) {
+    int t_, j_;
+    tc::amb_unpack(e, &t_, &j_, &cmask);
+    e = make_int2(t_, j_);
+  } else {
+    e = make_int2(-1, 0);
+  }
   if (e.x >= N || e.y >= M) e.x = -1;  // zero-padded tile rows / columns
+  if (e.x < 0) cmask = 0;
   const bool vq = rows_vectorisable(Q, ldq), vg = rows_vectorisable(G, ldg);
-  // loader view: lane owns column quad (lane % 8) of staged rows 4 i + lane / 8, i = 0..8
+  // loader view: lane owns column quad (lane % 8) of staged rows 4 i + lane / 8, i = 0..8;
+  // gallery rows outside the mask are not loaded at all (their chains run on zeros, unused)
   const T* src[RC_GROUP_ROWS];
   bool is_q[RC_GROUP_ROWS];
 #pragma unroll
@@ -153,12 +166,13 @@ __device__ __forceinline__ void recheck_groups_warp(
     const int g = row / RC_GROUP_ROWS, rr = row % RC_GROUP_ROWS;
     const int t = __shfl_sync(0xffffffffu, e.x, 8 * g);
     const int j0 = __shfl_sync(0xffffffffu, e.y, 8 * g);
+    const unsigned int gm = __shfl_sync(0xffffffffu, cmask, 8 * g);
     is_q[i] = rr == 0;
     src[i] = nullptr;
-    if (t >= 0) {
+    if (t >= 0 && gm != 0) {
       if (rr == 0)
         src[i] = Q + (int64_t)t * ldq;
-      else if ((int64_t)j0 + rr - 1 < M)
+      else if (((gm >> (rr - 1)) & 1u) && (int64_t)j0 + rr - 1 < M)
         src[i] = G + ((int64_t)j0 + rr - 1) * ldg;
     }
   }
@@ -194,7 +208,7 @@ __device__ __forceinline__ void recheck_groups_warp(
     }
     for (; k < kn; ++k) acc = fma((double)qs[k], (double)xs[k], acc);
   }
-  if (e.x >= 0) {
+  if (e.x >= 0 && ((cmask >> (lane & 7)) & 1u)) {
     const int64_t t = e.x, jl = (int64_t)e.y + (lane & 7);
     if (jl < M) {
       const int64_t g = gt ? gt[t] : t + row_offset;
@@ -217,19 +231,26 @@ static_assert(RC_GROUP_ROWS * RC1_LD <= RC_WARP_FLOATS, "the staging tile serves
 
 template <typename T>
 __device__ __forceinline__ void recheck_group_warp(
-    float* __restrict__ st, int64_t t, int64_t j0, const T* __restrict__ Q, int64_t ldq,
+    float* __restrict__ st, int2 entry, const T* __restrict__ Q, int64_t ldq,
     const T* __restrict__ G, int64_t ldg, const double* __restrict__ sq64,
     const double* __restrict__ dgt, int64_t N, int64_t M, int D, const int64_t* __restrict__ gt,
     int64_t row_offset, int64_t col_offset, int metric, int* __restrict__ rank) {
   const int lane = threadIdx.x & 31;
-  if (t >= N || j0 >= M) return;  // zero-padded tile rows / columns (warp-uniform)
+  int t_, j_;
+  unsigned int cmask;
+  tc::amb_unpack(entry, &t_, &j_, &cmask);
+  const int64_t t = t_, j0 = j_;
+  if (t >= N || j0 >= M || cmask == 0) return;  // zero-padded tile rows / columns (warp-uniform)
   const bool vq = rows_vectorisable(Q, ldq), vg = rows_vectorisable(G, ldg);
   const T* qrow = Q + t * ldq;
+  const T* xrow[RECHECK_GROUP];  // only the columns of the mask are loaded
+#pragma unroll
+  for (int r = 0; r < RECHECK_GROUP; ++r)
+    xrow[r] = (((cmask >> r) & 1u) && j0 + r < M) ? G + (j0 + r) * ldg : (const T*)nullptr;
   float v[RC_GROUP_ROWS][4];
   load_quad(qrow, 4 * lane, D, vq, v[0]);
 #pragma unroll
-  for (int r = 0; r < RECHECK_GROUP; ++r)
-    load_quad(j0 + r < M ? G + (j0 + r) * ldg : (const T*)nullptr, 4 * lane, D, vg, v[1 + r]);
+  for (int r = 0; r < RECHECK_GROUP; ++r) load_quad(xrow[r], 4 * lane, D, vg, v[1 + r]);
   double acc = 0.0;
   for (int k0 = 0; k0 < D; k0 += RC1_KC) {
     __syncwarp();  // the walkers have finished the previous chunk
@@ -240,9 +261,7 @@ __device__ __forceinline__ void recheck_group_warp(
     if (k0 + RC1_KC < D) {
       load_quad(qrow, k0 + RC1_KC + 4 * lane, D, vq, v[0]);
 #pragma unroll
-      for (int r = 0; r < RECHECK_GROUP; ++r)
-        load_quad(j0 + r < M ? G + (j0 + r) * ldg : (const T*)nullptr, k0 + RC1_KC + 4 * lane, D, vg,
-                  v[1 + r]);
+      for (int r = 0; r < RECHECK_GROUP; ++r) load_quad(xrow[r], k0 + RC1_KC + 4 * lane, D, vg, v[1 + r]);
     }
     if (lane < RECHECK_GROUP) {
       const int kn = min(RC1_KC, D - k0);
@@ -261,7 +280,7 @@ __device__ __forceinline__ void recheck_group_warp(
     }
   }
   const int64_t jl = j0 + lane;
-  if (lane < RECHECK_GROUP && jl < M) {
+  if (lane < RECHECK_GROUP && ((cmask >> lane) & 1u) && jl < M) {
     const int64_t g = gt ? gt[t] : t + row_offset;
     const int64_t jg = jl + col_offset;
     if (jg != g) {
@@ -297,16 +316,15 @@ __device__ __forceinline__ void recheck_all(
     if (n < 2u * RC_GROUPS * step) {
       // a few groups per warp at most: the variant with the shorter critical path
       for (unsigned int u = first; u < n; u += step) {
-        const int2 e = seg_list[u];
-        recheck_group_warp<T>(st, e.x, e.y, Q, ldq, G, ldg, sq64, dgt, N, M, D, gt, row_offset,
+        recheck_group_warp<T>(st, seg_list[u], Q, ldq, G, ldg, sq64, dgt, N, M, D, gt, row_offset,
                               col_offset, metric, rank);
       }
       continue;
     }
     for (unsigned int u = first * RC_GROUPS; u < n; u += step * RC_GROUPS) {
       const unsigned int mine = u + (lane >> 3);
-      const int2 e = mine < n ? seg_list[mine] : make_int2(-1, 0);
-      recheck_groups_warp<T>(st, e, Q, ldq, G, ldg, sq64, dgt, N, M, D, gt, row_offset, col_offset,
+      const int2 e = mine < n ? seg_list[mine] : make_int2(0, 0);
+      recheck_groups_warp<T>(st, e, mine < n, Q, ldq, G, ldg, sq64, dgt, N, M, D, gt, row_offset, col_offset,
                              metric, rank);
     }
   }

@@ -42,8 +42,8 @@ struct Params {
   const unsigned int* split_max_bits;   // float bits of max_j |lo(x_j)|^2, max_j |e(x_j)|^2
   int metric_l2;                     // 1: score = ||x||^2 - 2 q.x, 0: score = -q.x
   int* rank;          // [N] += #{j : score < lo}
-  int2* amb_list;     // (t, j0): row t has a score in [lo, hi] among columns [j0, j0 + 8);
-                      // one segment of amb_seg_cap entries per CTA
+  int2* amb_list;     // amb_pack(t, j0, mask): row t has a score in [lo, hi] at the columns j0 + i of
+                      // [j0, j0 + 8) whose mask bit i is set; one segment of amb_seg_cap entries per CTA
   unsigned int* amb_seg_count;  // [grid] entries each CTA wanted to push (may exceed the capacity)
   unsigned int amb_seg_cap;
   // ground-truth column of row t in THIS launch's column numbering:
@@ -133,6 +133,19 @@ int debug_prof_read(unsigned long long* out, int max_words);
 // below lo = d(t,gt) - delta and certainly not above hi = d(t,gt) + delta.
 //   dot error <= guard_rel * |q| * max|x|;  L2: d = sq32 - 2 acc in fp32 adds the roundings of sq32
 //   and of the FMA.  qq is an upper bound of |q|^2, gmax_sq the largest finite gallery norm^2.
+// One entry of the guard-band list: row t (< 2^29), first column j0 of an 8-column group (a multiple
+// of 8, < 2^30) and the 8-bit mask of its columns that need the canonical re-check.
+__host__ __device__ inline int2 amb_pack(int t, int j0, unsigned int mask) {
+  return make_int2((int)((unsigned int)t | ((mask >> 5) << 29)),
+                   (int)(((unsigned int)j0 >> 3) | ((mask & 31u) << 27)));
+}
+__host__ __device__ inline void amb_unpack(int2 e, int* t, int* j0, unsigned int* mask) {
+  const unsigned int x = (unsigned int)e.x, y = (unsigned int)e.y;
+  *t = (int)(x & 0x1fffffffu);
+  *j0 = (int)((y & 0x07ffffffu) << 3);
+  *mask = ((x >> 29) << 5) | (y >> 27);
+}
+
 // What hi*hi + hi*lo + lo*hi drops of q.x, with q = hi + lo + e per element (hi = bf16(q),
 // lo = bf16(q - hi), e = q - hi - lo, all exact in fp32):  q.x - (hq.hx + hq.lx + lq.hx) =
 // q.ex + lq.lx + eq.(x - ex), so by Cauchy-Schwarz

@@ -130,15 +130,16 @@ struct RankEpi {
     }
     rank_band(d0, (double)qq, gmax_sq, metric_l2, guard_rel, split_abs, lo, hi);
   }
-  // rare: this row has a score inside the guard band among columns [j, j+8): hand the whole group
-  // to the fp64 re-check (its definite count is NOT added here).  List segments are per CTA, slots
-  // come from a shared-memory counter, so there is no global atomic hot spot.
+  // rare: this row has scores inside the guard band among columns [j, j+8): hand the group and the
+  // mask of those columns to the fp64 re-check.  List segments are per CTA, slots come from a
+  // shared-memory counter, so there is no global atomic hot spot.
   // (static + by-value arguments: a member function would force the epilogue state through
   // `this`, i.e. into local memory, on the hot path)
   static __device__ __noinline__ void push_group(int2* __restrict__ seg_list, unsigned int seg_cap,
-                                                 unsigned int* seg_count, int t, int j) {
+                                                 unsigned int* seg_count, int t, int j,
+                                                 unsigned int mask) {
     const unsigned int slot = atomicAdd(seg_count, 1u);
-    if (slot < seg_cap) seg_list[slot] = make_int2(t, j);
+    if (slot < seg_cap) seg_list[slot] = amb_pack(t, j, mask);
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
@@ -165,17 +166,20 @@ struct RankEpi {
                        ((d2 <= hi ? 1.f : 0.f) + (d3 <= hi ? 1.f : 0.f)) +
                        ((d4 <= hi ? 1.f : 0.f) + (d5 <= hi ? 1.f : 0.f)) +
                        ((d6 <= hi ? 1.f : 0.f) + (d7 <= hi ? 1.f : 0.f));
+      csum += lt;  // columns certainly below the band count here, whatever the rest of the group does
       if (le != lt) {
-        // the ground truth's own score is in the band by construction: a group whose ONLY in-band
-        // column is that one is decided (the column is skipped by index in the count anyway)
+        // rare: some column of the group scores inside [lo, hi].  Those -- and only those -- go to
+        // the fp64 re-check, as a bit mask; the ground truth's own column is in the band by
+        // construction and is not a competitor (cleared by index).
         const int j0 = (int)jbase + RANK_GROUP * g;
-        if (le - lt == 1.f && (unsigned)(gtc - j0) < (unsigned)RANK_GROUP)
-          csum += lt;
-        else
+        unsigned int mask = (unsigned int)(d0 <= hi && !(d0 < lo)) | ((unsigned int)(d1 <= hi && !(d1 < lo)) << 1) |
+                            ((unsigned int)(d2 <= hi && !(d2 < lo)) << 2) | ((unsigned int)(d3 <= hi && !(d3 < lo)) << 3) |
+                            ((unsigned int)(d4 <= hi && !(d4 < lo)) << 4) | ((unsigned int)(d5 <= hi && !(d5 < lo)) << 5) |
+                            ((unsigned int)(d6 <= hi && !(d6 < lo)) << 6) | ((unsigned int)(d7 <= hi && !(d7 < lo)) << 7);
+        if ((unsigned)(gtc - j0) < (unsigned)RANK_GROUP) mask &= ~(1u << (gtc - j0));
+        if (mask)
           push_group(p.amb_list + (size_t)blockIdx.x * p.amb_seg_cap, p.amb_seg_cap, seg_count,
-                     (int)t, j0);
-      } else {
-        csum += lt;
+                     (int)t, j0, mask);
       }
     }
     cnt += (int)csum;
