@@ -136,10 +136,19 @@ struct RankEpi {
   // (static + by-value arguments: a member function would force the epilogue state through
   // `this`, i.e. into local memory, on the hot path)
   static __device__ __noinline__ void push_group(int2* __restrict__ seg_list, unsigned int seg_cap,
-                                                 unsigned int* seg_count, int t, int j,
-                                                 unsigned int mask) {
+                                                 unsigned int* seg_count, int t, int j0, int gtc,
+                                                 float lo, float hi, float d0, float d1, float d2,
+                                                 float d3, float d4, float d5, float d6, float d7) {
+    // which columns score inside [lo, hi]: those -- and only those -- go to the fp64 re-check; the
+    // ground truth's own column is in the band by construction and is not a competitor
+    unsigned int mask = (unsigned int)(d0 <= hi && !(d0 < lo)) | ((unsigned int)(d1 <= hi && !(d1 < lo)) << 1) |
+                        ((unsigned int)(d2 <= hi && !(d2 < lo)) << 2) | ((unsigned int)(d3 <= hi && !(d3 < lo)) << 3) |
+                        ((unsigned int)(d4 <= hi && !(d4 < lo)) << 4) | ((unsigned int)(d5 <= hi && !(d5 < lo)) << 5) |
+                        ((unsigned int)(d6 <= hi && !(d6 < lo)) << 6) | ((unsigned int)(d7 <= hi && !(d7 < lo)) << 7);
+    if ((unsigned)(gtc - j0) < (unsigned)RANK_GROUP) mask &= ~(1u << (gtc - j0));
+    if (mask == 0) return;
     const unsigned int slot = atomicAdd(seg_count, 1u);
-    if (slot < seg_cap) seg_list[slot] = amb_pack(t, j, mask);
+    if (slot < seg_cap) seg_list[slot] = amb_pack(t, j0, mask);
   }
   __device__ __forceinline__ void chunk(const Params& p, const uint32_t (&v)[32],
                                         const float* __restrict__ bias, float scale, int64_t jbase,
@@ -167,20 +176,9 @@ struct RankEpi {
                        ((d4 <= hi ? 1.f : 0.f) + (d5 <= hi ? 1.f : 0.f)) +
                        ((d6 <= hi ? 1.f : 0.f) + (d7 <= hi ? 1.f : 0.f));
       csum += lt;  // columns certainly below the band count here, whatever the rest of the group does
-      if (le != lt) {
-        // rare: some column of the group scores inside [lo, hi].  Those -- and only those -- go to
-        // the fp64 re-check, as a bit mask; the ground truth's own column is in the band by
-        // construction and is not a competitor (cleared by index).
-        const int j0 = (int)jbase + RANK_GROUP * g;
-        unsigned int mask = (unsigned int)(d0 <= hi && !(d0 < lo)) | ((unsigned int)(d1 <= hi && !(d1 < lo)) << 1) |
-                            ((unsigned int)(d2 <= hi && !(d2 < lo)) << 2) | ((unsigned int)(d3 <= hi && !(d3 < lo)) << 3) |
-                            ((unsigned int)(d4 <= hi && !(d4 < lo)) << 4) | ((unsigned int)(d5 <= hi && !(d5 < lo)) << 5) |
-                            ((unsigned int)(d6 <= hi && !(d6 < lo)) << 6) | ((unsigned int)(d7 <= hi && !(d7 < lo)) << 7);
-        if ((unsigned)(gtc - j0) < (unsigned)RANK_GROUP) mask &= ~(1u << (gtc - j0));
-        if (mask)
-          push_group(p.amb_list + (size_t)blockIdx.x * p.amb_seg_cap, p.amb_seg_cap, seg_count,
-                     (int)t, j0, mask);
-      }
+      if (le != lt)  // rare: some column of the group scores inside [lo, hi]
+        push_group(p.amb_list + (size_t)blockIdx.x * p.amb_seg_cap, p.amb_seg_cap, seg_count, (int)t,
+                   (int)jbase + RANK_GROUP * g, gtc, lo, hi, d0, d1, d2, d3, d4, d5, d6, d7);
     }
     cnt += (int)csum;
   }
@@ -548,25 +546,32 @@ struct TopkEpi {
 struct Work {
   int qg, split, t0, t1;
 };
-__device__ __forceinline__ Work decode_work(const Params& p, int item, int q_groups) {
+// (out of line, scalar arguments by value: called once per work item by each role; inlined five times
+// it grew the kernel by a quarter, and the epilogue-bound D = 256 shape lost 8 % to the instruction
+// cache -- a reference to Params would instead push the kernel parameters through local memory)
+static __device__ __noinline__ Work decode_work_impl(int item, int q_groups, int tail_first, int tail_parts,
+                                              int tiles_per_split, int g_tiles) {
   int base = item, part = 0, parts = 1;
-  if (item >= p.tail_first) {
-    const int u = item - p.tail_first;
-    base = p.tail_first + u / p.tail_parts;
-    part = u % p.tail_parts;
-    parts = p.tail_parts;
+  if (item >= tail_first) {
+    const int u = item - tail_first;
+    base = tail_first + u / tail_parts;
+    part = u % tail_parts;
+    parts = tail_parts;
   }
   Work w;
   w.qg = base % q_groups;
   w.split = base / q_groups;
-  w.t0 = w.split * p.tiles_per_split;
-  w.t1 = min(p.g_tiles, w.t0 + p.tiles_per_split);
+  w.t0 = w.split * tiles_per_split;
+  w.t1 = min(g_tiles, w.t0 + tiles_per_split);
   if (parts > 1) {
     const int len = w.t1 - w.t0, lo = w.t0;
     w.t0 = lo + (int)(((long long)len * part) / parts);
     w.t1 = lo + (int)(((long long)len * (part + 1)) / parts);
   }
   return w;
+}
+__device__ __forceinline__ Work decode_work(const Params& p, int item, int q_groups) {
+  return decode_work_impl(item, q_groups, p.tail_first, p.tail_parts, p.tiles_per_split, p.g_tiles);
 }
 
 template <typename Epi, bool kRes, int kC, bool kPair = false, int kBN = BN>
