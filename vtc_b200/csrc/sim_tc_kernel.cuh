@@ -565,8 +565,9 @@ static __device__ __noinline__ Work decode_work_impl(int item, int q_groups, int
   w.t1 = min(g_tiles, w.t0 + tiles_per_split);
   if (parts > 1) {
     const int len = w.t1 - w.t0, lo = w.t0;
-    w.t0 = lo + (int)(((long long)len * part) / parts);
-    w.t1 = lo + (int)(((long long)len * (part + 1)) / parts);
+    // (len <= 2^22 tiles and parts <= 148: the products fit 32 bits)
+    w.t0 = lo + (int)(((unsigned)len * (unsigned)part) / (unsigned)parts);
+    w.t1 = lo + (int)(((unsigned)len * (unsigned)(part + 1)) / (unsigned)parts);
   }
   return w;
 }
@@ -725,24 +726,20 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int t0 = wk.t0, t1 = wk.t1;
         if (t0 >= t1) continue;
         for (int tile = t0; tile < t1; ++tile) {
-          if (prof) {
-            const long long c0 = clock64();
-            mbar_wait(&tmem_empty[as], aphase ^ 1);
-            w_acc += (unsigned long long)(clock64() - c0);
-            ++n_tiles;
-          } else {
+          {
+            // (one copy of every wait: the profiling reads are predicated around it)
+            const long long c0 = prof ? clock64() : 0;
             mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue has drained this accumulator
+            if (prof) w_acc += (unsigned long long)(clock64() - c0), ++n_tiles;
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * kBN;
           for (int kb = 0; kb < nkb; ++kb) {
             if (kRes && tile == t0) mbar_wait(&a_full[kb], it & 1);
-            if (prof) {
-              const long long c0 = clock64();
+            {
+              const long long c0 = prof ? clock64() : 0;
               mbar_wait(&full[stage], phase);
-              w_ld += (unsigned long long)(clock64() - c0);
-            } else {
-              mbar_wait(&full[stage], phase);
+              if (prof) w_ld += (unsigned long long)(clock64() - c0);
             }
             tc_fence_after();
             uint8_t* st = stages + stage * L::kStageBytes;
@@ -832,12 +829,10 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         ? (int64_t)decode_work(p, nitem, q_groups).t0 * kBN + half * kHalfCols
                         : 0;
         }
-        if (eprof) {
-          const long long c0 = clock64();
+        {
+          const long long c0 = eprof ? clock64() : 0;
           mbar_wait(&tmem_full[as], aphase);
-          e_wait += (unsigned long long)(clock64() - c0);
-        } else {
-          mbar_wait(&tmem_full[as], aphase);
+          if (eprof) e_wait += (unsigned long long)(clock64() - c0);
         }
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_off + as * kBN + half * kHalfCols;
