@@ -320,7 +320,9 @@ struct StoreEpi {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float z = fmaf(scale, __uint_as_float(v[4 * i + e]), bb[e]);
-        if (p.act == 1) z = z / (1.f + __expf(-1.702f * z));  // QuickGELU: z * sigmoid(1.702 z)
+        // QuickGELU: z * sigmoid(1.702 z).  __fdividef (MUFU.RCP, 2 ulp): the IEEE division is a
+        // ~40-instruction subroutine per element and made c_fc's epilogue 4x its main loop
+        if (p.act == 1) z = __fdividef(z, 1.f + __expf(-1.702f * z));
         if (p.act == 2) {
           const float acc = __uint_as_float(v[4 * i + e]), x = scale * acc;
           // (the split operands carry fp32 logits: accurate exponentials there)
