@@ -23,6 +23,11 @@ for prec in ("brute", "exact", "bf16"):
     assert np.array_equal(r.cpu().numpy(), O.rank0_exact(Tq, Vq)), prec
     v, i = ops.sim_topk(q, g, 11, precision=prec)
     assert np.array_equal(i.cpu().numpy(), O.topk_exact(Tq, Vq, 11)[1]), prec
+# the one-call evaluation (prologue, tensor-core pass, re-check chain, hit counts, median)
+for prec in ("exact", "bf16"):
+    full = ops.rank_eval(q[:300], g[:300], [1, 5, 10], precision=prec)
+    Tq, Vq = (O.bf16_round(T), O.bf16_round(V)) if prec == "bf16" else (T, V)
+    assert np.array_equal(full["rank0"].cpu().numpy(), O.rank0_exact(Tq, Vq[:300])), prec
 # a gallery long enough for the top-k sample pass (dense scores + per-row threshold kernel)
 T2, V2 = make_retrieval_pair(200, 33000, 64, sigma=2.0, seed=4)
 v, i = ops.sim_topk(T2.to(dev), V2.to(dev), 11, precision="bf16")
@@ -40,6 +45,9 @@ for force in ("", "1"):
     loss.backward()
     want = O.clip_loss(O.sim_matrix(vis, txt, torch.tensor(20.0))).item()
     assert abs(loss.item() - want) < 1e-4 * abs(want)
+# clip_loss on a materialised sim (csrc/infonce_dense.cu)
+sim = (20.0 * vis @ txt.t()).to(dev).requires_grad_(True)
+clip_loss((None, None, sim), {}).backward()
 m = PretrainedCLIP_finaltf(64, n_layers=2, n_heads=2).to(dev)
 main, aux = make_cam_inputs(16, 3, 64, seed=2)
 with torch.no_grad():

@@ -93,6 +93,18 @@ def test_invalid_arguments_are_rejected_before_any_launch(lib):
     assert lib.vtc_rank_eval(p, p, 4, 4, 8, _ffi.F32, None, _ffi.METRIC_L2, _ffi.PREC_EXACT, None, 9,
                              p, p, None, None, None, 0, None) == -1
     assert lib.vtc_cam_attn_core(None, 6, 4, 512, 8, None, None) == -1
+    # round-2 entry points: the one-call CAM backward, clip_loss on a materialised sim, the backward's
+    # precision argument
+    assert lib.vtc_cam_backward(None, None, None, None, None, None, 6, 4, 512, 8, 2, None, 0, None, 0,
+                                1.0, None, None, _ffi.PREC_EXACT, None, None, None, None, 0, None) == -1
+    assert lib.vtc_cam_backward_workspace_bytes(6, 256, 512, _ffi.PREC_BF16) > 0
+    assert lib.vtc_cam_backward_workspace_bytes(0, 256, 512, _ffi.PREC_BF16) == 0
+    assert lib.vtc_infonce_dense_fwd(None, 4, 4, None, None, None, None, None) == -1
+    assert lib.vtc_infonce_dense_bwd(p, 4, 2, p, p, p, p, 4, None) == -1      # ld < n
+    assert lib.vtc_infonce_bwd(p, p, 4, 8, _ffi.F32, 7, p, p, p, p, p, p, p, None, 0, None) == -1
+    # the launch trace is off by default: ending one that was never begun reports zero launches
+    buf8 = ctypes.create_string_buffer(64)
+    assert lib.vtc_trace_end(buf8, 64) == 0
     assert lib.vtc_launch_count() == before
 
 

@@ -209,7 +209,7 @@ extern "C" int vtc_infonce_bwd(const void* A, const void* B, int64_t n, int D, i
       D <= 0 || (dtype != VTC_F32 && dtype != VTC_BF16) ||
       (precision != VTC_PREC_EXACT && precision != VTC_PREC_BF16))
     return VTC_ERR_INVALID_ARG;
-  static const bool force_tc = getenv("VTC_INFONCE_FORCE_TC") != nullptr;  // test knob (tests/ only)
+  const bool force_tc = getenv("VTC_INFONCE_FORCE_TC") != nullptr;  // test knob (tests/ only)
   if (n > 2048 || force_tc) {
     // the tensor-core path takes fp32 features (what training hands in)
     if (dtype != VTC_F32) return VTC_ERR_UNSUPPORTED_SHAPE;
