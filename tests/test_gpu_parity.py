@@ -624,6 +624,31 @@ def test_clip_loss_backward_and_dense_sim(cuda_dev, golden):
     np.testing.assert_allclose(_np(torch.diagonal(lz)), np.diag(g["small_sim"]), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("M_total,N", [(700, 333), (1023, 1000), (5000, 4096), (100_000, 10_001),
+                                       (3_000_000, 5000), (3_000_000, 4999), (1 << 28, 2048)])
+def test_rank_finalize_radix_levels(cuda_dev, M_total, N):
+    """R@K hit counts and MedR = median(rank0) + 1 with numpy semantics from the
+    finalisation chain alone (csrc/rank_stage.cu: commit + radix select).  The select takes one, two or
+    three digits depending on the gallery size (< 2^10, < 2^21, larger); the evaluation tests only reach
+    the first two.  Even and odd N (the two middle order statistics), heavy ties, NaN ground truths."""
+    from vtc_b200 import ops
+
+    rng = np.random.default_rng(M_total % 1000 + N)
+    ranks = np.minimum(rng.geometric(1.0 / max(2, M_total // 50), size=N) - 1, M_total - 1).astype(np.int32)
+    ranks[: N // 3] = rng.integers(0, 12, size=N // 3)          # many small, tied ranks
+    ranks[-5:] = M_total - 1                                      # the far end of the range
+    gts = rng.standard_normal(N)
+    gts[::97] = np.nan                                            # no ground truth -> rank M_total
+    want = ranks.copy()
+    want[::97] = M_total
+    k_vals = [1, 5, 10, 100]
+    r = torch.from_numpy(ranks).to(cuda_dev)
+    hits, medr = ops.rank_finalize(r, torch.from_numpy(gts).to(cuda_dev), M_total, k_vals)
+    np.testing.assert_array_equal(_np(r), want)
+    np.testing.assert_array_equal(_np(hits), [(want < k).sum() for k in k_vals])
+    assert medr.item() == float(np.median(want.astype(np.float64)) + 1.0)
+
+
 @pytest.mark.parametrize("n,s", [(300, 100.0), (1000, 14.29), (33, 1.0)])
 def test_clip_loss_on_a_materialised_sim(cuda_dev, n, s):
     """model/loss.py:18-22 handed a real tensor (the reference's own forward returns one,
