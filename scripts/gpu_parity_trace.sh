@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2 (1 GPU): parity after PDL + 64-column tiles + warp-cooperative re-check; trace and secondary benches with PDL on / off.
+# Parity + launch traces + secondary benches with PDL on / off + one headline bench (1 GPU).  usage: gpu_parity_trace.sh <tag>
 set -u
 TAG=${1:-r02f}
 mkdir -p gpurun_out
