@@ -402,19 +402,25 @@ int sim_topk_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
     return launch_topk_brute_rows(a, s);
   }
 
-  if (!aliasQ)
-    VTC_RETURN_IF_ERROR(launch_prep_operand(Q, in_bf16, N, D, D,
-                                            o.split ? PREP_SPLIT_A : PREP_PLAIN, w.opQ, o.Kp, s));
-  if (!aliasG)
-    VTC_RETURN_IF_ERROR(launch_prep_operand(G, in_bf16, M, D, D,
-                                            o.split ? PREP_SPLIT_B : PREP_PLAIN, w.opG, o.Kp, s));
-  VTC_RETURN_IF_ERROR(
-      launch_sqnorm64(a.ex.G, a.ex.bf16, M, D, a.ex.ldg, w.sq64, w.sq32, &w.scalars[0], s));
+  // one staged pass over the rows (rank_stage.cu): operands of both sides, canonical ||x||^2, the
+  // padded epilogue bias and the largest norm -- round 1 spent four launches on this
+  {
+    RankPrologueArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.Q = Q, pa.G = G, pa.in_bf16 = in_bf16 ? 1 : 0, pa.N = N, pa.M = M, pa.D = D;
+    pa.ldq = D, pa.ldg = D;
+    pa.mode_q = aliasQ ? STAGE_NONE : (o.split ? PREP_SPLIT_A : PREP_PLAIN);
+    pa.mode_g = aliasG ? STAGE_NONE : (o.split ? PREP_SPLIT_B : PREP_PLAIN);
+    pa.round_bf16 = (!o.split && !in_bf16) ? 1 : 0;
+    pa.opQ = w.opQ, pa.opG = w.opG, pa.Kp = o.Kp, pa.metric = metric;
+    pa.sq64 = w.sq64, pa.bias = w.sq32, pa.Mpad = round_up<int64_t>(M, tc::BN);
+    pa.max_sq_bits = &w.scalars[0];
+    if (aliasQ) pa.N = 0;  // nothing to do on the query side
+    VTC_RETURN_IF_ERROR(launch_rank_prologue(pa, s));
+  }
   tc::Params p;
   memset(&p, 0, sizeof(p));
   p.N = N, p.M = M, p.num_kb = o.Kp / tc::BK;
-  VTC_RETURN_IF_ERROR(launch_fill_bias(w.sq32, metric == VTC_METRIC_L2 ? w.sq32 : nullptr, M,
-                                       round_up<int64_t>(M, tc::BN), INFINITY, s));
   p.col_bias = w.sq32;
   p.scale = metric == VTC_METRIC_L2 ? -2.f : -1.f;
   p.pool = w.pool, p.pool_meta = w.pool_meta;
