@@ -144,6 +144,11 @@ Plan plan_tiles(Params& p, int max_splits, int cluster, int min_tiles_per_split,
     return e && *e ? atoi(e) : 0;
   }();
   p.dbg_skip_epilogue = skip_epi;
+  static const int dbg_stages = []() {
+    const char* e = getenv("VTC_DBG_STAGES");
+    return e && *e ? atoi(e) : 0;
+  }();
+  p.dbg_stages = dbg_stages;
   p.dbg_prof = dbg_prof_buffer();
   p.q_tiles = (int)ceil_div<int64_t>(p.N, BM);
   p.g_tiles = (int)ceil_div<int64_t>(p.M, pl.bn);

@@ -89,6 +89,7 @@ struct Params {
   int topk_keep;      // entries kept by a compaction (>= k, <= TOPK_KEEP_MAX)
   const float* tau_init;  // optional [N]: initial per-row threshold (from a sample pass); NULL = +inf
   int dbg_skip_epilogue;  // profiling only (VTC_DBG_SKIP_EPILOGUE=1): drain TMEM but reduce nothing
+  int dbg_stages;         // profiling only (VTC_DBG_STAGES=n): use only n stages of the operand ring
   // profiling only (VTC_DBG_PROF=1): per CTA 8 x u64 {clock64 ticks, globaltimer ns, MMA-issuer
   // ticks waiting for a free accumulator (epilogue-bound), ticks waiting for operand stages
   // (load-bound), tiles, epilogue-warp ticks waiting for a full accumulator, ...}

@@ -657,6 +657,9 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int q_groups = (p.q_tiles + kC - 1) / kC;
   const int num_items = p.num_items;  // incl. the sub-items of the balanced last round
   const int nkb = p.num_kb;
+  // ring depth in use (profiling: VTC_DBG_STAGES limits it to show how much load latency the ring hides)
+  const uint32_t nstages = p.dbg_stages > 0 && p.dbg_stages < L::kStages ? (uint32_t)p.dbg_stages
+                                                                         : (uint32_t)L::kStages;
   constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
   // CTA pair: rank 0 issues the MMAs and owns the `full` / `a_full` / `tmem_empty` barriers; both
   // CTAs' TMA loads and epilogue warps signal ITS barriers (shared::cluster addresses)
@@ -689,7 +692,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               if (!kRes) tma_load_2d_pair(st, &tmA, fbar, kb * BK, qt * BM);
               tma_load_2d_pair(st + (kRes ? 0 : A_TILE_BYTES), &tmB, fbar, kb * BK,
                                tile * kBN + cta_rank * (kBN / 2));
-              if (++stage == L::kStages) stage = 0, phase ^= 1;
+              if (++stage == nstages) stage = 0, phase ^= 1;
               continue;
             }
             if (kRes && tile == t0) {
@@ -708,7 +711,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               tma_load_2d_multicast(bdst + cta_rank * kSliceRows * (BK * 2), &tmB, &full[stage],
                                     kb * BK, tile * kBN + cta_rank * kSliceRows, kMask);
             }
-            if (++stage == L::kStages) stage = 0, phase ^= 1;
+            if (++stage == nstages) stage = 0, phase ^= 1;
           }
         }
       }
@@ -764,7 +767,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               umma_commit(&empty[stage]);
             else
               umma_commit_multicast(&empty[stage], kMask);
-            if (++stage == L::kStages) stage = 0, phase ^= 1;
+            if (++stage == nstages) stage = 0, phase ^= 1;
           }
           // accumulator complete (in both CTAs of a pair)
           if (kPair)
