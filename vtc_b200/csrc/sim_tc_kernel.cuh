@@ -660,6 +660,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   // ring depth in use (profiling: VTC_DBG_STAGES limits it to show how much load latency the ring hides)
   const uint32_t nstages = p.dbg_stages > 0 && p.dbg_stages < L::kStages ? (uint32_t)p.dbg_stages
                                                                          : (uint32_t)L::kStages;
+  const bool swap_pipelined = kRes && nstages <= (uint32_t)nkb;
   constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
   // CTA pair: rank 0 issues the MMAs and owns the `full` / `a_full` / `tmem_empty` barriers; both
   // CTAs' TMA loads and epilogue warps signal ITS barriers (shared::cluster addresses)
@@ -673,19 +674,23 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const Work wk = decode_work(p, item, q_groups);
         const int qt = wk.qg * kC + cta_rank, t0 = wk.t0, t1 = wk.t1;
         if (t0 >= t1) continue;  // an empty sub-range: skipped by every role alike
-        if (kRes) mbar_wait(a_empty, (it & 1) ^ 1);  // previous item's MMAs have drained
+        // The resident query tile is swapped k-block by k-block behind the previous item's last tile
+        // when the ring is no deeper than the tile (nstages <= nkb): the wait for ring slot P below
+        // guarantees that the MMAs of position P - nstages -- hence of P - nkb, the last reader of this
+        // k-block of the query tile -- have retired.  Otherwise wait for the whole item to drain.
+        if (kRes && !swap_pipelined) mbar_wait(a_empty, (it & 1) ^ 1);
         ++it;
         for (int tile = t0; tile < t1; ++tile) {
           for (int kb = 0; kb < nkb; ++kb) {
             if (kPair) {
               // each CTA loads its own query rows and its half of the gallery tile into its own
               // shared memory; the bytes of both are expected on the leader's barrier
+              mbar_wait(&empty[stage], phase ^ 1);
               if (kRes && tile == t0) {
                 if (leader) mbar_arrive_expect_tx(&a_full[kb], 2 * A_TILE_BYTES);
                 tma_load_2d_pair(res_a + kb * A_TILE_BYTES, &tmA,
                                  mapa_shared(smem_u32(&a_full[kb]), 0), kb * BK, qt * BM);
               }
-              mbar_wait(&empty[stage], phase ^ 1);
               if (leader) mbar_arrive_expect_tx(&full[stage], 2 * L::kStageBytes);
               const uint32_t fbar = mapa_shared(smem_u32(&full[stage]), 0);
               uint8_t* st = stages + stage * L::kStageBytes;
@@ -695,11 +700,11 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               if (++stage == nstages) stage = 0, phase ^= 1;
               continue;
             }
+            mbar_wait(&empty[stage], phase ^ 1);
             if (kRes && tile == t0) {
               mbar_arrive_expect_tx(&a_full[kb], A_TILE_BYTES);
               tma_load_2d(res_a + kb * A_TILE_BYTES, &tmA, &a_full[kb], kb * BK, qt * BM);
             }
-            mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], L::kStageBytes);
             uint8_t* st = stages + stage * L::kStageBytes;
             if (!kRes) tma_load_2d(st, &tmA, &full[stage], kb * BK, qt * BM);
