@@ -81,7 +81,9 @@ enum {
 enum {
   VTC_OK = 0,
   VTC_ERR_INVALID_ARG = -1,
-  VTC_ERR_UNSUPPORTED_SHAPE = -2,
+  VTC_ERR_UNSUPPORTED_SHAPE = -2, /* beyond the built limits: rows <= 2^29 per side, D <= 8192, k <= 16,
+                                     L <= 16 tokens; or a dtype / precision combination an entry
+                                     point documents as unsupported */
   VTC_ERR_WORKSPACE = -3,
   VTC_ERR_NO_DEVICE = -4,
   VTC_ERR_DRIVER = -5,
