@@ -172,12 +172,20 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
         sq_local = torch.zeros(mx, dtype=torch.float64, device=dev)   # padded like the shard
         qq = torch.empty(n_local, dtype=torch.float32, device=dev)
     local_done = False
+    work_sq = sq_all = None
     if gt_local:
         # every ground truth is in our own chunk: rank against it while the gather is in flight;
-        # the call also yields the ground-truth scores, the shard's norms and the query-norm bounds
-        gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0,
-                                    **({"sq64_out": sq_local[:g_sizes[rank]], "qq_out": qq}
-                                       if cached else {}))
+        # the call also yields the ground-truth scores and the query-norm bounds.  The shard's
+        # canonical norms are computed first, on their own, so that their (800 KB) all_gather runs
+        # behind the local tensor-core pass instead of after it.
+        if cached:
+            backend.rank_prepare(g_local, precision, True, False, sq64_out=sq_local[:g_sizes[rank]])
+            sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
+            work_sq = dist.all_gather_into_tensor(sq_all, sq_local, group=group, async_op=True)
+            gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0,
+                                        sq64=sq_local[:g_sizes[rank]], qq_out=qq)
+        else:
+            gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0)
         local_done = True
     else:
         if have_local:
@@ -191,11 +199,13 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
             backend.rank_prepare(q_local, precision, False, True, qq_out=qq)
     ph.mark("gt+local_rank")
     if work is not None:
-        sq_all = None
         if cached:
             # the owners' norms: [world * mx] fp64, laid out like the gathered rows
-            sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(sq_all, sq_local, group=group)
+            if work_sq is not None:
+                work_sq.wait()
+            else:
+                sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(sq_all, sq_local, group=group)
         work.wait()
         ph.mark("gather_wait")
         # remote row ranges as (start row in the global gallery, buffer start, buffer end)
