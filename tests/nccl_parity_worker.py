@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import vtc_oracle as O  # noqa: E402
-from vtc_b200.parallel import GraphedRankEval, shard_bounds, sharded_rank_eval, sharded_topk  # noqa: E402
+from vtc_b200.parallel import (GraphedRankEval, PipelinedRankEval, shard_bounds,  # noqa: E402
+                               sharded_rank_eval, sharded_topk)
 from vtc_b200.synthetic import make_retrieval_pair  # noqa: E402
 
 
@@ -54,6 +55,19 @@ def main():
                          list(res2["hits"].cpu().numpy()) == [int((want2 < k).sum()) for k in (1, 5, 10)]
                          and float(res2["medr"].cpu()[0]) == O.medr(want2))
         ev.close()
+        # a stream of evaluations from pinned host shards, copies overlapped with the previous replay:
+        # jobs alternate between the two problems, every result must be its own job's
+        pipe = PipelinedRankEval(T[qs:qe].contiguous().to(dev), V[gs:ge].contiguous().to(dev), N, M,
+                                 precision=prec)
+        jobs = [(T, V, want), (T2, V2, want2), (T2, V2, want2), (T, V, want), (T, V, want)]
+        pinned = {id(a): a[lo:hi].contiguous().pin_memory()
+                  for a, lo, hi in ((T, qs, qe), (T2, qs, qe), (V, gs, ge), (V2, gs, ge))}
+        results = [pipe.submit(pinned[id(a)], pinned[id(b)]) for a, b, _ in jobs] + [pipe.flush()]
+        good = good and results[0] is None
+        for (_, _, w), r in zip(jobs, results[1:]):
+            good = good and (list(r["hits"].numpy()) == [int((w < k).sum()) for k in (1, 5, 10)]
+                             and r["medr"] == O.medr(w))
+        pipe.close()
         print(f"[rank {rank}/{world}] N={N} M={M} D={D} {prec}: {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
     flag = torch.tensor([0 if ok else 1], device=dev)

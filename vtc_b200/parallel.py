@@ -334,6 +334,75 @@ class GraphedRankEval:
         self._held = []
 
 
+class PipelinedRankEval:
+    """A stream of sharded evaluations from pinned HOST shards with the copies hidden: two captured
+    steps (GraphedRankEval) with their own static input buffers alternate, so that the host-to-device
+    copy of evaluation k + 1 (on a copy stream) runs while evaluation k is being ranked, and the
+    16-byte result of evaluation k is read back while k + 1 runs.
+
+        pipe = PipelinedRankEval(q_dev, g_dev, N, M, precision="bf16")     # collective
+        for q_host, g_host in jobs:            # pinned fp32 shards of this rank
+            done = pipe.submit(q_host, g_host) # result of the evaluation submitted BEFORE this one
+        last = pipe.flush()
+    Every rank must submit the same number of jobs.  close() before destroy_process_group()."""
+
+    def __init__(self, q_local: torch.Tensor, g_local: torch.Tensor, N_total: int, M_total: int,
+                 k_vals: Sequence[int] = (1, 5, 10), metric: str = "l2", precision: str = "exact",
+                 group=None, want_medr: bool = True):
+        dev = q_local.device
+        self.dev = dev
+        self.steps = [GraphedRankEval(q_local, g_local, N_total, M_total, k_vals, metric, precision,
+                                      group, want_medr) for _ in range(2)]
+        self.copy = torch.cuda.Stream(dev)
+        self.ready = [None, None]      # inputs of slot i have landed (recorded on the copy stream)
+        self.consumed = [None, None]   # replay of slot i has finished reading its inputs (main stream)
+        self.host = [torch.empty(len(k_vals), dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.host_medr = [torch.empty(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.read = [None, None]       # device-to-host read of slot i's result is complete
+        self.k = 0
+        self.pending = None
+
+    def _result(self, slot):
+        self.read[slot].synchronize()
+        return {"hits": self.host[slot].clone(), "medr": float(self.host_medr[slot][0])}
+
+    def submit(self, q_host: torch.Tensor, g_host: torch.Tensor) -> Optional[Dict[str, object]]:
+        slot = self.k & 1
+        step = self.steps[slot]
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy):
+            if self.consumed[slot] is not None:
+                self.copy.wait_event(self.consumed[slot])   # the replay two jobs ago is done with them
+            step.q.copy_(q_host, non_blocking=True)
+            step.g.copy_(g_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy)
+            self.ready[slot] = ev
+        main.wait_event(self.ready[slot])
+        out = step()                                         # one graph launch
+        done = torch.cuda.Event()
+        done.record(main)
+        self.consumed[slot] = done
+        self.host[slot].copy_(out["hits"], non_blocking=True)
+        if out.get("medr") is not None:
+            self.host_medr[slot].copy_(out["medr"], non_blocking=True)
+        rd = torch.cuda.Event()
+        rd.record(main)
+        self.read[slot] = rd
+        prev, self.pending = self.pending, slot
+        self.k += 1
+        return None if prev is None else self._result(prev)
+
+    def flush(self) -> Optional[Dict[str, object]]:
+        prev, self.pending = self.pending, None
+        return None if prev is None else self._result(prev)
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.dev)
+        for s in self.steps:
+            s.close()
+
+
 def _gt_all_local(qs: int, qe: int, g_start: int, g_size: int) -> bool:
     return qs >= g_start and qe <= g_start + g_size
 
