@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-launch times of one sharded retrieval-evaluation step on rank 0 (profiling aid; run under
+"""Per-launch times of one sharded retrieval-evaluation step on rank 0 and on a middle rank (profiling aid; run under
 torchrun on a multi-GPU box).  The library's launch trace records one CUDA event after each of its
 launches, so every interval also contains whatever ran in the stream before that launch (casts,
 NCCL kernels): the sum is the step's device time.
@@ -53,11 +53,14 @@ def main():
         tr = _ffi.trace_end()
         torch.cuda.synchronize()
         runs.append((tr, ev0.elapsed_time(ev1) * 1e3))
-    if rank == 0:
+    for who in sorted({0, world // 2}):   # the first rank and a middle one (remote rows on both sides)
+        dist.barrier()
+        if rank != who:
+            continue
         n = len(runs[0][0])
         rows = [[runs[0][0][i][0], round(statistics.median(r[0][i][1] for r in runs if len(r[0]) == n), 2)]
                 for i in range(n)]
-        print(json.dumps({"what": "sharded_rank_eval eager", "world": world, "d": a.d,
+        print(json.dumps({"what": "sharded_rank_eval eager", "rank": rank, "world": world, "d": a.d,
                           "precision": a.precision, "step_us": round(statistics.median(r[1] for r in runs), 1),
                           "traced_us": round(sum(r[1] for r in rows), 1), "launches": rows}), flush=True)
     dist.barrier()

@@ -21,7 +21,7 @@ import json, sys
 for ln in open(sys.argv[1]):
     if not ln.startswith("{"): continue
     d = json.loads(ln)
-    print("step_us", d["step_us"], "traced_us", d["traced_us"])
+    print("rank", d.get("rank"), "step_us", d["step_us"], "traced_us", d["traced_us"])
     for w, us in d["launches"]:
         print("   %-28s %8.2f" % (w, us))
 for ln in open(sys.argv[2]):

@@ -24,11 +24,11 @@ class OracleBackend:
     def _m(self, metric):
         return self.O.METRIC_L2 if metric == "l2" else self.O.METRIC_DOT
 
-    def gt_scores(self, q, g, row_offset, col_offset, metric, precision):
+    def gt_scores(self, q, g, row_offset, col_offset, metric, precision, gt=None):
         full = self.O.scores64(q, g, self._m(metric)) if g.shape[0] else np.zeros((q.shape[0], 0))
         out = np.full(q.shape[0], np.nan)
         for t in range(q.shape[0]):
-            j = t + row_offset - col_offset
+            j = (int(gt[t]) if gt is not None else t + row_offset) - col_offset
             if 0 <= j < g.shape[0]:
                 out[t] = full[t, j]
         return torch.from_numpy(out)
@@ -44,7 +44,8 @@ class OracleBackend:
                 (torch.from_numpy((sq * (1 + 1e-4)).astype(np.float32)) if want_qq else None))
 
     def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0,
-                 sq64=None, qq=None, sq64_out=None, qq_out=None):
+                 sq64=None, qq=None, sq64_out=None, qq_out=None, gt=None):
+        self.rank_calls = getattr(self, "rank_calls", 0) + 1
         if sq64_out is not None:  # the owner's call computes and stores the cached quantities
             sq64_out.copy_(torch.from_numpy(self.O.sqnorm64(g.numpy()) if g.shape[0] else np.zeros(0)))
         if qq_out is not None:
@@ -57,11 +58,12 @@ class OracleBackend:
             if qq is not None:
                 assert qq.shape == (q.shape[0],) and (qq.numpy() >= self.O.sqnorm64(q.numpy())).all()
         if gt_score is None:
-            gt_score = self.gt_scores(q, g, row_offset, col_offset, metric, precision)
+            gt_score = self.gt_scores(q, g, row_offset, col_offset, metric, precision, gt=gt)
         full = self.O.scores64(q, g, self._m(metric))
         d0 = gt_score.numpy()
+        gts = gt
         for t in range(q.shape[0]):
-            gt = t + row_offset
+            gt = int(gts[t]) if gts is not None else t + row_offset
             jg = np.arange(g.shape[0]) + col_offset
             c = ((full[t] < d0[t]) & (jg != gt)).sum() + ((full[t] == d0[t]) & (jg < gt)).sum()
             rank0[t] += int(c)
@@ -100,7 +102,17 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, N, M, out_q):
+def _with_duplicates(V, dups):
+    """Exact ties across shards: copies of gallery rows below and above the original's shard."""
+    if dups:
+        M = V.shape[0]
+        for src, dst in ((2 * M // 5, 3), (2 * M // 5, M - 10), (2 * M // 5, 2 * M // 5 + 1),
+                         (M - 20, 10), (5, M // 2)):
+            V[dst] = V[src]
+    return V
+
+
+def _worker(rank, world, port, N, M, out_q, dups=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -110,10 +122,14 @@ def _worker(rank, world, port, N, M, out_q):
         from vtc_b200.synthetic import make_retrieval_pair
 
         T, V = make_retrieval_pair(N, M, 64, sigma=2.0, seed=13)
+        V = _with_duplicates(V, dups)
         qs, qe = shard_bounds(N, world, rank)
         gs, ge = shard_bounds(M, world, rank)
         be = OracleBackend()
         res = sharded_rank_eval(T[qs:qe].contiguous(), V[gs:ge].contiguous(), N, M, backend=be)
+        if N == M and qe > qs and M % world == 0:
+            # the own shard + ONE call for all remote rows (compacted around a stand-in row)
+            assert be.rank_calls <= 2, be.rank_calls
         # every call against gathered rows gets the owners' norms (none when a rank has no queries)
         assert getattr(be, "prepared_calls", 0) >= (1 if qe > qs and M > ge - gs else 0)
         tv, ti = sharded_topk(T[:16].contiguous(), V[gs:ge].contiguous(), M, 5, backend=be)
@@ -123,7 +139,7 @@ def _worker(rank, world, port, N, M, out_q):
         dist.destroy_process_group()
 
 
-def _run(N, M, world=2):
+def _run(N, M, world=2, dups=False):
     from oracle import vtc_oracle as O
     from vtc_b200.parallel import shard_bounds
     from vtc_b200.synthetic import make_retrieval_pair
@@ -131,7 +147,7 @@ def _run(N, M, world=2):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, N, M, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, M, q, dups)) for r in range(world)]
     for p in procs:
         p.start()
     got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
@@ -139,6 +155,7 @@ def _run(N, M, world=2):
         p.join(30)
         assert p.exitcode == 0
     T, V = make_retrieval_pair(N, M, 64, sigma=2.0, seed=13)
+    V = _with_duplicates(V, dups)
     want = O.rank0_exact(T, V)
     want_hits = [int((want < k).sum()) for k in (1, 5, 10)]
     _, want_topk = O.topk_exact(T[:16], V, 5)
@@ -171,3 +188,15 @@ def test_row_sharded_eval_unequal_and_tiny_world2():
     _run(101, 101)
     _run(1, 1)
     _run(1, 3)
+
+
+def test_row_sharded_eval_world4_remote_rows_in_one_call():
+    """Middle ranks: the remote rows lie on both sides of the own shard and are ranked as one
+    compacted chunk (parallel._CompactRemote) -- equal shards, unequal shards, and exact ties with
+    rows of lower and of higher shards (the tie-break by column id must come out as in the global
+    gallery); ground truths in other ranks' shards keep one call per remote range."""
+    _run(100, 100, world=4)
+    _run(100, 100, world=4, dups=True)
+    _run(103, 103, world=4, dups=True)
+    _run(90, 151, world=4, dups=True)
+    _run(3, 5, world=4)

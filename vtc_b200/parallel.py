@@ -63,15 +63,16 @@ class CudaBackend:
 
         self.ops = ops
 
-    def gt_scores(self, q, g, row_offset, col_offset, metric, precision):
-        return self.ops.gt_scores(q, g, None, row_offset, col_offset, metric, precision)
+    def gt_scores(self, q, g, row_offset, col_offset, metric, precision, gt=None):
+        return self.ops.gt_scores(q, g, gt, row_offset, col_offset, metric, precision)
 
     def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0,
-                 sq64=None, qq=None, sq64_out=None, qq_out=None):
+                 sq64=None, qq=None, sq64_out=None, qq_out=None, gt=None):
         """Accumulates into rank0; gt_score None = every ground truth lies inside g (computed and
         returned).  sq64 / qq hand cached per-row quantities in, sq64_out / qq_out have this call
-        compute and store them (vtc_sim_rank_prepared)."""
-        _, gs = self.ops.sim_rank(q, g, None, row_offset, col_offset, metric, precision, gt_score,
+        compute and store them (vtc_sim_rank_prepared).  gt (int64 [n], optional) = the ground
+        truths' column ids (j + col_offset) instead of t + row_offset."""
+        _, gs = self.ops.sim_rank(q, g, gt, row_offset, col_offset, metric, precision, gt_score,
                                   rank0, accumulate=True, sq64=sq64, qq=qq, sq64_out=sq64_out,
                                   qq_out=qq_out)
         return gs
@@ -105,6 +106,88 @@ def _all_gather_padded(x: torch.Tensor, sizes: Sequence[int], group, async_op: b
     out = [torch.empty_like(x) for _ in range(world)]
     work = dist.all_gather(out, x.contiguous(), group=group, async_op=async_op)
     return out, work
+
+
+_gt_cache: Dict[tuple, torch.Tensor] = {}
+_side_streams: Dict[str, "torch.cuda.Stream"] = {}
+
+
+def _compact_gt(qs: int, qe: int, gs0: int, own: int, dev) -> torch.Tensor:
+    """Column ids of the ground truths of the local queries [qs, qe) in the compacted remote gallery
+    of _CompactRemote: all of them lie in the own shard, i.e. ARE the stand-in row gs0 (rows below
+    the own shard keep their id, rows above it move down by own - 1, so "j_glob < gt" -- the
+    tie-break of the rank definition -- decides exactly as in the global gallery).  Cached per
+    shape: a captured step replays without rebuilding it."""
+    assert gs0 <= qs and qe <= gs0 + own
+    key = (qe - qs, gs0, str(dev))
+    t = _gt_cache.get(key)
+    if t is None:
+        t = _gt_cache[key] = torch.full((qe - qs,), gs0, dtype=torch.int64).to(dev)
+    return t
+
+
+class _CompactRemote:
+    """The gathered gallery without this rank's own shard, as ONE contiguous chunk.
+
+    In the gathered buffer the remote rows of a middle rank are two ranges around its own shard
+    (world - 1 ranges with unequal shards): one ranking call each, i.e. a second prologue, tensor-core
+    ramp and epilogue chain on every rank but the first and the last -- and the step is the maximum
+    over ranks.  Here the remote rows are copied (behind the local tensor-core pass, on a side
+    stream) into one buffer in global order in which a single zero row stands for the whole own
+    shard.  That row is handed to the library as every local query's ground-truth column: the
+    library skips the ground truth's own column by index and breaks exact ties by "column id <
+    ground-truth id", so rows of lower shards win ties and rows of higher shards lose them exactly
+    as in the global gallery, and the stand-in row itself is never counted (d(t,gt) is handed in).
+    One ranking call per step for the remote rows on every rank, no change in the library.  Only
+    used when every local query's ground truth lies in the own shard (N = M splits): for a query
+    whose ground truth is remote the stand-in would be an ordinary column."""
+
+    def __init__(self, gathered, work, sq_all, work_sq, g_sizes, rank, mx, dev):
+        own = g_sizes[rank]
+        self.lower = sum(g_sizes[:rank])
+        self.rows = sum(g_sizes) - own + 1
+        self.g = torch.empty((self.rows, gathered.shape[1]), dtype=gathered.dtype, device=dev)
+        self.sq = None if sq_all is None else torch.empty(self.rows, dtype=sq_all.dtype, device=dev)
+        pieces = []  # (first row here, first row in the gathered buffer, rows), merged where adjacent
+        pos = 0
+        for r, sz in enumerate(g_sizes):
+            if r == rank:
+                pos += 1
+                continue
+            if sz:
+                if pieces and pieces[-1][0] + pieces[-1][2] == pos and pieces[-1][1] + pieces[-1][2] == r * mx:
+                    pieces[-1] = (pieces[-1][0], pieces[-1][1], pieces[-1][2] + sz)
+                else:
+                    pieces.append((pos, r * mx, sz))
+                pos += sz
+        self.side = None
+        if dev.type == "cuda":
+            main = torch.cuda.current_stream(dev)
+            side = _side_streams.get(str(dev))
+            if side is None:
+                side = _side_streams[str(dev)] = torch.cuda.Stream(dev)
+            side.wait_stream(main)
+            self.side = side
+            ctx = torch.cuda.stream(side)
+        else:
+            import contextlib
+
+            ctx = contextlib.nullcontext()
+        with ctx:
+            work.wait()
+            if work_sq is not None:
+                work_sq.wait()
+            self.g[self.lower].zero_()
+            if self.sq is not None:
+                self.sq[self.lower] = 0
+            for dst, src, n in pieces:
+                self.g[dst:dst + n].copy_(gathered[src:src + n])
+                if self.sq is not None:
+                    self.sq[dst:dst + n].copy_(sq_all[src:src + n])
+
+    def join(self, dev):
+        if self.side is not None:
+            torch.cuda.current_stream(dev).wait_stream(self.side)
 
 
 def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int, M_total: int,
@@ -173,6 +256,15 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
         qq = torch.empty(n_local, dtype=torch.float32, device=dev)
     local_done = False
     work_sq = sq_all = None
+    # remote row ranges as (start row in the global gallery, buffer start, buffer end)
+    remote = []
+    if world > 1:
+        if equal:
+            remote = [(0, 0, gs0), (ge0, ge0, M_total)]
+        else:
+            remote = [(g_starts[r], r * mx, r * mx + g_sizes[r]) for r in range(world) if r != rank]
+        remote = [(st, b0, b1) for st, b0, b1 in remote if b1 > b0]
+    compact = None   # more than one remote range: ranked as one compacted chunk (_CompactRemote)
     if gt_local:
         # every ground truth is in our own chunk: rank against it while the gather is in flight;
         # the call also yields the ground-truth scores and the query-norm bounds.  The shard's
@@ -182,6 +274,8 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
             backend.rank_prepare(g_local, precision, True, False, sq64_out=sq_local[:g_sizes[rank]])
             sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
             work_sq = dist.all_gather_into_tensor(sq_all, sq_local, group=group, async_op=True)
+            if len(remote) > 1:   # the copies wait for both gathers on a side stream
+                compact = _CompactRemote(gathered, work, sq_all, work_sq, g_sizes, rank, mx, dev)
             gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0,
                                         sq64=sq_local[:g_sizes[rank]], qq_out=qq)
         else:
@@ -208,14 +302,17 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
                 dist.all_gather_into_tensor(sq_all, sq_local, group=group)
         work.wait()
         ph.mark("gather_wait")
-        # remote row ranges as (start row in the global gallery, buffer start, buffer end)
-        if equal:
-            remote = [(0, 0, gs0), (ge0, ge0, M_total)]
-        else:
-            remote = [(g_starts[r], r * mx, r * mx + g_sizes[r]) for r in range(world) if r != rank]
-        remote = [(st, b0, b1) for st, b0, b1 in remote if b1 > b0]
+        if compact is None and gt_local and len(remote) > 1:
+            compact = _CompactRemote(gathered, work, sq_all if cached else None, None, g_sizes, rank,
+                                     mx, dev)
+        gt_c = None
+        if compact is not None:
+            compact.join(dev)
+            gt_c = _compact_gt(qs, qe, gs0, g_sizes[rank], dev)
         if not gt_local:
-            # ground truths that live in another rank's shard (N != M splits): fill in where still NaN
+            # ground truths that live in another rank's shard (N != M splits): fill in where still
+            # NaN.  (No compaction here: the stand-in row is only inert for queries whose ground
+            # truth it stands for.)
             for st, b0, b1 in remote:
                 other = backend.gt_scores(q_local, gathered[b0:b1], qs, st, metric, precision)
                 gt_score = torch.where(torch.isnan(gt_score), other, gt_score)
@@ -223,9 +320,13 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
         if not local_done and have_local:
             backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0,
                              **({"sq64": sq_local[:g_sizes[rank]], "qq": qq} if cached else {}))
-        for st, b0, b1 in remote:
-            backend.sim_rank(q_local, gathered[b0:b1], qs, st, metric, precision, gt_score, rank0,
-                             **kw(b0, b1))
+        if compact is not None:
+            backend.sim_rank(q_local, compact.g, 0, 0, metric, precision, gt_score, rank0, gt=gt_c,
+                             **({"sq64": compact.sq, "qq": qq} if cached else {}))
+        else:
+            for st, b0, b1 in remote:
+                backend.sim_rank(q_local, gathered[b0:b1], qs, st, metric, precision, gt_score,
+                                 rank0, **kw(b0, b1))
     elif not local_done and have_local:
         backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
     ph.mark("remote_rank")
