@@ -1,6 +1,6 @@
 #!/bin/bash
-# NCCL parity (default + forced compaction of the remote rows) and the bench line on all GPUs of the
-# box (usage: gpurun --gpus N -- bash scripts/gpu_multi_quick.sh [tag])
+# NCCL parity and the bench line on all GPUs of the box, optionally (TRACE=1) the launch trace of the
+# first and of a middle rank (usage: gpurun --gpus N -- bash scripts/gpu_multi_quick.sh [tag])
 set -u
 TAG=${1:-r02q}
 mkdir -p gpurun_out
@@ -10,12 +10,12 @@ echo "gpus=$NG" > $S
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1"
 timeout 500 python -m pytest tests/test_multigpu.py -m gpu -q --tb=short ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/${TAG}_test_multi_n$NG.log 2>&1
 echo "test_multigpu exit=$?" >> $S; grep -E "rank .*(OK|MISMATCH)|passed|failed|Error" gpurun_out/${TAG}_test_multi_n$NG.log | tail -n 30 >> $S
-for C in ${COMPACT_SET:-1}; do
-  VTC_DBG_COMPACT=$( [ $C = 1 ] && echo 1 ) timeout 300 $TR --master-port 2953$C bench.py --gpus $NG --steps 20 --warmup 3 \
-      > gpurun_out/${TAG}_scale_n${NG}_c$C.json 2> gpurun_out/${TAG}_scale_n${NG}_c$C.err
-  echo "bench n=$NG compact=$C exit=$?" >> $S
-  grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" gpurun_out/${TAG}_scale_n${NG}_c$C.err | tail -n 5 >> $S
-  python - gpurun_out/${TAG}_scale_n${NG}_c$C.json >> $S <<'PY'
+for C in 0; do
+  timeout 300 $TR --master-port 2953$C bench.py --gpus $NG --steps 20 --warmup 3 \
+      > gpurun_out/${TAG}_scale_n${NG}.json 2> gpurun_out/${TAG}_scale_n${NG}.err
+  echo "bench n=$NG exit=$?" >> $S
+  grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" gpurun_out/${TAG}_scale_n${NG}.err | tail -n 5 >> $S
+  python - gpurun_out/${TAG}_scale_n${NG}.json >> $S <<'PY'
 import json, sys
 for ln in open(sys.argv[1]):
     if not ln.startswith("{"): continue

@@ -11,26 +11,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _run_workers(port, extra_env=None):
+def test_sharded_eval_nccl(cuda_dev):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     n = 2 if n < 4 else (4 if n < 8 else 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           "--master-addr", "127.0.0.1", "--master-port", "29517",
            os.path.join(ROOT, "tests", "nccl_parity_worker.py")]
-    env = dict(os.environ, **(extra_env or {}))
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MISMATCH" not in r.stdout
-
-
-def test_sharded_eval_nccl(cuda_dev):
-    _run_workers(29517)
-
-
-def test_sharded_eval_nccl_compacted_remote_rows(cuda_dev):
-    """The one-call ranking of the remote rows (parallel._CompactRemote) is what middle ranks of
-    >= 3 GPUs run; VTC_DBG_COMPACT=1 makes every rank take it, so that a 2-GPU box covers it too
-    (eager, captured and pipelined)."""
-    _run_workers(29518, {"VTC_DBG_COMPACT": "1"})

@@ -63,16 +63,15 @@ class CudaBackend:
 
         self.ops = ops
 
-    def gt_scores(self, q, g, row_offset, col_offset, metric, precision, gt=None):
-        return self.ops.gt_scores(q, g, gt, row_offset, col_offset, metric, precision)
+    def gt_scores(self, q, g, row_offset, col_offset, metric, precision):
+        return self.ops.gt_scores(q, g, None, row_offset, col_offset, metric, precision)
 
     def sim_rank(self, q, g, row_offset, col_offset, metric, precision, gt_score, rank0,
-                 sq64=None, qq=None, sq64_out=None, qq_out=None, gt=None):
+                 sq64=None, qq=None, sq64_out=None, qq_out=None):
         """Accumulates into rank0; gt_score None = every ground truth lies inside g (computed and
         returned).  sq64 / qq hand cached per-row quantities in, sq64_out / qq_out have this call
-        compute and store them (vtc_sim_rank_prepared).  gt (int64 [n], optional) = the ground
-        truths' column ids (j + col_offset) instead of t + row_offset."""
-        _, gs = self.ops.sim_rank(q, g, gt, row_offset, col_offset, metric, precision, gt_score,
+        compute and store them (vtc_sim_rank_prepared)."""
+        _, gs = self.ops.sim_rank(q, g, None, row_offset, col_offset, metric, precision, gt_score,
                                   rank0, accumulate=True, sq64=sq64, qq=qq, sq64_out=sq64_out,
                                   qq_out=qq_out)
         return gs
@@ -108,120 +107,6 @@ def _all_gather_padded(x: torch.Tensor, sizes: Sequence[int], group, async_op: b
     return out, work
 
 
-_gt_cache: Dict[tuple, torch.Tensor] = {}
-_side_streams: Dict[str, "torch.cuda.Stream"] = {}
-
-
-class _Exchange:
-    """The collectives (and the copies that follow them) of a sharded step that run BEHIND the local
-    ranking.  On CUDA they are issued on a side stream forked from the caller's stream and joined
-    back before the first consumer -- the plain fork / join pattern, so a captured step keeps the
-    overlap as parallel branches of the graph; with gloo (CPU tests) they are asynchronous handles
-    waited for at the join."""
-
-    def __init__(self, dev, group):
-        self.group = group
-        self.pending: List = []
-        self.side = self.main = None
-        if dev.type == "cuda":
-            self.main = torch.cuda.current_stream(dev)
-            self.side = _side_streams.get(str(dev))
-            if self.side is None:
-                self.side = _side_streams[str(dev)] = torch.cuda.Stream(dev)
-
-    def all_gather(self, out: torch.Tensor, inp: torch.Tensor) -> None:
-        """all_gather_into_tensor of `inp` as it is on the caller's stream now."""
-        if self.side is None:
-            self.pending.append(dist.all_gather_into_tensor(out, inp, group=self.group, async_op=True))
-            return
-        self.side.wait_stream(self.main)
-        with torch.cuda.stream(self.side):
-            dist.all_gather_into_tensor(out, inp, group=self.group)
-
-    def then(self, fn) -> None:
-        """fn() once everything issued so far has completed, still behind the caller's stream."""
-        if self.side is None:
-            self.join()
-            fn()
-            return
-        with torch.cuda.stream(self.side):
-            fn()
-
-    def join(self) -> None:
-        """The caller's stream (the host, with gloo) waits for everything issued so far."""
-        for w in self.pending:
-            w.wait()
-        self.pending = []
-        if self.side is not None:
-            self.main.wait_stream(self.side)
-
-
-def _compact_gt(qs: int, qe: int, gs0: int, own: int, dev) -> torch.Tensor:
-    """Column ids of the ground truths of the local queries [qs, qe) in the compacted remote gallery
-    of _CompactRemote: all of them lie in the own shard, i.e. ARE the stand-in row gs0 (rows below
-    the own shard keep their id, rows above it move down by own - 1, so "j_glob < gt" -- the
-    tie-break of the rank definition -- decides exactly as in the global gallery).  Cached per
-    shape: a captured step replays without rebuilding it."""
-    assert gs0 <= qs and qe <= gs0 + own
-    key = (qe - qs, gs0, str(dev))
-    t = _gt_cache.get(key)
-    if t is None:
-        t = _gt_cache[key] = torch.full((qe - qs,), gs0, dtype=torch.int64).to(dev)
-    return t
-
-
-class _CompactRemote:
-    """The gathered gallery without this rank's own shard, as ONE contiguous chunk.
-
-    In the gathered buffer the remote rows of a middle rank are two ranges around its own shard
-    (world - 1 ranges with unequal shards): one ranking call each, i.e. a second prologue, tensor-core
-    ramp and epilogue chain on every rank but the first and the last -- and the step is the maximum
-    over ranks.  Here the remote rows are copied (behind the local tensor-core pass, on the exchange's
-    side stream) into one buffer in global order in which a single row stands for the whole own
-    shard.  That row is handed to the library as every local query's ground-truth column, with d(t,gt)
-    handed in: the library breaks exact ties by "column id < ground-truth id", so rows of lower shards
-    win ties and rows of higher shards lose them exactly as in the global gallery.  The stand-in itself
-    must never count: its cached ||x||^2 is +inf, which the library turns into a +inf epilogue bias
-    (never below or inside a guard band, never re-checked) and keeps out of the largest-norm bound
-    (csrc/rank_stage.cu: "NaN / inf rows do not scale the guard band").  One ranking call per step for
-    the remote rows on every rank, no change in the library.  Needs the L2 metric with cached norms
-    (vtc_sim_rank_prepared; the inner-product score has no norm term to carry the +inf) and every
-    local query's ground truth in the own shard (N = M splits): for a query whose ground truth is
-    remote the stand-in would be an ordinary column.  Otherwise: one call per remote range.
-    VTC_DBG_COMPACT=1 (tests) compacts a single remote range too, so that 2 GPUs exercise the path."""
-
-    def __init__(self, gathered, sq_all, g_sizes, rank, mx, dev):
-        own = g_sizes[rank]
-        self.lower = sum(g_sizes[:rank])
-        self.rows = sum(g_sizes) - own + 1
-        self.g = torch.empty((self.rows, gathered.shape[1]), dtype=gathered.dtype, device=dev)
-        self.sq = torch.empty(self.rows, dtype=sq_all.dtype, device=dev)
-        # the stand-in row is written here, on the caller's stream (the copies below touch other rows;
-        # a scalar __setitem__ on the side stream allocates there and broke graph capture)
-        self.g[self.lower:self.lower + 1].zero_()
-        self.sq[self.lower:self.lower + 1].fill_(float("inf"))
-        self._src = (gathered, sq_all)
-        self.pieces = []  # (first row here, first row in the gathered buffer, rows), merged where adjacent
-        pos = 0
-        for r, sz in enumerate(g_sizes):
-            if r == rank:
-                pos += 1
-                continue
-            if sz:
-                last = self.pieces[-1] if self.pieces else None
-                if last and last[0] + last[2] == pos and last[1] + last[2] == r * mx:
-                    self.pieces[-1] = (last[0], last[1], last[2] + sz)
-                else:
-                    self.pieces.append((pos, r * mx, sz))
-                pos += sz
-
-    def copy(self) -> None:
-        gathered, sq_all = self._src
-        for dst, src, n in self.pieces:
-            self.g[dst:dst + n].copy_(gathered[src:src + n])
-            self.sq[dst:dst + n].copy_(sq_all[src:src + n])
-
-
 def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int, M_total: int,
                       k_vals: Sequence[int] = (1, 5, 10), metric: str = "l2",
                       precision: str = "exact", group=None, backend=None,
@@ -254,7 +139,7 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
 
     # gallery exchange: one all_gather into a single [world * max_shard, D] buffer, so that with
     # equal shards the remote rows form (at most) two contiguous ranges [0, gs) and [ge, M)
-    xch = _Exchange(dev, group)
+    work = None
     gathered = None
     mx = max(g_sizes)
     equal = all(sz == mx for sz in g_sizes)
@@ -263,58 +148,40 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
         if send.shape[0] < mx:
             pad = torch.zeros((mx - send.shape[0], send.shape[1]), dtype=send.dtype, device=dev)
             send = torch.cat([send, pad])
-        send = send.contiguous()
         gathered = torch.empty((world * mx, send.shape[1]), dtype=send.dtype, device=dev)
-        xch.all_gather(gathered, send)
+        work = dist.all_gather_into_tensor(gathered, send.contiguous(), group=group, async_op=True)
     ph.mark("cast+gather_issue")
 
     n_local = qe - qs
     gs0, ge0 = g_starts[rank], g_starts[rank] + g_sizes[rank]
     have_local = g_sizes[rank] > 0
     rank0 = torch.zeros(n_local, dtype=torch.int32, device=dev)
-    cached = hasattr(backend, "rank_prepare") and precision in ("bf16", "exact") and world > 1
-    sq_local = sq_all = qq = None
-    if cached:
-        sq_local = torch.zeros(mx, dtype=torch.float64, device=dev)   # padded like the shard
-        sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
     if n_local == 0:
         # more ranks than query rows: take part in the collectives, rank nothing
-        if cached:
-            if have_local:
-                backend.rank_prepare(g_local, precision, True, False,
-                                     sq64_out=sq_local[:g_sizes[rank]])
-            xch.all_gather(sq_all, sq_local)
-        xch.join()
+        if work is not None:
+            work.wait()
+            if hasattr(backend, "rank_prepare") and precision in ("bf16", "exact"):
+                _exchange_norms(backend, g_local, mx, world, precision, group, dev, have_local)
         gt_score = torch.empty(0, dtype=torch.float64, device=dev)
         return _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group,
                                want_medr, ph)
     gt_local = (world == 1 or _gt_all_local(qs, qe, gs0, g_sizes[rank])) and have_local
+    cached = hasattr(backend, "rank_prepare") and precision in ("bf16", "exact") and world > 1
+    sq_local = qq = None
     if cached:
+        sq_local = torch.zeros(mx, dtype=torch.float64, device=dev)   # padded like the shard
         qq = torch.empty(n_local, dtype=torch.float32, device=dev)
-    # remote row ranges as (start row in the global gallery, buffer start, buffer end)
-    remote = []
-    if world > 1:
-        if equal:
-            remote = [(0, 0, gs0), (ge0, ge0, M_total)]
-        else:
-            remote = [(g_starts[r], r * mx, r * mx + g_sizes[r]) for r in range(world) if r != rank]
-        remote = [(st, b0, b1) for st, b0, b1 in remote if b1 > b0]
-    # more than one remote range: ranked as one compacted chunk (_CompactRemote)
-    compact = None
-    if (cached and gt_local and metric == "l2"
-            and (len(remote) > 1 or (remote and os.environ.get("VTC_DBG_COMPACT")))):
-        compact = _CompactRemote(gathered, sq_all, g_sizes, rank, mx, dev)
     local_done = False
+    work_sq = sq_all = None
     if gt_local:
         # every ground truth is in our own chunk: rank against it while the gather is in flight;
         # the call also yields the ground-truth scores and the query-norm bounds.  The shard's
-        # canonical norms are computed first, on their own, so that their (800 KB) all_gather -- and
-        # the compaction of the remote rows -- run behind the local tensor-core pass, not after it.
+        # canonical norms are computed first, on their own, so that their (800 KB) all_gather runs
+        # behind the local tensor-core pass instead of after it.
         if cached:
             backend.rank_prepare(g_local, precision, True, False, sq64_out=sq_local[:g_sizes[rank]])
-            xch.all_gather(sq_all, sq_local)
-            if compact is not None:
-                xch.then(compact.copy)
+            sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
+            work_sq = dist.all_gather_into_tensor(sq_all, sq_local, group=group, async_op=True)
             gt_score = backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, None, rank0,
                                         sq64=sq_local[:g_sizes[rank]], qq_out=qq)
         else:
@@ -329,12 +196,24 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
             if have_local:
                 backend.rank_prepare(g_local, precision, True, False,
                                      sq64_out=sq_local[:g_sizes[rank]])
-            xch.all_gather(sq_all, sq_local)   # the owners' norms, laid out like the gathered rows
             backend.rank_prepare(q_local, precision, False, True, qq_out=qq)
     ph.mark("gt+local_rank")
-    if world > 1:
-        xch.join()
+    if work is not None:
+        if cached:
+            # the owners' norms: [world * mx] fp64, laid out like the gathered rows
+            if work_sq is not None:
+                work_sq.wait()
+            else:
+                sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(sq_all, sq_local, group=group)
+        work.wait()
         ph.mark("gather_wait")
+        # remote row ranges as (start row in the global gallery, buffer start, buffer end)
+        if equal:
+            remote = [(0, 0, gs0), (ge0, ge0, M_total)]
+        else:
+            remote = [(g_starts[r], r * mx, r * mx + g_sizes[r]) for r in range(world) if r != rank]
+        remote = [(st, b0, b1) for st, b0, b1 in remote if b1 > b0]
         if not gt_local:
             # ground truths that live in another rank's shard (N != M splits): fill in where still NaN
             for st, b0, b1 in remote:
@@ -344,14 +223,9 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
         if not local_done and have_local:
             backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0,
                              **({"sq64": sq_local[:g_sizes[rank]], "qq": qq} if cached else {}))
-        if compact is not None:
-            backend.sim_rank(q_local, compact.g, 0, 0, metric, precision, gt_score, rank0,
-                             sq64=compact.sq, qq=qq,
-                             gt=_compact_gt(qs, qe, gs0, g_sizes[rank], dev))
-        else:
-            for st, b0, b1 in remote:
-                backend.sim_rank(q_local, gathered[b0:b1], qs, st, metric, precision, gt_score,
-                                 rank0, **kw(b0, b1))
+        for st, b0, b1 in remote:
+            backend.sim_rank(q_local, gathered[b0:b1], qs, st, metric, precision, gt_score, rank0,
+                             **kw(b0, b1))
     elif not local_done and have_local:
         backend.sim_rank(q_local, g_local, qs, gs0, metric, precision, gt_score, rank0)
     ph.mark("remote_rank")
@@ -361,6 +235,15 @@ def sharded_rank_eval(q_local: torch.Tensor, g_local: torch.Tensor, N_total: int
                 "phases_ms": ph.result()}
     return _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group,
                            want_medr, ph)
+
+
+def _exchange_norms(backend, g_local, mx, world, precision, group, dev, have_local):
+    """A rank without query rows still owns gallery rows: contribute their norms to the exchange."""
+    sq_local = torch.zeros(mx, dtype=torch.float64, device=dev)
+    if have_local:
+        backend.rank_prepare(g_local, precision, True, False, sq64_out=sq_local[:g_local.shape[0]])
+    sq_all = torch.empty(world * mx, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(sq_all, sq_local, group=group)
 
 
 def _finish_sharded(backend, rank0, gt_score, N_total, M_total, k_vals, world, group, want_medr, ph):
