@@ -342,6 +342,65 @@ def test_recall_at_k_and_compute_recall_golden(cuda_dev, golden):
         np.testing.assert_array_equal(np.array([r for _, r in got]) * 100.0, g[key][:, 1])
 
 
+def _reference_hit_loop(I, k_vals, num_samples):
+    """model/metric.py:148-160, the loop the reference runs over the index lists faiss returns."""
+    return [(k, sum(1 for target, rp in enumerate(I) if target in rp[:k]) / num_samples)
+            for k in k_vals]
+
+
+def test_faiss_compat_index_on_reference_fixtures(cuda_dev, golden):
+    """The reference's faiss call site (model/metric.py:139-146) bound to vtc_b200.faiss_compat:
+    GpuIndexFlatL2.add / search(k = max(k_vals) + 1) + the reference's own hit loop reproduce the
+    fixtures the reference's RecallAtK.compute generated; numpy in -> numpy out like faiss."""
+    from vtc_b200 import faiss_compat as faiss
+
+    cfg = faiss.GpuIndexFlatConfig()
+    cfg.useFloat16 = False                       # model/metric.py:112-113
+    cfg.device = cuda_dev.index or 0             # :127
+    g = golden("retrieval_c1.npz")
+    for mixed, key in ((False, "df_values"), (True, "df_values_mixed")):
+        T, V = make_retrieval_pair(1000, 1000, 512, sigma=None if mixed else 6.0, seed=1023,
+                                   mixed=mixed)
+        for a, b, col in ((V, T, 1), (T, V, 0)):   # gallery a, queries b; both retrieval directions
+            index = faiss.GpuIndexFlatL2(faiss.StandardGpuResources(), a.shape[1], cfg)
+            index.add(a.numpy())
+            assert index.ntotal == 1000 and index.d == 512
+            D, I = index.search(b.numpy(), 11)
+            assert isinstance(I, np.ndarray) and I.dtype == np.int64 and I.shape == (1000, 11)
+            assert D.dtype == np.float32 and (np.diff(D, axis=1) >= 0).all()
+            got = _reference_hit_loop(I, [1, 5, 10], 1000)
+            np.testing.assert_array_equal(np.array([r for _, r in got]) * 100.0, g[key][:, col])
+            wv, wi = O.topk_exact(b, a, 11)
+            np.testing.assert_array_equal(I, wi)
+    # the adversarial fixture: exact ties, zero / non-unit rows, a NaN query, +-inf rows
+    s = golden("retrieval_small.npz")
+    Q, G = s["queries"], s["gallery"]
+    index = faiss.GpuIndexFlatL2(faiss.StandardGpuResources(), 64, cfg)
+    index.add(G[:100])
+    index.add(G[100:])                            # incremental adds concatenate
+    _, I = index.search(Q, 11)
+    got = np.array([r for _, r in _reference_hit_loop(I, list(s["k_vals"]), G.shape[0])])
+    np.testing.assert_array_equal(got, s["recall_q_from_g"])
+    ok = ~np.isnan(Q).any(1)
+    np.testing.assert_array_equal(I[ok], O.topk_exact(Q, G, 11)[1][ok])
+    # device tensors in -> device tensors out; the bf16 mode is exact on the rounded rows; k > ntotal
+    cfg16 = faiss.GpuIndexFlatConfig()
+    cfg16.useFloat16 = True
+    T, V = make_retrieval_pair(300, 2000, 256, sigma=3.0, seed=5)
+    index = faiss.GpuIndexFlatL2(None, 256, cfg16)
+    index.add(V.to(cuda_dev))
+    D, I = index.search(T.to(cuda_dev), 10)
+    assert I.is_cuda
+    np.testing.assert_array_equal(_np(I), O.topk_exact(O.bf16_round(T), O.bf16_round(V), 10)[1])
+    index.reset()
+    assert index.ntotal == 0
+    index.add(V[:4].numpy())
+    D, I = index.search(T[:3].numpy(), 6)
+    assert (I[:, 4:] == -1).all() and np.isinf(D[:, 4:]).all() and (I[:, :4] >= 0).all()
+    with pytest.raises(ValueError):
+        index.search(T[:3].numpy(), 17)
+
+
 def test_eval_consumer_six_keys(cuda_dev, tmp_path):
     """evaluation/eval.py:97-138: a loader of (vis, title, comments, meta) batches through a model,
     features kept on the device, six floats keyed R{k}_{title_from_im,im_from_title}."""

@@ -264,3 +264,22 @@ def test_metric_tracker_and_loss_metric_follow_the_trainer_protocol():
     assert w.scalars == [("loss", 2.0), ("loss", 4.0), ("loss", 6.0)]
     tr.reset()
     assert loss_metric.avg() == 0 and rec.insert_index == 0
+
+
+def test_faiss_compat_surface_and_no_cpu_fallback():
+    """vtc_b200.faiss_compat exposes the three names model/metric.py:112-113,139-146 uses; without a
+    CUDA device the index refuses to exist (no CPU search behind the reference's back)."""
+    from vtc_b200 import faiss_compat as faiss
+    from vtc_b200._ffi import VtcError
+
+    cfg = faiss.GpuIndexFlatConfig()
+    assert cfg.useFloat16 is False and cfg.device == 0
+    cfg.useFloat16, cfg.device = False, None          # what RecallAtK.update leaves for CPU tensors
+    faiss.StandardGpuResources()
+    for name in ("add", "search", "reset", "ntotal"):
+        assert hasattr(faiss.GpuIndexFlatL2, name)
+    if not torch.cuda.is_available():
+        with pytest.raises(VtcError):
+            faiss.GpuIndexFlatL2(faiss.StandardGpuResources(), 512, cfg)
+    with pytest.raises(ValueError):
+        faiss.GpuIndexFlatL2(None, 0, cfg)

@@ -349,3 +349,39 @@ def test_committed_goldens_are_reproduced_by_the_generator(tmp_path, monkeypatch
                 np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-7, err_msg=f"{name}:{key}")
             else:
                 np.testing.assert_array_equal(a, b, err_msg=f"{name}:{key}")
+
+
+def test_reference_metric_module_runs_unmodified_on_the_faiss_compat_binding(monkeypatch):
+    """The other way to switch (vtc_b200/faiss_compat.py): the reference's model/metric.py, byte for
+    byte, with its `import faiss` bound to the B200 library.  It imports, RecallAtK constructs and
+    accumulates exactly as before (:103-135), and compute() reaches GpuIndexFlatL2 -- which, in this
+    container without a GPU, must fail loudly instead of falling back to a CPU search."""
+    import collections
+    import importlib.util
+    import os
+    import sys
+
+    from vtc_b200 import faiss_compat
+    from vtc_b200._ffi import VtcError
+
+    RS.install()   # (collections.Iterable for model/metric.py:106)
+    assert hasattr(collections, "Iterable")
+    monkeypatch.setitem(sys.modules, "faiss", faiss_compat)
+    spec = importlib.util.spec_from_file_location(
+        "reference_metric_on_vtc_b200", os.path.join(RS.REFERENCE_ROOT, "model", "metric.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.faiss is faiss_compat
+    m = mod.RecallAtK("videos", "titles", [1, 5, 10])
+    assert isinstance(m.knn_config, faiss_compat.GpuIndexFlatConfig) and m.knn_config.useFloat16 is False
+    T, V = make_retrieval_pair(64, 64, 32, sigma=2.0, seed=4)
+    m.update(None, (V[:40], T[:40]), {})
+    m.update(None, (V[40:], T[40:]), {})
+    assert m.insert_index == 64 and m.knn_config.device is None   # CPU tensors: fa.device.index
+    if not torch.cuda.is_available():
+        with pytest.raises(VtcError):
+            m.compute(V.numpy(), T.numpy())
+    else:
+        got = m.compute(V.numpy(), T.numpy())
+        want = O.recall_at_k(V.numpy(), T.numpy(), [1, 5, 10])
+        assert [(int(k), float(r)) for k, r in got] == [(int(k), float(r)) for k, r in want]
