@@ -108,7 +108,7 @@ __device__ __forceinline__ void zero_pad_columns(__nv_bfloat16* op, int Kp, int 
 
 template <typename T>
 __global__ void __launch_bounds__(PR_THREADS)
-rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
+rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light, int paired) {
   __shared__ __align__(16) float tile_a[PR_ROWS * PR_LD];  // gallery rows / query rows
   __shared__ __align__(16) float tile_b[PR_ROWS * PR_LD];  // ground-truth gallery rows of the queries
   __shared__ int64_t srow_a[PR_ROWS], srow_b[PR_ROWS];
@@ -248,9 +248,15 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
   const bool need_qq = a.qq_in == nullptr && a.qq != nullptr;
   const bool emit = a.mode_q != STAGE_NONE;
   const bool pieces = emit && a.mode_q != PREP_PLAIN && a.qsplit != nullptr;
-  float s_lo[PR_Q], s_e[PR_Q];
+  // paired rows (gt(t) = t over the whole gallery, norms not given): the ground-truth row of query t
+  // IS gallery row t, which this block stages anyway -- it also emits that row's operand and takes
+  // its canonical norm (the sqx chain below is the gallery walker's chain, same order), so the
+  // gallery is read once instead of twice and there are no gallery blocks at all
+  const bool emit_g = paired != 0 && a.mode_g != STAGE_NONE;
+  const bool pieces_g = emit_g && a.mode_g != PREP_PLAIN && a.split_max_bits != nullptr;
+  float s_lo[PR_Q], s_e[PR_Q], g_lo[PR_Q], g_e[PR_Q];
 #pragma unroll
-  for (int i = 0; i < PR_Q; ++i) s_lo[i] = s_e[i] = 0.f;
+  for (int i = 0; i < PR_Q; ++i) s_lo[i] = s_e[i] = g_lo[i] = g_e[i] = 0.f;
   if (tid < PR_ROWS) {
     const int64_t t = t0 + tid;
     srow_a[tid] = t < a.N ? t : -1;
@@ -296,6 +302,9 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
         if (emit && qp[i])
           emit_quad(a.opQ + srow_a[row] * (int64_t)a.Kp, k0 + kq, a.D, a.mode_q, v[i], a.fallback,
                     pieces ? &s_lo[i] : nullptr, pieces ? &s_e[i] : nullptr);
+        if (emit_g && gp[i])
+          emit_quad(a.opG + srow_b[row] * (int64_t)a.Kp, k0 + kq, a.D, a.mode_g, w[i], a.fallback,
+                    pieces_g ? &g_lo[i] : nullptr, pieces_g ? &g_e[i] : nullptr);
       }
       __syncthreads();
       if (c + 1 < nchunks) {
@@ -330,6 +339,7 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
       }
     }
     if (emit) zero_pad_columns(a.opQ, a.Kp, a.mode_q == PREP_PLAIN ? a.D : 3 * a.D, srow_a);
+    if (emit_g) zero_pad_columns(a.opG, a.Kp, a.mode_g == PREP_PLAIN ? a.D : 3 * a.D, srow_b);
     if (pieces) {
 #pragma unroll
       for (int i = 0; i < PR_Q; ++i) {
@@ -355,13 +365,55 @@ rank_prologue_kernel(const RankPrologueArgs a, int g_blocks, int g_light) {
     // the guard band only needs an UPPER bound of ||q||^2: round up, one part in 10^6 of slack
     if (need_qq) a.qq[t] = __double2float_ru(qq * (1.0 + 1.0e-6));
   }
+  if (paired) {
+    // the gallery side of these rows: canonical norm, epilogue bias (the last block also pads it
+    // with +inf up to Mpad), and the block's maxima -- as the gallery blocks do it
+    float m_sq = 0.f, m_lo = 0.f, m_e = 0.f;
+    if (tid < PR_ROWS && srow_b[tid] >= 0) {
+      const int64_t j = srow_b[tid];
+      if (a.sq64) a.sq64[j] = sqx;
+      const float f = (float)sqx;
+      if (a.bias) a.bias[j] = a.metric == VTC_METRIC_L2 ? f : 0.f;
+      if (f == f && f < 3.0e38f) m_sq = f;
+    }
+    if (a.bias && t0 + PR_ROWS >= a.M)
+      for (int64_t j = a.M + tid; j < a.Mpad; j += PR_THREADS) a.bias[j] = INFINITY;
+    if (pieces_g) {
+#pragma unroll
+      for (int i = 0; i < PR_Q; ++i) {
+        float l = g_lo[i], e = g_e[i];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          l += __shfl_xor_sync(0xffffffffu, l, o);
+          e += __shfl_xor_sync(0xffffffffu, e, o);
+        }
+        l = piece_up(l), e = piece_up(e);
+        if (l < 3.0e38f) m_lo = fmaxf(m_lo, l);
+        if (e < 3.0e38f) m_e = fmaxf(m_e, e);
+      }
+    }
+    m_sq = warp_max(m_sq), m_lo = warp_max(m_lo), m_e = warp_max(m_e);
+    if (lane == 0) blk_max[warp][0] = m_sq, blk_max[warp][1] = m_lo, blk_max[warp][2] = m_e;
+    __syncthreads();
+    if (tid < 3) {
+      float m = 0.f;
+      for (int w = 0; w < PR_THREADS / 32; ++w) m = fmaxf(m, blk_max[w][tid]);
+      unsigned int* dst = tid == 0 ? a.max_sq_bits : (pieces_g ? a.split_max_bits + (tid - 1) : nullptr);
+      if (dst && m > 0.f) atomicMax(dst, __float_as_uint(m));
+    }
+  }
 }
 
 int launch_rank_prologue(const RankPrologueArgs& a, cudaStream_t s) {
   if (a.N <= 0 && a.M <= 0) return VTC_OK;
   const bool g_work = a.sq64_in == nullptr || a.mode_g != STAGE_NONE;
   const int g_light = g_work ? 0 : 1;
-  const int64_t g_blocks = a.Mpad > 0 ? ceil_div<int64_t>(a.Mpad, g_light ? PR_LIGHT_ROWS : PR_ROWS) : 0;
+  // paired rows: every query's ground truth is the gallery row of the same index and that covers
+  // the whole gallery (one evaluation, gt(t) = t): the query blocks do the gallery side as well
+  const int paired = (a.sq64_in == nullptr && a.gt_in == nullptr && a.dgt != nullptr &&
+                      a.gt == nullptr && a.row_offset == a.col_offset && a.N == a.M && a.N > 0 &&
+                      a.sq64 != nullptr && a.bias != nullptr && a.max_sq_bits != nullptr) ? 1 : 0;
+  const int64_t g_blocks = (paired || a.Mpad <= 0) ? 0 : ceil_div<int64_t>(a.Mpad, g_light ? PR_LIGHT_ROWS : PR_ROWS);
   const bool q_work = (a.gt_in == nullptr && a.dgt != nullptr) ||
                       (a.qq_in == nullptr && a.qq != nullptr) || a.mode_q != STAGE_NONE;
   const int64_t q_blocks = q_work ? ceil_div<int64_t>(a.N, PR_ROWS) : 0;
@@ -370,10 +422,10 @@ int launch_rank_prologue(const RankPrologueArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)(g_blocks + q_blocks);
   if (a.in_bf16)
     launch_pdl(rank_prologue_kernel<__nv_bfloat16>, dim3(grid), dim3(PR_THREADS), 0, s, a,
-               (int)g_blocks, g_light);
+               (int)g_blocks, g_light, paired);
   else
     launch_pdl(rank_prologue_kernel<float>, dim3(grid), dim3(PR_THREADS), 0, s, a, (int)g_blocks,
-               g_light);
+               g_light, paired);
   VTC_LAUNCH_CHECK();
   return VTC_OK;
 }
