@@ -122,14 +122,13 @@ __device__ __forceinline__ bool rows_vectorisable(const T* base, int64_t ld) {
 // arithmetic (round 2a re-decided all 8 columns of a group: 4.5x the L2 traffic for typically one
 // in-band column).
 //
-// One warp decides FOUR groups at a time, a lane per column: the 4 x (query row + 8 gallery rows) are
-// staged 32 columns at a time in a warp-private shared-memory tile by the whole warp (128-bit loads,
-// 8 lanes per row segment, the next chunk already in flight), and every lane walks one column's fp64
-// chain in k order.  A thread walking two rows on its own (round 1) is a chain of D/16 dependent L2
-// round trips (~20 us at D = 512); here the chain itself (D dependent DFMAs, ~3 us) is what is left,
-// with all 32 lanes busy -- this sits on the critical path of every chunked call.
+// A warp stages the rows of a step 32 columns at a time in a warp-private shared-memory tile (128-bit
+// loads, 8 lanes per row segment, the next chunk already in flight) and its lanes walk one fp64 chain
+// each in k order.  A thread walking two rows on its own (round 1) is a chain of D/16 dependent L2
+// round trips (~20 us at D = 512); here the chain itself (D dependent DFMAs, ~3 us) is what is left
+// -- this sits on the critical path of every chunked call.
 constexpr int RECHECK_GROUP = 8;
-constexpr int RC_GROUPS = 4;                       // groups per warp and step
+constexpr int RC_GROUPS = 4;                       // (sizes the staging tile: 36 rows)
 constexpr int RC_KC = 32;                          // staged columns per step
 constexpr int RC_LD = RC_KC + 4;                   // floats per staged row: 16-byte aligned rows, and
                                                    // 8 consecutive rows cover all 32 banks (LDS.128)
@@ -137,88 +136,120 @@ constexpr int RC_GROUP_ROWS = RECHECK_GROUP + 1;   // the query row + the group'
 constexpr int RC_ROWS = RC_GROUPS * RC_GROUP_ROWS; // 36
 constexpr int RC_WARP_FLOATS = RC_ROWS * RC_LD;       // 1296 floats
 
-// `e`: the packed entry of this lane's group (lanes 8g .. 8g+7 hold group g), if `has`.
+// SIXTEEN (row, column) pairs at a time.  A listed group typically has ONE in-band column, so with a
+// lane per column of four groups (the earlier round-2 layout) ~5 of the 32 chains of a step were
+// real.  Here a warp takes up to 32 list entries (a lane each), expands their masks into (t, j) pairs
+// without a buffer -- pair p of the batch is the (p - off[b])-th set lane of ballot b, bits first --
+// and decides 16 pairs per step: 16 query rows + 16 gallery rows staged 32 columns at a time by the
+// whole warp exactly as above, lanes 0..15 walk one pair's fp64 chain each.  3x fewer steps for the
+// same list (100k x 100k: 141 -> 67 us bf16, 322 -> 81 us exact).
+constexpr int RP_PAIRS = 16;
+static_assert(2 * RP_PAIRS * RC_LD <= RC_WARP_FLOATS, "the staging tile serves the pair variant");
+
 template <typename T>
-__device__ __forceinline__ void recheck_groups_warp(
+__device__ __forceinline__ void recheck_pairs_warp(
     float* __restrict__ st, int2 e, bool has, const T* __restrict__ Q, int64_t ldq, const T* __restrict__ G,
     int64_t ldg, const double* __restrict__ sq64, const double* __restrict__ dgt, int64_t N,
     int64_t M, int D, const int64_t* __restrict__ gt, int64_t row_offset, int64_t col_offset,
     int metric, int* __restrict__ rank) {
   const int lane = threadIdx.x & 31;
-  unsigned int cmask = 0;  // the group's columns that need the canonical decision
+  unsigned int cmask = 0;
+  int t_ = -1, j_ = 0;
   if (has) {
-    int t_, j_;
     tc::amb_unpack(e, &t_, &j_, &cmask);
-    e = make_int2(t_, j_);
-  } else {
-    e = make_int2(-1, 0);
+    if (t_ >= N || j_ >= M) cmask = 0;  // zero-padded tile rows / columns
+    if (cmask) {
+      const int64_t room = M - (int64_t)j_;  // columns of the group inside this gallery chunk
+      if (room < RECHECK_GROUP) cmask &= (1u << room) - 1u;
+      const int64_t g = (gt ? gt[t_] : (int64_t)t_ + row_offset) - col_offset - (int64_t)j_;
+      if (g >= 0 && g < RECHECK_GROUP) cmask &= ~(1u << g);  // the ground truth is no competitor
+    }
   }
-  if (e.x >= N || e.y >= M) e.x = -1;  // zero-padded tile rows / columns
-  if (e.x < 0) cmask = 0;
+  unsigned int bal[RECHECK_GROUP];
+  int off[RECHECK_GROUP + 1];
+  off[0] = 0;
+#pragma unroll
+  for (int b = 0; b < RECHECK_GROUP; ++b) {
+    bal[b] = __ballot_sync(0xffffffffu, (cmask >> b) & 1u);
+    off[b + 1] = off[b] + __popc(bal[b]);
+  }
+  const int total = off[RECHECK_GROUP];
   const bool vq = rows_vectorisable(Q, ldq), vg = rows_vectorisable(G, ldg);
-  // loader view: lane owns column quad (lane % 8) of staged rows 4 i + lane / 8, i = 0..8;
-  // gallery rows outside the mask are not loaded at all (their chains run on zeros, unused)
-  const T* src[RC_GROUP_ROWS];
-  bool is_q[RC_GROUP_ROWS];
-#pragma unroll
-  for (int i = 0; i < RC_GROUP_ROWS; ++i) {
-    const int row = 4 * i + (lane >> 3);
-    const int g = row / RC_GROUP_ROWS, rr = row % RC_GROUP_ROWS;
-    const int t = __shfl_sync(0xffffffffu, e.x, 8 * g);
-    const int j0 = __shfl_sync(0xffffffffu, e.y, 8 * g);
-    const unsigned int gm = __shfl_sync(0xffffffffu, cmask, 8 * g);
-    is_q[i] = rr == 0;
-    src[i] = nullptr;
-    if (t >= 0 && gm != 0) {
-      if (rr == 0)
-        src[i] = Q + (int64_t)t * ldq;
-      else if (((gm >> (rr - 1)) & 1u) && (int64_t)j0 + rr - 1 < M)
-        src[i] = G + ((int64_t)j0 + rr - 1) * ldg;
-    }
-  }
   const int kq = 4 * (lane & 7);
-  float v[RC_GROUP_ROWS][4];
+  for (int base = 0; base < total; base += RP_PAIRS) {
+    // lanes 0..15: pair base + lane -> (source lane, bit)
+    int pt = -1, pj = 0;
+    {
+      const int p = base + (lane & (RP_PAIRS - 1));
+      int b = 0, srcl = 0;
+      if (p < total) {
 #pragma unroll
-  for (int i = 0; i < RC_GROUP_ROWS; ++i) load_quad(src[i], kq, D, is_q[i] ? vq : vg, v[i]);
-  // walker view: lane = column (lane % 8) of group (lane / 8)
-  const float* qs = st + (lane >> 3) * RC_GROUP_ROWS * RC_LD;
-  const float* xs = qs + (1 + (lane & 7)) * RC_LD;
-  double acc = 0.0;
-  for (int k0 = 0; k0 < D; k0 += RC_KC) {
-    __syncwarp();  // the walkers have finished the previous chunk
+        for (int bb = 1; bb < RECHECK_GROUP; ++bb)
+          if (p >= off[bb]) b = bb;
+        unsigned int bm = bal[0];
+        int ob = off[0];
 #pragma unroll
-    for (int i = 0; i < RC_GROUP_ROWS; ++i)
-      *reinterpret_cast<float4*>(st + (4 * i + (lane >> 3)) * RC_LD + kq) =
-          make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
-    __syncwarp();
-    if (k0 + RC_KC < D) {
-#pragma unroll
-      for (int i = 0; i < RC_GROUP_ROWS; ++i)
-        load_quad(src[i], k0 + RC_KC + kq, D, is_q[i] ? vq : vg, v[i]);
+        for (int bb = 1; bb < RECHECK_GROUP; ++bb)
+          if (b == bb) bm = bal[bb], ob = off[bb];
+        srcl = __fns(bm, 0, p - ob + 1);
+      }
+      const int st_ = __shfl_sync(0xffffffffu, t_, srcl);
+      const int sj_ = __shfl_sync(0xffffffffu, j_, srcl);
+      if (p < total) pt = st_, pj = sj_ + b;
     }
-    const int kn = min(RC_KC, D - k0);
-    int k = 0;
-    for (; k + 4 <= kn; k += 4) {
-      const float4 q4 = *reinterpret_cast<const float4*>(qs + k);
-      const float4 x4 = *reinterpret_cast<const float4*>(xs + k);
-      acc = fma((double)q4.x, (double)x4.x, acc);
-      acc = fma((double)q4.y, (double)x4.y, acc);
-      acc = fma((double)q4.z, (double)x4.z, acc);
-      acc = fma((double)q4.w, (double)x4.w, acc);
+    // loader view: lane owns column quad (lane % 8) of staged rows lane / 8 + 4 i, i = 0..7;
+    // rows 0..15 = the pairs' query rows, rows 16..31 = their gallery rows
+    const T* src[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = (lane >> 3) + 4 * i;
+      const int pr = row & (RP_PAIRS - 1);
+      const int tt = __shfl_sync(0xffffffffu, pt, pr);
+      const int jj = __shfl_sync(0xffffffffu, pj, pr);
+      src[i] = tt < 0 ? (const T*)nullptr
+                      : (row < RP_PAIRS ? Q + (int64_t)tt * ldq : G + (int64_t)jj * ldg);
     }
-    for (; k < kn; ++k) acc = fma((double)qs[k], (double)xs[k], acc);
-  }
-  if (e.x >= 0 && ((cmask >> (lane & 7)) & 1u)) {
-    const int64_t t = e.x, jl = (int64_t)e.y + (lane & 7);
-    if (jl < M) {
-      const int64_t g = gt ? gt[t] : t + row_offset;
-      const int64_t jg = jl + col_offset;
-      if (jg != g) {
-        const double d = metric == VTC_METRIC_L2 ? sq64[jl] - 2.0 * acc : -acc;
-        const double d0 = dgt[t];
-        if ((d < d0) || (d == d0 && jg < g)) atomicAdd(&rank[t], 1);
+    float v[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) load_quad(src[i], kq, D, (i < 4) ? vq : vg, v[i]);
+    // walker view: lane p < 16 walks pair p
+    const float* qs = st + (lane & (RP_PAIRS - 1)) * RC_LD;
+    const float* xs = qs + RP_PAIRS * RC_LD;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < D; k0 += RC_KC) {
+      __syncwarp();  // the walkers have finished the previous chunk
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(st + ((lane >> 3) + 4 * i) * RC_LD + kq) =
+            make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+      __syncwarp();
+      if (k0 + RC_KC < D) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) load_quad(src[i], k0 + RC_KC + kq, D, (i < 4) ? vq : vg, v[i]);
+      }
+      if (lane < RP_PAIRS) {
+        const int kn = min(RC_KC, D - k0);
+        int k = 0;
+        for (; k + 4 <= kn; k += 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(qs + k);
+          const float4 x4 = *reinterpret_cast<const float4*>(xs + k);
+          acc = fma((double)q4.x, (double)x4.x, acc);
+          acc = fma((double)q4.y, (double)x4.y, acc);
+          acc = fma((double)q4.z, (double)x4.z, acc);
+          acc = fma((double)q4.w, (double)x4.w, acc);
+        }
+        for (; k < kn; ++k) acc = fma((double)qs[k], (double)xs[k], acc);
       }
     }
+    if (lane < RP_PAIRS && pt >= 0) {
+      const int64_t t = pt, jl = pj;
+      const int64_t g = gt ? gt[t] : t + row_offset;
+      const int64_t jg = jl + col_offset;
+      const double d = metric == VTC_METRIC_L2 ? sq64[jl] - 2.0 * acc : -acc;
+      const double d0 = dgt[t];
+      if ((d < d0) || (d == d0 && jg < g)) atomicAdd(&rank[t], 1);
+    }
+    __syncwarp();
   }
 }
 
@@ -313,19 +344,24 @@ __device__ __forceinline__ void recheck_all(
       continue;  // the brute-force fallback recomputes everything
     }
     const int2* seg_list = list + (size_t)seg * seg_cap;
-    if (n < 2u * RC_GROUPS * step) {
-      // a few groups per warp at most: the variant with the shorter critical path
+    const unsigned int per_warp = (n + step - 1u) / step;  // entries per warp of this segment
+    if (per_warp <= 2u) {
+      // a couple of groups per warp at most: the variant with the shorter critical path
       for (unsigned int u = first; u < n; u += step) {
         recheck_group_warp<T>(st, seg_list[u], Q, ldq, G, ldg, sq64, dgt, N, M, D, gt, row_offset,
                               col_offset, metric, rank);
       }
       continue;
     }
-    for (unsigned int u = first * RC_GROUPS; u < n; u += step * RC_GROUPS) {
-      const unsigned int mine = u + (lane >> 3);
-      const int2 e = mine < n ? seg_list[mine] : make_int2(0, 0);
-      recheck_groups_warp<T>(st, e, mine < n, Q, ldq, G, ldg, sq64, dgt, N, M, D, gt, row_offset, col_offset,
-                             metric, rank);
+    // batches of up to 32 consecutive entries per warp, sized so that every warp of the segment
+    // gets work; each batch is decided 16 (row, column) pairs at a time
+    const unsigned int batch = per_warp < 32u ? per_warp : 32u;
+    for (unsigned int u = first * batch; u < n; u += step * batch) {
+      const unsigned int mine = u + (unsigned int)lane;
+      const bool has = (unsigned int)lane < batch && mine < n;
+      const int2 e = has ? seg_list[mine] : make_int2(0, 0);
+      recheck_pairs_warp<T>(st, e, has, Q, ldq, G, ldg, sq64, dgt, N, M, D, gt, row_offset, col_offset,
+                            metric, rank);
     }
   }
 }
