@@ -28,6 +28,12 @@ for prec in ("exact", "bf16"):
     full = ops.rank_eval(q[:300], g[:300], [1, 5, 10], precision=prec)
     Tq, Vq = (O.bf16_round(T), O.bf16_round(V)) if prec == "bf16" else (T, V)
     assert np.array_equal(full["rank0"].cpu().numpy(), O.rank0_exact(Tq, Vq[:300])), prec
+# every pair ties -> every 8-column group is listed with a full mask: the 16-pairs-per-step re-check
+row = torch.randn(1, 64)
+Qd, Gd = row.repeat(200, 1).contiguous(), row.repeat(304, 1).contiguous()
+for prec in ("exact", "bf16"):
+    r, _ = ops.sim_rank(Qd.to(dev), Gd.to(dev), precision=prec)
+    assert np.array_equal(r.cpu().numpy(), np.arange(200)), prec
 # a gallery long enough for the top-k sample pass (dense scores + per-row threshold kernel)
 T2, V2 = make_retrieval_pair(200, 33000, 64, sigma=2.0, seed=4)
 v, i = ops.sim_topk(T2.to(dev), V2.to(dev), 11, precision="bf16")
