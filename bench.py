@@ -522,16 +522,43 @@ def measure_e2e(cx: Ctx, T, V, qs, qe, gs, ge, n, m, d, precision, steps, graphe
     cx.barrier()
     dt = cx.max_over_ranks((time.perf_counter() - t0) / n_e2e)
     hits = None
+    bf16_host = None
     if pipe is not None:
         hits = [int(x) for x in last["hits"].tolist()]
         pipe.close()
+        if precision == "bf16":
+            # the same stream from pinned bf16 host shards (a caller that keeps bf16 embeddings: the
+            # mode ranks the bf16 roundings anyway): half the bytes through the host's memory.  An
+            # extra record; `e2e` stays fp32 input.
+            try:
+                Tq16, Vg16 = Tq.to(torch.bfloat16).pin_memory(), Vg.to(torch.bfloat16).pin_memory()
+                pipe16 = PipelinedRankEval(graphed.q.to(torch.bfloat16), graphed.g.to(torch.bfloat16),
+                                           n, m, K_VALS, "l2", precision)
+                for _ in range(3):
+                    pipe16.submit(Tq16, Vg16)
+                pipe16.flush()
+                cx.barrier()
+                t0 = time.perf_counter()
+                for _ in range(n_e2e):
+                    pipe16.submit(Tq16, Vg16)
+                last16 = pipe16.flush()
+                cx.barrier()
+                dt16 = cx.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+                pipe16.close()
+                bf16_host = {"value": pairs / dt16, "unit": UNIT, "ms_per_step": dt16 * 1e3,
+                             "h2d_bytes_per_step": int(n * d * 2 + m * d * 2),
+                             "same_hits_as_fp32_input": [int(x) for x in last16["hits"].tolist()] == hits,
+                             "api": "PipelinedRankEval.submit(pinned bf16 host shards)"}
+            except Exception as exc:  # noqa: BLE001  (an extra record: never fail the bench line on it)
+                bf16_host = {"error": repr(exc)[:200]}
     return {"value": pairs / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * d * 4 + m * d * 4),
             "d2h_bytes_per_step": 8 * len(K_VALS) * cx.world, "ms_per_step": dt * 1e3,
             "hits": hits,
             "api": ("vtc_b200.parallel.PipelinedRankEval.submit(pinned fp32 host shards): two captured "
                     "steps alternate, the copies of evaluation k+1 overlap the ranking of evaluation k"
                     if pipe is not None
-                    else "vtc_b200.parallel.sharded_rank_eval(pinned fp32 host shards)")}
+                    else "vtc_b200.parallel.sharded_rank_eval(pinned fp32 host shards)"),
+            **({"bf16_host": bf16_host} if bf16_host is not None else {})}
 
 
 def parity_check(cx: Ctx, q_local, g_full, qs, ranks_by_mode, rows=256):
