@@ -115,7 +115,8 @@ struct RankWs {
   float *sq32, *qq;
   float2* qsplit;  // exact mode: norms of the split pieces of the query rows
   unsigned int* scalars;  // [0] max_sq_bits, [2] fallback flag, [64..] per-CTA list segment counts
-  int* rank_tmp;          // directly behind `scalars`: one memset clears both
+  int* rank_tmp;          // directly behind `scalars`, rank_alt behind it: one memset clears all three
+  int* rank_alt;          // counts of the canonical recount (fallback)
   unsigned int* hist;     // scratch of the fused finalisation (vtc_rank_eval)
   int2* amb;
   size_t amb_cap;
@@ -133,6 +134,7 @@ RankWs carve_rank(Workspace& ws, int64_t N, int64_t M, int D, int dtype, int pre
   memset(&r, 0, sizeof(r));
   r.scalars = ws.take<unsigned int>(kRankScalars);  // 1280 bytes: a whole number of 256-byte granules
   r.rank_tmp = ws.take<int>(N);
+  r.rank_alt = ws.take<int>(N);
   r.sq64 = ws.take<double>(M);
   r.dgt = ws.take<double>(N);
   r.hist = ws.take<unsigned int>(rank_epilogue_hist_words());
@@ -202,10 +204,11 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   if (N > kMaxRows || M > kMaxRows || D > 8192) return VTC_ERR_UNSUPPORTED_SHAPE;
   Workspace ws(wsp, ws_bytes);
   RankWs w = carve_rank(ws, N, M, D, dtype, precision, false);
-  if (!ws.ok() || !w.sq64 || !w.dgt || !w.scalars || !w.rank_tmp || !w.hist) return VTC_ERR_WORKSPACE;
+  if (!ws.ok() || !w.sq64 || !w.dgt || !w.scalars || !w.rank_tmp || !w.rank_alt || !w.hist)
+    return VTC_ERR_WORKSPACE;
   const bool in_bf16 = dtype == VTC_BF16;
   cudaError_t e = cudaMemsetAsync(
-      w.scalars, 0, kRankScalars * sizeof(unsigned int) + round_up<size_t>(sizeof(int) * N, 256), s);
+      w.scalars, 0, kRankScalars * sizeof(unsigned int) + 2 * round_up<size_t>(sizeof(int) * N, 256), s);
   if (e != cudaSuccess) return cuda_err(e);
 
   if (precision == VTC_PREC_BRUTE || M == 0) {
@@ -294,8 +297,8 @@ int sim_rank_impl(const void* Q, const void* G, int64_t N, int64_t M, int D, int
   RankEpilogueArgs ea;
   memset(&ea, 0, sizeof(ea));
   ea.ex = ex, ea.amb_list = w.amb, ea.seg_count = &w.scalars[64], ea.nseg = pl.grid;
-  ea.seg_cap = p.amb_seg_cap, ea.dgt = dgt, ea.rank_tmp = w.rank_tmp, ea.fallback = &w.scalars[2];
-  ea.ticket = &w.scalars[6];
+  ea.seg_cap = p.amb_seg_cap, ea.dgt = dgt, ea.rank_tmp = w.rank_tmp, ea.rank_alt = w.rank_alt;
+  ea.fallback = &w.scalars[2];
   ea.rank0 = rank0, ea.accumulate = accumulate;
   if (fin) {
     ea.finalize = 1, ea.M_total = fin->M_total, ea.nk = fin->nk;

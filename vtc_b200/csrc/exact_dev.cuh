@@ -331,7 +331,7 @@ __device__ __forceinline__ void recheck_all(
     const T* __restrict__ Q, int64_t ldq, const T* __restrict__ G, int64_t ldg,
     const double* __restrict__ sq64, const double* __restrict__ dgt, int64_t N, int64_t M, int D,
     const int64_t* __restrict__ gt, int64_t row_offset, int64_t col_offset, int metric,
-    int* __restrict__ rank, unsigned int* __restrict__ overflow) {
+    int* __restrict__ rank) {
   if (nseg <= 0) return;
   const int lane = threadIdx.x & 31;
   const bool shared_segs = num_warps >= nseg;
@@ -339,10 +339,8 @@ __device__ __forceinline__ void recheck_all(
     const unsigned int first = shared_segs ? (unsigned int)(gw / nseg) : 0u;
     const unsigned int step = shared_segs ? (unsigned int)((num_warps - seg + nseg - 1) / nseg) : 1u;
     const unsigned int n = seg_count[seg];
-    if (n > seg_cap) {
-      if (first == 0 && lane == 0) *overflow = 1u;
-      continue;  // the brute-force fallback recomputes everything
-    }
+    if (n > seg_cap) continue;  // (an overflowed segment routes the whole call to the canonical
+                                // recount before any re-check starts: rank_needs_fallback)
     const int2* seg_list = list + (size_t)seg * seg_cap;
     const unsigned int per_warp = (n + step - 1u) / step;  // entries per warp of this segment
     if (per_warp <= 2u) {

@@ -15,9 +15,9 @@
 //   walked 32 rows per block with one warp: 2.8x off the HBM bound).  HBM-bound:
 //   rows * D * sizeof(in) read + rows * K' * 2 written.
 //
-// rank_epilogue_kernel (+ rank_fallback_kernel, device-gated) -- see "epilogue" below:
-//   re-check of the guard-band groups -> [flag: zero + brute-force] -> commit into rank0 ->
-//   [NaN ground truth -> M, R@K hit counts, median rank by radix select].
+// the epilogue chain -- see "epilogue" below:
+//   re-check of the guard-band groups (or, rarely, the canonical recount of the whole call) -> commit
+//   into rank0 -> [NaN ground truth -> M, R@K hit counts, median rank by radix select].
 #include "rank_stage.cuh"
 
 #include "exact_dev.cuh"
@@ -435,12 +435,15 @@ int launch_rank_prologue(const RankPrologueArgs& a, cudaStream_t s) {
 // launch with grid-wide barriers; a kernel boundary under PDL is cheaper than a grid barrier plus the
 // cooperative launch, and every stage gets the grid size that suits it):
 //   rank_recheck_kernel   zero the finalisation scratch; every warp re-checks its share of the
-//                         guard-band groups in canonical arithmetic
-//   rank_fallback_kernel  gated on the device-side flag (list overflow, or split operands that could
-//                         not carry inf / NaN): exits at once in the normal case, otherwise the whole
-//                         grid recounts in canonical arithmetic
-//   rank_commit_kernel    rank0 = (accumulate ? rank0 : 0) + counts; with `finalize`: NaN ground truth
-//                         -> M_total, R@K hit counts, histogram of the first radix digit
+//                         guard-band groups in canonical arithmetic.  If the call has to fall back
+//                         (a list segment overflowed, or split operands could not carry inf / NaN --
+//                         every block of the chain decides that on its own from the list counts and
+//                         the prologue's flag, rank_needs_fallback) the grid recounts the whole call
+//                         in canonical arithmetic into a spare count array instead; until the last
+//                         session of round 2 that was a launch of its own that exited at once
+//   rank_commit_kernel    rank0 = (accumulate ? rank0 : 0) + counts (the spare array after a
+//                         fallback); with `finalize`: NaN ground truth -> M_total, R@K hit counts,
+//                         histogram of the first radix digit
 //   rank_select_kernel    (per further digit) pick the digit(s) of the two middle order statistics,
 //                         histogram of the next digit among the ranks that match; the LAST block of
 //                         the last level writes median(rank0) + 1 (numpy semantics).
@@ -518,11 +521,20 @@ __device__ __forceinline__ unsigned int* hist_ticket(unsigned int* hist, int lev
   return hist + (size_t)MED_LEVELS * 2 * MED_BINS + level;
 }
 
+// Does this call have to be recounted in canonical arithmetic?  Decided identically by every block of
+// every launch of the chain from data that is complete before the chain starts: the prologue's flag
+// (split operands that cannot carry inf / NaN) and the tensor-core pass's per-CTA list counts (a
+// segment that overflowed its capacity).  No launch has to wait for another one's verdict.
+__device__ __forceinline__ bool rank_needs_fallback(const RankEpilogueArgs& a) {
+  int over = __ldcg(a.fallback) != 0u ? 1 : 0;
+  for (int i = threadIdx.x; i < a.nseg; i += blockDim.x) over |= __ldcg(a.seg_count + i) > a.seg_cap ? 1 : 0;
+  return __syncthreads_or(over) != 0;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(EP_THREADS)
 rank_recheck_kernel(const RankEpilogueArgs a) {
   __shared__ EpilogueSmem sm;
-  __shared__ unsigned int sh_flag;
   griddep_launch();
   griddep_wait();
   const int tid = threadIdx.x;
@@ -533,27 +545,20 @@ rank_recheck_kernel(const RankEpilogueArgs a) {
     if (blockIdx.x == 0 && tid < a.nk) a.hits[tid] = 0ull;
   }
   if (!a.rank_tmp) return;  // finalisation only (vtc_rank_finalize): nothing to re-check
+  if (rank_needs_fallback(a)) {
+    // rare (adversarial duplicates overflowing the list, inf / NaN rows in the exact mode): the whole
+    // grid recounts the call in canonical arithmetic into the spare count array, which the commit
+    // launch then takes instead of the tensor-core counts
+    rank_brute_tiles<T>(sm.brute, static_cast<const T*>(a.ex.Q), a.ex.ldq, static_cast<const T*>(a.ex.G),
+                        a.ex.ldg, a.ex.sq64, a.dgt, a.ex.N, a.ex.M, a.ex.D, a.ex.gt, a.ex.row_offset,
+                        a.ex.col_offset, a.ex.metric, a.rank_alt, blockIdx.x, gridDim.x);
+    return;
+  }
   recheck_all<T>(sm.recheck[tid >> 5], (int)blockIdx.x * (EP_THREADS / 32) + (tid >> 5),
                  (int)gridDim.x * (EP_THREADS / 32), a.amb_list, a.seg_count, a.nseg, a.seg_cap,
                  static_cast<const T*>(a.ex.Q), a.ex.ldq, static_cast<const T*>(a.ex.G), a.ex.ldg,
                  a.ex.sq64, a.dgt, a.ex.N, a.ex.M, a.ex.D, a.ex.gt, a.ex.row_offset,
-                 a.ex.col_offset, a.ex.metric, a.rank_tmp, a.fallback);
-  // the fallback kernel recounts everything: the last block hands it zeroed counts
-  if (!last_block_here(a.ticket, &sh_flag)) return;
-  if (__ldcg(a.fallback) != 0u)
-    for (int64_t i = tid; i < a.ex.N; i += EP_THREADS) a.rank_tmp[i] = 0;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(EP_THREADS)
-rank_fallback_kernel(const RankEpilogueArgs a) {
-  __shared__ BruteSmem sm;
-  griddep_launch();
-  griddep_wait();
-  if (__ldcg(a.fallback) == 0u) return;  // the normal case: nothing to do
-  rank_brute_tiles<T>(sm, static_cast<const T*>(a.ex.Q), a.ex.ldq, static_cast<const T*>(a.ex.G),
-                      a.ex.ldg, a.ex.sq64, a.dgt, a.ex.N, a.ex.M, a.ex.D, a.ex.gt, a.ex.row_offset,
-                      a.ex.col_offset, a.ex.metric, a.rank_tmp, blockIdx.x, gridDim.x);
+                 a.ex.col_offset, a.ex.metric, a.rank_tmp);
 }
 
 // the median's radix-select state after the levels before `level`: prefixes (pa, pb) and remaining
@@ -587,10 +592,12 @@ rank_commit_kernel(const RankEpilogueArgs a) {
   const int tid = threadIdx.x;
   const int64_t N = a.ex.N;
   const int64_t i0 = ((int64_t)blockIdx.x * EP_THREADS + tid) * EP_ITEMS;
+  // the counts of this call: the tensor-core pass + re-check, or the canonical recount
+  const int* counts = a.rank_tmp ? (rank_needs_fallback(a) ? a.rank_alt : a.rank_tmp) : nullptr;
   if (!a.finalize) {
 #pragma unroll
     for (int e = 0; e < EP_ITEMS; ++e)
-      if (i0 + e < N) a.rank0[i0 + e] = (a.accumulate ? a.rank0[i0 + e] : 0) + __ldcg(a.rank_tmp + i0 + e);
+      if (i0 + e < N) a.rank0[i0 + e] = (a.accumulate ? a.rank0[i0 + e] : 0) + __ldcg(counts + i0 + e);
     return;
   }
   const bool want_med = a.medr != nullptr;
@@ -604,7 +611,7 @@ rank_commit_kernel(const RankEpilogueArgs a) {
   for (int e = 0; e < EP_ITEMS; ++e) {
     r[e] = -1;
     if (i0 + e < N) {
-      r[e] = (a.accumulate ? a.rank0[i0 + e] : 0) + (a.rank_tmp ? __ldcg(a.rank_tmp + i0 + e) : 0);
+      r[e] = (a.accumulate ? a.rank0[i0 + e] : 0) + (counts ? __ldcg(counts + i0 + e) : 0);
       if (a.dgt) {
         const double d0 = a.dgt[i0 + e];
         if (d0 != d0) r[e] = (int)a.M_total;  // no ground truth: never retrieved
@@ -684,14 +691,10 @@ template <typename T>
 static int launch_rank_epilogue_t(const RankEpilogueArgs& a, cudaStream_t s) {
   const int64_t N = a.ex.N;
   if (a.finalize && !a.hist) return VTC_ERR_WORKSPACE;
-  if (a.rank_tmp && !a.ticket) return VTC_ERR_INVALID_ARG;
+  if (a.rank_tmp && (!a.rank_alt || !a.fallback || !a.seg_count)) return VTC_ERR_INVALID_ARG;
   if (a.rank_tmp || a.finalize) {
     // finalisation only: the scratch is 12 K words -- a handful of blocks zero it
     launch_pdl(rank_recheck_kernel<T>, dim3(a.rank_tmp ? 2 * kNumSMs : 8), dim3(EP_THREADS), 0, s, a);
-    VTC_LAUNCH_CHECK();
-  }
-  if (a.rank_tmp) {
-    launch_pdl(rank_fallback_kernel<T>, dim3(2 * kNumSMs), dim3(EP_THREADS), 0, s, a);
     VTC_LAUNCH_CHECK();
   }
   const unsigned blocks = (unsigned)ceil_div<int64_t>(N, EP_THREADS * EP_ITEMS);

@@ -1,9 +1,10 @@
 // rank_stage.cuh -- the two kernels around the tensor-core pass of vtc_sim_rank / vtc_rank_eval
 // (rank_stage.cu): ONE prologue launch (bf16 operands, canonical norms, ground-truth scores, epilogue
-// bias, guard-band inputs) and the epilogue chain (fp64 re-check of the guard-band groups, device-gated
-// brute-force fallback, commit + R@K hit counts, radix-select median), short launches chained by
-// programmatic dependent launch.  A retrieval evaluation is memset + prologue + tensor-core pass +
-// 5 epilogue launches instead of the 17 launches of round 1.
+// bias, guard-band inputs) and the epilogue chain (fp64 re-check of the guard-band groups -- or, decided
+// up front by every block, the canonical recount of the whole call --, commit + R@K hit counts,
+// radix-select median), short launches chained by programmatic dependent launch.  A retrieval
+// evaluation is memset + prologue + tensor-core pass + 3 epilogue launches instead of the 17 launches
+// of round 1.
 #pragma once
 #include "common.cuh"
 #include "exact.cuh"
@@ -59,8 +60,9 @@ struct RankEpilogueArgs {
   unsigned int seg_cap;
   const double* dgt;
   int* rank_tmp;           // [N] counts of this call (tensor-core pass + re-check)
-  unsigned int* fallback;  // in/out: list overflow or non-finite split operands -> brute force
-  unsigned int* ticket;    // zeroed by the caller: arrival counter of the re-check launch
+  int* rank_alt;           // [N] zeroed by the caller: counts of the canonical recount, taken instead
+                           // of rank_tmp when the call falls back (rank_needs_fallback)
+  const unsigned int* fallback;  // set by the prologue: split operands that cannot carry inf / NaN
   int32_t* rank0;          // [N] result
   int accumulate;
   // optional finalisation (vtc_rank_eval): NaN ground truth -> rank M_total, hits, median
