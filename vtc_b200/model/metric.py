@@ -229,7 +229,7 @@ class RecallAtK(BaseMetric):
         b = _to_device(features_b, device)
         if a.dtype != b.dtype:
             a, b = a.float(), b.float()
-        # one library call: row prologue + tensor-core pass + cooperative epilogue (re-check, hit
+        # one library call: row prologue + tensor-core pass + epilogue chain (re-check, hit
         # counts, median)
         full = ops.rank_eval(b, a, self.k_vals, metric=self.metric, precision=self.precision)
         return {"rank0": full["rank0"], "hits": full["hits"], "medr": full["medr"],
@@ -247,7 +247,7 @@ class RecallAtK(BaseMetric):
     # Chunk pairs when both sides are staged from the host.  Once the last pair has landed, the
     # blocks it enables -- (2 r_last N - r_last^2) of the N^2 pairs for r_last rows -- are all that is
     # left, so the evaluation cannot end before T + that share of the ranking time W: equal chunks
-    # give (2c - 1) / c^2 (c = 6: 0.31 W, c = 12: 0.16 W), and every call is memset + 3 kernels
+    # give (2c - 1) / c^2 (c = 6: 0.31 W, c = 12: 0.16 W), and every call is memset + 4 launches
     # (rank_stage.cu), so a dozen pairs are affordable.
     PIPELINE_CHUNKS_2D = 10
 
