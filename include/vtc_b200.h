@@ -129,8 +129,8 @@ int vtc_sim_rank(const void* Q, const void* G, int64_t N, int64_t M, int D, int 
 /* ---- R1 + R3 in one call: similarity + rank + R@K hit counts + median rank -----------------------
  * The whole of RecallAtK.compute (model/metric.py:137-161) for one (queries, gallery) pair that is
  * resident on the device: vtc_sim_rank over the full gallery followed by vtc_rank_finalize, as
- * memset + row prologue + tensor-core pass + a chain of three short launches (re-check, commit + hit counts, median select).  hits [nk] int64 and
- * medr (fp64, nullable) are device pointers; gt_score_out [N] (nullable) receives d(t,gt).
+ * memset + row prologue + tensor-core pass + a chain of three short launches (re-check, commit +
+ * hit counts, median select).  hits [nk] int64 and medr (fp64, nullable) are device pointers; gt_score_out [N] (nullable) receives d(t,gt).
  * The workspace is that of VTC_OP_SIM_RANK. */
 int vtc_rank_eval(const void* Q, const void* G, int64_t N, int64_t M, int D, int dtype,
                   const int64_t* gt, int metric, int precision, const int* k_vals, int nk,

@@ -285,7 +285,8 @@ def rank_eval(q: torch.Tensor, g: torch.Tensor, k_vals: Sequence[int],
               gt: Optional[torch.Tensor] = None, metric="l2", precision="exact",
               want_medr: bool = True) -> Dict[str, Optional[torch.Tensor]]:
     """The whole of RecallAtK.compute (model/metric.py:137-161) for device-resident embeddings in
-    one library call -- memset + 5 launches (prologue, tensor-core pass, re-check, commit, median select): similarity + rank of ground truth over the full gallery,
+    one library call -- memset + 5 launches (prologue, tensor-core pass, re-check, commit, median
+    select): similarity + rank of ground truth over the full gallery,
     NaN ground truths -> rank M, hit counts for every k, median rank.  Returns
     {"rank0": int32 [N], "hits": int64 [nk], "medr": fp64 [1] | None, "gt_score": fp64 [N]}."""
     k_vals = [int(k) for k in k_vals]
