@@ -372,6 +372,9 @@ def test_faiss_compat_index_on_reference_fixtures(cuda_dev, golden):
             np.testing.assert_array_equal(np.array([r for _, r in got]) * 100.0, g[key][:, col])
             wv, wi = O.topk_exact(b, a, 11)
             np.testing.assert_array_equal(I, wi)
+            # faiss reports the full squared distance ||q||^2 + ||x||^2 - 2 q.x
+            np.testing.assert_allclose(D, wv + (b.numpy().astype(np.float64) ** 2).sum(1, keepdims=True),
+                                       rtol=1e-5, atol=1e-6)
     # the adversarial fixture: exact ties, zero / non-unit rows, a NaN query, +-inf rows
     s = golden("retrieval_small.npz")
     Q, G = s["queries"], s["gallery"]
